@@ -1,0 +1,283 @@
+"""oracle/binding.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes bindings for the two CPU checkers:
+
+* ``Port``  -> oracle/libl2f_oracle.so      (plain-C restatement, oracle/l2f_oracle.c)
+* ``Ref``   -> oracle/_ref/libl2f_ref.so    (the unmodified reference compiled from /root/reference
+                                             by oracle/Makefile; present only if it was built in the
+                                             build container -- it travels to the GPU box as a file)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  Nothing under raptor_b200/ does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PARAMS_DIM = 145
+SPEC_DEFAULT, SPEC_DEFAULT_DR, SPEC_RAPTOR, SPEC_TEACHER, SPEC_RAPTOR_DR, SPEC_TEACHER_DR = range(6)
+
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_u64 = ctypes.c_uint64
+f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+vp = ctypes.c_void_p
+
+
+def build(target="all"):
+    """Compile the checkers (building the checker is not using it)."""
+    subprocess.run(["make", "-s", "-C", HERE, target], check=True)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+class _Common:
+    prefix = ""
+
+    def __init__(self, path):
+        self.path = path
+        self.lib = ctypes.CDLL(path)
+        L, P = self.lib, self.prefix
+        g = lambda n: getattr(L, P + n)
+        g("rng_init").restype = c_u64
+        g("rng_init").argtypes = [c_u64]
+        g("rng_uniform").restype = c_float
+        g("rng_uniform").argtypes = [u64, c_float, c_float]
+        g("rng_normal").restype = c_float
+        g("rng_normal").argtypes = [u64, c_float, c_float]
+        g("nominal_parameters").argtypes = [c_int, f32]
+        g("sample_initial_parameters").argtypes = [c_int, f32, u64, f32]
+        g("initial_state").argtypes = [c_int, f32, f32]
+        g("sample_initial_state").argtypes = [c_int, f32, u64, f32]
+        g("observe").argtypes = [c_int, f32, f32, u64, f32]
+        g("step").restype = c_float
+        g("step").argtypes = [c_int, f32, f32, f32, u64, f32]
+        g("reward").restype = c_float
+        g("reward").argtypes = [c_int, f32, f32, f32, f32, u64]
+        g("terminated").argtypes = [c_int, f32, f32]
+        self._g = g
+
+    # ---- sizes
+    def state_dim(self, spec):
+        return self._g("state_dim")(spec)
+
+    def observation_dim(self, spec):
+        return self._g("observation_dim")(spec)
+
+    def action_history_length(self, spec):
+        return self._g("action_history_length")(spec)
+
+    # ---- rng
+    def rng_init(self, seed):
+        return int(self._g("rng_init")(int(seed)))
+
+    def rng_states(self, base_seed, n, first_env=0, warmup=0):
+        """per-environment streams: seed = base_seed + global env id, optionally advanced by `warmup` uniform draws"""
+        st = np.array([self.rng_init(base_seed + first_env + i) for i in range(n)], dtype=np.uint64)
+        if warmup:
+            for i in range(n):
+                s = st[i:i + 1].copy()
+                for _ in range(warmup):
+                    self._g("rng_uniform")(s, 0.0, 1.0)
+                st[i] = s[0]
+        return st
+
+    def rng_uniform(self, state, lo, hi):
+        return float(self._g("rng_uniform")(state, lo, hi))
+
+    def rng_normal(self, state, mean, std):
+        return float(self._g("rng_normal")(state, mean, std))
+
+    # ---- env (single environment, flat rows)
+    def nominal_parameters(self, spec):
+        p = np.zeros(PARAMS_DIM, np.float32)
+        self._g("nominal_parameters")(spec, p)
+        return p
+
+    def sample_initial_parameters(self, spec, env_p, rng):
+        out = np.zeros(PARAMS_DIM, np.float32)
+        self._g("sample_initial_parameters")(spec, np.ascontiguousarray(env_p, np.float32), rng, out)
+        return out
+
+    def initial_state(self, spec, p):
+        s = np.zeros(self.state_dim(spec), np.float32)
+        self._g("initial_state")(spec, np.ascontiguousarray(p, np.float32), s)
+        return s
+
+    def sample_initial_state(self, spec, p, rng):
+        s = np.zeros(self.state_dim(spec), np.float32)
+        self._g("sample_initial_state")(spec, np.ascontiguousarray(p, np.float32), rng, s)
+        return s
+
+    def observe(self, spec, p, s, rng):
+        o = np.zeros(self.observation_dim(spec), np.float32)
+        self._g("observe")(spec, np.ascontiguousarray(p, np.float32), np.ascontiguousarray(s, np.float32), rng, o)
+        return o
+
+    def step(self, spec, p, s, a, rng):
+        n = np.zeros(self.state_dim(spec), np.float32)
+        dt = self._g("step")(spec, np.ascontiguousarray(p, np.float32), np.ascontiguousarray(s, np.float32), np.ascontiguousarray(a, np.float32), rng, n)
+        return n, float(dt)
+
+    def reward(self, spec, p, s, a, n, rng=None):
+        rng = np.zeros(1, np.uint64) if rng is None else rng
+        return float(self._g("reward")(spec, np.ascontiguousarray(p, np.float32), np.ascontiguousarray(s, np.float32), np.ascontiguousarray(a, np.float32), np.ascontiguousarray(n, np.float32), rng))
+
+    def terminated(self, spec, p, s):
+        return bool(self._g("terminated")(spec, np.ascontiguousarray(p, np.float32), np.ascontiguousarray(s, np.float32)))
+
+    # ---- vector helpers (loops over the single-env entry points)
+    def sample_initial_parameters_n(self, spec, env_p, rngs):
+        n = len(rngs)
+        out = np.zeros((n, PARAMS_DIM), np.float32)
+        for i in range(n):
+            r = rngs[i:i + 1].copy()
+            out[i] = self.sample_initial_parameters(spec, env_p, r)
+            rngs[i] = r[0]
+        return out
+
+    def sample_initial_state_n(self, spec, params, rngs):
+        n = len(rngs)
+        out = np.zeros((n, self.state_dim(spec)), np.float32)
+        for i in range(n):
+            r = rngs[i:i + 1].copy()
+            out[i] = self.sample_initial_state(spec, params[i], r)
+            rngs[i] = r[0]
+        return out
+
+
+class OraclePolicy(ctypes.Structure):
+    _fields_ = [("arch", c_int), ("input_dim", c_int), ("hidden_dim", c_int), ("output_dim", c_int),
+                ("standardize", c_int), ("head", c_int), ("blob", ctypes.POINTER(c_float))]
+
+
+POLICY_RAPTOR_GRU, POLICY_MLP = 0, 1
+HEAD_IDENTITY, HEAD_SQUASH_EVAL, HEAD_PPO_GAUSSIAN = 0, 1, 2
+
+
+class Port(_Common):
+    """plain-C restatement (oracle/l2f_oracle.c)"""
+    prefix = "oracle_"
+    kind = "port"
+
+    def __init__(self, fast=False):
+        name = "libl2f_oracle_fast.so" if fast else "libl2f_oracle.so"
+        path = os.path.join(HERE, name)
+        if not os.path.exists(path):
+            build("port")
+        super().__init__(path)
+        L = self.lib
+        L.oracle_policy_num_parameters.argtypes = [ctypes.POINTER(OraclePolicy)]
+        L.oracle_policy_evaluate_step.argtypes = [ctypes.POINTER(OraclePolicy), c_int, f32, c_int, vp, vp, c_int, vp, f32, vp, vp]
+        L.oracle_rollout.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, f32, f32, u64, vp, vp, c_int, vp, vp, vp, vp, vp]
+        L.oracle_collect.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, f32, c_int]
+
+    def make_policy(self, blob, arch=POLICY_RAPTOR_GRU, input_dim=22, hidden_dim=16, output_dim=4, standardize=0, head=HEAD_IDENTITY):
+        blob = np.ascontiguousarray(blob, np.float32)
+        pol = OraclePolicy(arch, input_dim, hidden_dim, output_dim, standardize, head, blob.ctypes.data_as(ctypes.POINTER(c_float)))
+        pol._keep = blob
+        n = self.lib.oracle_policy_num_parameters(ctypes.byref(pol))
+        assert n == blob.size, (n, blob.size)
+        return pol
+
+    def policy_evaluate_step(self, pol, obs, hidden=None, gru_step=None, no_auto_reset=False, rng=None):
+        obs = np.ascontiguousarray(obs, np.float32)
+        n = obs.shape[0]
+        adim = pol.output_dim // 2 if pol.head == HEAD_SQUASH_EVAL else pol.output_dim
+        act = np.zeros((n, adim), np.float32)
+        mean = np.zeros((n, adim), np.float32)
+        lp = np.zeros(n, np.float32)
+        self.lib.oracle_policy_evaluate_step(ctypes.byref(pol), n, obs, obs.shape[1], _ptr(hidden), _ptr(gru_step), int(no_auto_reset), _ptr(rng), act, _ptr(mean), _ptr(lp))
+        return act, mean, lp
+
+    def rollout(self, spec, pol, params, states, rngs, T, hidden=None, gru_step=None, no_auto_reset=False, threads=1, record=True):
+        """runs T closed-loop steps IN PLACE on states/rngs/hidden/gru_step; returns dict of recorded arrays"""
+        n = states.shape[0]
+        sd, od = self.state_dim(spec), self.observation_dim(spec)
+        out = {}
+        if record:
+            out = dict(states=np.zeros((T + 1, n, sd), np.float32), observations=np.zeros((T, n, od), np.float32),
+                       actions=np.zeros((T, n, 4), np.float32), rewards=np.zeros((T, n), np.float32), terminated=np.zeros((T, n), np.uint8))
+        self.lib.oracle_rollout(spec, ctypes.byref(pol), n, T, threads, params, states, rngs, _ptr(hidden), _ptr(gru_step), int(no_auto_reset),
+                                _ptr(out.get("states")), _ptr(out.get("observations")), _ptr(out.get("actions")), _ptr(out.get("rewards")), _ptr(out.get("terminated")))
+        return out
+
+    def collect(self, spec, pol, env_params, params, states, rngs, episode_step, episode_return, truncated, T, step_limit, threads=1):
+        n = states.shape[0]
+        D = self.observation_dim(spec) + 15
+        data = np.zeros(((T + 1) * n, D), np.float32)
+        self.lib.oracle_collect(spec, ctypes.byref(pol), n, T, threads, step_limit, np.ascontiguousarray(env_params, np.float32), params, states, rngs,
+                                _ptr(episode_step), _ptr(episode_return), _ptr(truncated), data, D)
+        return data
+
+    def hardware_threads(self):
+        return int(self.lib.oracle_hardware_threads())
+
+
+class Ref(_Common):
+    """the unmodified reference (oracle/ref_l2f.cpp over /root/reference headers)"""
+    prefix = "ref_"
+    kind = "reference"
+
+    @staticmethod
+    def available(fast=False):
+        return os.path.exists(os.path.join(HERE, "_ref", "libl2f_ref_fast.so" if fast else "libl2f_ref.so"))
+
+    def __init__(self, fast=False):
+        super().__init__(os.path.join(HERE, "_ref", "libl2f_ref_fast.so" if fast else "libl2f_ref.so"))
+        L = self.lib
+        L.ref_policy_kat.restype = c_float
+        L.ref_policy_kat.argtypes = [ctypes.POINTER(c_float)]
+        L.ref_policy_export.argtypes = [f32]
+        L.ref_policy_kat_export.argtypes = [f32, f32]
+        L.ref_policy_evaluate_step.argtypes = [c_int, f32, f32, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), c_int, f32]
+        L.ref_policy_initial_hidden.argtypes = [f32]
+        L.ref_rollout.argtypes = [c_int, c_int, c_int, c_int, f32, f32, u64, vp, vp, c_int, vp, vp, vp, vp, vp]
+        L.ref_checkpoint_name.restype = ctypes.c_char_p
+
+    def policy_kat(self):
+        mx = c_float()
+        mean = self.lib.ref_policy_kat(ctypes.byref(mx))
+        return float(mean), float(mx.value)
+
+    def policy_export(self):
+        blob = np.zeros(self.lib.ref_policy_num_parameters(), np.float32)
+        self.lib.ref_policy_export(blob)
+        return blob
+
+    def policy_kat_export(self):
+        i = np.zeros((500, 2, 22), np.float32)
+        o = np.zeros((500, 2, 4), np.float32)
+        self.lib.ref_policy_kat_export(i, o)
+        return i, o
+
+    def policy_evaluate_step(self, obs22, hidden, gru_step, no_auto_reset=False):
+        obs22 = np.ascontiguousarray(obs22, np.float32)
+        act = np.zeros((obs22.shape[0], 4), np.float32)
+        self.lib.ref_policy_evaluate_step(obs22.shape[0], obs22, hidden, gru_step, int(no_auto_reset), act)
+        return act
+
+    def policy_initial_hidden(self):
+        h = np.zeros(16, np.float32)
+        self.lib.ref_policy_initial_hidden(h)
+        return h
+
+    def rollout(self, spec, params, states, rngs, T, hidden=None, gru_step=None, no_auto_reset=False, threads=1, record=True):
+        n = states.shape[0]
+        sd, od = self.state_dim(spec), self.observation_dim(spec)
+        out = {}
+        if record:
+            out = dict(states=np.zeros((T + 1, n, sd), np.float32), observations=np.zeros((T, n, od), np.float32),
+                       actions=np.zeros((T, n, 4), np.float32), rewards=np.zeros((T, n), np.float32), terminated=np.zeros((T, n), np.uint8))
+        self.lib.ref_rollout(spec, n, T, threads, params, states, rngs, _ptr(hidden), _ptr(gru_step), int(no_auto_reset),
+                             _ptr(out.get("states")), _ptr(out.get("observations")), _ptr(out.get("actions")), _ptr(out.get("rewards")), _ptr(out.get("terminated")))
+        return out
+
+    def hardware_threads(self):
+        return int(self.lib.ref_hardware_threads())

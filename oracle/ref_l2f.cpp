@@ -1,0 +1,583 @@
+// oracle/ref_l2f.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Thin extern "C" driver around the UNMODIFIED reference (rl-tools headers under
+// /root/reference/rl-tools/include, env factories under .../src/foundation_policy and the
+// Raptor checkpoint header extracted from /root/reference/data/raptor-policy-checkpoint.tar.gz).
+// It is compiled by oracle/Makefile into oracle/_ref/libl2f_ref.so *from the sources where they
+// lie* (never copied into this repository) and is used only by tests/, by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.
+//
+// Everything in here is glue: flat float32 rows <-> the reference's Parameters / State structs,
+// and loops that call the reference's own free functions
+//   rl_tools::sample_initial_parameters / sample_initial_state / initial_state / observe / step /
+//   reward / terminated                   (rl/environments/l2f/operations_generic.h:69-176)
+//   rl_tools::reset / evaluate_step       (nn_models/sequential/operations_generic.h:63-66,321-325)
+// in the order of rl_tools::evaluate      (rl/utils/evaluation/operations_generic.h:118-189).
+//
+// RNG contract (see DESIGN.md "RNG"): the engine is the reference's Generic xorshift64
+// (random/operations_generic.h:16-31, uniform :52-58, Box-Muller normal :59-71) plugged into the
+// reference's CPU device type, with the reference CPU device's "std == 0 returns the mean
+// without consuming the stream" rule (random/operations_cpu.h:39-41) for the normal
+// distribution.  One stream per environment, seeded base_seed + global_env_id
+// (precedent: rl/components/on_policy_runner/operations_cpu.h:36-44).
+
+#include <cstdint>
+#include <cstring>
+#include <cstdio>
+#include <thread>
+#include <vector>
+#include <chrono>
+
+#include <rl_tools/operations/cpu.h>
+
+// ---- RNG plug-in: must be declared before the l2f / nn operations are parsed (qualified calls
+// ---- inside templates only see overloads declared before the template definition).
+RL_TOOLS_NAMESPACE_WRAPPER_START
+namespace rl_tools{
+    namespace devices::random{
+        struct B200Contract: devices::random::Generic<devices::math::CPU>{
+            static constexpr Type TYPE = Type::random;
+        };
+    }
+    namespace random::normal_distribution{
+        template<typename T, typename RNG>
+        T sample(const devices::random::B200Contract& dev, T mean, T std, RNG& rng){
+            if(std == 0){ // reference CPU-device rule, random/operations_cpu.h:39-41
+                return mean;
+            }
+            return sample(static_cast<const devices::random::Generic<devices::math::CPU>&>(dev), mean, std, rng);
+        }
+    }
+}
+RL_TOOLS_NAMESPACE_WRAPPER_END
+
+#include <rl_tools/nn/layers/standardize/operations_generic.h>
+#include <rl_tools/nn/layers/dense/operations_generic.h>
+#include <rl_tools/nn/layers/sample_and_squash/operations_generic.h>
+#include <rl_tools/nn/layers/gru/operations_generic.h>
+#include <rl_tools/nn_models/mlp/operations_generic.h>
+#include <rl_tools/nn_models/mlp_unconditional_stddev/operations_generic.h>
+#include <rl_tools/nn_models/sequential/operations_generic.h>
+
+#include <rl_tools/rl/environments/l2f/operations_generic.h>
+
+namespace rlt = rl_tools;
+
+using DEV_SPEC = rlt::devices::cpu::Specification<rlt::devices::math::CPU, rlt::devices::random::B200Contract, rlt::devices::logging::CPU>;
+using DEVICE = rlt::devices::CPU<DEV_SPEC>;
+using RNG = rlt::devices::random::B200Contract::ENGINE<>;
+using T = float;
+using TI = typename DEVICE::index_t;
+static_assert(sizeof(RNG) == 8, "xorshift64 engine");
+
+// the reference's own environment factories for the foundation policy (Raptor) training
+#include "pre_training/options.h"
+struct OPTIONS_POST_TRAINING: OPTIONS_PRE_TRAINING{ // post_training/config.h:1-7 (values restated; config.h itself drags in the trainer)
+    static constexpr bool OBSERVE_THRASH_MARKOV = false;
+    static constexpr bool MOTOR_DELAY = true;
+    static constexpr bool ACTION_HISTORY = true;
+    static constexpr TI ACTION_HISTORY_LENGTH = 1;
+    static constexpr bool OBSERVATION_NOISE = true;
+};
+#include "post_training/environment.h"
+
+// the Raptor checkpoint (weights + known-answer test vectors), extracted by oracle/Makefile
+#include "checkpoint.h"
+
+// ------------------------------------------------------------------------------------------------
+// Environment specs. ids are shared with include/b200_l2f.h (B200L2F_SPEC_*)
+//   0 DEFAULT : l2f::Specification<float,size_t>, H=16, OBS 82, LANGEVIN off, DR options off   (parameters/default.h:29-176)
+//   1 DEFAULT_DR : same state/observation, DEFAULT_DOMAIN_RANDOMIZATION_OPTIONS<true>           (parameters/default.h:16-26)
+//   2 RAPTOR  : foundation-policy post-training env, H=1, OBS 22, LANGEVIN on                   (src/foundation_policy/post_training/environment.h:13-46)
+//   3 TEACHER : foundation-policy pre-training env,  H=1, OBS 26, LANGEVIN on                   (src/foundation_policy/pre_training/environment.h:58-90)
+//   4 RAPTOR_DR: RAPTOR state/observation/trajectory options but DR options on (used to draw per-env
+//               dynamics directly in float32; the reference draws them off-line in double and ships JSON,
+//               src/foundation_policy/pre_training/sample_dynamics_parameters.cpp:48-64)
+// ------------------------------------------------------------------------------------------------
+namespace l2f = rlt::rl::environments::l2f;
+using ENV_DEFAULT = rlt::rl::environments::Multirotor<l2f::Specification<T, TI>>;
+using FACTORY_DR = l2f::parameters::DEFAULT_PARAMETERS_FACTORY<T, TI, l2f::parameters::DEFAULT_DOMAIN_RANDOMIZATION_OPTIONS<true>>;
+using ENV_DEFAULT_DR = rlt::rl::environments::Multirotor<l2f::Specification<T, TI, FACTORY_DR::STATIC_PARAMETERS>>;
+using ENV_RAPTOR = typename builder::ENVIRONMENT_FACTORY_POST_TRAINING<DEVICE, T, TI, OPTIONS_POST_TRAINING>::ENVIRONMENT;
+using ENV_TEACHER = typename builder::ENVIRONMENT_FACTORY<DEVICE, T, TI, OPTIONS_PRE_TRAINING>::ENVIRONMENT;
+
+// RAPTOR_DR / TEACHER_DR: same static parameters but a parameter type whose DR options are enabled
+template <typename BASE_STATIC, typename PARAMS_DR>
+struct STATIC_WITH_DR: BASE_STATIC{
+    using PARAMETERS = PARAMS_DR;
+    static constexpr PARAMS_DR make(){
+        PARAMS_DR p{};
+        constexpr auto b = BASE_STATIC::PARAMETER_VALUES;
+        p.dynamics = b.dynamics; p.integration = b.integration; p.mdp = b.mdp;
+        p.disturbances = b.disturbances; p.domain_randomization = b.domain_randomization; p.trajectory = b.trajectory;
+        return p;
+    }
+    static constexpr PARAMS_DR PARAMETER_VALUES = make();
+};
+struct TRAJ_LANGEVIN{ static constexpr bool LANGEVIN = true; };
+using PARAMS_SPEC_BASE = l2f::ParametersBaseSpecification<T, TI, 4, l2f::parameters::reward_functions::Squared<T>>;
+using PARAMS_LANGEVIN_DR = l2f::ParametersTrajectory<l2f::ParametersTrajectorySpecification<T, TI, TRAJ_LANGEVIN,
+      l2f::ParametersDomainRandomization<l2f::ParametersDomainRandomizationSpecification<T, TI, l2f::parameters::DEFAULT_DOMAIN_RANDOMIZATION_OPTIONS<true>,
+      l2f::ParametersDisturbances<l2f::ParametersSpecification<T, TI, l2f::ParametersBase<PARAMS_SPEC_BASE>>>>>>>;
+using ENV_RAPTOR_DR = rlt::rl::environments::Multirotor<l2f::Specification<T, TI, STATIC_WITH_DR<typename ENV_RAPTOR::SPEC::STATIC_PARAMETERS, PARAMS_LANGEVIN_DR>>>;
+using ENV_TEACHER_DR = rlt::rl::environments::Multirotor<l2f::Specification<T, TI, STATIC_WITH_DR<typename ENV_TEACHER::SPEC::STATIC_PARAMETERS, PARAMS_LANGEVIN_DR>>>;
+
+static_assert(ENV_DEFAULT::Observation::DIM == 82);
+static_assert(ENV_RAPTOR::Observation::DIM == 22);
+static_assert(ENV_TEACHER::Observation::DIM == 26);
+
+// ------------------------------------------------------------------------------------------------
+// Flat layouts (shared with include/b200_l2f.h; offsets are asserted in tests)
+// ------------------------------------------------------------------------------------------------
+constexpr int PARAMS_DIM = 145;
+constexpr int state_dim(int H){ return 44 + 4 * H; }
+
+template <typename P>
+static void flatten_parameters(const P& p, float* o){
+    int k = 0;
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) o[k++] = p.dynamics.rotor_positions[i][j];
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) o[k++] = p.dynamics.rotor_thrust_directions[i][j];
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) o[k++] = p.dynamics.rotor_torque_directions[i][j];
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) o[k++] = p.dynamics.rotor_thrust_coefficients[i][j];
+    for(int i=0;i<4;i++) o[k++] = p.dynamics.rotor_torque_constants[i];
+    for(int i=0;i<4;i++) o[k++] = p.dynamics.rotor_time_constants_rising[i];
+    for(int i=0;i<4;i++) o[k++] = p.dynamics.rotor_time_constants_falling[i];
+    o[k++] = p.dynamics.mass;
+    for(int i=0;i<3;i++) o[k++] = p.dynamics.gravity[i];
+    for(int i=0;i<3;i++) for(int j=0;j<3;j++) o[k++] = p.dynamics.J[i][j];
+    for(int i=0;i<3;i++) for(int j=0;j<3;j++) o[k++] = p.dynamics.J_inv[i][j];
+    o[k++] = p.dynamics.hovering_throttle_relative;
+    o[k++] = p.dynamics.action_limit.min;
+    o[k++] = p.dynamics.action_limit.max;
+    o[k++] = p.integration.dt;                               // 85
+    o[k++] = p.mdp.init.guidance;                            // 86
+    o[k++] = p.mdp.init.max_position;
+    o[k++] = p.mdp.init.max_angle;
+    o[k++] = p.mdp.init.max_linear_velocity;
+    o[k++] = p.mdp.init.max_angular_velocity;
+    o[k++] = p.mdp.init.relative_rpm ? 1.0f : 0.0f;
+    o[k++] = p.mdp.init.min_rpm;
+    o[k++] = p.mdp.init.max_rpm;                             // 93
+    o[k++] = p.mdp.reward.non_negative ? 1.0f : 0.0f;        // 94
+    o[k++] = p.mdp.reward.scale;
+    o[k++] = p.mdp.reward.constant;
+    o[k++] = p.mdp.reward.termination_penalty;
+    o[k++] = p.mdp.reward.position;
+    o[k++] = p.mdp.reward.position_clip;
+    o[k++] = p.mdp.reward.orientation;
+    o[k++] = p.mdp.reward.linear_velocity;
+    o[k++] = p.mdp.reward.angular_velocity;
+    o[k++] = p.mdp.reward.linear_acceleration;
+    o[k++] = p.mdp.reward.angular_acceleration;
+    o[k++] = p.mdp.reward.action;
+    o[k++] = p.mdp.reward.d_action;
+    o[k++] = p.mdp.reward.position_error_integral;           // 107
+    o[k++] = p.mdp.observation_noise.position;               // 108
+    o[k++] = p.mdp.observation_noise.orientation;
+    o[k++] = p.mdp.observation_noise.linear_velocity;
+    o[k++] = p.mdp.observation_noise.angular_velocity;
+    o[k++] = p.mdp.observation_noise.imu_acceleration;       // 112
+    o[k++] = p.mdp.action_noise.normalized_rpm;              // 113
+    o[k++] = p.mdp.termination.enabled ? 1.0f : 0.0f;        // 114
+    o[k++] = p.mdp.termination.position_threshold;
+    o[k++] = p.mdp.termination.linear_velocity_threshold;
+    o[k++] = p.mdp.termination.angular_velocity_threshold;
+    o[k++] = p.mdp.termination.position_integral_threshold;
+    o[k++] = p.mdp.termination.orientation_integral_threshold; // 119
+    o[k++] = p.disturbances.random_force.mean;               // 120
+    o[k++] = p.disturbances.random_force.std;
+    o[k++] = p.disturbances.random_torque.mean;
+    o[k++] = p.disturbances.random_torque.std;               // 123
+    const auto& d = p.domain_randomization;                  // 124
+    o[k++] = d.thrust_to_weight_min; o[k++] = d.thrust_to_weight_max;
+    o[k++] = d.torque_to_inertia_min; o[k++] = d.torque_to_inertia_max;
+    o[k++] = d.mass_min; o[k++] = d.mass_max; o[k++] = d.mass_size_deviation;
+    o[k++] = d.rotor_time_constant_rising_min; o[k++] = d.rotor_time_constant_rising_max;
+    o[k++] = d.rotor_time_constant_falling_min; o[k++] = d.rotor_time_constant_falling_max;
+    o[k++] = d.rotor_torque_constant_min; o[k++] = d.rotor_torque_constant_max;
+    o[k++] = d.orientation_offset_angle_max; o[k++] = d.disturbance_force_max; // 138
+    o[k++] = p.trajectory.mixture[0]; o[k++] = p.trajectory.mixture[1];       // 139
+    o[k++] = p.trajectory.langevin.gamma; o[k++] = p.trajectory.langevin.omega;
+    o[k++] = p.trajectory.langevin.sigma; o[k++] = p.trajectory.langevin.alpha; // 144
+    if(k != PARAMS_DIM){ std::fprintf(stderr, "flatten_parameters: %d\n", k); std::abort(); }
+}
+template <typename P>
+static void unflatten_parameters(const float* o, P& p){
+    int k = 0;
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) p.dynamics.rotor_positions[i][j] = o[k++];
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) p.dynamics.rotor_thrust_directions[i][j] = o[k++];
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) p.dynamics.rotor_torque_directions[i][j] = o[k++];
+    for(int i=0;i<4;i++) for(int j=0;j<3;j++) p.dynamics.rotor_thrust_coefficients[i][j] = o[k++];
+    for(int i=0;i<4;i++) p.dynamics.rotor_torque_constants[i] = o[k++];
+    for(int i=0;i<4;i++) p.dynamics.rotor_time_constants_rising[i] = o[k++];
+    for(int i=0;i<4;i++) p.dynamics.rotor_time_constants_falling[i] = o[k++];
+    p.dynamics.mass = o[k++];
+    for(int i=0;i<3;i++) p.dynamics.gravity[i] = o[k++];
+    for(int i=0;i<3;i++) for(int j=0;j<3;j++) p.dynamics.J[i][j] = o[k++];
+    for(int i=0;i<3;i++) for(int j=0;j<3;j++) p.dynamics.J_inv[i][j] = o[k++];
+    p.dynamics.hovering_throttle_relative = o[k++];
+    p.dynamics.action_limit.min = o[k++];
+    p.dynamics.action_limit.max = o[k++];
+    p.integration.dt = o[k++];
+    p.mdp.init.guidance = o[k++];
+    p.mdp.init.max_position = o[k++];
+    p.mdp.init.max_angle = o[k++];
+    p.mdp.init.max_linear_velocity = o[k++];
+    p.mdp.init.max_angular_velocity = o[k++];
+    p.mdp.init.relative_rpm = o[k++] != 0;
+    p.mdp.init.min_rpm = o[k++];
+    p.mdp.init.max_rpm = o[k++];
+    p.mdp.reward.non_negative = o[k++] != 0;
+    p.mdp.reward.scale = o[k++];
+    p.mdp.reward.constant = o[k++];
+    p.mdp.reward.termination_penalty = o[k++];
+    p.mdp.reward.position = o[k++];
+    p.mdp.reward.position_clip = o[k++];
+    p.mdp.reward.orientation = o[k++];
+    p.mdp.reward.linear_velocity = o[k++];
+    p.mdp.reward.angular_velocity = o[k++];
+    p.mdp.reward.linear_acceleration = o[k++];
+    p.mdp.reward.angular_acceleration = o[k++];
+    p.mdp.reward.action = o[k++];
+    p.mdp.reward.d_action = o[k++];
+    p.mdp.reward.position_error_integral = o[k++];
+    p.mdp.observation_noise.position = o[k++];
+    p.mdp.observation_noise.orientation = o[k++];
+    p.mdp.observation_noise.linear_velocity = o[k++];
+    p.mdp.observation_noise.angular_velocity = o[k++];
+    p.mdp.observation_noise.imu_acceleration = o[k++];
+    p.mdp.action_noise.normalized_rpm = o[k++];
+    p.mdp.termination.enabled = o[k++] != 0;
+    p.mdp.termination.position_threshold = o[k++];
+    p.mdp.termination.linear_velocity_threshold = o[k++];
+    p.mdp.termination.angular_velocity_threshold = o[k++];
+    p.mdp.termination.position_integral_threshold = o[k++];
+    p.mdp.termination.orientation_integral_threshold = o[k++];
+    p.disturbances.random_force.mean = o[k++];
+    p.disturbances.random_force.std = o[k++];
+    p.disturbances.random_torque.mean = o[k++];
+    p.disturbances.random_torque.std = o[k++];
+    auto& d = p.domain_randomization;
+    d.thrust_to_weight_min = o[k++]; d.thrust_to_weight_max = o[k++];
+    d.torque_to_inertia_min = o[k++]; d.torque_to_inertia_max = o[k++];
+    d.mass_min = o[k++]; d.mass_max = o[k++]; d.mass_size_deviation = o[k++];
+    d.rotor_time_constant_rising_min = o[k++]; d.rotor_time_constant_rising_max = o[k++];
+    d.rotor_time_constant_falling_min = o[k++]; d.rotor_time_constant_falling_max = o[k++];
+    d.rotor_torque_constant_min = o[k++]; d.rotor_torque_constant_max = o[k++];
+    d.orientation_offset_angle_max = o[k++]; d.disturbance_force_max = o[k++];
+    p.trajectory.mixture[0] = o[k++]; p.trajectory.mixture[1] = o[k++];
+    p.trajectory.langevin.gamma = o[k++]; p.trajectory.langevin.omega = o[k++];
+    p.trajectory.langevin.sigma = o[k++]; p.trajectory.langevin.alpha = o[k++];
+}
+
+template <typename S>
+static void flatten_state(const S& s, float* o){
+    constexpr int H = S::HISTORY_LENGTH;
+    int k = 0;
+    for(int i=0;i<3;i++) o[k++] = s.position[i];
+    for(int i=0;i<4;i++) o[k++] = s.orientation[i];
+    for(int i=0;i<3;i++) o[k++] = s.linear_velocity[i];
+    for(int i=0;i<3;i++) o[k++] = s.angular_velocity[i];            // 13
+    for(int i=0;i<4;i++) o[k++] = s.last_action[i];                 // 17
+    for(int i=0;i<3;i++) o[k++] = s.angular_velocity_history[0][i]; // 20
+    for(int i=0;i<3;i++) o[k++] = s.force[i];
+    for(int i=0;i<3;i++) o[k++] = s.torque[i];                      // 26
+    for(int i=0;i<4;i++) o[k++] = s.rpm[i];                         // 30
+    o[k++] = (float)s.current_step;                                 // 31
+    for(int h=0;h<H;h++) for(int i=0;i<4;i++) o[k++] = s.action_history[h][i];
+    o[k++] = (float)(int)s.trajectory.type;
+    for(int i=0;i<3;i++) o[k++] = s.trajectory.langevin.position[i];
+    for(int i=0;i<3;i++) o[k++] = s.trajectory.langevin.velocity[i];
+    for(int i=0;i<3;i++) o[k++] = s.trajectory.langevin.position_raw[i];
+    for(int i=0;i<3;i++) o[k++] = s.trajectory.langevin.velocity_raw[i];
+    if(k != state_dim(H)){ std::fprintf(stderr, "flatten_state: %d\n", k); std::abort(); }
+}
+template <typename S>
+static void unflatten_state(const float* o, S& s){
+    constexpr int H = S::HISTORY_LENGTH;
+    int k = 0;
+    for(int i=0;i<3;i++) s.position[i] = o[k++];
+    for(int i=0;i<4;i++) s.orientation[i] = o[k++];
+    for(int i=0;i<3;i++) s.linear_velocity[i] = o[k++];
+    for(int i=0;i<3;i++) s.angular_velocity[i] = o[k++];
+    for(int i=0;i<4;i++) s.last_action[i] = o[k++];
+    for(int i=0;i<3;i++) s.angular_velocity_history[0][i] = o[k++];
+    for(int i=0;i<3;i++) s.force[i] = o[k++];
+    for(int i=0;i<3;i++) s.torque[i] = o[k++];
+    for(int i=0;i<4;i++) s.rpm[i] = o[k++];
+    s.current_step = (TI)o[k++];
+    for(int h=0;h<H;h++) for(int i=0;i<4;i++) s.action_history[h][i] = o[k++];
+    s.trajectory.type = (l2f::TrajectoryType)(int)o[k++];
+    for(int i=0;i<3;i++) s.trajectory.langevin.position[i] = o[k++];
+    for(int i=0;i<3;i++) s.trajectory.langevin.velocity[i] = o[k++];
+    for(int i=0;i<3;i++) s.trajectory.langevin.position_raw[i] = o[k++];
+    for(int i=0;i<3;i++) s.trajectory.langevin.velocity_raw[i] = o[k++];
+}
+template <typename S>
+static void zero_state(S& s){ // the reference leaves trajectory fields uninitialised when LANGEVIN is off
+    std::memset((void*)&s, 0, sizeof(S));
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-spec implementations
+// ------------------------------------------------------------------------------------------------
+template <typename ENV>
+struct Impl{
+    using State = typename ENV::State;
+    using Parameters = typename ENV::Parameters;
+    static constexpr int H = State::HISTORY_LENGTH;
+    static constexpr int OBS = ENV::Observation::DIM;
+    static void nominal_parameters(float* p){
+        ENV env; DEVICE device;
+        rlt::init(device, env);
+        Parameters params;
+        rlt::initial_parameters(device, env, params);
+        flatten_parameters(params, p);
+    }
+    static void sample_initial_parameters(const float* env_p, uint64_t* rng_state, float* out){
+        ENV env; DEVICE device; RNG rng; rng.state = *rng_state;
+        unflatten_parameters(env_p, env.parameters);
+        Parameters params;
+        rlt::sample_initial_parameters(device, env, params, rng);
+        flatten_parameters(params, out);
+        *rng_state = rng.state;
+    }
+    static void initial_state(const float* p, float* s){
+        ENV env; DEVICE device; Parameters params; State state; zero_state(state);
+        unflatten_parameters(p, params);
+        rlt::initial_state(device, env, params, state);
+        flatten_state(state, s);
+    }
+    static void sample_initial_state(const float* p, uint64_t* rng_state, float* s){
+        ENV env; DEVICE device; RNG rng; rng.state = *rng_state; Parameters params; State state; zero_state(state);
+        unflatten_parameters(p, params);
+        rlt::sample_initial_state(device, env, params, state, rng);
+        flatten_state(state, s);
+        *rng_state = rng.state;
+    }
+    static void observe(const float* p, const float* s, uint64_t* rng_state, float* obs){
+        ENV env; DEVICE device; RNG rng; rng.state = *rng_state; Parameters params; State state; zero_state(state);
+        unflatten_parameters(p, params); unflatten_state(s, state);
+        rlt::Matrix<rlt::matrix::Specification<T, TI, 1, OBS, false>> o;
+        rlt::observe(device, env, params, state, typename ENV::Observation{}, o, rng);
+        for(int i=0;i<OBS;i++) obs[i] = rlt::get(o, 0, i);
+        *rng_state = rng.state;
+    }
+    static float step(const float* p, const float* s, const float* a, uint64_t* rng_state, float* s_next){
+        ENV env; DEVICE device; RNG rng; rng.state = *rng_state; Parameters params; State state, next; zero_state(state); zero_state(next);
+        unflatten_parameters(p, params); unflatten_state(s, state);
+        rlt::Matrix<rlt::matrix::Specification<T, TI, 1, 4, false>> action;
+        for(int i=0;i<4;i++) rlt::set(action, 0, i, a[i]);
+        T dt = rlt::step(device, env, params, state, action, next, rng);
+        flatten_state(next, s_next);
+        *rng_state = rng.state;
+        return dt;
+    }
+    static float reward(const float* p, const float* s, const float* a, const float* s_next, uint64_t* rng_state){
+        ENV env; DEVICE device; RNG rng; rng.state = *rng_state; Parameters params; State state, next; zero_state(state); zero_state(next);
+        unflatten_parameters(p, params); unflatten_state(s, state); unflatten_state(s_next, next);
+        rlt::Matrix<rlt::matrix::Specification<T, TI, 1, 4, false>> action;
+        for(int i=0;i<4;i++) rlt::set(action, 0, i, a[i]);
+        T r = rlt::reward(device, env, params, state, action, next, rng);
+        *rng_state = rng.state;
+        return r;
+    }
+    static int terminated(const float* p, const float* s){
+        ENV env; DEVICE device; RNG rng; rng.state = 0; Parameters params; State state; zero_state(state);
+        unflatten_parameters(p, params); unflatten_state(s, state);
+        return rlt::terminated(device, env, params, state, rng) ? 1 : 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Raptor policy (the reference's own checkpoint model, batch size 1 per environment)
+// ------------------------------------------------------------------------------------------------
+using ACTOR = rlt::checkpoint::actor::TYPE::template CHANGE_BATCH_SIZE<TI, 1>::template CHANGE_SEQUENCE_LENGTH<TI, 1>;
+struct PolicyInstance{
+    ACTOR::template State<false> state;
+    ACTOR::template Buffer<false> buffer;
+};
+static void policy_reset(DEVICE& device, PolicyInstance& pi, RNG& rng){
+    rlt::reset(device, rlt::checkpoint::actor::module, pi.state, rng);
+}
+template <bool NO_AUTO_RESET>
+static void policy_evaluate_step(DEVICE& device, PolicyInstance& pi, const float* obs22, float* act4, RNG& rng){
+    rlt::Tensor<rlt::tensor::Specification<T, TI, rlt::tensor::Shape<TI, 1, 22>, false>> input;
+    rlt::Tensor<rlt::tensor::Specification<T, TI, rlt::tensor::Shape<TI, 1, 4>, false>> output;
+    for(TI i=0;i<22;i++) rlt::set(device, input, obs22[i], 0, i);
+    if constexpr(NO_AUTO_RESET){
+        rlt::Mode<rlt::nn::layers::gru::NoAutoResetMode<rlt::mode::Evaluation<>>> mode;
+        rlt::evaluate_step(device, rlt::checkpoint::actor::module, input, pi.state, output, pi.buffer, rng, mode);
+    }
+    else{
+        rlt::Mode<rlt::mode::Evaluation<>> mode;
+        rlt::evaluate_step(device, rlt::checkpoint::actor::module, input, pi.state, output, pi.buffer, rng, mode);
+    }
+    for(TI i=0;i<4;i++) act4[i] = rlt::get(device, output, 0, i);
+}
+static float* policy_hidden(PolicyInstance& pi){ // h [1,16] of the GRU layer
+    return rlt::data(pi.state.content_state.next_content_state.state.state);
+}
+static TI& policy_step_counter(PolicyInstance& pi){
+    return *rlt::data(pi.state.content_state.next_content_state.state.step);
+}
+
+// ------------------------------------------------------------------------------------------------
+// closed-loop rollout in the order of rl_tools::evaluate (rl/utils/evaluation/operations_generic.h:138-189),
+// per-environment RNG streams; no termination skip when flags&1 (plain README loop, R/README.md:94-99)
+// ------------------------------------------------------------------------------------------------
+struct RolloutOut{
+    float* states;      // [T+1, N, STATE_DIM] or null
+    float* observations;// [T, N, OBS] or null
+    float* actions;     // [T, N, 4] or null
+    float* rewards;     // [T, N] or null
+    unsigned char* terminated; // [T, N] or null
+    float* hidden;      // [N, 16] final hidden or null
+};
+template <typename ENV>
+static void rollout_range(int n0, int n1, int N, int T_steps, const float* params, float* states_io, uint64_t* rng_states, float* hidden_io, int* gru_step_io, int no_auto_reset, RolloutOut out){
+    using I = Impl<ENV>;
+    constexpr int SD = state_dim(I::H);
+    constexpr int OBS = I::OBS;
+    DEVICE device;
+    for(int n=n0;n<n1;n++){
+        ENV env; rlt::init(device, env);
+        typename ENV::Parameters p; unflatten_parameters(params + (size_t)n * PARAMS_DIM, p);
+        typename ENV::State state, next; zero_state(state); zero_state(next);
+        unflatten_state(states_io + (size_t)n * SD, state);
+        RNG rng; rng.state = rng_states[n];
+        PolicyInstance pi;
+        policy_reset(device, pi, rng);
+        if(hidden_io){ std::memcpy(policy_hidden(pi), hidden_io + (size_t)n*16, 16*sizeof(float)); }
+        if(gru_step_io){ policy_step_counter(pi) = gru_step_io[n]; }
+        rlt::Matrix<rlt::matrix::Specification<T, TI, 1, OBS, false>> o;
+        rlt::Matrix<rlt::matrix::Specification<T, TI, 1, 4, false>> action;
+        for(int t=0;t<T_steps;t++){
+            if(out.states) flatten_state(state, out.states + ((size_t)t * N + n) * SD);
+            rlt::observe(device, env, p, state, typename ENV::Observation{}, o, rng);
+            float obs[OBS]; for(int i=0;i<OBS;i++) obs[i] = rlt::get(o, 0, i);
+            if(out.observations) std::memcpy(out.observations + ((size_t)t * N + n) * OBS, obs, sizeof(obs));
+            float a[4];
+            if(no_auto_reset) policy_evaluate_step<true>(device, pi, obs, a, rng);
+            else policy_evaluate_step<false>(device, pi, obs, a, rng);
+            for(int i=0;i<4;i++) rlt::set(action, 0, i, a[i]);
+            if(out.actions) std::memcpy(out.actions + ((size_t)t * N + n) * 4, a, sizeof(a));
+            rlt::step(device, env, p, state, action, next, rng);
+            T r = rlt::reward(device, env, p, state, action, next, rng);
+            bool term = rlt::terminated(device, env, p, next, rng);
+            if(out.rewards) out.rewards[(size_t)t * N + n] = r;
+            if(out.terminated) out.terminated[(size_t)t * N + n] = term ? 1 : 0;
+            state = next;
+        }
+        if(out.states) flatten_state(state, out.states + ((size_t)T_steps * N + n) * SD);
+        flatten_state(state, states_io + (size_t)n * SD);
+        rng_states[n] = rng.state;
+        if(hidden_io) std::memcpy(hidden_io + (size_t)n*16, policy_hidden(pi), 16*sizeof(float));
+        if(gru_step_io) gru_step_io[n] = (int)policy_step_counter(pi);
+        if(out.hidden) std::memcpy(out.hidden + (size_t)n*16, policy_hidden(pi), 16*sizeof(float));
+    }
+}
+template <typename ENV>
+static void rollout(int N, int T_steps, int threads, const float* params, float* states_io, uint64_t* rng_states, float* hidden_io, int* gru_step_io, int no_auto_reset, RolloutOut out){
+    if(threads <= 1){ rollout_range<ENV>(0, N, N, T_steps, params, states_io, rng_states, hidden_io, gru_step_io, no_auto_reset, out); return; }
+    std::vector<std::thread> pool;
+    for(int t=0;t<threads;t++){
+        int n0 = (int)((long long)N * t / threads), n1 = (int)((long long)N * (t+1) / threads);
+        pool.emplace_back([=](){ rollout_range<ENV>(n0, n1, N, T_steps, params, states_io, rng_states, hidden_io, gru_step_io, no_auto_reset, out); });
+    }
+    for(auto& th: pool) th.join();
+}
+
+#define DISPATCH(spec, CALL) \
+    switch(spec){ \
+        case 0: { using E = ENV_DEFAULT;    CALL; } break; \
+        case 1: { using E = ENV_DEFAULT_DR; CALL; } break; \
+        case 2: { using E = ENV_RAPTOR;     CALL; } break; \
+        case 3: { using E = ENV_TEACHER;    CALL; } break; \
+        case 4: { using E = ENV_RAPTOR_DR;  CALL; } break; \
+        case 5: { using E = ENV_TEACHER_DR; CALL; } break; \
+        default: std::fprintf(stderr, "ref_l2f: bad spec %d\n", spec); std::abort(); \
+    }
+
+extern "C" {
+int ref_params_dim(){ return PARAMS_DIM; }
+int ref_state_dim(int spec){ int r = 0; DISPATCH(spec, r = state_dim(Impl<E>::H)); return r; }
+int ref_observation_dim(int spec){ int r = 0; DISPATCH(spec, r = Impl<E>::OBS); return r; }
+int ref_action_history_length(int spec){ int r = 0; DISPATCH(spec, r = Impl<E>::H); return r; }
+uint64_t ref_rng_init(uint64_t seed){ DEVICE device; RNG rng; rlt::init(device, rng, (TI)seed); return rng.state; }
+float ref_rng_uniform(uint64_t* state, float lo, float hi){ DEVICE device; RNG rng; rng.state = *state; float v = rlt::random::uniform_real_distribution(device.random, lo, hi, rng); *state = rng.state; return v; }
+float ref_rng_normal(uint64_t* state, float mean, float std){ DEVICE device; RNG rng; rng.state = *state; float v = rlt::random::normal_distribution::sample(device.random, mean, std, rng); *state = rng.state; return v; }
+void ref_nominal_parameters(int spec, float* p){ DISPATCH(spec, Impl<E>::nominal_parameters(p)); }
+void ref_sample_initial_parameters(int spec, const float* env_p, uint64_t* rng, float* out){ DISPATCH(spec, Impl<E>::sample_initial_parameters(env_p, rng, out)); }
+void ref_initial_state(int spec, const float* p, float* s){ DISPATCH(spec, Impl<E>::initial_state(p, s)); }
+void ref_sample_initial_state(int spec, const float* p, uint64_t* rng, float* s){ DISPATCH(spec, Impl<E>::sample_initial_state(p, rng, s)); }
+void ref_observe(int spec, const float* p, const float* s, uint64_t* rng, float* obs){ DISPATCH(spec, Impl<E>::observe(p, s, rng, obs)); }
+float ref_step(int spec, const float* p, const float* s, const float* a, uint64_t* rng, float* s_next){ float r = 0; DISPATCH(spec, r = Impl<E>::step(p, s, a, rng, s_next)); return r; }
+float ref_reward(int spec, const float* p, const float* s, const float* a, const float* s_next, uint64_t* rng){ float r = 0; DISPATCH(spec, r = Impl<E>::reward(p, s, a, s_next, rng)); return r; }
+int ref_terminated(int spec, const float* p, const float* s){ int r = 0; DISPATCH(spec, r = Impl<E>::terminated(p, s)); return r; }
+
+// ---- Raptor policy ----
+int ref_policy_num_parameters(){ return 16*22 + 16 + 48*16 + 48 + 48*16 + 48 + 16 + 4*16 + 4; }
+// blob layout (include/b200_l2f.h, B200L2F_POLICY_RAPTOR_GRU): W1[16][22] b1[16] W_ih[48][16] b_ih[48] W_hh[48][16] b_hh[48] h0[16] W2[4][16] b2[4]
+void ref_policy_export(float* blob){
+    namespace a = rlt::checkpoint::actor;
+    int k = 0;
+    auto cp = [&](const unsigned char* mem, int n){ std::memcpy(blob + k, mem, n * sizeof(float)); k += n; };
+    cp(a::layer_0::weights::parameters_memory::memory, 16*22);
+    cp(a::layer_0::biases::parameters_memory::memory, 16);
+    cp(a::layer_1::weights_input::parameters_memory::memory, 48*16);
+    cp(a::layer_1::biases_input::parameters_memory::memory, 48);
+    cp(a::layer_1::weights_hidden::parameters_memory::memory, 48*16);
+    cp(a::layer_1::biases_hidden::parameters_memory::memory, 48);
+    cp(a::layer_1::initial_hidden_state::parameters_memory::memory, 16);
+    cp(a::layer_2::weights::parameters_memory::memory, 4*16);
+    cp(a::layer_2::biases::parameters_memory::memory, 4);
+}
+void ref_policy_kat_shape(int* seq, int* batch){ *seq = 500; *batch = 2; }
+void ref_policy_kat_export(float* input /*[500,2,22]*/, float* output /*[500,2,4]*/){
+    std::memcpy(input, rlt::checkpoint::example::input::memory, sizeof(float) * 500*2*22);
+    std::memcpy(output, rlt::checkpoint::example::output::memory, sizeof(float) * 500*2*4);
+}
+// replays the checkpoint's own known-answer test exactly like inference/applications/l2f/c_backend.h:54-83
+float ref_policy_kat(float* max_abs){
+    DEVICE device; RNG rng; rng.state = 1;
+    double acc = 0; float mx = 0; size_t cnt = 0;
+    for(int b=0;b<2;b++){
+        PolicyInstance pi; policy_reset(device, pi, rng);
+        for(int t=0;t<500;t++){
+            const float* in = (const float*)rlt::checkpoint::example::input::memory + ((size_t)t*2 + b)*22;
+            const float* ref = (const float*)rlt::checkpoint::example::output::memory + ((size_t)t*2 + b)*4;
+            float a[4];
+            policy_evaluate_step<false>(device, pi, in, a, rng);
+            for(int i=0;i<4;i++){ float d = std::fabs(a[i]-ref[i]); acc += d; if(d>mx) mx = d; cnt++; }
+        }
+    }
+    if(max_abs) *max_abs = mx;
+    return (float)(acc / cnt);
+}
+// stateless single evaluate_step: h [N,16] and step counters [N] in/out
+void ref_policy_evaluate_step(int N, const float* obs /*[N,22]*/, float* hidden /*[N,16]*/, int* gru_step /*[N]*/, int no_auto_reset, float* actions /*[N,4]*/){
+    DEVICE device; RNG rng; rng.state = 1;
+    for(int n=0;n<N;n++){
+        PolicyInstance pi; policy_reset(device, pi, rng);
+        std::memcpy(policy_hidden(pi), hidden + (size_t)n*16, 16*sizeof(float));
+        policy_step_counter(pi) = gru_step[n];
+        if(no_auto_reset) policy_evaluate_step<true>(device, pi, obs + (size_t)n*22, actions + (size_t)n*4, rng);
+        else policy_evaluate_step<false>(device, pi, obs + (size_t)n*22, actions + (size_t)n*4, rng);
+        std::memcpy(hidden + (size_t)n*16, policy_hidden(pi), 16*sizeof(float));
+        gru_step[n] = (int)policy_step_counter(pi);
+    }
+}
+void ref_policy_initial_hidden(float* h16){
+    std::memcpy(h16, rlt::checkpoint::actor::layer_1::initial_hidden_state::parameters_memory::memory, 16*sizeof(float));
+}
+
+// ---- closed-loop rollout with the Raptor policy ----
+void ref_rollout(int spec, int N, int T_steps, int threads, const float* params, float* states_io, uint64_t* rng_states, float* hidden_io, int* gru_step_io, int no_auto_reset,
+                 float* out_states, float* out_observations, float* out_actions, float* out_rewards, unsigned char* out_terminated){
+    RolloutOut out{out_states, out_observations, out_actions, out_rewards, out_terminated, nullptr};
+    DISPATCH(spec, rollout<E>(N, T_steps, threads, params, states_io, rng_states, hidden_io, gru_step_io, no_auto_reset, out));
+}
+int ref_hardware_threads(){ return (int)std::thread::hardware_concurrency(); }
+const char* ref_checkpoint_name(){ return rlt::checkpoint::meta::name; }
+}

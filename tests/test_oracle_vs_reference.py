@@ -1,0 +1,142 @@
+"""The plain-C restatement (oracle/l2f_oracle.c) must be BIT-IDENTICAL to the unmodified reference
+(oracle/_ref/libl2f_ref.so, built from /root/reference by oracle/Makefile) on every function of the hot
+path.  Both are built with -ffp-contract=off, so equality is exact (np.array_equal), not approximate.
+Runs only where the reference could be compiled (the build container); on the GPU box the committed
+golden fixtures (tests/test_oracle_golden.py) pin the port instead."""
+import numpy as np
+import pytest
+
+from conftest import foundation_dr_env_params
+from oracle import binding as B
+
+SPECS = [B.SPEC_DEFAULT, B.SPEC_DEFAULT_DR, B.SPEC_RAPTOR, B.SPEC_TEACHER, B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR]
+DR_SPECS = [B.SPEC_DEFAULT_DR, B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR]
+
+
+def test_sizes(port, ref):
+    for s in SPECS:
+        assert port.state_dim(s) == ref.state_dim(s)
+        assert port.observation_dim(s) == ref.observation_dim(s)
+        assert port.action_history_length(s) == ref.action_history_length(s)
+
+
+def test_rng_stream(port, ref):
+    for seed in [0, 1, 7, 123456789, 2**40 + 5]:
+        a = np.array([port.rng_init(seed)], np.uint64)
+        b = np.array([ref.rng_init(seed)], np.uint64)
+        assert a[0] == b[0]
+        for i in range(200):
+            if i % 3 == 0:
+                x, y = port.rng_uniform(a, -2.0, 3.0), ref.rng_uniform(b, -2.0, 3.0)
+            elif i % 3 == 1:
+                x, y = port.rng_normal(a, 0.5, 2.0), ref.rng_normal(b, 0.5, 2.0)
+            else:
+                x, y = port.rng_normal(a, 0.5, 0.0), ref.rng_normal(b, 0.5, 0.0)  # std == 0: no draw
+            assert x == y and a[0] == b[0]
+
+
+@pytest.mark.parametrize("spec", SPECS)
+def test_nominal_parameters(port, ref, spec):
+    assert np.array_equal(port.nominal_parameters(spec), ref.nominal_parameters(spec))
+
+
+@pytest.mark.parametrize("spec", DR_SPECS)
+def test_sample_initial_parameters_dr(port, ref, spec):
+    env_p = foundation_dr_env_params(ref, spec)
+    for seed in range(64):
+        a = np.array([port.rng_init(seed)], np.uint64)
+        for _ in range(seed % 5):
+            port.rng_uniform(a, 0, 1)
+        b = a.copy()
+        pa = port.sample_initial_parameters(spec, env_p, a)
+        pb = ref.sample_initial_parameters(spec, env_p, b)
+        assert a[0] == b[0]
+        assert np.array_equal(pa, pb), np.nonzero(pa != pb)
+
+
+@pytest.mark.parametrize("spec", SPECS)
+def test_initial_and_sampled_state(port, ref, spec):
+    p = ref.nominal_parameters(spec)
+    assert np.array_equal(port.initial_state(spec, p), ref.initial_state(spec, p))
+    for seed in range(64):
+        a = np.array([port.rng_init(seed * 7919 + 13)], np.uint64)
+        for _ in range(20):
+            port.rng_uniform(a, 0, 1)
+        b = a.copy()
+        pp = p.copy()
+        pp[121] = 0.01 * (seed % 3)  # random force std
+        pp[123] = 1e-5 * (seed % 2)  # random torque std
+        sa = port.sample_initial_state(spec, pp, a)
+        sb = ref.sample_initial_state(spec, pp, b)
+        assert a[0] == b[0]
+        assert np.array_equal(sa, sb), np.nonzero(sa != sb)
+
+
+@pytest.mark.parametrize("spec", SPECS)
+@pytest.mark.parametrize("noise", [False, True])
+def test_step_observe_reward_terminated(port, ref, spec, noise):
+    rs = np.random.RandomState(spec * 2 + int(noise))
+    p0 = ref.nominal_parameters(spec)
+    if noise:
+        p0[108:113] = [0.01, 0.02, 0.03, 0.04, 0.05]
+        p0[113] = 0.05
+    for trial in range(24):
+        a = np.array([port.rng_init(trial + 1000)], np.uint64)
+        for _ in range(30):
+            port.rng_uniform(a, 0, 1)
+        b = a.copy()
+        sa = port.sample_initial_state(spec, p0, a)
+        sb = sa.copy()
+        b[0] = a[0]
+        for t in range(40):
+            oa, ob = port.observe(spec, p0, sa, a), ref.observe(spec, p0, sb, b)
+            assert np.array_equal(oa, ob)
+            act = rs.uniform(-1.2, 1.2, 4).astype(np.float32)
+            na, dta = port.step(spec, p0, sa, act, a)
+            nb, dtb = ref.step(spec, p0, sb, act, b)
+            assert dta == dtb and a[0] == b[0]
+            assert np.array_equal(na, nb), (t, np.nonzero(na != nb))
+            assert port.reward(spec, p0, sa, act, na) == ref.reward(spec, p0, sb, act, nb)
+            assert port.terminated(spec, p0, na) == ref.terminated(spec, p0, nb)
+            sa, sb = na, nb
+
+
+def test_policy_kat_and_single_step(port, ref):
+    blob = ref.policy_export()
+    pol = port.make_policy(blob)
+    kin, kout = ref.policy_kat_export()
+    mean, mx = ref.policy_kat()
+    assert mean < 5e-7 and mx < 2e-6
+    # port through the KAT, exact vs the reference's evaluate_step
+    for b in range(2):
+        h_p = np.tile(ref.policy_initial_hidden(), (1, 1)).astype(np.float32)
+        h_r = h_p.copy()
+        st_p = np.zeros(1, np.int32)
+        st_r = np.zeros(1, np.int32)
+        for t in range(500):
+            ap, _, _ = port.policy_evaluate_step(pol, kin[t, b:b + 1], h_p, st_p)
+            ar = ref.policy_evaluate_step(kin[t, b:b + 1], h_r, st_r)
+            assert np.array_equal(ap, ar) and np.array_equal(h_p, h_r) and st_p[0] == st_r[0]
+            assert np.abs(ap - kout[t, b]).max() < 2e-6
+
+
+@pytest.mark.parametrize("spec,T", [(B.SPEC_DEFAULT, 520), (B.SPEC_RAPTOR, 120), (B.SPEC_RAPTOR_DR, 120)])
+def test_closed_loop_rollout(port, ref, spec, T):
+    n = 16
+    blob = ref.policy_export()
+    pol = port.make_policy(blob)
+    rng = ref.rng_states(0, n, warmup=16)
+    if spec == B.SPEC_RAPTOR_DR:
+        params = ref.sample_initial_parameters_n(spec, foundation_dr_env_params(ref, spec), rng)
+    else:
+        params = np.tile(ref.nominal_parameters(spec), (n, 1))
+    states = ref.sample_initial_state_n(spec, params, rng)
+    s_a, s_b, r_a, r_b = states.copy(), states.copy(), rng.copy(), rng.copy()
+    h_a = np.tile(ref.policy_initial_hidden(), (n, 1)).astype(np.float32)
+    h_b = h_a.copy()
+    g_a, g_b = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    oa = port.rollout(spec, pol, params, s_a, r_a, T, hidden=h_a, gru_step=g_a)
+    ob = ref.rollout(spec, params, s_b, r_b, T, hidden=h_b, gru_step=g_b)
+    for k in ["states", "observations", "actions", "rewards", "terminated"]:
+        assert np.array_equal(oa[k], ob[k]), k
+    assert np.array_equal(h_a, h_b) and np.array_equal(g_a, g_b) and np.array_equal(r_a, r_b)
