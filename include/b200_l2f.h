@@ -1,0 +1,190 @@
+/* include/b200_l2f.h -- C ABI of the B200-native vectorised quadrotor rollout engine.
+ *
+ * Drop-in boundary for ONE hot path of rl-tools/raptor: the l2f environment's vectorised
+ * step/observe (+reward/terminated/samplers) fused with the actor forward.  Every entry point cites
+ * the reference interface it replaces.  Shorthands:
+ *   L2F/ = rl-tools/include/rl_tools/rl/environments/l2f/
+ *   INC/ = rl-tools/include/rl_tools/
+ *   R/   = the raptor repository root (README.md = the Python `l2f` / `foundation_policy` surface)
+ *
+ * Conventions (following the reference's only extern "C" precedent,
+ * INC/inference/applications/l2f/c_interface.h:12-31 and INC/inference/executor/c_interface.h:10-44):
+ *   - plain pointers and sizes only, float32 data, no C++/torch types, no exceptions across the ABI;
+ *   - every function returns an int status (0 = B200L2F_OK); b200l2f_last_error() gives the message;
+ *   - the opaque handle owns all device memory; one handle per GPU; a handle is not thread-safe,
+ *     different handles are independent;
+ *   - pointer arguments carry a memory-space tag (B200L2F_HOST / B200L2F_DEVICE).  Host transfers are
+ *     staged through pinned memory and are complete when the call returns; with device pointers the
+ *     work is only enqueued on the handle's stream (b200l2f_stream / b200l2f_synchronize);
+ *   - there is NO CPU fallback: creating a handle without a usable sm_100 device fails.
+ *
+ * Flat layouts (float32, row-major [n_envs, DIM] at the boundary; struct-of-arrays [DIM][n_envs] in HBM):
+ *
+ *   parameters row, B200L2F_PARAMS_DIM = 145  (L2F/multirotor.h:23-140, composed at L2F/parameters/default.h:136-149)
+ *     0  rotor_positions[4][3]          60 mass                      94  reward.non_negative (0/1)      120 disturbances.random_force.mean
+ *     12 rotor_thrust_directions[4][3]  61 gravity[3]                95  reward.scale                   121 disturbances.random_force.std
+ *     24 rotor_torque_directions[4][3]  64 J[3][3]                   96  reward.constant                122 disturbances.random_torque.mean
+ *     36 rotor_thrust_coefficients[4][3]73 J_inv[3][3]               97  reward.termination_penalty     123 disturbances.random_torque.std
+ *     48 rotor_torque_constants[4]      82 hovering_throttle_relative 98 reward.position                124..138 domain_randomization (15, struct order)
+ *     52 rotor_time_constants_rising[4] 83 action_limit.min          99  reward.position_clip           139 trajectory.mixture[2]
+ *     56 rotor_time_constants_falling[4]84 action_limit.max          100 reward.orientation             141 langevin.gamma
+ *                                       85 integration.dt            101 reward.linear_velocity         142 langevin.omega
+ *     86 init.guidance                  90 init.max_angular_velocity 102 reward.angular_velocity        143 langevin.sigma
+ *     87 init.max_position              91 init.relative_rpm (0/1)   103 reward.linear_acceleration     144 langevin.alpha
+ *     88 init.max_angle                 92 init.min_rpm              104 reward.angular_acceleration
+ *     89 init.max_linear_velocity       93 init.max_rpm              105 reward.action  106 reward.d_action  107 reward.position_error_integral
+ *     108..112 observation_noise {position, orientation, linear_velocity, angular_velocity, imu_acceleration}
+ *     113 action_noise.normalized_rpm   114 termination.enabled (0/1) 115..119 termination thresholds {position, linear_velocity,
+ *                                                                              angular_velocity, position_integral, orientation_integral}
+ *
+ *   state row, DIM = 44 + 4*H  (H = action history length; L2F/multirotor.h:574-725)
+ *     0 position[3]  3 orientation[4] (w,x,y,z)  7 linear_velocity[3]  10 angular_velocity[3]  13 last_action[4]
+ *     17 angular_velocity_history[1][3]  20 force[3]  23 torque[3]  26 rpm[4]  30 current_step (integer value)
+ *     31 action_history[H][4]   31+4H trajectory.type (0 POSITION, 1 LANGEVIN)
+ *     32+4H langevin {position[3], velocity[3], position_raw[3], velocity_raw[3]}
+ */
+#ifndef B200_L2F_H
+#define B200_L2F_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200L2F_PARAMS_DIM 145
+#define B200L2F_ACTION_DIM 4
+#define B200L2F_STATE_DIM(H) (44 + 4 * (H))
+
+/* status codes */
+enum { B200L2F_OK = 0, B200L2F_ERR_ARGUMENT = 1, B200L2F_ERR_CUDA = 2, B200L2F_ERR_NO_DEVICE = 3, B200L2F_ERR_STATE = 4, B200L2F_ERR_UNSUPPORTED = 5 };
+/* memory space of pointer arguments */
+enum { B200L2F_HOST = 0, B200L2F_DEVICE = 1 };
+/* b200l2f_config.flags */
+enum { B200L2F_FLAG_ACCURATE_MATH = 1 /* expf/tanhf/IEEE division in the actor instead of MUFU ex2/rcp (parity debugging) */ };
+
+/* Environment specifications = the reference's compile-time Specification instantiations that are on the path.
+ *   DEFAULT   l2f::Specification<float,size_t>: H=16, OBS 82, no Langevin target           (L2F/parameters/default.h:29-176)
+ *   RAPTOR    foundation-policy post-training env: H=1, OBS 22, Langevin target            (src/foundation_policy/post_training/environment.h:13-46)
+ *   TEACHER   foundation-policy pre-training env:  H=1, OBS 26, Langevin target            (src/foundation_policy/pre_training/environment.h:58-90)
+ *   *_DR      same state/observation with DEFAULT_DOMAIN_RANDOMIZATION_OPTIONS<true>         (L2F/parameters/default.h:16-26)            */
+enum { B200L2F_SPEC_DEFAULT = 0, B200L2F_SPEC_DEFAULT_DR = 1, B200L2F_SPEC_RAPTOR = 2, B200L2F_SPEC_TEACHER = 3, B200L2F_SPEC_RAPTOR_DR = 4, B200L2F_SPEC_TEACHER_DR = 5 };
+
+/* Actor architectures.
+ *   RAPTOR_GRU  Dense(in->hid, ReLU) -> GRU(hid) -> Dense(hid->out)          (checkpoint.h:40-185; post_training/config.h:62-68)
+ *               blob: W1[hid][in] b1[hid] W_ih[3hid][hid] b_ih[3hid] W_hh[3hid][hid] b_hh[3hid] h0[hid] W2[out][hid] b2[out]
+ *   MLP         [standardize(mean,precision)] -> Dense(in->hid,ReLU) -> Dense(hid->hid,ReLU) -> Dense(hid->out)   (INC/nn_models/mlp/network.h:15-51)
+ *               blob: [mean[in] precision[in]] W1[hid][in] b1[hid] W2[hid][hid] b2[hid] W3[out][hid] b3[out] [log_std[4] if head == PPO_GAUSSIAN]
+ * Heads.
+ *   IDENTITY      action = network output
+ *   SQUASH_EVAL   out = [mean, log_std]; action = tanh(mean)      (sample_and_squash in Mode<Evaluation>, INC/nn/layers/sample_and_squash/operations_generic.h:148-194)
+ *   PPO_GAUSSIAN  action ~ N(mean, exp(log_std)), log-prob summed  (INC/rl/components/on_policy_runner/operations_generic_per_env.h:43-58) */
+enum { B200L2F_POLICY_RAPTOR_GRU = 0, B200L2F_POLICY_MLP = 1 };
+enum { B200L2F_HEAD_IDENTITY = 0, B200L2F_HEAD_SQUASH_EVAL = 1, B200L2F_HEAD_PPO_GAUSSIAN = 2 };
+/* which kernels compute the policy GEMMs */
+enum { B200L2F_GEMM_FP32_CUDA_CORES = 0, B200L2F_GEMM_TCGEN05_3XTF32 = 1 };
+
+typedef struct b200l2f_handle b200l2f_handle;
+
+typedef struct {
+    int32_t struct_size;   /* sizeof(b200l2f_config), for ABI evolution */
+    int32_t spec;          /* B200L2F_SPEC_* */
+    int32_t n_envs;        /* environments owned by this handle (this GPU's shard) */
+    int32_t device;        /* CUDA device ordinal */
+    int64_t first_env_id;  /* global id of local environment 0: RNG streams are keyed by global id so results do not depend on the number of GPUs */
+    int32_t n_state_slots; /* state buffers (slot 0 = `state`, slot 1 = `next_state` of the reference's step signature); >= 2 */
+    int32_t flags;         /* B200L2F_FLAG_* */
+    void*   stream;        /* cudaStream_t to enqueue on, or NULL: the handle creates its own non-blocking stream */
+} b200l2f_config;
+
+typedef struct {
+    int32_t arch, input_dim, hidden_dim, output_dim, standardize, head;
+    int32_t gru_sequence_length; /* GRU auto-reset period (SEQUENCE_LENGTH, INC/nn/layers/gru/operations_generic.h:80,403); Raptor: 500 */
+    int32_t gemm;                /* B200L2F_GEMM_* */
+} b200l2f_policy_desc;
+
+/* outputs of the fused rollout; any pointer may be NULL. All row-major, step-major: [T, n_envs, ...]. */
+typedef struct {
+    int32_t memspace;        /* B200L2F_HOST / B200L2F_DEVICE for all pointers below */
+    int32_t state_stride;    /* record a state snapshot every `state_stride` steps (0 = never): states[T/stride + 1, n_envs, STATE_DIM] */
+    float*   states;
+    float*   observations;   /* [T, n_envs, policy input_dim] */
+    float*   actions;        /* [T, n_envs, 4] */
+    float*   rewards;        /* [T, n_envs] */
+    uint8_t* terminated;     /* [T, n_envs] */
+    float*   returns;        /* [n_envs] sum of rewards until (and including) the first termination, rl_tools::evaluate semantics */
+    int32_t* episode_length; /* [n_envs] steps until (and including) the first termination */
+} b200l2f_rollout_out;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int  b200l2f_create(const b200l2f_config* config, b200l2f_handle** out);
+int  b200l2f_destroy(b200l2f_handle* h);
+const char* b200l2f_last_error(const b200l2f_handle* h); /* h may be NULL: error of the last failed create on this thread */
+int  b200l2f_synchronize(b200l2f_handle* h);
+void* b200l2f_stream(b200l2f_handle* h);                 /* the cudaStream_t all work is enqueued on */
+int  b200l2f_state_dim(const b200l2f_handle* h);
+int  b200l2f_observation_dim(const b200l2f_handle* h);
+int  b200l2f_action_history_length(const b200l2f_handle* h);
+int  b200l2f_n_envs(const b200l2f_handle* h);
+int64_t b200l2f_kernel_launches(const b200l2f_handle* h); /* number of engine kernels launched so far on this handle */
+
+/* ---- RNG: vector.initialize_rng(device, rng, seed)  (R/README.md:58; rl_tools::init INC/random/operations_generic.h:16-18).
+ * One xorshift64 stream per environment, state = 0xAAAAAAAA + seed + global_env_id; `warmup` extra engine
+ * advances decorrelate neighbouring seeds (the reference warms its RNG up the same way, pre_training/config.h RNG_PARAMS_WARMUP_STEPS). */
+int b200l2f_initialize_rng(b200l2f_handle* h, uint64_t seed, int32_t warmup);
+int b200l2f_get_rng(b200l2f_handle* h, uint64_t* states, int memspace);
+int b200l2f_set_rng(b200l2f_handle* h, const uint64_t* states, int memspace);
+
+/* ---- environment: vector.initialize_environment (R/README.md:59; rl_tools::init L2F/operations_generic.h:43-46) */
+int b200l2f_initialize_environment(b200l2f_handle* h);                                   /* env.parameters = nominal values of the spec */
+int b200l2f_get_environment_parameters(b200l2f_handle* h, float* row145);                /* host pointer */
+int b200l2f_set_environment_parameters(b200l2f_handle* h, const float* row145);          /* host pointer; e.g. to install DR ranges */
+
+/* ---- parameters: rl_tools::initial_parameters / sample_initial_parameters (L2F/operations_generic.h:69-78,
+ * L2F/operations_generic/10_sample_initial_parameters.h:20-206); vector.sample_initial_parameters (R/README.md:60) */
+int b200l2f_initial_parameters(b200l2f_handle* h);
+int b200l2f_sample_initial_parameters(b200l2f_handle* h);
+int b200l2f_get_parameters(b200l2f_handle* h, float* rows, int memspace);                /* [n_envs, 145] */
+int b200l2f_set_parameters(b200l2f_handle* h, const float* rows, int memspace);
+
+/* ---- state: rl_tools::initial_state / sample_initial_state (L2F/operations_generic.h:79-86,
+ * L2F/operations_generic/20_initial_state.h, 30_sample_initial_state.h); vector.sample_initial_state (R/README.md:61) */
+int b200l2f_initial_state(b200l2f_handle* h, int slot);
+int b200l2f_sample_initial_state(b200l2f_handle* h, int slot);
+int b200l2f_get_state(b200l2f_handle* h, int slot, float* rows, int memspace);           /* [n_envs, STATE_DIM] */
+int b200l2f_set_state(b200l2f_handle* h, int slot, const float* rows, int memspace);
+int b200l2f_copy_state(b200l2f_handle* h, int dst_slot, int src_slot);                   /* state.assign(next_state), R/README.md:99 */
+
+/* ---- rl_tools::observe (L2F/operations_generic.h:87-92, L2F/operations_generic/40_observe.h); vector.observe (R/README.md:96).
+ * observations: [n_envs, ld] with ld >= OBSERVATION_DIM */
+int b200l2f_observe(b200l2f_handle* h, int slot, float* observations, int ld, int memspace);
+/* ---- rl_tools::step (L2F/operations_generic.h:94-130); vector.step (R/README.md:98). actions [n_envs, 4]; dts [n_envs] or NULL */
+int b200l2f_step(b200l2f_handle* h, int slot, const float* actions, int next_slot, float* dts, int memspace);
+/* ---- rl_tools::reward / terminated (L2F/operations_generic.h:142-176, L2F/parameters/reward_functions/squared/operations_generic.h:100-129) */
+int b200l2f_reward(b200l2f_handle* h, int slot, const float* actions, int next_slot, float* rewards, int memspace);
+int b200l2f_terminated(b200l2f_handle* h, int slot, uint8_t* flags, int memspace);
+
+/* ---- actor: foundation_policy.Raptor().reset() / .evaluate_step(obs[:, :22]) (R/README.md:19-24,94-97);
+ * rl_tools::reset / evaluate_step (INC/nn_models/sequential/operations_generic.h:63-66,321-325) */
+int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, const float* blob, size_t n_floats); /* host blob */
+int b200l2f_policy_reset(b200l2f_handle* h, const uint8_t* mask, int memspace);          /* mask[n_envs] or NULL = all (mode::sequential::ResetMask) */
+int b200l2f_policy_evaluate_step(b200l2f_handle* h, const float* observations, int ld, float* actions, int no_auto_reset, int memspace);
+int b200l2f_policy_get_hidden(b200l2f_handle* h, float* hidden, int32_t* gru_step, int memspace); /* [n_envs, hidden_dim], [n_envs] */
+int b200l2f_policy_set_hidden(b200l2f_handle* h, const float* hidden, const int32_t* gru_step, int memspace);
+
+/* ---- the fused hot path: T closed-loop steps of observe -> actor -> step -> reward -> terminated for every environment in ONE
+ * persistent kernel launch, state / hidden state / RNG resident on chip; replaces the loop body of rl_tools::evaluate
+ * (INC/rl/utils/evaluation/operations_generic.h:138-189) and of the README loop (R/README.md:94-99). Operates in place on slot 0. */
+int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, const b200l2f_rollout_out* out);
+
+/* ---- PPO collection with on-device auto-reset and trajectory write-back: replaces rl_tools::collect
+ * (INC/rl/components/on_policy_runner/operations_generic.h:99-131, operations_generic_per_env.h:8-75).
+ * dataset: [(T+1)*n_envs, OBS+15] rows = step*n_envs + env, columns obs | actions_mean[4] | actions[4] | log_prob | reward |
+ * terminated | truncated | value | advantage | target_value (on_policy_runner.h:42-64); the last n_envs rows hold the final observations. */
+int b200l2f_collect_reset(b200l2f_handle* h);                                             /* runner init: truncated = true, episode_step/return = 0 (operations_generic.h:65-75) */
+int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, float* dataset, int memspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_L2F_H */

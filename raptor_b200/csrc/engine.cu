@@ -1,0 +1,641 @@
+// raptor_b200/csrc/engine.cu -- handle + C ABI (include/b200_l2f.h) of the B200-native quadrotor rollout engine.
+//
+// The handle owns struct-of-arrays device buffers (parameters [145][n], K state slots [STATE_DIM][n], RNG [n], actor hidden state
+// [HD][n]); every entry point enqueues hand-written sm_100a kernels (kernels.cuh) on the handle's stream.  There is no CPU path.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/b200_l2f.h"
+#include "kernels.cuh"
+
+using namespace b200l2f;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum SpecKind { KIND_DEFAULT = 0, KIND_RAPTOR = 1, KIND_TEACHER = 2 };
+
+}  // namespace
+
+struct b200l2f_handle {
+    b200l2f_config cfg{};
+    int kind = 0; bool dr = false; int H = 0, obs_dim = 0, sdim = 0;
+    int n = 0;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    float* d_params = nullptr;       // [145][n]
+    float* d_env_row = nullptr;      // [145]
+    float h_env_row[B200L2F_PARAMS_DIM];
+    std::vector<float*> d_state;     // slots x [sdim][n]
+    uint64_t* d_rng = nullptr;
+    int* d_flags = nullptr;          // [0] error flag, [1] parameter features
+    bool features_dirty = true; int features = 0;
+    // actor
+    bool policy_loaded = false; b200l2f_policy_desc pol{};
+    float* d_blob = nullptr; size_t blob_floats = 0;
+    float* d_hidden = nullptr; int* d_gru_step = nullptr;
+    // PPO runner bookkeeping (rl/components/on_policy_runner/on_policy_runner.h: episode_step, episode_return, truncated)
+    int* d_episode_step = nullptr; float* d_episode_return = nullptr; uint8_t* d_truncated = nullptr;
+    // staging
+    void* h_pinned = nullptr; size_t pinned_bytes = 0;
+    void* d_stage = nullptr; size_t stage_bytes = 0;
+    std::string err;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(b200l2f_handle* h, int code, const std::string& msg){
+    if(h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call) do{ cudaError_t e_ = (call); if(e_ != cudaSuccess){ return fail(h, B200L2F_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } }while(0)
+#define LAUNCH_CHECK() do{ h->launches++; cudaError_t e_ = cudaGetLastError(); if(e_ != cudaSuccess){ return fail(h, B200L2F_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); } }while(0)
+
+inline int grid_for(int n, int block){ return (n + block - 1) / block; }
+
+int ensure_pinned(b200l2f_handle* h, size_t bytes){
+    if(bytes <= h->pinned_bytes) return B200L2F_OK;
+    if(h->h_pinned){ cudaFreeHost(h->h_pinned); h->h_pinned = nullptr; h->pinned_bytes = 0; }
+    CU(cudaMallocHost(&h->h_pinned, bytes));
+    h->pinned_bytes = bytes;
+    return B200L2F_OK;
+}
+int ensure_stage(b200l2f_handle* h, size_t bytes){
+    if(bytes <= h->stage_bytes) return B200L2F_OK;
+    if(h->d_stage){ cudaFree(h->d_stage); h->d_stage = nullptr; h->stage_bytes = 0; }
+    CU(cudaMalloc(&h->d_stage, bytes));
+    h->stage_bytes = bytes;
+    return B200L2F_OK;
+}
+// host -> device staging buffer (pinned bounce), returns device pointer in *dev
+int upload(b200l2f_handle* h, const void* src, size_t bytes, int memspace, const void** dev){
+    if(memspace == B200L2F_DEVICE){ *dev = src; return B200L2F_OK; }
+    int rc;
+    if((rc = ensure_pinned(h, bytes))) return rc;
+    if((rc = ensure_stage(h, bytes))) return rc;
+    std::memcpy(h->h_pinned, src, bytes);
+    CU(cudaMemcpyAsync(h->d_stage, h->h_pinned, bytes, cudaMemcpyHostToDevice, h->stream));
+    *dev = h->d_stage;
+    return B200L2F_OK;
+}
+// device result buffer: the caller's pointer (device) or the staging buffer (host); finish() copies back
+int result_buffer(b200l2f_handle* h, void* dst, size_t bytes, int memspace, void** dev, size_t stage_offset = 0){
+    if(memspace == B200L2F_DEVICE){ *dev = dst; return B200L2F_OK; }
+    int rc;
+    if((rc = ensure_stage(h, stage_offset + bytes))) return rc;
+    *dev = (char*)h->d_stage + stage_offset;
+    return B200L2F_OK;
+}
+int download(b200l2f_handle* h, void* dst, const void* dev, size_t bytes, int memspace){
+    if(memspace == B200L2F_DEVICE) return B200L2F_OK;
+    int rc;
+    if((rc = ensure_pinned(h, bytes))) return rc;
+    CU(cudaMemcpyAsync(h->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::memcpy(dst, h->h_pinned, bytes);
+    return B200L2F_OK;
+}
+int transpose(b200l2f_handle* h, const float* in, float* out, int rows, int cols){
+    dim3 block(32, 8), grid((cols + 31) / 32, (rows + 31) / 32);
+    k_transpose<<<grid, block, 0, h->stream>>>(in, out, rows, cols);
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+int check_slot(b200l2f_handle* h, int slot){
+    if(slot < 0 || slot >= (int)h->d_state.size()) return fail(h, B200L2F_ERR_ARGUMENT, "state slot out of range");
+    return B200L2F_OK;
+}
+void nominal_parameters(int spec, float* p);
+
+template <class F>
+int dispatch_spec(b200l2f_handle* h, F&& f){
+    switch(h->kind){
+        case KIND_DEFAULT: return f(SpecDefault{});
+        case KIND_RAPTOR: return f(SpecRaptor{});
+        case KIND_TEACHER: return f(SpecTeacher{});
+    }
+    return fail(h, B200L2F_ERR_UNSUPPORTED, "unknown spec");
+}
+
+// nominal parameter values of the supported specifications: rl/environments/l2f/parameters/dynamics/crazyflie.h:10-123,
+// parameters/default.h:34-134 (reward, termination, noise, DR ranges of the DR-enabled factory, trajectory), parameters/init/default.h:22-31
+void nominal_parameters(int spec, float* p){
+    std::memset(p, 0, sizeof(float) * B200L2F_PARAMS_DIM);
+    const float pos[4][3] = {{0.028f, -0.028f, 0}, {-0.028f, -0.028f, 0}, {-0.028f, 0.028f, 0}, {0.028f, 0.028f, 0}};
+    const float tdir[4] = {-1, +1, -1, +1};
+    for(int i = 0; i < 4; i++){
+        for(int j = 0; j < 3; j++) p[P_ROTOR_POS + 3 * i + j] = pos[i][j];
+        p[P_THRUST_DIR + 3 * i + 2] = 1;
+        p[P_TORQUE_DIR + 3 * i + 2] = tdir[i];
+        p[P_THRUST_COEF + 3 * i + 0] = (float)0.00352526;
+        p[P_THRUST_COEF + 3 * i + 1] = (float)0.01437313;
+        p[P_THRUST_COEF + 3 * i + 2] = (float)0.09223048;
+        p[P_TORQUE_CONST + i] = (float)4.665e-3;
+        p[P_TAU_RISE + i] = (float)0.05545454545454546;
+        p[P_TAU_FALL + i] = (float)0.24939393939393945;
+    }
+    p[P_MASS] = (float)(0.027 + 0.0017 + 0.0003 + 0.0016);
+    p[P_GRAVITY + 2] = (float)-9.81;
+    p[P_J + 0] = (float)9.416556729130406e-06; p[P_J + 4] = (float)9.644051701582312e-06; p[P_J + 8] = (float)1.745951732253285e-05;
+    p[P_JINV + 0] = (float)106195.93007988465; p[P_JINV + 4] = (float)103690.85846314249; p[P_JINV + 8] = (float)57275.35197719487;
+    p[P_HOVER] = (float)0.7261389721508553;
+    p[P_ACT_MIN] = 0; p[P_ACT_MAX] = 1;
+    p[P_DT] = (float)(1.0 / 100.0f);
+    p[P_INIT_GUIDANCE] = (float)0.1; p[P_INIT_MAX_POS] = (float)0.5; p[P_INIT_MAX_ANGLE] = (float)1.5707963267948966;
+    p[P_INIT_MAX_LINVEL] = 1; p[P_INIT_MAX_ANGVEL] = 1; p[P_INIT_REL_RPM] = 1; p[P_INIT_MIN_RPM] = -1; p[P_INIT_MAX_RPM] = 0;
+    p[P_RW_SCALE] = 1; p[P_RW_CONSTANT] = (float)0.5; p[P_RW_TERM_PENALTY] = -100; p[P_RW_POSITION] = 1;
+    p[P_RW_ORIENTATION] = (float)0.1; p[P_RW_DACTION] = 1;
+    p[P_TERM_ENABLED] = 1; p[P_TERM_POS] = 1; p[P_TERM_LINVEL] = 2; p[P_TERM_ANGVEL] = 35; p[P_TERM_POS_INT] = 10000; p[P_TERM_ORI_INT] = 50000;
+    if(spec == B200L2F_SPEC_DEFAULT_DR){
+        p[P_DR_T2W_MIN] = (float)1.5; p[P_DR_T2W_MAX] = (float)5.0; p[P_DR_T2I_MIN] = (float)0.001; p[P_DR_T2I_MAX] = (float)0.100;
+        p[P_DR_MASS_MIN] = (float)0.02; p[P_DR_MASS_MAX] = (float)5.00; p[P_DR_MASS_SIZE_DEV] = (float)0.1;
+        p[P_DR_KQ_MIN] = (float)0.005; p[P_DR_KQ_MAX] = (float)0.05; p[P_DR_DIST_FORCE_MAX] = (float)0.1;
+    }
+    p[P_TRAJ_MIX0] = (float)0.5; p[P_TRAJ_MIX1] = (float)0.5;
+    p[P_LANGEVIN_GAMMA] = 1; p[P_LANGEVIN_OMEGA] = 2; p[P_LANGEVIN_SIGMA] = (float)0.5; p[P_LANGEVIN_ALPHA] = (float)0.01;
+}
+
+int refresh_features(b200l2f_handle* h){
+    if(!h->features_dirty) return B200L2F_OK;
+    CU(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->stream));
+    k_param_features<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->n, h->d_flags + 1);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(&h->features, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->features_dirty = false;
+    return B200L2F_OK;
+}
+
+template <class Spec, bool NOISE, bool FAST>
+int launch_rollout_raptor(b200l2f_handle* h, const RolloutArgs& a){
+    constexpr int IN = 22, HD = 16, OUT = 4;
+    auto kern = k_rollout_raptor<Spec, IN, HD, OUT, NOISE, FAST>;
+    const size_t smem = (size_t)(RaptorImage<IN, HD, OUT>::SIZE + P_DYN_DIM * BLOCK) * sizeof(float);
+    static bool configured[8] = {};   // per device
+    int dev = h->cfg.device & 7;
+    if(!configured[dev]){
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = true;
+    }
+    kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a);
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200l2f_last_error(const b200l2f_handle* h){ return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b200l2f_create(const b200l2f_config* config, b200l2f_handle** out){
+    b200l2f_handle* h = nullptr;
+    if(!config || !out) return fail(nullptr, B200L2F_ERR_ARGUMENT, "null argument");
+    if(config->struct_size != (int32_t)sizeof(b200l2f_config)) return fail(nullptr, B200L2F_ERR_ARGUMENT, "b200l2f_config.struct_size mismatch");
+    if(config->n_envs <= 0) return fail(nullptr, B200L2F_ERR_ARGUMENT, "n_envs must be positive");
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(nullptr, B200L2F_ERR_NO_DEVICE, "no CUDA device visible: this engine has no CPU fallback");
+    if(config->device < 0 || config->device >= count) return fail(nullptr, B200L2F_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if(cudaGetDeviceProperties(&prop, config->device) != cudaSuccess) return fail(nullptr, B200L2F_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
+    if(prop.major != 10) return fail(nullptr, B200L2F_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) + ", the engine is built for sm_100a only");
+    h = new (std::nothrow) b200l2f_handle();
+    if(!h) return fail(nullptr, B200L2F_ERR_ARGUMENT, "out of host memory");
+    h->cfg = *config;
+    switch(config->spec){
+        case B200L2F_SPEC_DEFAULT: h->kind = KIND_DEFAULT; h->dr = false; break;
+        case B200L2F_SPEC_DEFAULT_DR: h->kind = KIND_DEFAULT; h->dr = true; break;
+        case B200L2F_SPEC_RAPTOR: h->kind = KIND_RAPTOR; h->dr = false; break;
+        case B200L2F_SPEC_RAPTOR_DR: h->kind = KIND_RAPTOR; h->dr = true; break;
+        case B200L2F_SPEC_TEACHER: h->kind = KIND_TEACHER; h->dr = false; break;
+        case B200L2F_SPEC_TEACHER_DR: h->kind = KIND_TEACHER; h->dr = true; break;
+        default: delete h; return fail(nullptr, B200L2F_ERR_ARGUMENT, "unknown spec");
+    }
+    h->H = h->kind == KIND_DEFAULT ? 16 : 1;
+    h->obs_dim = h->kind == KIND_DEFAULT ? 82 : (h->kind == KIND_RAPTOR ? 22 : 26);
+    h->sdim = state_dim(h->H);
+    h->n = config->n_envs;
+    const int slots = config->n_state_slots < 2 ? 2 : config->n_state_slots;
+    auto bail = [&](const std::string& m, int code){ g_create_error = m; b200l2f_destroy(h); return code; };
+#define CUC(call) do{ cudaError_t e_ = (call); if(e_ != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e_), B200L2F_ERR_CUDA); }while(0)
+    CUC(cudaSetDevice(config->device));
+    if(config->stream){ h->stream = (cudaStream_t)config->stream; h->own_stream = false; }
+    else{ CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    const size_t n = (size_t)h->n;
+    CUC(cudaMalloc(&h->d_params, sizeof(float) * B200L2F_PARAMS_DIM * n));
+    CUC(cudaMalloc(&h->d_env_row, sizeof(float) * B200L2F_PARAMS_DIM));
+    for(int s = 0; s < slots; s++){
+        float* p = nullptr;
+        CUC(cudaMalloc(&p, sizeof(float) * h->sdim * n));
+        h->d_state.push_back(p);
+        CUC(cudaMemsetAsync(p, 0, sizeof(float) * h->sdim * n, h->stream));
+    }
+    CUC(cudaMalloc(&h->d_rng, sizeof(uint64_t) * n));
+    CUC(cudaMalloc(&h->d_flags, sizeof(int) * 4));
+    CUC(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 4, h->stream));
+    CUC(cudaMalloc(&h->d_episode_step, sizeof(int) * n));
+    CUC(cudaMalloc(&h->d_episode_return, sizeof(float) * n));
+    CUC(cudaMalloc(&h->d_truncated, sizeof(uint8_t) * n));
+#undef CUC
+    *out = h;
+    int rc = b200l2f_initialize_environment(h);
+    if(rc == B200L2F_OK) rc = b200l2f_initialize_rng(h, 0, 0);
+    if(rc == B200L2F_OK) rc = b200l2f_initial_parameters(h);
+    if(rc == B200L2F_OK) rc = b200l2f_collect_reset(h);
+    if(rc != B200L2F_OK){ g_create_error = h->err; b200l2f_destroy(h); *out = nullptr; return rc; }
+    return B200L2F_OK;
+}
+
+int b200l2f_destroy(b200l2f_handle* h){
+    if(!h) return B200L2F_OK;
+    cudaSetDevice(h->cfg.device);
+    if(h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_params); cudaFree(h->d_env_row);
+    for(float* p : h->d_state) cudaFree(p);
+    cudaFree(h->d_rng); cudaFree(h->d_flags); cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
+    cudaFree(h->d_episode_step); cudaFree(h->d_episode_return); cudaFree(h->d_truncated);
+    if(h->d_stage) cudaFree(h->d_stage);
+    if(h->h_pinned) cudaFreeHost(h->h_pinned);
+    if(h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B200L2F_OK;
+}
+int b200l2f_synchronize(b200l2f_handle* h){ CU(cudaStreamSynchronize(h->stream)); return B200L2F_OK; }
+void* b200l2f_stream(b200l2f_handle* h){ return (void*)h->stream; }
+int b200l2f_state_dim(const b200l2f_handle* h){ return h->sdim; }
+int b200l2f_observation_dim(const b200l2f_handle* h){ return h->obs_dim; }
+int b200l2f_action_history_length(const b200l2f_handle* h){ return h->H; }
+int b200l2f_n_envs(const b200l2f_handle* h){ return h->n; }
+int64_t b200l2f_kernel_launches(const b200l2f_handle* h){ return h->launches; }
+
+// ---- RNG ------------------------------------------------------------------------------------------------------
+int b200l2f_initialize_rng(b200l2f_handle* h, uint64_t seed, int32_t warmup){
+    CU(cudaSetDevice(h->cfg.device));
+    k_init_rng<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_rng, h->n, seed, (uint64_t)h->cfg.first_env_id, warmup);
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+int b200l2f_get_rng(b200l2f_handle* h, uint64_t* states, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    if(memspace == B200L2F_DEVICE){ CU(cudaMemcpyAsync(states, h->d_rng, sizeof(uint64_t) * h->n, cudaMemcpyDeviceToDevice, h->stream)); return B200L2F_OK; }
+    return download(h, states, h->d_rng, sizeof(uint64_t) * h->n, memspace);
+}
+int b200l2f_set_rng(b200l2f_handle* h, const uint64_t* states, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    const void* dev; int rc;
+    if((rc = upload(h, states, sizeof(uint64_t) * h->n, memspace, &dev))) return rc;
+    CU(cudaMemcpyAsync(h->d_rng, dev, sizeof(uint64_t) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+    return B200L2F_OK;
+}
+
+// ---- environment / parameters -----------------------------------------------------------------------------------
+int b200l2f_initialize_environment(b200l2f_handle* h){
+    CU(cudaSetDevice(h->cfg.device));
+    nominal_parameters(h->cfg.spec, h->h_env_row);
+    return b200l2f_set_environment_parameters(h, h->h_env_row);
+}
+int b200l2f_get_environment_parameters(b200l2f_handle* h, float* row145){
+    std::memcpy(row145, h->h_env_row, sizeof(float) * B200L2F_PARAMS_DIM);
+    return B200L2F_OK;
+}
+int b200l2f_set_environment_parameters(b200l2f_handle* h, const float* row145){
+    CU(cudaSetDevice(h->cfg.device));
+    if(row145 != h->h_env_row) std::memcpy(h->h_env_row, row145, sizeof(float) * B200L2F_PARAMS_DIM);
+    CU(cudaStreamSynchronize(h->stream));   // h_env_row is pageable: make the copy synchronous w.r.t. earlier kernels that read d_env_row
+    CU(cudaMemcpy(h->d_env_row, h->h_env_row, sizeof(float) * B200L2F_PARAMS_DIM, cudaMemcpyHostToDevice));
+    return B200L2F_OK;
+}
+int b200l2f_initial_parameters(b200l2f_handle* h){
+    CU(cudaSetDevice(h->cfg.device));
+    k_fill_params<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->d_env_row, h->n);
+    LAUNCH_CHECK();
+    h->features_dirty = true;
+    return B200L2F_OK;
+}
+int b200l2f_sample_initial_parameters(b200l2f_handle* h){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->dr){
+        // the reference asserts that all DR ranges are zero when the options are disabled (10_sample_initial_parameters.h:74,92,122,132,166,181,196-199)
+        for(int i = P_DR_T2W_MIN; i <= P_DR_DIST_FORCE_MAX; i++){
+            if(i == P_DR_ORI_OFFSET || i == P_DR_T2W_MAX) continue;
+            if(h->h_env_row[i] != 0.0f) return fail(h, B200L2F_ERR_STATE, "L2f: domain randomization ranges must be 0 when the spec's DR options are disabled");
+        }
+        k_sample_params<false><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->d_env_row, h->d_rng, h->n, h->d_flags);
+        LAUNCH_CHECK();
+    }
+    else{
+        CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
+        k_sample_params<true><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->d_env_row, h->d_rng, h->n, h->d_flags);
+        LAUNCH_CHECK();
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if(flag) return fail(h, B200L2F_ERR_STATE, "L2f: invalid domain randomization ranges (see the reference's assert_exit conditions in 10_sample_initial_parameters.h:68-199)");
+    }
+    h->features_dirty = true;
+    return B200L2F_OK;
+}
+int b200l2f_get_parameters(b200l2f_handle* h, float* rows, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t bytes = sizeof(float) * B200L2F_PARAMS_DIM * (size_t)h->n;
+    void* dev; int rc;
+    if((rc = result_buffer(h, rows, bytes, memspace, &dev))) return rc;
+    if((rc = transpose(h, h->d_params, (float*)dev, B200L2F_PARAMS_DIM, h->n))) return rc;
+    return download(h, rows, dev, bytes, memspace);
+}
+int b200l2f_set_parameters(b200l2f_handle* h, const float* rows, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    const void* dev; int rc;
+    if((rc = upload(h, rows, sizeof(float) * B200L2F_PARAMS_DIM * (size_t)h->n, memspace, &dev))) return rc;
+    h->features_dirty = true;
+    return transpose(h, (const float*)dev, h->d_params, h->n, B200L2F_PARAMS_DIM);
+}
+
+// ---- state ------------------------------------------------------------------------------------------------------
+int b200l2f_initial_state(b200l2f_handle* h, int slot){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    return dispatch_spec(h, [&](auto spec){
+        using Spec = decltype(spec);
+        k_init_state<Spec, false><<<grid_for(h->n, BLOCK), BLOCK, 0, h->stream>>>(h->d_params, h->d_state[slot], h->d_rng, h->n);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    });
+}
+int b200l2f_sample_initial_state(b200l2f_handle* h, int slot){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    return dispatch_spec(h, [&](auto spec){
+        using Spec = decltype(spec);
+        k_init_state<Spec, true><<<grid_for(h->n, BLOCK), BLOCK, 0, h->stream>>>(h->d_params, h->d_state[slot], h->d_rng, h->n);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    });
+}
+int b200l2f_get_state(b200l2f_handle* h, int slot, float* rows, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    const size_t bytes = sizeof(float) * h->sdim * (size_t)h->n;
+    void* dev;
+    if((rc = result_buffer(h, rows, bytes, memspace, &dev))) return rc;
+    if((rc = transpose(h, h->d_state[slot], (float*)dev, h->sdim, h->n))) return rc;
+    return download(h, rows, dev, bytes, memspace);
+}
+int b200l2f_set_state(b200l2f_handle* h, int slot, const float* rows, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    const void* dev;
+    if((rc = upload(h, rows, sizeof(float) * h->sdim * (size_t)h->n, memspace, &dev))) return rc;
+    return transpose(h, (const float*)dev, h->d_state[slot], h->n, h->sdim);
+}
+int b200l2f_copy_state(b200l2f_handle* h, int dst_slot, int src_slot){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, dst_slot)) || (rc = check_slot(h, src_slot))) return rc;
+    if(dst_slot == src_slot) return B200L2F_OK;
+    CU(cudaMemcpyAsync(h->d_state[dst_slot], h->d_state[src_slot], sizeof(float) * h->sdim * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    return B200L2F_OK;
+}
+
+// ---- observe / step / reward / terminated -------------------------------------------------------------------------
+int b200l2f_observe(b200l2f_handle* h, int slot, float* observations, int ld, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    if(ld < h->obs_dim) return fail(h, B200L2F_ERR_ARGUMENT, "observe: ld < OBSERVATION_DIM");
+    const size_t bytes = sizeof(float) * (size_t)ld * h->n;
+    void* dev;
+    if((rc = result_buffer(h, observations, bytes, memspace, &dev))) return rc;
+    if(memspace == B200L2F_HOST && ld != h->obs_dim) CU(cudaMemsetAsync(dev, 0, bytes, h->stream));
+    rc = dispatch_spec(h, [&](auto spec){
+        using Spec = decltype(spec);
+        k_observe<Spec><<<grid_for(h->n, BLOCK), BLOCK, 0, h->stream>>>(h->d_params, h->d_state[slot], h->d_rng, (float*)dev, ld, h->n);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    });
+    if(rc) return rc;
+    if(memspace == B200L2F_HOST && ld != h->obs_dim){
+        // preserve the caller's padding columns: copy row by row
+        if((rc = ensure_pinned(h, bytes))) return rc;
+        CU(cudaMemcpyAsync(h->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for(int e = 0; e < h->n; e++) std::memcpy(observations + (size_t)e * ld, (float*)h->h_pinned + (size_t)e * ld, sizeof(float) * h->obs_dim);
+        return B200L2F_OK;
+    }
+    return download(h, observations, dev, bytes, memspace);
+}
+int b200l2f_step(b200l2f_handle* h, int slot, const float* actions, int next_slot, float* dts, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot)) || (rc = check_slot(h, next_slot))) return rc;
+    const size_t act_bytes = sizeof(float) * 4 * (size_t)h->n, dts_bytes = sizeof(float) * (size_t)h->n;
+    if(memspace == B200L2F_HOST){ if((rc = ensure_stage(h, act_bytes + dts_bytes))) return rc; }   // reserve before any pointer into the staging buffer is taken
+    const void* d_act;
+    if((rc = upload(h, actions, act_bytes, memspace, &d_act))) return rc;
+    void* d_dts = nullptr;
+    if(dts){ if((rc = result_buffer(h, dts, dts_bytes, memspace, &d_dts, act_bytes))) return rc; }
+    rc = dispatch_spec(h, [&](auto spec){
+        using Spec = decltype(spec);
+        auto kern = k_step<Spec>;
+        const size_t smem = sizeof(float) * P_DYN_DIM * BLOCK;
+        kern<<<grid_for(h->n, BLOCK), BLOCK, smem, h->stream>>>(h->d_params, h->d_state[slot], (const float*)d_act, h->d_state[next_slot], h->d_rng, (float*)d_dts, h->n);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    });
+    if(rc) return rc;
+    if(dts) return download(h, dts, d_dts, dts_bytes, memspace);
+    return B200L2F_OK;
+}
+int b200l2f_reward(b200l2f_handle* h, int slot, const float* actions, int next_slot, float* rewards, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot)) || (rc = check_slot(h, next_slot))) return rc;
+    const size_t act_bytes = sizeof(float) * 4 * (size_t)h->n, out_bytes = sizeof(float) * (size_t)h->n;
+    if(memspace == B200L2F_HOST){ if((rc = ensure_stage(h, act_bytes + out_bytes))) return rc; }
+    const void* d_act;
+    if((rc = upload(h, actions, act_bytes, memspace, &d_act))) return rc;
+    void* d_out;
+    if((rc = result_buffer(h, rewards, out_bytes, memspace, &d_out, act_bytes))) return rc;
+    rc = dispatch_spec(h, [&](auto spec){
+        using Spec = decltype(spec);
+        k_reward<Spec><<<grid_for(h->n, BLOCK), BLOCK, 0, h->stream>>>(h->d_params, h->d_state[slot], (const float*)d_act, h->d_state[next_slot], (float*)d_out, h->n);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    });
+    if(rc) return rc;
+    return download(h, rewards, d_out, out_bytes, memspace);
+}
+int b200l2f_terminated(b200l2f_handle* h, int slot, uint8_t* flags, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    void* d_out;
+    if((rc = result_buffer(h, flags, h->n, memspace, &d_out))) return rc;
+    rc = dispatch_spec(h, [&](auto spec){
+        using Spec = decltype(spec);
+        k_terminated<Spec><<<grid_for(h->n, BLOCK), BLOCK, 0, h->stream>>>(h->d_params, h->d_state[slot], (uint8_t*)d_out, h->n);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    });
+    if(rc) return rc;
+    return download(h, flags, d_out, h->n, memspace);
+}
+
+// ---- actor ------------------------------------------------------------------------------------------------------
+static size_t policy_num_parameters(const b200l2f_policy_desc& d){
+    const size_t in = d.input_dim, hd = d.hidden_dim, o = d.output_dim;
+    if(d.arch == B200L2F_POLICY_RAPTOR_GRU) return hd * in + hd + 2 * (3 * hd * hd + 3 * hd) + hd + o * hd + o;
+    return (d.standardize ? 2 * in : 0) + hd * in + hd + hd * hd + hd + o * hd + o + (d.head == B200L2F_HEAD_PPO_GAUSSIAN ? 4 : 0);
+}
+int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, const float* blob, size_t n_floats){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!desc || !blob) return fail(h, B200L2F_ERR_ARGUMENT, "policy_load: null argument");
+    if(policy_num_parameters(*desc) != n_floats) return fail(h, B200L2F_ERR_ARGUMENT, "policy_load: blob size does not match the descriptor");
+    if(desc->arch == B200L2F_POLICY_RAPTOR_GRU){
+        if(!(desc->input_dim == 22 && desc->hidden_dim == 16 && desc->output_dim == 4 && desc->head == B200L2F_HEAD_IDENTITY))
+            return fail(h, B200L2F_ERR_UNSUPPORTED, "policy_load: the GRU actor is instantiated for Dense(22->16) -> GRU(16) -> Dense(16->4)");
+        if(h->obs_dim < 22) return fail(h, B200L2F_ERR_ARGUMENT, "policy_load: observation narrower than the actor input");
+    }
+    else return fail(h, B200L2F_ERR_UNSUPPORTED, "policy_load: MLP actors are not built yet");
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
+    h->d_blob = nullptr; h->d_hidden = nullptr; h->d_gru_step = nullptr;
+    CU(cudaMalloc(&h->d_blob, sizeof(float) * n_floats));
+    CU(cudaMemcpy(h->d_blob, blob, sizeof(float) * n_floats, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->d_hidden, sizeof(float) * desc->hidden_dim * (size_t)h->n));
+    CU(cudaMalloc(&h->d_gru_step, sizeof(int) * (size_t)h->n));
+    h->pol = *desc; h->blob_floats = n_floats; h->policy_loaded = true;
+    if(h->pol.gru_sequence_length <= 0) h->pol.gru_sequence_length = 500;
+    return b200l2f_policy_reset(h, nullptr, B200L2F_HOST);
+}
+static const float* raptor_h0(const b200l2f_handle* h){
+    const int in = h->pol.input_dim, hd = h->pol.hidden_dim;
+    return h->d_blob + (hd * in + hd + 2 * (3 * hd * hd + 3 * hd));
+}
+int b200l2f_policy_reset(b200l2f_handle* h, const uint8_t* mask, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->policy_loaded) return fail(h, B200L2F_ERR_STATE, "policy_reset: no policy loaded");
+    const void* d_mask = nullptr; int rc;
+    if(mask){ if((rc = upload(h, mask, h->n, memspace, &d_mask))) return rc; }
+    k_policy_reset<16><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_hidden, h->d_gru_step, raptor_h0(h), (const uint8_t*)d_mask, h->n);
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+int b200l2f_policy_evaluate_step(b200l2f_handle* h, const float* observations, int ld, float* actions, int no_auto_reset, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->policy_loaded) return fail(h, B200L2F_ERR_STATE, "policy_evaluate_step: no policy loaded");
+    if(ld < h->pol.input_dim) return fail(h, B200L2F_ERR_ARGUMENT, "policy_evaluate_step: ld < input_dim");
+    const size_t obs_bytes = sizeof(float) * (size_t)ld * h->n, act_bytes = sizeof(float) * 4 * (size_t)h->n;
+    const void* d_obs; void* d_act; int rc;
+    if(memspace == B200L2F_HOST){ if((rc = ensure_stage(h, obs_bytes + act_bytes))) return rc; }
+    if((rc = upload(h, observations, obs_bytes, memspace, &d_obs))) return rc;
+    if((rc = result_buffer(h, actions, act_bytes, memspace, &d_act, obs_bytes))) return rc;
+    const size_t smem = sizeof(float) * RaptorImage<22, 16, 4>::SIZE;
+    if(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH)
+        k_raptor_step<22, 16, 4, false><<<grid_for(h->n, BLOCK), BLOCK, smem, h->stream>>>(h->d_blob, (const float*)d_obs, ld, h->d_hidden, h->d_gru_step, h->pol.gru_sequence_length, no_auto_reset, (float*)d_act, h->n);
+    else
+        k_raptor_step<22, 16, 4, true><<<grid_for(h->n, BLOCK), BLOCK, smem, h->stream>>>(h->d_blob, (const float*)d_obs, ld, h->d_hidden, h->d_gru_step, h->pol.gru_sequence_length, no_auto_reset, (float*)d_act, h->n);
+    LAUNCH_CHECK();
+    return download(h, actions, d_act, act_bytes, memspace);
+}
+int b200l2f_policy_get_hidden(b200l2f_handle* h, float* hidden, int32_t* gru_step, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->policy_loaded) return fail(h, B200L2F_ERR_STATE, "policy_get_hidden: no policy loaded");
+    int rc;
+    if(hidden){
+        const size_t bytes = sizeof(float) * h->pol.hidden_dim * (size_t)h->n;
+        void* dev;
+        if((rc = result_buffer(h, hidden, bytes, memspace, &dev))) return rc;
+        if((rc = transpose(h, h->d_hidden, (float*)dev, h->pol.hidden_dim, h->n))) return rc;
+        if((rc = download(h, hidden, dev, bytes, memspace))) return rc;
+    }
+    if(gru_step){
+        if(memspace == B200L2F_DEVICE) CU(cudaMemcpyAsync(gru_step, h->d_gru_step, sizeof(int) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+        else if((rc = download(h, gru_step, h->d_gru_step, sizeof(int) * h->n, memspace))) return rc;
+    }
+    return B200L2F_OK;
+}
+int b200l2f_policy_set_hidden(b200l2f_handle* h, const float* hidden, const int32_t* gru_step, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->policy_loaded) return fail(h, B200L2F_ERR_STATE, "policy_set_hidden: no policy loaded");
+    int rc; const void* dev;
+    if(hidden){
+        if((rc = upload(h, hidden, sizeof(float) * h->pol.hidden_dim * (size_t)h->n, memspace, &dev))) return rc;
+        if((rc = transpose(h, (const float*)dev, h->d_hidden, h->n, h->pol.hidden_dim))) return rc;
+    }
+    if(gru_step){
+        if((rc = upload(h, gru_step, sizeof(int) * h->n, memspace, &dev))) return rc;
+        CU(cudaMemcpyAsync(h->d_gru_step, dev, sizeof(int) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return B200L2F_OK;
+}
+
+// ---- fused rollout ------------------------------------------------------------------------------------------------
+int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, const b200l2f_rollout_out* out){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->policy_loaded) return fail(h, B200L2F_ERR_STATE, "rollout: no policy loaded");
+    if(n_steps < 0) return fail(h, B200L2F_ERR_ARGUMENT, "rollout: n_steps < 0");
+    if(h->kind == KIND_TEACHER) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the Raptor actor is paired with the DEFAULT and RAPTOR specs");
+    int rc;
+    if((rc = refresh_features(h))) return rc;
+    RolloutArgs a{};
+    a.params = h->d_params; a.state = h->d_state[0]; a.rng = h->d_rng; a.hidden = h->d_hidden; a.gru_step = h->d_gru_step; a.blob = h->d_blob;
+    a.n = h->n; a.T = n_steps; a.no_auto_reset = no_auto_reset; a.seq_len = h->pol.gru_sequence_length; a.state_stride = 1;
+    // outputs: device pointers are used directly, host pointers get a slice of the staging buffer
+    const size_t n = (size_t)h->n, T = (size_t)n_steps;
+    struct Slice { void** kernel_ptr; void* user; size_t bytes; size_t offset; };
+    std::vector<Slice> slices;
+    size_t total = 0;
+    const int ms = out ? out->memspace : B200L2F_DEVICE;
+    auto add = [&](void** kp, void* user, size_t bytes){
+        if(!user) return;
+        const size_t off = (total + 255) / 256 * 256;
+        slices.push_back({kp, user, bytes, off});
+        total = off + bytes;
+    };
+    if(out){
+        if(out->states){
+            if(out->state_stride <= 0) return fail(h, B200L2F_ERR_ARGUMENT, "rollout: states requested with state_stride <= 0");
+            a.state_stride = out->state_stride;
+            add((void**)&a.out_states, out->states, sizeof(float) * (T / out->state_stride + 1) * n * h->sdim);
+        }
+        add((void**)&a.out_obs, out->observations, sizeof(float) * T * n * 22);
+        add((void**)&a.out_actions, out->actions, sizeof(float) * T * n * 4);
+        add((void**)&a.out_rewards, out->rewards, sizeof(float) * T * n);
+        add((void**)&a.out_term, out->terminated, T * n);
+        add((void**)&a.out_returns, out->returns, sizeof(float) * n);
+        add((void**)&a.out_eplen, out->episode_length, sizeof(int) * n);
+    }
+    if(ms == B200L2F_HOST && total){ if((rc = ensure_stage(h, total))) return rc; }
+    for(auto& s : slices) *s.kernel_ptr = (ms == B200L2F_HOST) ? (void*)((char*)h->d_stage + s.offset) : s.user;
+    const bool noise = (h->features & 1) != 0;
+    const bool fast = !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
+    auto go = [&](auto spec) -> int {
+        using Spec = decltype(spec);
+        if(noise) return fast ? launch_rollout_raptor<Spec, true, true>(h, a) : launch_rollout_raptor<Spec, true, false>(h, a);
+        return fast ? launch_rollout_raptor<Spec, false, true>(h, a) : launch_rollout_raptor<Spec, false, false>(h, a);
+    };
+    rc = h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
+    if(rc) return rc;
+    if(ms == B200L2F_HOST && total){
+        if((rc = ensure_pinned(h, total))) return rc;
+        CU(cudaMemcpyAsync(h->h_pinned, h->d_stage, total, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for(auto& s : slices) std::memcpy(s.user, (char*)h->h_pinned + s.offset, s.bytes);
+    }
+    return B200L2F_OK;
+}
+
+// ---- PPO collection -------------------------------------------------------------------------------------------------
+int b200l2f_collect_reset(b200l2f_handle* h){
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemsetAsync(h->d_episode_step, 0, sizeof(int) * h->n, h->stream));
+    CU(cudaMemsetAsync(h->d_episode_return, 0, sizeof(float) * h->n, h->stream));
+    CU(cudaMemsetAsync(h->d_truncated, 1, h->n, h->stream));
+    return B200L2F_OK;
+}
+int b200l2f_collect(b200l2f_handle* h, int32_t, int32_t, float*, int){
+    return fail(h, B200L2F_ERR_UNSUPPORTED, "collect: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,326 @@
+// raptor_b200/csrc/kernels.cuh -- the engine's kernels (sm_100a).  One environment per thread, 128-thread CTAs.
+//
+// Vector-API kernels (one reference call each) and the fused persistent rollout kernel that replaces the loop body of
+// rl_tools::evaluate (rl_tools/rl/utils/evaluation/operations_generic.h:138-189): observe -> actor -> step -> reward -> terminated
+// for T steps in ONE launch with the integrated state, the GRU hidden state and the RNG stream resident in registers, the
+// per-environment dynamics parameters staged once in shared memory and the actor weights staged once in shared memory.
+#pragma once
+#include <cstdint>
+#include "layout.h"
+#include "rng.cuh"
+#include "env.cuh"
+#include "samplers.cuh"
+#include "policy.cuh"
+
+namespace b200l2f {
+
+constexpr int BLOCK = 128;
+
+// stage the dynamics block of this thread's environment: sm[i * BLOCK + tid] = params[i][env]; time constants -> reciprocals
+__device__ __forceinline__ ParamsStaged stage_dynamics(float* __restrict__ sm_dyn, const float* __restrict__ params, size_t n, size_t env){
+    float* sm = sm_dyn + threadIdx.x;
+    const float* g = params + env;
+#pragma unroll 4
+    for(int i = 0; i < P_DYN_DIM; i++) sm[i * BLOCK] = __ldg(g + (size_t)i * n);
+#pragma unroll
+    for(int r = 0; r < 8; r++) sm[(P_TAU_RISE + r) * BLOCK] = 1.0f / sm[(P_TAU_RISE + r) * BLOCK];
+    ParamsStaged p;
+    p.sm = sm; p.sm_stride = BLOCK; p.base = g; p.stride = n;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// utility kernels
+// ---------------------------------------------------------------------------------------------------------------
+// out[c][r] = in[r][c]; 32x32 tiles through shared memory, coalesced on both sides (AoS rows <-> SoA columns)
+__global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols){
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for(int j = threadIdx.y; j < 32; j += blockDim.y){
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if(r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for(int j = threadIdx.y; j < 32; j += blockDim.y){
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if(r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+__global__ void k_init_rng(uint64_t* __restrict__ rng, int n, uint64_t seed, uint64_t first_env, int warmup){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    uint64_t s = rng_seed_state(seed + first_env + (uint64_t)e);
+    for(int i = 0; i < warmup; i++) rng_next(s);
+    rng[e] = s;
+}
+__global__ void k_fill_params(float* __restrict__ params, const float* __restrict__ env_row, int n){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    for(int i = 0; i < PARAMS_DIM; i++) params[(size_t)i * n + e] = env_row[i];
+}
+template <bool DR>
+__global__ void k_sample_params(float* __restrict__ params, const float* __restrict__ env_row, uint64_t* __restrict__ rng, int n, int* __restrict__ error_flag){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    uint64_t s = rng[e];
+    ParamsRW p{params + e, (size_t)n};
+    if(!sample_parameters<DR>(env_row, p, s)) atomicExch(error_flag, 1);
+    rng[e] = s;
+}
+// features of the parameter set that select kernel variants: bit0 = some observation/action noise std != 0
+__global__ void k_param_features(const float* __restrict__ params, int n, int* __restrict__ features){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = 0;
+    if(e < n){
+        for(int i = P_NOISE_POS; i <= P_ACTION_NOISE; i++) if(params[(size_t)i * n + e] != 0.0f) f |= 1;
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if((threadIdx.x & 31) == 0 && f) atomicOr(features, f);
+}
+
+template <class Spec, bool SAMPLE>
+__global__ void k_init_state(const float* __restrict__ params, float* __restrict__ state, uint64_t* __restrict__ rng, int n){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    ParamsGlobal p{params + e, (size_t)n};
+    EnvState<Spec> st;
+    float* hist = state + (size_t)S_HIST * n + e;
+    if constexpr(SAMPLE){
+        uint64_t s = rng[e];
+        sample_state(st, p, s, hist, (size_t)n);
+        rng[e] = s;
+    }
+    else{
+        initial_state(st, p, hist, (size_t)n);
+    }
+    store_state(st, state + e, (size_t)n);
+}
+
+template <class Spec>
+__global__ void k_observe(const float* __restrict__ params, const float* __restrict__ state, uint64_t* __restrict__ rng, float* __restrict__ obs, int ld, int n){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    ParamsGlobal p{params + e, (size_t)n};
+    EnvState<Spec> st;
+    load_state(st, state + e, (size_t)n);
+    uint64_t s = rng[e];
+    float o[18];
+    observe18<Spec, true>(st, p, s, o);
+    rng[e] = s;
+    float* row = obs + (size_t)e * ld;
+#pragma unroll
+    for(int i = 0; i < 18; i++) row[i] = o[i];
+    float tail[4 * Spec::H + 4];
+    observe_tail(st, p, state + (size_t)S_HIST * n + e, (size_t)n, tail, Spec::H);
+    for(int i = 0; i < Spec::OBS_DIM - 18; i++) row[18 + i] = tail[i];
+}
+
+template <class Spec>
+__global__ void __launch_bounds__(BLOCK) k_step(const float* __restrict__ params, const float* __restrict__ state, const float* __restrict__ actions,
+                                                  float* __restrict__ next, uint64_t* __restrict__ rng, float* __restrict__ dts, int n){
+    extern __shared__ float sm_dyn[];
+    const int e = blockIdx.x * BLOCK + threadIdx.x;
+    if(e >= n) return;
+    ParamsStaged p = stage_dynamics(sm_dyn, params, (size_t)n, (size_t)e);
+    EnvState<Spec> st;
+    load_state(st, state + e, (size_t)n);
+    DynInvariants d;
+    dyn_invariants(d, p, st);
+    float a[4];
+    const float4 av = *reinterpret_cast<const float4*>(actions + (size_t)e * 4);
+    a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+    uint64_t s = rng[e];
+    float* hist_next = next + (size_t)S_HIST * n + e;
+    if constexpr(Spec::H > 1){
+        if(next != state){
+            const float* hist_prev = state + (size_t)S_HIST * n + e;
+            for(int i = 0; i < 4 * Spec::H; i++) hist_next[(size_t)i * n] = hist_prev[(size_t)i * n];
+        }
+    }
+    env_step<Spec, true>(st, p, d, a, s, hist_next, (size_t)n);
+    rng[e] = s;
+    store_state(st, next + e, (size_t)n);
+    if(dts) dts[e] = d.dt;
+}
+
+template <class Spec>
+__global__ void k_reward(const float* __restrict__ params, const float* __restrict__ state, const float* __restrict__ actions, const float* __restrict__ next,
+                         float* __restrict__ rewards, int n){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    ParamsGlobal p{params + e, (size_t)n};
+    EnvState<Spec> st, nx;
+    load_state(st, state + e, (size_t)n);
+    load_state(nx, next + e, (size_t)n);
+    RewardInputs ri;
+    reward_inputs(ri, st);
+    float a[4];
+#pragma unroll
+    for(int i = 0; i < 4; i++) a[i] = actions[(size_t)e * 4 + i];
+    rewards[e] = env_reward(p, ri, a, nx.x, env_terminated(p, nx.x), p[P_DT]);
+}
+template <class Spec>
+__global__ void k_terminated(const float* __restrict__ params, const float* __restrict__ state, uint8_t* __restrict__ flags, int n){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    ParamsGlobal p{params + e, (size_t)n};
+    EnvState<Spec> st;
+    load_state(st, state + e, (size_t)n);
+    flags[e] = env_terminated(p, st.x) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// actor kernels (Raptor GRU).  hidden is SoA [HD][n].
+// ---------------------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void k_policy_reset(float* __restrict__ hidden, int* __restrict__ gru_step, const float* __restrict__ h0, const uint8_t* __restrict__ mask, int n){
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= n) return;
+    if(mask && !mask[e]) return;
+    for(int j = 0; j < HD; j++) hidden[(size_t)j * n + e] = h0[j];
+    gru_step[e] = 0;
+}
+template <int IN, int HD, int OUT, bool FAST>
+__global__ void __launch_bounds__(BLOCK) k_raptor_step(const float* __restrict__ blob, const float* __restrict__ obs, int ld, float* __restrict__ hidden, int* __restrict__ gru_step,
+                                                         int seq_len, int no_auto_reset, float* __restrict__ actions, int n){
+    extern __shared__ __align__(16) float sm_img[];
+    stage_raptor<IN, HD, OUT>(sm_img, blob);
+    __syncthreads();
+    const int e = blockIdx.x * BLOCK + threadIdx.x;
+    if(e >= n) return;
+    float o[IN], h[HD], a[OUT];
+#pragma unroll
+    for(int i = 0; i < IN; i++) o[i] = obs[(size_t)e * ld + i];
+#pragma unroll
+    for(int j = 0; j < HD; j++) h[j] = hidden[(size_t)j * n + e];
+    int gs = gru_step[e];
+    raptor_forward<IN, HD, OUT, FAST>(sm_img, o, h, gs, seq_len, no_auto_reset != 0, a);
+#pragma unroll
+    for(int j = 0; j < HD; j++) hidden[(size_t)j * n + e] = h[j];
+    gru_step[e] = gs;
+#pragma unroll
+    for(int j = 0; j < OUT; j++) actions[(size_t)e * OUT + j] = a[j];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// THE hot path: fused persistent rollout with the Raptor actor
+// ---------------------------------------------------------------------------------------------------------------
+struct RolloutArgs {
+    const float* params;   // [145][n]
+    float* state;          // [STATE_DIM][n], advanced in place
+    uint64_t* rng;         // [n]
+    float* hidden;         // [HD][n]
+    int* gru_step;         // [n]
+    const float* blob;     // actor weights (row-major blob)
+    int n, T, no_auto_reset, seq_len;
+    // optional outputs
+    float* out_states; int state_stride;  // [T/stride + 1][n][STATE_DIM]
+    float* out_obs;        // [T][n][IN]
+    float* out_actions;    // [T][n][4]
+    float* out_rewards;    // [T][n]
+    uint8_t* out_term;     // [T][n]
+    float* out_returns;    // [n]
+    int* out_eplen;        // [n]
+};
+
+template <class Spec>
+__device__ __forceinline__ void write_state_row(const EnvState<Spec>& st, const float* __restrict__ hist_ptr, size_t n, float* __restrict__ row){
+#pragma unroll
+    for(int i = 0; i < 13; i++) row[i] = st.x[i];
+#pragma unroll
+    for(int i = 0; i < 4; i++) row[S_LAST_ACTION + i] = st.last_action[i];
+#pragma unroll
+    for(int i = 0; i < 3; i++) row[S_ANGVEL_HIST + i] = st.x[X_OMEGA + i];
+#pragma unroll
+    for(int i = 0; i < 3; i++){ row[S_FORCE + i] = st.force[i]; row[S_TORQUE + i] = st.torque[i]; }
+#pragma unroll
+    for(int i = 0; i < 4; i++) row[S_RPM + i] = st.x[X_RPM + i];
+    row[S_CURRENT_STEP] = (float)st.current_step;
+    if constexpr(Spec::H == 1){
+#pragma unroll
+        for(int i = 0; i < 4; i++) row[S_HIST + i] = st.hist[i];
+    }
+    else{
+        for(int i = 0; i < 4 * Spec::H; i++) row[S_HIST + i] = hist_ptr[(size_t)i * n];
+    }
+    row[s_traj_type(Spec::H)] = (float)st.traj_type;
+    if constexpr(Spec::LANGEVIN){
+#pragma unroll
+        for(int i = 0; i < 12; i++) row[s_langevin(Spec::H) + i] = st.lang[i];
+    }
+    else{
+#pragma unroll
+        for(int i = 0; i < 12; i++) row[s_langevin(Spec::H) + i] = 0.0f;
+    }
+}
+
+template <class Spec, int IN, int HD, int OUT, bool NOISE, bool FAST>
+__global__ void __launch_bounds__(BLOCK) k_rollout_raptor(const RolloutArgs a){
+    static_assert(IN == 22 && OUT == 4, "the Raptor actor consumes the first 22 observation columns and emits 4 motor commands");
+    extern __shared__ __align__(16) float smem[];
+    float* sm_img = smem;                                         // RaptorImage<IN,HD,OUT>::SIZE floats
+    float* sm_dyn = smem + RaptorImage<IN, HD, OUT>::SIZE;       // P_DYN_DIM * BLOCK floats
+    stage_raptor<IN, HD, OUT>(sm_img, a.blob);
+    const int e = blockIdx.x * BLOCK + threadIdx.x;
+    const bool active = e < a.n;
+    const size_t n = (size_t)a.n;
+    const size_t env = active ? (size_t)e : 0;                    // inactive lanes shadow environment 0 and never store
+    ParamsStaged p = stage_dynamics(sm_dyn, a.params, n, env);
+    __syncthreads();
+    EnvState<Spec> st;
+    load_state(st, a.state + env, n);
+    DynInvariants d;
+    dyn_invariants(d, p, st);
+    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
+    uint64_t rng = a.rng[env];
+    float h[HD];
+#pragma unroll
+    for(int j = 0; j < HD; j++) h[j] = a.hidden[(size_t)j * n + env];
+    int gs = a.gru_step[env];
+    float ret = 0.0f; int eplen = 0; bool done = false;
+    const bool no_auto_reset = a.no_auto_reset != 0;
+
+    for(int t = 0; t < a.T; t++){
+        if(a.out_states && active && (t % a.state_stride) == 0)
+            write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
+        float obs[IN];
+        observe18<Spec, NOISE>(st, p, rng, obs);
+        if constexpr(Spec::H == 1){
+#pragma unroll
+            for(int i = 0; i < 4; i++) obs[18 + i] = st.hist[i];
+        }
+        else{   // most recent ring entry (40_observe.h:281); before the first step it holds the normalised initial rpm
+            const int cur = st.current_step == 0 ? Spec::H - 1 : st.current_step - 1;
+#pragma unroll
+            for(int i = 0; i < 4; i++) obs[18 + i] = hist_ptr[(size_t)(4 * cur + i) * n];
+        }
+        if(a.out_obs && active){
+            float* row = a.out_obs + ((size_t)t * n + env) * IN;
+#pragma unroll
+            for(int i = 0; i < IN; i++) row[i] = obs[i];
+        }
+        float act[OUT];
+        raptor_forward<IN, HD, OUT, FAST>(sm_img, obs, h, gs, a.seq_len, no_auto_reset, act);
+        if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
+        RewardInputs ri;
+        reward_inputs(ri, st);
+        if(Spec::H == 1 || active) env_step<Spec, NOISE>(st, p, d, act, rng, hist_ptr, n);   // H > 1 writes the ring in HBM: shadow lanes must not
+        const bool term = env_terminated(p, st.x);
+        const float r = env_reward(p, ri, act, st.x, term, d.dt);
+        if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = r;
+        if(a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
+        if(!done){ ret += r; eplen += 1; done = term; }
+    }
+    if(!active) return;
+    if(a.out_states && (a.T % a.state_stride) == 0)
+        write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(a.T / a.state_stride) * n + env) * Spec::STATE_DIM);
+    store_state(st, a.state + env, n);
+    a.rng[env] = rng;
+#pragma unroll
+    for(int j = 0; j < HD; j++) a.hidden[(size_t)j * n + env] = h[j];
+    a.gru_step[env] = gs;
+    if(a.out_returns) a.out_returns[env] = ret;
+    if(a.out_eplen) a.out_eplen[env] = eplen;
+}
+
+}  // namespace b200l2f

@@ -1,0 +1,44 @@
+// raptor_b200/csrc/rng.cuh -- per-environment RNG streams.
+//
+// Contract (DESIGN.md "RNG"): the reference's Generic xorshift64 engine
+//   init     rl_tools/random/operations_generic.h:16-18   state = 0xAAAAAAAA + seed
+//   next     rl_tools/random/operations_generic.h:26-31   x ^= x<<13; x ^= x>>17; x ^= x<<5
+//   uniform  rl_tools/random/operations_generic.h:52-58   state / (T)MAX_INDEX * (hi-lo) + lo      (MAX_INDEX = 2^64-1 -> (float) = 2^64)
+//   normal   rl_tools/random/operations_generic.h:59-71   Box-Muller, cosine branch, always two draws
+// combined with the CPU device's rule that a zero standard deviation returns the mean WITHOUT touching the
+// stream (rl_tools/random/operations_cpu.h:39-41).  One stream per environment, seeded seed + global_env_id
+// (precedent: rl_tools/rl/components/on_policy_runner/operations_cpu.h:36-44).  The integer stream is bit-exact
+// with the oracle; the float transforms agree to the last ulp of logf/cosf.
+#pragma once
+#include <cstdint>
+
+namespace b200l2f {
+
+__host__ __device__ __forceinline__ uint64_t rng_seed_state(uint64_t seed){ return 0xAAAAAAAAull + seed; }
+
+__device__ __forceinline__ void rng_next(uint64_t& s){
+    s ^= (s << 13);
+    s ^= (s >> 17);
+    s ^= (s << 5);
+}
+// state / (float)MAX_INDEX: the conversion rounds to nearest, the division by 2^64 is exact
+__device__ __forceinline__ float rng_unit(uint64_t& s){
+    rng_next(s);
+    return __ull2float_rn(s) * 5.42101086242752217e-20f;  // 2^-64
+}
+__device__ __forceinline__ float rng_uniform(uint64_t& s, float lo, float hi){
+    float u = rng_unit(s);
+    return __fadd_rn(__fmul_rn(u, __fsub_rn(hi, lo)), lo);  // no FMA contraction: bit-exact with the oracle
+}
+__device__ __forceinline__ float rng_normal(uint64_t& s, float mean, float std){
+    if(std == 0.0f){ return mean; }
+    float u1 = rng_unit(s);
+    float u2 = rng_unit(s);
+    // the reference's literals are double: sqrt(-2.0 * log(u1)) and 2.0 * PI<float> * u2 are evaluated in double
+    float x = (float)sqrt(-2.0 * (double)logf(u1));
+    float y = (float)(2.0 * (double)3.14159274101257324f * (double)u2);
+    float z = __fmul_rn(x, cosf(y));
+    return __fadd_rn(__fmul_rn(z, std), mean);
+}
+
+}  // namespace b200l2f

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's vector:: environment interface on top of the C ABI (include/b200_l2f.h).
+
+Arguments may be numpy float32 arrays (host memory: copies are staged through pinned memory inside the call) or torch CUDA tensors
+(device memory: zero-copy, work is enqueued on the engine's stream).  Names, argument meaning and error behaviour follow the reference:
+  rl_tools::init / initial_parameters / sample_initial_parameters / initial_state / sample_initial_state / observe / step / reward /
+  terminated   (rl_tools/rl/environments/l2f/operations_generic.h:43-176)
+  rl_tools::reset / evaluate_step  (rl_tools/nn_models/sequential/operations_generic.h:63-66,321-325)
+  rl_tools::evaluate               (rl_tools/rl/utils/evaluation/operations_generic.h:93-214)  -> VectorEnvironment.rollout
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def raptor_policy_blob():
+    """the Raptor checkpoint's 2084 weights in the engine's blob layout (extracted from the reference checkpoint by tests/golden/generate.py)"""
+    return np.fromfile(os.path.join(HERE, "data", "raptor_policy_2084.f32"), dtype=np.float32)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _arg(x, dtype, shape=None, name="array"):
+    """-> (pointer, memspace, keepalive)"""
+    if x is None:
+        return None, L.HOST, None
+    if _is_torch(x):
+        import torch
+        want = {np.float32: torch.float32, np.uint64: torch.int64, np.int32: torch.int32, np.uint8: torch.uint8}[dtype]
+        if x.dtype != want and not (dtype == np.uint64 and x.dtype == getattr(torch, "uint64", None)):
+            raise TypeError("%s: expected torch dtype %s, got %s" % (name, want, x.dtype))
+        if not x.is_cuda or not x.is_contiguous():
+            raise ValueError("%s: torch tensors must be contiguous CUDA tensors (use numpy arrays for host data)" % name)
+        if shape is not None and tuple(x.shape) != tuple(shape):
+            raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(x.shape)))
+        return ctypes.c_void_p(x.data_ptr()), L.DEVICE, x
+    a = x
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("%s: expected a C-contiguous numpy array of dtype %s" % (name, np.dtype(dtype)))
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(a.shape)))
+    return ctypes.c_void_p(a.ctypes.data), L.HOST, a
+
+
+class VectorEnvironment:
+    """N quadrotor environments on one GPU (one handle = one shard; shards never communicate)."""
+
+    def __init__(self, n_envs, spec=L.SPEC_DEFAULT, device=0, first_env_id=0, n_state_slots=2, flags=0, stream=None):
+        self._lib = L.load()
+        cfg = L.Config(ctypes.sizeof(L.Config), spec, n_envs, device, first_env_id, n_state_slots, flags, stream)
+        h = ctypes.c_void_p()
+        rc = self._lib.b200l2f_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc != 0:
+            raise EngineError("b200l2f_create failed (%d): %s" % (rc, self._lib.b200l2f_last_error(None).decode()))
+        self._h = h
+        self.spec = spec
+        self.N_ENVIRONMENTS = n_envs
+        self.OBSERVATION_DIM = self._lib.b200l2f_observation_dim(h)
+        self.STATE_DIM = self._lib.b200l2f_state_dim(h)
+        self.ACTION_DIM = 4
+        self.ACTION_HISTORY_LENGTH = self._lib.b200l2f_action_history_length(h)
+        self.policy = None
+
+    # ---- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError("b200l2f error %d: %s" % (rc, self._lib.b200l2f_last_error(self._h).decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200l2f_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self._lib.b200l2f_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.b200l2f_stream(self._h)
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.b200l2f_kernel_launches(self._h))
+
+    # ---- RNG / environment / parameters
+    def initialize_rng(self, seed=0, warmup=0):
+        self._check(self._lib.b200l2f_initialize_rng(self._h, seed, warmup))
+
+    def get_rng(self):
+        out = np.zeros(self.N_ENVIRONMENTS, np.uint64)
+        self._check(self._lib.b200l2f_get_rng(self._h, out.ctypes.data, L.HOST))
+        return out
+
+    def set_rng(self, states):
+        p, ms, _ = _arg(states, np.uint64, (self.N_ENVIRONMENTS,), "rng")
+        self._check(self._lib.b200l2f_set_rng(self._h, p, ms))
+
+    def initialize_environment(self):
+        self._check(self._lib.b200l2f_initialize_environment(self._h))
+
+    def get_environment_parameters(self):
+        row = np.zeros(L.PARAMS_DIM, np.float32)
+        self._check(self._lib.b200l2f_get_environment_parameters(self._h, row.ctypes.data))
+        return row
+
+    def set_environment_parameters(self, row):
+        row = np.ascontiguousarray(row, np.float32)
+        assert row.shape == (L.PARAMS_DIM,)
+        self._check(self._lib.b200l2f_set_environment_parameters(self._h, row.ctypes.data))
+
+    def initial_parameters(self):
+        self._check(self._lib.b200l2f_initial_parameters(self._h))
+
+    def sample_initial_parameters(self):
+        self._check(self._lib.b200l2f_sample_initial_parameters(self._h))
+
+    def get_parameters(self, out=None):
+        out = np.zeros((self.N_ENVIRONMENTS, L.PARAMS_DIM), np.float32) if out is None else out
+        p, ms, _ = _arg(out, np.float32, (self.N_ENVIRONMENTS, L.PARAMS_DIM), "parameters")
+        self._check(self._lib.b200l2f_get_parameters(self._h, p, ms))
+        return out
+
+    def set_parameters(self, rows):
+        p, ms, _ = _arg(rows, np.float32, (self.N_ENVIRONMENTS, L.PARAMS_DIM), "parameters")
+        self._check(self._lib.b200l2f_set_parameters(self._h, p, ms))
+
+    # ---- state
+    def initial_state(self, slot=0):
+        self._check(self._lib.b200l2f_initial_state(self._h, slot))
+
+    def sample_initial_state(self, slot=0):
+        self._check(self._lib.b200l2f_sample_initial_state(self._h, slot))
+
+    def get_state(self, slot=0, out=None):
+        out = np.zeros((self.N_ENVIRONMENTS, self.STATE_DIM), np.float32) if out is None else out
+        p, ms, _ = _arg(out, np.float32, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")
+        self._check(self._lib.b200l2f_get_state(self._h, slot, p, ms))
+        return out
+
+    def set_state(self, rows, slot=0):
+        p, ms, _ = _arg(rows, np.float32, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")
+        self._check(self._lib.b200l2f_set_state(self._h, slot, p, ms))
+
+    def copy_state(self, dst_slot, src_slot):
+        self._check(self._lib.b200l2f_copy_state(self._h, dst_slot, src_slot))
+
+    # ---- observe / step / reward / terminated
+    def observe(self, observation=None, slot=0):
+        if observation is None:
+            observation = np.zeros((self.N_ENVIRONMENTS, self.OBSERVATION_DIM), np.float32)
+        if observation.shape[0] != self.N_ENVIRONMENTS or observation.shape[1] < self.OBSERVATION_DIM:
+            raise ValueError("observe: observation must be [N_ENVIRONMENTS, >= OBSERVATION_DIM]")
+        p, ms, _ = _arg(observation, np.float32, None, "observation")
+        self._check(self._lib.b200l2f_observe(self._h, slot, p, observation.shape[1], ms))
+        return observation
+
+    def step(self, action, slot=0, next_slot=1, dts=None):
+        p, ms, _ = _arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
+        if dts is None and ms == L.HOST:
+            dts = np.zeros(self.N_ENVIRONMENTS, np.float32)
+        pd, msd, _ = _arg(dts, np.float32, (self.N_ENVIRONMENTS,), "dts")
+        if dts is not None and msd != ms:
+            raise ValueError("step: action and dts must live in the same memory space")
+        self._check(self._lib.b200l2f_step(self._h, slot, p, next_slot, pd, ms))
+        return dts
+
+    def reward(self, action, slot=0, next_slot=1, out=None):
+        p, ms, _ = _arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
+        out = np.zeros(self.N_ENVIRONMENTS, np.float32) if out is None else out
+        po, mso, _ = _arg(out, np.float32, (self.N_ENVIRONMENTS,), "rewards")
+        if mso != ms:
+            raise ValueError("reward: action and out must live in the same memory space")
+        self._check(self._lib.b200l2f_reward(self._h, slot, p, next_slot, po, ms))
+        return out
+
+    def terminated(self, slot=0, out=None):
+        out = np.zeros(self.N_ENVIRONMENTS, np.uint8) if out is None else out
+        p, ms, _ = _arg(out, np.uint8, (self.N_ENVIRONMENTS,), "flags")
+        self._check(self._lib.b200l2f_terminated(self._h, slot, p, ms))
+        return out
+
+    # ---- actor
+    def load_policy(self, blob=None, arch=L.POLICY_RAPTOR_GRU, input_dim=22, hidden_dim=16, output_dim=4, standardize=0, head=L.HEAD_IDENTITY,
+                    gru_sequence_length=500, gemm=L.GEMM_FP32_CUDA_CORES):
+        blob = raptor_policy_blob() if blob is None else np.ascontiguousarray(blob, np.float32)
+        desc = L.PolicyDesc(arch, input_dim, hidden_dim, output_dim, standardize, head, gru_sequence_length, gemm)
+        self._check(self._lib.b200l2f_policy_load(self._h, ctypes.byref(desc), blob.ctypes.data, blob.size))
+        self.policy = desc
+
+    def policy_reset(self, mask=None):
+        p, ms, _ = _arg(mask, np.uint8, (self.N_ENVIRONMENTS,), "mask")
+        self._check(self._lib.b200l2f_policy_reset(self._h, p, ms))
+
+    def policy_evaluate_step(self, observation, action=None, no_auto_reset=False):
+        po, ms, _ = _arg(observation, np.float32, None, "observation")
+        if observation.shape[0] != self.N_ENVIRONMENTS or observation.shape[1] < self.policy.input_dim:
+            raise ValueError("evaluate_step: observation must be [N_ENVIRONMENTS, >= input_dim]")
+        if action is None:
+            if ms == L.HOST:
+                action = np.zeros((self.N_ENVIRONMENTS, 4), np.float32)
+            else:
+                import torch
+                action = torch.empty((self.N_ENVIRONMENTS, 4), dtype=torch.float32, device=observation.device)
+        pa, msa, _ = _arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
+        if msa != ms:
+            raise ValueError("evaluate_step: observation and action must live in the same memory space")
+        self._check(self._lib.b200l2f_policy_evaluate_step(self._h, po, observation.shape[1], pa, int(no_auto_reset), ms))
+        return action
+
+    def get_hidden(self):
+        h = np.zeros((self.N_ENVIRONMENTS, self.policy.hidden_dim), np.float32)
+        g = np.zeros(self.N_ENVIRONMENTS, np.int32)
+        self._check(self._lib.b200l2f_policy_get_hidden(self._h, h.ctypes.data, g.ctypes.data, L.HOST))
+        return h, g
+
+    def set_hidden(self, hidden=None, gru_step=None):
+        ph, ms, _ = _arg(hidden, np.float32, (self.N_ENVIRONMENTS, self.policy.hidden_dim), "hidden")
+        pg, msg, _ = _arg(gru_step, np.int32, (self.N_ENVIRONMENTS,), "gru_step")
+        self._check(self._lib.b200l2f_policy_set_hidden(self._h, ph, pg, ms if hidden is not None else msg))
+
+    # ---- the fused hot path
+    def rollout(self, n_steps, record=(), state_stride=1, no_auto_reset=False, out=None):
+        """T closed-loop steps in ONE kernel launch, in place on slot 0.
+        record: subset of {"states","observations","actions","rewards","terminated","returns","episode_length"} -> numpy arrays (host),
+        or pass `out` = dict of preallocated torch CUDA tensors / numpy arrays (all in one memory space)."""
+        n, T = self.N_ENVIRONMENTS, n_steps
+        shapes = {"states": ((T // max(state_stride, 1) + 1, n, self.STATE_DIM), np.float32), "observations": ((T, n, 22), np.float32),
+                  "actions": ((T, n, 4), np.float32), "rewards": ((T, n), np.float32), "terminated": ((T, n), np.uint8),
+                  "returns": ((n,), np.float32), "episode_length": ((n,), np.int32)}
+        out = dict(out) if out else {}
+        for k in record:
+            if k not in out:
+                out[k] = np.zeros(shapes[k][0], shapes[k][1])
+        ro = L.RolloutOut()
+        ro.state_stride = state_stride
+        spaces = set()
+        for k, v in out.items():
+            p, ms, _ = _arg(v, shapes[k][1], shapes[k][0], k)
+            setattr(ro, k, p)
+            spaces.add(ms)
+        if len(spaces) > 1:
+            raise ValueError("rollout: all outputs must live in one memory space")
+        ro.memspace = spaces.pop() if spaces else L.DEVICE
+        self._check(self._lib.b200l2f_rollout(self._h, T, int(no_auto_reset), ctypes.byref(ro) if out else None))
+        return out

@@ -1,0 +1,53 @@
+"""CPU-only checks of the drop-in boundary: the shared library loads and exports every symbol include/b200_l2f.h declares,
+the ctypes table matches the header, and the product package never touches the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200_l2f.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200l2f_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from raptor_b200 import build, _lib
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import raptor_b200
+    with pytest.raises(raptor_b200.EngineError) as e:
+        raptor_b200.VectorEnvironment(8)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "raptor_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "l2f_oracle" not in txt and "libl2f_ref" not in txt, f
+
+
+def test_policy_blob_matches_golden():
+    import numpy as np
+    import raptor_b200
+    blob = raptor_b200.raptor_policy_blob()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "raptor_kat.npz"))
+    assert blob.shape == (2084,) and np.array_equal(blob, g["blob"])

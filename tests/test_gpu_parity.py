@@ -1,0 +1,236 @@
+"""GPU parity tests proper (-m gpu): the CUDA engine, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances: integer work (RNG streams, ring-buffer indices, GRU step counters, terminated flags) is bit-exact; float32 state/action
+trajectories are compared with rtol 1e-4 (the north-star's bound over 100 closed-loop steps) plus a small absolute floor for values
+that cross zero; single steps from identical inputs are held to 2e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import foundation_dr_env_params
+from oracle import binding as B
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import raptor_b200
+    return raptor_b200
+
+
+def close(a, b, rtol, atol, what=""):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=what)
+
+
+def test_rng_streams_bit_exact(rb, port):
+    env = rb.VectorEnvironment(1000, rb.SPEC_RAPTOR, first_env_id=12345)
+    env.initialize_rng(seed=99, warmup=7)
+    want = port.rng_states(99, 1000, first_env=12345, warmup=0)
+    for i in range(1000):   # warmup advances the raw engine (uniform draws advance it once each)
+        s = want[i:i + 1].copy()
+        for _ in range(7):
+            port.rng_uniform(s, 0, 1)
+        want[i] = s[0]
+    assert np.array_equal(env.get_rng(), want)
+
+
+@pytest.mark.parametrize("spec", [B.SPEC_DEFAULT_DR, B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR])
+def test_samplers(rb, port, spec):
+    n = 512
+    env = rb.VectorEnvironment(n, spec)
+    env_p = foundation_dr_env_params(port, spec)
+    env.set_environment_parameters(env_p)
+    env.initialize_rng(seed=3, warmup=16)
+    rng = env.get_rng()
+    env.sample_initial_parameters()
+    want_p = port.sample_initial_parameters_n(spec, env_p, rng)
+    got_p = env.get_parameters()
+    assert np.array_equal(env.get_rng(), rng)
+    close(got_p, want_p, 2e-6, 0, "sampled parameters")
+    env.set_parameters(want_p)     # continue from identical parameters
+    env.sample_initial_state()
+    want_s = port.sample_initial_state_n(spec, want_p, rng)
+    assert np.array_equal(env.get_rng(), rng)
+    close(env.get_state(), want_s, 2e-6, 1e-7, "sampled states")
+    env.initial_state(slot=1)
+    want_i = np.array([port.initial_state(spec, want_p[i]) for i in range(n)])
+    close(env.get_state(slot=1), want_i, 1e-6, 0, "initial states")
+
+
+@pytest.mark.parametrize("spec", [B.SPEC_DEFAULT, B.SPEC_RAPTOR, B.SPEC_TEACHER])
+@pytest.mark.parametrize("noise", [False, True])
+def test_vector_api_single_steps(rb, port, spec, noise):
+    """observe / step / reward / terminated from identical inputs, re-anchored on the oracle every step"""
+    n, T = 256, 24
+    rs = np.random.RandomState(spec)
+    env = rb.VectorEnvironment(n, spec)
+    p = port.nominal_parameters(spec)
+    if noise:
+        p[108:113] = [0.01, 0.02, 0.03, 0.04, 0.05]
+        p[113] = 0.05
+    params = np.tile(p, (n, 1))
+    rng = port.rng_states(5, n, warmup=24)
+    s = port.sample_initial_state_n(spec, params, rng)
+    env.set_parameters(params)
+    for t in range(T):
+        env.set_state(s)
+        env.set_rng(rng)
+        a = rs.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+        obs = env.observe()
+        dts = env.step(a)
+        nxt = env.get_state(slot=1)
+        rew = env.reward(a)
+        term = env.terminated(slot=1)
+        got_rng = env.get_rng()
+        w_obs = np.zeros_like(obs); w_nxt = np.zeros_like(nxt); w_rew = np.zeros(n, np.float32); w_term = np.zeros(n, np.uint8)
+        for i in range(n):
+            r = rng[i:i + 1].copy()
+            w_obs[i] = port.observe(spec, p, s[i], r)
+            w_nxt[i], dt = port.step(spec, p, s[i], a[i], r)
+            w_rew[i] = port.reward(spec, p, s[i], a[i], w_nxt[i])
+            w_term[i] = port.terminated(spec, p, w_nxt[i])
+            rng[i] = r[0]
+            assert dts[i] == dt
+        assert np.array_equal(got_rng, rng)
+        tol = 2e-5 if noise else 2e-6   # logf/cosf of the Box-Muller transform differ by an ulp between libm and CUDA
+        close(obs, w_obs, tol, tol, "observe")
+        close(nxt, w_nxt, 5e-6 if not noise else 5e-5, 2e-6 if not noise else 2e-5, "step")
+        close(rew, w_rew, 1e-5, 2e-5, "reward")
+        assert np.array_equal(term, w_term)
+        s = w_nxt
+
+
+def test_policy_known_answer_test(rb):
+    """the KAT that ships in the checkpoint, through the GPU actor (2 sequences x 500 steps)"""
+    k = np.load(os.path.join(G, "raptor_kat.npz"))
+    for flags, bound in [(rb.FLAG_ACCURATE_MATH, 3e-6), (0, 1e-5)]:
+        env = rb.VectorEnvironment(2, rb.SPEC_RAPTOR, flags=flags)
+        env.load_policy(k["blob"])
+        env.policy_reset()
+        errs = []
+        for t in range(500):
+            a = env.policy_evaluate_step(np.ascontiguousarray(k["input"][t]))
+            errs.append(np.abs(a - k["output"][t]))
+        errs = np.array(errs)
+        assert errs.max() < bound, (flags, errs.max())
+        h, g = env.get_hidden()
+        assert np.all(g == 0)   # 500 steps == SEQUENCE_LENGTH: the counter wrapped and the hidden state was reset (gru/operations_generic.h:400-410)
+        assert np.array_equal(h, np.tile(k["h0"], (2, 1)))
+
+
+@pytest.mark.parametrize("name,T_cmp", [("default_8x500.npz", 100), ("raptor_dr_64x100.npz", 100), ("raptor_noise_8x50.npz", 50)])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_fused_rollout_vs_golden(rb, name, T_cmp, flags):
+    """closed loop from identical seeds: states and actions within 1e-4 relative over 100 steps, RNG / counters bit-exact"""
+    g = np.load(os.path.join(G, name))
+    spec = int(g["spec"])
+    n = g["states0"].shape[0]
+    T = g["actions"].shape[0]
+    env = rb.VectorEnvironment(n, spec, flags=flags)
+    env.set_parameters(np.ascontiguousarray(g["params"]))
+    env.set_state(np.ascontiguousarray(g["states0"]))
+    env.set_rng(np.ascontiguousarray(g["rng0"]))
+    env.load_policy(np.load(os.path.join(G, "raptor_kat.npz"))["blob"])
+    out = env.rollout(T, record=("states", "actions", "rewards", "terminated"))
+    noise = "noise" in name
+    rtol, atol = (1e-4, 2e-5) if not noise else (1e-3, 2e-4)
+    steps = g["state_steps"]
+    sel = steps <= T_cmp
+    close(out["states"][steps[sel]], g["states"][sel], rtol, atol, "states")
+    close(out["actions"][:T_cmp], g["actions"][:T_cmp], rtol, atol * 5, "actions")
+    close(out["rewards"][:T_cmp], g["rewards"][:T_cmp], 1e-3, 1e-3, "rewards")
+    assert np.array_equal(out["terminated"], g["terminated"])
+    assert np.array_equal(env.get_rng(), g["final_rng"])
+    h, gs = env.get_hidden()
+    assert np.array_equal(gs, g["final_gru_step"])
+    # the whole horizon stays bounded-close as well (closed loop is stable under the policy)
+    close(out["states"][steps], g["states"], 50 * rtol, 50 * atol, "states, full horizon")
+    close(env.get_state(), out["states"][-1], 0, 0, "final state row == slot 0")
+
+
+@pytest.mark.parametrize("spec", [B.SPEC_DEFAULT, B.SPEC_RAPTOR])
+def test_fused_rollout_equals_stepwise_api(rb, port, spec):
+    """ONE fused launch == T x (observe, evaluate_step, step) through the vector API"""
+    n, T = 300, 40
+    blob = rb.raptor_policy_blob()
+    a_env = rb.VectorEnvironment(n, spec)
+    b_env = rb.VectorEnvironment(n, spec)
+    for e in (a_env, b_env):
+        e.initialize_rng(11, warmup=20)
+        e.sample_initial_state()
+        e.load_policy(blob)
+    out = a_env.rollout(T, record=("actions", "rewards", "terminated", "returns", "episode_length"))
+    acts, rews = [], []
+    for t in range(T):
+        o = b_env.observe()
+        a = b_env.policy_evaluate_step(np.ascontiguousarray(o[:, :22]))
+        b_env.step(a)
+        rews.append(b_env.reward(a))
+        b_env.copy_state(0, 1)
+        acts.append(a.copy())
+    close(out["actions"], np.array(acts), 1e-5, 1e-6, "actions")
+    close(out["rewards"], np.array(rews), 1e-4, 1e-4, "rewards")
+    close(a_env.get_state(), b_env.get_state(), 1e-5, 1e-6, "final states")
+    assert np.array_equal(a_env.get_rng(), b_env.get_rng())
+    # evaluate()-style statistics: return accumulated until (and including) the first terminated step
+    term = out["terminated"].astype(bool)
+    first = np.where(term.any(0), term.argmax(0), T - 1)
+    want_len = first + 1
+    assert np.array_equal(out["episode_length"], want_len)
+    want_ret = np.array([out["rewards"][:want_len[i], i].sum() for i in range(n)])
+    close(out["returns"], want_ret, 1e-4, 1e-3, "returns")
+
+
+def test_full_size_properties(rb):
+    """BASELINE config 2 size (65 536 envs): determinism, shard invariance (global env ids), quaternion norm, bounded states"""
+    n, T = 65536, 200
+    blob = rb.raptor_policy_blob()
+
+    def run(n_envs, first):
+        e = rb.VectorEnvironment(n_envs, rb.SPEC_RAPTOR, first_env_id=first)
+        e.initialize_rng(2024, warmup=16)
+        e.sample_initial_state()
+        e.load_policy(blob)
+        o = e.rollout(T, record=("returns", "episode_length"))
+        return e.get_state(), o["returns"], o["episode_length"], e.get_rng()
+
+    s1, r1, l1, g1 = run(n, 0)
+    s2, r2, l2, g2 = run(n, 0)
+    assert np.array_equal(s1, s2) and np.array_equal(r1, r2) and np.array_equal(g1, g2)       # deterministic
+    sa, ra, la, ga = run(n // 2, 0)
+    sb, rb_, lb, gb = run(n // 2, n // 2)
+    assert np.array_equal(np.concatenate([sa, sb]), s1) and np.array_equal(np.concatenate([ra, rb_]), r1)   # shard invariant
+    assert np.array_equal(np.concatenate([ga, gb]), g1)
+    q = s1[:, 3:7]
+    close(np.linalg.norm(q, axis=1), np.ones(n), 1e-5, 0, "unit quaternions")
+    assert np.isfinite(s1).all()
+    alive = l1 == T
+    assert alive.mean() > 0.8            # the policy keeps the nominal Crazyflie in the box from the init distribution
+    assert np.abs(s1[alive, :3]).max() <= 1.0 + 1e-6
+
+
+def test_ragged_sizes_and_errors(rb):
+    for n in [1, 31, 129, 1000]:
+        e = rb.VectorEnvironment(n, rb.SPEC_DEFAULT)
+        e.initialize_rng(1, warmup=8)
+        e.sample_initial_state()
+        e.load_policy()
+        o = e.rollout(3, record=("actions",))
+        assert o["actions"].shape == (3, n, 4) and np.isfinite(o["actions"]).all()
+        o0 = e.rollout(0, record=("returns",))
+        assert np.all(o0["returns"] == 0)
+    e = rb.VectorEnvironment(4, rb.SPEC_RAPTOR)
+    with pytest.raises(rb.EngineError):
+        e.rollout(1)                                 # no policy loaded
+    with pytest.raises(rb.EngineError):
+        e.observe(slot=7)                            # bad slot
+    with pytest.raises(rb.EngineError):
+        bad = e.get_environment_parameters(); bad[126] = 1.0; e.set_environment_parameters(bad); e.sample_initial_parameters()  # DR range without DR spec
+    with pytest.raises(rb.EngineError):
+        rb.VectorEnvironment(0)
