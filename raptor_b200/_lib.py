@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb200l2f.so")
+LIB_PATH = os.environ.get("B200L2F_LIB") or os.path.join(HERE, "lib", "libb200l2f.so")   # B200L2F_LIB: tuning experiments only
 
 c_int, c_i32, c_i64, c_u64, c_f = ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float
 vp = ctypes.c_void_p

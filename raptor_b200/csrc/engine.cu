@@ -5,12 +5,14 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <new>
 
 #include "../../include/b200_l2f.h"
 #include "kernels.cuh"
+#include "rollout_tc.cuh"
 
 using namespace b200l2f;
 
@@ -38,6 +40,9 @@ struct b200l2f_handle {
     bool policy_loaded = false; b200l2f_policy_desc pol{};
     float* d_blob = nullptr; size_t blob_floats = 0;
     float* d_hidden = nullptr; int* d_gru_step = nullptr;
+    float* d_tc_image = nullptr;     // tensor-core weight image (hi/lo planes of the three B operands, TMA source)
+    std::vector<float> h_image;      // k-major actor image passed by value to the fused kernels (constant-bank weights)
+    bool weights_in_constant_bank = false; bool rolled = false;
     // PPO runner bookkeeping (rl/components/on_policy_runner/on_policy_runner.h: episode_step, episode_return, truncated)
     int* d_episode_step = nullptr; float* d_episode_return = nullptr; uint8_t* d_truncated = nullptr;
     // staging
@@ -171,18 +176,38 @@ int refresh_features(b200l2f_handle* h){
     return B200L2F_OK;
 }
 
-template <class Spec, bool NOISE, bool FAST>
+template <class Spec, bool NOISE, bool FAST, bool CONSTW, bool ROLLED = false>
 int launch_rollout_raptor(b200l2f_handle* h, const RolloutArgs& a){
     constexpr int IN = 22, HD = 16, OUT = 4;
-    auto kern = k_rollout_raptor<Spec, IN, HD, OUT, NOISE, FAST>;
-    const size_t smem = (size_t)(RaptorImage<IN, HD, OUT>::SIZE + P_DYN_DIM * BLOCK) * sizeof(float);
+    constexpr int IMG = RaptorImage<IN, HD, OUT>::SIZE;
+    auto kern = k_rollout_raptor<Spec, IN, HD, OUT, NOISE, FAST, CONSTW, ROLLED>;
+    const size_t smem = (size_t)((CONSTW ? 0 : IMG) + P_DYN_DIM * BLOCK + (ROLLED ? RaptorScratch<IN, HD>::ROWS * BLOCK : 0)) * sizeof(float);
     static bool configured[8] = {};   // per device
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
-    kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a);
+    if constexpr(CONSTW){
+        kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, *reinterpret_cast<const WeightBlock<IMG>*>(h->h_image.data()));
+    }
+    else{
+        kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, WeightBlock<1>{});
+    }
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+
+template <class Spec, bool FAST>
+int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
+    auto kern = k_rollout_raptor_tc<Spec, FAST>;
+    static bool configured[8] = {};
+    int dev = h->cfg.device & 7;
+    if(!configured[dev]){
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem::TOTAL));
+        configured[dev] = true;
+    }
+    kern<<<grid_for(a.n, BLOCK), BLOCK, TcSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
     LAUNCH_CHECK();
     return B200L2F_OK;
 }
@@ -257,6 +282,7 @@ int b200l2f_destroy(b200l2f_handle* h){
     if(h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_params); cudaFree(h->d_env_row);
     for(float* p : h->d_state) cudaFree(p);
+    cudaFree(h->d_tc_image);
     cudaFree(h->d_rng); cudaFree(h->d_flags); cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
     cudaFree(h->d_episode_step); cudaFree(h->d_episode_return); cudaFree(h->d_truncated);
     if(h->d_stage) cudaFree(h->d_stage);
@@ -504,6 +530,21 @@ int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
     CU(cudaMemcpy(h->d_blob, blob, sizeof(float) * n_floats, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&h->d_hidden, sizeof(float) * desc->hidden_dim * (size_t)h->n));
     CU(cudaMalloc(&h->d_gru_step, sizeof(int) * (size_t)h->n));
+    h->h_image.assign(RaptorImage<22, 16, 4>::SIZE, 0.0f);
+    build_raptor_image_host<22, 16, 4>(h->h_image.data(), blob);
+    {   // tensor-core operand image: tf32 hi/lo planes in the canonical K-major core-matrix order
+        std::vector<float> tcimg(TcImage::SIZE);
+        build_tc_image_host(tcimg.data(), blob);
+        cudaFree(h->d_tc_image); h->d_tc_image = nullptr;
+        CU(cudaMalloc(&h->d_tc_image, TcImage::BYTES));
+        CU(cudaMemcpy(h->d_tc_image, tcimg.data(), TcImage::BYTES, cudaMemcpyHostToDevice));
+    }
+    {   // tuning knob, measured on B200 (profiles/r01_summary.md): weights staged in shared memory (broadcast LDS.128) are ~3% faster than
+        // riding in the launch's constant bank (LDCU + uniform-register FFMA operands), so shared memory is the default
+        const char* env = std::getenv("B200L2F_WEIGHTS");
+        h->weights_in_constant_bank = env && std::string(env) == "const";
+        const char* code = std::getenv("B200L2F_CODE");      // "rolled": compact-code variant (rolled actor k-loops + RK4 stage loop), fits the instruction cache
+        h->rolled = code && std::string(code) == "rolled"; }   // measured equal within 2 % on B200 (profiles/): the unrolled body stays the default
     h->pol = *desc; h->blob_floats = n_floats; h->policy_loaded = true;
     if(h->pol.gru_sequence_length <= 0) h->pol.gru_sequence_length = 500;
     return b200l2f_policy_reset(h, nullptr, B200L2F_HOST);
@@ -610,10 +651,16 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     for(auto& s : slices) *s.kernel_ptr = (ms == B200L2F_HOST) ? (void*)((char*)h->d_stage + s.offset) : s.user;
     const bool noise = (h->features & 1) != 0;
     const bool fast = !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
+    const bool constw = h->weights_in_constant_bank;
+    const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32;
+    if(tensor_cores && noise) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the tcgen05 variant is built for noise-free observation/action parameters");
     auto go = [&](auto spec) -> int {
         using Spec = decltype(spec);
-        if(noise) return fast ? launch_rollout_raptor<Spec, true, true>(h, a) : launch_rollout_raptor<Spec, true, false>(h, a);
-        return fast ? launch_rollout_raptor<Spec, false, true>(h, a) : launch_rollout_raptor<Spec, false, false>(h, a);
+        if(tensor_cores) return fast ? launch_rollout_tc<Spec, true>(h, a) : launch_rollout_tc<Spec, false>(h, a);
+        if(noise) return fast ? launch_rollout_raptor<Spec, true, true, true>(h, a) : launch_rollout_raptor<Spec, true, false, true>(h, a);
+        if(!fast) return launch_rollout_raptor<Spec, false, false, true>(h, a);
+        if(constw) return launch_rollout_raptor<Spec, false, true, true>(h, a);
+        return h->rolled ? launch_rollout_raptor<Spec, false, true, false, true>(h, a) : launch_rollout_raptor<Spec, false, true, false, false>(h, a);
     };
     rc = h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
     if(rc) return rc;

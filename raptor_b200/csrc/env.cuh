@@ -199,7 +199,7 @@ __device__ __forceinline__ void dynamics(const P& p, const DynInvariants& d, con
 // `p` must be an accessor whose time-constant slots hold RECIPROCALS (see stage_dynamics / ParamsInvTau).
 // hist_ptr: H > 1 only, the SoA rows of action_history of the NEXT state (element (h,a) at hist_ptr[(4h+a)*n]).
 // ---------------------------------------------------------------------------------------------------------------
-template <class Spec, bool NOISE, class P>
+template <class Spec, bool NOISE, class P, bool ROLLED_RK4 = false>
 __device__ __forceinline__ void env_step(EnvState<Spec>& st, const P& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
                                          float* __restrict__ hist_ptr, size_t n){
     float setpoint[4];
@@ -213,18 +213,35 @@ __device__ __forceinline__ void env_step(EnvState<Spec>& st, const P& p, const D
     const float dt = d.dt;
     const float dt2 = dt / 2.0f, dt3 = dt / 3.0f, dt6 = dt / 6.0f;
     float k[X_DIM], tmp[X_DIM], acc[X_DIM];
-    dynamics(p, d, st.x, setpoint, k);                                            // k1
+    if constexpr(ROLLED_RK4){
+        // same arithmetic as below with the four stages as ONE loop body (a quarter of the code; the stage weights are selected per iteration)
 #pragma unroll
-    for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i] + dt6 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
-    dynamics(p, d, tmp, setpoint, k);                                             // k2
+        for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i]; tmp[i] = st.x[i]; }
+#pragma unroll 1
+        for(int s = 0; s < 4; s++){
+            dynamics(p, d, tmp, setpoint, k);
+            const float wa = (s == 0 || s == 3) ? dt6 : dt3;     // next = x + dt/6 k1 + dt/3 k2 + dt/3 k3 + dt/6 k4, accumulated in that order
+            const float wt = (s == 2) ? dt : dt2;                 // stage inputs x + dt/2 k1, x + dt/2 k2, x + dt k3
 #pragma unroll
-    for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
-    dynamics(p, d, tmp, setpoint, k);                                             // k3
+            for(int i = 0; i < X_DIM; i++){ acc[i] += wa * k[i]; tmp[i] = st.x[i] + wt * k[i]; }
+        }
 #pragma unroll
-    for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt * k[i]; }
-    dynamics(p, d, tmp, setpoint, k);                                             // k4
+        for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i];
+    }
+    else{
+        dynamics(p, d, st.x, setpoint, k);                                            // k1
 #pragma unroll
-    for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i] + dt6 * k[i];
+        for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i] + dt6 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
+        dynamics(p, d, tmp, setpoint, k);                                             // k2
+#pragma unroll
+        for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
+        dynamics(p, d, tmp, setpoint, k);                                             // k3
+#pragma unroll
+        for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt * k[i]; }
+        dynamics(p, d, tmp, setpoint, k);                                             // k4
+#pragma unroll
+        for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i] + dt6 * k[i];
+    }
     // ---- post integration
     {
         float nrm = 0.0f;

@@ -14,7 +14,14 @@
 
 namespace b200l2f {
 
-constexpr int BLOCK = 128;
+#ifndef B200L2F_BLOCK
+#define B200L2F_BLOCK 128
+#endif
+#ifndef B200L2F_MIN_BLOCKS
+#define B200L2F_MIN_BLOCKS 2
+#endif
+constexpr int BLOCK = B200L2F_BLOCK;               // environments (= threads) per CTA
+constexpr int MIN_BLOCKS = B200L2F_MIN_BLOCKS;     // resident CTAs per SM the fused kernels are register-budgeted for
 
 // stage the dynamics block of this thread's environment: sm[i * BLOCK + tid] = params[i][env]; time constants -> reciprocals
 __device__ __forceinline__ ParamsStaged stage_dynamics(float* __restrict__ sm_dyn, const float* __restrict__ params, size_t n, size_t env){
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(BLOCK) k_raptor_step(const float* __restrict__
 #pragma unroll
     for(int j = 0; j < HD; j++) h[j] = hidden[(size_t)j * n + e];
     int gs = gru_step[e];
-    raptor_forward<IN, HD, OUT, FAST>(sm_img, o, h, gs, seq_len, no_auto_reset != 0, a);
+    raptor_forward<IN, HD, OUT, FAST>(WeightsShared{sm_img}, o, h, gs, seq_len, no_auto_reset != 0, a);
 #pragma unroll
     for(int j = 0; j < HD; j++) hidden[(size_t)j * n + e] = h[j];
     gru_step[e] = gs;
@@ -254,13 +261,19 @@ __device__ __forceinline__ void write_state_row(const EnvState<Spec>& st, const 
     }
 }
 
-template <class Spec, int IN, int HD, int OUT, bool NOISE, bool FAST>
-__global__ void __launch_bounds__(BLOCK) k_rollout_raptor(const RolloutArgs a){
+// CONSTW: actor weights in the launch's constant bank instead of shared memory.  ROLLED: compact-code variant (rolled actor k-loops with the
+// loop-indexed vectors and the hidden state in a shared-memory scratch column, RK4 stages as one loop body).
+template <class Spec, int IN, int HD, int OUT, bool NOISE, bool FAST, bool CONSTW, bool ROLLED>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor(const __grid_constant__ RolloutArgs a, const __grid_constant__ WeightBlock<CONSTW ? RaptorImage<IN, HD, OUT>::SIZE : 1> wk){
+    static_assert(!(CONSTW && ROLLED), "the rolled actor indexes the weight image with a loop variable: it needs the shared-memory image");
     static_assert(IN == 22 && OUT == 4, "the Raptor actor consumes the first 22 observation columns and emits 4 motor commands");
     extern __shared__ __align__(16) float smem[];
-    float* sm_img = smem;                                         // RaptorImage<IN,HD,OUT>::SIZE floats
-    float* sm_dyn = smem + RaptorImage<IN, HD, OUT>::SIZE;       // P_DYN_DIM * BLOCK floats
-    stage_raptor<IN, HD, OUT>(sm_img, a.blob);
+    constexpr int IMG = RaptorImage<IN, HD, OUT>::SIZE;
+    float* sm_img = smem;                                         // IMG floats (unused when the weights ride in the constant bank)
+    float* sm_dyn = smem + (CONSTW ? 0 : IMG);                    // P_DYN_DIM * BLOCK floats
+    using SCR = RaptorScratch<IN, HD>;
+    float* scr = sm_dyn + P_DYN_DIM * BLOCK + threadIdx.x;       // ROLLED: SCR::ROWS * BLOCK floats, this thread's column
+    if constexpr(!CONSTW) stage_raptor<IN, HD, OUT>(sm_img, a.blob);
     const int e = blockIdx.x * BLOCK + threadIdx.x;
     const bool active = e < a.n;
     const size_t n = (size_t)a.n;
@@ -273,9 +286,15 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_raptor(const RolloutArgs a){
     dyn_invariants(d, p, st);
     float* hist_ptr = a.state + (size_t)S_HIST * n + env;
     uint64_t rng = a.rng[env];
-    float h[HD];
+    float h[ROLLED ? 1 : HD];
+    if constexpr(ROLLED){
 #pragma unroll
-    for(int j = 0; j < HD; j++) h[j] = a.hidden[(size_t)j * n + env];
+        for(int j = 0; j < HD; j++) scr[(SCR::H + j) * BLOCK] = a.hidden[(size_t)j * n + env];
+    }
+    else{
+#pragma unroll
+        for(int j = 0; j < HD; j++) h[j] = a.hidden[(size_t)j * n + env];
+    }
     int gs = a.gru_step[env];
     float ret = 0.0f; int eplen = 0; bool done = false;
     const bool no_auto_reset = a.no_auto_reset != 0;
@@ -300,11 +319,17 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_raptor(const RolloutArgs a){
             for(int i = 0; i < IN; i++) row[i] = obs[i];
         }
         float act[OUT];
-        raptor_forward<IN, HD, OUT, FAST>(sm_img, obs, h, gs, a.seq_len, no_auto_reset, act);
+        if constexpr(ROLLED){
+#pragma unroll
+            for(int i = 0; i < IN; i++) scr[(SCR::OBS + i) * BLOCK] = obs[i];
+            raptor_forward_rolled<IN, HD, OUT, FAST>(sm_img, scr, BLOCK, gs, a.seq_len, no_auto_reset, act);
+        }
+        else if constexpr(CONSTW) raptor_forward<IN, HD, OUT, FAST>(WeightsParam<IMG>{wk}, obs, h, gs, a.seq_len, no_auto_reset, act);
+        else raptor_forward<IN, HD, OUT, FAST>(WeightsShared{sm_img}, obs, h, gs, a.seq_len, no_auto_reset, act);
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        if(Spec::H == 1 || active) env_step<Spec, NOISE>(st, p, d, act, rng, hist_ptr, n);   // H > 1 writes the ring in HBM: shadow lanes must not
+        if(Spec::H == 1 || active) env_step<Spec, NOISE, ParamsStaged, ROLLED>(st, p, d, act, rng, hist_ptr, n);   // H > 1 writes the ring in HBM: shadow lanes must not
         const bool term = env_terminated(p, st.x);
         const float r = env_reward(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = r;
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_raptor(const RolloutArgs a){
     store_state(st, a.state + env, n);
     a.rng[env] = rng;
 #pragma unroll
-    for(int j = 0; j < HD; j++) a.hidden[(size_t)j * n + env] = h[j];
+    for(int j = 0; j < HD; j++) a.hidden[(size_t)j * n + env] = ROLLED ? scr[(SCR::H + j) * BLOCK] : h[ROLLED ? 0 : j];
     a.gru_step[env] = gs;
     if(a.out_returns) a.out_returns[env] = ret;
     if(a.out_eplen) a.out_eplen[env] = eplen;

@@ -1,0 +1,448 @@
+// raptor_b200/csrc/rollout_tc.cuh -- fused persistent rollout with the actor GEMMs on the 5th-generation tensor cores.
+//
+// One CTA = 128 threads = 128 environments = the M dimension of every MMA.  Per control step the CTA runs three dependent GEMMs
+//   G1  [128 x 24] x [24 x 16]   obs(22) | 1 | 0          -> dense-1 pre-activation (bias folded in as a K column)
+//   G2  [128 x 40] x [40 x 64]   x1(16) | h(16) | 1 1 0.. -> r,z pre-activations (32), n_x (16), n_h (16)   (block-structured B)
+//   G3  [128 x 24] x [24 x 16]   h'(16) | 1 | 0           -> action (4 of 16 columns used)
+// as tcgen05.mma.kind::tf32 with the 3xTF32 error-compensated split (A_hi B_hi + A_lo B_hi + A_hi B_lo; plain TF32 has a 10-bit
+// mantissa and breaks the 1e-4 closed-loop parity bound).  Activations are produced on chip: every thread writes ITS row of the A
+// operand (hi and lo planes) straight into the canonical K-major core-matrix layout in shared memory with conflict-free STS.128,
+// one elected thread issues the MMAs, accumulators live in TMEM and each thread reads back its own row with tcgen05.ld (lane = env).
+// The weight image (hi/lo planes of the three B operands, 26 KB) arrives once per CTA by a 1-D TMA bulk copy.
+// Everything that is not a dense contraction (observe, gates, RK4, reward) stays on the fp32 CUDA cores exactly as in k_rollout_raptor,
+// except that the per-rotor force/torque accumulation uses the per-environment rotor matrices A_F, A_T (thrust and torque are linear in
+// the four rotor thrusts), which shrinks the staged parameter block from 86 to 67 floats and a dynamics evaluation by ~50 instructions.
+#pragma once
+#include "kernels.cuh"
+#include "tc.cuh"
+
+namespace b200l2f {
+
+// ---- B operand image (host-built): for each GEMM two planes (hi, lo), each [K/4][N][4] floats ------------------------------
+struct TcImage {
+    static constexpr int K1 = 24, N1 = 16, K2 = 40, N2 = 64, K3 = 24, N3 = 16;
+    static constexpr int B1_HI = 0, B1_LO = B1_HI + K1 * N1;
+    static constexpr int B2_HI = B1_LO + K1 * N1, B2_LO = B2_HI + K2 * N2;
+    static constexpr int B3_HI = B2_LO + K2 * N2, B3_LO = B3_HI + K3 * N3;
+    static constexpr int H0 = B3_LO + K3 * N3;   // initial hidden state (16 floats) for the auto-reset
+    static constexpr int SIZE = H0 + 16;         // floats
+    static constexpr int BYTES = SIZE * 4;
+    static_assert(BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+};
+inline void tc_split_host(float x, float& hi, float& lo){
+    uint32_t u; std::memcpy(&u, &x, 4); u &= 0xFFFFE000u; std::memcpy(&hi, &u, 4); lo = x - hi;
+}
+// blob (include/b200_l2f.h RAPTOR_GRU order) -> image
+inline void build_tc_image_host(float* img, const float* blob){
+    constexpr int IN = 22, HD = 16, OUT = 4;
+    const float* W1 = blob; const float* b1 = W1 + HD * IN;
+    const float* Wih = b1 + HD; const float* bih = Wih + 3 * HD * HD;
+    const float* Whh = bih + 3 * HD; const float* bhh = Whh + 3 * HD * HD;
+    const float* h0 = bhh + 3 * HD; const float* W2 = h0 + HD; const float* b2 = W2 + OUT * HD;
+    for(int i = 0; i < TcImage::SIZE; i++) img[i] = 0.0f;
+    auto put = [&](int hi_base, int lo_base, int N, int n, int k, float v){
+        float hi, lo; tc_split_host(v, hi, lo);
+        const int idx = (k / 4) * N * 4 + n * 4 + (k % 4);
+        img[hi_base + idx] = hi; img[lo_base + idx] = lo;
+    };
+    for(int n = 0; n < HD; n++){
+        for(int k = 0; k < IN; k++) put(TcImage::B1_HI, TcImage::B1_LO, 16, n, k, W1[n * IN + k]);
+        put(TcImage::B1_HI, TcImage::B1_LO, 16, n, 22, b1[n]);
+    }
+    // G2 columns: 0..15 x1, 16..31 h, 32 -> b_hh, 33 -> b_ih (A holds 1.0 in both)
+    for(int j = 0; j < 2 * HD; j++){            // r, z rows
+        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, j, k, Wih[j * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 16 + k, Whh[j * HD + k]); }
+        put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 32, bhh[j]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 33, bih[j]);
+    }
+    for(int j = 0; j < HD; j++){                // n_x rows 32..47, n_h rows 48..63
+        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, k, Wih[(2 * HD + j) * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 16 + k, Whh[(2 * HD + j) * HD + k]); }
+        put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, 33, bih[2 * HD + j]);
+        put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 32, bhh[2 * HD + j]);
+    }
+    for(int n = 0; n < OUT; n++){
+        for(int k = 0; k < HD; k++) put(TcImage::B3_HI, TcImage::B3_LO, 16, n, k, W2[n * HD + k]);
+        put(TcImage::B3_HI, TcImage::B3_LO, 16, n, 16, b2[n]);
+    }
+    for(int j = 0; j < HD; j++) img[TcImage::H0 + j] = h0[j];
+}
+
+// ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
+enum DynC : int { C_COEF = 0, C_AF = 12, C_AT = 24, C_ITAU_RISE = 36, C_ITAU_FALL = 40, C_GRAVITY = 44, C_J = 47, C_JINV = 56, C_ACT_MIN = 65, C_ACT_MAX = 66, C_DIM = 67 };
+struct ParamsCompiled {
+    const float* sm; const float* __restrict__ base; size_t stride;   // sm: staged block (this thread's column); base/stride: full parameter column in HBM
+    __device__ __forceinline__ float c(int i) const { return sm[i * BLOCK]; }
+    __device__ __forceinline__ float operator[](int i) const { return __ldg(base + (size_t)i * stride); }   // everything outside the dynamics block
+};
+__device__ __forceinline__ ParamsCompiled stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* __restrict__ params, size_t n, size_t env){
+    float* sm = sm_dyn + threadIdx.x;
+    const float* g = params + env;
+    auto P = [&](int i){ return __ldg(g + (size_t)i * n); };
+#pragma unroll
+    for(int i = 0; i < 12; i++) sm[(C_COEF + i) * BLOCK] = P(P_THRUST_COEF + i);
+#pragma unroll
+    for(int r = 0; r < 4; r++){
+        const float dx = P(P_THRUST_DIR + 3 * r), dy = P(P_THRUST_DIR + 3 * r + 1), dz = P(P_THRUST_DIR + 3 * r + 2);
+        const float px = P(P_ROTOR_POS + 3 * r), py = P(P_ROTOR_POS + 3 * r + 1), pz = P(P_ROTOR_POS + 3 * r + 2);
+        const float kq = P(P_TORQUE_CONST + r);
+        sm[(C_AF + 0 * 4 + r) * BLOCK] = dx; sm[(C_AF + 1 * 4 + r) * BLOCK] = dy; sm[(C_AF + 2 * 4 + r) * BLOCK] = dz;
+        // torque of rotor r per unit thrust: torque_dir * k_q + r x dir   (60_dynamics.h:38-39)
+        sm[(C_AT + 0 * 4 + r) * BLOCK] = P(P_TORQUE_DIR + 3 * r + 0) * kq + (py * dz - pz * dy);
+        sm[(C_AT + 1 * 4 + r) * BLOCK] = P(P_TORQUE_DIR + 3 * r + 1) * kq + (pz * dx - px * dz);
+        sm[(C_AT + 2 * 4 + r) * BLOCK] = P(P_TORQUE_DIR + 3 * r + 2) * kq + (px * dy - py * dx);
+        sm[(C_ITAU_RISE + r) * BLOCK] = 1.0f / P(P_TAU_RISE + r);
+        sm[(C_ITAU_FALL + r) * BLOCK] = 1.0f / P(P_TAU_FALL + r);
+    }
+#pragma unroll
+    for(int i = 0; i < 3; i++) sm[(C_GRAVITY + i) * BLOCK] = P(P_GRAVITY + i);
+#pragma unroll
+    for(int i = 0; i < 9; i++){ sm[(C_J + i) * BLOCK] = P(P_J + i); sm[(C_JINV + i) * BLOCK] = P(P_JINV + i); }
+    sm[C_ACT_MIN * BLOCK] = P(P_ACT_MIN); sm[C_ACT_MAX * BLOCK] = P(P_ACT_MAX);
+    ParamsCompiled p; p.sm = sm; p.base = g; p.stride = n;
+    return p;
+}
+// multirotor dynamics with the rotor matrices (same physics as dynamics() in env.cuh; thrust/torque summed as matrix-vector products)
+__device__ __forceinline__ void dynamics_compiled(const ParamsCompiled& p, const DynInvariants& d, const float* __restrict__ x, const float* __restrict__ setpoint, float* __restrict__ dx){
+    float tm[4];
+#pragma unroll
+    for(int r = 0; r < 4; r++){
+        const float rpm = x[X_RPM + r];
+        tm[r] = p.c(C_COEF + 3 * r) + p.c(C_COEF + 3 * r + 1) * rpm + p.c(C_COEF + 3 * r + 2) * rpm * rpm;
+    }
+    float thrust[3], torque[3];
+#pragma unroll
+    for(int i = 0; i < 3; i++){
+        thrust[i] = p.c(C_AF + 4 * i) * tm[0] + p.c(C_AF + 4 * i + 1) * tm[1] + p.c(C_AF + 4 * i + 2) * tm[2] + p.c(C_AF + 4 * i + 3) * tm[3];
+        torque[i] = p.c(C_AT + 4 * i) * tm[0] + p.c(C_AT + 4 * i + 1) * tm[1] + p.c(C_AT + 4 * i + 2) * tm[2] + p.c(C_AT + 4 * i + 3) * tm[3];
+    }
+#pragma unroll
+    for(int i = 0; i < 3; i++) dx[X_POS + i] = x[X_VEL + i];
+    const float q0 = x[X_ORI], q1 = x[X_ORI + 1], q2 = x[X_ORI + 2], q3 = x[X_ORI + 3];
+    const float w0 = x[X_OMEGA], w1 = x[X_OMEGA + 1], w2 = x[X_OMEGA + 2];
+    dx[X_ORI + 0] = (-q1 * w0 - q2 * w1 - q3 * w2) * 0.5f;
+    dx[X_ORI + 1] = ( q0 * w0 + q2 * w2 - q3 * w1) * 0.5f;
+    dx[X_ORI + 2] = ( q0 * w1 + q3 * w0 - q1 * w2) * 0.5f;
+    dx[X_ORI + 3] = ( q0 * w2 + q1 * w1 - q2 * w0) * 0.5f;
+    {
+        float v0 = (q2 * thrust[2] - q3 * thrust[1]) * 2.0f;
+        float v1 = (q3 * thrust[0] - q1 * thrust[2]) * 2.0f;
+        float v2 = (q1 * thrust[1] - q2 * thrust[0]) * 2.0f;
+        float o0 = q2 * v2 - q3 * v1, o1 = q3 * v0 - q1 * v2, o2 = q1 * v1 - q2 * v0;
+        o0 += v0 * q0; o1 += v1 * q0; o2 += v2 * q0;
+        o0 += thrust[0]; o1 += thrust[1]; o2 += thrust[2];
+        dx[X_VEL + 0] = o0 * d.inv_mass + p.c(C_GRAVITY + 0) + d.fa[0];
+        dx[X_VEL + 1] = o1 * d.inv_mass + p.c(C_GRAVITY + 1) + d.fa[1];
+        dx[X_VEL + 2] = o2 * d.inv_mass + p.c(C_GRAVITY + 2) + d.fa[2];
+    }
+    {
+        float v[3];
+#pragma unroll
+        for(int i = 0; i < 3; i++) v[i] = p.c(C_J + 3 * i) * w0 + p.c(C_J + 3 * i + 1) * w1 + p.c(C_J + 3 * i + 2) * w2;
+        const float t0 = torque[0] - (w1 * v[2] - w2 * v[1]);
+        const float t1 = torque[1] - (w2 * v[0] - w0 * v[2]);
+        const float t2 = torque[2] - (w0 * v[1] - w1 * v[0]);
+#pragma unroll
+        for(int i = 0; i < 3; i++) dx[X_OMEGA + i] = p.c(C_JINV + 3 * i) * t0 + p.c(C_JINV + 3 * i + 1) * t1 + p.c(C_JINV + 3 * i + 2) * t2 + d.ta[i];
+    }
+#pragma unroll
+    for(int r = 0; r < 4; r++){
+        const float rpm = x[X_RPM + r];
+        const float inv_tau = setpoint[r] >= rpm ? p.c(C_ITAU_RISE + r) : p.c(C_ITAU_FALL + r);
+        dx[X_RPM + r] = (setpoint[r] - rpm) * inv_tau;
+    }
+}
+// env_step twin for the compiled block (no observation/action noise in this variant; Langevin target as in env_step)
+template <class Spec>
+__device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const ParamsCompiled& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
+                                                  float* __restrict__ hist_ptr, size_t n){
+    float setpoint[4];
+    const float amin = p.c(C_ACT_MIN), amax = p.c(C_ACT_MAX);
+#pragma unroll
+    for(int i = 0; i < 4; i++) setpoint[i] = clampf(action[i], -1.0f, 1.0f) * d.half_range + amin + d.half_range;
+    const float dt = d.dt;
+    const float dt2 = dt / 2.0f, dt3 = dt / 3.0f, dt6 = dt / 6.0f;
+    float k[X_DIM], tmp[X_DIM], acc[X_DIM];
+    dynamics_compiled(p, d, st.x, setpoint, k);
+#pragma unroll
+    for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i] + dt6 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
+    dynamics_compiled(p, d, tmp, setpoint, k);
+#pragma unroll
+    for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
+    dynamics_compiled(p, d, tmp, setpoint, k);
+#pragma unroll
+    for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt * k[i]; }
+    dynamics_compiled(p, d, tmp, setpoint, k);
+#pragma unroll
+    for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i] + dt6 * k[i];
+    {
+        float nrm = 0.0f;
+#pragma unroll
+        for(int i = 0; i < 4; i++) nrm += st.x[X_ORI + i] * st.x[X_ORI + i];
+        nrm = sqrtf(nrm);
+#pragma unroll
+        for(int i = 0; i < 4; i++) st.x[X_ORI + i] = st.x[X_ORI + i] / nrm;
+#pragma unroll
+        for(int i = 0; i < 3; i++){
+            st.x[X_POS + i] = clampf(st.x[X_POS + i], -100000.0f, 100000.0f);
+            st.x[X_VEL + i] = clampf(st.x[X_VEL + i], -100000.0f, 100000.0f);
+            st.x[X_OMEGA + i] = clampf(st.x[X_OMEGA + i], -100000.0f, 100000.0f);
+        }
+    }
+#pragma unroll
+    for(int i = 0; i < 4; i++) st.last_action[i] = action[i];
+#pragma unroll
+    for(int i = 0; i < 4; i++) st.x[X_RPM + i] = clampf(st.x[X_RPM + i], amin, amax);
+    if constexpr(Spec::H == 1){
+#pragma unroll
+        for(int i = 0; i < 4; i++) st.hist[i] = action[i];
+    }
+    else{
+        const int cs = st.current_step;
+#pragma unroll
+        for(int i = 0; i < 4; i++) hist_ptr[(size_t)(4 * cs + i) * n] = action[i];
+        st.current_step = (cs + 1) % Spec::H;
+    }
+    if constexpr(Spec::LANGEVIN){
+        if(st.traj_type == 1){
+            const float gamma = p[P_LANGEVIN_GAMMA], omega = p[P_LANGEVIN_OMEGA], sigma = p[P_LANGEVIN_SIGMA], alpha = p[P_LANGEVIN_ALPHA];
+            const float sqrt_dt = sqrtf(dt);
+#pragma unroll
+            for(int dim = 0; dim < 3; dim++){
+                const float x_prev = st.lang[6 + dim], v_prev = st.lang[9 + dim];
+                const float dW = sqrt_dt * rng_normal(rng, 0.0f, 1.0f);
+                const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
+                const float x_next = x_prev + v_next * dt;
+                st.lang[6 + dim] = x_next; st.lang[9 + dim] = v_next;
+                const float v_smooth = alpha * v_next + (1.0f - alpha) * st.lang[3 + dim];
+                st.lang[dim] = st.lang[dim] + v_smooth * dt;
+                st.lang[3 + dim] = v_smooth;
+            }
+        }
+    }
+}
+
+// ---- shared-memory plan (bytes) ---------------------------------------------------------------------------------------
+struct TcSmem {
+    static constexpr int CHUNK = BLOCK * 16;                  // one K chunk (4 tf32 columns) of all 128 rows: 2 KB
+    static constexpr int A_CHUNKS_HI = 12, A_CHUNKS_LO = 10;  // chunk pairs: (0,1)(2,3)(4,5) obs | x1 ; (6,7)(8,9) h ; (10,11) constants (hi plane only)
+    static constexpr int A_HI = 0;
+    static constexpr int A_LO = A_HI + A_CHUNKS_HI * CHUNK;
+    static constexpr int B = A_LO + A_CHUNKS_LO * CHUNK;     // weight image (TMA destination, 16-byte aligned)
+    static constexpr int DYN = B + TcImage::BYTES;
+    static constexpr int BAR = DYN + C_DIM * BLOCK * 4;       // two mbarriers + TMEM base address
+    static constexpr int TOTAL = BAR + 32;
+};
+static_assert(BLOCK == 128, "the tensor-core rollout maps one CTA to one M = 128 MMA tile");
+
+template <class Spec, bool FAST>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
+    constexpr int HD = 16;
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    float* a_hi = reinterpret_cast<float*>(smraw + TcSmem::A_HI);
+    float* a_lo = reinterpret_cast<float*>(smraw + TcSmem::A_LO);
+    float* sm_b = reinterpret_cast<float*>(smraw + TcSmem::B);
+    float* sm_dyn = reinterpret_cast<float*>(smraw + TcSmem::DYN);
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + TcSmem::BAR);
+    uint64_t* bar_mma = bar_tma + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if(tid == 0){
+        tc::mbar_init(bar_tma, 1);
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_fence_init();
+    }
+    if(warp == 0) tc::tmem_alloc<128>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if(tid == 0){
+        tc::mbar_expect_tx(bar_tma, TcImage::BYTES);
+        tc::tma_load_1d(sm_b, tc_image, TcImage::BYTES, bar_tma);
+    }
+    const int e = blockIdx.x * BLOCK + tid;
+    const bool active = e < a.n;
+    const size_t n = (size_t)a.n;
+    const size_t env = active ? (size_t)e : 0;
+    ParamsCompiled p = stage_dynamics_compiled(sm_dyn, a.params, n, env);
+    EnvState<Spec> st;
+    load_state(st, a.state + env, n);
+    DynInvariants d;
+    {
+        ParamsGlobal pg{a.params + env, n};
+        dyn_invariants(d, pg, st);
+    }
+    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
+    uint64_t rng = a.rng[env];
+    float h[HD];
+#pragma unroll
+    for(int j = 0; j < HD; j++) h[j] = a.hidden[(size_t)j * n + env];
+    int gs = a.gru_step[env];
+    float ret = 0.0f; int eplen = 0; bool done = false;
+    const bool no_auto_reset = a.no_auto_reset != 0;
+    // this thread's row inside a K chunk: 16 bytes at chunk * 2048 + tid * 16  (8-row core matrices are 128 contiguous bytes: SBO = 128)
+    float4* row_hi = reinterpret_cast<float4*>(a_hi) + tid;
+    float4* row_lo = reinterpret_cast<float4*>(a_lo) + tid;
+    constexpr int CH = BLOCK;   // float4 stride between chunks
+    auto put4 = [&](int chunk, float v0, float v1, float v2, float v3){
+        float h0, h1, h2, h3, l0, l1, l2, l3;
+        tc::split_tf32(v0, h0, l0); tc::split_tf32(v1, h1, l1); tc::split_tf32(v2, h2, l2); tc::split_tf32(v3, h3, l3);
+        row_hi[chunk * CH] = make_float4(h0, h1, h2, h3);
+        row_lo[chunk * CH] = make_float4(l0, l1, l2, l3);
+    };
+    row_hi[10 * CH] = make_float4(1.0f, 1.0f, 0.0f, 0.0f);   // constant columns: two ones (b_hh / b_ih; G3 uses the first for b2), then zeros
+    row_hi[11 * CH] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    put4(6, h[0], h[1], h[2], h[3]); put4(7, h[4], h[5], h[6], h[7]); put4(8, h[8], h[9], h[10], h[11]); put4(9, h[12], h[13], h[14], h[15]);
+
+    // descriptors (issuing thread only uses them)
+    const uint32_t a_hi_s = tc::smem_u32(a_hi), a_lo_s = tc::smem_u32(a_lo), b_s = tc::smem_u32(sm_b);
+    constexpr uint32_t A_LBO = TcSmem::CHUNK, SBO = 128;
+    constexpr uint32_t IDESC16 = tc::make_idesc_tf32(128, 16), IDESC64 = tc::make_idesc_tf32(128, 64);
+    const uint32_t d1 = tmem_base + 0, d2 = tmem_base + 16, d3 = tmem_base + 80;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    uint32_t phase = 0;
+    // one GEMM = `pairs` K=8 steps over the chunk pairs first_pair.. of A against consecutive chunk pairs of B (3 products per step)
+    auto issue_gemm = [&](uint32_t dcol, int a_first_chunk_0, int n_pairs_0, int a_first_chunk_1, int n_pairs_1, int b_hi_off, int b_lo_off, uint32_t N, uint32_t idesc){
+        uint32_t acc = 0;
+        int bpair = 0;
+        for(int seg = 0; seg < 2; seg++){
+            const int first = seg == 0 ? a_first_chunk_0 : a_first_chunk_1;
+            const int cnt = seg == 0 ? n_pairs_0 : n_pairs_1;
+            for(int i = 0; i < cnt; i++, bpair++){
+                const int chunk = first + 2 * i;
+                const uint64_t ahi = tc::make_smem_desc(a_hi_s + chunk * TcSmem::CHUNK, A_LBO, SBO);
+                const uint64_t bhi = tc::make_smem_desc(b_s + b_hi_off * 4 + bpair * 2 * N * 16, N * 16, SBO);
+                const uint64_t blo = tc::make_smem_desc(b_s + b_lo_off * 4 + bpair * 2 * N * 16, N * 16, SBO);
+                tc::mma_tf32(dcol, ahi, bhi, idesc, acc); acc = 1;
+                tc::mma_tf32(dcol, ahi, blo, idesc, 1);
+                if(chunk < TcSmem::A_CHUNKS_LO){   // the constant chunks have no lo plane (their lo part is exactly zero)
+                    const uint64_t alo = tc::make_smem_desc(a_lo_s + chunk * TcSmem::CHUNK, A_LBO, SBO);
+                    tc::mma_tf32(dcol, alo, bhi, idesc, 1);
+                }
+            }
+        }
+        tc::mma_commit(bar_mma);
+    };
+    tc::mbar_wait(bar_tma, 0);   // weight image landed (async proxy write -> visible to the tensor core, no generic-proxy reads needed except h0)
+    __syncthreads();
+
+    for(int t = 0; t < a.T; t++){
+        if(a.out_states && active && (t % a.state_stride) == 0)
+            write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
+        float obs[22];
+        observe18<Spec, false>(st, p, rng, obs);
+        if constexpr(Spec::H == 1){
+#pragma unroll
+            for(int i = 0; i < 4; i++) obs[18 + i] = st.hist[i];
+        }
+        else{
+            const int cur = st.current_step == 0 ? Spec::H - 1 : st.current_step - 1;
+#pragma unroll
+            for(int i = 0; i < 4; i++) obs[18 + i] = hist_ptr[(size_t)(4 * cur + i) * n];
+        }
+        if(a.out_obs && active){
+            float* row = a.out_obs + ((size_t)t * n + env) * 22;
+#pragma unroll
+            for(int i = 0; i < 22; i++) row[i] = obs[i];
+        }
+        // ---- G1: dense 1
+        put4(0, obs[0], obs[1], obs[2], obs[3]); put4(1, obs[4], obs[5], obs[6], obs[7]); put4(2, obs[8], obs[9], obs[10], obs[11]);
+        put4(3, obs[12], obs[13], obs[14], obs[15]); put4(4, obs[16], obs[17], obs[18], obs[19]); put4(5, obs[20], obs[21], 1.0f, 0.0f);
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        if(tid == 0){
+            tc::tc_fence_after();
+            issue_gemm(d1, 0, 3, 0, 0, TcImage::B1_HI, TcImage::B1_LO, 16, IDESC16);
+        }
+        tc::mbar_wait(bar_mma, phase); phase ^= 1;
+        tc::tc_fence_after();
+        float x1[HD];
+        tc::tmem_ld16(d1 + lane_off, x1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for(int j = 0; j < HD; j++) x1[j] = fmaxf(x1[j], 0.0f);
+        // reset_truncate (gru/operations_generic.h:76-86): the hidden rows of A are rewritten when the counter wrapped
+        if(!no_auto_reset && gs >= a.seq_len){
+#pragma unroll
+            for(int j = 0; j < HD; j++) h[j] = sm_b[TcImage::H0 + j];
+            put4(6, h[0], h[1], h[2], h[3]); put4(7, h[4], h[5], h[6], h[7]); put4(8, h[8], h[9], h[10], h[11]); put4(9, h[12], h[13], h[14], h[15]);
+            gs = 0;
+        }
+        // ---- G2: GRU pre-activations
+        put4(0, x1[0], x1[1], x1[2], x1[3]); put4(1, x1[4], x1[5], x1[6], x1[7]); put4(2, x1[8], x1[9], x1[10], x1[11]); put4(3, x1[12], x1[13], x1[14], x1[15]);
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        if(tid == 0){
+            tc::tc_fence_after();
+            issue_gemm(d2, 0, 2, 6, 3, TcImage::B2_HI, TcImage::B2_LO, 64, IDESC64);
+        }
+        tc::mbar_wait(bar_mma, phase); phase ^= 1;
+        tc::tc_fence_after();
+        float hn[HD];
+        {
+            float r[HD], nx[HD], nh[HD];
+            tc::tmem_ld16(d2 + lane_off + 0, r);
+            tc::tmem_ld16(d2 + lane_off + 32, nx);
+            tc::tmem_ld16(d2 + lane_off + 48, nh);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for(int j = 0; j < HD; j++) nx[j] = tanhf_<FAST>(nx[j] + nh[j] * sigmoidf_<FAST>(r[j]));
+            float z[HD];
+            tc::tmem_ld16(d2 + lane_off + 16, z);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for(int j = 0; j < HD; j++){ const float zz = sigmoidf_<FAST>(z[j]); hn[j] = (1.0f - zz) * nx[j] + zz * h[j]; }
+        }
+        // ---- G3: dense 2 (reads the same hidden rows the next step's G2 will read)
+        put4(6, hn[0], hn[1], hn[2], hn[3]); put4(7, hn[4], hn[5], hn[6], hn[7]); put4(8, hn[8], hn[9], hn[10], hn[11]); put4(9, hn[12], hn[13], hn[14], hn[15]);
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        if(tid == 0){
+            tc::tc_fence_after();
+            issue_gemm(d3, 6, 3, 0, 0, TcImage::B3_HI, TcImage::B3_LO, 16, IDESC16);
+        }
+        tc::mbar_wait(bar_mma, phase); phase ^= 1;
+        tc::tc_fence_after();
+        float act[4];
+        tc::tmem_ld4(d3 + lane_off, act);
+        tc::tmem_ld_wait();
+        {   // gru/operations_generic.h:400-410: this step's output is kept, the stored state resets when the counter wraps
+            const int new_step = gs + 1;
+            const bool wrap = !no_auto_reset && new_step >= a.seq_len;
+#pragma unroll
+            for(int j = 0; j < HD; j++) h[j] = wrap ? sm_b[TcImage::H0 + j] : hn[j];
+            gs = wrap ? 0 : new_step;
+            if(wrap){   // rare: the A rows must hold the reset state (G3 of this step has completed)
+                put4(6, h[0], h[1], h[2], h[3]); put4(7, h[4], h[5], h[6], h[7]); put4(8, h[8], h[9], h[10], h[11]); put4(9, h[12], h[13], h[14], h[15]);
+            }
+        }
+        if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
+        RewardInputs ri;
+        reward_inputs(ri, st);
+        if(Spec::H == 1 || active) env_step_compiled<Spec>(st, p, d, act, rng, hist_ptr, n);
+        const bool term = env_terminated(p, st.x);
+        const float rw = env_reward(p, ri, act, st.x, term, d.dt);
+        if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
+        if(a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
+        if(!done){ ret += rw; eplen += 1; done = term; }
+    }
+    if(active){
+        if(a.out_states && (a.T % a.state_stride) == 0)
+            write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(a.T / a.state_stride) * n + env) * Spec::STATE_DIM);
+        store_state(st, a.state + env, n);
+        a.rng[env] = rng;
+#pragma unroll
+        for(int j = 0; j < HD; j++) a.hidden[(size_t)j * n + env] = h[j];
+        a.gru_step[env] = gs;
+        if(a.out_returns) a.out_returns[env] = ret;
+        if(a.out_eplen) a.out_eplen[env] = eplen;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if(warp == 0) tc::tmem_dealloc<128>(tmem_base);
+}
+
+}  // namespace b200l2f

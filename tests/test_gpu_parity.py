@@ -28,6 +28,22 @@ def close(a, b, rtol, atol, what=""):
     np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=what)
 
 
+# field groups of a state row that share a physical unit: |error| is judged relative to the group's magnitude along the trajectory
+STATE_GROUPS = {"position": (slice(0, 3), 0.1), "orientation": (slice(3, 7), 1.0), "linear_velocity": (slice(7, 10), 0.1),
+                "angular_velocity": (slice(10, 13), 0.1), "last_action": (slice(13, 17), 0.1), "rpm": (slice(26, 30), 0.1)}
+
+
+def close_relative(got, want, rtol, groups, what=""):
+    """got/want: [T, n, D].  For every env and field group g: max_t |got - want| <= rtol * max(max_t |want_g|, floor_g),
+    i.e. "within rtol relative fp32" with the magnitude of the physical quantity as the reference scale."""
+    for name, (sl, floor) in groups.items():
+        g, w = got[..., sl], want[..., sl]
+        scale = np.maximum(np.abs(w).max(axis=(0, 2)), floor)            # [n]
+        err = np.abs(g - w).max(axis=(0, 2))                             # [n]
+        bad = err > rtol * scale
+        assert not bad.any(), "%s/%s: %d envs exceed rtol %g (worst err/scale = %.3g)" % (what, name, bad.sum(), rtol, (err / scale).max())
+
+
 def test_rng_streams_bit_exact(rb, port):
     env = rb.VectorEnvironment(1000, rb.SPEC_RAPTOR, first_env_id=12345)
     env.initialize_rng(seed=99, warmup=7)
@@ -139,18 +155,18 @@ def test_fused_rollout_vs_golden(rb, name, T_cmp, flags):
     env.load_policy(np.load(os.path.join(G, "raptor_kat.npz"))["blob"])
     out = env.rollout(T, record=("states", "actions", "rewards", "terminated"))
     noise = "noise" in name
-    rtol, atol = (1e-4, 2e-5) if not noise else (1e-3, 2e-4)
+    rtol = 1e-4 if not noise else 1e-3      # with noise on, ulp differences of logf/cosf in Box-Muller enter the loop as 1e-7-level input noise
     steps = g["state_steps"]
     sel = steps <= T_cmp
-    close(out["states"][steps[sel]], g["states"][sel], rtol, atol, "states")
-    close(out["actions"][:T_cmp], g["actions"][:T_cmp], rtol, atol * 5, "actions")
+    close_relative(out["states"][steps[sel]], g["states"][sel], rtol, STATE_GROUPS, "states")
+    close_relative(out["actions"][:T_cmp], g["actions"][:T_cmp], rtol, {"action": (slice(0, 4), 0.1)}, "actions")
     close(out["rewards"][:T_cmp], g["rewards"][:T_cmp], 1e-3, 1e-3, "rewards")
     assert np.array_equal(out["terminated"], g["terminated"])
     assert np.array_equal(env.get_rng(), g["final_rng"])
     h, gs = env.get_hidden()
     assert np.array_equal(gs, g["final_gru_step"])
     # the whole horizon stays bounded-close as well (closed loop is stable under the policy)
-    close(out["states"][steps], g["states"], 50 * rtol, 50 * atol, "states, full horizon")
+    close_relative(out["states"][steps], g["states"], 50 * rtol, STATE_GROUPS, "states, full horizon")
     close(env.get_state(), out["states"][-1], 0, 0, "final state row == slot 0")
 
 
@@ -174,9 +190,10 @@ def test_fused_rollout_equals_stepwise_api(rb, port, spec):
         rews.append(b_env.reward(a))
         b_env.copy_state(0, 1)
         acts.append(a.copy())
-    close(out["actions"], np.array(acts), 1e-5, 1e-6, "actions")
-    close(out["rewards"], np.array(rews), 1e-4, 1e-4, "rewards")
-    close(a_env.get_state(), b_env.get_state(), 1e-5, 1e-6, "final states")
+    # same device functions, different kernels: the compiler may contract different multiply-adds into FMAs, so compare at 1e-4 relative
+    close_relative(out["actions"], np.array(acts), 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
+    close(out["rewards"], np.array(rews), 1e-3, 1e-3, "rewards")
+    close_relative(a_env.get_state()[None], b_env.get_state()[None], 1e-4, STATE_GROUPS, "final states")
     assert np.array_equal(a_env.get_rng(), b_env.get_rng())
     # evaluate()-style statistics: return accumulated until (and including) the first terminated step
     term = out["terminated"].astype(bool)
@@ -234,3 +251,44 @@ def test_ragged_sizes_and_errors(rb):
         bad = e.get_environment_parameters(); bad[126] = 1.0; e.set_environment_parameters(bad); e.sample_initial_parameters()  # DR range without DR spec
     with pytest.raises(rb.EngineError):
         rb.VectorEnvironment(0)
+
+
+@pytest.mark.parametrize("name,T_cmp", [("default_8x500.npz", 100), ("raptor_dr_64x100.npz", 100)])
+def test_tcgen05_rollout_vs_golden(rb, name, T_cmp):
+    """actor GEMMs on the tensor cores (tcgen05, 3xTF32): same 1e-4 closed-loop bound against the reference fixtures"""
+    g = np.load(os.path.join(G, name))
+    spec = int(g["spec"])
+    n, T = g["states0"].shape[0], g["actions"].shape[0]
+    env = rb.VectorEnvironment(n, spec)
+    env.set_parameters(np.ascontiguousarray(g["params"]))
+    env.set_state(np.ascontiguousarray(g["states0"]))
+    env.set_rng(np.ascontiguousarray(g["rng0"]))
+    env.load_policy(np.load(os.path.join(G, "raptor_kat.npz"))["blob"], gemm=rb.GEMM_TCGEN05_3XTF32)
+    out = env.rollout(T, record=("states", "actions", "rewards", "terminated"))
+    steps = g["state_steps"]
+    sel = steps <= T_cmp
+    close_relative(out["states"][steps[sel]], g["states"][sel], 1e-4, STATE_GROUPS, "states")
+    close_relative(out["actions"][:T_cmp], g["actions"][:T_cmp], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
+    assert np.array_equal(out["terminated"], g["terminated"])
+    assert np.array_equal(env.get_rng(), g["final_rng"])
+    assert np.array_equal(env.get_hidden()[1], g["final_gru_step"])
+
+
+def test_tcgen05_rollout_matches_fp32_rollout(rb):
+    """same inputs through both GEMM back ends, 3000 envs (ragged last CTA), 600 steps (crosses the GRU auto-reset at 500)"""
+    n, T = 3000, 600
+    outs = []
+    for gemm in (rb.GEMM_FP32_CUDA_CORES, rb.GEMM_TCGEN05_3XTF32):
+        e = rb.VectorEnvironment(n, rb.SPEC_RAPTOR)
+        e.initialize_rng(77, warmup=16)
+        e.sample_initial_state()
+        e.load_policy(gemm=gemm)
+        o = e.rollout(T, record=("actions", "returns", "episode_length"), )
+        outs.append((o, e.get_state(), e.get_hidden(), e.get_rng()))
+    (oa, sa, (ha, ga), ra), (ob, sb, (hb, gb), rb_) = outs
+    assert np.array_equal(ra, rb_) and np.array_equal(ga, gb)
+    stable = (oa["episode_length"] == T) & (ob["episode_length"] == T)
+    assert stable.mean() > 0.8
+    close_relative(ob["actions"][:100, stable], oa["actions"][:100, stable], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions, first 100 steps")
+    close_relative(sb[None, stable], sa[None, stable], 5e-3, STATE_GROUPS, "final states after 600 steps")
+    assert (oa["episode_length"] == ob["episode_length"]).mean() > 0.995

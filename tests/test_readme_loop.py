@@ -1,0 +1,60 @@
+"""The README loop (R/README.md:40-105, without UI/websocket) run verbatim against the README-compatible modules, compared with the
+golden trajectory of BASELINE config 1 (default l2f spec, 8 envs x 500 steps, seed 0, Raptor checkpoint) generated from the reference."""
+import os
+from copy import copy
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_readme_loop_matches_reference_config1():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import raptor_b200.l2f as l2f
+    from raptor_b200.l2f import vector8 as vector
+    from raptor_b200.foundation_policy import Raptor
+    g = np.load(os.path.join(G, "default_8x500.npz"))
+
+    policy = Raptor()
+    device = l2f.Device()
+    rng = vector.VectorRng()
+    env = vector.VectorEnvironment()
+    ui = l2f.UI()
+    params = vector.VectorParameters()
+    state = vector.VectorState()
+    observation = np.zeros((env.N_ENVIRONMENTS, env.OBSERVATION_DIM), dtype=np.float32)
+    next_state = vector.VectorState()
+    vector.initialize_rng(device, rng, 0)
+    vector.initialize_environment(device, env)
+    vector.sample_initial_parameters(device, env, params, rng)
+    vector.sample_initial_state(device, env, params, state, rng)
+    np.testing.assert_allclose(state.numpy(), g["states0"], rtol=2e-6, atol=1e-7)
+
+    ui_state = copy(state)
+    for i, s in enumerate(ui_state.states):
+        s.position[0] += i * 0.1
+    assert '"channel": "setStateAction"' in vector.set_state_action_message(device, env, params, ui, ui_state, np.zeros((8, 4)))
+    assert '"channel": "setParameters"' in vector.set_parameters_message(device, env, params, ui)
+
+    policy.reset()
+    actions = []
+    for _ in range(100):
+        vector.observe(device, env, params, state, observation, rng)
+        action = policy.evaluate_step(observation[:, :22])
+        dts = vector.step(device, env, params, state, action, next_state, rng)
+        state.assign(next_state)
+        actions.append(action.copy())
+        assert abs(dts[-1] - 0.01) < 1e-9
+    actions = np.array(actions)
+    scale = np.maximum(np.abs(g["actions"][:100]).max(axis=(0, 2)), 0.1)
+    assert (np.abs(actions - g["actions"][:100]).max(axis=(0, 2)) <= 1e-4 * scale).all()
+    got = state.numpy()
+    want = g["states"][list(g["state_steps"]).index(100)]
+    for sl, floor in [(slice(0, 3), 0.1), (slice(3, 7), 1.0), (slice(7, 10), 0.1), (slice(10, 13), 0.1), (slice(26, 30), 0.1)]:
+        sc = np.maximum(np.abs(want[:, sl]).max(axis=1), floor)
+        assert (np.abs(got[:, sl] - want[:, sl]).max(axis=1) <= 1e-4 * sc).all()
+    assert np.array_equal(got[:, 30], want[:, 30])   # ring-buffer index
