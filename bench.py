@@ -172,9 +172,10 @@ def main():
     ap.add_argument("--rollout-steps", type=int, default=1000)
     ap.add_argument("--cpu-envs-per-thread", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tcgen05", action="store_true", help="policy GEMMs on tcgen05 (3xTF32) instead of fp32 CUDA cores")
+    ap.add_argument("--fp32-gemm", action="store_true", help="actor GEMMs on the fp32 CUDA cores instead of tcgen05 (3xTF32)")
     ap.add_argument("--accurate-math", action="store_true")
     args = ap.parse_args()
+    args.tcgen05 = not args.fp32_gemm
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local, world = dist_env()
     if args.impl == "reference":
@@ -286,7 +287,7 @@ def main():
         fp32_ach = steps_per_s_gpu * (FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES) / 1e12
         roofline = {"bound": "tensor", "achieved": tensor_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tensor_ach / peaks["bf16_tflops_sustained"], "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long launch)",
-                    "kernel": "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,
+                    "kernel": "k_rollout_raptor_tc" if args.tcgen05 else "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,
                     "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": n * BYTES_PER_ENV_LAUNCH},
                     "fp32_issue": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
                                    "note": "dominant ceiling of this kernel (SURVEY 8d): algorithmic fp32 FLOPs / (148 SMs x 128 lanes x 2 x max SM clock); state, parameters and weights are on-chip for the whole launch"}}

@@ -36,6 +36,7 @@ struct b200l2f_handle {
     uint64_t* d_rng = nullptr;
     int* d_flags = nullptr;          // [0] error flag, [1] parameter features
     bool features_dirty = true; int features = 0;
+    float row0[B200L2F_PARAMS_DIM];   // parameter row of environment 0 (uniform MDP constants of the fused kernels)
     // actor
     bool policy_loaded = false; b200l2f_policy_desc pol{};
     float* d_blob = nullptr; size_t blob_floats = 0;
@@ -171,6 +172,7 @@ int refresh_features(b200l2f_handle* h){
     k_param_features<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->n, h->d_flags + 1);
     LAUNCH_CHECK();
     CU(cudaMemcpyAsync(&h->features, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpy2DAsync(h->row0, sizeof(float), h->d_params, sizeof(float) * (size_t)h->n, sizeof(float), B200L2F_PARAMS_DIM, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->features_dirty = false;
     return B200L2F_OK;
@@ -198,9 +200,9 @@ int launch_rollout_raptor(b200l2f_handle* h, const RolloutArgs& a){
     return B200L2F_OK;
 }
 
-template <class Spec, bool FAST>
+template <class Spec, bool FAST, bool UNIFORM, bool G1_TC>
 int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
-    auto kern = k_rollout_raptor_tc<Spec, FAST>;
+    auto kern = k_rollout_raptor_tc<Spec, FAST, UNIFORM, G1_TC>;
     static bool configured[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -622,6 +624,7 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     RolloutArgs a{};
     a.params = h->d_params; a.state = h->d_state[0]; a.rng = h->d_rng; a.hidden = h->d_hidden; a.gru_step = h->d_gru_step; a.blob = h->d_blob;
     a.n = h->n; a.T = n_steps; a.no_auto_reset = no_auto_reset; a.seq_len = h->pol.gru_sequence_length; a.state_stride = 1;
+    std::memcpy(a.row0, h->row0, sizeof(a.row0));
     // outputs: device pointers are used directly, host pointers get a slice of the staging buffer
     const size_t n = (size_t)h->n, T = (size_t)n_steps;
     struct Slice { void** kernel_ptr; void* user; size_t bytes; size_t offset; };
@@ -656,7 +659,13 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     if(tensor_cores && noise) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the tcgen05 variant is built for noise-free observation/action parameters");
     auto go = [&](auto spec) -> int {
         using Spec = decltype(spec);
-        if(tensor_cores) return fast ? launch_rollout_tc<Spec, true>(h, a) : launch_rollout_tc<Spec, false>(h, a);
+        if(tensor_cores){
+            const bool uniform = (h->features & 2) == 0;
+            static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
+            if(!fast) return launch_rollout_tc<Spec, false, false, true>(h, a);
+            if(!uniform) return launch_rollout_tc<Spec, true, false, true>(h, a);
+            return g1_tc ? launch_rollout_tc<Spec, true, true, true>(h, a) : launch_rollout_tc<Spec, true, true, false>(h, a);
+        }
         if(noise) return fast ? launch_rollout_raptor<Spec, true, true, true>(h, a) : launch_rollout_raptor<Spec, true, false, true>(h, a);
         if(!fast) return launch_rollout_raptor<Spec, false, false, true>(h, a);
         if(constw) return launch_rollout_raptor<Spec, false, true, true>(h, a);

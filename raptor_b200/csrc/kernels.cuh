@@ -74,12 +74,20 @@ __global__ void k_sample_params(float* __restrict__ params, const float* __restr
     if(!sample_parameters<DR>(env_row, p, s)) atomicExch(error_flag, 1);
     rng[e] = s;
 }
-// features of the parameter set that select kernel variants: bit0 = some observation/action noise std != 0
+// MDP parameters that are normally identical for every environment (reward weights, termination switches, Langevin constants): when they
+// are, the fused kernels read them from the launch's constant bank instead of per-environment loads inside the time loop.
+__host__ __device__ constexpr bool mdp_uniform_index(int i){
+    return (i >= P_RW_NONNEG && i <= P_RW_POS_INTEGRAL) || i == P_HOVER || i == P_TERM_ENABLED || i == P_TERM_LINVEL || i == P_TERM_ANGVEL ||
+           (i >= P_LANGEVIN_GAMMA && i <= P_LANGEVIN_ALPHA);
+}
+// features of the parameter set that select kernel variants: bit0 = some observation/action noise std != 0,
+// bit1 = some environment's "uniform" MDP parameter differs from environment 0's
 __global__ void k_param_features(const float* __restrict__ params, int n, int* __restrict__ features){
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     int f = 0;
     if(e < n){
         for(int i = P_NOISE_POS; i <= P_ACTION_NOISE; i++) if(params[(size_t)i * n + e] != 0.0f) f |= 1;
+        for(int i = 0; i < PARAMS_DIM; i++) if(mdp_uniform_index(i) && params[(size_t)i * n + e] != params[(size_t)i * n]) f |= 2;
     }
     f = __reduce_or_sync(0xffffffffu, f);
     if((threadIdx.x & 31) == 0 && f) atomicOr(features, f);
@@ -228,6 +236,7 @@ struct RolloutArgs {
     uint8_t* out_term;     // [T][n]
     float* out_returns;    // [n]
     int* out_eplen;        // [n]
+    float row0[PARAMS_DIM];  // parameter row of environment 0 (source of the uniform MDP constants)
 };
 
 template <class Spec>

@@ -34,9 +34,11 @@ __device__ __forceinline__ float rng_normal(uint64_t& s, float mean, float std){
     if(std == 0.0f){ return mean; }
     float u1 = rng_unit(s);
     float u2 = rng_unit(s);
-    // the reference's literals are double: sqrt(-2.0 * log(u1)) and 2.0 * PI<float> * u2 are evaluated in double
-    float x = (float)sqrt(-2.0 * (double)logf(u1));
-    float y = (float)(2.0 * (double)3.14159274101257324f * (double)u2);
+    // the reference evaluates sqrt(-2.0 * log(u1)) and 2.0 * PI<float> * u2 in double (double literals) and rounds to float; -2 * logf(u1) and
+    // 2 * PI<float> are exact in float, so the float evaluation below differs from that only by double rounding (< 1 ulp, rare) and keeps
+    // fp64 instructions out of the hot loop
+    float x = sqrtf(-2.0f * logf(u1));
+    float y = __fmul_rn(6.28318548202514648f, u2);
     float z = __fmul_rn(x, cosf(y));
     return __fadd_rn(__fmul_rn(z, std), mean);
 }

@@ -25,7 +25,9 @@ struct TcImage {
     static constexpr int B2_HI = B1_LO + K1 * N1, B2_LO = B2_HI + K2 * N2;
     static constexpr int B3_HI = B2_LO + K2 * N2, B3_LO = B3_HI + K3 * N3;
     static constexpr int H0 = B3_LO + K3 * N3;   // initial hidden state (16 floats) for the auto-reset
-    static constexpr int SIZE = H0 + 16;         // floats
+    static constexpr int W2T = H0 + 16;          // fp32 dense-2 weights, k-major [16][4], then b2[4]
+    static constexpr int W1T = W2T + 68;         // fp32 dense-1 weights, k-major [22][16], then b1[16]
+    static constexpr int SIZE = W1T + 22 * 16 + 16;   // floats
     static constexpr int BYTES = SIZE * 4;
     static_assert(BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 };
@@ -64,16 +66,28 @@ inline void build_tc_image_host(float* img, const float* blob){
         put(TcImage::B3_HI, TcImage::B3_LO, 16, n, 16, b2[n]);
     }
     for(int j = 0; j < HD; j++) img[TcImage::H0 + j] = h0[j];
+    for(int k = 0; k < HD; k++) for(int n = 0; n < OUT; n++) img[TcImage::W2T + 4 * k + n] = W2[n * HD + k];
+    for(int n = 0; n < OUT; n++) img[TcImage::W2T + 64 + n] = b2[n];
+    for(int k = 0; k < IN; k++) for(int n = 0; n < HD; n++) img[TcImage::W1T + k * HD + n] = W1[n * IN + k];
+    for(int n = 0; n < HD; n++) img[TcImage::W1T + IN * HD + n] = b1[n];
 }
 
 // ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
-enum DynC : int { C_COEF = 0, C_AF = 12, C_AT = 24, C_ITAU_RISE = 36, C_ITAU_FALL = 40, C_GRAVITY = 44, C_J = 47, C_JINV = 56, C_ACT_MIN = 65, C_ACT_MAX = 66, C_DIM = 67 };
-struct ParamsCompiled {
+enum DynC : int { C_COEF = 0, C_AF = 12, C_AT = 24, C_ITAU_RISE = 36, C_ITAU_FALL = 40, C_GRAVITY = 44, C_J = 47, C_JINV = 56, C_ACT_MIN = 65, C_ACT_MAX = 66, C_TERM_POS = 67, C_DIM = 68 };
+template <bool UNIFORM>
+struct ParamsCompiledT {
     const float* sm; const float* __restrict__ base; size_t stride;   // sm: staged block (this thread's column); base/stride: full parameter column in HBM
+    const float* row0;                                                // UNIFORM: environment 0's row in the launch's constant bank
     __device__ __forceinline__ float c(int i) const { return sm[i * BLOCK]; }
-    __device__ __forceinline__ float operator[](int i) const { return __ldg(base + (size_t)i * stride); }   // everything outside the dynamics block
+    __device__ __forceinline__ float operator[](int i) const {       // everything outside the dynamics block
+        if(i == P_TERM_POS) return sm[C_TERM_POS * BLOCK];            // per environment even under DR (10_sample_initial_parameters.h:154)
+        if(UNIFORM && mdp_uniform_index(i)) return row0[i];
+        return __ldg(base + (size_t)i * stride);
+    }
 };
-__device__ __forceinline__ ParamsCompiled stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* __restrict__ params, size_t n, size_t env){
+using ParamsCompiled = ParamsCompiledT<false>;
+template <bool UNIFORM>
+__device__ __forceinline__ ParamsCompiledT<UNIFORM> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* __restrict__ params, size_t n, size_t env, const float* row0){
     float* sm = sm_dyn + threadIdx.x;
     const float* g = params + env;
     auto P = [&](int i){ return __ldg(g + (size_t)i * n); };
@@ -96,12 +110,13 @@ __device__ __forceinline__ ParamsCompiled stage_dynamics_compiled(float* __restr
     for(int i = 0; i < 3; i++) sm[(C_GRAVITY + i) * BLOCK] = P(P_GRAVITY + i);
 #pragma unroll
     for(int i = 0; i < 9; i++){ sm[(C_J + i) * BLOCK] = P(P_J + i); sm[(C_JINV + i) * BLOCK] = P(P_JINV + i); }
-    sm[C_ACT_MIN * BLOCK] = P(P_ACT_MIN); sm[C_ACT_MAX * BLOCK] = P(P_ACT_MAX);
-    ParamsCompiled p; p.sm = sm; p.base = g; p.stride = n;
+    sm[C_ACT_MIN * BLOCK] = P(P_ACT_MIN); sm[C_ACT_MAX * BLOCK] = P(P_ACT_MAX); sm[C_TERM_POS * BLOCK] = P(P_TERM_POS);
+    ParamsCompiledT<UNIFORM> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
     return p;
 }
 // multirotor dynamics with the rotor matrices (same physics as dynamics() in env.cuh; thrust/torque summed as matrix-vector products)
-__device__ __forceinline__ void dynamics_compiled(const ParamsCompiled& p, const DynInvariants& d, const float* __restrict__ x, const float* __restrict__ setpoint, float* __restrict__ dx){
+template <class PC>
+__device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvariants& d, const float* __restrict__ x, const float* __restrict__ setpoint, float* __restrict__ dx){
     float tm[4];
 #pragma unroll
     for(int r = 0; r < 4; r++){
@@ -151,8 +166,8 @@ __device__ __forceinline__ void dynamics_compiled(const ParamsCompiled& p, const
     }
 }
 // env_step twin for the compiled block (no observation/action noise in this variant; Langevin target as in env_step)
-template <class Spec>
-__device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const ParamsCompiled& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
+template <class Spec, class PC>
+__device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
                                                   float* __restrict__ hist_ptr, size_t n){
     float setpoint[4];
     const float amin = p.c(C_ACT_MIN), amax = p.c(C_ACT_MAX);
@@ -233,7 +248,9 @@ struct TcSmem {
 };
 static_assert(BLOCK == 128, "the tensor-core rollout maps one CTA to one M = 128 MMA tile");
 
-template <class Spec, bool FAST>
+// G1_TC: dense 1 on the tensor cores as well (two MMA round trips per step) or on the CUDA cores (one round trip: only the GRU GEMM,
+// 1536 of the 1952 MACs, uses tcgen05).  Measured on B200 (profiles/): see DESIGN.md section 7.
+template <class Spec, bool FAST, bool UNIFORM, bool G1_TC>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     constexpr int HD = 16;
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -264,7 +281,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
     const bool active = e < a.n;
     const size_t n = (size_t)a.n;
     const size_t env = active ? (size_t)e : 0;
-    ParamsCompiled p = stage_dynamics_compiled(sm_dyn, a.params, n, env);
+    const ParamsCompiledT<UNIFORM> p = stage_dynamics_compiled<UNIFORM>(sm_dyn, a.params, n, env, a.row0);
     EnvState<Spec> st;
     load_state(st, a.state + env, n);
     DynInvariants d;
@@ -345,21 +362,37 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
 #pragma unroll
             for(int i = 0; i < 22; i++) row[i] = obs[i];
         }
-        // ---- G1: dense 1
-        put4(0, obs[0], obs[1], obs[2], obs[3]); put4(1, obs[4], obs[5], obs[6], obs[7]); put4(2, obs[8], obs[9], obs[10], obs[11]);
-        put4(3, obs[12], obs[13], obs[14], obs[15]); put4(4, obs[16], obs[17], obs[18], obs[19]); put4(5, obs[20], obs[21], 1.0f, 0.0f);
-        tc::fence_async_smem();
-        tc::tc_fence_before();
-        __syncthreads();
-        if(tid == 0){
-            tc::tc_fence_after();
-            issue_gemm(d1, 0, 3, 0, 0, TcImage::B1_HI, TcImage::B1_LO, 16, IDESC16);
-        }
-        tc::mbar_wait(bar_mma, phase); phase ^= 1;
-        tc::tc_fence_after();
         float x1[HD];
-        tc::tmem_ld16(d1 + lane_off, x1);
-        tc::tmem_ld_wait();
+        if constexpr(G1_TC){
+            // ---- G1: dense 1 on the tensor cores
+            put4(0, obs[0], obs[1], obs[2], obs[3]); put4(1, obs[4], obs[5], obs[6], obs[7]); put4(2, obs[8], obs[9], obs[10], obs[11]);
+            put4(3, obs[12], obs[13], obs[14], obs[15]); put4(4, obs[16], obs[17], obs[18], obs[19]); put4(5, obs[20], obs[21], 1.0f, 0.0f);
+            tc::fence_async_smem();
+            tc::tc_fence_before();
+            __syncthreads();
+            if(tid == 0){
+                tc::tc_fence_after();
+                issue_gemm(d1, 0, 3, 0, 0, TcImage::B1_HI, TcImage::B1_LO, 16, IDESC16);
+            }
+            tc::mbar_wait(bar_mma, phase); phase ^= 1;
+            tc::tc_fence_after();
+            tc::tmem_ld16(d1 + lane_off, x1);
+            tc::tmem_ld_wait();
+        }
+        else{
+            // ---- dense 1 (22 -> 16, 352 MACs) on the CUDA cores: one tensor-core round trip less per step
+            const float* w1 = sm_b + TcImage::W1T;
+#pragma unroll
+            for(int j = 0; j < HD; j++) x1[j] = w1[22 * HD + j];
+#pragma unroll
+            for(int k = 0; k < 22; k++){
+#pragma unroll
+                for(int j4 = 0; j4 < HD / 4; j4++){
+                    const float4 w = *reinterpret_cast<const float4*>(w1 + k * HD + 4 * j4);
+                    x1[4 * j4] += w.x * obs[k]; x1[4 * j4 + 1] += w.y * obs[k]; x1[4 * j4 + 2] += w.z * obs[k]; x1[4 * j4 + 3] += w.w * obs[k];
+                }
+            }
+        }
 #pragma unroll
         for(int j = 0; j < HD; j++) x1[j] = fmaxf(x1[j], 0.0f);
         // reset_truncate (gru/operations_generic.h:76-86): the hidden rows of A are rewritten when the counter wrapped
@@ -395,29 +428,26 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
 #pragma unroll
             for(int j = 0; j < HD; j++){ const float zz = sigmoidf_<FAST>(z[j]); hn[j] = (1.0f - zz) * nx[j] + zz * h[j]; }
         }
-        // ---- G3: dense 2 (reads the same hidden rows the next step's G2 will read)
-        put4(6, hn[0], hn[1], hn[2], hn[3]); put4(7, hn[4], hn[5], hn[6], hn[7]); put4(8, hn[8], hn[9], hn[10], hn[11]); put4(9, hn[12], hn[13], hn[14], hn[15]);
-        tc::fence_async_smem();
-        tc::tc_fence_before();
-        __syncthreads();
-        if(tid == 0){
-            tc::tc_fence_after();
-            issue_gemm(d3, 6, 3, 0, 0, TcImage::B3_HI, TcImage::B3_LO, 16, IDESC16);
-        }
-        tc::mbar_wait(bar_mma, phase); phase ^= 1;
-        tc::tc_fence_after();
+        // ---- dense 2 (16 -> 4, 64 MACs): on the CUDA cores -- a third tensor-core round trip per step costs more latency than 64 FFMAs
         float act[4];
-        tc::tmem_ld4(d3 + lane_off, act);
-        tc::tmem_ld_wait();
+        {
+            const float* w2 = sm_b + TcImage::W2T;
+            const float4 b = *reinterpret_cast<const float4*>(w2 + 64);
+            act[0] = b.x; act[1] = b.y; act[2] = b.z; act[3] = b.w;
+#pragma unroll
+            for(int k = 0; k < HD; k++){
+                const float4 w = *reinterpret_cast<const float4*>(w2 + 4 * k);
+                act[0] += w.x * hn[k]; act[1] += w.y * hn[k]; act[2] += w.z * hn[k]; act[3] += w.w * hn[k];
+            }
+        }
         {   // gru/operations_generic.h:400-410: this step's output is kept, the stored state resets when the counter wraps
             const int new_step = gs + 1;
             const bool wrap = !no_auto_reset && new_step >= a.seq_len;
 #pragma unroll
             for(int j = 0; j < HD; j++) h[j] = wrap ? sm_b[TcImage::H0 + j] : hn[j];
             gs = wrap ? 0 : new_step;
-            if(wrap){   // rare: the A rows must hold the reset state (G3 of this step has completed)
-                put4(6, h[0], h[1], h[2], h[3]); put4(7, h[4], h[5], h[6], h[7]); put4(8, h[8], h[9], h[10], h[11]); put4(9, h[12], h[13], h[14], h[15]);
-            }
+            // the hidden rows of the A operand for the next step's G2 (its MMAs are issued only after the next barrier)
+            put4(6, h[0], h[1], h[2], h[3]); put4(7, h[4], h[5], h[6], h[7]); put4(8, h[8], h[9], h[10], h[11]); put4(9, h[12], h[13], h[14], h[15]);
         }
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;

@@ -292,3 +292,29 @@ def test_tcgen05_rollout_matches_fp32_rollout(rb):
     close_relative(ob["actions"][:100, stable], oa["actions"][:100, stable], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions, first 100 steps")
     close_relative(sb[None, stable], sa[None, stable], 5e-3, STATE_GROUPS, "final states after 600 steps")
     assert (oa["episode_length"] == ob["episode_length"]).mean() > 0.995
+
+
+def test_per_environment_mdp_parameters(rb, port):
+    """reward weights / termination thresholds that differ per environment take the general (non-uniform) kernel path"""
+    n, T = 256, 30
+    spec = rb.SPEC_RAPTOR
+    rs = np.random.RandomState(3)
+    params = np.tile(port.nominal_parameters(spec), (n, 1))
+    params[:, 96] = rs.uniform(0.2, 2.0, n)        # reward.constant
+    params[:, 98] = rs.uniform(0.5, 1.5, n)        # reward.position
+    params[:, 101] = rs.uniform(0.0, 0.3, n)       # reward.linear_velocity
+    params[:, 116] = rs.uniform(1.0, 3.0, n)       # termination.linear_velocity_threshold
+    params = params.astype(np.float32)
+    rng = port.rng_states(9, n, warmup=16)
+    states = port.sample_initial_state_n(spec, params, rng)
+    pol = port.make_policy(rb.raptor_policy_blob())
+    h = np.tile(rb.raptor_policy_blob()[352 + 16 + 2 * (768 + 48):][:16], (n, 1)).astype(np.float32)
+    want = port.rollout(spec, pol, params, states.copy(), rng.copy(), T, hidden=h, gru_step=np.zeros(n, np.int32))
+    for gemm in (rb.GEMM_FP32_CUDA_CORES, rb.GEMM_TCGEN05_3XTF32):
+        e = rb.VectorEnvironment(n, spec)
+        e.set_parameters(params); e.set_state(states); e.set_rng(rng)
+        e.load_policy(gemm=gemm)
+        out = e.rollout(T, record=("rewards", "terminated", "actions"))
+        assert np.array_equal(out["terminated"], want["terminated"])
+        close(out["rewards"], want["rewards"], 1e-4, 2e-4, "rewards")
+        close_relative(out["actions"], want["actions"], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
