@@ -9,10 +9,12 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <type_traits>
 
 #include "../../include/b200_l2f.h"
 #include "kernels.cuh"
 #include "rollout_tc.cuh"
+#include "mlp.cuh"
 
 using namespace b200l2f;
 
@@ -524,7 +526,13 @@ int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
             return fail(h, B200L2F_ERR_UNSUPPORTED, "policy_load: the GRU actor is instantiated for Dense(22->16) -> GRU(16) -> Dense(16->4)");
         if(h->obs_dim < 22) return fail(h, B200L2F_ERR_ARGUMENT, "policy_load: observation narrower than the actor input");
     }
-    else return fail(h, B200L2F_ERR_UNSUPPORTED, "policy_load: MLP actors are not built yet");
+    else if(desc->arch == B200L2F_POLICY_MLP){
+        if(desc->hidden_dim != MLP_HD) return fail(h, B200L2F_ERR_UNSUPPORTED, "policy_load: MLP actors are instantiated for hidden_dim 64");
+        if(desc->input_dim != h->obs_dim) return fail(h, B200L2F_ERR_ARGUMENT, "policy_load: an MLP actor consumes the full observation of the spec (input_dim must equal OBSERVATION_DIM)");
+        const bool ok = (desc->head == B200L2F_HEAD_SQUASH_EVAL && desc->output_dim == 8) || (desc->head != B200L2F_HEAD_SQUASH_EVAL && desc->output_dim == 4);
+        if(!ok) return fail(h, B200L2F_ERR_ARGUMENT, "policy_load: output_dim must be 8 for SQUASH_EVAL ([mean, log_std]) and 4 otherwise");
+    }
+    else return fail(h, B200L2F_ERR_ARGUMENT, "policy_load: unknown architecture");
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
     h->d_blob = nullptr; h->d_hidden = nullptr; h->d_gru_step = nullptr;
@@ -532,6 +540,12 @@ int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
     CU(cudaMemcpy(h->d_blob, blob, sizeof(float) * n_floats, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&h->d_hidden, sizeof(float) * desc->hidden_dim * (size_t)h->n));
     CU(cudaMalloc(&h->d_gru_step, sizeof(int) * (size_t)h->n));
+    if(desc->arch == B200L2F_POLICY_MLP){
+        h->pol = *desc; h->blob_floats = n_floats; h->policy_loaded = true;
+        CU(cudaMemsetAsync(h->d_hidden, 0, sizeof(float) * desc->hidden_dim * (size_t)h->n, h->stream));
+        CU(cudaMemsetAsync(h->d_gru_step, 0, sizeof(int) * (size_t)h->n, h->stream));
+        return B200L2F_OK;
+    }
     h->h_image.assign(RaptorImage<22, 16, 4>::SIZE, 0.0f);
     build_raptor_image_host<22, 16, 4>(h->h_image.data(), blob);
     {   // tensor-core operand image: tf32 hi/lo planes in the canonical K-major core-matrix order
@@ -558,6 +572,7 @@ static const float* raptor_h0(const b200l2f_handle* h){
 int b200l2f_policy_reset(b200l2f_handle* h, const uint8_t* mask, int memspace){
     CU(cudaSetDevice(h->cfg.device));
     if(!h->policy_loaded) return fail(h, B200L2F_ERR_STATE, "policy_reset: no policy loaded");
+    if(h->pol.arch == B200L2F_POLICY_MLP) return B200L2F_OK;   // stateless actor
     const void* d_mask = nullptr; int rc;
     if(mask){ if((rc = upload(h, mask, h->n, memspace, &d_mask))) return rc; }
     k_policy_reset<16><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_hidden, h->d_gru_step, raptor_h0(h), (const uint8_t*)d_mask, h->n);
@@ -573,6 +588,27 @@ int b200l2f_policy_evaluate_step(b200l2f_handle* h, const float* observations, i
     if(memspace == B200L2F_HOST){ if((rc = ensure_stage(h, obs_bytes + act_bytes))) return rc; }
     if((rc = upload(h, observations, obs_bytes, memspace, &d_obs))) return rc;
     if((rc = result_buffer(h, actions, act_bytes, memspace, &d_act, obs_bytes))) return rc;
+    if(h->pol.arch == B200L2F_POLICY_MLP){
+        const int has_std = h->pol.standardize, has_ls = h->pol.head == B200L2F_HEAD_PPO_GAUSSIAN, head = h->pol.head;
+        auto go = [&](auto in_c, auto out_c) -> int {
+            constexpr int IN = decltype(in_c)::value, OUT = decltype(out_c)::value;
+            constexpr int ROWS = IN > MLP_HD ? IN : MLP_HD;
+            auto kern = k_mlp_step<IN, OUT>;
+            const size_t smem = sizeof(float) * (MlpImg<IN, OUT>::SIZE + (size_t)ROWS * BLOCK);
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid_for(h->n, BLOCK), BLOCK, smem, h->stream>>>(h->d_blob, has_std, has_ls, head, (const float*)d_obs, ld, h->d_rng, (float*)d_act, h->n);
+            LAUNCH_CHECK();
+            return (int)B200L2F_OK;
+        };
+        using I22 = std::integral_constant<int, 22>; using I26 = std::integral_constant<int, 26>; using I82 = std::integral_constant<int, 82>;
+        using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
+        const bool o8 = h->pol.output_dim == 8;
+        if(h->pol.input_dim == 22) rc = o8 ? go(I22{}, O8{}) : go(I22{}, O4{});
+        else if(h->pol.input_dim == 26) rc = o8 ? go(I26{}, O8{}) : go(I26{}, O4{});
+        else rc = o8 ? go(I82{}, O8{}) : go(I82{}, O4{});
+        if(rc) return rc;
+        return download(h, actions, d_act, act_bytes, memspace);
+    }
     const size_t smem = sizeof(float) * RaptorImage<22, 16, 4>::SIZE;
     if(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH)
         k_raptor_step<22, 16, 4, false><<<grid_for(h->n, BLOCK), BLOCK, smem, h->stream>>>(h->d_blob, (const float*)d_obs, ld, h->d_hidden, h->d_gru_step, h->pol.gru_sequence_length, no_auto_reset, (float*)d_act, h->n);
@@ -618,7 +654,8 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     CU(cudaSetDevice(h->cfg.device));
     if(!h->policy_loaded) return fail(h, B200L2F_ERR_STATE, "rollout: no policy loaded");
     if(n_steps < 0) return fail(h, B200L2F_ERR_ARGUMENT, "rollout: n_steps < 0");
-    if(h->kind == KIND_TEACHER) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the Raptor actor is paired with the DEFAULT and RAPTOR specs");
+    if(h->pol.arch == B200L2F_POLICY_RAPTOR_GRU && h->kind == KIND_TEACHER) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the Raptor actor is paired with the DEFAULT and RAPTOR specs");
+    if(h->pol.arch == B200L2F_POLICY_MLP && h->pol.head == B200L2F_HEAD_PPO_GAUSSIAN) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: stochastic PPO actors are driven by b200l2f_collect");
     int rc;
     if((rc = refresh_features(h))) return rc;
     RolloutArgs a{};
@@ -643,7 +680,7 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
             a.state_stride = out->state_stride;
             add((void**)&a.out_states, out->states, sizeof(float) * (T / out->state_stride + 1) * n * h->sdim);
         }
-        add((void**)&a.out_obs, out->observations, sizeof(float) * T * n * 22);
+        add((void**)&a.out_obs, out->observations, sizeof(float) * T * n * (h->pol.arch == B200L2F_POLICY_MLP ? h->obs_dim : 22));
         add((void**)&a.out_actions, out->actions, sizeof(float) * T * n * 4);
         add((void**)&a.out_rewards, out->rewards, sizeof(float) * T * n);
         add((void**)&a.out_term, out->terminated, T * n);
@@ -671,7 +708,23 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
         if(constw) return launch_rollout_raptor<Spec, false, true, true>(h, a);
         return h->rolled ? launch_rollout_raptor<Spec, false, true, false, true>(h, a) : launch_rollout_raptor<Spec, false, true, false, false>(h, a);
     };
-    rc = h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
+    if(h->pol.arch == B200L2F_POLICY_MLP){
+        auto gomlp = [&](auto spec, auto out_c) -> int {
+            using Spec = decltype(spec);
+            constexpr int OUT = decltype(out_c)::value, IN = Spec::OBS_DIM;
+            constexpr int ROWS = IN > MLP_HD ? IN : MLP_HD;
+            auto kern = k_rollout_mlp<Spec, OUT>;
+            const size_t smem = sizeof(float) * (MlpImg<IN, OUT>::SIZE + (size_t)P_DYN_DIM * BLOCK + (size_t)ROWS * BLOCK);
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, h->pol.standardize);
+            LAUNCH_CHECK();
+            return (int)B200L2F_OK;
+        };
+        using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
+        const bool o8 = h->pol.output_dim == 8;
+        rc = dispatch_spec(h, [&](auto spec){ return o8 ? gomlp(spec, O8{}) : gomlp(spec, O4{}); });
+    }
+    else rc = h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
     if(rc) return rc;
     if(ms == B200L2F_HOST && total){
         if((rc = ensure_pinned(h, total))) return rc;
@@ -690,8 +743,45 @@ int b200l2f_collect_reset(b200l2f_handle* h){
     CU(cudaMemsetAsync(h->d_truncated, 1, h->n, h->stream));
     return B200L2F_OK;
 }
-int b200l2f_collect(b200l2f_handle* h, int32_t, int32_t, float*, int){
-    return fail(h, B200L2F_ERR_UNSUPPORTED, "collect: not built yet");
+int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, float* dataset, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->policy_loaded || h->pol.arch != B200L2F_POLICY_MLP || h->pol.head != B200L2F_HEAD_PPO_GAUSSIAN)
+        return fail(h, B200L2F_ERR_STATE, "collect: load an MLP actor with the PPO_GAUSSIAN head first");
+    if(h->kind == KIND_DEFAULT) return fail(h, B200L2F_ERR_UNSUPPORTED, "collect: instantiated for the H = 1 specs (RAPTOR, TEACHER)");
+    if(n_steps < 0 || !dataset) return fail(h, B200L2F_ERR_ARGUMENT, "collect: bad arguments");
+    const int D = h->obs_dim + 15;
+    const size_t bytes = sizeof(float) * (size_t)(n_steps + 1) * h->n * D;
+    void* dev; int rc;
+    if((rc = result_buffer(h, dataset, bytes, memspace, &dev))) return rc;
+    if(memspace == B200L2F_HOST) CU(cudaMemsetAsync(dev, 0, bytes, h->stream));
+    CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
+    CollectArgs a{};
+    a.params = h->d_params; a.env_row = h->d_env_row; a.state = h->d_state[0]; a.rng = h->d_rng; a.blob = h->d_blob; a.has_std = h->pol.standardize;
+    a.episode_step = h->d_episode_step; a.episode_return = h->d_episode_return; a.truncated = h->d_truncated; a.dataset = (float*)dev;
+    a.n = h->n; a.T = n_steps; a.step_limit = episode_step_limit; a.error_flag = h->d_flags;
+    auto go = [&](auto spec, auto dr_c) -> int {
+        using Spec = decltype(spec);
+        constexpr bool DR = decltype(dr_c)::value;
+        constexpr int IN = Spec::OBS_DIM;
+        auto kern = k_collect<Spec, DR>;
+        const size_t smem = sizeof(float) * (MlpImg<IN, 4>::SIZE + (size_t)P_DYN_DIM * BLOCK + (size_t)(MLP_HD + IN) * BLOCK);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    };
+    if(h->kind == KIND_RAPTOR) rc = h->dr ? go(SpecRaptor{}, std::true_type{}) : go(SpecRaptor{}, std::false_type{});
+    else rc = h->dr ? go(SpecTeacher{}, std::true_type{}) : go(SpecTeacher{}, std::false_type{});
+    if(rc) return rc;
+    h->features_dirty = true;   // resets rewrite parameter columns
+    if((rc = download(h, dataset, dev, bytes, memspace))) return rc;
+    if(h->dr){
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if(flag) return fail(h, B200L2F_ERR_STATE, "L2f: invalid domain randomization ranges (reset inside collect)");
+    }
+    return B200L2F_OK;
 }
 
 }  // extern "C"

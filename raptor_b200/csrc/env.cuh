@@ -19,15 +19,20 @@ struct ParamsGlobal {  // struct-of-arrays in HBM: element i of environment e at
     size_t stride;
     __device__ __forceinline__ float operator[](int i) const { return __ldg(base + (size_t)i * stride); }
 };
-struct ParamsStaged {  // dynamics block [0, P_DYN_DIM) staged in shared memory as sm[i * blockDim.x + tid]; the rest from HBM/L1
+// dynamics block [0, P_DYN_DIM) staged in shared memory as sm[i * blockDim.x + tid]; the rest from HBM/L1.
+// NC: the parameter buffer is read-only for the whole launch (ld.global.nc); kernels that rewrite parameters (collect's reset) use NC = false.
+template <bool NC>
+struct ParamsStagedT {
     const float* sm;   // already offset by threadIdx.x
     int sm_stride;
-    const float* __restrict__ base;
+    const float* base;
     size_t stride;
     __device__ __forceinline__ float operator[](int i) const {
-        return i < P_DYN_DIM ? sm[i * sm_stride] : __ldg(base + (size_t)i * stride);
+        if(i < P_DYN_DIM) return sm[i * sm_stride];
+        return NC ? __ldg(base + (size_t)i * stride) : base[(size_t)i * stride];
     }
 };
+using ParamsStaged = ParamsStagedT<true>;
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi){ return x < lo ? lo : (x > hi ? hi : x); }
 

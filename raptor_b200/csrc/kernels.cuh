@@ -24,14 +24,15 @@ constexpr int BLOCK = B200L2F_BLOCK;               // environments (= threads) p
 constexpr int MIN_BLOCKS = B200L2F_MIN_BLOCKS;     // resident CTAs per SM the fused kernels are register-budgeted for
 
 // stage the dynamics block of this thread's environment: sm[i * BLOCK + tid] = params[i][env]; time constants -> reciprocals
-__device__ __forceinline__ ParamsStaged stage_dynamics(float* __restrict__ sm_dyn, const float* __restrict__ params, size_t n, size_t env){
+template <bool NC = true>
+__device__ __forceinline__ ParamsStagedT<NC> stage_dynamics(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env){
     float* sm = sm_dyn + threadIdx.x;
     const float* g = params + env;
 #pragma unroll 4
-    for(int i = 0; i < P_DYN_DIM; i++) sm[i * BLOCK] = __ldg(g + (size_t)i * n);
+    for(int i = 0; i < P_DYN_DIM; i++) sm[i * BLOCK] = NC ? __ldg(g + (size_t)i * n) : g[(size_t)i * n];
 #pragma unroll
     for(int r = 0; r < 8; r++) sm[(P_TAU_RISE + r) * BLOCK] = 1.0f / sm[(P_TAU_RISE + r) * BLOCK];
-    ParamsStaged p;
+    ParamsStagedT<NC> p;
     p.sm = sm; p.sm_stride = BLOCK; p.base = g; p.stride = n;
     return p;
 }

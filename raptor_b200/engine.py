@@ -223,6 +223,21 @@ class VectorEnvironment:
         self._check(self._lib.b200l2f_policy_evaluate_step(self._h, po, observation.shape[1], pa, int(no_auto_reset), ms))
         return action
 
+    # ---- PPO collection (rl_tools::collect): on-device auto-reset + trajectory write-back
+    def collect_reset(self):
+        self._check(self._lib.b200l2f_collect_reset(self._h))
+
+    def collect(self, n_steps, episode_step_limit, dataset=None):
+        """dataset: [(T+1)*N, OBS+15] rows = step*N + env, columns obs | actions_mean[4] | actions[4] | log_prob | reward | terminated |
+        truncated | value | advantage | target_value (the last three are the learner's); numpy (host) or torch CUDA tensor"""
+        D = self.OBSERVATION_DIM + 15
+        shape = ((n_steps + 1) * self.N_ENVIRONMENTS, D)
+        if dataset is None:
+            dataset = np.zeros(shape, np.float32)
+        p, ms, _ = _arg(dataset, np.float32, shape, "dataset")
+        self._check(self._lib.b200l2f_collect(self._h, n_steps, episode_step_limit, p, ms))
+        return dataset
+
     def get_hidden(self):
         h = np.zeros((self.N_ENVIRONMENTS, self.policy.hidden_dim), np.float32)
         g = np.zeros(self.N_ENVIRONMENTS, np.int32)
@@ -240,7 +255,7 @@ class VectorEnvironment:
         record: subset of {"states","observations","actions","rewards","terminated","returns","episode_length"} -> numpy arrays (host),
         or pass `out` = dict of preallocated torch CUDA tensors / numpy arrays (all in one memory space)."""
         n, T = self.N_ENVIRONMENTS, n_steps
-        shapes = {"states": ((T // max(state_stride, 1) + 1, n, self.STATE_DIM), np.float32), "observations": ((T, n, 22), np.float32),
+        shapes = {"states": ((T // max(state_stride, 1) + 1, n, self.STATE_DIM), np.float32), "observations": ((T, n, 22 if self.policy is None or self.policy.arch == L.POLICY_RAPTOR_GRU else self.OBSERVATION_DIM), np.float32),
                   "actions": ((T, n, 4), np.float32), "rewards": ((T, n), np.float32), "terminated": ((T, n), np.uint8),
                   "returns": ((n,), np.float32), "episode_length": ((n,), np.int32)}
         out = dict(out) if out else {}

@@ -318,3 +318,108 @@ def test_per_environment_mdp_parameters(rb, port):
         assert np.array_equal(out["terminated"], want["terminated"])
         close(out["rewards"], want["rewards"], 1e-4, 2e-4, "rewards")
         close_relative(out["actions"], want["actions"], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# MLP actors (SAC teacher, PPO) and PPO collection
+# ---------------------------------------------------------------------------------------------------------------------------
+def random_mlp_blob(rs, in_dim, out_dim, standardize, log_std):
+    hd = 64
+    parts = []
+    if standardize:
+        parts += [rs.normal(0, 0.1, in_dim), 1.0 / rs.uniform(0.5, 2.0, in_dim)]
+    for (o, i) in [(hd, in_dim), (hd, hd), (out_dim, hd)]:
+        bound = np.sqrt(6.0 / i)
+        w = rs.uniform(-bound, bound, (o, i))
+        if o == out_dim:
+            w *= 0.3
+        parts += [w.ravel(), rs.uniform(-0.05, 0.05, o)]
+    if log_std:
+        parts.append(np.log(np.full(4, 0.5)))
+    return np.concatenate(parts).astype(np.float32)
+
+
+@pytest.mark.parametrize("spec,head", [(B.SPEC_RAPTOR, "ppo"), (B.SPEC_TEACHER, "squash"), (B.SPEC_DEFAULT, "identity")])
+def test_mlp_evaluate_step(rb, port, spec, head):
+    n = 300
+    rs = np.random.RandomState(7)
+    in_dim = port.observation_dim(spec)
+    out_dim = 8 if head == "squash" else 4
+    hd_id = {"identity": (rb.HEAD_IDENTITY, B.HEAD_IDENTITY), "squash": (rb.HEAD_SQUASH_EVAL, B.HEAD_SQUASH_EVAL), "ppo": (rb.HEAD_PPO_GAUSSIAN, B.HEAD_PPO_GAUSSIAN)}[head]
+    blob = random_mlp_blob(rs, in_dim, out_dim, True, head == "ppo")
+    env = rb.VectorEnvironment(n, spec)
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=in_dim, hidden_dim=64, output_dim=out_dim, standardize=1, head=hd_id[0])
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=in_dim, hidden_dim=64, output_dim=out_dim, standardize=1, head=hd_id[1])
+    obs = rs.normal(0, 1, (n, in_dim)).astype(np.float32)
+    rng = port.rng_states(4, n, warmup=16)
+    env.set_rng(rng)
+    got = env.policy_evaluate_step(obs)
+    want, _, _ = port.policy_evaluate_step(pol, obs, rng=rng)
+    close(got, want, 2e-5, 2e-5, head)
+    if head == "ppo":
+        assert np.array_equal(env.get_rng(), rng)
+
+
+def test_rollout_with_teacher_mlp(rb, port):
+    """BASELINE config 3 shape: TEACHER spec (OBS 26), per-env DR dynamics, SAC-teacher MLP 26-64-64-8 + squash (evaluation mode)"""
+    n, T = 200, 60
+    spec = B.SPEC_TEACHER_DR
+    rs = np.random.RandomState(11)
+    blob = random_mlp_blob(rs, 26, 8, False, False)
+    env_p = foundation_dr_env_params(port, spec)
+    rng = port.rng_states(21, n, warmup=16)
+    params = port.sample_initial_parameters_n(spec, env_p, rng)
+    states = port.sample_initial_state_n(spec, params, rng)
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_EVAL)
+    want = port.rollout(spec, pol, params, states.copy(), rng.copy(), T)
+    env = rb.VectorEnvironment(n, spec)
+    env.set_parameters(params); env.set_state(states); env.set_rng(rng)
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL)
+    out = env.rollout(T, record=("states", "observations", "actions", "rewards", "terminated"))
+    # a random actor does not stabilise the vehicle: compare while trajectories are still regular (first 20 steps) at 1e-4, the rest loosely
+    close_relative(out["actions"][:20], want["actions"][:20], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
+    close_relative(out["states"][:21], want["states"][:21], 1e-4, STATE_GROUPS, "states")
+    close(out["observations"][:20], want["observations"][:20], 1e-3, 1e-4, "observations")
+    assert (out["terminated"][:20] == want["terminated"][:20]).mean() > 0.999
+    assert np.array_equal(env.get_rng(), port_final_rng(port, spec, pol, params, states, rng, T))
+
+
+def port_final_rng(port, spec, pol, params, states, rng, T):
+    r = rng.copy()
+    port.rollout(spec, pol, params, states.copy(), r, T, record=False)
+    return r
+
+
+@pytest.mark.parametrize("spec", [B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR])
+def test_ppo_collect_vs_oracle(rb, port, spec):
+    """BASELINE config 4 shape: PPO actor (standardize -> 64 -> 64 -> 4, learned log_std), Gaussian sampling, auto-reset on
+    terminated-or-step-limit with re-sampled parameters and state, dataset rows in the reference layout"""
+    n, T, limit = 96, 40, 12
+    rs = np.random.RandomState(5)
+    blob = random_mlp_blob(rs, 22, 4, True, True)
+    env = rb.VectorEnvironment(n, spec)
+    env_p = foundation_dr_env_params(port, spec) if spec == B.SPEC_RAPTOR_DR else port.nominal_parameters(spec)
+    env.set_environment_parameters(env_p)
+    env.initialize_rng(31, warmup=16)
+    env.initial_parameters()
+    env.initial_state()
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN)
+    env.collect_reset()
+    rng = env.get_rng()
+    params, states = env.get_parameters(), env.get_state()
+    data = env.collect(T, limit)
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
+    ep_step = np.zeros(n, np.int32); ep_ret = np.zeros(n, np.float32); trunc = np.ones(n, np.uint8)
+    want = port.collect(spec, pol, env_p, params, states, rng, ep_step, ep_ret, trunc, T, limit)
+    D = 37
+    got3, want3 = data.reshape(T + 1, n, D), want.reshape(T + 1, n, D)
+    assert np.array_equal(env.get_rng(), rng)                                     # every draw (resets, sampling) in the same order
+    assert np.array_equal(got3[:T, :, 32], want3[:T, :, 32])                       # terminated
+    assert np.array_equal(got3[:T, :, 33], want3[:T, :, 33])                       # truncated
+    assert want3[:T, :, 33].sum() >= n * (T // limit)                              # resets really happened
+    close(got3[..., :22], want3[..., :22], 2e-3, 2e-4, "observations (incl. the final row)")
+    close(got3[:T, :, 22:30], want3[:T, :, 22:30], 2e-3, 2e-3, "action means / actions")
+    close(got3[:T, :, 30], want3[:T, :, 30], 1e-3, 1e-3, "log-prob")
+    close(got3[:T, :, 31], want3[:T, :, 31], 2e-3, 2e-2, "reward")
+    assert np.all(got3[..., 34:] == 0)                                            # learner columns untouched
+    close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
