@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""tools/bench_configs.py -- throughput of the other BASELINE configs (3: 1M envs + SAC-teacher MLP, 4: PPO collection with write-back).
+Prints one JSON object per config.  Timing: CUDA events on the engine's stream, 3 warm-ups, L2 flushed between timed launches."""
+import json
+import sys
+import os
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import raptor_b200 as rb  # noqa: E402
+
+DR = [1.5, 5.0, 40, 1200, 0.02, 5.0, 0.1, 0.03, 0.10, 0.03, 0.30, 0.005, 0.05, 0.0, 0.3]
+
+
+def mlp_blob(rs, i, o, std, ls):
+    parts = []
+    if std:
+        parts += [np.zeros(i), np.ones(i)]
+    for (oo, ii) in [(64, i), (64, 64), (o, 64)]:
+        b = np.sqrt(6.0 / ii)
+        parts += [rs.uniform(-b, b, (oo, ii)).ravel() * (0.3 if oo == o else 1.0), np.zeros(oo)]
+    if ls:
+        parts.append(np.log(np.full(4, 0.5)))
+    return np.concatenate(parts).astype(np.float32)
+
+
+def timed(fn, reset, steps=3, warmup=3, stream=None, flush=None):
+    for _ in range(warmup):
+        reset(); fn()
+    ms = []
+    for _ in range(steps):
+        reset(); flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); fn(); b.record(stream)
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return sum(ms) / len(ms)
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rs = np.random.RandomState(0)
+    out = []
+    # ---- config 3
+    n, T = 1048576, 100
+    env = rb.VectorEnvironment(n, rb.SPEC_TEACHER_DR, stream=stream.cuda_stream)
+    row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32); env.set_environment_parameters(row)
+    env.initialize_rng(3, warmup=16); env.sample_initial_parameters(); env.sample_initial_state()
+    env.load_policy(mlp_blob(rs, 26, 8, False, False), arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL)
+    s0 = torch.from_numpy(env.get_state()).to(dev); ret = torch.zeros(n, device=dev)
+    ms = timed(lambda: env.rollout(T, out={"returns": ret}), lambda: env.set_state(s0), stream=stream, flush=flush)
+    out.append({"config": "3: 1 048 576 envs, per-env DR, SAC-teacher MLP 26-64-64-8 + squash (eval), %d-step rollout" % T, "env_steps_per_s": n * T / ms * 1e3, "ms_per_launch": ms,
+                "algorithmic_flop_per_env_step": 1100 + 2 * 6272, "fp32_tflops": n * T / ms * 1e3 * (1100 + 2 * 6272) / 1e12})
+    del env, s0, ret
+    # ---- config 4
+    n, T = 262144, 256
+    env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR, stream=stream.cuda_stream)
+    row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32); env.set_environment_parameters(row)
+    env.initialize_rng(4, warmup=16); env.initial_parameters(); env.initial_state()
+    env.load_policy(mlp_blob(rs, 22, 4, True, True), arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN)
+    data = torch.zeros(((T + 1) * n, 37), dtype=torch.float32, device=dev)
+    ms = timed(lambda: env.collect(T, 500, data), lambda: env.collect_reset(), stream=stream, flush=flush)
+    written = n * T * 34 * 4 + n * 22 * 4
+    out.append({"config": "4: 262 144 envs x 256-step PPO collection, PPO MLP 22-64-64-4 (standardize, learned log_std), DR resets, dataset rows [(T+1)N, 37] in HBM",
+                "env_steps_per_s": n * T / ms * 1e3, "ms_per_launch": ms, "dataset_bytes_written": written, "hbm_write_gbs": written / ms / 1e6,
+                "mean_reward": float(data[: T * n, 31].mean().item()), "truncated_fraction": float(data[: T * n, 33].mean().item())})
+    for o in out:
+        print(json.dumps(o))
+
+
+if __name__ == "__main__":
+    main()
