@@ -36,7 +36,7 @@ SCRIPT = textwrap.dedent("""
         assert full.shape == (T, n_global, D), full.shape
         want = torch.arange(n_global, dtype=torch.float32)[None, :, None].expand(T, n_global, D) + torch.arange(T, dtype=torch.float32)[:, None, None] * 1000
         assert torch.equal(full, want)
-    print("rank", rank, "ok")
+    sys.stdout.write("rank%d-ok\n" % rank); sys.stdout.flush()
 """) % ROOT
 
 
@@ -46,7 +46,7 @@ def test_gloo_world_size_2_gather(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "rank0-ok" in r.stdout and "rank1-ok" in r.stdout
 
 
 def test_reference_arm_under_torchrun_only_rank0_works(tmp_path):
