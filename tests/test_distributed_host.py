@@ -36,7 +36,7 @@ SCRIPT = textwrap.dedent("""
         assert full.shape == (T, n_global, D), full.shape
         want = torch.arange(n_global, dtype=torch.float32)[None, :, None].expand(T, n_global, D) + torch.arange(T, dtype=torch.float32)[:, None, None] * 1000
         assert torch.equal(full, want)
-    sys.stdout.write("rank%d-ok\n" % rank); sys.stdout.flush()
+    sys.stdout.write("rank" + str(rank) + "-ok" + chr(10)); sys.stdout.flush()
 """) % ROOT
 
 
