@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-(timeout -s KILL 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8) | tee gpurun_out/pytest_gpu9.log
-timeout -s KILL 600 python tools/bench_configs.py 2>&1 | tail -4 | tee gpurun_out/bench_configs_r01.json
+nvidia-smi -L
+timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 2 --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_r01_n2.json | cut -c1-1200
+timeout -s KILL 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_r01_n1_b.json | cut -c1-900
