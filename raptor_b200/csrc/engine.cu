@@ -216,6 +216,20 @@ int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
     return B200L2F_OK;
 }
 
+template <class Spec, bool FAST, bool UNIFORM>
+int launch_rollout_ts(b200l2f_handle* h, const RolloutArgs& a){
+    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM>;
+    static bool configured[8] = {};
+    int dev = h->cfg.device & 7;
+    if(!configured[dev]){
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::TOTAL));
+        configured[dev] = true;
+    }
+    kern<<<grid_for(a.n, BLOCK), BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -698,6 +712,10 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
         using Spec = decltype(spec);
         if(tensor_cores){
             const bool uniform = (h->features & 2) == 0;
+            // A operand in TMEM ("TS" MMAs, 63 KB smem + 128 TMEM columns per CTA -> 3 CTAs/SM) is the default; B200L2F_A=smem selects the
+            // shared-memory-A variant (2 CTAs/SM).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
+            static const bool a_in_tmem = [](){ const char* e = std::getenv("B200L2F_A"); return !(e && std::string(e) == "smem"); }();
+            if(a_in_tmem && fast) return uniform ? launch_rollout_ts<Spec, true, true>(h, a) : launch_rollout_ts<Spec, true, false>(h, a);
             static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
             if(!fast) return launch_rollout_tc<Spec, false, false, true>(h, a);
             if(!uniform) return launch_rollout_tc<Spec, true, false, true>(h, a);

@@ -27,7 +27,8 @@ struct TcImage {
     static constexpr int H0 = B3_LO + K3 * N3;   // initial hidden state (16 floats) for the auto-reset
     static constexpr int W2T = H0 + 16;          // fp32 dense-2 weights, k-major [16][4], then b2[4]
     static constexpr int W1T = W2T + 68;         // fp32 dense-1 weights, k-major [22][16], then b1[16]
-    static constexpr int SIZE = W1T + 22 * 16 + 16;   // floats
+    static constexpr int BIAS2 = W1T + 22 * 16 + 16;  // fp32 GRU biases for the epilogue of the TMEM-A variant: (b_ih + b_hh)[0:32] | b_in[16] | b_hn[16]
+    static constexpr int SIZE = BIAS2 + 64;      // floats
     static constexpr int BYTES = SIZE * 4;
     static_assert(BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 };
@@ -70,6 +71,8 @@ inline void build_tc_image_host(float* img, const float* blob){
     for(int n = 0; n < OUT; n++) img[TcImage::W2T + 64 + n] = b2[n];
     for(int k = 0; k < IN; k++) for(int n = 0; n < HD; n++) img[TcImage::W1T + k * HD + n] = W1[n * IN + k];
     for(int n = 0; n < HD; n++) img[TcImage::W1T + IN * HD + n] = b1[n];
+    for(int j = 0; j < 2 * HD; j++) img[TcImage::BIAS2 + j] = bih[j] + bhh[j];
+    for(int j = 0; j < HD; j++){ img[TcImage::BIAS2 + 32 + j] = bih[2 * HD + j]; img[TcImage::BIAS2 + 48 + j] = bhh[2 * HD + j]; }
 }
 
 // ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
@@ -466,6 +469,219 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
         a.rng[env] = rng;
 #pragma unroll
         for(int j = 0; j < HD; j++) a.hidden[(size_t)j * n + env] = h[j];
+        a.gru_step[env] = gs;
+        if(a.out_returns) a.out_returns[env] = ret;
+        if(a.out_eplen) a.out_eplen[env] = eplen;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if(warp == 0) tc::tmem_dealloc<128>(tmem_base);
+}
+
+
+// =================================================================================================================================
+// TMEM-A variant ("TS" MMAs): the A operand lives in tensor memory as well.  Every thread writes ITS row of the activations (hi and lo
+// planes) with tcgen05.st into its TMEM lane, the GRU hidden state lives ONLY in TMEM (hi + lo == h exactly in fp32; the tensor core
+// ignores the 13 low mantissa bits it cannot use), and shared memory holds just the weight image and the staged dynamics block:
+// 63 KB per CTA instead of 107 KB, 128 TMEM columns per CTA -> THREE CTAs (12 warps) per SM instead of two.
+//   TMEM columns (128):  [0,16) h hi | [16,32) h lo | [32,56) obs hi | [56,80) obs lo | [80,96) D1 | later: [32,48) x1 hi | [48,64) x1 lo | [64,128) D2
+//   lifetimes make the overlaps safe: obs/D1 are dead before x1 is written, x1/h are read by G2 while it writes D2 into [64,128).
+// G1 folds its bias in as K column 22 (= 1.0); G2 has no spare K column (K = 32 exactly), its biases are added in the epilogue.
+// =================================================================================================================================
+struct TsSmem {
+    static constexpr int B = 0;                                // weight image (TMA destination)
+    static constexpr int DYN = B + TcImage::BYTES;
+    static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
+    static constexpr int TOTAL = BAR + 32;
+};
+template <class Spec, bool FAST, bool UNIFORM>
+__global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
+    constexpr int HD = 16;
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    float* sm_b = reinterpret_cast<float*>(smraw + TsSmem::B);
+    float* sm_dyn = reinterpret_cast<float*>(smraw + TsSmem::DYN);
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + TsSmem::BAR);
+    uint64_t* bar_mma = bar_tma + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if(tid == 0){
+        tc::mbar_init(bar_tma, 1);
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_fence_init();
+    }
+    if(warp == 0) tc::tmem_alloc<128>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if(tid == 0){
+        tc::mbar_expect_tx(bar_tma, TcImage::BYTES);
+        tc::tma_load_1d(sm_b, tc_image, TcImage::BYTES, bar_tma);
+    }
+    const int e = blockIdx.x * BLOCK + tid;
+    const bool active = e < a.n;
+    const size_t n = (size_t)a.n;
+    const size_t env = active ? (size_t)e : 0;
+    const ParamsCompiledT<UNIFORM> p = stage_dynamics_compiled<UNIFORM>(sm_dyn, a.params, n, env, a.row0);
+    EnvState<Spec> st;
+    load_state(st, a.state + env, n);
+    DynInvariants d;
+    {
+        ParamsGlobal pg{a.params + env, n};
+        dyn_invariants(d, pg, st);
+    }
+    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
+    uint64_t rng = a.rng[env];
+    int gs = a.gru_step[env];
+    float ret = 0.0f; int eplen = 0; bool done = false;
+    const bool no_auto_reset = a.no_auto_reset != 0;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    constexpr uint32_t C_H_HI = 0, C_H_LO = 16, C_OBS_HI = 32, C_OBS_LO = 56, C_D1 = 80, C_X1_HI = 32, C_X1_LO = 48, C_D2 = 64;
+    // write 8 values as a hi block and a lo block (8 columns each) of this thread's lane
+    auto put8 = [&](uint32_t col_hi, uint32_t col_lo, const float* v){
+        float hi[8], lo[8];
+#pragma unroll
+        for(int i = 0; i < 8; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+        tc::tmem_st8(tmem_base + lane_off + col_hi, hi);
+        tc::tmem_st8(tmem_base + lane_off + col_lo, lo);
+    };
+    {
+        float h[HD];
+#pragma unroll
+        for(int j = 0; j < HD; j++) h[j] = a.hidden[(size_t)j * n + env];
+        put8(C_H_HI, C_H_LO, h); put8(C_H_HI + 8, C_H_LO + 8, h + 8);
+    }
+    const uint32_t b_s = tc::smem_u32(sm_b);
+    constexpr uint32_t SBO = 128;
+    constexpr uint32_t IDESC16 = tc::make_idesc_tf32(128, 16), IDESC64 = tc::make_idesc_tf32(128, 64);
+    uint32_t phase = 0;
+    // ksteps K=8 steps: A columns [a_hi + 8 s, +8) / [a_lo + 8 s, +8) against B chunk pairs (b_pair0 + s)
+    auto issue_gemm = [&](uint32_t dcol, uint32_t a_hi, uint32_t a_lo, int ksteps, int b_hi_off, int b_lo_off, int b_pair0, uint32_t N, uint32_t idesc, uint32_t acc){
+        for(int s = 0; s < ksteps; s++){
+            const uint64_t bhi = tc::make_smem_desc(b_s + b_hi_off * 4 + (b_pair0 + s) * 2 * N * 16, N * 16, SBO);
+            const uint64_t blo = tc::make_smem_desc(b_s + b_lo_off * 4 + (b_pair0 + s) * 2 * N * 16, N * 16, SBO);
+            tc::mma_tf32_ts(tmem_base + dcol, tmem_base + a_hi + 8 * s, bhi, idesc, acc); acc = 1;
+            tc::mma_tf32_ts(tmem_base + dcol, tmem_base + a_hi + 8 * s, blo, idesc, 1);
+            tc::mma_tf32_ts(tmem_base + dcol, tmem_base + a_lo + 8 * s, bhi, idesc, 1);
+        }
+    };
+    tc::mbar_wait(bar_tma, 0);
+    tc::tmem_st_wait();
+    __syncthreads();
+
+    for(int t = 0; t < a.T; t++){
+        if(a.out_states && active && (t % a.state_stride) == 0)
+            write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
+        float obs[24];
+        observe18<Spec, false>(st, p, rng, obs);
+        if constexpr(Spec::H == 1){
+#pragma unroll
+            for(int i = 0; i < 4; i++) obs[18 + i] = st.hist[i];
+        }
+        else{
+            const int cur = st.current_step == 0 ? Spec::H - 1 : st.current_step - 1;
+#pragma unroll
+            for(int i = 0; i < 4; i++) obs[18 + i] = hist_ptr[(size_t)(4 * cur + i) * n];
+        }
+        if(a.out_obs && active){
+            float* row = a.out_obs + ((size_t)t * n + env) * 22;
+#pragma unroll
+            for(int i = 0; i < 22; i++) row[i] = obs[i];
+        }
+        obs[22] = 1.0f; obs[23] = 0.0f;   // bias column, pad
+        // ---- G1: dense 1 (A = obs in TMEM)
+        put8(C_OBS_HI, C_OBS_LO, obs); put8(C_OBS_HI + 8, C_OBS_LO + 8, obs + 8); put8(C_OBS_HI + 16, C_OBS_LO + 16, obs + 16);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncthreads();
+        if(tid == 0){
+            tc::tc_fence_after();
+            issue_gemm(C_D1, C_OBS_HI, C_OBS_LO, 3, TcImage::B1_HI, TcImage::B1_LO, 0, 16, IDESC16, 0);
+            tc::mma_commit(bar_mma);
+        }
+        tc::mbar_wait(bar_mma, phase); phase ^= 1;
+        tc::tc_fence_after();
+        float x1[HD];
+        tc::tmem_ld16(tmem_base + lane_off + C_D1, x1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for(int j = 0; j < HD; j++) x1[j] = fmaxf(x1[j], 0.0f);
+        if(!no_auto_reset && gs >= a.seq_len){   // reset_truncate (gru/operations_generic.h:76-86)
+            put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8);
+            gs = 0;
+        }
+        // ---- G2: GRU pre-activations (A = [x1 | h] in TMEM, K = 32)
+        put8(C_X1_HI, C_X1_LO, x1); put8(C_X1_HI + 8, C_X1_LO + 8, x1 + 8);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncthreads();
+        if(tid == 0){
+            tc::tc_fence_after();
+            issue_gemm(C_D2, C_X1_HI, C_X1_LO, 2, TcImage::B2_HI, TcImage::B2_LO, 0, 64, IDESC64, 0);
+            issue_gemm(C_D2, C_H_HI, C_H_LO, 2, TcImage::B2_HI, TcImage::B2_LO, 2, 64, IDESC64, 1);
+            tc::mma_commit(bar_mma);
+        }
+        tc::mbar_wait(bar_mma, phase); phase ^= 1;
+        tc::tc_fence_after();
+        float hn[HD];
+        {
+            const float* bias = sm_b + TcImage::BIAS2;
+            float r[HD], nx[HD], nh[HD];
+            tc::tmem_ld16(tmem_base + lane_off + C_D2 + 0, r);
+            tc::tmem_ld16(tmem_base + lane_off + C_D2 + 32, nx);
+            tc::tmem_ld16(tmem_base + lane_off + C_D2 + 48, nh);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for(int j = 0; j < HD; j++) nx[j] = tanhf_<FAST>((nx[j] + bias[32 + j]) + (nh[j] + bias[48 + j]) * sigmoidf_<FAST>(r[j] + bias[j]));
+            float z[HD], hh[HD], hl[HD];
+            tc::tmem_ld16(tmem_base + lane_off + C_D2 + 16, z);
+            tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
+            tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for(int j = 0; j < HD; j++){ const float zz = sigmoidf_<FAST>(z[j] + bias[16 + j]); hn[j] = (1.0f - zz) * nx[j] + zz * (hh[j] + hl[j]); }
+        }
+        // ---- dense 2 (16 -> 4) on the CUDA cores
+        float act[4];
+        {
+            const float* w2 = sm_b + TcImage::W2T;
+            const float4 b = *reinterpret_cast<const float4*>(w2 + 64);
+            act[0] = b.x; act[1] = b.y; act[2] = b.z; act[3] = b.w;
+#pragma unroll
+            for(int k = 0; k < HD; k++){
+                const float4 w = *reinterpret_cast<const float4*>(w2 + 4 * k);
+                act[0] += w.x * hn[k]; act[1] += w.y * hn[k]; act[2] += w.z * hn[k]; act[3] += w.w * hn[k];
+            }
+        }
+        {   // gru/operations_generic.h:400-410: this step's output is kept, the stored state resets when the counter wraps
+            const int new_step = gs + 1;
+            const bool wrap = !no_auto_reset && new_step >= a.seq_len;
+            if(wrap){ put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8); }
+            else{ put8(C_H_HI, C_H_LO, hn); put8(C_H_HI + 8, C_H_LO + 8, hn + 8); }
+            gs = wrap ? 0 : new_step;
+        }
+        if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
+        RewardInputs ri;
+        reward_inputs(ri, st);
+        if(Spec::H == 1 || active) env_step_compiled<Spec>(st, p, d, act, rng, hist_ptr, n);
+        const bool term = env_terminated(p, st.x);
+        const float rw = env_reward(p, ri, act, st.x, term, d.dt);
+        if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
+        if(a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
+        if(!done){ ret += rw; eplen += 1; done = term; }
+    }
+    tc::tmem_st_wait();
+    float hh[HD], hl[HD];   // tcgen05.ld is warp-collective (.sync.aligned): every lane executes it, only active lanes store
+    tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
+    tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+    tc::tmem_ld_wait();
+    if(active){
+        if(a.out_states && (a.T % a.state_stride) == 0)
+            write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(a.T / a.state_stride) * n + env) * Spec::STATE_DIM);
+        store_state(st, a.state + env, n);
+        a.rng[env] = rng;
+#pragma unroll
+        for(int j = 0; j < HD; j++) a.hidden[(size_t)j * n + env] = hh[j] + hl[j];
         a.gru_step[env] = gs;
         if(a.out_returns) a.out_returns[env] = ret;
         if(a.out_eplen) a.out_eplen[env] = eplen;

@@ -82,6 +82,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one 32-bit column per tf32 element, 8 columns per instruction)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate){
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when complete (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar){
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -102,6 +111,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v){
 #pragma unroll
     for(int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// registers -> TMEM: thread t of warp w writes N consecutive columns of lane 32w + t
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v){
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait(){ asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait(){ asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- 3xTF32 operand split: x ~= hi + lo with hi, lo exactly representable in tf32 (10-bit mantissa; the tensor core ignores the low 13 bits)
