@@ -260,9 +260,15 @@ def main():
     value = total_env_steps / t_total
     mean_return = float(returns_dev.mean().item())
 
-    # ---- end-to-end through the public API with host buffers ("e2e")
-    host_state = state0.copy()
-    host_ret = np.zeros(n, np.float32)
+    # ---- end-to-end through the public API with host buffers ("e2e"): inputs and results live in PINNED host memory (numpy views of
+    # ---- torch pinned tensors), every step copies them H2D / D2H inside the timed region
+    def pinned(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t.numpy(), t
+    params0, _keep_p = pinned(params0)
+    state0, _keep_s = pinned(state0)
+    host_state, _keep_hs = pinned(state0.copy())
+    host_ret, _keep_hr = pinned(np.zeros(n, np.float32))
     for _ in range(2):
         env.set_parameters(params0); env.set_state(state0); env.policy_reset(); env.rollout(T, out={"returns": host_ret}); env.get_state(out=host_state)
     barrier()

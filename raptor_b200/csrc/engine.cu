@@ -43,6 +43,8 @@ struct b200l2f_handle {
     bool policy_loaded = false; b200l2f_policy_desc pol{};
     float* d_blob = nullptr; size_t blob_floats = 0;
     float* d_hidden = nullptr; int* d_gru_step = nullptr;
+    int* d_sched = nullptr; size_t sched_ints = 0;     // work counter + per-tile progress of the time-chunked scheduler
+    float* d_acc_ret = nullptr; int* d_acc_len = nullptr;
     float* d_tc_image = nullptr;     // tensor-core weight image (hi/lo planes of the three B operands, TMA source)
     std::vector<float> h_image;      // k-major actor image passed by value to the fused kernels (constant-bank weights)
     bool weights_in_constant_bank = false; bool rolled = false;
@@ -80,14 +82,25 @@ int ensure_stage(b200l2f_handle* h, size_t bytes){
     h->stage_bytes = bytes;
     return B200L2F_OK;
 }
-// host -> device staging buffer (pinned bounce), returns device pointer in *dev
+// is this host pointer page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory)?  Then the DMA engine can read/write it directly.
+bool is_pinned_host(const void* p){
+    cudaPointerAttributes attr;
+    if(cudaPointerGetAttributes(&attr, p) != cudaSuccess){ cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+// host -> device staging buffer, returns device pointer in *dev.  Pageable memory bounces through the handle's pinned buffer.
 int upload(b200l2f_handle* h, const void* src, size_t bytes, int memspace, const void** dev){
     if(memspace == B200L2F_DEVICE){ *dev = src; return B200L2F_OK; }
     int rc;
-    if((rc = ensure_pinned(h, bytes))) return rc;
     if((rc = ensure_stage(h, bytes))) return rc;
-    std::memcpy(h->h_pinned, src, bytes);
-    CU(cudaMemcpyAsync(h->d_stage, h->h_pinned, bytes, cudaMemcpyHostToDevice, h->stream));
+    if(is_pinned_host(src)){
+        CU(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    else{
+        if((rc = ensure_pinned(h, bytes))) return rc;
+        std::memcpy(h->h_pinned, src, bytes);
+        CU(cudaMemcpyAsync(h->d_stage, h->h_pinned, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     *dev = h->d_stage;
     return B200L2F_OK;
 }
@@ -102,6 +115,11 @@ int result_buffer(b200l2f_handle* h, void* dst, size_t bytes, int memspace, void
 int download(b200l2f_handle* h, void* dst, const void* dev, size_t bytes, int memspace){
     if(memspace == B200L2F_DEVICE) return B200L2F_OK;
     int rc;
+    if(is_pinned_host(dst)){
+        CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return B200L2F_OK;
+    }
     if((rc = ensure_pinned(h, bytes))) return rc;
     CU(cudaMemcpyAsync(h->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -217,15 +235,43 @@ int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
 }
 
 template <class Spec, bool FAST, bool UNIFORM>
-int launch_rollout_ts(b200l2f_handle* h, const RolloutArgs& a){
+int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
     auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM>;
-    static bool configured[8] = {};
+    static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::TOTAL));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, TsSmem::TOTAL));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] k_rollout_raptor_ts: occupancy API reports %d CTAs/SM on %d SMs\n", per_sm, sms);
+        if(per_sm < 3) per_sm = 3;           // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
+        capacity[dev] = per_sm * sms;        // co-resident CTAs (3 x 148 = 444 on B200)
         configured[dev] = true;
     }
-    kern<<<grid_for(a.n, BLOCK), BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
+    // persistent grid + work queue.  When the tiles do not fill an integer number of waves (e.g. 65 536 envs = 512 tiles on 444 slots), the
+    // rollout is cut into time chunks so that every slot stays busy until the end: makespan 512/444 instead of 2 tile-times.
+    const int n_tiles = grid_for(a.n, BLOCK);
+    const int cap = capacity[dev] > 0 ? capacity[dev] : n_tiles;
+    int n_chunks = 1;
+    const int forced = [](){ const char* e = std::getenv("B200L2F_CHUNKS"); return e ? std::atoi(e) : 0; }();   // test / tuning override
+    if(forced > 0) n_chunks = forced;
+    else if(n_tiles > cap && n_tiles < 6 * cap && n_tiles % cap != 0 && a.T >= 64) n_chunks = a.T / 32 < 16 ? a.T / 32 : 16;
+    if(n_chunks < 1) n_chunks = 1;
+    a.chunk_steps = a.T > 0 ? (a.T + n_chunks - 1) / n_chunks : 0;
+    a.n_chunks = a.T > 0 ? (a.T + a.chunk_steps - 1) / a.chunk_steps : 1;
+    const size_t need = 1 + (size_t)n_tiles;
+    if(need > h->sched_ints){
+        cudaFree(h->d_sched); h->d_sched = nullptr; h->sched_ints = 0;
+        CU(cudaMalloc(&h->d_sched, sizeof(int) * need));
+        h->sched_ints = need;
+    }
+    if(!h->d_acc_ret){ CU(cudaMalloc(&h->d_acc_ret, sizeof(float) * (size_t)h->n)); CU(cudaMalloc(&h->d_acc_len, sizeof(int) * (size_t)h->n)); }
+    CU(cudaMemsetAsync(h->d_sched, 0, sizeof(int) * need, h->stream));
+    a.sched = h->d_sched; a.acc_ret = h->d_acc_ret; a.acc_len = h->d_acc_len;
+    const int grid = n_tiles < cap ? n_tiles : cap;
+    kern<<<grid, BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
     LAUNCH_CHECK();
     return B200L2F_OK;
 }
@@ -300,7 +346,7 @@ int b200l2f_destroy(b200l2f_handle* h){
     if(h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_params); cudaFree(h->d_env_row);
     for(float* p : h->d_state) cudaFree(p);
-    cudaFree(h->d_tc_image);
+    cudaFree(h->d_tc_image); cudaFree(h->d_sched); cudaFree(h->d_acc_ret); cudaFree(h->d_acc_len);
     cudaFree(h->d_rng); cudaFree(h->d_flags); cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
     cudaFree(h->d_episode_step); cudaFree(h->d_episode_return); cudaFree(h->d_truncated);
     if(h->d_stage) cudaFree(h->d_stage);

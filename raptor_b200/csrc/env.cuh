@@ -75,6 +75,28 @@ __device__ __forceinline__ void load_state(EnvState<Spec>& st, const float* __re
         for(int i = 0; i < 4; i++) st.hist[i] = s[(size_t)(S_HIST + i) * n];
     }
 }
+// same through L2 only (ld.global.cg): used where another CTA of the SAME launch may have written the buffer (time-chunked scheduler)
+template <class Spec>
+__device__ __forceinline__ void load_state_cg(EnvState<Spec>& st, const float* s, size_t n){
+#pragma unroll
+    for(int i = 0; i < 13; i++) st.x[i] = __ldcg(s + (size_t)i * n);
+#pragma unroll
+    for(int i = 0; i < 4; i++) st.x[X_RPM + i] = __ldcg(s + (size_t)(S_RPM + i) * n);
+#pragma unroll
+    for(int i = 0; i < 4; i++) st.last_action[i] = __ldcg(s + (size_t)(S_LAST_ACTION + i) * n);
+#pragma unroll
+    for(int i = 0; i < 3; i++){ st.force[i] = __ldcg(s + (size_t)(S_FORCE + i) * n); st.torque[i] = __ldcg(s + (size_t)(S_TORQUE + i) * n); }
+    st.current_step = (int)__ldcg(s + (size_t)S_CURRENT_STEP * n);
+    st.traj_type = (int)__ldcg(s + (size_t)s_traj_type(Spec::H) * n);
+    if constexpr(Spec::LANGEVIN){
+#pragma unroll
+        for(int i = 0; i < 12; i++) st.lang[i] = __ldcg(s + (size_t)(s_langevin(Spec::H) + i) * n);
+    }
+    if constexpr(Spec::H == 1){
+#pragma unroll
+        for(int i = 0; i < 4; i++) st.hist[i] = __ldcg(s + (size_t)(S_HIST + i) * n);
+    }
+}
 // stores everything except the H > 1 action-history ring (maintained in place by the callers)
 template <class Spec>
 __device__ __forceinline__ void store_state(const EnvState<Spec>& st, float* __restrict__ s, size_t n){

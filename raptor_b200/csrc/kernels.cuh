@@ -238,6 +238,9 @@ struct RolloutArgs {
     float* out_returns;    // [n]
     int* out_eplen;        // [n]
     float row0[PARAMS_DIM];  // parameter row of environment 0 (source of the uniform MDP constants)
+    // time-chunked persistent scheduler (tensor-core TS kernel): sched[0] = work counter, sched[1 + tile] = chunks published for the tile
+    int* sched; int n_chunks, chunk_steps;
+    float* acc_ret; int* acc_len;   // per-environment return / (episode length << 1 | done) carried between the chunks of one rollout
 };
 
 template <class Spec>

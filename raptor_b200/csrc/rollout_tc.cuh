@@ -518,24 +518,10 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         tc::mbar_expect_tx(bar_tma, TcImage::BYTES);
         tc::tma_load_1d(sm_b, tc_image, TcImage::BYTES, bar_tma);
     }
-    const int e = blockIdx.x * BLOCK + tid;
-    const bool active = e < a.n;
     const size_t n = (size_t)a.n;
-    const size_t env = active ? (size_t)e : 0;
-    const ParamsCompiledT<UNIFORM> p = stage_dynamics_compiled<UNIFORM>(sm_dyn, a.params, n, env, a.row0);
-    EnvState<Spec> st;
-    load_state(st, a.state + env, n);
-    DynInvariants d;
-    {
-        ParamsGlobal pg{a.params + env, n};
-        dyn_invariants(d, pg, st);
-    }
-    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
-    uint64_t rng = a.rng[env];
-    int gs = a.gru_step[env];
-    float ret = 0.0f; int eplen = 0; bool done = false;
     const bool no_auto_reset = a.no_auto_reset != 0;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    __shared__ int s_item;
     constexpr uint32_t C_H_HI = 0, C_H_LO = 16, C_OBS_HI = 32, C_OBS_LO = 56, C_D1 = 80, C_X1_HI = 32, C_X1_LO = 48, C_D2 = 64;
     // write 8 values as a hi block and a lo block (8 columns each) of this thread's lane
     auto put8 = [&](uint32_t col_hi, uint32_t col_lo, const float* v){
@@ -545,12 +531,6 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         tc::tmem_st8(tmem_base + lane_off + col_hi, hi);
         tc::tmem_st8(tmem_base + lane_off + col_lo, lo);
     };
-    {
-        float h[HD];
-#pragma unroll
-        for(int j = 0; j < HD; j++) h[j] = a.hidden[(size_t)j * n + env];
-        put8(C_H_HI, C_H_LO, h); put8(C_H_HI + 8, C_H_LO + 8, h + 8);
-    }
     const uint32_t b_s = tc::smem_u32(sm_b);
     constexpr uint32_t SBO = 128;
     constexpr uint32_t IDESC16 = tc::make_idesc_tf32(128, 16), IDESC64 = tc::make_idesc_tf32(128, 64);
@@ -566,10 +546,57 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         }
     };
     tc::mbar_wait(bar_tma, 0);
-    tc::tmem_st_wait();
     __syncthreads();
 
-    for(int t = 0; t < a.T; t++){
+    // ---- persistent work loop over (tile, time-chunk) items.  Items are handed out in chunk-major order by one atomic counter; an item may
+    // ---- start once the previous chunk of the same tile has been published (that item has a smaller index, i.e. it was claimed earlier by
+    // ---- a CTA that is already running, so waiting can never deadlock).  With one chunk per tile this degenerates to a plain tile loop.
+    const int n_tiles = (a.n + BLOCK - 1) / BLOCK;
+    const int n_chunks = a.n_chunks;
+    const int total_items = n_tiles * n_chunks;
+    for(;;){
+    if(tid == 0) s_item = atomicAdd(a.sched, 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if(item >= total_items) break;
+    const int tile = item % n_tiles, chunk = item / n_tiles;
+    if(chunk > 0){
+        if(tid == 0){
+            const int* prog = a.sched + 1 + tile;
+            int v;
+            do{ asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prog) : "memory"); if(v < chunk) __nanosleep(64); } while(v < chunk);
+        }
+        __syncthreads();
+        __threadfence();   // gpu-scope fence in every thread: drops stale L1 lines of the tile's buffers (another SM wrote them during this launch)
+    }
+    const int t_begin = chunk * a.chunk_steps;
+    const int t_end = min(a.T, t_begin + a.chunk_steps);
+    const int e = tile * BLOCK + tid;
+    const bool active = e < a.n;
+    const size_t env = active ? (size_t)e : 0;
+    const ParamsCompiledT<UNIFORM> p = stage_dynamics_compiled<UNIFORM>(sm_dyn, a.params, n, env, a.row0);
+    EnvState<Spec> st;
+    load_state_cg(st, a.state + env, n);
+    DynInvariants d;
+    {
+        ParamsGlobal pg{a.params + env, n};
+        dyn_invariants(d, pg, st);
+    }
+    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
+    uint64_t rng = __ldcg(a.rng + env);
+    int gs = __ldcg(a.gru_step + env);
+    float ret = 0.0f; int eplen = 0; bool done = false;
+    if(chunk > 0){ ret = __ldcg(a.acc_ret + env); const int v = __ldcg(a.acc_len + env); eplen = v >> 1; done = (v & 1) != 0; }
+    {
+        float h[HD];
+#pragma unroll
+        for(int j = 0; j < HD; j++) h[j] = __ldcg(a.hidden + (size_t)j * n + env);
+        put8(C_H_HI, C_H_LO, h); put8(C_H_HI + 8, C_H_LO + 8, h + 8);
+    }
+    tc::tmem_st_wait();
+
+    for(int t = t_begin; t < t_end; t++){
         if(a.out_states && active && (t % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
         float obs[24];
@@ -675,17 +702,27 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
     tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
     tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
     tc::tmem_ld_wait();
+    const bool last_chunk = chunk == n_chunks - 1;
     if(active){
-        if(a.out_states && (a.T % a.state_stride) == 0)
+        if(last_chunk && a.out_states && (a.T % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(a.T / a.state_stride) * n + env) * Spec::STATE_DIM);
         store_state(st, a.state + env, n);
         a.rng[env] = rng;
 #pragma unroll
         for(int j = 0; j < HD; j++) a.hidden[(size_t)j * n + env] = hh[j] + hl[j];
         a.gru_step[env] = gs;
-        if(a.out_returns) a.out_returns[env] = ret;
-        if(a.out_eplen) a.out_eplen[env] = eplen;
+        if(last_chunk){
+            if(a.out_returns) a.out_returns[env] = ret;
+            if(a.out_eplen) a.out_eplen[env] = eplen;
+        }
+        else{ a.acc_ret[env] = ret; a.acc_len[env] = (eplen << 1) | (done ? 1 : 0); }
     }
+    if(!last_chunk){   // publish: every thread's stores, then the tile's progress counter
+        __threadfence();
+        __syncthreads();
+        if(tid == 0) atomicExch(a.sched + 1 + tile, chunk + 1);
+    }
+    }   // work loop
     tc::tc_fence_before();
     __syncthreads();
     if(warp == 0) tc::tmem_dealloc<128>(tmem_base);

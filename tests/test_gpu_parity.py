@@ -423,3 +423,26 @@ def test_ppo_collect_vs_oracle(rb, port, spec):
     close(got3[:T, :, 31], want3[:T, :, 31], 2e-3, 2e-2, "reward")
     assert np.all(got3[..., 34:] == 0)                                            # learner columns untouched
     close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
+
+
+def test_time_chunked_scheduler_is_transparent(rb):
+    """the persistent (tile, time-chunk) work queue of the tensor-core kernel must not change results: 1 chunk vs 7 chunks, bit for bit;
+    3000 envs = 24 tiles incl. a ragged one, 333 steps (chunks of unequal length), DEFAULT spec keeps its action ring in HBM across chunks"""
+    import os
+    for spec in (rb.SPEC_RAPTOR, rb.SPEC_DEFAULT):
+        res = []
+        for chunks in ("1", "7"):
+            os.environ["B200L2F_CHUNKS"] = chunks
+            try:
+                e = rb.VectorEnvironment(3000, spec)
+                e.initialize_rng(5, warmup=16)
+                e.sample_initial_state()
+                e.load_policy(gemm=rb.GEMM_TCGEN05_3XTF32)
+                o = e.rollout(333, record=("returns", "episode_length", "actions"))
+                res.append((e.get_state(), e.get_hidden(), e.get_rng(), o))
+            finally:
+                del os.environ["B200L2F_CHUNKS"]
+        (s1, (h1, g1), r1, o1), (s7, (h7, g7), r7, o7) = res
+        assert np.array_equal(s1, s7) and np.array_equal(h1, h7) and np.array_equal(g1, g7) and np.array_equal(r1, r7)
+        for k in ("returns", "episode_length", "actions"):
+            assert np.array_equal(o1[k], o7[k]), k
