@@ -164,7 +164,7 @@ def workload_config(args, world):
     return {"workload": "BASELINE configs[1]: %d envs/GPU x %d-step closed-loop rollout, Raptor GRU policy (Dense22-16/GRU16/Dense16-4), foundation-policy env spec (H=1, OBS 22, Langevin targets), per-env domain-randomised dynamics" % (args.envs_per_gpu, args.rollout_steps),
             "envs_per_gpu": args.envs_per_gpu, "rollout_steps": args.rollout_steps, "global_envs": args.envs_per_gpu * world,
             "env_steps_per_bench_step": args.envs_per_gpu * world * args.rollout_steps, "parallelism": "env-shards x%d (no collective on the rollout path)" % world,
-            "l2": "flushed (256 MiB write) before every timed launch", "gemm": "fp32 CUDA cores" if not args.tcgen05 else "tcgen05 3xTF32"}
+            "l2": "flushed (256 MiB write) before every timed launch", "gemm": "fp32 CUDA cores" if not args.tcgen05 else "tcgen05 kind::tf32, 3xTF32 split, A operand and accumulators in TMEM"}
 
 
 def main():
@@ -298,7 +298,7 @@ def main():
         fp32_ach = steps_per_s_gpu * (FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES) / 1e12
         roofline = {"bound": "tensor", "achieved": tensor_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tensor_ach / peaks["bf16_tflops_sustained"], "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long launch)",
-                    "kernel": "k_rollout_raptor_tc" if args.tcgen05 else "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,
+                    "kernel": "k_rollout_raptor_ts" if args.tcgen05 else "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,
                     "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": n * BYTES_PER_ENV_LAUNCH},
                     "fp32_issue": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
                                    "note": "dominant ceiling of this kernel (SURVEY 8d): algorithmic fp32 FLOPs / (148 SMs x 128 lanes x 2 x max SM clock); state, parameters and weights are on-chip for the whole launch"}}

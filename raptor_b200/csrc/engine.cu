@@ -234,9 +234,9 @@ int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
     return B200L2F_OK;
 }
 
-template <class Spec, bool FAST, bool UNIFORM>
+template <class Spec, bool FAST, bool UNIFORM, bool ROLLED_RK4>
 int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
-    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM>;
+    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, ROLLED_RK4>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -752,8 +752,8 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     const bool noise = (h->features & 1) != 0;
     const bool fast = !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     const bool constw = h->weights_in_constant_bank;
-    const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32;
-    if(tensor_cores && noise) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the tcgen05 variant is built for noise-free observation/action parameters");
+    // observation / action noise present: the CUDA-core kernel carries the Box-Muller draws; the tcgen05 kernels are the noise-free fast path
+    const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && !noise;
     auto go = [&](auto spec) -> int {
         using Spec = decltype(spec);
         if(tensor_cores){
@@ -761,7 +761,11 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
             // A operand in TMEM ("TS" MMAs, 63 KB smem + 128 TMEM columns per CTA -> 3 CTAs/SM) is the default; B200L2F_A=smem selects the
             // shared-memory-A variant (2 CTAs/SM).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
             static const bool a_in_tmem = [](){ const char* e = std::getenv("B200L2F_A"); return !(e && std::string(e) == "smem"); }();
-            if(a_in_tmem && fast) return uniform ? launch_rollout_ts<Spec, true, true>(h, a) : launch_rollout_ts<Spec, true, false>(h, a);
+            if(a_in_tmem && fast){
+                static const bool rolled_rk4 = [](){ const char* e = std::getenv("B200L2F_RK4"); return e && std::string(e) == "rolled"; }();
+                if(!uniform) return launch_rollout_ts<Spec, true, false, false>(h, a);
+                return rolled_rk4 ? launch_rollout_ts<Spec, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false>(h, a);
+            }
             static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
             if(!fast) return launch_rollout_tc<Spec, false, false, true>(h, a);
             if(!uniform) return launch_rollout_tc<Spec, true, false, true>(h, a);

@@ -169,7 +169,7 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
     }
 }
 // env_step twin for the compiled block (no observation/action noise in this variant; Langevin target as in env_step)
-template <class Spec, class PC>
+template <class Spec, bool ROLLED_RK4 = false, class PC>
 __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
                                                   float* __restrict__ hist_ptr, size_t n){
     float setpoint[4];
@@ -179,6 +179,21 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
     const float dt = d.dt;
     const float dt2 = dt / 2.0f, dt3 = dt / 3.0f, dt6 = dt / 6.0f;
     float k[X_DIM], tmp[X_DIM], acc[X_DIM];
+    if constexpr(ROLLED_RK4){   // four stages as one loop body (a quarter of the code, same arithmetic and accumulation order)
+#pragma unroll
+        for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i]; tmp[i] = st.x[i]; }
+#pragma unroll 1
+        for(int s = 0; s < 4; s++){
+            dynamics_compiled(p, d, tmp, setpoint, k);
+            const float wa = (s == 0 || s == 3) ? dt6 : dt3;
+            const float wt = (s == 2) ? dt : dt2;
+#pragma unroll
+            for(int i = 0; i < X_DIM; i++){ acc[i] += wa * k[i]; tmp[i] = st.x[i] + wt * k[i]; }
+        }
+#pragma unroll
+        for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i];
+    }
+    else{
     dynamics_compiled(p, d, st.x, setpoint, k);
 #pragma unroll
     for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i] + dt6 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
@@ -191,6 +206,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
     dynamics_compiled(p, d, tmp, setpoint, k);
 #pragma unroll
     for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i] + dt6 * k[i];
+    }
     {
         float nrm = 0.0f;
 #pragma unroll
@@ -494,7 +510,7 @@ struct TsSmem {
     static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
     static constexpr int TOTAL = BAR + 32;
 };
-template <class Spec, bool FAST, bool UNIFORM>
+template <class Spec, bool FAST, bool UNIFORM, bool ROLLED_RK4>
 __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     constexpr int HD = 16;
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -690,7 +706,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        if(Spec::H == 1 || active) env_step_compiled<Spec>(st, p, d, act, rng, hist_ptr, n);
+        if(Spec::H == 1 || active) env_step_compiled<Spec, ROLLED_RK4>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;

@@ -197,7 +197,7 @@ class VectorEnvironment:
 
     # ---- actor
     def load_policy(self, blob=None, arch=L.POLICY_RAPTOR_GRU, input_dim=22, hidden_dim=16, output_dim=4, standardize=0, head=L.HEAD_IDENTITY,
-                    gru_sequence_length=500, gemm=L.GEMM_FP32_CUDA_CORES):
+                    gru_sequence_length=500, gemm=L.GEMM_TCGEN05_3XTF32):
         blob = raptor_policy_blob() if blob is None else np.ascontiguousarray(blob, np.float32)
         desc = L.PolicyDesc(arch, input_dim, hidden_dim, output_dim, standardize, head, gru_sequence_length, gemm)
         self._check(self._lib.b200l2f_policy_load(self._h, ctypes.byref(desc), blob.ctypes.data, blob.size))
