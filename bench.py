@@ -296,7 +296,12 @@ def main():
         hbm_ach = n * BYTES_PER_ENV_LAUNCH / per_launch_s / 1e9
         fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
         fp32_ach = steps_per_s_gpu * (FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES) / 1e12
-        roofline = {"bound": "tensor", "achieved": tensor_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tensor_ach / peaks["bf16_tflops_sustained"], "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` capture of this exact configuration
+        # (39.44 MB read + 1.98 MB written: parameters / state in, state out; the per-chunk hand-over lives in the 126 MB L2)
+        traffic, traffic_src = None, None
+        if args.tcgen05 and n == 65536 and T == 1000 and not args.accurate_math:
+            traffic, traffic_src = 41.42e6, "profiles/r01_ncu_k_rollout_raptor_ts_T1000_default_bench.txt"
+        roofline = {"bound": "tensor", "achieved": tensor_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tensor_ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long launch)",
                     "kernel": "k_rollout_raptor_ts" if args.tcgen05 else "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,
                     "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": n * BYTES_PER_ENV_LAUNCH},

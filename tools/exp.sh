@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-for r in unrolled rolled; do for n in 65536 1048576; do
-  T=1000; if [ $n = 1048576 ]; then T=200; fi
-  echo "== rk4=$r n=$n" | tee -a gpurun_out/exp11.log
-  B200L2F_RK4=$r timeout -s KILL 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --envs-per-gpu $n --rollout-steps $T 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['fp32_issue']['frac'], d['e2e']['value'], d['mean_episode_return'])" | tee -a gpurun_out/exp11.log
-done; done
+(timeout -s KILL 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) | tee gpurun_out/pytest_gpu12.log
+(timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3) | tee gpurun_out/smoke2.log
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:k_rollout -c 1 -o gpurun_out/prof_v4_ts_T1000 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_v4b.log 2>&1
