@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "rollout_tc.cuh"
 #include "mlp.cuh"
+#include "mlp_tc.cuh"
 
 using namespace b200l2f;
 
@@ -46,6 +47,7 @@ struct b200l2f_handle {
     int* d_sched = nullptr; size_t sched_ints = 0;     // work counter + per-tile progress of the time-chunked scheduler
     float* d_acc_ret = nullptr; int* d_acc_len = nullptr;
     float* d_tc_image = nullptr;     // tensor-core weight image (hi/lo planes of the three B operands, TMA source)
+    float* d_mlp_tc_image = nullptr; // same for an MLP actor (MlpTcImage<IN, OUT>), null when the actor has no tensor-core instantiation
     std::vector<float> h_image;      // k-major actor image passed by value to the fused kernels (constant-bank weights)
     bool weights_in_constant_bank = false; bool rolled = false;
     // PPO runner bookkeeping (rl/components/on_policy_runner/on_policy_runner.h: episode_step, episode_return, truncated)
@@ -234,26 +236,12 @@ int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
     return B200L2F_OK;
 }
 
-template <class Spec, bool FAST, bool UNIFORM, bool ROLLED_RK4>
-int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
-    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, ROLLED_RK4>;
-    static bool configured[8] = {}; static int capacity[8] = {};
-    int dev = h->cfg.device & 7;
-    if(!configured[dev]){
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::TOTAL));
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        int per_sm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, TsSmem::TOTAL));
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-        if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] k_rollout_raptor_ts: occupancy API reports %d CTAs/SM on %d SMs\n", per_sm, sms);
-        if(per_sm < 3) per_sm = 3;           // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
-        capacity[dev] = per_sm * sms;        // co-resident CTAs (3 x 148 = 444 on B200)
-        configured[dev] = true;
-    }
-    // persistent grid + work queue.  When the tiles do not fill an integer number of waves (e.g. 65 536 envs = 512 tiles on 444 slots), the
-    // rollout is cut into time chunks so that every slot stays busy until the end: makespan 512/444 instead of 2 tile-times.
+// persistent grid + work queue of the tcgen05 rollout kernels.  When the tiles do not fill an integer number of waves (e.g. 65 536 envs =
+// 512 tiles on 444 slots), the rollout is cut into time chunks so that every slot stays busy until the end: makespan 512/444 instead of 2
+// tile-times.  Fills a.sched / n_chunks / chunk_steps / acc_*, returns the grid size in *grid.
+int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid){
     const int n_tiles = grid_for(a.n, BLOCK);
-    const int cap = capacity[dev] > 0 ? capacity[dev] : n_tiles;
+    const int cap = cap_in > 0 ? cap_in : n_tiles;
     int n_chunks = 1;
     const int forced = [](){ const char* e = std::getenv("B200L2F_CHUNKS"); return e ? std::atoi(e) : 0; }();   // test / tuning override
     if(forced > 0) n_chunks = forced;
@@ -270,8 +258,51 @@ int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
     if(!h->d_acc_ret){ CU(cudaMalloc(&h->d_acc_ret, sizeof(float) * (size_t)h->n)); CU(cudaMalloc(&h->d_acc_len, sizeof(int) * (size_t)h->n)); }
     CU(cudaMemsetAsync(h->d_sched, 0, sizeof(int) * need, h->stream));
     a.sched = h->d_sched; a.acc_ret = h->d_acc_ret; a.acc_len = h->d_acc_len;
-    const int grid = n_tiles < cap ? n_tiles : cap;
+    *grid = n_tiles < cap ? n_tiles : cap;
+    return B200L2F_OK;
+}
+
+template <class Spec, bool FAST, bool UNIFORM, bool ROLLED_RK4>
+int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
+    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, ROLLED_RK4>;
+    static bool configured[8] = {}; static int capacity[8] = {};
+    int dev = h->cfg.device & 7;
+    if(!configured[dev]){
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::TOTAL));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, TsSmem::TOTAL));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] k_rollout_raptor_ts: occupancy API reports %d CTAs/SM on %d SMs\n", per_sm, sms);
+        if(per_sm < 3) per_sm = 3;           // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
+        capacity[dev] = per_sm * sms;        // co-resident CTAs (3 x 148 = 444 on B200)
+        configured[dev] = true;
+    }
+    int grid = 0, rc;
+    if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
     kern<<<grid, BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+
+template <class Spec, int OUT, bool UNIFORM>
+int launch_rollout_mlp_ts(b200l2f_handle* h, RolloutArgs a){
+    constexpr int IN = Spec::OBS_DIM;
+    using SM = MlpTsSmem<IN, OUT>;
+    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM>;
+    static bool configured[8] = {}; static int capacity[8] = {};
+    int dev = h->cfg.device & 7;
+    if(!configured[dev]){
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL_ROLLOUT));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int sms = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        capacity[dev] = 2 * sms;             // design point: ~92 KB smem and 256 TMEM columns per CTA -> 2 CTAs/SM
+        configured[dev] = true;
+    }
+    int grid = 0, rc;
+    if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
+    kern<<<grid, BLOCK, SM::TOTAL_ROLLOUT, h->stream>>>(a, h->d_mlp_tc_image);
     LAUNCH_CHECK();
     return B200L2F_OK;
 }
@@ -346,7 +377,7 @@ int b200l2f_destroy(b200l2f_handle* h){
     if(h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_params); cudaFree(h->d_env_row);
     for(float* p : h->d_state) cudaFree(p);
-    cudaFree(h->d_tc_image); cudaFree(h->d_sched); cudaFree(h->d_acc_ret); cudaFree(h->d_acc_len);
+    cudaFree(h->d_tc_image); cudaFree(h->d_mlp_tc_image); cudaFree(h->d_sched); cudaFree(h->d_acc_ret); cudaFree(h->d_acc_len);
     cudaFree(h->d_rng); cudaFree(h->d_flags); cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
     cudaFree(h->d_episode_step); cudaFree(h->d_episode_return); cudaFree(h->d_truncated);
     if(h->d_stage) cudaFree(h->d_stage);
@@ -602,6 +633,23 @@ int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
     CU(cudaMalloc(&h->d_gru_step, sizeof(int) * (size_t)h->n));
     if(desc->arch == B200L2F_POLICY_MLP){
         h->pol = *desc; h->blob_floats = n_floats; h->policy_loaded = true;
+        cudaFree(h->d_mlp_tc_image); h->d_mlp_tc_image = nullptr;
+        if(h->kind != KIND_DEFAULT){   // tensor-core operand image (H = 1 specs: the observation fits one K <= 32 operand)
+            auto build = [&](auto in_c, auto out_c) -> int {
+                constexpr int IN = decltype(in_c)::value, OUT = decltype(out_c)::value;
+                std::vector<float> img(MlpTcImage<IN, OUT>::SIZE);
+                build_mlp_tc_image_host<IN, OUT>(img.data(), blob, desc->standardize != 0, desc->head == B200L2F_HEAD_PPO_GAUSSIAN);
+                CU(cudaMalloc(&h->d_mlp_tc_image, MlpTcImage<IN, OUT>::BYTES));
+                CU(cudaMemcpy(h->d_mlp_tc_image, img.data(), MlpTcImage<IN, OUT>::BYTES, cudaMemcpyHostToDevice));
+                return (int)B200L2F_OK;
+            };
+            using I22 = std::integral_constant<int, 22>; using I26 = std::integral_constant<int, 26>;
+            using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
+            int brc;
+            if(h->obs_dim == 22) brc = desc->output_dim == 8 ? build(I22{}, O8{}) : build(I22{}, O4{});
+            else brc = desc->output_dim == 8 ? build(I26{}, O8{}) : build(I26{}, O4{});
+            if(brc) return brc;
+        }
         CU(cudaMemsetAsync(h->d_hidden, 0, sizeof(float) * desc->hidden_dim * (size_t)h->n, h->stream));
         CU(cudaMemsetAsync(h->d_gru_step, 0, sizeof(int) * (size_t)h->n, h->stream));
         return B200L2F_OK;
@@ -790,7 +838,17 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
         };
         using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
         const bool o8 = h->pol.output_dim == 8;
-        rc = dispatch_spec(h, [&](auto spec){ return o8 ? gomlp(spec, O8{}) : gomlp(spec, O4{}); });
+        // tcgen05 path: H = 1 specs, no observation / action noise (as for the GRU actor), default math flags
+        if(tensor_cores && fast && h->d_mlp_tc_image && h->kind != KIND_DEFAULT){
+            const bool uniform = (h->features & 2) == 0;
+            auto gots = [&](auto spec) -> int {
+                using Spec = decltype(spec);
+                if(o8) return uniform ? launch_rollout_mlp_ts<Spec, 8, true>(h, a) : launch_rollout_mlp_ts<Spec, 8, false>(h, a);
+                return uniform ? launch_rollout_mlp_ts<Spec, 4, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, false>(h, a);
+            };
+            rc = h->kind == KIND_RAPTOR ? gots(SpecRaptor{}) : gots(SpecTeacher{});
+        }
+        else rc = dispatch_spec(h, [&](auto spec){ return o8 ? gomlp(spec, O8{}) : gomlp(spec, O4{}); });
     }
     else rc = h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
     if(rc) return rc;
@@ -838,7 +896,29 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
         LAUNCH_CHECK();
         return (int)B200L2F_OK;
     };
-    if(h->kind == KIND_RAPTOR) rc = h->dr ? go(SpecRaptor{}, std::true_type{}) : go(SpecRaptor{}, std::false_type{});
+    auto gots = [&](auto spec, auto dr_c) -> int {
+        using Spec = decltype(spec);
+        constexpr bool DR = decltype(dr_c)::value;
+        using SM = MlpTsSmem<Spec::OBS_DIM, 4>;
+        auto kern = k_collect_ts<Spec, DR>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL_COLLECT));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int sms = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        if(!h->d_sched){ CU(cudaMalloc(&h->d_sched, sizeof(int) * 64)); h->sched_ints = 64; }
+        CU(cudaMemsetAsync(h->d_sched, 0, sizeof(int), h->stream));
+        const int n_tiles = grid_for(a.n, BLOCK);
+        const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;    // ~110 KB smem, 256 TMEM columns per CTA -> 2 CTAs/SM, persistent tile loop
+        kern<<<grid, BLOCK, SM::TOTAL_COLLECT, h->stream>>>(a, h->d_mlp_tc_image, h->d_sched);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    };
+    const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
+    if(tensor_cores){
+        if(h->kind == KIND_RAPTOR) rc = h->dr ? gots(SpecRaptor{}, std::true_type{}) : gots(SpecRaptor{}, std::false_type{});
+        else rc = h->dr ? gots(SpecTeacher{}, std::true_type{}) : gots(SpecTeacher{}, std::false_type{});
+    }
+    else if(h->kind == KIND_RAPTOR) rc = h->dr ? go(SpecRaptor{}, std::true_type{}) : go(SpecRaptor{}, std::false_type{});
     else rc = h->dr ? go(SpecTeacher{}, std::true_type{}) : go(SpecTeacher{}, std::false_type{});
     if(rc) return rc;
     h->features_dirty = true;   // resets rewrite parameter columns

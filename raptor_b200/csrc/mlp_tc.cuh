@@ -1,0 +1,424 @@
+// raptor_b200/csrc/mlp_tc.cuh -- MLP actors (SAC teacher / PPO, hidden 64) on the sm_100a tensor cores, for the H = 1 specs (RAPTOR, TEACHER):
+//   k_rollout_mlp_ts   closed-loop rollout with a deterministic MLP actor          (BASELINE config 3; CUDA-core twin: k_rollout_mlp)
+//   k_collect_ts       PPO collection with on-device auto-reset and write-back     (BASELINE config 4; CUDA-core twin: k_collect)
+// Reference semantics are those of mlp.cuh (INC/nn_models/mlp/network.h:15-51, standardize, squash, on_policy_runner) -- only the three dense
+// layers move: each is one [128 envs] x [K] x [N] GEMM per CTA and step, tcgen05.mma kind::tf32 with the 3xTF32 split
+// (A_hi B_hi + A_hi B_lo + A_lo B_hi, fp32 accumulate), the A operand (activations, lane = environment) and the accumulators in tensor
+// memory, the weight image (hi/lo planes, canonical K-major core-matrix order) in shared memory, loaded once per CTA by a TMA bulk copy.
+//
+// TMEM plan (256 columns per CTA, 2 CTAs/SM):      layer 1: A1 hi [0,32)   lo [32,64)    -> D1 [64,128)
+//                                                  layer 2: A2 hi [128,192) lo [192,256) -> D2 [0,64)      (A1 is dead)
+//                                                  layer 3: A3 hi [64,128)  lo [128,192) -> D3 [192,208)   (D1, A2 are dead)
+// Layer 1 carries its bias as an extra K column (A = 1.0); the biases of layers 2 and 3 (K = 64 is full) are added in the epilogues.
+#pragma once
+#include "mlp.cuh"
+#include "rollout_tc.cuh"
+
+namespace b200l2f {
+
+template <int IN, int OUT>
+struct MlpTcImage {
+    static constexpr int HD = MLP_HD;
+    static constexpr int K1 = (IN + 1 + 7) / 8 * 8;   // observation + bias column, padded to the instruction K
+    static constexpr int N3 = 16;                     // smallest N of an M = 128 instruction
+    static_assert(K1 <= 32 && OUT <= N3, "TMEM plan");
+    static constexpr int B1_HI = 0, B1_LO = B1_HI + K1 * HD;
+    static constexpr int B2_HI = B1_LO + K1 * HD, B2_LO = B2_HI + HD * HD;
+    static constexpr int B3_HI = B2_LO + HD * HD, B3_LO = B3_HI + HD * N3;
+    static constexpr int MEAN = B3_LO + HD * N3, PREC = MEAN + K1;
+    static constexpr int BIAS2 = PREC + K1, BIAS3 = BIAS2 + HD, LOG_STD = BIAS3 + N3;
+    static constexpr int SIZE = LOG_STD + 4;
+    static constexpr int BYTES = SIZE * 4;
+    static_assert(BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+};
+// blob (include/b200_l2f.h MLP order; standardize / log_std blocks optional) -> image
+template <int IN, int OUT>
+inline void build_mlp_tc_image_host(float* img, const float* blob, bool has_std, bool has_log_std){
+    using I = MlpTcImage<IN, OUT>;
+    constexpr int HD = MLP_HD;
+    for(int i = 0; i < I::SIZE; i++) img[i] = 0.0f;
+    const float* b = blob;
+    for(int i = 0; i < IN; i++){ img[I::MEAN + i] = has_std ? b[i] : 0.0f; img[I::PREC + i] = has_std ? b[IN + i] : 1.0f; }
+    if(has_std) b += 2 * IN;
+    const float* W1 = b; const float* b1 = W1 + HD * IN; const float* W2 = b1 + HD; const float* b2 = W2 + HD * HD;
+    const float* W3 = b2 + HD; const float* b3 = W3 + OUT * HD; const float* ls = b3 + OUT;
+    auto put = [&](int hi_base, int lo_base, int N, int n, int k, float v){
+        float hi, lo; tc_split_host(v, hi, lo);
+        const int idx = (k / 4) * N * 4 + n * 4 + (k % 4);
+        img[hi_base + idx] = hi; img[lo_base + idx] = lo;
+    };
+    for(int n = 0; n < HD; n++){
+        for(int k = 0; k < IN; k++) put(I::B1_HI, I::B1_LO, HD, n, k, W1[n * IN + k]);
+        put(I::B1_HI, I::B1_LO, HD, n, IN, b1[n]);
+        for(int k = 0; k < HD; k++) put(I::B2_HI, I::B2_LO, HD, n, k, W2[n * HD + k]);
+        img[I::BIAS2 + n] = b2[n];
+    }
+    for(int n = 0; n < OUT; n++){
+        for(int k = 0; k < HD; k++) put(I::B3_HI, I::B3_LO, I::N3, n, k, W3[n * HD + k]);
+        img[I::BIAS3 + n] = b3[n];
+    }
+    for(int i = 0; i < 4; i++) img[I::LOG_STD + i] = has_log_std ? ls[i] : 0.0f;
+}
+
+// per-thread view of the CTA's tensor-core state
+struct TsCtx {
+    const float* sm_b;        // weight image in shared memory
+    uint32_t b_s;             // its shared-memory address
+    uint32_t tmem_base;       // allocation base (lane 0)
+    uint32_t tmem_lane;       // base + this warp's lane offset: what tcgen05.ld / st address
+    uint64_t* bar_mma;
+    uint32_t phase;
+    int tid;
+};
+__device__ __forceinline__ void ts_put8(uint32_t t_hi, uint32_t t_lo, const float* v){
+    float hi[8], lo[8];
+#pragma unroll
+    for(int i = 0; i < 8; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+    tc::tmem_st8(t_hi, hi);
+    tc::tmem_st8(t_lo, lo);
+}
+// ksteps instructions of K = 8: A columns [a_hi + 8 s, +8) / [a_lo + 8 s, +8) against the B chunk pair s (issued by one thread)
+__device__ __forceinline__ void ts_issue_gemm(const TsCtx& c, uint32_t dcol, uint32_t a_hi, uint32_t a_lo, int ksteps, int b_hi_off, int b_lo_off, uint32_t N, uint32_t idesc){
+    uint32_t acc = 0;
+    for(int s = 0; s < ksteps; s++){
+        const uint64_t bhi = tc::make_smem_desc(c.b_s + b_hi_off * 4 + s * 2 * N * 16, N * 16, 128);
+        const uint64_t blo = tc::make_smem_desc(c.b_s + b_lo_off * 4 + s * 2 * N * 16, N * 16, 128);
+        tc::mma_tf32_ts(c.tmem_base + dcol, c.tmem_base + a_hi + 8 * s, bhi, idesc, acc); acc = 1;
+        tc::mma_tf32_ts(c.tmem_base + dcol, c.tmem_base + a_hi + 8 * s, blo, idesc, 1);
+        tc::mma_tf32_ts(c.tmem_base + dcol, c.tmem_base + a_lo + 8 * s, bhi, idesc, 1);
+    }
+}
+// the A operand of the next GEMM is complete in TMEM: hand it to the tensor core, wait for the accumulator.  Called by ALL threads of the CTA.
+template <class F>
+__device__ __forceinline__ void ts_run(TsCtx& c, F&& issue){
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncthreads();
+    if(c.tid == 0){
+        tc::tc_fence_after();
+        issue();
+        tc::mma_commit(c.bar_mma);
+    }
+    tc::mbar_wait(c.bar_mma, c.phase); c.phase ^= 1;
+    tc::tc_fence_after();
+}
+
+// obs: RAW observation (IN values, registers) -> out[OUT] (pre-head outputs).  Called by all 128 threads (inactive lanes compute garbage rows).
+template <int IN, int OUT>
+__device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict__ obs, float* __restrict__ out){
+    using I = MlpTcImage<IN, OUT>;
+    constexpr int HD = MLP_HD, K1 = I::K1;
+    constexpr uint32_t A1_HI = 0, A1_LO = 32, D1 = 64, A2_HI = 128, A2_LO = 192, D2 = 0, A3_HI = 64, A3_LO = 128, D3 = 192;
+    constexpr uint32_t IDESC64 = tc::make_idesc_tf32(128, 64), IDESC16 = tc::make_idesc_tf32(128, 16);
+    {
+        float x[K1];
+#pragma unroll
+        for(int k = 0; k < IN; k++){   // standardize: (x - mean) [* precision unless it is 0]
+            float v = obs[k] - c.sm_b[I::MEAN + k];
+            const float pr = c.sm_b[I::PREC + k];
+            if(pr != 0.0f) v *= pr;
+            x[k] = v;
+        }
+        x[IN] = 1.0f;                  // bias column
+#pragma unroll
+        for(int k = IN + 1; k < K1; k++) x[k] = 0.0f;
+#pragma unroll
+        for(int g = 0; g < K1 / 8; g++) ts_put8(c.tmem_lane + A1_HI + 8 * g, c.tmem_lane + A1_LO + 8 * g, x + 8 * g);
+    }
+    ts_run(c, [&](){ ts_issue_gemm(c, D1, A1_HI, A1_LO, K1 / 8, I::B1_HI, I::B1_LO, HD, IDESC64); });
+#pragma unroll
+    for(int g = 0; g < HD / 32; g++){
+        float v[32];
+        tc::tmem_ld16(c.tmem_lane + D1 + 32 * g, v);
+        tc::tmem_ld16(c.tmem_lane + D1 + 32 * g + 16, v + 16);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for(int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.0f);
+#pragma unroll
+        for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A2_HI + 32 * g + 8 * q, c.tmem_lane + A2_LO + 32 * g + 8 * q, v + 8 * q);
+    }
+    ts_run(c, [&](){ ts_issue_gemm(c, D2, A2_HI, A2_LO, HD / 8, I::B2_HI, I::B2_LO, HD, IDESC64); });
+#pragma unroll
+    for(int g = 0; g < HD / 32; g++){
+        float v[32];
+        tc::tmem_ld16(c.tmem_lane + D2 + 32 * g, v);
+        tc::tmem_ld16(c.tmem_lane + D2 + 32 * g + 16, v + 16);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for(int j4 = 0; j4 < 8; j4++){
+            const float4 b = *reinterpret_cast<const float4*>(c.sm_b + I::BIAS2 + 32 * g + 4 * j4);
+            v[4 * j4] = fmaxf(v[4 * j4] + b.x, 0.0f); v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b.y, 0.0f);
+            v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b.z, 0.0f); v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b.w, 0.0f);
+        }
+#pragma unroll
+        for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A3_HI + 32 * g + 8 * q, c.tmem_lane + A3_LO + 32 * g + 8 * q, v + 8 * q);
+    }
+    ts_run(c, [&](){ ts_issue_gemm(c, D3, A3_HI, A3_LO, HD / 8, I::B3_HI, I::B3_LO, I::N3, IDESC16); });
+    {
+        float v[16];
+        tc::tmem_ld16(c.tmem_lane + D3, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for(int j = 0; j < OUT; j++) out[j] = v[j] + c.sm_b[I::BIAS3 + j];
+    }
+}
+
+// full observation of an H = 1 spec in registers (same values and RNG order as observe_to_scratch)
+template <class Spec, bool NOISE, class P>
+__device__ __forceinline__ void observe_regs(const EnvState<Spec>& st, const P& p, uint64_t& rng, float* __restrict__ o){
+    static_assert(Spec::H == 1, "register observation: H = 1 specs");
+    observe18<Spec, NOISE>(st, p, rng, o);
+#pragma unroll
+    for(int i = 0; i < 4; i++) o[18 + i] = st.hist[i];
+    if constexpr(Spec::OBS_LAYOUT == OBS_TEACHER){
+#pragma unroll
+        for(int i = 0; i < 4; i++) o[22 + i] = (st.x[X_RPM + i] - p[P_ACT_MIN]) / (p[P_ACT_MAX] - p[P_ACT_MIN]) * 2.0f - 1.0f;
+    }
+}
+
+template <int IN, int OUT>
+struct MlpTsSmem {
+    static constexpr int B = 0;
+    static constexpr int DYN = (MlpTcImage<IN, OUT>::BYTES + 127) / 128 * 128;
+    static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
+    static constexpr int SLAB = BAR + 32;                                 // collect only: per-warp [32][W] write-back windows
+    static constexpr int TOTAL_ROLLOUT = SLAB;
+    static constexpr int TOTAL_COLLECT = SLAB + 4 * 32 * (IN + 12) * 4;
+};
+
+// CTA prologue shared by both kernels: barriers, TMEM allocation, weight image by TMA.  Returns the context; every thread must call it.
+template <int IN, int OUT>
+__device__ __forceinline__ TsCtx mlp_ts_prologue(unsigned char* smraw, const float* __restrict__ tc_image){
+    using SM = MlpTsSmem<IN, OUT>;
+    float* sm_b = reinterpret_cast<float*>(smraw + SM::B);
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + SM::BAR);
+    uint64_t* bar_mma = bar_tma + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if(tid == 0){
+        tc::mbar_init(bar_tma, 1);
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_fence_init();
+    }
+    if(warp == 0) tc::tmem_alloc<256>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    TsCtx c;
+    c.sm_b = sm_b; c.b_s = tc::smem_u32(sm_b); c.tmem_base = *tmem_slot; c.tmem_lane = c.tmem_base + ((uint32_t)(warp * 32) << 16);
+    c.bar_mma = bar_mma; c.phase = 0; c.tid = tid;
+    if(tid == 0){
+        tc::mbar_expect_tx(bar_tma, MlpTcImage<IN, OUT>::BYTES);
+        tc::tma_load_1d(sm_b, tc_image, MlpTcImage<IN, OUT>::BYTES, bar_tma);
+    }
+    tc::mbar_wait(bar_tma, 0);
+    __syncthreads();
+    return c;
+}
+__device__ __forceinline__ void mlp_ts_epilogue(const TsCtx& c){
+    tc::tc_fence_before();
+    __syncthreads();
+    if((c.tid >> 5) == 0) tc::tmem_dealloc<256>(c.tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// closed-loop rollout, deterministic MLP actor (head identity or squash-eval), persistent (tile, time-chunk) work queue as in
+// k_rollout_raptor_ts (the actor is stateless, so a chunk hands over the environment state and the episode accumulators only)
+// ---------------------------------------------------------------------------------------------------------------
+template <class Spec, int OUT, bool UNIFORM>
+__global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
+    constexpr int IN = Spec::OBS_DIM;
+    using SM = MlpTsSmem<IN, OUT>;
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    float* sm_dyn = reinterpret_cast<float*>(smraw + SM::DYN);
+    TsCtx c = mlp_ts_prologue<IN, OUT>(smraw, tc_image);
+    const int tid = threadIdx.x;
+    const size_t n = (size_t)a.n;
+    __shared__ int s_item;
+    const int n_tiles = (a.n + BLOCK - 1) / BLOCK;
+    const int n_chunks = a.n_chunks;
+    const int total_items = n_tiles * n_chunks;
+    for(;;){
+    if(tid == 0) s_item = atomicAdd(a.sched, 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if(item >= total_items) break;
+    const int tile = item % n_tiles, chunk = item / n_tiles;
+    if(chunk > 0){
+        if(tid == 0){
+            const int* prog = a.sched + 1 + tile;
+            int v;
+            do{ asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prog) : "memory"); if(v < chunk) __nanosleep(64); } while(v < chunk);
+        }
+        __syncthreads();
+        __threadfence();
+    }
+    const int t_begin = chunk * a.chunk_steps;
+    const int t_end = min(a.T, t_begin + a.chunk_steps);
+    const int e = tile * BLOCK + tid;
+    const bool active = e < a.n;
+    const size_t env = active ? (size_t)e : 0;
+    const ParamsCompiledT<UNIFORM> p = stage_dynamics_compiled<UNIFORM>(sm_dyn, a.params, n, env, a.row0);
+    EnvState<Spec> st;
+    load_state_cg(st, a.state + env, n);
+    DynInvariants d;
+    {
+        ParamsGlobal pg{a.params + env, n};
+        dyn_invariants(d, pg, st);
+    }
+    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
+    uint64_t rng = __ldcg(a.rng + env);
+    float ret = 0.0f; int eplen = 0; bool done = false;
+    if(chunk > 0){ ret = __ldcg(a.acc_ret + env); const int v = __ldcg(a.acc_len + env); eplen = v >> 1; done = (v & 1) != 0; }
+
+    for(int t = t_begin; t < t_end; t++){
+        if(a.out_states && active && (t % a.state_stride) == 0)
+            write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
+        float obs[IN];
+        observe_regs<Spec, false>(st, p, rng, obs);
+        if(a.out_obs && active){
+            float* row = a.out_obs + ((size_t)t * n + env) * IN;
+#pragma unroll
+            for(int i = 0; i < IN; i++) row[i] = obs[i];
+        }
+        float o[OUT], act[4];
+        mlp_forward_ts<IN, OUT>(c, obs, o);
+#pragma unroll
+        for(int i = 0; i < 4; i++) act[i] = OUT == 8 ? tanhf(o[i]) : o[i];
+        if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
+        RewardInputs ri;
+        reward_inputs(ri, st);
+        env_step_compiled<Spec>(st, p, d, act, rng, hist_ptr, n);
+        const bool term = env_terminated(p, st.x);
+        const float rw = env_reward(p, ri, act, st.x, term, d.dt);
+        if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
+        if(a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
+        if(!done){ ret += rw; eplen += 1; done = term; }
+    }
+    const bool last_chunk = chunk == n_chunks - 1;
+    if(active){
+        if(last_chunk && a.out_states && (a.T % a.state_stride) == 0)
+            write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(a.T / a.state_stride) * n + env) * Spec::STATE_DIM);
+        store_state(st, a.state + env, n);
+        a.rng[env] = rng;
+        if(last_chunk){
+            if(a.out_returns) a.out_returns[env] = ret;
+            if(a.out_eplen) a.out_eplen[env] = eplen;
+        }
+        else{ a.acc_ret[env] = ret; a.acc_len[env] = (eplen << 1) | (done ? 1 : 0); }
+    }
+    if(!last_chunk){
+        __threadfence();
+        __syncthreads();
+        if(tid == 0) atomicExch(a.sched + 1 + tile, chunk + 1);
+    }
+    }   // work loop
+    mlp_ts_epilogue(c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PPO collection (rl_tools::collect), same dataset contract as k_collect.  One tile per CTA visit (persistent tile loop); an environment's
+// reset (parameter / state re-sampling) is divergent CUDA-core work inside the step loop, the three GEMMs are CTA-collective and therefore
+// sit outside every lane-dependent branch.
+// ---------------------------------------------------------------------------------------------------------------
+template <class Spec, bool DR>
+__global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__ CollectArgs a, const float* __restrict__ tc_image, int* __restrict__ sched){
+    constexpr int IN = Spec::OBS_DIM, OUT = 4;
+    constexpr int D = IN + 15, W = IN + 12;
+    using SM = MlpTsSmem<IN, OUT>;
+    using I = MlpTcImage<IN, OUT>;
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    float* sm_dyn = reinterpret_cast<float*>(smraw + SM::DYN);
+    TsCtx c = mlp_ts_prologue<IN, OUT>(smraw, tc_image);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* slab = reinterpret_cast<float*>(smraw + SM::SLAB) + (size_t)warp * 32 * W;   // private to this warp
+    const size_t n = (size_t)a.n;
+    __shared__ int s_item;
+    const int n_tiles = (a.n + BLOCK - 1) / BLOCK;
+    for(;;){
+    if(tid == 0) s_item = atomicAdd(sched, 1);
+    __syncthreads();
+    const int tile = s_item;
+    __syncthreads();
+    if(tile >= n_tiles) break;
+    const int e = tile * BLOCK + tid;
+    const bool active = e < a.n;
+    const size_t env = active ? (size_t)e : 0;
+    ParamsCompiledT<false, false> p = stage_dynamics_compiled<false, false>(sm_dyn, a.params, n, env, nullptr);
+    EnvState<Spec> st;
+    load_state(st, a.state + env, n);
+    DynInvariants d;
+    {
+        ParamsRW pg{a.params + env, n};
+        dyn_invariants(d, pg, st);
+    }
+    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
+    uint64_t rng = a.rng[env];
+    int ep_step = a.episode_step[env]; float ep_ret = a.episode_return[env]; bool truncated = a.truncated[env] != 0;
+    const int warp_env0 = tile * BLOCK + warp * 32;
+    const int rows_valid = min(32, a.n - warp_env0);
+
+    for(int t = 0; t <= a.T; t++){
+        const bool last = t == a.T;                       // final observation only (operations_generic.h:122-129)
+        if(!last && truncated && active){                 // prologue (operations_generic_per_env.h:17-25): re-sample parameters and state
+            truncated = false; ep_step = 0; ep_ret = 0.0f;
+            ParamsRW prw{a.params + env, n};
+            if(!sample_parameters<DR>(a.env_row, prw, rng)) atomicExch(a.error_flag, 1);
+            p = stage_dynamics_compiled<false, false>(sm_dyn, a.params, n, env, nullptr);   // this thread's column only
+            sample_state(st, prw, rng, hist_ptr, n);
+            dyn_invariants(d, prw, st);
+        }
+        float obs[IN];
+        observe_regs<Spec, true>(st, p, rng, obs);
+        float vals[12];
+        if(!last){                                        // uniform across the CTA
+            float mean[OUT], act[4];
+            mlp_forward_ts<IN, OUT>(c, obs, mean);
+            float lp = 0.0f;
+#pragma unroll
+            for(int i = 0; i < 4; i++){                   // epilogue (operations_generic_per_env.h:43-58)
+                const float ls = c.sm_b[I::LOG_STD + i];
+                act[i] = rng_normal(rng, mean[i], expf(ls));
+                lp += normal_log_prob(mean[i], ls, act[i]);
+            }
+            RewardInputs ri;
+            reward_inputs(ri, st);
+            env_step_compiled<Spec, false, true>(st, p, d, act, rng, hist_ptr, n);
+            const bool term = env_terminated(p, st.x);
+            const float r = env_reward(p, ri, act, st.x, term, d.dt);
+            ep_ret += r; ep_step += 1;
+            truncated = term || (a.step_limit > 0 && ep_step >= a.step_limit);
+#pragma unroll
+            for(int i = 0; i < 4; i++){ vals[i] = mean[i]; vals[4 + i] = act[i]; }
+            vals[8] = lp; vals[9] = r; vals[10] = term ? 1.0f : 0.0f; vals[11] = truncated ? 1.0f : 0.0f;
+        }
+        // ---- coalesced write-back through the warp's [32][W] window
+        __syncwarp();
+#pragma unroll
+        for(int i = 0; i < IN; i++) slab[lane * W + i] = obs[i];
+        if(!last){
+#pragma unroll
+            for(int i = 0; i < 12; i++) slab[lane * W + IN + i] = vals[i];
+        }
+        __syncwarp();
+        {
+            const int ncols = last ? IN : W;
+            float* gbase = a.dataset + ((size_t)t * n + warp_env0) * D;
+            for(int idx = lane; idx < 32 * ncols; idx += 32){
+                const int r = idx / ncols, cc = idx - r * ncols;
+                if(r < rows_valid) gbase[(size_t)r * D + cc] = slab[r * W + cc];
+            }
+        }
+        __syncwarp();
+    }
+    if(active){
+        store_state(st, a.state + env, n);
+        a.rng[env] = rng;
+        a.episode_step[env] = ep_step; a.episode_return[env] = ep_ret; a.truncated[env] = truncated ? 1 : 0;
+    }
+    }   // tile loop
+    mlp_ts_epilogue(c);
+}
+
+}  // namespace b200l2f

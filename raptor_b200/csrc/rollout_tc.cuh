@@ -77,23 +77,26 @@ inline void build_tc_image_host(float* img, const float* blob){
 
 // ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
 enum DynC : int { C_COEF = 0, C_AF = 12, C_AT = 24, C_ITAU_RISE = 36, C_ITAU_FALL = 40, C_GRAVITY = 44, C_J = 47, C_JINV = 56, C_ACT_MIN = 65, C_ACT_MAX = 66, C_TERM_POS = 67, C_DIM = 68 };
-template <bool UNIFORM>
+// NC: the parameter columns are read-only for the whole launch (ld.global.nc); false when the kernel itself rewrites them (collect's resets)
+template <bool UNIFORM, bool NC = true>
 struct ParamsCompiledT {
-    const float* sm; const float* __restrict__ base; size_t stride;   // sm: staged block (this thread's column); base/stride: full parameter column in HBM
+    const float* sm; const float* base; size_t stride;                // sm: staged block (this thread's column); base/stride: full parameter column in HBM
     const float* row0;                                                // UNIFORM: environment 0's row in the launch's constant bank
     __device__ __forceinline__ float c(int i) const { return sm[i * BLOCK]; }
     __device__ __forceinline__ float operator[](int i) const {       // everything outside the dynamics block
         if(i == P_TERM_POS) return sm[C_TERM_POS * BLOCK];            // per environment even under DR (10_sample_initial_parameters.h:154)
+        if(i == P_ACT_MIN) return sm[C_ACT_MIN * BLOCK];
+        if(i == P_ACT_MAX) return sm[C_ACT_MAX * BLOCK];
         if(UNIFORM && mdp_uniform_index(i)) return row0[i];
-        return __ldg(base + (size_t)i * stride);
+        return NC ? __ldg(base + (size_t)i * stride) : base[(size_t)i * stride];
     }
 };
 using ParamsCompiled = ParamsCompiledT<false>;
-template <bool UNIFORM>
-__device__ __forceinline__ ParamsCompiledT<UNIFORM> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* __restrict__ params, size_t n, size_t env, const float* row0){
+template <bool UNIFORM, bool NC = true>
+__device__ __forceinline__ ParamsCompiledT<UNIFORM, NC> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env, const float* row0){
     float* sm = sm_dyn + threadIdx.x;
     const float* g = params + env;
-    auto P = [&](int i){ return __ldg(g + (size_t)i * n); };
+    auto P = [&](int i){ return NC ? __ldg(g + (size_t)i * n) : g[(size_t)i * n]; };
 #pragma unroll
     for(int i = 0; i < 12; i++) sm[(C_COEF + i) * BLOCK] = P(P_THRUST_COEF + i);
 #pragma unroll
@@ -114,7 +117,7 @@ __device__ __forceinline__ ParamsCompiledT<UNIFORM> stage_dynamics_compiled(floa
 #pragma unroll
     for(int i = 0; i < 9; i++){ sm[(C_J + i) * BLOCK] = P(P_J + i); sm[(C_JINV + i) * BLOCK] = P(P_JINV + i); }
     sm[C_ACT_MIN * BLOCK] = P(P_ACT_MIN); sm[C_ACT_MAX * BLOCK] = P(P_ACT_MAX); sm[C_TERM_POS * BLOCK] = P(P_TERM_POS);
-    ParamsCompiledT<UNIFORM> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
+    ParamsCompiledT<UNIFORM, NC> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
     return p;
 }
 // multirotor dynamics with the rotor matrices (same physics as dynamics() in env.cuh; thrust/torque summed as matrix-vector products)
@@ -168,14 +171,18 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
         dx[X_RPM + r] = (setpoint[r] - rpm) * inv_tau;
     }
 }
-// env_step twin for the compiled block (no observation/action noise in this variant; Langevin target as in env_step)
-template <class Spec, bool ROLLED_RK4 = false, class PC>
+// env_step twin for the compiled block (NOISE: action noise as in env_step; Langevin target as in env_step)
+template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, class PC>
 __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
                                                   float* __restrict__ hist_ptr, size_t n){
     float setpoint[4];
     const float amin = p.c(C_ACT_MIN), amax = p.c(C_ACT_MAX);
 #pragma unroll
-    for(int i = 0; i < 4; i++) setpoint[i] = clampf(action[i], -1.0f, 1.0f) * d.half_range + amin + d.half_range;
+    for(int i = 0; i < 4; i++){
+        float a = action[i];
+        if constexpr(NOISE) a += rng_normal(rng, 0.0f, p[P_ACTION_NOISE]);
+        setpoint[i] = clampf(a, -1.0f, 1.0f) * d.half_range + amin + d.half_range;
+    }
     const float dt = d.dt;
     const float dt2 = dt / 2.0f, dt3 = dt / 3.0f, dt6 = dt / 6.0f;
     float k[X_DIM], tmp[X_DIM], acc[X_DIM];

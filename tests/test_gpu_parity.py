@@ -360,8 +360,11 @@ def test_mlp_evaluate_step(rb, port, spec, head):
         assert np.array_equal(env.get_rng(), rng)
 
 
-def test_rollout_with_teacher_mlp(rb, port):
-    """BASELINE config 3 shape: TEACHER spec (OBS 26), per-env DR dynamics, SAC-teacher MLP 26-64-64-8 + squash (evaluation mode)"""
+@pytest.mark.parametrize("gemm", ["fp32", "tcgen05"])
+def test_rollout_with_teacher_mlp(rb, port, gemm):
+    """BASELINE config 3 shape: TEACHER spec (OBS 26), per-env DR dynamics, SAC-teacher MLP 26-64-64-8 + squash (evaluation mode);
+    CUDA-core kernel (k_rollout_mlp) and tensor-core kernel (k_rollout_mlp_ts) against the same oracle rollout"""
+    gemm = rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32
     n, T = 200, 60
     spec = B.SPEC_TEACHER_DR
     rs = np.random.RandomState(11)
@@ -374,7 +377,7 @@ def test_rollout_with_teacher_mlp(rb, port):
     want = port.rollout(spec, pol, params, states.copy(), rng.copy(), T)
     env = rb.VectorEnvironment(n, spec)
     env.set_parameters(params); env.set_state(states); env.set_rng(rng)
-    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL)
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=gemm)
     out = env.rollout(T, record=("states", "observations", "actions", "rewards", "terminated"))
     # a random actor does not stabilise the vehicle: compare while trajectories are still regular (first 20 steps) at 1e-4, the rest loosely
     close_relative(out["actions"][:20], want["actions"][:20], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
@@ -390,11 +393,14 @@ def port_final_rng(port, spec, pol, params, states, rng, T):
     return r
 
 
+@pytest.mark.parametrize("gemm", ["fp32", "tcgen05"])
 @pytest.mark.parametrize("spec", [B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR])
-def test_ppo_collect_vs_oracle(rb, port, spec):
+def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     """BASELINE config 4 shape: PPO actor (standardize -> 64 -> 64 -> 4, learned log_std), Gaussian sampling, auto-reset on
-    terminated-or-step-limit with re-sampled parameters and state, dataset rows in the reference layout"""
-    n, T, limit = 96, 40, 12
+    terminated-or-step-limit with re-sampled parameters and state, dataset rows in the reference layout; CUDA-core kernel (k_collect)
+    and tensor-core kernel (k_collect_ts); 200 environments = one full tile + a ragged one"""
+    gemm = rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32
+    n, T, limit = 200, 40, 12
     rs = np.random.RandomState(5)
     blob = random_mlp_blob(rs, 22, 4, True, True)
     env = rb.VectorEnvironment(n, spec)
@@ -403,7 +409,7 @@ def test_ppo_collect_vs_oracle(rb, port, spec):
     env.initialize_rng(31, warmup=16)
     env.initial_parameters()
     env.initial_state()
-    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN)
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=gemm)
     env.collect_reset()
     rng = env.get_rng()
     params, states = env.get_parameters(), env.get_state()
@@ -446,3 +452,32 @@ def test_time_chunked_scheduler_is_transparent(rb):
         assert np.array_equal(s1, s7) and np.array_equal(h1, h7) and np.array_equal(g1, g7) and np.array_equal(r1, r7)
         for k in ("returns", "episode_length", "actions"):
             assert np.array_equal(o1[k], o7[k]), k
+
+
+def test_mlp_tensor_core_rollout_properties(rb):
+    """k_rollout_mlp_ts at a size with several waves and time chunks: identical results for 1 and 5 chunks (bit for bit), agreement with the
+    CUDA-core kernel (fp32 tolerance), for both H = 1 specs and both heads"""
+    import os
+    rs = np.random.RandomState(3)
+    for spec, in_dim, out_dim, head in ((rb.SPEC_TEACHER, 26, 8, rb.HEAD_SQUASH_EVAL), (rb.SPEC_RAPTOR, 22, 4, rb.HEAD_IDENTITY)):
+        blob = random_mlp_blob(rs, in_dim, out_dim, out_dim == 4, False)
+        res = {}
+        for key, gemm, chunks in (("fp32", rb.GEMM_FP32_CUDA_CORES, None), ("ts1", rb.GEMM_TCGEN05_3XTF32, "1"), ("ts5", rb.GEMM_TCGEN05_3XTF32, "5")):
+            if chunks:
+                os.environ["B200L2F_CHUNKS"] = chunks
+            try:
+                e = rb.VectorEnvironment(2900, spec)
+                e.initialize_rng(9, warmup=16)
+                e.sample_initial_state()
+                e.load_policy(blob, arch=rb.POLICY_MLP, input_dim=in_dim, hidden_dim=64, output_dim=out_dim, standardize=int(out_dim == 4), head=head, gemm=gemm)
+                o = e.rollout(30, record=("returns", "episode_length", "actions", "states"))
+                res[key] = (e.get_state(), e.get_rng(), o)
+            finally:
+                os.environ.pop("B200L2F_CHUNKS", None)
+        s1, r1, o1 = res["ts1"]; s5, r5, o5 = res["ts5"]; sf, rf, of = res["fp32"]
+        assert np.array_equal(s1, s5) and np.array_equal(r1, r5)
+        for k in ("returns", "episode_length", "actions", "states"):
+            assert np.array_equal(o1[k], o5[k]), k
+        assert np.array_equal(r1, rf)
+        close_relative(o1["actions"][:15], of["actions"][:15], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions ts vs fp32")
+        close_relative(o1["states"][:16], of["states"][:16], 1e-4, STATE_GROUPS, "states ts vs fp32")

@@ -45,12 +45,14 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rs = np.random.RandomState(0)
     out = []
+    gemm = rb.GEMM_FP32_CUDA_CORES if "--fp32-gemm" in sys.argv else rb.GEMM_TCGEN05_3XTF32
+    gemm_name = "fp32 CUDA cores" if "--fp32-gemm" in sys.argv else "tcgen05 3xTF32"
     # ---- config 3
     n, T = 1048576, 100
     env = rb.VectorEnvironment(n, rb.SPEC_TEACHER_DR, stream=stream.cuda_stream)
     row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32); env.set_environment_parameters(row)
     env.initialize_rng(3, warmup=16); env.sample_initial_parameters(); env.sample_initial_state()
-    env.load_policy(mlp_blob(rs, 26, 8, False, False), arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL)
+    env.load_policy(mlp_blob(rs, 26, 8, False, False), arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=gemm)
     s0 = torch.from_numpy(env.get_state()).to(dev); ret = torch.zeros(n, device=dev)
     ms = timed(lambda: env.rollout(T, out={"returns": ret}), lambda: env.set_state(s0), stream=stream, flush=flush)
     out.append({"config": "3: 1 048 576 envs, per-env DR, SAC-teacher MLP 26-64-64-8 + squash (eval), %d-step rollout" % T, "env_steps_per_s": n * T / ms * 1e3, "ms_per_launch": ms,
@@ -61,7 +63,7 @@ def main():
     env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR, stream=stream.cuda_stream)
     row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32); env.set_environment_parameters(row)
     env.initialize_rng(4, warmup=16); env.initial_parameters(); env.initial_state()
-    env.load_policy(mlp_blob(rs, 22, 4, True, True), arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN)
+    env.load_policy(mlp_blob(rs, 22, 4, True, True), arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=gemm)
     data = torch.zeros(((T + 1) * n, 37), dtype=torch.float32, device=dev)
     ms = timed(lambda: env.collect(T, 500, data), lambda: env.collect_reset(), stream=stream, flush=flush)
     written = n * T * 34 * 4 + n * 22 * 4
@@ -69,6 +71,7 @@ def main():
                 "env_steps_per_s": n * T / ms * 1e3, "ms_per_launch": ms, "dataset_bytes_written": written, "hbm_write_gbs": written / ms / 1e6,
                 "mean_reward": float(data[: T * n, 31].mean().item()), "truncated_fraction": float(data[: T * n, 33].mean().item())})
     for o in out:
+        o["gemm"] = gemm_name
         print(json.dumps(o))
 
 
