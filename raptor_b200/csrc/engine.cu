@@ -39,6 +39,7 @@ struct b200l2f_handle {
     uint64_t* d_rng = nullptr;
     int* d_flags = nullptr;          // [0] error flag, [1] parameter features
     bool features_dirty = true; int features = 0;
+    bool params_follow_env_row = false;   // every column was filled from h_env_row (initial / sampled parameters, collect's resets) and not edited since
     float row0[B200L2F_PARAMS_DIM];   // parameter row of environment 0 (uniform MDP constants of the fused kernels)
     // actor
     bool policy_loaded = false; b200l2f_policy_desc pol{};
@@ -285,11 +286,11 @@ int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
     return B200L2F_OK;
 }
 
-template <class Spec, int OUT, bool UNIFORM>
+template <class Spec, int OUT, bool UNIFORM, bool ROLLED_RK4>
 int launch_rollout_mlp_ts(b200l2f_handle* h, RolloutArgs a){
     constexpr int IN = Spec::OBS_DIM;
     using SM = MlpTsSmem<IN, OUT>;
-    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM>;
+    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM, ROLLED_RK4>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -429,6 +430,7 @@ int b200l2f_set_environment_parameters(b200l2f_handle* h, const float* row145){
     if(row145 != h->h_env_row) std::memcpy(h->h_env_row, row145, sizeof(float) * B200L2F_PARAMS_DIM);
     CU(cudaStreamSynchronize(h->stream));   // h_env_row is pageable: make the copy synchronous w.r.t. earlier kernels that read d_env_row
     CU(cudaMemcpy(h->d_env_row, h->h_env_row, sizeof(float) * B200L2F_PARAMS_DIM, cudaMemcpyHostToDevice));
+    h->params_follow_env_row = false;
     return B200L2F_OK;
 }
 int b200l2f_initial_parameters(b200l2f_handle* h){
@@ -436,6 +438,7 @@ int b200l2f_initial_parameters(b200l2f_handle* h){
     k_fill_params<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->d_env_row, h->n);
     LAUNCH_CHECK();
     h->features_dirty = true;
+    h->params_follow_env_row = true;
     return B200L2F_OK;
 }
 int b200l2f_sample_initial_parameters(b200l2f_handle* h){
@@ -459,6 +462,7 @@ int b200l2f_sample_initial_parameters(b200l2f_handle* h){
         if(flag) return fail(h, B200L2F_ERR_STATE, "L2f: invalid domain randomization ranges (see the reference's assert_exit conditions in 10_sample_initial_parameters.h:68-199)");
     }
     h->features_dirty = true;
+    h->params_follow_env_row = true;
     return B200L2F_OK;
 }
 int b200l2f_get_parameters(b200l2f_handle* h, float* rows, int memspace){
@@ -843,8 +847,10 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
             const bool uniform = (h->features & 2) == 0;
             auto gots = [&](auto spec) -> int {
                 using Spec = decltype(spec);
-                if(o8) return uniform ? launch_rollout_mlp_ts<Spec, 8, true>(h, a) : launch_rollout_mlp_ts<Spec, 8, false>(h, a);
-                return uniform ? launch_rollout_mlp_ts<Spec, 4, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, false>(h, a);
+                static const bool rolled_rk4 = [](){ const char* e = std::getenv("B200L2F_RK4"); return e && std::string(e) == "rolled"; }();
+                if(!uniform) return o8 ? launch_rollout_mlp_ts<Spec, 8, false, false>(h, a) : launch_rollout_mlp_ts<Spec, 4, false, false>(h, a);
+                if(rolled_rk4) return o8 ? launch_rollout_mlp_ts<Spec, 8, true, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, true>(h, a);
+                return o8 ? launch_rollout_mlp_ts<Spec, 8, true, false>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, false>(h, a);
             };
             rc = h->kind == KIND_RAPTOR ? gots(SpecRaptor{}) : gots(SpecTeacher{});
         }
@@ -896,11 +902,16 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
         LAUNCH_CHECK();
         return (int)B200L2F_OK;
     };
-    auto gots = [&](auto spec, auto dr_c) -> int {
+    std::memcpy(a.row, h->h_env_row, sizeof(a.row));
+    const bool follow = h->params_follow_env_row;
+    // the collection kernel carries the reset samplers next to the step: the rolled RK4 stage loop keeps its code inside the instruction
+    // cache (+8 % measured, profiles/r01_configs34.md); B200L2F_RK4=unrolled selects the straight-line integrator
+    static const bool rolled_rk4 = [](){ const char* e = std::getenv("B200L2F_RK4"); return !(e && std::string(e) == "unrolled"); }();
+    auto gots2 = [&](auto spec, auto dr_c, auto follow_c, auto rolled_c) -> int {
         using Spec = decltype(spec);
         constexpr bool DR = decltype(dr_c)::value;
         using SM = MlpTsSmem<Spec::OBS_DIM, 4>;
-        auto kern = k_collect_ts<Spec, DR>;
+        auto kern = k_collect_ts<Spec, DR, decltype(follow_c)::value, decltype(rolled_c)::value>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL_COLLECT));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int sms = 0;
@@ -913,6 +924,10 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
         LAUNCH_CHECK();
         return (int)B200L2F_OK;
     };
+    auto gots = [&](auto spec, auto dr_c) -> int {
+        if(follow) return rolled_rk4 ? gots2(spec, dr_c, std::true_type{}, std::true_type{}) : gots2(spec, dr_c, std::true_type{}, std::false_type{});
+        return gots2(spec, dr_c, std::false_type{}, std::true_type{});
+    };
     const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     if(tensor_cores){
         if(h->kind == KIND_RAPTOR) rc = h->dr ? gots(SpecRaptor{}, std::true_type{}) : gots(SpecRaptor{}, std::false_type{});
@@ -921,7 +936,7 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     else if(h->kind == KIND_RAPTOR) rc = h->dr ? go(SpecRaptor{}, std::true_type{}) : go(SpecRaptor{}, std::false_type{});
     else rc = h->dr ? go(SpecTeacher{}, std::true_type{}) : go(SpecTeacher{}, std::false_type{});
     if(rc) return rc;
-    h->features_dirty = true;   // resets rewrite parameter columns
+    if(!follow) h->features_dirty = true;   // resets rewrite parameter columns (when they follow the row, the variant-selecting features cannot change)
     if((rc = download(h, dataset, dev, bytes, memspace))) return rc;
     if(h->dr){
         int flag = 0;

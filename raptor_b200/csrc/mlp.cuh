@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_mlp(const __grid_
 // ---------------------------------------------------------------------------------------------------------------
 struct CollectArgs {
     float* params;            // [145][n]   (rewritten on reset)
-    const float* env_row;     // [145] nominal / DR-range row the reset sampler starts from
+    const float* env_row;     // [145] nominal / DR-range row the reset sampler starts from (device copy)
+    float row[PARAMS_DIM];    // the same row by value: rides in the launch's constant bank (tensor-core kernel)
     float* state;             // [STATE_DIM][n] slot 0
     uint64_t* rng;
     const float* blob; int has_std;
@@ -270,10 +271,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
         const bool last = t == a.T;                       // final observation only (operations_generic.h:122-129)
         if(!last && truncated && active){                 // prologue (operations_generic_per_env.h:17-25): re-sample parameters and state
             truncated = false; ep_step = 0; ep_ret = 0.0f;
-            ParamsRW prw{a.params + env, n};
-            if(!sample_parameters<DR>(a.env_row, prw, rng)) atomicExch(a.error_flag, 1);
+            ParamsOverlay o;                              // sampled in registers: no dependent HBM round trips on the reset path
+            o.init(a.env_row);
+            if(!sample_parameters<DR>(o, rng)) atomicExch(a.error_flag, 1);
+            o.flush(ParamsRW{a.params + env, n});
             p = stage_dynamics<false>(sm_dyn, a.params, n, env);   // re-stage this thread's column only
-            sample_state(st, prw, rng, hist_ptr, n);
+            sample_state(st, o, rng, hist_ptr, n);
             dyn_invariants(d, p, st);
         }
         observe_to_scratch(st, p, rng, hist_ptr, n, scr + OBS0 * 32, 32);

@@ -225,7 +225,7 @@ __device__ __forceinline__ void mlp_ts_epilogue(const TsCtx& c){
 // closed-loop rollout, deterministic MLP actor (head identity or squash-eval), persistent (tile, time-chunk) work queue as in
 // k_rollout_raptor_ts (the actor is stateless, so a chunk hands over the environment state and the episode accumulators only)
 // ---------------------------------------------------------------------------------------------------------------
-template <class Spec, int OUT, bool UNIFORM>
+template <class Spec, int OUT, bool UNIFORM, bool ROLLED_RK4>
 __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     constexpr int IN = Spec::OBS_DIM;
     using SM = MlpTsSmem<IN, OUT>;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        env_step_compiled<Spec>(st, p, d, act, rng, hist_ptr, n);
+        env_step_compiled<Spec, ROLLED_RK4>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
 // reset (parameter / state re-sampling) is divergent CUDA-core work inside the step loop, the three GEMMs are CTA-collective and therefore
 // sit outside every lane-dependent branch.
 // ---------------------------------------------------------------------------------------------------------------
-template <class Spec, bool DR>
+// FOLLOW: every parameter column was filled from a.row before (initial_parameters / sample_initial_parameters / earlier resets) -- the
+// non-randomised entries equal the row, so the MDP constants are read from the constant bank and a reset writes only the randomised entries.
+template <class Spec, bool DR, bool FOLLOW, bool ROLLED_RK4>
 __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__ CollectArgs a, const float* __restrict__ tc_image, int* __restrict__ sched){
     constexpr int IN = Spec::OBS_DIM, OUT = 4;
     constexpr int D = IN + 15, W = IN + 12;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
     const int e = tile * BLOCK + tid;
     const bool active = e < a.n;
     const size_t env = active ? (size_t)e : 0;
-    ParamsCompiledT<false, false> p = stage_dynamics_compiled<false, false>(sm_dyn, a.params, n, env, nullptr);
+    ParamsCompiledT<FOLLOW, false, FOLLOW> p = stage_dynamics_compiled<FOLLOW, false, FOLLOW>(sm_dyn, a.params, n, env, a.row);
     EnvState<Spec> st;
     load_state(st, a.state + env, n);
     DynInvariants d;
@@ -363,11 +365,13 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         const bool last = t == a.T;                       // final observation only (operations_generic.h:122-129)
         if(!last && truncated && active){                 // prologue (operations_generic_per_env.h:17-25): re-sample parameters and state
             truncated = false; ep_step = 0; ep_ret = 0.0f;
-            ParamsRW prw{a.params + env, n};
-            if(!sample_parameters<DR>(a.env_row, prw, rng)) atomicExch(a.error_flag, 1);
-            p = stage_dynamics_compiled<false, false>(sm_dyn, a.params, n, env, nullptr);   // this thread's column only
-            sample_state(st, prw, rng, hist_ptr, n);
-            dyn_invariants(d, prw, st);
+            ParamsOverlay o;                              // sampled in registers: no dependent HBM round trips on the reset path
+            o.init(a.row);
+            if(!sample_parameters<DR>(o, rng)) atomicExch(a.error_flag, 1);
+            if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
+            compile_dynamics_block(sm_dyn + tid, [&](int i){ return o[i]; });   // this thread's column only
+            sample_state(st, o, rng, hist_ptr, n);
+            dyn_invariants(d, o, st);
         }
         float obs[IN];
         observe_regs<Spec, true>(st, p, rng, obs);
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             }
             RewardInputs ri;
             reward_inputs(ri, st);
-            env_step_compiled<Spec, false, true>(st, p, d, act, rng, hist_ptr, n);
+            env_step_compiled<Spec, ROLLED_RK4, true>(st, p, d, act, rng, hist_ptr, n);
             const bool term = env_terminated(p, st.x);
             const float r = env_reward(p, ri, act, st.x, term, d.dt);
             ep_ret += r; ep_step += 1;
@@ -405,9 +409,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         {
             const int ncols = last ? IN : W;
             float* gbase = a.dataset + ((size_t)t * n + warp_env0) * D;
-            for(int idx = lane; idx < 32 * ncols; idx += 32){
-                const int r = idx / ncols, cc = idx - r * ncols;
-                if(r < rows_valid) gbase[(size_t)r * D + cc] = slab[r * W + cc];
+            int r = 0, cc = lane;                          // element idx = r * ncols + cc, advanced by 32 per iteration without a division
+            while(cc >= ncols){ cc -= ncols; r++; }
+            for(int it = 0; it < ncols; it++){             // 32 * ncols elements / 32 lanes
+                if(r < rows_valid) gbase[r * D + cc] = slab[r * W + cc];
+                cc += 32;
+                while(cc >= ncols){ cc -= ncols; r++; }
             }
         }
         __syncwarp();

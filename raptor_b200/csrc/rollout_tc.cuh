@@ -78,7 +78,8 @@ inline void build_tc_image_host(float* img, const float* blob){
 // ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
 enum DynC : int { C_COEF = 0, C_AF = 12, C_AT = 24, C_ITAU_RISE = 36, C_ITAU_FALL = 40, C_GRAVITY = 44, C_J = 47, C_JINV = 56, C_ACT_MIN = 65, C_ACT_MAX = 66, C_TERM_POS = 67, C_DIM = 68 };
 // NC: the parameter columns are read-only for the whole launch (ld.global.nc); false when the kernel itself rewrites them (collect's resets)
-template <bool UNIFORM, bool NC = true>
+// FOLLOW: every entry outside the domain-randomised set equals row0 (collect, see k_collect_ts)
+template <bool UNIFORM, bool NC = true, bool FOLLOW = false>
 struct ParamsCompiledT {
     const float* sm; const float* base; size_t stride;                // sm: staged block (this thread's column); base/stride: full parameter column in HBM
     const float* row0;                                                // UNIFORM: environment 0's row in the launch's constant bank
@@ -88,15 +89,14 @@ struct ParamsCompiledT {
         if(i == P_ACT_MIN) return sm[C_ACT_MIN * BLOCK];
         if(i == P_ACT_MAX) return sm[C_ACT_MAX * BLOCK];
         if(UNIFORM && mdp_uniform_index(i)) return row0[i];
+        if(FOLLOW && !dr_overlay_index(i)) return row0[i];
         return NC ? __ldg(base + (size_t)i * stride) : base[(size_t)i * stride];
     }
 };
 using ParamsCompiled = ParamsCompiledT<false>;
-template <bool UNIFORM, bool NC = true>
-__device__ __forceinline__ ParamsCompiledT<UNIFORM, NC> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env, const float* row0){
-    float* sm = sm_dyn + threadIdx.x;
-    const float* g = params + env;
-    auto P = [&](int i){ return NC ? __ldg(g + (size_t)i * n) : g[(size_t)i * n]; };
+// compile this thread's dynamics block from any parameter accessor P(i) (HBM column, register overlay, ...)
+template <class F>
+__device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F&& P){
 #pragma unroll
     for(int i = 0; i < 12; i++) sm[(C_COEF + i) * BLOCK] = P(P_THRUST_COEF + i);
 #pragma unroll
@@ -117,7 +117,13 @@ __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC> stage_dynamics_compiled(
 #pragma unroll
     for(int i = 0; i < 9; i++){ sm[(C_J + i) * BLOCK] = P(P_J + i); sm[(C_JINV + i) * BLOCK] = P(P_JINV + i); }
     sm[C_ACT_MIN * BLOCK] = P(P_ACT_MIN); sm[C_ACT_MAX * BLOCK] = P(P_ACT_MAX); sm[C_TERM_POS * BLOCK] = P(P_TERM_POS);
-    ParamsCompiledT<UNIFORM, NC> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
+}
+template <bool UNIFORM, bool NC = true, bool FOLLOW = false>
+__device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env, const float* row0){
+    float* sm = sm_dyn + threadIdx.x;
+    const float* g = params + env;
+    compile_dynamics_block(sm, [&](int i){ return NC ? __ldg(g + (size_t)i * n) : g[(size_t)i * n]; });
+    ParamsCompiledT<UNIFORM, NC, FOLLOW> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
     return p;
 }
 // multirotor dynamics with the rotor matrices (same physics as dynamics() in env.cuh; thrust/torque summed as matrix-vector products)

@@ -26,92 +26,165 @@ struct ParamsRW {  // read/write view of one environment's parameter column in t
 #define B200_SUB(a, b) __fsub_rn((a), (b))
 #define B200_DIV(a, b) __fdiv_rn((a), (b))
 
-// returns false if the DR ranges violate the reference's assert_exit conditions (the caller records the error)
+// Register overlay over the (uniform) nominal row: the 47 entries domain randomisation rewrites live in registers, everything else is read
+// from the row.  The sampler therefore issues no dependent global loads; the column in HBM is written once at the end (flush).  All indices
+// reach get/set as compile-time constants (unrolled loops), so the selection chains fold away.
+__host__ __device__ constexpr bool dr_overlay_index(int i){   // the entries sample_initial_parameters may rewrite
+    return i == P_MASS || (i >= P_THRUST_COEF && i < P_THRUST_COEF + 12) || (i >= P_ROTOR_POS && i < P_ROTOR_POS + 12) ||
+           (i >= P_J && i < P_J + 9 && (i - P_J) % 4 == 0) || (i >= P_JINV && i < P_JINV + 9 && (i - P_JINV) % 4 == 0) ||
+           i == P_TERM_POS || i == P_INIT_MAX_POS || (i >= P_TORQUE_CONST && i < P_TORQUE_CONST + 4) || i == P_DIST_FORCE_MEAN || i == P_DIST_FORCE_STD ||
+           (i >= P_TAU_RISE && i < P_TAU_RISE + 4) || (i >= P_TAU_FALL && i < P_TAU_FALL + 4);
+}
+struct ParamsOverlay {
+    const float* __restrict__ row;
+    float mass, coef[12], jd[3], jinvd[3], rpos[12], term_pos, init_max_pos, kq[4], dist_f_mean, dist_f_std, tau_rise[4], tau_fall[4];
+    __device__ __forceinline__ void init(const float* __restrict__ r){
+        row = r;
+        mass = r[P_MASS]; term_pos = r[P_TERM_POS]; init_max_pos = r[P_INIT_MAX_POS]; dist_f_mean = r[P_DIST_FORCE_MEAN]; dist_f_std = r[P_DIST_FORCE_STD];
+#pragma unroll
+        for(int i = 0; i < 12; i++){ coef[i] = r[P_THRUST_COEF + i]; rpos[i] = r[P_ROTOR_POS + i]; }
+#pragma unroll
+        for(int i = 0; i < 3; i++){ jd[i] = r[P_J + 4 * i]; jinvd[i] = r[P_JINV + 4 * i]; }
+#pragma unroll
+        for(int i = 0; i < 4; i++){ kq[i] = r[P_TORQUE_CONST + i]; tau_rise[i] = r[P_TAU_RISE + i]; tau_fall[i] = r[P_TAU_FALL + i]; }
+    }
+    static __host__ __device__ constexpr bool diag(int i, int base){ return i >= base && i < base + 9 && (i - base) % 4 == 0; }
+    __device__ __forceinline__ float operator[](int i) const {
+        if(i == P_MASS) return mass;
+        if(i >= P_THRUST_COEF && i < P_THRUST_COEF + 12) return coef[i - P_THRUST_COEF];
+        if(i >= P_ROTOR_POS && i < P_ROTOR_POS + 12) return rpos[i - P_ROTOR_POS];
+        if(diag(i, P_J)) return jd[(i - P_J) / 4];
+        if(diag(i, P_JINV)) return jinvd[(i - P_JINV) / 4];
+        if(i == P_TERM_POS) return term_pos;
+        if(i == P_INIT_MAX_POS) return init_max_pos;
+        if(i >= P_TORQUE_CONST && i < P_TORQUE_CONST + 4) return kq[i - P_TORQUE_CONST];
+        if(i == P_DIST_FORCE_MEAN) return dist_f_mean;
+        if(i == P_DIST_FORCE_STD) return dist_f_std;
+        if(i >= P_TAU_RISE && i < P_TAU_RISE + 4) return tau_rise[i - P_TAU_RISE];
+        if(i >= P_TAU_FALL && i < P_TAU_FALL + 4) return tau_fall[i - P_TAU_FALL];
+        return row[i];
+    }
+    // the column in HBM: the row, then the overlaid entries (same thread, same addresses: program order).  FULL = false: the caller knows
+    // that the column's other entries already equal the row (it was filled from the same row before), only the overlay is written.
+    template <bool FULL = true>
+    __device__ __forceinline__ void flush(const ParamsRW& g) const {
+        if constexpr(FULL){
+#pragma unroll 5
+            for(int i = 0; i < PARAMS_DIM; i++) g[i] = row[i];
+        }
+        g[P_MASS] = mass; g[P_TERM_POS] = term_pos; g[P_INIT_MAX_POS] = init_max_pos; g[P_DIST_FORCE_MEAN] = dist_f_mean; g[P_DIST_FORCE_STD] = dist_f_std;
+#pragma unroll
+        for(int i = 0; i < 12; i++){ g[P_THRUST_COEF + i] = coef[i]; g[P_ROTOR_POS + i] = rpos[i]; }
+#pragma unroll
+        for(int i = 0; i < 3; i++){ g[P_J + 4 * i] = jd[i]; g[P_JINV + 4 * i] = jinvd[i]; }
+#pragma unroll
+        for(int i = 0; i < 4; i++){ g[P_TORQUE_CONST + i] = kq[i]; g[P_TAU_RISE + i] = tau_rise[i]; g[P_TAU_FALL + i] = tau_fall[i]; }
+    }
+};
+
+// sample_initial_parameters on the overlay (p.init(row) done by the caller).  Returns false if the DR ranges violate the reference's
+// assert_exit conditions (the caller records the error).  Arithmetic and draw order: 10_sample_initial_parameters.h:20-160.
 template <bool DR>
-__device__ __forceinline__ bool sample_parameters(const float* __restrict__ env_p, const ParamsRW& p, uint64_t& rng){
-    for(int i = 0; i < PARAMS_DIM; i++) p[i] = env_p[i];
+__device__ __forceinline__ bool sample_parameters(ParamsOverlay& p, uint64_t& rng){
     if constexpr(!DR){ return true; }
     else{
+        const float* __restrict__ row = p.row;
         float t2w_nominal;
-        float gravity_norm = sqrtf(B200_ADD(B200_ADD(B200_MUL(p[P_GRAVITY], p[P_GRAVITY]), B200_MUL(p[P_GRAVITY + 1], p[P_GRAVITY + 1])), B200_MUL(p[P_GRAVITY + 2], p[P_GRAVITY + 2])));
+        float gravity_norm = sqrtf(B200_ADD(B200_ADD(B200_MUL(row[P_GRAVITY], row[P_GRAVITY]), B200_MUL(row[P_GRAVITY + 1], row[P_GRAVITY + 1])), B200_MUL(row[P_GRAVITY + 2], row[P_GRAVITY + 2])));
         {
-            const float max_action = p[P_ACT_MAX];
+            const float max_action = row[P_ACT_MAX];
             float max_thrust_nominal = 0.0f;
+#pragma unroll
             for(int r = 0; r < 4; r++){
-                float v = B200_ADD(B200_ADD(p[P_THRUST_COEF + 3 * r], B200_MUL(p[P_THRUST_COEF + 3 * r + 1], max_action)), B200_MUL(B200_MUL(p[P_THRUST_COEF + 3 * r + 2], max_action), max_action));
+                float v = B200_ADD(B200_ADD(p.coef[3 * r], B200_MUL(p.coef[3 * r + 1], max_action)), B200_MUL(B200_MUL(p.coef[3 * r + 2], max_action), max_action));
                 max_thrust_nominal = B200_ADD(max_thrust_nominal, v);
             }
-            t2w_nominal = B200_DIV(max_thrust_nominal, B200_MUL(p[P_MASS], gravity_norm));
+            t2w_nominal = B200_DIV(max_thrust_nominal, B200_MUL(p.mass, gravity_norm));
         }
-        if(!(p[P_DR_T2W_MIN] < p[P_DR_T2W_MAX]) || !(p[P_DR_T2W_MIN] >= 1.5f)) return false;
-        const float t2w = rng_uniform(rng, p[P_DR_T2W_MIN], p[P_DR_T2W_MAX]);
+        if(!(row[P_DR_T2W_MIN] < row[P_DR_T2W_MAX]) || !(row[P_DR_T2W_MIN] >= 1.5f)) return false;
+        const float t2w = rng_uniform(rng, row[P_DR_T2W_MIN], row[P_DR_T2W_MAX]);
         const float factor_t2w = B200_DIV(t2w, t2w_nominal);
-        if(!(p[P_DR_MASS_MIN] < p[P_DR_MASS_MAX])) return false;
-        const float size_min = cbrtf(p[P_DR_MASS_MIN]);
-        const float size_max = cbrtf(p[P_DR_MASS_MAX]);
+        if(!(row[P_DR_MASS_MIN] < row[P_DR_MASS_MAX])) return false;
+        const float size_min = cbrtf(row[P_DR_MASS_MIN]);
+        const float size_max = cbrtf(row[P_DR_MASS_MAX]);
         const float size_new = rng_uniform(rng, size_min, size_max);
         float mass_new = B200_MUL(B200_MUL(size_new, size_new), size_new);
-        mass_new = clampf(mass_new, p[P_DR_MASS_MIN], p[P_DR_MASS_MAX]);
-        const float scale_relative = cbrtf(B200_DIV(mass_new, p[P_MASS]));
-        const float factor_mass = B200_DIV(mass_new, p[P_MASS]);
-        p[P_MASS] = mass_new;
+        mass_new = clampf(mass_new, row[P_DR_MASS_MIN], row[P_DR_MASS_MAX]);
+        const float scale_relative = cbrtf(B200_DIV(mass_new, p.mass));
+        const float factor_mass = B200_DIV(mass_new, p.mass);
+        p.mass = mass_new;
         const float factor_coef = B200_MUL(factor_t2w, factor_mass);
-        for(int i = 0; i < 12; i++) p[P_THRUST_COEF + i] = B200_MUL(p[P_THRUST_COEF + i], factor_coef);
+#pragma unroll
+        for(int i = 0; i < 12; i++) p.coef[i] = B200_MUL(p.coef[i], factor_coef);
         float t2i_factor;
         {
-            const float max_thrust = B200_DIV(B200_MUL(B200_MUL(t2w, p[P_MASS]), gravity_norm), 4.0f);
-            const float first_rotor_distance = fabsf(p[P_ROTOR_POS]);
+            const float max_thrust = B200_DIV(B200_MUL(B200_MUL(t2w, p.mass), gravity_norm), 4.0f);
+            const float first_rotor_distance = fabsf(p.rpos[0]);
             const float max_torque = (float)((double)first_rotor_distance * 1.414213562373095 * (double)max_thrust);
-            const float t2i_nominal = B200_DIV(max_torque, p[P_J]);
-            if(!(p[P_DR_T2I_MIN] < p[P_DR_T2I_MAX])) return false;
-            const float t2i = rng_uniform(rng, p[P_DR_T2I_MIN], p[P_DR_T2I_MAX]);
+            const float t2i_nominal = B200_DIV(max_torque, p.jd[0]);
+            if(!(row[P_DR_T2I_MIN] < row[P_DR_T2I_MAX])) return false;
+            const float t2i = rng_uniform(rng, row[P_DR_T2I_MIN], row[P_DR_T2I_MAX]);
             t2i_factor = B200_DIV(t2i, t2i_nominal);
         }
-        if(p[P_DR_MASS_SIZE_DEV] == 0.0f) return false;
+        if(row[P_DR_MASS_SIZE_DEV] == 0.0f) return false;
         float size_factor;
         {
-            const float range = p[P_DR_MASS_SIZE_DEV];
+            const float range = row[P_DR_MASS_SIZE_DEV];
             const float f = rng_normal(rng, -range, range);
             size_factor = f < 0.0f ? B200_DIV(1.0f, B200_SUB(1.0f, f)) : B200_ADD(1.0f, f);
         }
         const float rotor_distance_factor = B200_MUL(scale_relative, size_factor);
         {
             const float inertia_factor = B200_DIV(t2i_factor, rotor_distance_factor);
+#pragma unroll
             for(int a = 0; a < 3; a++){
-                p[P_J + 4 * a] = B200_DIV(p[P_J + 4 * a], inertia_factor);
-                p[P_JINV + 4 * a] = B200_MUL(p[P_JINV + 4 * a], inertia_factor);
+                p.jd[a] = B200_DIV(p.jd[a], inertia_factor);
+                p.jinvd[a] = B200_MUL(p.jinvd[a], inertia_factor);
             }
-            for(int i = 0; i < 12; i++) p[P_ROTOR_POS + i] = B200_MUL(p[P_ROTOR_POS + i], rotor_distance_factor);
+#pragma unroll
+            for(int i = 0; i < 12; i++) p.rpos[i] = B200_MUL(p.rpos[i], rotor_distance_factor);
             float max_rotor_distance = 0.0f;
+#pragma unroll
             for(int r = 0; r < 4; r++){
-                const float x = p[P_ROTOR_POS + 3 * r], y = p[P_ROTOR_POS + 3 * r + 1], z = p[P_ROTOR_POS + 3 * r + 2];
+                const float x = p.rpos[3 * r], y = p.rpos[3 * r + 1], z = p.rpos[3 * r + 2];
                 const float dd = sqrtf(B200_ADD(B200_ADD(B200_MUL(x, x), B200_MUL(y, y)), B200_MUL(z, z)));
                 if(dd > max_rotor_distance) max_rotor_distance = dd;
             }
-            p[P_TERM_POS] = B200_MUL(max_rotor_distance, 20.0f);
-            p[P_INIT_MAX_POS] = B200_MUL(max_rotor_distance, 10.0f);
+            p.term_pos = B200_MUL(max_rotor_distance, 20.0f);
+            p.init_max_pos = B200_MUL(max_rotor_distance, 10.0f);
         }
-        if(p[P_DR_KQ_MIN] == 0.0f || p[P_DR_KQ_MAX] == 0.0f) return false;
+        if(row[P_DR_KQ_MIN] == 0.0f || row[P_DR_KQ_MAX] == 0.0f) return false;
         {
-            const float kq = rng_uniform(rng, p[P_DR_KQ_MIN], p[P_DR_KQ_MAX]);
-            for(int r = 0; r < 4; r++) p[P_TORQUE_CONST + r] = kq;
+            const float kq = rng_uniform(rng, row[P_DR_KQ_MIN], row[P_DR_KQ_MAX]);
+#pragma unroll
+            for(int r = 0; r < 4; r++) p.kq[r] = kq;
         }
-        if(p[P_DR_DIST_FORCE_MAX] == 0.0f) return false;
+        if(row[P_DR_DIST_FORCE_MAX] == 0.0f) return false;
         {
             float surplus = (float)((double)t2w - 1.0);
             if(surplus < 0.0f) surplus = 0.0f;
-            const float multiple = rng_uniform(rng, 0.0f, B200_MUL(surplus, p[P_DR_DIST_FORCE_MAX]));
-            p[P_DIST_FORCE_MEAN] = 0.0f;
-            p[P_DIST_FORCE_STD] = B200_DIV(B200_MUL(B200_MUL(multiple, t2w), p[P_MASS]), 3.0f);
+            const float multiple = rng_uniform(rng, 0.0f, B200_MUL(surplus, row[P_DR_DIST_FORCE_MAX]));
+            p.dist_f_mean = 0.0f;
+            p.dist_f_std = B200_DIV(B200_MUL(B200_MUL(multiple, t2w), p.mass), 3.0f);
         }
-        if(p[P_DR_TAU_RISE_MIN] == 0.0f || p[P_DR_TAU_RISE_MAX] == 0.0f || p[P_DR_TAU_FALL_MIN] == 0.0f || p[P_DR_TAU_FALL_MAX] == 0.0f) return false;
+        if(row[P_DR_TAU_RISE_MIN] == 0.0f || row[P_DR_TAU_RISE_MAX] == 0.0f || row[P_DR_TAU_FALL_MIN] == 0.0f || row[P_DR_TAU_FALL_MAX] == 0.0f) return false;
         {
-            const float rising = rng_uniform(rng, p[P_DR_TAU_RISE_MIN], p[P_DR_TAU_RISE_MAX]);
-            const float falling = rng_uniform(rng, p[P_DR_TAU_FALL_MIN], p[P_DR_TAU_FALL_MAX]);
-            for(int r = 0; r < 4; r++){ p[P_TAU_RISE + r] = rising; p[P_TAU_FALL + r] = falling; }
+            const float rising = rng_uniform(rng, row[P_DR_TAU_RISE_MIN], row[P_DR_TAU_RISE_MAX]);
+            const float falling = rng_uniform(rng, row[P_DR_TAU_FALL_MIN], row[P_DR_TAU_FALL_MAX]);
+#pragma unroll
+            for(int r = 0; r < 4; r++){ p.tau_rise[r] = rising; p.tau_fall[r] = falling; }
         }
         return true;
     }
+}
+// row -> sampled column in HBM.  On a range error the column holds the state at the point of the error (the caller raises the error).
+template <bool DR>
+__device__ __forceinline__ bool sample_parameters(const float* __restrict__ env_p, const ParamsRW& out, uint64_t& rng){
+    ParamsOverlay o;
+    o.init(env_p);
+    const bool ok = sample_parameters<DR>(o, rng);
+    o.flush(out);
+    return ok;
 }
 
 // hist_ptr: SoA rows of action_history for H > 1 (element (h,a) at hist_ptr[(4h+a)*n]); unused for H == 1

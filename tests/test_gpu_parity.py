@@ -393,12 +393,13 @@ def port_final_rng(port, spec, pol, params, states, rng, T):
     return r
 
 
-@pytest.mark.parametrize("gemm", ["fp32", "tcgen05"])
+@pytest.mark.parametrize("gemm", ["fp32", "tcgen05", "tcgen05-edited-parameters"])
 @pytest.mark.parametrize("spec", [B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR])
 def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     """BASELINE config 4 shape: PPO actor (standardize -> 64 -> 64 -> 4, learned log_std), Gaussian sampling, auto-reset on
     terminated-or-step-limit with re-sampled parameters and state, dataset rows in the reference layout; CUDA-core kernel (k_collect)
     and tensor-core kernel (k_collect_ts); 200 environments = one full tile + a ragged one"""
+    edited = gemm.endswith("edited-parameters")   # parameters written by the caller: the kernel may not assume the columns follow the nominal row
     gemm = rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32
     n, T, limit = 200, 40, 12
     rs = np.random.RandomState(5)
@@ -413,6 +414,8 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     env.collect_reset()
     rng = env.get_rng()
     params, states = env.get_parameters(), env.get_state()
+    if edited:
+        env.set_parameters(params)
     data = env.collect(T, limit)
     pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
     ep_step = np.zeros(n, np.int32); ep_ret = np.zeros(n, np.float32); trunc = np.ones(n, np.uint8)
