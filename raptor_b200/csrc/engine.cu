@@ -892,7 +892,7 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     a.episode_step = h->d_episode_step; a.episode_return = h->d_episode_return; a.truncated = h->d_truncated; a.dataset = (float*)dev;
     a.n = h->n; a.T = n_steps; a.step_limit = episode_step_limit; a.error_flag = h->d_flags;
     auto go = [&](auto spec, auto dr_c) -> int {
-        using Spec = decltype(spec);
+        using Spec = SpecCompactCode<decltype(spec)>;
         constexpr bool DR = decltype(dr_c)::value;
         constexpr int IN = Spec::OBS_DIM;
         auto kern = k_collect<Spec, DR>;
@@ -908,7 +908,7 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     // cache (+8 % measured, profiles/r01_configs34.md); B200L2F_RK4=unrolled selects the straight-line integrator
     static const bool rolled_rk4 = [](){ const char* e = std::getenv("B200L2F_RK4"); return !(e && std::string(e) == "unrolled"); }();
     auto gots2 = [&](auto spec, auto dr_c, auto follow_c, auto rolled_c) -> int {
-        using Spec = decltype(spec);
+        using Spec = SpecCompactCode<decltype(spec)>;
         constexpr bool DR = decltype(dr_c)::value;
         using SM = MlpTsSmem<Spec::OBS_DIM, 4>;
         auto kern = k_collect_ts<Spec, DR, decltype(follow_c)::value, decltype(rolled_c)::value>;

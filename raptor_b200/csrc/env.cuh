@@ -233,7 +233,7 @@ __device__ __forceinline__ void env_step(EnvState<Spec>& st, const P& p, const D
 #pragma unroll
     for(int i = 0; i < 4; i++){
         float a = action[i];
-        if constexpr(NOISE) a += rng_normal(rng, 0.0f, p[P_ACTION_NOISE]);
+        if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_ACTION_NOISE]);
         a = clampf(a, -1.0f, 1.0f);
         setpoint[i] = a * d.half_range + p[P_ACT_MIN] + d.half_range;
     }
@@ -306,7 +306,7 @@ __device__ __forceinline__ void env_step(EnvState<Spec>& st, const P& p, const D
             for(int dim = 0; dim < 3; dim++){
                 const float x_prev = st.lang[6 + dim];
                 const float v_prev = st.lang[9 + dim];
-                const float dW = sqrt_dt * rng_normal(rng, 0.0f, 1.0f);
+                const float dW = sqrt_dt * rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, 1.0f);
                 const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
                 const float x_next = x_prev + v_next * dt;
                 st.lang[6 + dim] = x_next;
@@ -348,7 +348,7 @@ __device__ __forceinline__ void observe18(const EnvState<Spec>& st, const P& p, 
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float v = (Spec::OBS_LAYOUT == OBS_RAPTOR) ? st.x[X_POS + i] : st.x[X_POS + i] - dpos[i];
-        if constexpr(NOISE) v += rng_normal(rng, 0.0f, p[P_NOISE_POS]);
+        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_POS]);
         o[i] = v;
     }
     const float q0 = st.x[X_ORI], q1 = st.x[X_ORI + 1], q2 = st.x[X_ORI + 2], q3 = st.x[X_ORI + 3];
@@ -363,18 +363,18 @@ __device__ __forceinline__ void observe18(const EnvState<Spec>& st, const P& p, 
     o[11] = (1 - 2 * q1 * q1 - 2 * q2 * q2);
     if constexpr(NOISE){
 #pragma unroll
-        for(int i = 0; i < 9; i++) o[3 + i] += rng_normal(rng, 0.0f, p[P_NOISE_ORI]);
+        for(int i = 0; i < 9; i++) o[3 + i] += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_ORI]);
     }
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float v = (Spec::OBS_LAYOUT == OBS_RAPTOR) ? st.x[X_VEL + i] : st.x[X_VEL + i] - dvel[i];
-        if constexpr(NOISE) v += rng_normal(rng, 0.0f, p[P_NOISE_LINVEL]);
+        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_LINVEL]);
         o[12 + i] = v;
     }
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float v = st.x[X_OMEGA + i];
-        if constexpr(NOISE) v += rng_normal(rng, 0.0f, p[P_NOISE_ANGVEL]);
+        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_ANGVEL]);
         o[15 + i] = v;
     }
 }

@@ -35,8 +35,10 @@ __host__ __device__ constexpr int state_dim(int H){ return 44 + 4 * H; }
 enum ObsLayout : int { OBS_DEFAULT = 0, OBS_RAPTOR = 1, OBS_TEACHER = 2 };
 
 // compile-time description of an environment specification (the reference does the same with template parameter packs)
-template <int T_H, bool T_LANGEVIN, int T_OBS_LAYOUT>
+// T_RNG_OOL: the Box-Muller draw is an out-of-line call (kernels with ~30 draw sites, see rng.cuh); false: inlined (rollout kernels)
+template <int T_H, bool T_LANGEVIN, int T_OBS_LAYOUT, bool T_RNG_OOL = false>
 struct EnvSpec {
+    static constexpr bool RNG_OOL = T_RNG_OOL;
     static constexpr int H = T_H;
     static constexpr bool LANGEVIN = T_LANGEVIN;
     static constexpr int OBS_LAYOUT = T_OBS_LAYOUT;
@@ -46,5 +48,6 @@ struct EnvSpec {
 using SpecDefault = EnvSpec<16, false, OBS_DEFAULT>;  // rl/environments/l2f/parameters/default.h:159-171
 using SpecRaptor  = EnvSpec<1, true, OBS_RAPTOR>;     // src/foundation_policy/post_training/environment.h:23-33
 using SpecTeacher = EnvSpec<1, true, OBS_TEACHER>;    // src/foundation_policy/pre_training/environment.h:64-75
+template <class Spec> using SpecCompactCode = EnvSpec<Spec::H, Spec::LANGEVIN, Spec::OBS_LAYOUT, true>;
 
 }  // namespace b200l2f

@@ -13,6 +13,7 @@
 // layer consumes lives in a per-thread shared-memory column (so the k loops can stay rolled and the 64 accumulators of a layer are the
 // only wide register array); dataset rows are transposed through shared memory and written as fully coalesced 128-byte lines.
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace b200l2f {
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
             truncated = false; ep_step = 0; ep_ret = 0.0f;
             ParamsOverlay o;                              // sampled in registers: no dependent HBM round trips on the reset path
             o.init(a.env_row);
-            if(!sample_parameters<DR>(o, rng)) atomicExch(a.error_flag, 1);
+            if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
             o.flush(ParamsRW{a.params + env, n});
             p = stage_dynamics<false>(sm_dyn, a.params, n, env);   // re-stage this thread's column only
             sample_state(st, o, rng, hist_ptr, n);
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
 #pragma unroll
             for(int i = 0; i < 4; i++){                   // epilogue (operations_generic_per_env.h:43-58)
                 const float ls = img[MlpImg<IN, OUT>::LOG_STD + i];
-                act[i] = rng_normal(rng, mean[i], expf(ls));
+                act[i] = rng_normal_t<Spec::RNG_OOL>(rng, mean[i], expf(ls));
                 lp += normal_log_prob(mean[i], ls, act[i]);
             }
             RewardInputs ri;
@@ -312,12 +313,18 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
         }
         __syncwarp();
         {
-            const int ncols = last ? IN : W;
             float* gbase = a.dataset + ((size_t)t * n + warp_env0) * D;
-            for(int idx = lane; idx < 32 * ncols; idx += 32){
-                const int r = idx / ncols, c = idx - r * ncols;
-                if(r < rows_valid) gbase[(size_t)r * D + c] = slab[r * W + c];
-            }
+            auto stream_rows = [&](auto ncols_c){          // compile-time divisor -> multiply-shift
+                constexpr int NC = decltype(ncols_c)::value;
+#pragma unroll 2
+                for(int it = 0; it < NC; it++){
+                    const int idx = lane + 32 * it;
+                    const int r = idx / NC, c = idx - r * NC;
+                    if(r < rows_valid) gbase[r * D + c] = slab[r * W + c];
+                }
+            };
+            if(!last) stream_rows(std::integral_constant<int, W>{});
+            else stream_rows(std::integral_constant<int, IN>{});
         }
         __syncwarp();
     }

@@ -183,7 +183,7 @@ struct MlpTsSmem {
     static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
     static constexpr int SLAB = BAR + 32;                                 // collect only: per-warp [32][W] write-back windows
     static constexpr int TOTAL_ROLLOUT = SLAB;
-    static constexpr int TOTAL_COLLECT = SLAB + 4 * 32 * (IN + 12) * 4;
+    static constexpr int TOTAL_COLLECT = SLAB + 4 * 32 * (IN + 13) * 4;   // row stride W + 1 (odd): conflict-free on both sides
 };
 
 // CTA prologue shared by both kernels: barriers, TMEM allocation, weight image by TMA.  Returns the context; every thread must call it.
@@ -327,14 +327,14 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
 template <class Spec, bool DR, bool FOLLOW, bool ROLLED_RK4>
 __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__ CollectArgs a, const float* __restrict__ tc_image, int* __restrict__ sched){
     constexpr int IN = Spec::OBS_DIM, OUT = 4;
-    constexpr int D = IN + 15, W = IN + 12;
+    constexpr int D = IN + 15, W = IN + 12, WS = W + 1;   // W columns written per step; WS: row stride of the staging window
     using SM = MlpTsSmem<IN, OUT>;
     using I = MlpTcImage<IN, OUT>;
     extern __shared__ __align__(1024) unsigned char smraw[];
     float* sm_dyn = reinterpret_cast<float*>(smraw + SM::DYN);
     TsCtx c = mlp_ts_prologue<IN, OUT>(smraw, tc_image);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* slab = reinterpret_cast<float*>(smraw + SM::SLAB) + (size_t)warp * 32 * W;   // private to this warp
+    float* slab = reinterpret_cast<float*>(smraw + SM::SLAB) + (size_t)warp * 32 * WS;   // private to this warp
     const size_t n = (size_t)a.n;
     __shared__ int s_item;
     const int n_tiles = (a.n + BLOCK - 1) / BLOCK;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             truncated = false; ep_step = 0; ep_ret = 0.0f;
             ParamsOverlay o;                              // sampled in registers: no dependent HBM round trips on the reset path
             o.init(a.row);
-            if(!sample_parameters<DR>(o, rng)) atomicExch(a.error_flag, 1);
+            if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
             if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
             compile_dynamics_block(sm_dyn + tid, [&](int i){ return o[i]; });   // this thread's column only
             sample_state(st, o, rng, hist_ptr, n);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
 #pragma unroll
             for(int i = 0; i < 4; i++){                   // epilogue (operations_generic_per_env.h:43-58)
                 const float ls = c.sm_b[I::LOG_STD + i];
-                act[i] = rng_normal(rng, mean[i], expf(ls));
+                act[i] = rng_normal_t<Spec::RNG_OOL>(rng, mean[i], expf(ls));
                 lp += normal_log_prob(mean[i], ls, act[i]);
             }
             RewardInputs ri;
@@ -397,25 +397,29 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             for(int i = 0; i < 4; i++){ vals[i] = mean[i]; vals[4 + i] = act[i]; }
             vals[8] = lp; vals[9] = r; vals[10] = term ? 1.0f : 0.0f; vals[11] = truncated ? 1.0f : 0.0f;
         }
-        // ---- coalesced write-back through the warp's [32][W] window
+        // ---- coalesced write-back through the warp's [32][WS] window
         __syncwarp();
 #pragma unroll
-        for(int i = 0; i < IN; i++) slab[lane * W + i] = obs[i];
+        for(int i = 0; i < IN; i++) slab[lane * WS + i] = obs[i];
         if(!last){
 #pragma unroll
-            for(int i = 0; i < 12; i++) slab[lane * W + IN + i] = vals[i];
+            for(int i = 0; i < 12; i++) slab[lane * WS + IN + i] = vals[i];
         }
         __syncwarp();
         {
-            const int ncols = last ? IN : W;
             float* gbase = a.dataset + ((size_t)t * n + warp_env0) * D;
-            int r = 0, cc = lane;                          // element idx = r * ncols + cc, advanced by 32 per iteration without a division
-            while(cc >= ncols){ cc -= ncols; r++; }
-            for(int it = 0; it < ncols; it++){             // 32 * ncols elements / 32 lanes
-                if(r < rows_valid) gbase[r * D + cc] = slab[r * W + cc];
-                cc += 32;
-                while(cc >= ncols){ cc -= ncols; r++; }
-            }
+            // the window is the 32 rows back to back: element idx sits in row idx / ncols (compile-time divisor -> multiply-shift)
+            auto stream_rows = [&](auto ncols_c){
+                constexpr int NC = decltype(ncols_c)::value;
+#pragma unroll 2
+                for(int it = 0; it < NC; it++){
+                    const int idx = lane + 32 * it;
+                    const int r = idx / NC, cc = idx - r * NC;
+                    if(r < rows_valid) gbase[r * D + cc] = slab[r * WS + cc];
+                }
+            };
+            if(!last) stream_rows(std::integral_constant<int, W>{});
+            else stream_rows(std::integral_constant<int, IN>{});
         }
         __syncwarp();
     }

@@ -30,8 +30,7 @@ __device__ __forceinline__ float rng_uniform(uint64_t& s, float lo, float hi){
     float u = rng_unit(s);
     return __fadd_rn(__fmul_rn(u, __fsub_rn(hi, lo)), lo);  // no FMA contraction: bit-exact with the oracle
 }
-__device__ __forceinline__ float rng_normal(uint64_t& s, float mean, float std){
-    if(std == 0.0f){ return mean; }
+__device__ __forceinline__ float rng_normal_draw(uint64_t& s, float mean, float std){
     float u1 = rng_unit(s);
     float u2 = rng_unit(s);
     // the reference evaluates sqrt(-2.0 * log(u1)) and 2.0 * PI<float> * u2 in double (double literals) and rounds to float; -2 * logf(u1) and
@@ -42,5 +41,16 @@ __device__ __forceinline__ float rng_normal(uint64_t& s, float mean, float std){
     float z = __fmul_rn(x, cosf(y));
     return __fadd_rn(__fmul_rn(z, std), mean);
 }
+// Out-of-line twin: the collection kernels contain ~30 draw sites (observation / action noise, action sampling, reset samplers); the
+// inlined logf / cosf bodies would double their size and push them out of the instruction cache (profiles/r01_configs34.md).  The rollout
+// kernels have three sites (Langevin target) and keep the inlined draw (a call there costs 4 %).
+__device__ __noinline__ float rng_normal_draw_ool(uint64_t& s, float mean, float std){ return rng_normal_draw(s, mean, std); }
+template <bool OOL>
+__device__ __forceinline__ float rng_normal_t(uint64_t& s, float mean, float std){
+    if(std == 0.0f){ return mean; }
+    if constexpr(OOL) return rng_normal_draw_ool(s, mean, std);
+    else return rng_normal_draw(s, mean, std);
+}
+__device__ __forceinline__ float rng_normal(uint64_t& s, float mean, float std){ return rng_normal_t<false>(s, mean, std); }
 
 }  // namespace b200l2f

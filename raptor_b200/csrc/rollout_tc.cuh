@@ -186,7 +186,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
 #pragma unroll
     for(int i = 0; i < 4; i++){
         float a = action[i];
-        if constexpr(NOISE) a += rng_normal(rng, 0.0f, p[P_ACTION_NOISE]);
+        if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_ACTION_NOISE]);
         setpoint[i] = clampf(a, -1.0f, 1.0f) * d.half_range + amin + d.half_range;
     }
     const float dt = d.dt;
@@ -255,7 +255,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
 #pragma unroll
             for(int dim = 0; dim < 3; dim++){
                 const float x_prev = st.lang[6 + dim], v_prev = st.lang[9 + dim];
-                const float dW = sqrt_dt * rng_normal(rng, 0.0f, 1.0f);
+                const float dW = sqrt_dt * rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, 1.0f);
                 const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
                 const float x_next = x_prev + v_next * dt;
                 st.lang[6 + dim] = x_next; st.lang[9 + dim] = v_next;

@@ -84,7 +84,7 @@ struct ParamsOverlay {
 
 // sample_initial_parameters on the overlay (p.init(row) done by the caller).  Returns false if the DR ranges violate the reference's
 // assert_exit conditions (the caller records the error).  Arithmetic and draw order: 10_sample_initial_parameters.h:20-160.
-template <bool DR>
+template <bool DR, bool RNG_OOL = false>
 __device__ __forceinline__ bool sample_parameters(ParamsOverlay& p, uint64_t& rng){
     if constexpr(!DR){ return true; }
     else{
@@ -130,7 +130,7 @@ __device__ __forceinline__ bool sample_parameters(ParamsOverlay& p, uint64_t& rn
         float size_factor;
         {
             const float range = row[P_DR_MASS_SIZE_DEV];
-            const float f = rng_normal(rng, -range, range);
+            const float f = rng_normal_t<RNG_OOL>(rng, -range, range);
             size_factor = f < 0.0f ? B200_DIV(1.0f, B200_SUB(1.0f, f)) : B200_ADD(1.0f, f);
         }
         const float rotor_distance_factor = B200_MUL(scale_relative, size_factor);
@@ -260,10 +260,10 @@ __device__ __forceinline__ void sample_state(EnvState<Spec>& st, const P& p, uin
     for(int i = 0; i < 4; i++) st.last_action[i] = 0.0f;
     {
         const float fm = p[P_DIST_FORCE_MEAN], fs = p[P_DIST_FORCE_STD], tm = p[P_DIST_TORQUE_MEAN], ts = p[P_DIST_TORQUE_STD];
-        for(int i = 0; i < 3; i++) st.force[i] = rng_normal(rng, fm, fs);
-        st.torque[0] = rng_normal(rng, tm, ts);
-        st.torque[1] = rng_normal(rng, tm, ts);
-        st.torque[2] = rng_normal(rng, tm, B200_DIV(ts, 100.0f));
+        for(int i = 0; i < 3; i++) st.force[i] = rng_normal_t<Spec::RNG_OOL>(rng, fm, fs);
+        st.torque[0] = rng_normal_t<Spec::RNG_OOL>(rng, tm, ts);
+        st.torque[1] = rng_normal_t<Spec::RNG_OOL>(rng, tm, ts);
+        st.torque[2] = rng_normal_t<Spec::RNG_OOL>(rng, tm, B200_DIV(ts, 100.0f));
     }
     {
         float min_rpm, max_rpm;
