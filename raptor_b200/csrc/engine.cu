@@ -48,6 +48,7 @@ struct b200l2f_handle {
     int* d_sched = nullptr; size_t sched_ints = 0;     // work counter + per-tile progress of the time-chunked scheduler
     float* d_acc_ret = nullptr; int* d_acc_len = nullptr;
     float* d_tc_image = nullptr;     // tensor-core weight image (hi/lo planes of the three B operands, TMA source)
+    float* d_ts_image = nullptr;     // the same with scaled GRU gate rows (k_rollout_raptor_ts)
     float* d_mlp_tc_image = nullptr; // same for an MLP actor (MlpTcImage<IN, OUT>), null when the actor has no tensor-core instantiation
     std::vector<float> h_image;      // k-major actor image passed by value to the fused kernels (constant-bank weights)
     bool weights_in_constant_bank = false; bool rolled = false;
@@ -281,7 +282,7 @@ int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
     }
     int grid = 0, rc;
     if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
-    kern<<<grid, BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
+    kern<<<grid, BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_ts_image);
     LAUNCH_CHECK();
     return B200L2F_OK;
 }
@@ -378,7 +379,7 @@ int b200l2f_destroy(b200l2f_handle* h){
     if(h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_params); cudaFree(h->d_env_row);
     for(float* p : h->d_state) cudaFree(p);
-    cudaFree(h->d_tc_image); cudaFree(h->d_mlp_tc_image); cudaFree(h->d_sched); cudaFree(h->d_acc_ret); cudaFree(h->d_acc_len);
+    cudaFree(h->d_tc_image); cudaFree(h->d_ts_image); cudaFree(h->d_mlp_tc_image); cudaFree(h->d_sched); cudaFree(h->d_acc_ret); cudaFree(h->d_acc_len);
     cudaFree(h->d_rng); cudaFree(h->d_flags); cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
     cudaFree(h->d_episode_step); cudaFree(h->d_episode_return); cudaFree(h->d_truncated);
     if(h->d_stage) cudaFree(h->d_stage);
@@ -666,6 +667,10 @@ int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
         cudaFree(h->d_tc_image); h->d_tc_image = nullptr;
         CU(cudaMalloc(&h->d_tc_image, TcImage::BYTES));
         CU(cudaMemcpy(h->d_tc_image, tcimg.data(), TcImage::BYTES, cudaMemcpyHostToDevice));
+        build_tc_image_host(tcimg.data(), blob, true);   // TMEM-A kernel: gate rows pre-multiplied by the exponent scale of their activation
+        cudaFree(h->d_ts_image); h->d_ts_image = nullptr;
+        CU(cudaMalloc(&h->d_ts_image, TcImage::BYTES));
+        CU(cudaMemcpy(h->d_ts_image, tcimg.data(), TcImage::BYTES, cudaMemcpyHostToDevice));
     }
     {   // tuning knob, measured on B200 (profiles/r01_summary.md): weights staged in shared memory (broadcast LDS.128) are ~3% faster than
         // riding in the launch's constant bank (LDCU + uniform-register FFMA operands), so shared memory is the default

@@ -427,44 +427,46 @@ __device__ __forceinline__ void reward_inputs(RewardInputs& r, const EnvState<Sp
     for(int i = 0; i < 4; i++) r.last_action[i] = st.last_action[i];
     desired_state(st, r.dpos, r.dvel);
 }
-template <class P>
+// FAST (default-math fused kernels): a term whose weight is zero is skipped instead of multiplied by zero (same value for finite states; the
+// foundation-policy reward has five zero weights out of eight), square roots on the MUFU unit.
+template <bool FAST = false, class P>
 __device__ __forceinline__ float env_reward(const P& p, const RewardInputs& s, const float* __restrict__ action, const float* __restrict__ xn, bool terminated_next, float dt){
     float weighted = 0.0f;
-    {
+    auto on = [](float w){ return !FAST || w != 0.0f; };
+    if(const float w = p[P_RW_POSITION]; on(w)){
         const float x = s.pos[0] - s.dpos[0], y = s.pos[1] - s.dpos[1], z = s.pos[2] - s.dpos[2];
-        float c = sqrtf(x * x + y * y + z * z);
+        float c = sqrt_t<FAST>(x * x + y * y + z * z);
         const float clip = p[P_RW_POSITION_CLIP];
         if(clip > 0.0f) c = fminf(c, clip);
-        weighted += p[P_RW_POSITION] * c;
+        weighted += w * c;
     }
-    weighted += p[P_RW_ORIENTATION] * (2.0f * acosf(1.0f - fabsf(s.q3)));
-    {
-        const float w = p[P_RW_LINVEL];
+    if(const float w = p[P_RW_ORIENTATION]; on(w)) weighted += w * (2.0f * acosf(1.0f - fabsf(s.q3)));
+    if(const float w = p[P_RW_LINVEL]; on(w)){
         const float x = s.vel[0] - s.dvel[0], y = s.vel[1] - s.dvel[1], z = s.vel[2] - s.dvel[2];
-        weighted += w * sqrtf(x * x + y * y + z * z);
+        weighted += w * sqrt_t<FAST>(x * x + y * y + z * z);
     }
-    weighted += p[P_RW_ANGVEL] * sqrtf(s.omega[0] * s.omega[0] + s.omega[1] * s.omega[1] + s.omega[2] * s.omega[2]);
-    {
+    if(const float w = p[P_RW_ANGVEL]; on(w)) weighted += w * sqrt_t<FAST>(s.omega[0] * s.omega[0] + s.omega[1] * s.omega[1] + s.omega[2] * s.omega[2]);
+    if(const float w = p[P_RW_LINACC]; on(w)){
         const float x = xn[X_VEL] - s.vel[0], y = xn[X_VEL + 1] - s.vel[1], z = xn[X_VEL + 2] - s.vel[2];
-        weighted += p[P_RW_LINACC] * (sqrtf(x * x + y * y + z * z) / dt);
+        weighted += w * (sqrt_t<FAST>(x * x + y * y + z * z) / dt);
     }
-    {
+    if(const float w = p[P_RW_ANGACC]; on(w)){
         const float x = xn[X_OMEGA] - s.omega[0], y = xn[X_OMEGA + 1] - s.omega[1], z = xn[X_OMEGA + 2] - s.omega[2];
-        weighted += p[P_RW_ANGACC] * (sqrtf(x * x + y * y + z * z) / dt);
+        weighted += w * (sqrt_t<FAST>(x * x + y * y + z * z) / dt);
     }
-    {
+    if(const float w = p[P_RW_ACTION]; on(w)){
         const float hover = p[P_HOVER];
         float acc = 0.0f;
 #pragma unroll
         for(int i = 0; i < 4; i++){ const float dd = (action[i] + 1.0f) / 2.0f - hover; acc += dd * dd; }
-        float c = sqrtf(acc);
-        weighted += p[P_RW_ACTION] * (c * c);
+        float c = sqrt_t<FAST>(acc);
+        weighted += w * (c * c);
     }
-    {
+    if(const float w = p[P_RW_DACTION]; on(w)){
         float acc = 0.0f;
 #pragma unroll
         for(int i = 0; i < 4; i++){ const float dd = action[i] - s.last_action[i]; acc += dd * dd; }
-        weighted += p[P_RW_DACTION] * sqrtf(acc);
+        weighted += w * sqrt_t<FAST>(acc);
     }
     const float scaled = p[P_RW_SCALE] * weighted;
     float r;

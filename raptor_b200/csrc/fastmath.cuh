@@ -1,0 +1,20 @@
+// raptor_b200/csrc/fastmath.cuh -- the approximate special functions of the default-math kernels (B200L2F_FLAG_ACCURATE_MATH selects the
+// libdevice functions instead).  Each is one MUFU instruction (+ a multiply), ~2 ulp.
+#pragma once
+
+namespace b200l2f {
+
+constexpr float LOG2E = 1.4426950408889634f;
+// .ftz: a denormal result is 0, which is exact enough next to the 1.0 it is added to in the gate activations
+__device__ __forceinline__ float ex2_approx(float x){ float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x){ float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_of_scaled(float t){ return rcp_approx(1.0f + ex2_approx(t)); }              // t = -log2(e) * a
+__device__ __forceinline__ float tanh_of_scaled(float t){ return fmaf(-2.0f, rcp_approx(ex2_approx(t) + 1.0f), 1.0f); } // t = 2 log2(e) * a
+__device__ __forceinline__ float sqrt_approx(float x){ float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x){ float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <bool FAST> __device__ __forceinline__ float sqrt_t(float x){ if constexpr(FAST) return sqrt_approx(x); else return sqrtf(x); }
+// clamp: the literal form propagates NaN like the reference's math::clamp; the min/max form is two instructions instead of four
+__device__ __forceinline__ float clamp_literal(float x, float lo, float hi){ return x < lo ? lo : (x > hi ? hi : x); }
+template <bool FAST> __device__ __forceinline__ float clamp_t(float x, float lo, float hi){ if constexpr(FAST) return fminf(fmaxf(x, lo), hi); else return clamp_literal(x, lo, hi); }
+
+}  // namespace b200l2f

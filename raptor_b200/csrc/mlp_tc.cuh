@@ -289,9 +289,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        env_step_compiled<Spec, ROLLED_RK4>(st, p, d, act, rng, hist_ptr, n);
+        env_step_compiled<Spec, ROLLED_RK4, false, true>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
-        const float rw = env_reward(p, ri, act, st.x, term, d.dt);
+        const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
         if(a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
         if(!done){ ret += rw; eplen += 1; done = term; }
@@ -388,9 +388,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             }
             RewardInputs ri;
             reward_inputs(ri, st);
-            env_step_compiled<Spec, ROLLED_RK4, true>(st, p, d, act, rng, hist_ptr, n);
+            env_step_compiled<Spec, ROLLED_RK4, true, true>(st, p, d, act, rng, hist_ptr, n);
             const bool term = env_terminated(p, st.x);
-            const float r = env_reward(p, ri, act, st.x, term, d.dt);
+            const float r = env_reward<true>(p, ri, act, st.x, term, d.dt);
             ep_ret += r; ep_step += 1;
             truncated = term || (a.step_limit > 0 && ep_step >= a.step_limit);
 #pragma unroll

@@ -102,14 +102,12 @@ __device__ __forceinline__ void matvec_acc(float* __restrict__ acc, const W& img
 
 template <bool FAST>
 __device__ __forceinline__ float sigmoidf_(float a){
-    if constexpr(FAST) return __fdividef(1.0f, 1.0f + __expf(-a));
+    if constexpr(FAST) return sigmoid_of_scaled(a * -LOG2E);   // 1 / (1 + e^-a); saturates to 0 / 1 through ex2 -> inf / 0
     else return 1.0f / (1.0f + expf(-a));
 }
 template <bool FAST>
 __device__ __forceinline__ float tanhf_(float a){
-    if constexpr(FAST){  // 1 - 2 / (e^{2a} + 1): two MUFU ops, absolute error ~1e-7, saturates correctly for |a| large
-        return 1.0f - __fdividef(2.0f, __expf(2.0f * a) + 1.0f);
-    }
+    if constexpr(FAST) return tanh_of_scaled(a * (2.0f * LOG2E));   // 1 - 2 / (e^{2a} + 1): absolute error ~1e-7, saturates correctly
     else return tanhf(a);
 }
 

@@ -11,6 +11,7 @@
 // with the oracle; the float transforms agree to the last ulp of logf/cosf.
 #pragma once
 #include <cstdint>
+#include "fastmath.cuh"
 
 namespace b200l2f {
 
@@ -45,10 +46,20 @@ __device__ __forceinline__ float rng_normal_draw(uint64_t& s, float mean, float 
 // inlined logf / cosf bodies would double their size and push them out of the instruction cache (profiles/r01_configs34.md).  The rollout
 // kernels have three sites (Langevin target) and keep the inlined draw (a call there costs 4 %).
 __device__ __noinline__ float rng_normal_draw_ool(uint64_t& s, float mean, float std){ return rng_normal_draw(s, mean, std); }
-template <bool OOL>
+// default-math twin: same two uniforms (the integer stream stays bit-exact), MUFU logarithm / cosine / square root (absolute error ~5e-7)
+__device__ __forceinline__ float rng_normal_draw_fast(uint64_t& s, float mean, float std){
+    const float u1 = rng_unit(s);
+    float u2 = rng_unit(s);
+    const float x = sqrt_approx(-2.0f * __logf(u1));
+    if(u2 > 0.5f) u2 -= 1.0f;                            // cos(2 pi u) with the argument reduced to (-pi, pi], where cos.approx is tight
+    const float z = x * __cosf(6.28318548202514648f * u2);
+    return fmaf(z, std, mean);
+}
+template <bool OOL, bool FAST = false>
 __device__ __forceinline__ float rng_normal_t(uint64_t& s, float mean, float std){
     if(std == 0.0f){ return mean; }
-    if constexpr(OOL) return rng_normal_draw_ool(s, mean, std);
+    if constexpr(FAST) return rng_normal_draw_fast(s, mean, std);
+    else if constexpr(OOL) return rng_normal_draw_ool(s, mean, std);
     else return rng_normal_draw(s, mean, std);
 }
 __device__ __forceinline__ float rng_normal(uint64_t& s, float mean, float std){ return rng_normal_t<false>(s, mean, std); }

@@ -35,8 +35,10 @@ struct TcImage {
 inline void tc_split_host(float x, float& hi, float& lo){
     uint32_t u; std::memcpy(&u, &x, 4); u &= 0xFFFFE000u; std::memcpy(&hi, &u, 4); lo = x - hi;
 }
-// blob (include/b200_l2f.h RAPTOR_GRU order) -> image
-inline void build_tc_image_host(float* img, const float* blob){
+// blob (include/b200_l2f.h RAPTOR_GRU order) -> image.  scaled_gates (TMEM-A kernel): the GRU rows and biases carry the exponent scale of
+// their activation -- r, z rows times -log2(e), n rows times 2 log2(e) -- so the epilogue feeds the accumulators straight into ex2.
+inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates = false){
+    const float s_rz = scaled_gates ? -1.4426950408889634f : 1.0f, s_n = scaled_gates ? 2.8853900817779268f : 1.0f;
     constexpr int IN = 22, HD = 16, OUT = 4;
     const float* W1 = blob; const float* b1 = W1 + HD * IN;
     const float* Wih = b1 + HD; const float* bih = Wih + 3 * HD * HD;
@@ -54,13 +56,13 @@ inline void build_tc_image_host(float* img, const float* blob){
     }
     // G2 columns: 0..15 x1, 16..31 h, 32 -> b_hh, 33 -> b_ih (A holds 1.0 in both)
     for(int j = 0; j < 2 * HD; j++){            // r, z rows
-        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, j, k, Wih[j * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 16 + k, Whh[j * HD + k]); }
-        put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 32, bhh[j]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 33, bih[j]);
+        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, j, k, s_rz * Wih[j * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 16 + k, s_rz * Whh[j * HD + k]); }
+        put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 32, s_rz * bhh[j]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 33, s_rz * bih[j]);
     }
     for(int j = 0; j < HD; j++){                // n_x rows 32..47, n_h rows 48..63
-        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, k, Wih[(2 * HD + j) * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 16 + k, Whh[(2 * HD + j) * HD + k]); }
-        put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, 33, bih[2 * HD + j]);
-        put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 32, bhh[2 * HD + j]);
+        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, k, s_n * Wih[(2 * HD + j) * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 16 + k, s_n * Whh[(2 * HD + j) * HD + k]); }
+        put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, 33, s_n * bih[2 * HD + j]);
+        put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 32, s_n * bhh[2 * HD + j]);
     }
     for(int n = 0; n < OUT; n++){
         for(int k = 0; k < HD; k++) put(TcImage::B3_HI, TcImage::B3_LO, 16, n, k, W2[n * HD + k]);
@@ -71,8 +73,8 @@ inline void build_tc_image_host(float* img, const float* blob){
     for(int n = 0; n < OUT; n++) img[TcImage::W2T + 64 + n] = b2[n];
     for(int k = 0; k < IN; k++) for(int n = 0; n < HD; n++) img[TcImage::W1T + k * HD + n] = W1[n * IN + k];
     for(int n = 0; n < HD; n++) img[TcImage::W1T + IN * HD + n] = b1[n];
-    for(int j = 0; j < 2 * HD; j++) img[TcImage::BIAS2 + j] = bih[j] + bhh[j];
-    for(int j = 0; j < HD; j++){ img[TcImage::BIAS2 + 32 + j] = bih[2 * HD + j]; img[TcImage::BIAS2 + 48 + j] = bhh[2 * HD + j]; }
+    for(int j = 0; j < 2 * HD; j++) img[TcImage::BIAS2 + j] = s_rz * (bih[j] + bhh[j]);
+    for(int j = 0; j < HD; j++){ img[TcImage::BIAS2 + 32 + j] = s_n * bih[2 * HD + j]; img[TcImage::BIAS2 + 48 + j] = s_n * bhh[2 * HD + j]; }
 }
 
 // ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
@@ -178,7 +180,8 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
     }
 }
 // env_step twin for the compiled block (NOISE: action noise as in env_step; Langevin target as in env_step)
-template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, class PC>
+// FAST: default-math variant (min/max clamps, MUFU reciprocal square root for the quaternion, MUFU Box-Muller for the Langevin target)
+template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, bool FAST = false, class PC>
 __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
                                                   float* __restrict__ hist_ptr, size_t n){
     float setpoint[4];
@@ -187,7 +190,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
     for(int i = 0; i < 4; i++){
         float a = action[i];
         if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_ACTION_NOISE]);
-        setpoint[i] = clampf(a, -1.0f, 1.0f) * d.half_range + amin + d.half_range;
+        setpoint[i] = clamp_t<FAST>(a, -1.0f, 1.0f) * d.half_range + amin + d.half_range;
     }
     const float dt = d.dt;
     const float dt2 = dt / 2.0f, dt3 = dt / 3.0f, dt6 = dt / 6.0f;
@@ -224,20 +227,27 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
         float nrm = 0.0f;
 #pragma unroll
         for(int i = 0; i < 4; i++) nrm += st.x[X_ORI + i] * st.x[X_ORI + i];
-        nrm = sqrtf(nrm);
+        if constexpr(FAST){
+            const float inv = rsqrt_approx(nrm);
 #pragma unroll
-        for(int i = 0; i < 4; i++) st.x[X_ORI + i] = st.x[X_ORI + i] / nrm;
+            for(int i = 0; i < 4; i++) st.x[X_ORI + i] = st.x[X_ORI + i] * inv;
+        }
+        else{
+            nrm = sqrtf(nrm);
+#pragma unroll
+            for(int i = 0; i < 4; i++) st.x[X_ORI + i] = st.x[X_ORI + i] / nrm;
+        }
 #pragma unroll
         for(int i = 0; i < 3; i++){
-            st.x[X_POS + i] = clampf(st.x[X_POS + i], -100000.0f, 100000.0f);
-            st.x[X_VEL + i] = clampf(st.x[X_VEL + i], -100000.0f, 100000.0f);
-            st.x[X_OMEGA + i] = clampf(st.x[X_OMEGA + i], -100000.0f, 100000.0f);
+            st.x[X_POS + i] = clamp_t<FAST>(st.x[X_POS + i], -100000.0f, 100000.0f);
+            st.x[X_VEL + i] = clamp_t<FAST>(st.x[X_VEL + i], -100000.0f, 100000.0f);
+            st.x[X_OMEGA + i] = clamp_t<FAST>(st.x[X_OMEGA + i], -100000.0f, 100000.0f);
         }
     }
 #pragma unroll
     for(int i = 0; i < 4; i++) st.last_action[i] = action[i];
 #pragma unroll
-    for(int i = 0; i < 4; i++) st.x[X_RPM + i] = clampf(st.x[X_RPM + i], amin, amax);
+    for(int i = 0; i < 4; i++) st.x[X_RPM + i] = clamp_t<FAST>(st.x[X_RPM + i], amin, amax);
     if constexpr(Spec::H == 1){
 #pragma unroll
         for(int i = 0; i < 4; i++) st.hist[i] = action[i];
@@ -255,7 +265,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
 #pragma unroll
             for(int dim = 0; dim < 3; dim++){
                 const float x_prev = st.lang[6 + dim], v_prev = st.lang[9 + dim];
-                const float dW = sqrt_dt * rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, 1.0f);
+                const float dW = sqrt_dt * rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, 1.0f);
                 const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
                 const float x_next = x_prev + v_next * dt;
                 st.lang[6 + dim] = x_next; st.lang[9 + dim] = v_next;
@@ -525,6 +535,7 @@ struct TsSmem {
 };
 template <class Spec, bool FAST, bool UNIFORM, bool ROLLED_RK4>
 __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
+    static_assert(FAST, "the TMEM-A kernel reads the scaled-gate image (build_tc_image_host(..., true)): default math only");
     constexpr int HD = 16;
     extern __shared__ __align__(1024) unsigned char smraw[];
     float* sm_b = reinterpret_cast<float*>(smraw + TsSmem::B);
@@ -688,14 +699,14 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
             tc::tmem_ld16(tmem_base + lane_off + C_D2 + 48, nh);
             tc::tmem_ld_wait();
 #pragma unroll
-            for(int j = 0; j < HD; j++) nx[j] = tanhf_<FAST>((nx[j] + bias[32 + j]) + (nh[j] + bias[48 + j]) * sigmoidf_<FAST>(r[j] + bias[j]));
+            for(int j = 0; j < HD; j++) nx[j] = tanh_of_scaled((nx[j] + bias[32 + j]) + (nh[j] + bias[48 + j]) * sigmoid_of_scaled(r[j] + bias[j]));   // scaled image
             float z[HD], hh[HD], hl[HD];
             tc::tmem_ld16(tmem_base + lane_off + C_D2 + 16, z);
             tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
             tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
             tc::tmem_ld_wait();
 #pragma unroll
-            for(int j = 0; j < HD; j++){ const float zz = sigmoidf_<FAST>(z[j] + bias[16 + j]); hn[j] = (1.0f - zz) * nx[j] + zz * (hh[j] + hl[j]); }
+            for(int j = 0; j < HD; j++){ const float zz = sigmoid_of_scaled(z[j] + bias[16 + j]); hn[j] = fmaf(zz, (hh[j] + hl[j]) - nx[j], nx[j]); }   // (1 - z) n + z h
         }
         // ---- dense 2 (16 -> 4) on the CUDA cores
         float act[4];
@@ -719,9 +730,9 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        if(Spec::H == 1 || active) env_step_compiled<Spec, ROLLED_RK4>(st, p, d, act, rng, hist_ptr, n);
+        if(Spec::H == 1 || active) env_step_compiled<Spec, ROLLED_RK4, false, true>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
-        const float rw = env_reward(p, ri, act, st.x, term, d.dt);
+        const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
         if(a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
         if(!done){ ret += rw; eplen += 1; done = term; }
