@@ -264,9 +264,9 @@ int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid){
     return B200L2F_OK;
 }
 
-template <class Spec, bool FAST, bool UNIFORM, bool ROLLED_RK4>
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL>
 int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
-    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, ROLLED_RK4>;
+    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -287,11 +287,11 @@ int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
     return B200L2F_OK;
 }
 
-template <class Spec, int OUT, bool UNIFORM, bool ROLLED_RK4>
+template <class Spec, int OUT, bool UNIFORM, bool AXIAL>
 int launch_rollout_mlp_ts(b200l2f_handle* h, RolloutArgs a){
     constexpr int IN = Spec::OBS_DIM;
     using SM = MlpTsSmem<IN, OUT>;
-    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM, ROLLED_RK4>;
+    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM, AXIAL>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -811,6 +811,9 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     const bool constw = h->weights_in_constant_bank;
     // observation / action noise present: the CUDA-core kernel carries the Box-Muller draws; the tcgen05 kernels are the noise-free fast path
     const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && !noise;
+    // every vehicle thrusts along body z with diagonal inertia (true for all reference vehicles; B200L2F_DYNAMICS=general forces the full matrices)
+    const bool allow_axial = [](){ const char* e = std::getenv("B200L2F_DYNAMICS"); return !(e && std::string(e) == "general"); }();
+    const bool axial = allow_axial && (h->features & 4) == 0;
     auto go = [&](auto spec) -> int {
         using Spec = decltype(spec);
         if(tensor_cores){
@@ -819,9 +822,8 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
             // shared-memory-A variant (2 CTAs/SM).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
             static const bool a_in_tmem = [](){ const char* e = std::getenv("B200L2F_A"); return !(e && std::string(e) == "smem"); }();
             if(a_in_tmem && fast){
-                static const bool rolled_rk4 = [](){ const char* e = std::getenv("B200L2F_RK4"); return e && std::string(e) == "rolled"; }();
                 if(!uniform) return launch_rollout_ts<Spec, true, false, false>(h, a);
-                return rolled_rk4 ? launch_rollout_ts<Spec, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false>(h, a);
+                return axial ? launch_rollout_ts<Spec, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false>(h, a);
             }
             static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
             if(!fast) return launch_rollout_tc<Spec, false, false, true>(h, a);
@@ -852,9 +854,8 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
             const bool uniform = (h->features & 2) == 0;
             auto gots = [&](auto spec) -> int {
                 using Spec = decltype(spec);
-                static const bool rolled_rk4 = [](){ const char* e = std::getenv("B200L2F_RK4"); return e && std::string(e) == "rolled"; }();
                 if(!uniform) return o8 ? launch_rollout_mlp_ts<Spec, 8, false, false>(h, a) : launch_rollout_mlp_ts<Spec, 4, false, false>(h, a);
-                if(rolled_rk4) return o8 ? launch_rollout_mlp_ts<Spec, 8, true, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, true>(h, a);
+                if(axial) return o8 ? launch_rollout_mlp_ts<Spec, 8, true, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, true>(h, a);
                 return o8 ? launch_rollout_mlp_ts<Spec, 8, true, false>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, false>(h, a);
             };
             rc = h->kind == KIND_RAPTOR ? gots(SpecRaptor{}) : gots(SpecTeacher{});
@@ -909,14 +910,16 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     };
     std::memcpy(a.row, h->h_env_row, sizeof(a.row));
     const bool follow = h->params_follow_env_row;
-    // the collection kernel carries the reset samplers next to the step: the rolled RK4 stage loop keeps its code inside the instruction
-    // cache (+8 % measured, profiles/r01_configs34.md); B200L2F_RK4=unrolled selects the straight-line integrator
-    static const bool rolled_rk4 = [](){ const char* e = std::getenv("B200L2F_RK4"); return !(e && std::string(e) == "unrolled"); }();
-    auto gots2 = [&](auto spec, auto dr_c, auto follow_c, auto rolled_c) -> int {
+    // axial vehicles (see b200l2f_rollout): decided from the nominal row when the columns follow it (domain randomisation keeps the property)
+    const bool allow_axial = [](){ const char* e = std::getenv("B200L2F_DYNAMICS"); return !(e && std::string(e) == "general"); }();
+    bool row_axial = allow_axial;
+    for(int r = 0; r < 4; r++) if(a.row[P_THRUST_DIR + 3 * r] != 0.0f || a.row[P_THRUST_DIR + 3 * r + 1] != 0.0f || a.row[P_THRUST_DIR + 3 * r + 2] != 1.0f) row_axial = false;
+    for(int i = 0; i < 9; i++) if(i % 4 != 0 && (a.row[P_J + i] != 0.0f || a.row[P_JINV + i] != 0.0f)) row_axial = false;
+    auto gots2 = [&](auto spec, auto dr_c, auto follow_c, auto axial_c) -> int {
         using Spec = SpecCompactCode<decltype(spec)>;
         constexpr bool DR = decltype(dr_c)::value;
         using SM = MlpTsSmem<Spec::OBS_DIM, 4>;
-        auto kern = k_collect_ts<Spec, DR, decltype(follow_c)::value, decltype(rolled_c)::value>;
+        auto kern = k_collect_ts<Spec, DR, decltype(follow_c)::value, decltype(axial_c)::value>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL_COLLECT));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int sms = 0;
@@ -930,8 +933,8 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
         return (int)B200L2F_OK;
     };
     auto gots = [&](auto spec, auto dr_c) -> int {
-        if(follow) return rolled_rk4 ? gots2(spec, dr_c, std::true_type{}, std::true_type{}) : gots2(spec, dr_c, std::true_type{}, std::false_type{});
-        return gots2(spec, dr_c, std::false_type{}, std::true_type{});
+        if(follow) return row_axial ? gots2(spec, dr_c, std::true_type{}, std::true_type{}) : gots2(spec, dr_c, std::true_type{}, std::false_type{});
+        return gots2(spec, dr_c, std::false_type{}, std::false_type{});
     };
     const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     if(tensor_cores){

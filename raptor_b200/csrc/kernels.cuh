@@ -82,13 +82,17 @@ __host__ __device__ constexpr bool mdp_uniform_index(int i){
            (i >= P_LANGEVIN_GAMMA && i <= P_LANGEVIN_ALPHA);
 }
 // features of the parameter set that select kernel variants: bit0 = some observation/action noise std != 0,
-// bit1 = some environment's "uniform" MDP parameter differs from environment 0's
+// bit1 = some environment's "uniform" MDP parameter differs from environment 0's, bit2 = some vehicle is not "axial" (a rotor thrust
+// direction other than body z, or an off-diagonal entry in J / J^-1): the fused kernels then keep the general rotor / inertia matrices
 __global__ void k_param_features(const float* __restrict__ params, int n, int* __restrict__ features){
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     int f = 0;
     if(e < n){
-        for(int i = P_NOISE_POS; i <= P_ACTION_NOISE; i++) if(params[(size_t)i * n + e] != 0.0f) f |= 1;
-        for(int i = 0; i < PARAMS_DIM; i++) if(mdp_uniform_index(i) && params[(size_t)i * n + e] != params[(size_t)i * n]) f |= 2;
+        auto P = [&](int i){ return params[(size_t)i * n + e]; };
+        for(int i = P_NOISE_POS; i <= P_ACTION_NOISE; i++) if(P(i) != 0.0f) f |= 1;
+        for(int i = 0; i < PARAMS_DIM; i++) if(mdp_uniform_index(i) && P(i) != params[(size_t)i * n]) f |= 2;
+        for(int r = 0; r < 4; r++) if(P(P_THRUST_DIR + 3 * r) != 0.0f || P(P_THRUST_DIR + 3 * r + 1) != 0.0f || P(P_THRUST_DIR + 3 * r + 2) != 1.0f) f |= 4;
+        for(int i = 0; i < 9; i++) if(i % 4 != 0 && (P(P_J + i) != 0.0f || P(P_JINV + i) != 0.0f)) f |= 4;
     }
     f = __reduce_or_sync(0xffffffffu, f);
     if((threadIdx.x & 31) == 0 && f) atomicOr(features, f);

@@ -225,7 +225,7 @@ __device__ __forceinline__ void mlp_ts_epilogue(const TsCtx& c){
 // closed-loop rollout, deterministic MLP actor (head identity or squash-eval), persistent (tile, time-chunk) work queue as in
 // k_rollout_raptor_ts (the actor is stateless, so a chunk hands over the environment state and the episode accumulators only)
 // ---------------------------------------------------------------------------------------------------------------
-template <class Spec, int OUT, bool UNIFORM, bool ROLLED_RK4>
+template <class Spec, int OUT, bool UNIFORM, bool AXIAL>
 __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     constexpr int IN = Spec::OBS_DIM;
     using SM = MlpTsSmem<IN, OUT>;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        env_step_compiled<Spec, ROLLED_RK4, false, true>(st, p, d, act, rng, hist_ptr, n);
+        env_step_compiled<Spec, false, false, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------
 // FOLLOW: every parameter column was filled from a.row before (initial_parameters / sample_initial_parameters / earlier resets) -- the
 // non-randomised entries equal the row, so the MDP constants are read from the constant bank and a reset writes only the randomised entries.
-template <class Spec, bool DR, bool FOLLOW, bool ROLLED_RK4>
+// The RK4 stages are one rolled loop here: next to the reset samplers the straight-line integrator would not fit the instruction cache.
+template <class Spec, bool DR, bool FOLLOW, bool AXIAL>
 __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__ CollectArgs a, const float* __restrict__ tc_image, int* __restrict__ sched){
     constexpr int IN = Spec::OBS_DIM, OUT = 4;
     constexpr int D = IN + 15, W = IN + 12, WS = W + 1;   // W columns written per step; WS: row stride of the staging window
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             }
             RewardInputs ri;
             reward_inputs(ri, st);
-            env_step_compiled<Spec, ROLLED_RK4, true, true>(st, p, d, act, rng, hist_ptr, n);
+            env_step_compiled<Spec, true, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
             const bool term = env_terminated(p, st.x);
             const float r = env_reward<true>(p, ri, act, st.x, term, d.dt);
             ep_ret += r; ep_step += 1;

@@ -128,8 +128,10 @@ __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_c
     ParamsCompiledT<UNIFORM, NC, FOLLOW> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
     return p;
 }
-// multirotor dynamics with the rotor matrices (same physics as dynamics() in env.cuh; thrust/torque summed as matrix-vector products)
-template <class PC>
+// multirotor dynamics with the rotor matrices (same physics as dynamics() in env.cuh; thrust/torque summed as matrix-vector products).
+// AXIAL: every rotor thrusts along body z and J, J^-1 are diagonal (all reference vehicles; k_param_features bit2 guards it): the zero
+// products are dropped, the remaining operations keep the order of the general form, so both forms give the same bits.
+template <bool AXIAL = false, class PC>
 __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvariants& d, const float* __restrict__ x, const float* __restrict__ setpoint, float* __restrict__ dx){
     float tm[4];
 #pragma unroll
@@ -140,9 +142,10 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
     float thrust[3], torque[3];
 #pragma unroll
     for(int i = 0; i < 3; i++){
-        thrust[i] = p.c(C_AF + 4 * i) * tm[0] + p.c(C_AF + 4 * i + 1) * tm[1] + p.c(C_AF + 4 * i + 2) * tm[2] + p.c(C_AF + 4 * i + 3) * tm[3];
+        if constexpr(!AXIAL) thrust[i] = p.c(C_AF + 4 * i) * tm[0] + p.c(C_AF + 4 * i + 1) * tm[1] + p.c(C_AF + 4 * i + 2) * tm[2] + p.c(C_AF + 4 * i + 3) * tm[3];
         torque[i] = p.c(C_AT + 4 * i) * tm[0] + p.c(C_AT + 4 * i + 1) * tm[1] + p.c(C_AT + 4 * i + 2) * tm[2] + p.c(C_AT + 4 * i + 3) * tm[3];
     }
+    if constexpr(AXIAL) thrust[2] = ((tm[0] + tm[1]) + tm[2]) + tm[3];
 #pragma unroll
     for(int i = 0; i < 3; i++) dx[X_POS + i] = x[X_VEL + i];
     const float q0 = x[X_ORI], q1 = x[X_ORI + 1], q2 = x[X_ORI + 2], q3 = x[X_ORI + 3];
@@ -152,12 +155,22 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
     dx[X_ORI + 2] = ( q0 * w1 + q3 * w0 - q1 * w2) * 0.5f;
     dx[X_ORI + 3] = ( q0 * w2 + q1 * w1 - q2 * w0) * 0.5f;
     {
-        float v0 = (q2 * thrust[2] - q3 * thrust[1]) * 2.0f;
-        float v1 = (q3 * thrust[0] - q1 * thrust[2]) * 2.0f;
-        float v2 = (q1 * thrust[1] - q2 * thrust[0]) * 2.0f;
-        float o0 = q2 * v2 - q3 * v1, o1 = q3 * v0 - q1 * v2, o2 = q1 * v1 - q2 * v0;
-        o0 += v0 * q0; o1 += v1 * q0; o2 += v2 * q0;
-        o0 += thrust[0]; o1 += thrust[1]; o2 += thrust[2];
+        float o0, o1, o2;
+        if constexpr(AXIAL){   // rotate (0, 0, T) by q
+            const float T = thrust[2];
+            const float v0 = (q2 * T) * 2.0f, v1 = (-(q1 * T)) * 2.0f;
+            o0 = -(q3 * v1); o1 = q3 * v0; o2 = q1 * v1 - q2 * v0;
+            o0 += v0 * q0; o1 += v1 * q0;
+            o2 += T;
+        }
+        else{
+            float v0 = (q2 * thrust[2] - q3 * thrust[1]) * 2.0f;
+            float v1 = (q3 * thrust[0] - q1 * thrust[2]) * 2.0f;
+            float v2 = (q1 * thrust[1] - q2 * thrust[0]) * 2.0f;
+            o0 = q2 * v2 - q3 * v1; o1 = q3 * v0 - q1 * v2; o2 = q1 * v1 - q2 * v0;
+            o0 += v0 * q0; o1 += v1 * q0; o2 += v2 * q0;
+            o0 += thrust[0]; o1 += thrust[1]; o2 += thrust[2];
+        }
         dx[X_VEL + 0] = o0 * d.inv_mass + p.c(C_GRAVITY + 0) + d.fa[0];
         dx[X_VEL + 1] = o1 * d.inv_mass + p.c(C_GRAVITY + 1) + d.fa[1];
         dx[X_VEL + 2] = o2 * d.inv_mass + p.c(C_GRAVITY + 2) + d.fa[2];
@@ -165,12 +178,18 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
     {
         float v[3];
 #pragma unroll
-        for(int i = 0; i < 3; i++) v[i] = p.c(C_J + 3 * i) * w0 + p.c(C_J + 3 * i + 1) * w1 + p.c(C_J + 3 * i + 2) * w2;
+        for(int i = 0; i < 3; i++){
+            if constexpr(AXIAL) v[i] = p.c(C_J + 4 * i) * (i == 0 ? w0 : (i == 1 ? w1 : w2));
+            else v[i] = p.c(C_J + 3 * i) * w0 + p.c(C_J + 3 * i + 1) * w1 + p.c(C_J + 3 * i + 2) * w2;
+        }
         const float t0 = torque[0] - (w1 * v[2] - w2 * v[1]);
         const float t1 = torque[1] - (w2 * v[0] - w0 * v[2]);
         const float t2 = torque[2] - (w0 * v[1] - w1 * v[0]);
 #pragma unroll
-        for(int i = 0; i < 3; i++) dx[X_OMEGA + i] = p.c(C_JINV + 3 * i) * t0 + p.c(C_JINV + 3 * i + 1) * t1 + p.c(C_JINV + 3 * i + 2) * t2 + d.ta[i];
+        for(int i = 0; i < 3; i++){
+            if constexpr(AXIAL) dx[X_OMEGA + i] = p.c(C_JINV + 4 * i) * (i == 0 ? t0 : (i == 1 ? t1 : t2)) + d.ta[i];
+            else dx[X_OMEGA + i] = p.c(C_JINV + 3 * i) * t0 + p.c(C_JINV + 3 * i + 1) * t1 + p.c(C_JINV + 3 * i + 2) * t2 + d.ta[i];
+        }
     }
 #pragma unroll
     for(int r = 0; r < 4; r++){
@@ -181,7 +200,7 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
 }
 // env_step twin for the compiled block (NOISE: action noise as in env_step; Langevin target as in env_step)
 // FAST: default-math variant (min/max clamps, MUFU reciprocal square root for the quaternion, MUFU Box-Muller for the Langevin target)
-template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, bool FAST = false, class PC>
+template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, bool FAST = false, bool AXIAL = false, class PC>
 __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
                                                   float* __restrict__ hist_ptr, size_t n){
     float setpoint[4];
@@ -200,7 +219,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
         for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i]; tmp[i] = st.x[i]; }
 #pragma unroll 1
         for(int s = 0; s < 4; s++){
-            dynamics_compiled(p, d, tmp, setpoint, k);
+            dynamics_compiled<AXIAL>(p, d, tmp, setpoint, k);
             const float wa = (s == 0 || s == 3) ? dt6 : dt3;
             const float wt = (s == 2) ? dt : dt2;
 #pragma unroll
@@ -210,16 +229,16 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
         for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i];
     }
     else{
-    dynamics_compiled(p, d, st.x, setpoint, k);
+    dynamics_compiled<AXIAL>(p, d, st.x, setpoint, k);
 #pragma unroll
     for(int i = 0; i < X_DIM; i++){ acc[i] = st.x[i] + dt6 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
-    dynamics_compiled(p, d, tmp, setpoint, k);
+    dynamics_compiled<AXIAL>(p, d, tmp, setpoint, k);
 #pragma unroll
     for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt2 * k[i]; }
-    dynamics_compiled(p, d, tmp, setpoint, k);
+    dynamics_compiled<AXIAL>(p, d, tmp, setpoint, k);
 #pragma unroll
     for(int i = 0; i < X_DIM; i++){ acc[i] += dt3 * k[i]; tmp[i] = st.x[i] + dt * k[i]; }
-    dynamics_compiled(p, d, tmp, setpoint, k);
+    dynamics_compiled<AXIAL>(p, d, tmp, setpoint, k);
 #pragma unroll
     for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i] + dt6 * k[i];
     }
@@ -533,7 +552,7 @@ struct TsSmem {
     static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
     static constexpr int TOTAL = BAR + 32;
 };
-template <class Spec, bool FAST, bool UNIFORM, bool ROLLED_RK4>
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL>
 __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     static_assert(FAST, "the TMEM-A kernel reads the scaled-gate image (build_tc_image_host(..., true)): default math only");
     constexpr int HD = 16;
@@ -730,7 +749,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        if(Spec::H == 1 || active) env_step_compiled<Spec, ROLLED_RK4, false, true>(st, p, d, act, rng, hist_ptr, n);
+        if(Spec::H == 1 || active) env_step_compiled<Spec, false, false, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;

@@ -484,3 +484,52 @@ def test_mlp_tensor_core_rollout_properties(rb):
         assert np.array_equal(r1, rf)
         close_relative(o1["actions"][:15], of["actions"][:15], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions ts vs fp32")
         close_relative(o1["states"][:16], of["states"][:16], 1e-4, STATE_GROUPS, "states ts vs fp32")
+
+
+def test_axial_dynamics_specialisation(rb, port):
+    """the tensor-core kernels drop the zero products of the rotor / inertia matrices when every vehicle thrusts along body z with diagonal
+    inertia (k_param_features bit2).  (1) same bits as the general form on such vehicles; (2) a tilted rotor and an off-diagonal inertia
+    entry switch the general form on, which must agree with the CUDA-core kernel and the oracle"""
+    import os
+    n, T = 300, 40
+    blob = np.load(os.path.join(G, "raptor_kat.npz"))["blob"]
+
+    def run(params=None, gemm=rb.GEMM_TCGEN05_3XTF32, general=False):
+        if general:
+            os.environ["B200L2F_DYNAMICS"] = "general"
+        try:
+            e = rb.VectorEnvironment(n, rb.SPEC_RAPTOR)
+            e.initialize_rng(17, warmup=16)
+            if params is not None:
+                e.set_parameters(params)
+            e.sample_initial_state()
+            e.load_policy(blob, gemm=gemm)
+            s0, r0 = e.get_state(), e.get_rng()
+            o = e.rollout(T, record=("states", "actions", "rewards"))
+            return e, s0, r0, o
+        finally:
+            os.environ.pop("B200L2F_DYNAMICS", None)
+
+    _, _, _, oa = run()
+    _, _, _, og = run(general=True)
+    for k in ("states", "actions", "rewards"):
+        assert np.array_equal(oa[k], og[k]), k
+    # non-axial vehicles
+    e0 = rb.VectorEnvironment(n, rb.SPEC_RAPTOR)
+    params = e0.get_parameters()
+    rs = np.random.RandomState(2)
+    tilt = rs.normal(0, 0.05, (n, 4, 2)).astype(np.float32)
+    d = params[:, 12:24].reshape(n, 4, 3)
+    d[:, :, 0] = tilt[:, :, 0]; d[:, :, 1] = tilt[:, :, 1]; d[:, :, 2] = np.sqrt(1 - tilt[:, :, 0] ** 2 - tilt[:, :, 1] ** 2)
+    J = params[:, 64:73].reshape(n, 3, 3).astype(np.float64)
+    J[:, 0, 1] = J[:, 1, 0] = 0.1 * J[:, 0, 0]
+    params[:, 64:73] = J.reshape(n, 9).astype(np.float32)
+    params[:, 73:82] = np.linalg.inv(J).reshape(n, 9).astype(np.float32)
+    et, s0, r0, ot = run(params)
+    _, _, _, of = run(params, gemm=rb.GEMM_FP32_CUDA_CORES)
+    pol = port.make_policy(blob)
+    want = port.rollout(B.SPEC_RAPTOR, pol, params, s0.copy(), r0.copy(), T)
+    assert not np.allclose(ot["states"][10], oa["states"][10], atol=1e-4)       # the perturbation matters
+    for got, name in ((ot, "tcgen05"), (of, "fp32")):
+        close_relative(got["actions"], want["actions"], 1e-4, {"action": (slice(0, 4), 0.1)}, name + " actions")
+        close_relative(got["states"], want["states"], 1e-4, STATE_GROUPS, name + " states")
