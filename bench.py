@@ -32,9 +32,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # algorithmic cost per env-step (restated in DESIGN.md "Rooflines")
-FLOP_ENV = 1100.0          # RK4 (4 dynamics evaluations) + observe + reward, fp32 CUDA cores
+FLOP_ENV = 1100.0          # reference algorithm: RK4 (4 dynamics evaluations) + observe + reward, fp32
 FLOP_POLICY_GEMM = 3904.0  # 2 * (22*16 + 48*16 + 48*16 + 16*4) multiply-accumulates, tensor-core eligible
 FLOP_POLICY_GATES = 150.0
+# what k_rollout_raptor_ts EXECUTES on the CUDA cores per environment step (ncu, profiles/r01_ncu_k_rollout_raptor_ts_v6_default_bench.txt):
+# fadd + fmul + 2 ffma thread instructions, and all thread instructions.  The actor's GEMMs run on tcgen05 and are not in these counts.
+TS_CUDA_CORE_FLOP = 1283.0
+TS_THREAD_INSTRUCTIONS = 1509.0
 BYTES_PER_ENV_LAUNCH = 4.0 * (2 * (48 + 16 + 2) + 145)   # read+write state, hidden, rng; read parameters (once per launch)
 
 DR_RANGES = [1.5, 5.0, 40, 1200, 0.02, 5.0, 0.1, 0.03, 0.10, 0.03, 0.30, 0.005, 0.05, 0.0, 0.3]  # sample_dynamics_parameters.cpp:48-64
@@ -295,18 +299,30 @@ def main():
         tensor_ach = steps_per_s_gpu * FLOP_POLICY_GEMM / 1e12
         hbm_ach = n * BYTES_PER_ENV_LAUNCH / per_launch_s / 1e9
         fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-        fp32_ach = steps_per_s_gpu * (FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES) / 1e12
+        issue_peak = 148 * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12          # thread instructions / s: 4 schedulers x 32 lanes per SM and clock
+        if args.tcgen05:
+            fp32_ach = steps_per_s_gpu * TS_CUDA_CORE_FLOP / 1e12
+            fp32_note = "executed CUDA-core fp32 FLOPs of k_rollout_raptor_ts (ncu op counts per env-step x measured rate); the actor GEMMs are on the tensor pipe"
+            issue = {"achieved": steps_per_s_gpu * TS_THREAD_INSTRUCTIONS / 1e12, "peak": issue_peak, "unit": "T thread-instructions/s",
+                     "frac": steps_per_s_gpu * TS_THREAD_INSTRUCTIONS / 1e12 / issue_peak, "thread_instructions_per_env_step": TS_THREAD_INSTRUCTIONS,
+                     "note": "the ceiling that binds this kernel: instruction issue slots (148 SMs x 4 schedulers x 32 lanes x max SM clock); "
+                             "per-step instruction count from the committed ncu capture, rate measured live"}
+        else:
+            fp32_ach = steps_per_s_gpu * (FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES) / 1e12
+            fp32_note = "algorithmic fp32 FLOPs (SURVEY 8d) of the CUDA-core kernel, actor GEMMs included"
+            issue = None
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` capture of this exact configuration
         # (39.44 MB read + 1.98 MB written: parameters / state in, state out; the per-chunk hand-over lives in the 126 MB L2)
         traffic, traffic_src = None, None
         if args.tcgen05 and n == 65536 and T == 1000 and not args.accurate_math:
-            traffic, traffic_src = 41.42e6, "profiles/r01_ncu_k_rollout_raptor_ts_T1000_default_bench.txt"
+            traffic, traffic_src = 42.64e6, "profiles/r01_ncu_k_rollout_raptor_ts_v6_default_bench.txt"
         roofline = {"bound": "tensor", "achieved": tensor_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tensor_ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long launch)",
                     "kernel": "k_rollout_raptor_ts" if args.tcgen05 else "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,
                     "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": n * BYTES_PER_ENV_LAUNCH},
-                    "fp32_issue": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
-                                   "note": "dominant ceiling of this kernel (SURVEY 8d): algorithmic fp32 FLOPs / (148 SMs x 128 lanes x 2 x max SM clock); state, parameters and weights are on-chip for the whole launch"}}
+                    "fp32_issue": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak, "note": fp32_note},
+                    "issue": issue,
+                    "algorithmic_flop_per_env_step": FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-(timeout -s KILL 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -12) | tee gpurun_out/pytest_gpu16.log
-(timeout -s KILL 300 python bench.py --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200) | tee gpurun_out/bench_quick.log
-(B200L2F_DYNAMICS=general timeout -s KILL 300 python bench.py --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200) | tee gpurun_out/bench_quick_general.log
-(timeout -s KILL 200 python tools/bench_configs.py 2>&1 | tail -2 | cut -c1-260) | tee gpurun_out/configs34_ts.log
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:k_rollout -c 1 -o gpurun_out/prof_v6_ts_T1000 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_v6.log 2>&1
+tail -2 gpurun_out/ncu_v6.log | cut -c1-200
