@@ -1,7 +1,11 @@
 """Builds the engine's shared library in-tree with nvcc for sm_100a (no torch involved in the .so).
 
     python -m raptor_b200.build            # raptor_b200/lib/libb200l2f.so
+
+The engine is several translation units (one per family of heavy kernel instantiations) compiled in parallel and linked into ONE
+shared library; only the units whose sources changed are recompiled.
 """
+import concurrent.futures
 import os
 import shutil
 import subprocess
@@ -10,10 +14,23 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libb200l2f.so")
-SOURCES = ["engine.cu"]
-HEADERS = ["layout.h", "rng.cuh", "env.cuh", "samplers.cuh", "policy.cuh", "kernels.cuh", os.path.join("..", "..", "include", "b200_l2f.h")]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-shared"]
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
+LIB = os.environ.get("B200L2F_BUILD_LIB") or os.path.join(LIB_DIR, "libb200l2f.so")
+COMMON = ["layout.h", "fastmath.cuh", "rng.cuh", "env.cuh", "samplers.cuh", "policy.cuh", "kernels.cuh", "handle.h", "launch.h", "mlp.cuh",
+          os.path.join("..", "..", "include", "b200_l2f.h")]
+TC = ["tc.cuh", "rollout_tc.cuh"]
+# translation unit -> the headers it depends on besides COMMON
+SOURCES = {
+    "engine.cu": TC,
+    "rollout_fp32.cu": [],
+    "rollout_tc.cu": TC,
+    "rollout_ts.cu": TC,
+    "rollout_mlp.cu": [],
+    "rollout_mlp_ts.cu": TC + ["mlp_tc.cuh"],
+    "collect.cu": [],
+    "collect_ts.cu": TC + ["mlp_tc.cuh"],
+}
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
 def nvcc():
@@ -23,19 +40,47 @@ def nvcc():
     return exe
 
 
-def stale():
-    if not os.path.exists(LIB):
+def _obj(src):
+    return os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+
+
+def _mtime(path):
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def _unit_stale(src):
+    o = _obj(src)
+    if not os.path.exists(o):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS if os.path.exists(os.path.join(CSRC, s))]
-    return any(os.path.getmtime(d) > t for d in deps)
+    t = os.path.getmtime(o)
+    deps = [os.path.join(CSRC, d) for d in [src] + COMMON + SOURCES[src]]
+    return any(_mtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=()):
+def stale():
+    return not os.path.exists(LIB) or any(_unit_stale(s) or _mtime(_obj(s)) > os.path.getmtime(LIB) for s in SOURCES)
+
+
+def build(force=False, verbose=False, extra_flags=(), jobs=None):
     if not force and not stale():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    todo = [s for s in SOURCES if force or extra_flags or _unit_stale(s)]
+
+    def compile_unit(src):
+        cmd = [nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-c", "-o", _obj(src), os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, r
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=jobs or min(len(todo) or 1, os.cpu_count() or 1)) as pool:
+        for src, r in pool.map(compile_unit, todo):
+            if verbose or r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode:
+                raise RuntimeError("nvcc failed on %s" % src)
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

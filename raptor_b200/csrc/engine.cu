@@ -1,156 +1,21 @@
-// raptor_b200/csrc/engine.cu -- handle + C ABI (include/b200_l2f.h) of the B200-native quadrotor rollout engine.
+// raptor_b200/csrc/engine.cu -- C ABI (include/b200_l2f.h) of the B200-native quadrotor rollout engine: lifetime, RNG, parameters, state,
+// the vector-API calls, actor loading and the host side of the fused rollout / collection.
 //
-// The handle owns struct-of-arrays device buffers (parameters [145][n], K state slots [STATE_DIM][n], RNG [n], actor hidden state
-// [HD][n]); every entry point enqueues hand-written sm_100a kernels (kernels.cuh) on the handle's stream.  There is no CPU path.
-#include <cuda_runtime.h>
-#include <cstdio>
-#include <cstring>
-#include <cstdlib>
-#include <string>
-#include <vector>
-#include <new>
-#include <type_traits>
-
-#include "../../include/b200_l2f.h"
-#include "kernels.cuh"
-#include "rollout_tc.cuh"
-#include "mlp.cuh"
-#include "mlp_tc.cuh"
+// The handle (handle.h) owns struct-of-arrays device buffers (parameters [145][n], K state slots [STATE_DIM][n], RNG [n], actor hidden
+// state [HD][n]); every entry point enqueues hand-written sm_100a kernels on the handle's stream.  There is no CPU path.  The heavy kernel
+// instantiations live in rollout_*.cu / collect*.cu (launch.h).
+#include "launch.h"
+#include "rollout_tc.cuh"   // TcImage, build_tc_image_host
 
 using namespace b200l2f;
 
-namespace {
-
-thread_local std::string g_create_error;
-
-enum SpecKind { KIND_DEFAULT = 0, KIND_RAPTOR = 1, KIND_TEACHER = 2 };
-
-}  // namespace
-
-struct b200l2f_handle {
-    b200l2f_config cfg{};
-    int kind = 0; bool dr = false; int H = 0, obs_dim = 0, sdim = 0;
-    int n = 0;
-    cudaStream_t stream = nullptr; bool own_stream = false;
-    float* d_params = nullptr;       // [145][n]
-    float* d_env_row = nullptr;      // [145]
-    float h_env_row[B200L2F_PARAMS_DIM];
-    std::vector<float*> d_state;     // slots x [sdim][n]
-    uint64_t* d_rng = nullptr;
-    int* d_flags = nullptr;          // [0] error flag, [1] parameter features
-    bool features_dirty = true; int features = 0;
-    bool params_follow_env_row = false;   // every column was filled from h_env_row (initial / sampled parameters, collect's resets) and not edited since
-    float row0[B200L2F_PARAMS_DIM];   // parameter row of environment 0 (uniform MDP constants of the fused kernels)
-    // actor
-    bool policy_loaded = false; b200l2f_policy_desc pol{};
-    float* d_blob = nullptr; size_t blob_floats = 0;
-    float* d_hidden = nullptr; int* d_gru_step = nullptr;
-    int* d_sched = nullptr; size_t sched_ints = 0;     // work counter + per-tile progress of the time-chunked scheduler
-    float* d_acc_ret = nullptr; int* d_acc_len = nullptr;
-    float* d_tc_image = nullptr;     // tensor-core weight image (hi/lo planes of the three B operands, TMA source)
-    float* d_ts_image = nullptr;     // the same with scaled GRU gate rows (k_rollout_raptor_ts)
-    float* d_mlp_tc_image = nullptr; // same for an MLP actor (MlpTcImage<IN, OUT>), null when the actor has no tensor-core instantiation
-    std::vector<float> h_image;      // k-major actor image passed by value to the fused kernels (constant-bank weights)
-    bool weights_in_constant_bank = false; bool rolled = false;
-    // PPO runner bookkeeping (rl/components/on_policy_runner/on_policy_runner.h: episode_step, episode_return, truncated)
-    int* d_episode_step = nullptr; float* d_episode_return = nullptr; uint8_t* d_truncated = nullptr;
-    // staging
-    void* h_pinned = nullptr; size_t pinned_bytes = 0;
-    void* d_stage = nullptr; size_t stage_bytes = 0;
-    std::string err;
-    int64_t launches = 0;
-};
+namespace b200l2f {
+std::string& create_error(){ thread_local std::string e; return e; }
+}
 
 namespace {
-
-int fail(b200l2f_handle* h, int code, const std::string& msg){
-    if(h) h->err = msg; else g_create_error = msg;
-    return code;
-}
-#define CU(call) do{ cudaError_t e_ = (call); if(e_ != cudaSuccess){ return fail(h, B200L2F_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } }while(0)
-#define LAUNCH_CHECK() do{ h->launches++; cudaError_t e_ = cudaGetLastError(); if(e_ != cudaSuccess){ return fail(h, B200L2F_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); } }while(0)
-
-inline int grid_for(int n, int block){ return (n + block - 1) / block; }
-
-int ensure_pinned(b200l2f_handle* h, size_t bytes){
-    if(bytes <= h->pinned_bytes) return B200L2F_OK;
-    if(h->h_pinned){ cudaFreeHost(h->h_pinned); h->h_pinned = nullptr; h->pinned_bytes = 0; }
-    CU(cudaMallocHost(&h->h_pinned, bytes));
-    h->pinned_bytes = bytes;
-    return B200L2F_OK;
-}
-int ensure_stage(b200l2f_handle* h, size_t bytes){
-    if(bytes <= h->stage_bytes) return B200L2F_OK;
-    if(h->d_stage){ cudaFree(h->d_stage); h->d_stage = nullptr; h->stage_bytes = 0; }
-    CU(cudaMalloc(&h->d_stage, bytes));
-    h->stage_bytes = bytes;
-    return B200L2F_OK;
-}
-// is this host pointer page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory)?  Then the DMA engine can read/write it directly.
-bool is_pinned_host(const void* p){
-    cudaPointerAttributes attr;
-    if(cudaPointerGetAttributes(&attr, p) != cudaSuccess){ cudaGetLastError(); return false; }
-    return attr.type == cudaMemoryTypeHost;
-}
-// host -> device staging buffer, returns device pointer in *dev.  Pageable memory bounces through the handle's pinned buffer.
-int upload(b200l2f_handle* h, const void* src, size_t bytes, int memspace, const void** dev){
-    if(memspace == B200L2F_DEVICE){ *dev = src; return B200L2F_OK; }
-    int rc;
-    if((rc = ensure_stage(h, bytes))) return rc;
-    if(is_pinned_host(src)){
-        CU(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, h->stream));
-    }
-    else{
-        if((rc = ensure_pinned(h, bytes))) return rc;
-        std::memcpy(h->h_pinned, src, bytes);
-        CU(cudaMemcpyAsync(h->d_stage, h->h_pinned, bytes, cudaMemcpyHostToDevice, h->stream));
-    }
-    *dev = h->d_stage;
-    return B200L2F_OK;
-}
-// device result buffer: the caller's pointer (device) or the staging buffer (host); finish() copies back
-int result_buffer(b200l2f_handle* h, void* dst, size_t bytes, int memspace, void** dev, size_t stage_offset = 0){
-    if(memspace == B200L2F_DEVICE){ *dev = dst; return B200L2F_OK; }
-    int rc;
-    if((rc = ensure_stage(h, stage_offset + bytes))) return rc;
-    *dev = (char*)h->d_stage + stage_offset;
-    return B200L2F_OK;
-}
-int download(b200l2f_handle* h, void* dst, const void* dev, size_t bytes, int memspace){
-    if(memspace == B200L2F_DEVICE) return B200L2F_OK;
-    int rc;
-    if(is_pinned_host(dst)){
-        CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        return B200L2F_OK;
-    }
-    if((rc = ensure_pinned(h, bytes))) return rc;
-    CU(cudaMemcpyAsync(h->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    std::memcpy(dst, h->h_pinned, bytes);
-    return B200L2F_OK;
-}
-int transpose(b200l2f_handle* h, const float* in, float* out, int rows, int cols){
-    dim3 block(32, 8), grid((cols + 31) / 32, (rows + 31) / 32);
-    k_transpose<<<grid, block, 0, h->stream>>>(in, out, rows, cols);
-    LAUNCH_CHECK();
-    return B200L2F_OK;
-}
-int check_slot(b200l2f_handle* h, int slot){
-    if(slot < 0 || slot >= (int)h->d_state.size()) return fail(h, B200L2F_ERR_ARGUMENT, "state slot out of range");
-    return B200L2F_OK;
-}
 void nominal_parameters(int spec, float* p);
 
-template <class F>
-int dispatch_spec(b200l2f_handle* h, F&& f){
-    switch(h->kind){
-        case KIND_DEFAULT: return f(SpecDefault{});
-        case KIND_RAPTOR: return f(SpecRaptor{});
-        case KIND_TEACHER: return f(SpecTeacher{});
-    }
-    return fail(h, B200L2F_ERR_UNSUPPORTED, "unknown spec");
-}
 
 // nominal parameter values of the supported specifications: rl/environments/l2f/parameters/dynamics/crazyflie.h:10-123,
 // parameters/default.h:34-134 (reward, termination, noise, DR ranges of the DR-enabled factory, trajectory), parameters/init/default.h:22-31
@@ -190,6 +55,10 @@ void nominal_parameters(int spec, float* p){
     p[P_LANGEVIN_GAMMA] = 1; p[P_LANGEVIN_OMEGA] = 2; p[P_LANGEVIN_SIGMA] = (float)0.5; p[P_LANGEVIN_ALPHA] = (float)0.01;
 }
 
+}  // namespace
+
+namespace b200l2f {
+
 int refresh_features(b200l2f_handle* h){
     if(!h->features_dirty) return B200L2F_OK;
     CU(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->stream));
@@ -202,41 +71,6 @@ int refresh_features(b200l2f_handle* h){
     return B200L2F_OK;
 }
 
-template <class Spec, bool NOISE, bool FAST, bool CONSTW, bool ROLLED = false>
-int launch_rollout_raptor(b200l2f_handle* h, const RolloutArgs& a){
-    constexpr int IN = 22, HD = 16, OUT = 4;
-    constexpr int IMG = RaptorImage<IN, HD, OUT>::SIZE;
-    auto kern = k_rollout_raptor<Spec, IN, HD, OUT, NOISE, FAST, CONSTW, ROLLED>;
-    const size_t smem = (size_t)((CONSTW ? 0 : IMG) + P_DYN_DIM * BLOCK + (ROLLED ? RaptorScratch<IN, HD>::ROWS * BLOCK : 0)) * sizeof(float);
-    static bool configured[8] = {};   // per device
-    int dev = h->cfg.device & 7;
-    if(!configured[dev]){
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = true;
-    }
-    if constexpr(CONSTW){
-        kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, *reinterpret_cast<const WeightBlock<IMG>*>(h->h_image.data()));
-    }
-    else{
-        kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, WeightBlock<1>{});
-    }
-    LAUNCH_CHECK();
-    return B200L2F_OK;
-}
-
-template <class Spec, bool FAST, bool UNIFORM, bool G1_TC>
-int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
-    auto kern = k_rollout_raptor_tc<Spec, FAST, UNIFORM, G1_TC>;
-    static bool configured[8] = {};
-    int dev = h->cfg.device & 7;
-    if(!configured[dev]){
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem::TOTAL));
-        configured[dev] = true;
-    }
-    kern<<<grid_for(a.n, BLOCK), BLOCK, TcSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
-    LAUNCH_CHECK();
-    return B200L2F_OK;
-}
 
 // persistent grid + work queue of the tcgen05 rollout kernels.  When the tiles do not fill an integer number of waves (e.g. 65 536 envs =
 // 512 tiles on 444 slots), the rollout is cut into time chunks so that every slot stays busy until the end: makespan 512/444 instead of 2
@@ -264,56 +98,12 @@ int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid){
     return B200L2F_OK;
 }
 
-template <class Spec, bool FAST, bool UNIFORM, bool AXIAL>
-int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
-    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL>;
-    static bool configured[8] = {}; static int capacity[8] = {};
-    int dev = h->cfg.device & 7;
-    if(!configured[dev]){
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::TOTAL));
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        int per_sm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, TsSmem::TOTAL));
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-        if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] k_rollout_raptor_ts: occupancy API reports %d CTAs/SM on %d SMs\n", per_sm, sms);
-        if(per_sm < 3) per_sm = 3;           // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
-        capacity[dev] = per_sm * sms;        // co-resident CTAs (3 x 148 = 444 on B200)
-        configured[dev] = true;
-    }
-    int grid = 0, rc;
-    if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
-    kern<<<grid, BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_ts_image);
-    LAUNCH_CHECK();
-    return B200L2F_OK;
-}
+}  // namespace b200l2f
 
-template <class Spec, int OUT, bool UNIFORM, bool AXIAL>
-int launch_rollout_mlp_ts(b200l2f_handle* h, RolloutArgs a){
-    constexpr int IN = Spec::OBS_DIM;
-    using SM = MlpTsSmem<IN, OUT>;
-    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM, AXIAL>;
-    static bool configured[8] = {}; static int capacity[8] = {};
-    int dev = h->cfg.device & 7;
-    if(!configured[dev]){
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL_ROLLOUT));
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        int sms = 0;
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-        capacity[dev] = 2 * sms;             // design point: ~92 KB smem and 256 TMEM columns per CTA -> 2 CTAs/SM
-        configured[dev] = true;
-    }
-    int grid = 0, rc;
-    if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
-    kern<<<grid, BLOCK, SM::TOTAL_ROLLOUT, h->stream>>>(a, h->d_mlp_tc_image);
-    LAUNCH_CHECK();
-    return B200L2F_OK;
-}
-
-}  // namespace
 
 extern "C" {
 
-const char* b200l2f_last_error(const b200l2f_handle* h){ return h ? h->err.c_str() : g_create_error.c_str(); }
+const char* b200l2f_last_error(const b200l2f_handle* h){ return h ? h->err.c_str() : create_error().c_str(); }
 
 int b200l2f_create(const b200l2f_config* config, b200l2f_handle** out){
     b200l2f_handle* h = nullptr;
@@ -343,7 +133,7 @@ int b200l2f_create(const b200l2f_config* config, b200l2f_handle** out){
     h->sdim = state_dim(h->H);
     h->n = config->n_envs;
     const int slots = config->n_state_slots < 2 ? 2 : config->n_state_slots;
-    auto bail = [&](const std::string& m, int code){ g_create_error = m; b200l2f_destroy(h); return code; };
+    auto bail = [&](const std::string& m, int code){ create_error() = m; b200l2f_destroy(h); return code; };
 #define CUC(call) do{ cudaError_t e_ = (call); if(e_ != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e_), B200L2F_ERR_CUDA); }while(0)
     CUC(cudaSetDevice(config->device));
     if(config->stream){ h->stream = (cudaStream_t)config->stream; h->own_stream = false; }
@@ -369,7 +159,7 @@ int b200l2f_create(const b200l2f_config* config, b200l2f_handle** out){
     if(rc == B200L2F_OK) rc = b200l2f_initialize_rng(h, 0, 0);
     if(rc == B200L2F_OK) rc = b200l2f_initial_parameters(h);
     if(rc == B200L2F_OK) rc = b200l2f_collect_reset(h);
-    if(rc != B200L2F_OK){ g_create_error = h->err; b200l2f_destroy(h); *out = nullptr; return rc; }
+    if(rc != B200L2F_OK){ create_error() = h->err; b200l2f_destroy(h); *out = nullptr; return rc; }
     return B200L2F_OK;
 }
 
@@ -640,19 +430,7 @@ int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
         h->pol = *desc; h->blob_floats = n_floats; h->policy_loaded = true;
         cudaFree(h->d_mlp_tc_image); h->d_mlp_tc_image = nullptr;
         if(h->kind != KIND_DEFAULT){   // tensor-core operand image (H = 1 specs: the observation fits one K <= 32 operand)
-            auto build = [&](auto in_c, auto out_c) -> int {
-                constexpr int IN = decltype(in_c)::value, OUT = decltype(out_c)::value;
-                std::vector<float> img(MlpTcImage<IN, OUT>::SIZE);
-                build_mlp_tc_image_host<IN, OUT>(img.data(), blob, desc->standardize != 0, desc->head == B200L2F_HEAD_PPO_GAUSSIAN);
-                CU(cudaMalloc(&h->d_mlp_tc_image, MlpTcImage<IN, OUT>::BYTES));
-                CU(cudaMemcpy(h->d_mlp_tc_image, img.data(), MlpTcImage<IN, OUT>::BYTES, cudaMemcpyHostToDevice));
-                return (int)B200L2F_OK;
-            };
-            using I22 = std::integral_constant<int, 22>; using I26 = std::integral_constant<int, 26>;
-            using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
-            int brc;
-            if(h->obs_dim == 22) brc = desc->output_dim == 8 ? build(I22{}, O8{}) : build(I22{}, O4{});
-            else brc = desc->output_dim == 8 ? build(I26{}, O8{}) : build(I26{}, O4{});
+            int brc = build_mlp_tc_image(h, desc, blob);
             if(brc) return brc;
         }
         CU(cudaMemsetAsync(h->d_hidden, 0, sizeof(float) * desc->hidden_dim * (size_t)h->n, h->stream));
@@ -706,24 +484,7 @@ int b200l2f_policy_evaluate_step(b200l2f_handle* h, const float* observations, i
     if((rc = upload(h, observations, obs_bytes, memspace, &d_obs))) return rc;
     if((rc = result_buffer(h, actions, act_bytes, memspace, &d_act, obs_bytes))) return rc;
     if(h->pol.arch == B200L2F_POLICY_MLP){
-        const int has_std = h->pol.standardize, has_ls = h->pol.head == B200L2F_HEAD_PPO_GAUSSIAN, head = h->pol.head;
-        auto go = [&](auto in_c, auto out_c) -> int {
-            constexpr int IN = decltype(in_c)::value, OUT = decltype(out_c)::value;
-            constexpr int ROWS = IN > MLP_HD ? IN : MLP_HD;
-            auto kern = k_mlp_step<IN, OUT>;
-            const size_t smem = sizeof(float) * (MlpImg<IN, OUT>::SIZE + (size_t)ROWS * BLOCK);
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid_for(h->n, BLOCK), BLOCK, smem, h->stream>>>(h->d_blob, has_std, has_ls, head, (const float*)d_obs, ld, h->d_rng, (float*)d_act, h->n);
-            LAUNCH_CHECK();
-            return (int)B200L2F_OK;
-        };
-        using I22 = std::integral_constant<int, 22>; using I26 = std::integral_constant<int, 26>; using I82 = std::integral_constant<int, 82>;
-        using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
-        const bool o8 = h->pol.output_dim == 8;
-        if(h->pol.input_dim == 22) rc = o8 ? go(I22{}, O8{}) : go(I22{}, O4{});
-        else if(h->pol.input_dim == 26) rc = o8 ? go(I26{}, O8{}) : go(I26{}, O4{});
-        else rc = o8 ? go(I82{}, O8{}) : go(I82{}, O4{});
-        if(rc) return rc;
+        if((rc = launch_mlp_step(h, (const float*)d_obs, ld, (float*)d_act))) return rc;
         return download(h, actions, d_act, act_bytes, memspace);
     }
     const size_t smem = sizeof(float) * RaptorImage<22, 16, 4>::SIZE;
@@ -814,55 +575,21 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     // every vehicle thrusts along body z with diagonal inertia (true for all reference vehicles; B200L2F_DYNAMICS=general forces the full matrices)
     const bool allow_axial = [](){ const char* e = std::getenv("B200L2F_DYNAMICS"); return !(e && std::string(e) == "general"); }();
     const bool axial = allow_axial && (h->features & 4) == 0;
-    auto go = [&](auto spec) -> int {
-        using Spec = decltype(spec);
-        if(tensor_cores){
-            const bool uniform = (h->features & 2) == 0;
-            // A operand in TMEM ("TS" MMAs, 63 KB smem + 128 TMEM columns per CTA -> 3 CTAs/SM) is the default; B200L2F_A=smem selects the
-            // shared-memory-A variant (2 CTAs/SM).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
-            static const bool a_in_tmem = [](){ const char* e = std::getenv("B200L2F_A"); return !(e && std::string(e) == "smem"); }();
-            if(a_in_tmem && fast){
-                if(!uniform) return launch_rollout_ts<Spec, true, false, false>(h, a);
-                return axial ? launch_rollout_ts<Spec, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false>(h, a);
-            }
-            static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
-            if(!fast) return launch_rollout_tc<Spec, false, false, true>(h, a);
-            if(!uniform) return launch_rollout_tc<Spec, true, false, true>(h, a);
-            return g1_tc ? launch_rollout_tc<Spec, true, true, true>(h, a) : launch_rollout_tc<Spec, true, true, false>(h, a);
-        }
-        if(noise) return fast ? launch_rollout_raptor<Spec, true, true, true>(h, a) : launch_rollout_raptor<Spec, true, false, true>(h, a);
-        if(!fast) return launch_rollout_raptor<Spec, false, false, true>(h, a);
-        if(constw) return launch_rollout_raptor<Spec, false, true, true>(h, a);
-        return h->rolled ? launch_rollout_raptor<Spec, false, true, false, true>(h, a) : launch_rollout_raptor<Spec, false, true, false, false>(h, a);
-    };
+    const bool uniform = (h->features & 2) == 0;
     if(h->pol.arch == B200L2F_POLICY_MLP){
-        auto gomlp = [&](auto spec, auto out_c) -> int {
-            using Spec = decltype(spec);
-            constexpr int OUT = decltype(out_c)::value, IN = Spec::OBS_DIM;
-            constexpr int ROWS = IN > MLP_HD ? IN : MLP_HD;
-            auto kern = k_rollout_mlp<Spec, OUT>;
-            const size_t smem = sizeof(float) * (MlpImg<IN, OUT>::SIZE + (size_t)P_DYN_DIM * BLOCK + (size_t)ROWS * BLOCK);
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, h->pol.standardize);
-            LAUNCH_CHECK();
-            return (int)B200L2F_OK;
-        };
-        using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
-        const bool o8 = h->pol.output_dim == 8;
         // tcgen05 path: H = 1 specs, no observation / action noise (as for the GRU actor), default math flags
-        if(tensor_cores && fast && h->d_mlp_tc_image && h->kind != KIND_DEFAULT){
-            const bool uniform = (h->features & 2) == 0;
-            auto gots = [&](auto spec) -> int {
-                using Spec = decltype(spec);
-                if(!uniform) return o8 ? launch_rollout_mlp_ts<Spec, 8, false, false>(h, a) : launch_rollout_mlp_ts<Spec, 4, false, false>(h, a);
-                if(axial) return o8 ? launch_rollout_mlp_ts<Spec, 8, true, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, true>(h, a);
-                return o8 ? launch_rollout_mlp_ts<Spec, 8, true, false>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, false>(h, a);
-            };
-            rc = h->kind == KIND_RAPTOR ? gots(SpecRaptor{}) : gots(SpecTeacher{});
-        }
-        else rc = dispatch_spec(h, [&](auto spec){ return o8 ? gomlp(spec, O8{}) : gomlp(spec, O4{}); });
+        if(tensor_cores && fast && h->d_mlp_tc_image && h->kind != KIND_DEFAULT) rc = launch_mlp_ts(h, a, uniform, axial);
+        else rc = launch_mlp_fp32(h, a);
     }
-    else rc = h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
+    else if(tensor_cores){
+        // A operand in TMEM ("TS" MMAs, 63 KB smem + 128 TMEM columns per CTA -> 3 CTAs/SM) is the default; B200L2F_A=smem selects the
+        // shared-memory-A variant (2 CTAs/SM).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
+        static const bool a_in_tmem = [](){ const char* e = std::getenv("B200L2F_A"); return !(e && std::string(e) == "smem"); }();
+        static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
+        if(a_in_tmem && fast) rc = launch_raptor_ts(h, a, uniform, axial);
+        else rc = launch_raptor_tc(h, a, fast, uniform, g1_tc);
+    }
+    else rc = launch_raptor_fp32(h, a, noise, fast, constw, h->rolled);
     if(rc) return rc;
     if(ms == B200L2F_HOST && total){
         if((rc = ensure_pinned(h, total))) return rc;
@@ -897,17 +624,6 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     a.params = h->d_params; a.env_row = h->d_env_row; a.state = h->d_state[0]; a.rng = h->d_rng; a.blob = h->d_blob; a.has_std = h->pol.standardize;
     a.episode_step = h->d_episode_step; a.episode_return = h->d_episode_return; a.truncated = h->d_truncated; a.dataset = (float*)dev;
     a.n = h->n; a.T = n_steps; a.step_limit = episode_step_limit; a.error_flag = h->d_flags;
-    auto go = [&](auto spec, auto dr_c) -> int {
-        using Spec = SpecCompactCode<decltype(spec)>;
-        constexpr bool DR = decltype(dr_c)::value;
-        constexpr int IN = Spec::OBS_DIM;
-        auto kern = k_collect<Spec, DR>;
-        const size_t smem = sizeof(float) * (MlpImg<IN, 4>::SIZE + (size_t)P_DYN_DIM * BLOCK + (size_t)(MLP_HD + IN) * BLOCK);
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a);
-        LAUNCH_CHECK();
-        return (int)B200L2F_OK;
-    };
     std::memcpy(a.row, h->h_env_row, sizeof(a.row));
     const bool follow = h->params_follow_env_row;
     // axial vehicles (see b200l2f_rollout): decided from the nominal row when the columns follow it (domain randomisation keeps the property)
@@ -915,34 +631,8 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     bool row_axial = allow_axial;
     for(int r = 0; r < 4; r++) if(a.row[P_THRUST_DIR + 3 * r] != 0.0f || a.row[P_THRUST_DIR + 3 * r + 1] != 0.0f || a.row[P_THRUST_DIR + 3 * r + 2] != 1.0f) row_axial = false;
     for(int i = 0; i < 9; i++) if(i % 4 != 0 && (a.row[P_J + i] != 0.0f || a.row[P_JINV + i] != 0.0f)) row_axial = false;
-    auto gots2 = [&](auto spec, auto dr_c, auto follow_c, auto axial_c) -> int {
-        using Spec = SpecCompactCode<decltype(spec)>;
-        constexpr bool DR = decltype(dr_c)::value;
-        using SM = MlpTsSmem<Spec::OBS_DIM, 4>;
-        auto kern = k_collect_ts<Spec, DR, decltype(follow_c)::value, decltype(axial_c)::value>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL_COLLECT));
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        int sms = 0;
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-        if(!h->d_sched){ CU(cudaMalloc(&h->d_sched, sizeof(int) * 64)); h->sched_ints = 64; }
-        CU(cudaMemsetAsync(h->d_sched, 0, sizeof(int), h->stream));
-        const int n_tiles = grid_for(a.n, BLOCK);
-        const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;    // ~110 KB smem, 256 TMEM columns per CTA -> 2 CTAs/SM, persistent tile loop
-        kern<<<grid, BLOCK, SM::TOTAL_COLLECT, h->stream>>>(a, h->d_mlp_tc_image, h->d_sched);
-        LAUNCH_CHECK();
-        return (int)B200L2F_OK;
-    };
-    auto gots = [&](auto spec, auto dr_c) -> int {
-        if(follow) return row_axial ? gots2(spec, dr_c, std::true_type{}, std::true_type{}) : gots2(spec, dr_c, std::true_type{}, std::false_type{});
-        return gots2(spec, dr_c, std::false_type{}, std::false_type{});
-    };
     const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
-    if(tensor_cores){
-        if(h->kind == KIND_RAPTOR) rc = h->dr ? gots(SpecRaptor{}, std::true_type{}) : gots(SpecRaptor{}, std::false_type{});
-        else rc = h->dr ? gots(SpecTeacher{}, std::true_type{}) : gots(SpecTeacher{}, std::false_type{});
-    }
-    else if(h->kind == KIND_RAPTOR) rc = h->dr ? go(SpecRaptor{}, std::true_type{}) : go(SpecRaptor{}, std::false_type{});
-    else rc = h->dr ? go(SpecTeacher{}, std::true_type{}) : go(SpecTeacher{}, std::false_type{});
+    rc = tensor_cores ? launch_collect_ts(h, a, follow, row_axial) : launch_collect_fp32(h, a);
     if(rc) return rc;
     if(!follow) h->features_dirty = true;   // resets rewrite parameter columns (when they follow the row, the variant-selecting features cannot change)
     if((rc = download(h, dataset, dev, bytes, memspace))) return rc;

@@ -41,7 +41,7 @@ __device__ __forceinline__ ParamsStagedT<NC> stage_dynamics(float* __restrict__ 
 // utility kernels
 // ---------------------------------------------------------------------------------------------------------------
 // out[c][r] = in[r][c]; 32x32 tiles through shared memory, coalesced on both sides (AoS rows <-> SoA columns)
-__global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols){
+static __global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols){
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for(int j = threadIdx.y; j < 32; j += blockDim.y){
@@ -54,14 +54,14 @@ __global__ void k_transpose(const float* __restrict__ in, float* __restrict__ ou
         if(r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
     }
 }
-__global__ void k_init_rng(uint64_t* __restrict__ rng, int n, uint64_t seed, uint64_t first_env, int warmup){
+static __global__ void k_init_rng(uint64_t* __restrict__ rng, int n, uint64_t seed, uint64_t first_env, int warmup){
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= n) return;
     uint64_t s = rng_seed_state(seed + first_env + (uint64_t)e);
     for(int i = 0; i < warmup; i++) rng_next(s);
     rng[e] = s;
 }
-__global__ void k_fill_params(float* __restrict__ params, const float* __restrict__ env_row, int n){
+static __global__ void k_fill_params(float* __restrict__ params, const float* __restrict__ env_row, int n){
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= n) return;
     for(int i = 0; i < PARAMS_DIM; i++) params[(size_t)i * n + e] = env_row[i];
@@ -84,7 +84,7 @@ __host__ __device__ constexpr bool mdp_uniform_index(int i){
 // features of the parameter set that select kernel variants: bit0 = some observation/action noise std != 0,
 // bit1 = some environment's "uniform" MDP parameter differs from environment 0's, bit2 = some vehicle is not "axial" (a rotor thrust
 // direction other than body z, or an off-diagonal entry in J / J^-1): the fused kernels then keep the general rotor / inertia matrices
-__global__ void k_param_features(const float* __restrict__ params, int n, int* __restrict__ features){
+static __global__ void k_param_features(const float* __restrict__ params, int n, int* __restrict__ features){
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     int f = 0;
     if(e < n){

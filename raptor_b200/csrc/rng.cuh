@@ -45,7 +45,7 @@ __device__ __forceinline__ float rng_normal_draw(uint64_t& s, float mean, float 
 // Out-of-line twin: the collection kernels contain ~30 draw sites (observation / action noise, action sampling, reset samplers); the
 // inlined logf / cosf bodies would double their size and push them out of the instruction cache (profiles/r01_configs34.md).  The rollout
 // kernels have three sites (Langevin target) and keep the inlined draw (a call there costs 4 %).
-__device__ __noinline__ float rng_normal_draw_ool(uint64_t& s, float mean, float std){ return rng_normal_draw(s, mean, std); }
+static __device__ __noinline__ float rng_normal_draw_ool(uint64_t& s, float mean, float std){ return rng_normal_draw(s, mean, std); }
 // default-math twin: same two uniforms (the integer stream stays bit-exact), MUFU logarithm / cosine / square root (absolute error ~5e-7)
 __device__ __forceinline__ float rng_normal_draw_fast(uint64_t& s, float mean, float std){
     const float u1 = rng_unit(s);

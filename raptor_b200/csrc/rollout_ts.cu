@@ -1,0 +1,40 @@
+// raptor_b200/csrc/rollout_ts.cu -- instantiations of k_rollout_raptor_ts (rollout_tc.cuh): THE default hot path (tcgen05, A operand and
+// GRU hidden state in TMEM, persistent (tile, time-chunk) work queue).
+#include "launch.h"
+#include "rollout_tc.cuh"
+
+namespace b200l2f {
+namespace {
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL>
+int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
+    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL>;
+    static bool configured[8] = {}; static int capacity[8] = {};
+    int dev = h->cfg.device & 7;
+    if(!configured[dev]){
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::TOTAL));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, TsSmem::TOTAL));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] k_rollout_raptor_ts: occupancy API reports %d CTAs/SM on %d SMs\n", per_sm, sms);
+        if(per_sm < 3) per_sm = 3;           // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
+        capacity[dev] = per_sm * sms;        // co-resident CTAs (3 x 148 = 444 on B200)
+        configured[dev] = true;
+    }
+    int grid = 0, rc;
+    if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
+    kern<<<grid, BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_ts_image);
+    LAUNCH_CHECK();
+    return B200L2F_OK;
+}
+}  // namespace
+
+int launch_raptor_ts(b200l2f_handle* h, const RolloutArgs& a, bool uniform, bool axial){
+    auto go = [&](auto spec) -> int {
+        using Spec = decltype(spec);
+        if(!uniform) return launch_rollout_ts<Spec, true, false, false>(h, a);
+        return axial ? launch_rollout_ts<Spec, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false>(h, a);
+    };
+    return h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
+}
+}  // namespace b200l2f
