@@ -184,6 +184,23 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
 int b200l2f_collect_reset(b200l2f_handle* h);                                             /* runner init: truncated = true, episode_step/return = 0 (operations_generic.h:65-75) */
 int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, float* dataset, int memspace);
 
+/* ---- PPO learner feed: what the reference's loop step does between collect and train on the dataset above
+ * (INC/rl/algorithms/ppo/loop/core/operations_generic.h:104-117), without the data leaving the GPU.
+ * critic_load: the value network [standardize ->] Dense(OBS,64,ReLU) -> Dense(64,64,ReLU) -> Dense(64,1) (loop/core/config.h:62-76), blob in the
+ *   MLP order above with output_dim 1, head IDENTITY; desc->gemm selects tcgen05 (3xTF32) or fp32 CUDA cores.
+ * evaluate_values: `evaluate(device, critic, all_observations_privileged, all_values, ...)` (:112-116) over all (T+1) n rows -> column OBS+12.
+ * estimate_generalized_advantages: INC/rl/algorithms/ppo/operations_generic.h:54-89 on the value column -> columns OBS+13 (advantage), OBS+14
+ *   (target_value); gamma / lambda / ignore_termination = PPO_PARAMETERS::GAMMA / LAMBDA / IGNORE_TERMINATION (ppo.h:15-16,33).
+ * values_and_advantages: both in ONE backward pass over time (the dataset is read once).
+ * normalizer_update: rl::components::running_normalizer `update` (INC/rl/components/running_normalizer/operations_generic.h:27-49) with the
+ *   observation block [0, T n) x [0, OBS) as data; mean_io / std_io [OBS] and age_io are host pointers (the normalizer lives with the caller,
+ *   who passes mean and 1 / std to the standardize layers: set_statistics, INC/nn/layers/standardize/operations_generic.h). */
+int b200l2f_critic_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, const float* blob, size_t n_floats); /* host blob */
+int b200l2f_evaluate_values(b200l2f_handle* h, int32_t n_steps, float* dataset, int memspace);
+int b200l2f_estimate_generalized_advantages(b200l2f_handle* h, int32_t n_steps, float gamma, float lambda, int ignore_termination, float* dataset, int memspace);
+int b200l2f_values_and_advantages(b200l2f_handle* h, int32_t n_steps, float gamma, float lambda, int ignore_termination, float* dataset, int memspace);
+int b200l2f_normalizer_update(b200l2f_handle* h, int32_t n_steps, const float* dataset, int memspace, float* mean_io, float* std_io, int32_t* age_io);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,6 +177,9 @@ class Port(_Common):
         L.oracle_policy_evaluate_step.argtypes = [ctypes.POINTER(OraclePolicy), c_int, f32, c_int, vp, vp, c_int, vp, f32, vp, vp]
         L.oracle_rollout.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, f32, f32, u64, vp, vp, c_int, vp, vp, vp, vp, vp]
         L.oracle_collect.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, f32, c_int]
+        L.oracle_evaluate_values.argtypes = [ctypes.POINTER(OraclePolicy), c_int, c_int, f32, c_int]
+        L.oracle_estimate_generalized_advantages.argtypes = [c_int, c_int, f32, c_int, c_float, c_float, c_int]
+        L.oracle_normalizer_update.argtypes = [c_int, c_int, f32, c_int, f32, f32, ctypes.POINTER(c_int)]
 
     def make_policy(self, blob, arch=POLICY_RAPTOR_GRU, input_dim=22, hidden_dim=16, output_dim=4, standardize=0, head=HEAD_IDENTITY):
         blob = np.ascontiguousarray(blob, np.float32)
@@ -216,6 +219,18 @@ class Port(_Common):
                                 _ptr(episode_step), _ptr(episode_return), _ptr(truncated), data, D)
         return data
 
+    def evaluate_values(self, critic, data, n, T):
+        """critic values over all (T+1)*n observation rows -> the all_values column, in place"""
+        self.lib.oracle_evaluate_values(ctypes.byref(critic), n, T, data, data.shape[1])
+
+    def estimate_generalized_advantages(self, data, n, T, gamma=0.99, lam=0.95, ignore_termination=False):
+        self.lib.oracle_estimate_generalized_advantages(n, T, data, data.shape[1], gamma, lam, int(ignore_termination))
+
+    def normalizer_update(self, data, n, T, mean, std, age):
+        a = c_int(age)
+        self.lib.oracle_normalizer_update(n, T, data, data.shape[1], mean, std, ctypes.byref(a))
+        return int(a.value)
+
     def hardware_threads(self):
         return int(self.lib.oracle_hardware_threads())
 
@@ -240,6 +255,13 @@ class Ref(_Common):
         L.ref_policy_initial_hidden.argtypes = [f32]
         L.ref_rollout.argtypes = [c_int, c_int, c_int, c_int, f32, f32, u64, vp, vp, c_int, vp, vp, vp, vp, vp]
         L.ref_checkpoint_name.restype = ctypes.c_char_p
+        if hasattr(L, "ref_collect"):
+            L.ref_ppo_gamma.restype = c_float
+            L.ref_ppo_lambda.restype = c_float
+            L.ref_mlp_evaluate.argtypes = [c_int, c_int, f32, c_int, c_int, f32, c_int, f32, c_int]
+            L.ref_collect.argtypes = [c_int, f32, c_int, f32, f32, f32, u64, vp, vp, vp, f32]
+            L.ref_gae.argtypes = [c_int, f32, c_int]
+            L.ref_normalizer_update.argtypes = [c_int, f32, f32, f32, ctypes.POINTER(c_int)]
 
     def policy_kat(self):
         mx = c_float()
@@ -278,6 +300,39 @@ class Ref(_Common):
         self.lib.ref_rollout(spec, n, T, threads, params, states, rngs, _ptr(hidden), _ptr(gru_step), int(no_auto_reset),
                              _ptr(out.get("states")), _ptr(out.get("observations")), _ptr(out.get("actions")), _ptr(out.get("rewards")), _ptr(out.get("terminated")))
         return out
+
+    # ---- PPO data path (sizes fixed at compile time in oracle/ref_l2f.cpp)
+    def ppo_sizes(self):
+        n, t, lim = c_int(), c_int(), c_int()
+        self.lib.ref_ppo_sizes(ctypes.byref(n), ctypes.byref(t), ctypes.byref(lim))
+        return int(n.value), int(t.value), int(lim.value)
+
+    def ppo_gamma_lambda(self):
+        return float(self.lib.ref_ppo_gamma()), float(self.lib.ref_ppo_lambda())
+
+    def mlp_evaluate(self, blob, in_dim, out_dim, standardize, x):
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.zeros((x.shape[0], out_dim), np.float32)
+        rc = self.lib.ref_mlp_evaluate(in_dim, out_dim, np.ascontiguousarray(blob, np.float32), int(standardize), x.shape[0], x, x.shape[1], y, out_dim)
+        assert rc == 0, "ref_mlp_evaluate: shape not instantiated"
+        return y
+
+    def collect(self, spec, blob, standardize, env_params, params, states, rngs, episode_step, episode_return, truncated):
+        n, T, _ = self.ppo_sizes()
+        assert states.shape[0] == n
+        D = self.observation_dim(spec) + 15
+        data = np.zeros(((T + 1) * n, D), np.float32)
+        self.lib.ref_collect(spec, np.ascontiguousarray(blob, np.float32), int(standardize), np.ascontiguousarray(env_params, np.float32), params, states, rngs,
+                             _ptr(episode_step), _ptr(episode_return), _ptr(truncated), data)
+        return data
+
+    def estimate_generalized_advantages(self, spec, data, ignore_termination=False):
+        self.lib.ref_gae(spec, data, int(ignore_termination))
+
+    def normalizer_update(self, spec, data, mean, std, age):
+        a = c_int(age)
+        self.lib.ref_normalizer_update(spec, data, mean, std, ctypes.byref(a))
+        return int(a.value)
 
     def hardware_threads(self):
         return int(self.lib.ref_hardware_threads())

@@ -823,7 +823,12 @@ static void* collect_range(void* arg){
             if(j->truncated[n]){
                 j->truncated[n] = 0; j->episode_step[n] = 0; j->episode_return[n] = 0;
                 oracle_sample_initial_parameters(j->spec, j->env_params, &rng, p);
+                /* the reference's reset leaves the previous episode's Langevin target in place when it draws the POSITION trajectory
+                 * (30_sample_initial_state.h:217-219); oracle_sample_initial_state builds a fresh state, so carry the block over here */
+                float dead_target[12];
+                memcpy(dead_target, s + S_TRAJ_TYPE(sp.H) + 1, sizeof(dead_target));
                 oracle_sample_initial_state(j->spec, p, &rng, s);
+                if(sp.langevin && (int)s[S_TRAJ_TYPE(sp.H)] == 0) memcpy(s + S_TRAJ_TYPE(sp.H) + 1, dead_target, sizeof(dead_target));
             }
             observe_impl(&sp, p, s, &rng, row);
             float* mean = row + OBS; float* act = row + OBS + 4; float lp = 0;
@@ -860,5 +865,64 @@ void oracle_collect(int spec, const oracle_policy_t* pol, int N, int T, int thre
     if(threads == 1){ collect_range(&jobs[0]); return; }
     for(int t = 0; t < threads; t++) pthread_create(&th[t], NULL, collect_range, &jobs[t]);
     for(int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * learner feed of the PPO loop step (INC/rl/algorithms/ppo/loop/core/operations_generic.h:104-117): critic values over
+ * all_observations -> all_values column, generalized advantage estimation, running observation normalizer.
+ * dataset rows: [(T+1)*N, D], D = OBS + 15, columns as documented above oracle_collect.
+ * ------------------------------------------------------------------------------------------- */
+/* evaluate(device, critic, all_observations_privileged, all_values): operations_generic.h:112-116 (critic = standardize -> MLP, output 1) */
+void oracle_evaluate_values(const oracle_policy_t* critic, int N, int T, float* dataset, int data_dim){
+    const int OBS = data_dim - 15;
+    for(size_t r = 0; r < (size_t)(T + 1) * N; r++){
+        float* row = dataset + r * data_dim;
+        float v = 0;
+        mlp_forward(critic, row, NULL, &v, NULL, NULL);
+        row[OBS + 12] = v;
+    }
+}
+/* estimate_generalized_advantages: INC/rl/algorithms/ppo/operations_generic.h:54-89 */
+void oracle_estimate_generalized_advantages(int N, int T, float* dataset, int data_dim, float gamma, float lambda, int ignore_termination){
+    const int OBS = data_dim - 15, D = data_dim;
+    for(int env = 0; env < N; env++){
+        float previous_value = dataset[((size_t)T * N + env) * D + OBS + 12];
+        float previous_advantage = 0;
+        for(int fwd = 0; fwd < T; fwd++){
+            const int step = T - 1 - fwd;
+            float* row = dataset + ((size_t)step * N + env) * D;
+            const int terminated = row[OBS + 10] != 0, truncated = row[OBS + 11] != 0;
+            const float current_step_value = row[OBS + 12];
+            const int terminated_actual = terminated && !ignore_termination;
+            const float next_step_value = terminated_actual ? 0 : previous_value;
+            float td_error = row[OBS + 9] + gamma * next_step_value - current_step_value;
+            if(truncated){
+                if(!terminated) td_error = 0;
+                previous_advantage = 0;
+            }
+            const float advantage = lambda * gamma * previous_advantage + td_error;
+            row[OBS + 13] = advantage;
+            row[OBS + 14] = advantage + current_step_value;
+            previous_advantage = advantage;
+            previous_value = current_step_value;
+        }
+    }
+}
+/* rl::components::running_normalizer update: INC/rl/components/running_normalizer/operations_generic.h:27-49 with the column mean / std of
+ * INC/containers/matrix/operations_generic.h:641-691 (sequential fp32 sums, sample std, acc < 1e-6 -> 0), over the T*N observation rows */
+void oracle_normalizer_update(int N, int T, const float* dataset, int data_dim, float* mean_io, float* std_io, int* age_io){
+    const int OBS = data_dim - 15;
+    const size_t rows = (size_t)T * N;
+    *age_io += 1;
+    for(int c = 0; c < OBS; c++){
+        float acc = 0;
+        for(size_t r = 0; r < rows; r++) acc += dataset[r * data_dim + c];
+        const float data_mean = acc / rows;
+        float acc2 = 0;
+        for(size_t r = 0; r < rows; r++){ const float diff = dataset[r * data_dim + c] - data_mean; acc2 += diff * diff; }
+        const float data_std = acc2 < 1e-6 ? 0 : sqrtf(acc2 / (rows - 1));
+        mean_io[c] = mean_io[c] + (data_mean - mean_io[c]) / (*age_io);
+        std_io[c] = std_io[c] + (data_std - std_io[c]) / (*age_io);
+    }
 }
 int oracle_hardware_threads(void){ long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }

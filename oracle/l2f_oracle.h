@@ -72,6 +72,10 @@ void oracle_rollout(int spec, const oracle_policy_t* pol, int N, int T, int thre
 void oracle_collect(int spec, const oracle_policy_t* pol, int N, int T, int threads, int episode_step_limit, const float* env_params,
                     float* params_io, float* states_io, uint64_t* rng_states, int* episode_step_io, float* episode_return_io, unsigned char* truncated_io,
                     float* dataset, int data_dim);
+/* learner feed (PPO loop step between collect and train): critic values, GAE, running observation normalizer */
+void oracle_evaluate_values(const oracle_policy_t* critic, int N, int T, float* dataset, int data_dim);
+void oracle_estimate_generalized_advantages(int N, int T, float* dataset, int data_dim, float gamma, float lambda, int ignore_termination);
+void oracle_normalizer_update(int N, int T, const float* dataset, int data_dim, float* mean_io, float* std_io, int* age_io);
 int oracle_hardware_threads(void);
 #ifdef __cplusplus
 }

@@ -581,3 +581,214 @@ void ref_rollout(int spec, int N, int T_steps, int threads, const float* params,
 int ref_hardware_threads(){ return (int)std::thread::hardware_concurrency(); }
 const char* ref_checkpoint_name(){ return rlt::checkpoint::meta::name; }
 }
+
+// ================================================================================================
+// PPO data path: MLP actor / critic forward, rl_tools::collect's per-environment prologue / epilogue and
+// rl_tools::estimate_generalized_advantages, all the reference's own templates.  Sizes that the reference fixes at
+// compile time (N_ENVIRONMENTS, STEPS_PER_ENV, STEP_LIMIT) are fixed here at REF_PPO_N / REF_PPO_T / REF_PPO_STEP_LIMIT; the
+// tests run the port and the GPU engine at exactly these sizes.
+// ================================================================================================
+#include <rl_tools/rl/components/on_policy_runner/operations_generic.h>
+#include <rl_tools/rl/components/running_normalizer/operations_generic.h>
+#include <rl_tools/rl/algorithms/ppo/ppo.h>
+#include <rl_tools/rl/algorithms/ppo/operations_generic.h>
+
+namespace ref_ppo{
+    constexpr TI N = 32, STEPS = 48, STEP_LIMIT = 20;
+    using CAP = rlt::nn::capability::Forward<true>;
+    template <TI IN, TI OUT, TI BATCH>
+    struct Net{ // rl/algorithms/ppo/loop/core/config.h:48-76 (actor and critic have the same structure: standardize -> mlp_unconditional_stddev)
+        using INPUT_SHAPE = rlt::tensor::Shape<TI, 1, BATCH, IN>;
+        using STANDARDIZATION_LAYER = rlt::nn::layers::standardize::BindConfiguration<rlt::nn::layers::standardize::Configuration<T, TI>>;
+        using CONFIG = rlt::nn_models::mlp::Configuration<T, TI, OUT, 3, 64, rlt::nn::activation_functions::ActivationFunction::RELU, rlt::nn::activation_functions::IDENTITY>;
+        using TYPE = rlt::nn_models::mlp_unconditional_stddev::BindConfiguration<CONFIG>;
+        template <typename T_CONTENT, typename T_NEXT_MODULE = rlt::nn_models::sequential::OutputModule>
+        using Module = typename rlt::nn_models::sequential::Module<T_CONTENT, T_NEXT_MODULE>;
+        using MODEL = rlt::nn_models::sequential::Build<CAP, Module<STANDARDIZATION_LAYER, Module<TYPE>>, INPUT_SHAPE>;
+    };
+    // blob order of include/b200_l2f.h: [mean[in] precision[in]] W1 b1 W2 b2 W3 b3 [log_std[out]]
+    template <typename MODEL, TI IN, TI OUT>
+    static void load(DEVICE& device, MODEL& model, const float* blob, int has_std, int has_log_std){
+        auto& stdz = rlt::get_first_layer(model);
+        auto& mlp = rlt::get_last_layer(model);
+        const float* b = blob;
+        for(TI i = 0; i < IN; i++){
+            rlt::set(stdz.mean.parameters, 0, i, has_std ? b[i] : 0.0f);
+            rlt::set(stdz.precision.parameters, 0, i, has_std ? b[IN + i] : 1.0f);
+        }
+        if(has_std) b += 2 * IN;
+        auto put = [&](auto& layer, TI out, TI in){
+            for(TI o = 0; o < out; o++) for(TI i = 0; i < in; i++) rlt::set(layer.weights.parameters, o, i, *b++);
+            for(TI o = 0; o < out; o++) rlt::set(layer.biases.parameters, 0, o, *b++);
+        };
+        put(mlp.input_layer, 64, IN);
+        put(mlp.hidden_layers[0], 64, 64);
+        put(mlp.output_layer, OUT, 64);
+        for(TI o = 0; o < OUT; o++) rlt::set(mlp.log_std.parameters, 0, o, has_log_std ? b[o] : 0.0f);
+    }
+    template <TI IN, TI OUT>
+    static void mlp_evaluate(const float* blob, int has_std, int n_rows, const float* in, int ld_in, float* out, int ld_out){
+        using NET = Net<IN, OUT, 1>;
+        DEVICE device; RNG rng; rng.state = 0;
+        typename NET::MODEL model;
+        typename NET::MODEL::template Buffer<> buffer;
+        rlt::malloc(device, model); rlt::malloc(device, buffer);
+        load<typename NET::MODEL, IN, OUT>(device, model, blob, has_std, 0);
+        rlt::Tensor<rlt::tensor::Specification<T, TI, typename NET::INPUT_SHAPE>> x;
+        rlt::Tensor<rlt::tensor::Specification<T, TI, rlt::tensor::Shape<TI, 1, 1, OUT>>> y;
+        rlt::malloc(device, x); rlt::malloc(device, y);
+        for(int r = 0; r < n_rows; r++){
+            for(TI i = 0; i < IN; i++) rlt::set(device, x, in[(size_t)r * ld_in + i], 0, 0, i);
+            rlt::evaluate(device, model, x, y, buffer, rng);
+            for(TI o = 0; o < OUT; o++) out[(size_t)r * ld_out + o] = rlt::get(device, y, 0, 0, o);
+        }
+        rlt::free(device, x); rlt::free(device, y); rlt::free(device, model); rlt::free(device, buffer);
+    }
+
+    template <typename ENV>
+    struct RunnerSpec{
+        using OPR_SPEC = rlt::rl::components::on_policy_runner::Specification<T, TI, ENV, N, STEP_LIMIT>;
+        using RUNNER = rlt::rl::components::OnPolicyRunner<OPR_SPEC>;
+        using DATASET_SPEC = rlt::rl::components::on_policy_runner::DatasetSpecification<OPR_SPEC, STEPS>;
+        using DATASET = rlt::rl::components::on_policy_runner::Dataset<DATASET_SPEC>;
+    };
+    // rl_tools::collect (on_policy_runner/operations_generic.h:99-131) with ONE RNG STREAM PER ENVIRONMENT: the loop below is the reference's
+    // step loop, its per-environment prologue / epilogue are called with that environment's stream (the reference's multi-threaded collect does
+    // the same, on_policy_runner/operations_cpu.h:36-44).
+    template <typename ENV>
+    static void collect(const float* actor_blob, int has_std, const float* env_params, float* params_io, float* states_io, uint64_t* rng_states,
+                        int* episode_step_io, float* episode_return_io, unsigned char* truncated_io, float* dataset_out){
+        using RS = RunnerSpec<ENV>;
+        constexpr TI OBS = ENV::Observation::DIM;
+        using NET = Net<OBS, 4, N>;
+        DEVICE device;
+        typename RS::RUNNER runner; typename RS::DATASET dataset;
+        rlt::malloc(device, runner); rlt::malloc(device, dataset);
+        typename NET::MODEL actor; typename NET::MODEL::template Buffer<> buffer;
+        rlt::malloc(device, actor); rlt::malloc(device, buffer);
+        load<typename NET::MODEL, OBS, 4>(device, actor, actor_blob, has_std, 1);
+        const int SD = state_dim(Impl<ENV>::H);
+        static ENV envs[N]; static typename ENV::Parameters params[N];
+        for(TI e = 0; e < N; e++){
+            rlt::init(device, envs[e]);
+            unflatten_parameters(env_params, envs[e].parameters);
+            unflatten_parameters(params_io + e * PARAMS_DIM, params[e]);
+        }
+        RNG rng0; rng0.state = 0;
+        rlt::init(device, runner, envs, params, rng0);
+        for(TI e = 0; e < N; e++){
+            auto& st = rlt::get(runner.states, 0, e); zero_state(st); unflatten_state(states_io + e * SD, st);
+            rlt::set(runner.episode_step, 0, e, (TI)episode_step_io[e]);
+            rlt::set(runner.episode_return, 0, e, episode_return_io[e]);
+            rlt::set(runner.truncated, 0, e, truncated_io[e] != 0);
+        }
+        std::vector<RNG> rngs(N);
+        for(TI e = 0; e < N; e++) rngs[e].state = rng_states[e];
+        rlt::set_all(device, dataset.data, 0);
+        for(TI step_i = 0; step_i < STEPS; step_i++){
+            auto actions_mean            = rlt::view(device, dataset.actions_mean               , rlt::matrix::ViewSpec<N, 4>()  , step_i*N, 0);
+            auto actions                 = rlt::view(device, dataset.actions                    , rlt::matrix::ViewSpec<N, 4>()  , step_i*N, 0);
+            auto observations_privileged = rlt::view(device, dataset.all_observations_privileged, rlt::matrix::ViewSpec<N, ENV::ObservationPrivileged::DIM>(), step_i*N, 0);
+            auto observations            = rlt::view(device, dataset.observations               , rlt::matrix::ViewSpec<N, OBS>(), step_i*N, 0);
+            for(TI e = 0; e < N; e++) rlt::rl::components::on_policy_runner::per_env::prologue(device, observations_privileged, observations, runner, rngs[e], e);
+            typename NET::MODEL::template State<> actor_state;
+            rlt::Mode<rlt::mode::Rollout<>> mode;
+            auto observations_tensor = rlt::to_tensor(device, observations);
+            auto actions_mean_tensor = rlt::to_tensor(device, actions_mean);
+            rlt::evaluate_step(device, actor, observations_tensor, actor_state, actions_mean_tensor, buffer, rng0, mode);
+            auto& last_layer = rlt::get_last_layer(actor);
+            for(TI e = 0; e < N; e++) rlt::rl::components::on_policy_runner::per_env::epilogue(device, dataset, runner, actions_mean, actions, last_layer.log_std.parameters, rngs[e], step_i * N + e, e);
+        }
+        for(TI e = 0; e < N; e++){
+            auto& env = rlt::get(runner.environments, 0, e);
+            auto& state = rlt::get(runner.states, 0, e);
+            auto& parameters = rlt::get(runner.env_parameters, 0, e);
+            auto observation = rlt::row(device, dataset.all_observations_privileged, STEPS * N + e);
+            rlt::observe(device, env, parameters, state, typename ENV::ObservationPrivileged{}, observation, rngs[e]);
+        }
+        constexpr TI D = RS::DATASET::DATA_DIM;
+        for(TI r = 0; r < (STEPS + 1) * N; r++) for(TI c = 0; c < D; c++) dataset_out[r * D + c] = rlt::get(dataset.data, r, c);
+        for(TI e = 0; e < N; e++){
+            flatten_parameters(rlt::get(runner.env_parameters, 0, e), params_io + e * PARAMS_DIM);
+            flatten_state(rlt::get(runner.states, 0, e), states_io + e * SD);
+            rng_states[e] = rngs[e].state;
+            episode_step_io[e] = (int)rlt::get(runner.episode_step, 0, e);
+            episode_return_io[e] = rlt::get(runner.episode_return, 0, e);
+            truncated_io[e] = rlt::get(runner.truncated, 0, e) ? 1 : 0;
+        }
+        rlt::free(device, runner); rlt::free(device, dataset); rlt::free(device, actor); rlt::free(device, buffer);
+    }
+    template <bool T_IGNORE_TERMINATION>
+    struct PPOParameters: rlt::rl::algorithms::ppo::DefaultParameters<T, TI, 64>{ static constexpr bool IGNORE_TERMINATION = T_IGNORE_TERMINATION; };
+    template <typename ENV>
+    static void gae(float* data, int ignore_termination){
+        using RS = RunnerSpec<ENV>;
+        DEVICE device;
+        typename RS::DATASET dataset;
+        rlt::malloc(device, dataset);
+        constexpr TI D = RS::DATASET::DATA_DIM;
+        for(TI r = 0; r < (STEPS + 1) * N; r++) for(TI c = 0; c < D; c++) rlt::set(dataset.data, r, c, data[r * D + c]);
+        if(ignore_termination) rlt::estimate_generalized_advantages(device, dataset, PPOParameters<true>{});
+        else rlt::estimate_generalized_advantages(device, dataset, PPOParameters<false>{});
+        for(TI r = 0; r < (STEPS + 1) * N; r++) for(TI c = 0; c < D; c++) data[r * D + c] = rlt::get(dataset.data, r, c);
+        rlt::free(device, dataset);
+    }
+    // rl::components::running_normalizer update (operations_generic.h:27-49) on the dataset's observation columns
+    template <typename ENV>
+    static void normalizer_update(const float* data, float* mean_io, float* std_io, int* age_io){
+        using RS = RunnerSpec<ENV>;
+        constexpr TI OBS = ENV::Observation::DIM, D = RS::DATASET::DATA_DIM;
+        DEVICE device;
+        rlt::rl::components::RunningNormalizer<rlt::rl::components::running_normalizer::Specification<T, TI, OBS>> normalizer;
+        rlt::malloc(device, normalizer);
+        normalizer.age = *age_io;
+        for(TI i = 0; i < OBS; i++){ rlt::set(normalizer.mean, 0, i, mean_io[i]); rlt::set(normalizer.std, 0, i, std_io[i]); }
+        rlt::Matrix<rlt::matrix::Specification<T, TI, STEPS * N, OBS>> obs;
+        rlt::malloc(device, obs);
+        for(TI r = 0; r < STEPS * N; r++) for(TI c = 0; c < OBS; c++) rlt::set(obs, r, c, data[r * D + c]);
+        rlt::update(device, normalizer, obs);
+        *age_io = (int)normalizer.age;
+        for(TI i = 0; i < OBS; i++){ mean_io[i] = rlt::get(normalizer.mean, 0, i); std_io[i] = rlt::get(normalizer.std, 0, i); }
+        rlt::free(device, obs); rlt::free(device, normalizer);
+    }
+}
+
+extern "C" {
+void ref_ppo_sizes(int* n, int* steps, int* step_limit){ *n = ref_ppo::N; *steps = ref_ppo::STEPS; *step_limit = ref_ppo::STEP_LIMIT; }
+float ref_ppo_gamma(){ return ref_ppo::PPOParameters<false>::GAMMA; }
+float ref_ppo_lambda(){ return ref_ppo::PPOParameters<false>::LAMBDA; }
+// standardize -> Dense(in,64,ReLU) -> Dense(64,64,ReLU) -> Dense(64,out): in/out pairs on the path (PPO actor 22/26 -> 4, critic 22/26 -> 1, SAC teacher 26 -> 8)
+int ref_mlp_evaluate(int in_dim, int out_dim, const float* blob, int has_std, int n_rows, const float* in, int ld_in, float* out, int ld_out){
+    if(in_dim == 22 && out_dim == 4) ref_ppo::mlp_evaluate<22, 4>(blob, has_std, n_rows, in, ld_in, out, ld_out);
+    else if(in_dim == 26 && out_dim == 4) ref_ppo::mlp_evaluate<26, 4>(blob, has_std, n_rows, in, ld_in, out, ld_out);
+    else if(in_dim == 22 && out_dim == 1) ref_ppo::mlp_evaluate<22, 1>(blob, has_std, n_rows, in, ld_in, out, ld_out);
+    else if(in_dim == 26 && out_dim == 1) ref_ppo::mlp_evaluate<26, 1>(blob, has_std, n_rows, in, ld_in, out, ld_out);
+    else if(in_dim == 26 && out_dim == 8) ref_ppo::mlp_evaluate<26, 8>(blob, has_std, n_rows, in, ld_in, out, ld_out);
+    else if(in_dim == 82 && out_dim == 4) ref_ppo::mlp_evaluate<82, 4>(blob, has_std, n_rows, in, ld_in, out, ld_out);
+    else return 1;
+    return 0;
+}
+void ref_collect(int spec, const float* actor_blob, int has_std, const float* env_params, float* params_io, float* states_io, uint64_t* rng_states,
+                 int* episode_step_io, float* episode_return_io, unsigned char* truncated_io, float* dataset){
+    switch(spec){
+        case 2: ref_ppo::collect<ENV_RAPTOR>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;
+        case 4: ref_ppo::collect<ENV_RAPTOR_DR>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;
+        case 5: ref_ppo::collect<ENV_TEACHER_DR>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;
+        default: std::fprintf(stderr, "ref_collect: spec %d not instantiated\n", spec); std::abort();
+    }
+}
+void ref_gae(int spec, float* dataset, int ignore_termination){
+    switch(spec){
+        case 2: case 4: ref_ppo::gae<ENV_RAPTOR>(dataset, ignore_termination); break;
+        case 3: case 5: ref_ppo::gae<ENV_TEACHER>(dataset, ignore_termination); break;
+        default: std::fprintf(stderr, "ref_gae: spec %d not instantiated\n", spec); std::abort();
+    }
+}
+void ref_normalizer_update(int spec, const float* dataset, float* mean_io, float* std_io, int* age_io){
+    switch(spec){
+        case 2: case 4: ref_ppo::normalizer_update<ENV_RAPTOR>(dataset, mean_io, std_io, age_io); break;
+        case 3: case 5: ref_ppo::normalizer_update<ENV_TEACHER>(dataset, mean_io, std_io, age_io); break;
+        default: std::fprintf(stderr, "ref_normalizer_update: spec %d not instantiated\n", spec); std::abort();
+    }
+}
+}

@@ -72,6 +72,11 @@ SYMBOLS = {
     "b200l2f_rollout": (c_int, [vp, c_i32, c_i32, ctypes.POINTER(RolloutOut)]),
     "b200l2f_collect_reset": (c_int, [vp]),
     "b200l2f_collect": (c_int, [vp, c_i32, c_i32, vp, c_int]),
+    "b200l2f_critic_load": (c_int, [vp, ctypes.POINTER(PolicyDesc), vp, ctypes.c_size_t]),
+    "b200l2f_evaluate_values": (c_int, [vp, c_i32, vp, c_int]),
+    "b200l2f_estimate_generalized_advantages": (c_int, [vp, c_i32, c_f, c_f, c_int, vp, c_int]),
+    "b200l2f_values_and_advantages": (c_int, [vp, c_i32, c_f, c_f, c_int, vp, c_int]),
+    "b200l2f_normalizer_update": (c_int, [vp, c_i32, vp, c_int, vp, vp, vp]),
 }
 
 _lib = None

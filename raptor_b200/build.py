@@ -29,6 +29,7 @@ SOURCES = {
     "rollout_mlp_ts.cu": TC + ["mlp_tc.cuh"],
     "collect.cu": [],
     "collect_ts.cu": TC + ["mlp_tc.cuh"],
+    "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
 }
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

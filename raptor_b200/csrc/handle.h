@@ -42,6 +42,10 @@ struct b200l2f_handle {
     float* d_tc_image = nullptr;     // tensor-core weight image (hi/lo planes of the three B operands, TMA source)
     float* d_ts_image = nullptr;     // the same with scaled GRU gate rows (k_rollout_raptor_ts)
     float* d_mlp_tc_image = nullptr; // same for an MLP actor (MlpTcImage<IN, OUT>), null when the actor has no tensor-core instantiation
+    // critic of the learner feed (learner.cu): MLP blob with the single output row padded to 4, and its tensor-core operand image
+    bool critic_loaded = false; int critic_std = 0, critic_gemm = 0;
+    float* d_critic_blob = nullptr; float* d_critic_tc_image = nullptr;
+    double* d_colstats = nullptr; size_t colstats_doubles = 0;
     std::vector<float> h_image;      // k-major actor image passed by value to the fused kernels (constant-bank weights)
     bool weights_in_constant_bank = false; bool rolled = false;
     // PPO runner bookkeeping (rl/components/on_policy_runner/on_policy_runner.h: episode_step, episode_return, truncated)

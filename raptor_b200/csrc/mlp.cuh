@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
             if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
             o.flush(ParamsRW{a.params + env, n});
             p = stage_dynamics<false>(sm_dyn, a.params, n, env);   // re-stage this thread's column only
-            sample_state(st, o, rng, hist_ptr, n);
+            sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
             dyn_invariants(d, p, st);
         }
         observe_to_scratch(st, p, rng, hist_ptr, n, scr + OBS0 * 32, 32);

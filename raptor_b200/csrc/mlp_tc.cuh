@@ -188,10 +188,9 @@ struct MlpTsSmem {
 
 // CTA prologue shared by both kernels: barriers, TMEM allocation, weight image by TMA.  Returns the context; every thread must call it.
 template <int IN, int OUT>
-__device__ __forceinline__ TsCtx mlp_ts_prologue(unsigned char* smraw, const float* __restrict__ tc_image){
-    using SM = MlpTsSmem<IN, OUT>;
-    float* sm_b = reinterpret_cast<float*>(smraw + SM::B);
-    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + SM::BAR);
+__device__ __forceinline__ TsCtx mlp_ts_prologue_at(unsigned char* smraw, int b_offset, int bar_offset, const float* __restrict__ tc_image){
+    float* sm_b = reinterpret_cast<float*>(smraw + b_offset);
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + bar_offset);
     uint64_t* bar_mma = bar_tma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -214,6 +213,10 @@ __device__ __forceinline__ TsCtx mlp_ts_prologue(unsigned char* smraw, const flo
     tc::mbar_wait(bar_tma, 0);
     __syncthreads();
     return c;
+}
+template <int IN, int OUT>
+__device__ __forceinline__ TsCtx mlp_ts_prologue(unsigned char* smraw, const float* __restrict__ tc_image){
+    return mlp_ts_prologue_at<IN, OUT>(smraw, MlpTsSmem<IN, OUT>::B, MlpTsSmem<IN, OUT>::BAR, tc_image);
 }
 __device__ __forceinline__ void mlp_ts_epilogue(const TsCtx& c){
     tc::tc_fence_before();
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
             if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
             compile_dynamics_block(sm_dyn + tid, [&](int i){ return o[i]; });   // this thread's column only
-            sample_state(st, o, rng, hist_ptr, n);
+            sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
             dyn_invariants(d, o, st);
         }
         float obs[IN];

@@ -225,7 +225,10 @@ __device__ __forceinline__ void initial_state(EnvState<Spec>& st, const P& p, fl
     }
 }
 
-template <class Spec, class P>
+// KEEP_DEAD_TARGET: a reset that draws the POSITION trajectory leaves the previous episode's Langevin target in the state, exactly as the
+// reference does (30_sample_initial_state.h:217-219: `case POSITION: break;`); the values are never read while the type is POSITION and are
+// zeroed when the type becomes LANGEVIN again.  false: the state is built from scratch (the vector-API call on a fresh State).
+template <class Spec, class P, bool KEEP_DEAD_TARGET = false>
 __device__ __forceinline__ void sample_state(EnvState<Spec>& st, const P& p, uint64_t& rng, float* __restrict__ hist_ptr, size_t n){
 #pragma unroll
     for(int i = 0; i < X_DIM; i++) st.x[i] = 0.0f;
@@ -291,8 +294,10 @@ __device__ __forceinline__ void sample_state(EnvState<Spec>& st, const P& p, uin
             if(threshold < acc){ type = t; break; }
         }
         st.traj_type = type;
+        if(!KEEP_DEAD_TARGET || type == 1){
 #pragma unroll
-        for(int i = 0; i < 12; i++) st.lang[i] = 0.0f;
+            for(int i = 0; i < 12; i++) st.lang[i] = 0.0f;
+        }
     }
 }
 

@@ -238,6 +238,44 @@ class VectorEnvironment:
         self._check(self._lib.b200l2f_collect(self._h, n_steps, episode_step_limit, p, ms))
         return dataset
 
+    # ---- PPO learner feed (what the reference's loop step does between collect and train, rl/algorithms/ppo/loop/core/operations_generic.h:104-117)
+    def load_critic(self, blob, standardize=0, gemm=L.GEMM_TCGEN05_3XTF32):
+        """value network [standardize ->] Dense(OBS,64,ReLU) -> Dense(64,64,ReLU) -> Dense(64,1), blob in the MLP order of include/b200_l2f.h"""
+        blob = np.ascontiguousarray(blob, np.float32)
+        desc = L.PolicyDesc(L.POLICY_MLP, self.OBSERVATION_DIM, 64, 1, standardize, L.HEAD_IDENTITY, 0, gemm)
+        self._check(self._lib.b200l2f_critic_load(self._h, ctypes.byref(desc), blob.ctypes.data, blob.size))
+
+    def _dataset_arg(self, dataset, n_steps):
+        return _arg(dataset, np.float32, ((n_steps + 1) * self.N_ENVIRONMENTS, self.OBSERVATION_DIM + 15), "dataset")
+
+    def evaluate_values(self, dataset, n_steps):
+        """critic over all (T+1) N observation rows -> the all_values column, in place"""
+        p, ms, _ = self._dataset_arg(dataset, n_steps)
+        self._check(self._lib.b200l2f_evaluate_values(self._h, n_steps, p, ms))
+        return dataset
+
+    def estimate_generalized_advantages(self, dataset, n_steps, gamma=0.99, lam=0.95, ignore_termination=False):
+        """rl_tools::estimate_generalized_advantages (rl/algorithms/ppo/operations_generic.h:54-89) on the value column, in place"""
+        p, ms, _ = self._dataset_arg(dataset, n_steps)
+        self._check(self._lib.b200l2f_estimate_generalized_advantages(self._h, n_steps, gamma, lam, int(ignore_termination), p, ms))
+        return dataset
+
+    def values_and_advantages(self, dataset, n_steps, gamma=0.99, lam=0.95, ignore_termination=False):
+        """evaluate_values + estimate_generalized_advantages in one backward pass over time (the dataset is read once)"""
+        p, ms, _ = self._dataset_arg(dataset, n_steps)
+        self._check(self._lib.b200l2f_values_and_advantages(self._h, n_steps, gamma, lam, int(ignore_termination), p, ms))
+        return dataset
+
+    def normalizer_update(self, dataset, n_steps, mean, std, age):
+        """rl::components::running_normalizer update with the dataset's observation block; mean / std: host float32 [OBS], updated in place;
+        returns the new age"""
+        p, ms, _ = self._dataset_arg(dataset, n_steps)
+        pm, _, _ = _arg(mean, np.float32, (self.OBSERVATION_DIM,), "mean")
+        ps, _, _ = _arg(std, np.float32, (self.OBSERVATION_DIM,), "std")
+        a = ctypes.c_int32(age)
+        self._check(self._lib.b200l2f_normalizer_update(self._h, n_steps, p, ms, pm, ps, ctypes.byref(a)))
+        return int(a.value)
+
     def get_hidden(self):
         h = np.zeros((self.N_ENVIRONMENTS, self.policy.hidden_dim), np.float32)
         g = np.zeros(self.N_ENVIRONMENTS, np.int32)

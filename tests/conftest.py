@@ -42,3 +42,19 @@ def foundation_dr_env_params(lib, spec):
     p[124:139] = np.array([d["t2w"][0], d["t2w"][1], d["t2i"][0], d["t2i"][1], d["mass"][0], d["mass"][1], d["size_dev"],
                            d["tau_rise"][0], d["tau_rise"][1], d["tau_fall"][0], d["tau_fall"][1], d["kq"][0], d["kq"][1], 0.0, d["dist_force"]], np.float32)
     return p
+
+
+def random_mlp_blob(rs, in_dim, out_dim, standardize, log_std):
+    hd = 64
+    parts = []
+    if standardize:
+        parts += [rs.normal(0, 0.1, in_dim), 1.0 / rs.uniform(0.5, 2.0, in_dim)]
+    for (o, i) in [(hd, in_dim), (hd, hd), (out_dim, hd)]:
+        bound = np.sqrt(6.0 / i)
+        w = rs.uniform(-bound, bound, (o, i))
+        if o == out_dim:
+            w *= 0.3
+        parts += [w.ravel(), rs.uniform(-0.05, 0.05, o)]
+    if log_std:
+        parts.append(np.log(np.full(4, 0.5)))
+    return np.concatenate(parts).astype(np.float32)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import foundation_dr_env_params
+from conftest import foundation_dr_env_params, random_mlp_blob
 from oracle import binding as B
 
 pytestmark = pytest.mark.gpu
@@ -323,22 +323,6 @@ def test_per_environment_mdp_parameters(rb, port):
 # ---------------------------------------------------------------------------------------------------------------------------
 # MLP actors (SAC teacher, PPO) and PPO collection
 # ---------------------------------------------------------------------------------------------------------------------------
-def random_mlp_blob(rs, in_dim, out_dim, standardize, log_std):
-    hd = 64
-    parts = []
-    if standardize:
-        parts += [rs.normal(0, 0.1, in_dim), 1.0 / rs.uniform(0.5, 2.0, in_dim)]
-    for (o, i) in [(hd, in_dim), (hd, hd), (out_dim, hd)]:
-        bound = np.sqrt(6.0 / i)
-        w = rs.uniform(-bound, bound, (o, i))
-        if o == out_dim:
-            w *= 0.3
-        parts += [w.ravel(), rs.uniform(-0.05, 0.05, o)]
-    if log_std:
-        parts.append(np.log(np.full(4, 0.5)))
-    return np.concatenate(parts).astype(np.float32)
-
-
 @pytest.mark.parametrize("spec,head", [(B.SPEC_RAPTOR, "ppo"), (B.SPEC_TEACHER, "squash"), (B.SPEC_DEFAULT, "identity")])
 def test_mlp_evaluate_step(rb, port, spec, head):
     n = 300
@@ -432,6 +416,67 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     close(got3[:T, :, 31], want3[:T, :, 31], 2e-3, 2e-2, "reward")
     assert np.all(got3[..., 34:] == 0)                                            # learner columns untouched
     close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,n,gemm", [(B.SPEC_RAPTOR, 256, "tcgen05"), (B.SPEC_RAPTOR_DR, 200, "tcgen05"), (B.SPEC_TEACHER_DR, 203, "tcgen05"), (B.SPEC_RAPTOR, 203, "fp32")])
+def test_learner_feed_vs_oracle(rb, port, spec, n, gemm):
+    """critic values, GAE and the running normalizer on the collected dataset (the PPO loop step between collect and train) against the oracle,
+    which is pinned bit-for-bit to the reference's own evaluate / estimate_generalized_advantages / running_normalizer update
+    (tests/test_oracle_vs_reference.py::test_collect_gae_normalizer).  n = 256: every warp takes the TMA bulk path; 200: a ragged last tile;
+    203: row pitch not 16-byte aligned (generic loads)."""
+    import torch
+    gemm = rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32
+    T, limit = 24, 9
+    obs = port.observation_dim(spec)
+    D = obs + 15
+    rs = np.random.RandomState(17)
+    actor = random_mlp_blob(rs, obs, 4, True, True)
+    critic = random_mlp_blob(rs, obs, 1, True, False)
+    critic[-65:] *= 20.0        # values of order 1..10 so that the advantage recursion is exercised with realistic magnitudes
+    env = rb.VectorEnvironment(n, spec)
+    env_p = foundation_dr_env_params(port, spec) if spec in (B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR) else port.nominal_parameters(spec)
+    env.set_environment_parameters(env_p)
+    env.initialize_rng(3, warmup=16)
+    env.initial_parameters()
+    env.initial_state()
+    env.load_policy(actor, arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN)
+    env.load_critic(critic, standardize=1, gemm=gemm)
+    env.collect_reset()
+    data = env.collect(T, limit)
+    assert data[:T * n, obs + 11].sum() > 0
+    crit = port.make_policy(critic, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=1, standardize=1, head=B.HEAD_IDENTITY)
+    want = data.copy()
+    port.evaluate_values(crit, want, n, T)
+    # (1) values, host dataset
+    got = env.evaluate_values(data.copy(), T)
+    close(got[:, obs + 12], want[:, obs + 12], 1e-4, 1e-4, "critic values")
+    assert np.array_equal(got[:, :obs + 12], data[:, :obs + 12]) and np.all(got[:, obs + 13:] == 0)
+    # (2) stand-alone GAE on the ORACLE's values: bit-exact (the recursion is pure fp32 add / mul in the reference's order)
+    for ignore in (False, True):
+        w = want.copy()
+        port.estimate_generalized_advantages(w, n, T, 0.99, 0.95, ignore)
+        g = env.estimate_generalized_advantages(want.copy(), T, 0.99, 0.95, ignore)
+        assert np.array_equal(g, w), "GAE ignore_termination=%s" % ignore
+        assert np.abs(w[:T * n, obs + 13]).max() > 0.1
+    # (3) fused single pass == values pass followed by the stand-alone GAE (bit for bit), on a device-resident dataset
+    dev = torch.from_numpy(data.copy()).cuda()
+    env.values_and_advantages(dev, T, 0.99, 0.95, False)
+    env.synchronize()
+    two_pass = env.estimate_generalized_advantages(got.copy(), T, 0.99, 0.95, False)
+    assert np.array_equal(dev.cpu().numpy(), two_pass)
+    w = want.copy()
+    port.estimate_generalized_advantages(w, n, T, 0.99, 0.95, False)
+    close(two_pass[:T * n, obs + 13:], w[:T * n, obs + 13:], 1e-3, 1e-3, "advantages / target values from the GPU critic")
+    # (4) running observation normalizer, two updates
+    mean_g, std_g, mean_w, std_w = np.zeros(obs, np.float32), np.ones(obs, np.float32), np.zeros(obs, np.float32), np.ones(obs, np.float32)
+    age_g = age_w = 0
+    for _ in range(2):
+        age_g = env.normalizer_update(data, T, mean_g, std_g, age_g)
+        age_w = port.normalizer_update(data, n, T, mean_w, std_w, age_w)
+    assert age_g == age_w == 2
+    close(mean_g, mean_w, 1e-5, 1e-6, "normalizer mean")
+    close(std_g, std_w, 1e-5, 1e-6, "normalizer std")
 
 
 def test_time_chunked_scheduler_is_transparent(rb):

@@ -140,3 +140,66 @@ def test_closed_loop_rollout(port, ref, spec, T):
     for k in ["states", "observations", "actions", "rewards", "terminated"]:
         assert np.array_equal(oa[k], ob[k]), k
     assert np.array_equal(h_a, h_b) and np.array_equal(g_a, g_b) and np.array_equal(r_a, r_b)
+
+
+# ---- PPO data path: MLP actor / critic, collect (the reference's own per-environment prologue / epilogue), GAE, running normalizer ----------
+from conftest import random_mlp_blob  # noqa: E402
+
+
+@pytest.mark.parametrize("in_dim,out_dim,standardize", [(22, 4, True), (26, 4, False), (22, 1, True), (26, 1, True), (26, 8, False), (82, 4, True)])
+def test_mlp_forward(port, ref, in_dim, out_dim, standardize):
+    rs = np.random.RandomState(in_dim * 10 + out_dim)
+    blob = random_mlp_blob(rs, in_dim, out_dim, standardize, False)
+    x = rs.normal(0, 1.0, (64, in_dim)).astype(np.float32)
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=in_dim, hidden_dim=64, output_dim=out_dim, standardize=int(standardize), head=B.HEAD_IDENTITY)
+    got, _, _ = port.policy_evaluate_step(pol, x)
+    want = ref.mlp_evaluate(blob, in_dim, out_dim, standardize, x)
+    assert np.array_equal(got, want)
+
+
+def _collect_inputs(lib, spec, n, seed):
+    env_p = foundation_dr_env_params(lib, spec) if spec in (B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR) else lib.nominal_parameters(spec)
+    rng = lib.rng_states(seed, n, warmup=16)
+    params = np.tile(env_p, (n, 1)).astype(np.float32)
+    states = lib.sample_initial_state_n(spec, params, rng)
+    return env_p, params, states, rng
+
+
+@pytest.mark.parametrize("spec", [B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR])
+def test_collect_gae_normalizer(port, ref, spec):
+    n, T, limit = ref.ppo_sizes()
+    obs = port.observation_dim(spec)
+    rs = np.random.RandomState(3 + spec)
+    actor = random_mlp_blob(rs, obs, 4, True, True)
+    critic = random_mlp_blob(rs, obs, 1, True, False)
+    env_p, params, states, rng = _collect_inputs(ref, spec, n, 11)
+    pol = port.make_policy(actor, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
+    crit = port.make_policy(critic, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=1, standardize=1, head=B.HEAD_IDENTITY)
+    A = dict(params=params.copy(), states=states.copy(), rng=rng.copy(), step=np.zeros(n, np.int32), ret=np.zeros(n, np.float32), trunc=np.ones(n, np.uint8))
+    Bk = {k: v.copy() for k, v in A.items()}
+    for it in range(2):   # second pass starts from carried-over runner state
+        da = port.collect(spec, pol, env_p, A["params"], A["states"], A["rng"], A["step"], A["ret"], A["trunc"], T, limit)
+        db = ref.collect(spec, actor, True, env_p, Bk["params"], Bk["states"], Bk["rng"], Bk["step"], Bk["ret"], Bk["trunc"])
+        assert np.array_equal(da, db), "dataset, pass %d" % it
+        for k in A:
+            assert np.array_equal(A[k], Bk[k]), k
+        assert da[:T * n, obs + 11].sum() > 0, "the fixture must contain truncations"
+    # critic values (port) vs the reference MLP, then GAE on both
+    port.evaluate_values(crit, da, n, T)
+    want_v = ref.mlp_evaluate(critic, obs, 1, True, db[:, :obs])
+    assert np.array_equal(da[:, obs + 12], want_v[:, 0])
+    db[:, obs + 12] = want_v[:, 0]
+    gamma, lam = ref.ppo_gamma_lambda()
+    for ignore in (False, True):
+        ga, gb = da.copy(), db.copy()
+        port.estimate_generalized_advantages(ga, n, T, gamma, lam, ignore)
+        ref.estimate_generalized_advantages(spec, gb, ignore)
+        assert np.array_equal(ga, gb)
+        assert np.abs(ga[:T * n, obs + 13]).max() > 0
+    # running normalizer, two updates
+    mean_a, std_a, mean_b, std_b = np.zeros(obs, np.float32), np.ones(obs, np.float32), np.zeros(obs, np.float32), np.ones(obs, np.float32)
+    age_a = age_b = 0
+    for _ in range(2):
+        age_a = port.normalizer_update(da, n, T, mean_a, std_a, age_a)
+        age_b = ref.normalizer_update(spec, db, mean_b, std_b, age_b)
+    assert age_a == age_b == 2 and np.array_equal(mean_a, mean_b) and np.array_equal(std_a, std_b)
