@@ -571,23 +571,26 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     const bool noise = (h->features & 1) != 0;
     const bool fast = !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     const bool constw = h->weights_in_constant_bank;
-    // observation / action noise present: the CUDA-core kernel carries the Box-Muller draws; the tcgen05 kernels are the noise-free fast path
-    const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && !noise;
+    const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32;
     // every vehicle thrusts along body z with diagonal inertia (true for all reference vehicles; B200L2F_DYNAMICS=general forces the full matrices)
     const bool allow_axial = [](){ const char* e = std::getenv("B200L2F_DYNAMICS"); return !(e && std::string(e) == "general"); }();
     const bool axial = allow_axial && (h->features & 4) == 0;
     const bool uniform = (h->features & 2) == 0;
+    // observation / action noise: carried by the tcgen05 TMEM-A kernels (MUFU Box-Muller) when the MDP constants, which include the noise
+    // standard deviations, are uniform across environments; otherwise by the CUDA-core kernels
+    const bool noise_on_tc = !noise || uniform;
     if(h->pol.arch == B200L2F_POLICY_MLP){
-        // tcgen05 path: H = 1 specs, no observation / action noise (as for the GRU actor), default math flags
-        if(tensor_cores && fast && h->d_mlp_tc_image && h->kind != KIND_DEFAULT) rc = launch_mlp_ts(h, a, uniform, axial);
+        // tcgen05 path: H = 1 specs, default math flags
+        if(tensor_cores && fast && noise_on_tc && h->d_mlp_tc_image && h->kind != KIND_DEFAULT) rc = launch_mlp_ts(h, a, uniform, axial, noise);
         else rc = launch_mlp_fp32(h, a);
     }
-    else if(tensor_cores){
+    else if(tensor_cores && !(noise && !(fast && uniform))){
         // A operand in TMEM ("TS" MMAs, 63 KB smem + 128 TMEM columns per CTA -> 3 CTAs/SM) is the default; B200L2F_A=smem selects the
-        // shared-memory-A variant (2 CTAs/SM).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
+        // shared-memory-A variant (2 CTAs/SM, no noise variant).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
         static const bool a_in_tmem = [](){ const char* e = std::getenv("B200L2F_A"); return !(e && std::string(e) == "smem"); }();
         static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
-        if(a_in_tmem && fast) rc = launch_raptor_ts(h, a, uniform, axial);
+        if(a_in_tmem && fast) rc = launch_raptor_ts(h, a, uniform, axial, noise);
+        else if(noise) rc = launch_raptor_fp32(h, a, noise, fast, constw, h->rolled);
         else rc = launch_raptor_tc(h, a, fast, uniform, g1_tc);
     }
     else rc = launch_raptor_fp32(h, a, noise, fast, constw, h->rolled);

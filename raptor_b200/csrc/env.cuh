@@ -341,14 +341,15 @@ __device__ __forceinline__ void desired_state(const EnvState<Spec>& st, float dp
 //   LinearVelocity :108-125 / TrajectoryTrackingLinearVelocity :409-429, AngularVelocityDelayed<0> :221-254.
 // Noise draws happen in column order (3 + 9 + 3 + 3 normals), each skipped when its std is 0.
 // ---------------------------------------------------------------------------------------------------------------
-template <class Spec, bool NOISE, class P>
+// FAST: the noise draws use the MUFU Box-Muller of the default-math kernels (same integer stream, |error| ~5e-7 x std)
+template <class Spec, bool NOISE, bool FAST = false, class P>
 __device__ __forceinline__ void observe18(const EnvState<Spec>& st, const P& p, uint64_t& rng, float* __restrict__ o){
     float dpos[3], dvel[3];
     desired_state(st, dpos, dvel);
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float v = (Spec::OBS_LAYOUT == OBS_RAPTOR) ? st.x[X_POS + i] : st.x[X_POS + i] - dpos[i];
-        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_POS]);
+        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, p[P_NOISE_POS]);
         o[i] = v;
     }
     const float q0 = st.x[X_ORI], q1 = st.x[X_ORI + 1], q2 = st.x[X_ORI + 2], q3 = st.x[X_ORI + 3];
@@ -363,18 +364,18 @@ __device__ __forceinline__ void observe18(const EnvState<Spec>& st, const P& p, 
     o[11] = (1 - 2 * q1 * q1 - 2 * q2 * q2);
     if constexpr(NOISE){
 #pragma unroll
-        for(int i = 0; i < 9; i++) o[3 + i] += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_ORI]);
+        for(int i = 0; i < 9; i++) o[3 + i] += rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, p[P_NOISE_ORI]);
     }
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float v = (Spec::OBS_LAYOUT == OBS_RAPTOR) ? st.x[X_VEL + i] : st.x[X_VEL + i] - dvel[i];
-        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_LINVEL]);
+        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, p[P_NOISE_LINVEL]);
         o[12 + i] = v;
     }
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float v = st.x[X_OMEGA + i];
-        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_NOISE_ANGVEL]);
+        if constexpr(NOISE) v += rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, p[P_NOISE_ANGVEL]);
         o[15 + i] = v;
     }
 }

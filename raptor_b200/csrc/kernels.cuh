@@ -79,7 +79,7 @@ __global__ void k_sample_params(float* __restrict__ params, const float* __restr
 // are, the fused kernels read them from the launch's constant bank instead of per-environment loads inside the time loop.
 __host__ __device__ constexpr bool mdp_uniform_index(int i){
     return (i >= P_RW_NONNEG && i <= P_RW_POS_INTEGRAL) || i == P_HOVER || i == P_TERM_ENABLED || i == P_TERM_LINVEL || i == P_TERM_ANGVEL ||
-           (i >= P_LANGEVIN_GAMMA && i <= P_LANGEVIN_ALPHA);
+           (i >= P_LANGEVIN_GAMMA && i <= P_LANGEVIN_ALPHA) || (i >= P_NOISE_POS && i <= P_ACTION_NOISE);
 }
 // features of the parameter set that select kernel variants: bit0 = some observation/action noise std != 0,
 // bit1 = some environment's "uniform" MDP parameter differs from environment 0's, bit2 = some vehicle is not "axial" (a rotor thrust

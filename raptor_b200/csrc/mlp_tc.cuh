@@ -164,10 +164,10 @@ __device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict
 }
 
 // full observation of an H = 1 spec in registers (same values and RNG order as observe_to_scratch)
-template <class Spec, bool NOISE, class P>
+template <class Spec, bool NOISE, bool FAST = false, class P>
 __device__ __forceinline__ void observe_regs(const EnvState<Spec>& st, const P& p, uint64_t& rng, float* __restrict__ o){
     static_assert(Spec::H == 1, "register observation: H = 1 specs");
-    observe18<Spec, NOISE>(st, p, rng, o);
+    observe18<Spec, NOISE, FAST>(st, p, rng, o);
 #pragma unroll
     for(int i = 0; i < 4; i++) o[18 + i] = st.hist[i];
     if constexpr(Spec::OBS_LAYOUT == OBS_TEACHER){
@@ -228,7 +228,7 @@ __device__ __forceinline__ void mlp_ts_epilogue(const TsCtx& c){
 // closed-loop rollout, deterministic MLP actor (head identity or squash-eval), persistent (tile, time-chunk) work queue as in
 // k_rollout_raptor_ts (the actor is stateless, so a chunk hands over the environment state and the episode accumulators only)
 // ---------------------------------------------------------------------------------------------------------------
-template <class Spec, int OUT, bool UNIFORM, bool AXIAL>
+template <class Spec, int OUT, bool UNIFORM, bool AXIAL, bool NOISE = false>
 __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     constexpr int IN = Spec::OBS_DIM;
     using SM = MlpTsSmem<IN, OUT>;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
         if(a.out_states && active && (t % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
         float obs[IN];
-        observe_regs<Spec, false>(st, p, rng, obs);
+        observe_regs<Spec, NOISE, true>(st, p, rng, obs);
         if(a.out_obs && active){
             float* row = a.out_obs + ((size_t)t * n + env) * IN;
 #pragma unroll
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        env_step_compiled<Spec, false, false, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
+        env_step_compiled<Spec, false, NOISE, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;

@@ -4,11 +4,11 @@
 
 namespace b200l2f {
 namespace {
-template <class Spec, int OUT, bool UNIFORM, bool AXIAL>
+template <class Spec, int OUT, bool UNIFORM, bool AXIAL, bool NOISE = false>
 int launch_rollout_mlp_ts(b200l2f_handle* h, RolloutArgs a){
     constexpr int IN = Spec::OBS_DIM;
     using SM = MlpTsSmem<IN, OUT>;
-    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM, AXIAL>;
+    auto kern = k_rollout_mlp_ts<Spec, OUT, UNIFORM, AXIAL, NOISE>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -27,8 +27,17 @@ int launch_rollout_mlp_ts(b200l2f_handle* h, RolloutArgs a){
 }
 }  // namespace
 
-int launch_mlp_ts(b200l2f_handle* h, const RolloutArgs& a, bool uniform, bool axial){
+int launch_mlp_ts(b200l2f_handle* h, const RolloutArgs& a, bool uniform, bool axial, bool noise){
     const bool o8 = h->pol.output_dim == 8;
+    if(noise){
+        if(!uniform) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the tcgen05 noise variant needs uniform MDP constants");
+        auto gon = [&](auto spec) -> int {
+            using Spec = decltype(spec);
+            if(axial) return o8 ? launch_rollout_mlp_ts<Spec, 8, true, true, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, true, true>(h, a);
+            return o8 ? launch_rollout_mlp_ts<Spec, 8, true, false, true>(h, a) : launch_rollout_mlp_ts<Spec, 4, true, false, true>(h, a);
+        };
+        return h->kind == KIND_RAPTOR ? gon(SpecRaptor{}) : gon(SpecTeacher{});
+    }
             auto gots = [&](auto spec) -> int {
                 using Spec = decltype(spec);
                 if(!uniform) return o8 ? launch_rollout_mlp_ts<Spec, 8, false, false>(h, a) : launch_rollout_mlp_ts<Spec, 4, false, false>(h, a);

@@ -208,7 +208,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
 #pragma unroll
     for(int i = 0; i < 4; i++){
         float a = action[i];
-        if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL>(rng, 0.0f, p[P_ACTION_NOISE]);
+        if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL, FAST && !Spec::RNG_OOL>(rng, 0.0f, p[P_ACTION_NOISE]);
         setpoint[i] = clamp_t<FAST>(a, -1.0f, 1.0f) * d.half_range + amin + d.half_range;
     }
     const float dt = d.dt;
@@ -552,7 +552,8 @@ struct TsSmem {
     static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
     static constexpr int TOTAL = BAR + 32;
 };
-template <class Spec, bool FAST, bool UNIFORM, bool AXIAL>
+// NOISE: observation / action noise (18 + 4 normal draws per step, each skipped when its std is 0) with the MUFU Box-Muller.
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false>
 __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     static_assert(FAST, "the TMEM-A kernel reads the scaled-gate image (build_tc_image_host(..., true)): default math only");
     constexpr int HD = 16;
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         if(a.out_states && active && (t % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
         float obs[24];
-        observe18<Spec, false>(st, p, rng, obs);
+        observe18<Spec, NOISE, true>(st, p, rng, obs);
         if constexpr(Spec::H == 1){
 #pragma unroll
             for(int i = 0; i < 4; i++) obs[18 + i] = st.hist[i];
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        if(Spec::H == 1 || active) env_step_compiled<Spec, false, false, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
+        if(Spec::H == 1 || active) env_step_compiled<Spec, false, NOISE, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;

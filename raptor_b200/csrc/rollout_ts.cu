@@ -5,9 +5,9 @@
 
 namespace b200l2f {
 namespace {
-template <class Spec, bool FAST, bool UNIFORM, bool AXIAL>
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false>
 int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
-    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL>;
+    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL, NOISE>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -29,9 +29,13 @@ int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
 }
 }  // namespace
 
-int launch_raptor_ts(b200l2f_handle* h, const RolloutArgs& a, bool uniform, bool axial){
+int launch_raptor_ts(b200l2f_handle* h, const RolloutArgs& a, bool uniform, bool axial, bool noise){
     auto go = [&](auto spec) -> int {
         using Spec = decltype(spec);
+        if(noise){
+            if(!uniform) return fail(h, B200L2F_ERR_UNSUPPORTED, "rollout: the tcgen05 noise variant needs uniform MDP constants");
+            return axial ? launch_rollout_ts<Spec, true, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false, true>(h, a);
+        }
         if(!uniform) return launch_rollout_ts<Spec, true, false, false>(h, a);
         return axial ? launch_rollout_ts<Spec, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false>(h, a);
     };

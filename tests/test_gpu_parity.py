@@ -294,6 +294,48 @@ def test_tcgen05_rollout_matches_fp32_rollout(rb):
     assert (oa["episode_length"] == ob["episode_length"]).mean() > 0.995
 
 
+@pytest.mark.parametrize("actor", ["raptor_gru", "teacher_mlp"])
+def test_tcgen05_noise_variants_match_cuda_core_kernels(rb, port, actor):
+    """observation / action noise inside the tcgen05 rollout kernels (MUFU Box-Muller) against the CUDA-core kernels (libdevice Box-Muller) and
+    the oracle: the integer RNG streams are bit-exact, trajectories agree to the closed-loop tolerance of the noise fixture"""
+    n, T = 300, 60
+    spec = rb.SPEC_RAPTOR if actor == "raptor_gru" else rb.SPEC_TEACHER
+    row = port.nominal_parameters(spec).copy()
+    row[108:114] = np.array([0.02, 0.03, 0.05, 0.1, 0.0, 0.05], np.float32)   # imu noise unused by these observations; action noise on
+    blob = None if actor == "raptor_gru" else random_mlp_blob(np.random.RandomState(9), 26, 8, False, False)
+    outs = []
+    for gemm in (rb.GEMM_FP32_CUDA_CORES, rb.GEMM_TCGEN05_3XTF32):
+        e = rb.VectorEnvironment(n, spec)
+        e.set_environment_parameters(row)
+        e.initialize_rng(21, warmup=16)
+        e.initial_parameters()
+        e.sample_initial_state()
+        if actor == "raptor_gru":
+            e.load_policy(gemm=gemm)
+        else:
+            e.load_policy(blob, arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=gemm)
+        params, states, rng = e.get_parameters(), e.get_state(), e.get_rng()
+        o = e.rollout(T, record=("observations", "actions", "terminated"))
+        outs.append((o, e.get_rng()))
+    (oa, ra), (ob, rb_) = outs
+    assert np.array_equal(ra, rb_)
+    close(ob["observations"][:20], oa["observations"][:20], 1e-3, 1e-4, "noisy observations, first 20 steps")
+    close(ob["actions"][:20], oa["actions"][:20], 2e-3, 2e-3, "actions, first 20 steps")
+    assert (oa["terminated"] == ob["terminated"]).mean() > 0.999
+    # and against the oracle (same stream, same draw order)
+    if actor == "raptor_gru":
+        pol = port.make_policy(rb.raptor_policy_blob())
+        h = np.tile(rb.raptor_policy_blob()[352 + 16 + 2 * (768 + 48):][:16], (n, 1)).astype(np.float32)
+        want = port.rollout(spec, pol, params, states, rng, T, hidden=h, gru_step=np.zeros(n, np.int32))
+    else:
+        pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_EVAL)
+        want = port.rollout(spec, pol, params, states, rng, T)
+    assert np.array_equal(rng, rb_)
+    obs_dim = 22 if actor == "raptor_gru" else 26
+    close(ob["observations"][:20], want["observations"][:20, :, :obs_dim], 1e-3, 1e-4, "noisy observations vs oracle")
+    close(ob["actions"][:20], want["actions"][:20], 2e-3, 2e-3, "actions vs oracle")
+
+
 def test_per_environment_mdp_parameters(rb, port):
     """reward weights / termination thresholds that differ per environment take the general (non-uniform) kernel path"""
     n, T = 256, 30

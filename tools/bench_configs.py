@@ -70,6 +70,22 @@ def main():
     out.append({"config": "4: 262 144 envs x 256-step PPO collection, PPO MLP 22-64-64-4 (standardize, learned log_std), DR resets, dataset rows [(T+1)N, 37] in HBM",
                 "env_steps_per_s": n * T / ms * 1e3, "ms_per_launch": ms, "dataset_bytes_written": written, "hbm_write_gbs": written / ms / 1e6,
                 "mean_reward": float(data[: T * n, 31].mean().item()), "truncated_fraction": float(data[: T * n, 33].mean().item())})
+    # ---- learner feed on the config-4 dataset (stays in HBM): critic values + GAE in one pass, stand-alone GAE, normalizer update
+    env.load_critic(mlp_blob(rs, 22, 1, True, False), standardize=1, gemm=gemm)
+    rows = (T + 1) * n
+    nop = lambda: None
+    ms_f = timed(lambda: env.values_and_advantages(data, T), nop, stream=stream, flush=flush)
+    ms_v = timed(lambda: env.evaluate_values(data, T), nop, stream=stream, flush=flush)
+    ms_g = timed(lambda: env.estimate_generalized_advantages(data, T), nop, stream=stream, flush=flush)
+    mean, std = np.zeros(22, np.float32), np.ones(22, np.float32)
+    ms_n = timed(lambda: env.normalizer_update(data, T, mean, std, 0), nop, stream=stream, flush=flush)
+    row_bytes = 37 * 4
+    out.append({"config": "4 learner feed: critic 22-64-64-1 values + GAE on the [(T+1)N, 37] dataset in HBM (%.1f GB)" % (rows * row_bytes / 1e9),
+                "fused_values_gae_ms": ms_f, "fused_rows_per_s": rows / ms_f * 1e3,
+                "fused_hbm_gbs_algorithmic": (rows * (22 + 3) * 4 + rows * 3 * 4) / ms_f / 1e6, "fused_hbm_gbs_rows_streamed": (rows * row_bytes + rows * 12) / ms_f / 1e6,
+                "values_only_ms": ms_v, "gae_only_ms": ms_g, "gae_hbm_gbs_algorithmic": rows * 6 * 4 / ms_g / 1e6,
+                "normalizer_update_ms": ms_n, "normalizer_hbm_gbs": 2 * T * n * row_bytes / ms_n / 1e6,
+                "collect_plus_feed_env_steps_per_s": n * T / (ms + ms_f) * 1e3})
     for o in out:
         o["gemm"] = gemm_name
         print(json.dumps(o))
