@@ -180,6 +180,10 @@ class Port(_Common):
         L.oracle_evaluate_values.argtypes = [ctypes.POINTER(OraclePolicy), c_int, c_int, f32, c_int]
         L.oracle_estimate_generalized_advantages.argtypes = [c_int, c_int, f32, c_int, c_float, c_float, c_int]
         L.oracle_normalizer_update.argtypes = [c_int, c_int, f32, c_int, f32, f32, ctypes.POINTER(c_int)]
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        L.oracle_dagger_add_to_dataset.restype = ctypes.c_longlong
+        L.oracle_dagger_add_to_dataset.argtypes = [c_int, c_int, c_int, f32, f32, u8, u64, f32, f32, i32, f32, f32, u8, u8]
 
     def make_policy(self, blob, arch=POLICY_RAPTOR_GRU, input_dim=22, hidden_dim=16, output_dim=4, standardize=0, head=HEAD_IDENTITY):
         blob = np.ascontiguousarray(blob, np.float32)
@@ -231,6 +235,18 @@ class Port(_Common):
         self.lib.oracle_normalizer_update(n, T, data, data.shape[1], mean, std, ctypes.byref(a))
         return int(a.value)
 
+    def dagger_add_to_dataset(self, params, states, terminated, rng, teacher_blobs, offsets, episodes_per_teacher):
+        """states [T, n, SD] step-major, terminated [T, n]; returns dict(rows, episode_start, input_student, output_target, truncated, reset)"""
+        T, n = terminated.shape
+        cap = T * n
+        out = dict(episode_start=np.zeros(cap, np.int32), input_student=np.zeros((cap, 22), np.float32), output_target=np.zeros((cap, 4), np.float32),
+                   truncated=np.zeros(cap, np.uint8), reset=np.zeros(cap, np.uint8))
+        out["rows"] = int(self.lib.oracle_dagger_add_to_dataset(n, T, episodes_per_teacher, np.ascontiguousarray(params, np.float32), np.ascontiguousarray(states, np.float32),
+                                                                np.ascontiguousarray(terminated, np.uint8), rng, np.ascontiguousarray(teacher_blobs, np.float32),
+                                                                np.ascontiguousarray(offsets, np.float32), out["episode_start"], out["input_student"], out["output_target"],
+                                                                out["truncated"], out["reset"]))
+        return out
+
     def hardware_threads(self):
         return int(self.lib.oracle_hardware_threads())
 
@@ -262,6 +278,10 @@ class Ref(_Common):
             L.ref_collect.argtypes = [c_int, f32, c_int, f32, f32, f32, u64, vp, vp, vp, f32]
             L.ref_gae.argtypes = [c_int, f32, c_int]
             L.ref_normalizer_update.argtypes = [c_int, f32, f32, f32, ctypes.POINTER(c_int)]
+        if hasattr(L, "ref_dagger_add_to_dataset"):
+            u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+            i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+            L.ref_dagger_add_to_dataset.argtypes = [f32, f32, u8, f32, f32, i32, f32, f32, u8, u8]
 
     def policy_kat(self):
         mx = c_float()
@@ -333,6 +353,23 @@ class Ref(_Common):
         a = c_int(age)
         self.lib.ref_normalizer_update(spec, data, mean, std, ctypes.byref(a))
         return int(a.value)
+
+    def dagger_sizes(self):
+        a, b = c_int(), c_int()
+        self.lib.ref_dagger_sizes(ctypes.byref(a), ctypes.byref(b))
+        return int(a.value), int(b.value)
+
+    def dagger_add_to_dataset(self, params, states_episode_major, terminated_episode_major, teacher_blob, offset):
+        """the reference's add_to_dataset for ONE teacher: params [10, 145], states [10, 500, 48], terminated [10, 500]"""
+        ne, T = self.dagger_sizes()
+        cap = ne * T
+        out = dict(episode_start=np.zeros(cap, np.int32), input_student=np.zeros((cap, 22), np.float32), output_target=np.zeros((cap, 4), np.float32),
+                   truncated=np.zeros(cap, np.uint8), reset=np.zeros(cap, np.uint8))
+        out["rows"] = int(self.lib.ref_dagger_add_to_dataset(np.ascontiguousarray(params, np.float32), np.ascontiguousarray(states_episode_major, np.float32),
+                                                             np.ascontiguousarray(terminated_episode_major, np.uint8), np.ascontiguousarray(teacher_blob, np.float32),
+                                                             np.ascontiguousarray(offset, np.float32), out["episode_start"], out["input_student"], out["output_target"],
+                                                             out["truncated"], out["reset"]))
+        return out
 
     def hardware_threads(self):
         return int(self.lib.ref_hardware_threads())

@@ -925,4 +925,46 @@ void oracle_normalizer_update(int N, int T, const float* dataset, int data_dim, 
         std_io[c] = std_io[c] + (data_std - std_io[c]) / (*age_io);
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Foundation-policy DAgger data path: add_to_dataset, src/foundation_policy/post_training/helper.h:43-110, for all teachers at once.
+ * The student rollout was recorded step-major (states [T][n][SD], terminated [T][n]); environment e belongs to teacher e / episodes_per_teacher
+ * and episodes are appended in environment order (= the reference's teacher loop, post_training/main.cpp:304-309, then its episode loop).
+ * Per episode and step, up to and including the first terminated step: teacher observation (26, pre-training layout) and student observation
+ * (22, post-training layout, position minus the teacher's steady-state offset) of the recorded state, with the environment's parameters and
+ * its RNG stream (draws only when the observation noise is on: teacher observation first, helper.h:64-65); truncated = terminated or last step
+ * (:70); reset: the reference's flag is initialised true and never cleared (:52,72-75), so every row carries true; episode_start[episode] = its
+ * first row (:55); then the teacher (MLP 26-64-64-8 + sample_and_squash in Evaluation mode: tanh(mean)) labels every
+ * row (:92-104).  Returns the number of rows.
+ * ------------------------------------------------------------------------------------------- */
+long long oracle_dagger_add_to_dataset(int n, int T, int episodes_per_teacher, const float* params, const float* states, const unsigned char* terminated, uint64_t* rng,
+                                       const float* teacher_blobs, const float* offsets, int* episode_start, float* input_student, float* output_target,
+                                       unsigned char* truncated_out, unsigned char* reset_out){
+    spec_t sp_student = get_spec(ORACLE_SPEC_RAPTOR), sp_teacher = get_spec(ORACLE_SPEC_TEACHER);
+    const int SD = 44 + 4 * sp_student.H;
+    const int BLOB = 64 * 26 + 64 + 64 * 64 + 64 + 8 * 64 + 8;
+    long long index = 0;
+    for(int e = 0; e < n; e++){
+        const int teacher = e / episodes_per_teacher;
+        const float* p = params + (size_t)e * ORACLE_PARAMS_DIM;
+        oracle_policy_t pol = {ORACLE_POLICY_MLP, 26, 64, 8, 0, ORACLE_HEAD_SQUASH_EVAL, teacher_blobs + (size_t)teacher * BLOB};
+        episode_start[e] = (int)index;
+        int step;
+        for(step = 0; step < T; step++){
+            const float* s = states + ((size_t)step * n + e) * SD;
+            float obs_teacher[26], obs_student[22];
+            observe_impl(&sp_teacher, p, s, &rng[e], obs_teacher);
+            observe_impl(&sp_student, p, s, &rng[e], obs_student);
+            for(int i = 0; i < 3; i++) obs_student[i] = obs_student[i] - offsets[teacher * 3 + i];
+            memcpy(input_student + (size_t)(index + step) * 22, obs_student, sizeof(obs_student));
+            const int term = terminated[(size_t)step * n + e] != 0;
+            truncated_out[index + step] = (unsigned char)(term || step == T - 1);
+            reset_out[index + step] = 1;
+            mlp_forward(&pol, obs_teacher, NULL, output_target + (size_t)(index + step) * 4, NULL, NULL);
+            if(term){ step++; break; }
+        }
+        index += step;
+    }
+    return index;
+}
 int oracle_hardware_threads(void){ long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }

@@ -76,6 +76,10 @@ void oracle_collect(int spec, const oracle_policy_t* pol, int N, int T, int thre
 void oracle_evaluate_values(const oracle_policy_t* critic, int N, int T, float* dataset, int data_dim);
 void oracle_estimate_generalized_advantages(int N, int T, float* dataset, int data_dim, float gamma, float lambda, int ignore_termination);
 void oracle_normalizer_update(int N, int T, const float* dataset, int data_dim, float* mean_io, float* std_io, int* age_io);
+/* foundation-policy DAgger data path (post_training/helper.h:43-110): see l2f_oracle.c */
+long long oracle_dagger_add_to_dataset(int n, int T, int episodes_per_teacher, const float* params, const float* states, const unsigned char* terminated, uint64_t* rng,
+                                       const float* teacher_blobs, const float* offsets, int* episode_start, float* input_student, float* output_target,
+                                       unsigned char* truncated_out, unsigned char* reset_out);
 int oracle_hardware_threads(void);
 #ifdef __cplusplus
 }

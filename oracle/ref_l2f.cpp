@@ -792,3 +792,86 @@ void ref_normalizer_update(int spec, const float* dataset, float* mean_io, float
     }
 }
 }
+
+// ================================================================================================
+// Foundation-policy DAgger data path: the reference's own add_to_dataset (src/foundation_policy/post_training/helper.h:43-110), called on
+// rollout data recorded elsewhere (the engine / the port): teacher + student observations of every recorded state up to the first termination,
+// episode compaction, truncated / reset flags and the teacher's action targets (MLP 26-64-64-8 + sample_and_squash in Evaluation mode).
+// helper.h is included where it lies; its sample_trajectories is the reference's rollout (rl_tools::evaluate) and stays uninstantiated here.
+// ================================================================================================
+#include <iostream>
+#include <sstream>
+#include <rl_tools/rl/environments/l2f/operations_cpu.h>
+#include <rl_tools/rl/utils/evaluation/operations_generic.h>
+#include "post_training/helper.h"
+
+namespace ref_dagger{
+    constexpr TI N_EPISODES = 10;
+    constexpr TI STEP_LIMIT = ENV_RAPTOR::EPISODE_STEP_LIMIT;
+    constexpr TI DATASET_SIZE = N_EPISODES * STEP_LIMIT;
+    static_assert(STEP_LIMIT == 500, "post_training/environment.h:14");
+    using CAP = rlt::nn::capability::Forward<true>;
+    struct Teacher{ // rl/algorithms/sac/loop/core/approximators_mlp.h:14-37 with pre_training/config.h:27-29 (3 layers, hidden 64, ReLU)
+        using INPUT_SHAPE = rlt::tensor::Shape<TI, 1, 32, ENV_TEACHER::Observation::DIM>;
+        using MLP_CONFIG = rlt::nn_models::mlp::Configuration<T, TI, 2 * 4, 3, 64, rlt::nn::activation_functions::ActivationFunction::RELU, rlt::nn::activation_functions::IDENTITY>;
+        using MLP = rlt::nn_models::mlp::BindConfiguration<MLP_CONFIG>;
+        using SAMPLE_AND_SQUASH_CONFIG = rlt::nn::layers::sample_and_squash::Configuration<T, TI, rlt::nn::layers::sample_and_squash::DefaultParameters<T>>;
+        using SAMPLE_AND_SQUASH = rlt::nn::layers::sample_and_squash::BindConfiguration<SAMPLE_AND_SQUASH_CONFIG>;
+        template <typename T_CONTENT, typename T_NEXT_MODULE = rlt::nn_models::sequential::OutputModule>
+        using Module = typename rlt::nn_models::sequential::Module<T_CONTENT, T_NEXT_MODULE>;
+        using MODEL = rlt::nn_models::sequential::Build<CAP, Module<MLP, Module<SAMPLE_AND_SQUASH>>, INPUT_SHAPE>;
+    };
+    using RESULT_SPEC = rlt::rl::utils::evaluation::Specification<T, TI, ENV_RAPTOR, N_EPISODES, STEP_LIMIT>;
+    using DATA = rlt::rl::utils::evaluation::Data<rlt::rl::utils::evaluation::DataSpecification<RESULT_SPEC>>;
+}
+
+extern "C" {
+void ref_dagger_sizes(int* n_episodes, int* step_limit){ *n_episodes = ref_dagger::N_EPISODES; *step_limit = ref_dagger::STEP_LIMIT; }
+// params [10][145], states [10][500][48], terminated [10][500] (u8), teacher_blob: W1[64][26] b1 W2[64][64] b2 W3[8][64] b3, offset[3]
+// -> episode_start [5000] (i32, the reference stores the running episode number at each episode's first row), input_student [5000][22],
+//    output_target [5000][4], truncated / reset [5000] (u8); returns the number of rows added
+int ref_dagger_add_to_dataset(const float* params, const float* states, const unsigned char* terminated, const float* teacher_blob, const float* offset,
+                              int* episode_start, float* input_student, float* output_target, unsigned char* truncated_out, unsigned char* reset_out){
+    using namespace ref_dagger;
+    DEVICE device; RNG rng; rng.state = 0x1234;
+    DATA data; rlt::malloc(device, data);
+    const int SD = state_dim(1);
+    for(TI e = 0; e < N_EPISODES; e++){
+        ENV_RAPTOR::Parameters p; unflatten_parameters(params + e * PARAMS_DIM, p);
+        rlt::set(device, data.parameters, p, e);
+        for(TI t = 0; t < STEP_LIMIT; t++){
+            ENV_RAPTOR::State s; zero_state(s); unflatten_state(states + ((size_t)e * STEP_LIMIT + t) * SD, s);
+            rlt::set(device, data.states, s, e, t);
+            rlt::set(device, data.terminated, terminated[e * STEP_LIMIT + t] != 0, e, t);
+        }
+    }
+    Teacher::MODEL teacher; rlt::malloc(device, teacher);
+    {
+        auto& mlp = rlt::get_first_layer(teacher);
+        const float* b = teacher_blob;
+        auto put = [&](auto& layer, TI out, TI in){
+            for(TI o = 0; o < out; o++) for(TI i = 0; i < in; i++) rlt::set(layer.weights.parameters, o, i, *b++);
+            for(TI o = 0; o < out; o++) rlt::set(layer.biases.parameters, 0, o, *b++);
+        };
+        put(mlp.input_layer, 64, 26); put(mlp.hidden_layers[0], 64, 64); put(mlp.output_layer, 8, 64);
+    }
+    TeacherMeta<T> meta; for(int i = 0; i < 3; i++) meta.steady_state_position_offset[i] = offset[i];
+    rlt::Tensor<rlt::tensor::Specification<TI, TI, rlt::tensor::Shape<TI, DATASET_SIZE>>> ds_start;
+    rlt::Tensor<rlt::tensor::Specification<T, TI, rlt::tensor::Shape<TI, DATASET_SIZE, 22>>> ds_in;
+    rlt::Tensor<rlt::tensor::Specification<T, TI, rlt::tensor::Shape<TI, DATASET_SIZE, 4>>> ds_out;
+    rlt::Tensor<rlt::tensor::Specification<bool, TI, rlt::tensor::Shape<TI, DATASET_SIZE>>> ds_trunc, ds_reset;
+    rlt::malloc(device, ds_start); rlt::malloc(device, ds_in); rlt::malloc(device, ds_out); rlt::malloc(device, ds_trunc); rlt::malloc(device, ds_reset);
+    rlt::set_all(device, ds_start, (TI)0); rlt::set_all(device, ds_in, (T)0); rlt::set_all(device, ds_out, (T)0); rlt::set_all(device, ds_trunc, false); rlt::set_all(device, ds_reset, false);
+    TI current_episode = 0, current_index = 0;
+    TI added = add_to_dataset<ENV_RAPTOR, ENV_TEACHER::Observation, ENV_RAPTOR::Observation, true>(device, data, teacher, meta, ds_start, ds_in, ds_out, ds_trunc, ds_reset, current_episode, current_index, rng);
+    for(TI r = 0; r < DATASET_SIZE; r++){
+        episode_start[r] = (int)rlt::get(device, ds_start, r);
+        for(TI c = 0; c < 22; c++) input_student[r * 22 + c] = rlt::get(device, ds_in, r, c);
+        for(TI c = 0; c < 4; c++) output_target[r * 4 + c] = rlt::get(device, ds_out, r, c);
+        truncated_out[r] = rlt::get(device, ds_trunc, r) ? 1 : 0;
+        reset_out[r] = rlt::get(device, ds_reset, r) ? 1 : 0;
+    }
+    rlt::free(device, data); rlt::free(device, teacher); rlt::free(device, ds_start); rlt::free(device, ds_in); rlt::free(device, ds_out); rlt::free(device, ds_trunc); rlt::free(device, ds_reset);
+    return (int)added;
+}
+}

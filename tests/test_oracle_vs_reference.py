@@ -203,3 +203,33 @@ def test_collect_gae_normalizer(port, ref, spec):
         age_a = port.normalizer_update(da, n, T, mean_a, std_a, age_a)
         age_b = ref.normalizer_update(spec, db, mean_b, std_b, age_b)
     assert age_a == age_b == 2 and np.array_equal(mean_a, mean_b) and np.array_equal(std_a, std_b)
+
+
+def test_dagger_add_to_dataset(port, ref):
+    """the port's DAgger data path against the reference's own add_to_dataset (post_training/helper.h:43-110) on a recorded student rollout of
+    one teacher: 10 episodes x 500 steps, tight termination thresholds so that episodes end early and the compaction is exercised"""
+    ne, T = ref.dagger_sizes()
+    spec = B.SPEC_RAPTOR
+    rs = np.random.RandomState(23)
+    row = ref.nominal_parameters(spec).copy()
+    row[115] = 0.6          # termination.position_threshold: some of the sampled initial positions (|p| <= 0.5) drift out
+    params = np.tile(row, (ne, 1)).astype(np.float32)
+    rng = ref.rng_states(5, ne, warmup=16)
+    states = ref.sample_initial_state_n(spec, params, rng)
+    pol = port.make_policy(ref.policy_export())
+    h = np.tile(ref.policy_initial_hidden(), (ne, 1)).astype(np.float32)
+    out = port.rollout(spec, pol, params, states, rng, T, hidden=h, gru_step=np.zeros(ne, np.int32))
+    term = out["terminated"].copy()
+    term[137:, 3] = 1       # and one forced mid-episode termination
+    first = np.where(term.any(0), term.argmax(0), T)
+    assert (first < T).sum() >= 1 and (first == T).sum() >= 1, first
+    teacher = random_mlp_blob(rs, 26, 8, False, False)
+    offset = np.array([0.01, -0.02, 0.03], np.float32)
+    got = port.dagger_add_to_dataset(params, out["states"][:T], term, rng.copy(), teacher[None], offset[None], ne)
+    want = ref.dagger_add_to_dataset(params, np.ascontiguousarray(out["states"][:T].transpose(1, 0, 2)), np.ascontiguousarray(term.T), teacher, offset)
+    rows = want["rows"]
+    assert got["rows"] == rows == int(np.minimum(first + 1, T).sum())
+    for k in ("input_student", "output_target", "truncated", "reset"):
+        assert np.array_equal(got[k][:rows], want[k][:rows]), k
+    assert np.array_equal(got["episode_start"][:ne], want["episode_start"][:ne]) and want["episode_start"][1] == first[0] + 1
+    assert want["reset"][:rows].all() and want["truncated"][:rows].sum() == ne
