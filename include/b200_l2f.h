@@ -201,6 +201,34 @@ int b200l2f_estimate_generalized_advantages(b200l2f_handle* h, int32_t n_steps, 
 int b200l2f_values_and_advantages(b200l2f_handle* h, int32_t n_steps, float gamma, float lambda, int ignore_termination, float* dataset, int memspace);
 int b200l2f_normalizer_update(b200l2f_handle* h, int32_t n_steps, const float* dataset, int memspace, float* mean_io, float* std_io, int32_t* age_io);
 
+/* ---- Foundation-policy DAgger data path: gather_epoch = sample_trajectories + add_to_dataset
+ * (src/foundation_policy/post_training/helper.h:6-41,43-110,112-123; driven per teacher by post_training/main.cpp:261-309) for ALL teachers in one
+ * call.  Handle spec RAPTOR / RAPTOR_DR (the post-training environment); environment e is an episode of teacher e / episodes_per_teacher and runs
+ * with the parameters the caller installed for it (b200l2f_set_parameters: teacher_parameters[i], main.cpp:96,205-207); the student is the
+ * loaded Raptor GRU actor; initial states are whatever slot 0 holds (b200l2f_sample_initial_state).
+ * teachers_load: blobs [n_teachers][6408] = W1[64][26] b1[64] W2[64][64] b2[64] W3[8][64] b3[8] (SAC actor MLP, rl/algorithms/sac/loop/core/
+ *   approximators_mlp.h:14-37; evaluated with sample_and_squash in Evaluation mode: action = tanh(mean)); position_offsets [n_teachers][3] =
+ *   TeacherMeta::steady_state_position_offset (helper.h:1-4, main.cpp:214-235) or NULL for zeros.  Host pointers.
+ * dagger_gather: rolls the student out for n_steps (= ENVIRONMENT::EPISODE_STEP_LIMIT, 500), then for every episode up to and including its
+ *   first terminated step appends: input_student [rows][22] (student observation, position minus the teacher's offset), output_target [rows][4]
+ *   (the teacher's action for the teacher observation of the same state), truncated / reset [rows], episode_start [n_envs] (first row of each
+ *   episode).  Rows are ordered by environment, then step.  *rows_added = rows (<= capacity_rows, else B200L2F_ERR_ARGUMENT "Dataset size
+ *   exceeded").  returns / episode_length [n_envs] (optional) are the Result of sample_trajectories.  Observation noise must be off. */
+typedef struct {
+    int32_t memspace;        /* B200L2F_HOST / B200L2F_DEVICE for all pointers below */
+    int32_t reserved;
+    int64_t capacity_rows;   /* rows the row-indexed buffers can hold; n_envs * n_steps always suffices */
+    float*   input_student;
+    float*   output_target;
+    uint8_t* truncated;
+    uint8_t* reset;
+    int32_t* episode_start;
+    float*   returns;        /* may be NULL */
+    int32_t* episode_length; /* may be NULL */
+} b200l2f_dagger_out;
+int b200l2f_teachers_load(b200l2f_handle* h, int32_t n_teachers, int32_t episodes_per_teacher, const float* blobs, const float* position_offsets, int32_t gemm);
+int b200l2f_dagger_gather(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, const b200l2f_dagger_out* out, int64_t* rows_added);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,11 @@ class RolloutOut(ctypes.Structure):
                 ("terminated", vp), ("returns", vp), ("episode_length", vp)]
 
 
+class DaggerOut(ctypes.Structure):
+    _fields_ = [("memspace", c_i32), ("reserved", c_i32), ("capacity_rows", c_i64), ("input_student", vp), ("output_target", vp), ("truncated", vp),
+                ("reset", vp), ("episode_start", vp), ("returns", vp), ("episode_length", vp)]
+
+
 # every symbol include/b200_l2f.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "b200l2f_create": (c_int, [ctypes.POINTER(Config), ctypes.POINTER(vp)]),
@@ -77,6 +82,8 @@ SYMBOLS = {
     "b200l2f_estimate_generalized_advantages": (c_int, [vp, c_i32, c_f, c_f, c_int, vp, c_int]),
     "b200l2f_values_and_advantages": (c_int, [vp, c_i32, c_f, c_f, c_int, vp, c_int]),
     "b200l2f_normalizer_update": (c_int, [vp, c_i32, vp, c_int, vp, vp, vp]),
+    "b200l2f_teachers_load": (c_int, [vp, c_i32, c_i32, vp, vp, c_i32]),
+    "b200l2f_dagger_gather": (c_int, [vp, c_i32, c_i32, ctypes.POINTER(DaggerOut), ctypes.POINTER(c_i64)]),
 }
 
 _lib = None

@@ -30,6 +30,7 @@ SOURCES = {
     "collect.cu": [],
     "collect_ts.cu": TC + ["mlp_tc.cuh"],
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
+    "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
 }
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -173,6 +173,8 @@ int b200l2f_destroy(b200l2f_handle* h){
     cudaFree(h->d_rng); cudaFree(h->d_flags); cudaFree(h->d_blob); cudaFree(h->d_hidden); cudaFree(h->d_gru_step);
     cudaFree(h->d_episode_step); cudaFree(h->d_episode_return); cudaFree(h->d_truncated);
     cudaFree(h->d_critic_blob); cudaFree(h->d_critic_tc_image); cudaFree(h->d_colstats);
+    cudaFree(h->d_teacher_images); cudaFree(h->d_teacher_blobs); cudaFree(h->d_teacher_offsets);
+    cudaFree(h->d_dg_states); cudaFree(h->d_dg_term); cudaFree(h->d_dg_eplen); cudaFree(h->d_dg_offsets); cudaFree(h->d_dg_returns);
     if(h->d_stage) cudaFree(h->d_stage);
     if(h->h_pinned) cudaFreeHost(h->h_pinned);
     if(h->own_stream && h->stream) cudaStreamDestroy(h->stream);

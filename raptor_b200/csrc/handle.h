@@ -46,6 +46,11 @@ struct b200l2f_handle {
     bool critic_loaded = false; int critic_std = 0, critic_gemm = 0;
     float* d_critic_blob = nullptr; float* d_critic_tc_image = nullptr;
     double* d_colstats = nullptr; size_t colstats_doubles = 0;
+    // DAgger data path (dagger.cu): teacher weights (tensor-core images + blobs), steady-state offsets, recorded student rollout
+    float* d_teacher_images = nullptr; float* d_teacher_blobs = nullptr; float* d_teacher_offsets = nullptr;
+    int n_teachers = 0, episodes_per_teacher = 0, teacher_gemm = 0;
+    float* d_dg_states = nullptr; uint8_t* d_dg_term = nullptr; size_t dg_state_floats = 0;
+    int* d_dg_eplen = nullptr; int* d_dg_offsets = nullptr; float* d_dg_returns = nullptr;
     std::vector<float> h_image;      // k-major actor image passed by value to the fused kernels (constant-bank weights)
     bool weights_in_constant_bank = false; bool rolled = false;
     // PPO runner bookkeeping (rl/components/on_policy_runner/on_policy_runner.h: episode_step, episode_return, truncated)

@@ -206,6 +206,7 @@ __device__ __forceinline__ TsCtx mlp_ts_prologue_at(unsigned char* smraw, int b_
     TsCtx c;
     c.sm_b = sm_b; c.b_s = tc::smem_u32(sm_b); c.tmem_base = *tmem_slot; c.tmem_lane = c.tmem_base + ((uint32_t)(warp * 32) << 16);
     c.bar_mma = bar_mma; c.phase = 0; c.tid = tid;
+    if(tc_image == nullptr) return c;          // the caller loads (and reloads) the image itself (dagger.cuh: one image per teacher)
     if(tid == 0){
         tc::mbar_expect_tx(bar_tma, MlpTcImage<IN, OUT>::BYTES);
         tc::tma_load_1d(sm_b, tc_image, MlpTcImage<IN, OUT>::BYTES, bar_tma);

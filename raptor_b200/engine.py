@@ -276,6 +276,41 @@ class VectorEnvironment:
         self._check(self._lib.b200l2f_normalizer_update(self._h, n_steps, p, ms, pm, ps, ctypes.byref(a)))
         return int(a.value)
 
+    # ---- foundation-policy DAgger data path (src/foundation_policy/post_training/helper.h: gather_epoch = sample_trajectories + add_to_dataset)
+    def load_teachers(self, blobs, position_offsets=None, episodes_per_teacher=10, gemm=L.GEMM_TCGEN05_3XTF32):
+        """blobs [n_teachers, 6408] (SAC actor MLP 26-64-64-8), position_offsets [n_teachers, 3] or None; environment e is an episode of teacher
+        e // episodes_per_teacher"""
+        blobs = np.ascontiguousarray(blobs, np.float32)
+        n_teachers = blobs.shape[0]
+        off = None if position_offsets is None else np.ascontiguousarray(position_offsets, np.float32)
+        if blobs.ndim != 2 or blobs.shape[1] != 6408 or (off is not None and off.shape != (n_teachers, 3)):
+            raise ValueError("load_teachers: blobs [n_teachers, 6408], position_offsets [n_teachers, 3]")
+        self._check(self._lib.b200l2f_teachers_load(self._h, n_teachers, episodes_per_teacher, blobs.ctypes.data, None if off is None else off.ctypes.data, gemm))
+
+    def dagger_gather(self, n_steps, out=None, no_auto_reset=False):
+        """student rollout + dataset rows of all teachers; returns dict(rows, input_student, output_target, truncated, reset, episode_start,
+        returns, episode_length).  out: dict of preallocated buffers (numpy, or torch CUDA tensors for a device-resident dataset)"""
+        n, cap = self.N_ENVIRONMENTS, self.N_ENVIRONMENTS * n_steps
+        if out is None:
+            out = dict(input_student=np.zeros((cap, 22), np.float32), output_target=np.zeros((cap, 4), np.float32), truncated=np.zeros(cap, np.uint8),
+                       reset=np.zeros(cap, np.uint8), episode_start=np.zeros(n, np.int32), returns=np.zeros(n, np.float32), episode_length=np.zeros(n, np.int32))
+        dt = dict(input_student=np.float32, output_target=np.float32, truncated=np.uint8, reset=np.uint8, episode_start=np.int32, returns=np.float32, episode_length=np.int32)
+        ptr, spaces = {}, set()
+        for k, d in dt.items():
+            p, ms, _ = _arg(out.get(k), d, None, k)
+            ptr[k] = p
+            if out.get(k) is not None:
+                spaces.add(ms)
+        if len(spaces) != 1:
+            raise ValueError("dagger_gather: all buffers must live in the same memory space")
+        o = L.DaggerOut(spaces.pop(), 0, int(out["input_student"].shape[0]), ptr["input_student"], ptr["output_target"], ptr["truncated"], ptr["reset"],
+                        ptr["episode_start"], ptr["returns"], ptr["episode_length"])
+        rows = ctypes.c_int64(0)
+        self._check(self._lib.b200l2f_dagger_gather(self._h, n_steps, int(no_auto_reset), ctypes.byref(o), ctypes.byref(rows)))
+        out = dict(out)
+        out["rows"] = int(rows.value)
+        return out
+
     def get_hidden(self):
         h = np.zeros((self.N_ENVIRONMENTS, self.policy.hidden_dim), np.float32)
         g = np.zeros(self.N_ENVIRONMENTS, np.int32)

@@ -521,6 +521,59 @@ def test_learner_feed_vs_oracle(rb, port, spec, n, gemm):
     close(std_g, std_w, 1e-5, 1e-6, "normalizer std")
 
 
+@pytest.mark.parametrize("gemm", ["tcgen05", "fp32"])
+def test_dagger_gather_vs_oracle(rb, port, gemm):
+    """gather_epoch for all teachers in one call (student rollout -> compaction -> teacher / student observations -> teacher labels) against the
+    oracle's add_to_dataset, which is pinned bit-for-bit to the reference's own (tests/test_oracle_vs_reference.py::test_dagger_add_to_dataset).
+    37 teachers x 8 episodes = 296 environments (a ragged last CTA in the rollout), 90 steps, tight position threshold so that episodes end early."""
+    import torch
+    n_teachers, E, T = 37, 8, 90
+    n = n_teachers * E
+    spec = rb.SPEC_RAPTOR_DR
+    rs = np.random.RandomState(41)
+    env = rb.VectorEnvironment(n, spec)
+    env_p = foundation_dr_env_params(port, spec)
+    env.set_environment_parameters(env_p)
+    env.initialize_rng(13, warmup=16)
+    env.sample_initial_parameters()
+    params = env.get_parameters()
+    params = np.repeat(params[::E], E, axis=0)                 # the episodes of a teacher share the teacher's dynamics
+    params[:, 115] = 0.45 * params[:, 115]                      # termination.position_threshold
+    env.set_parameters(np.ascontiguousarray(params))
+    env.sample_initial_state()
+    env.load_policy()
+    teachers = np.stack([random_mlp_blob(rs, 26, 8, False, False) for _ in range(n_teachers)])
+    offsets = rs.uniform(-0.05, 0.05, (n_teachers, 3)).astype(np.float32)
+    env.load_teachers(teachers, offsets, episodes_per_teacher=E, gemm=rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32)
+    states0, rng0 = env.get_state(), env.get_rng()
+    h0, g0 = env.get_hidden()
+    rec = env.rollout(T, record=("states", "terminated", "returns", "episode_length"))     # what gather records internally (deterministic)
+    env.set_state(states0); env.set_rng(rng0); env.set_hidden(h0, g0)
+    got = env.dagger_gather(T)
+    rows = got["rows"]
+    assert np.array_equal(got["episode_length"], rec["episode_length"]) and np.array_equal(got["returns"], rec["returns"])
+    assert rows == int(rec["episode_length"].sum()) and 0.2 * n * T < rows < n * T, rows
+    want = port.dagger_add_to_dataset(params, rec["states"][:T], rec["terminated"], rng0.copy(), teachers, offsets, E)
+    assert want["rows"] == rows
+    for k in ("truncated", "reset"):
+        assert np.array_equal(got[k][:rows], want[k][:rows]), k
+    assert np.array_equal(got["episode_start"], want["episode_start"][:n])
+    assert got["truncated"][:rows].sum() == n and (got["truncated"][rows:] == 0).all()
+    close(got["input_student"][:rows], want["input_student"][:rows], 1e-5, 1e-6, "student observations")
+    close(got["output_target"][:rows], want["output_target"][:rows], 2e-4, 2e-4, "teacher action targets")
+    assert np.abs(want["output_target"][:rows]).mean() > 0.05
+    # device-resident dataset, same bits
+    env.set_state(states0); env.set_rng(rng0); env.set_hidden(h0, g0)
+    cap = n * T
+    dev = dict(input_student=torch.zeros((cap, 22), device="cuda"), output_target=torch.zeros((cap, 4), device="cuda"), truncated=torch.zeros(cap, dtype=torch.uint8, device="cuda"),
+               reset=torch.zeros(cap, dtype=torch.uint8, device="cuda"), episode_start=torch.zeros(n, dtype=torch.int32, device="cuda"))
+    got_d = env.dagger_gather(T, out=dev)
+    env.synchronize()
+    assert got_d["rows"] == rows
+    for k in ("input_student", "output_target", "truncated", "reset", "episode_start"):
+        assert np.array_equal(got_d[k].cpu().numpy()[:rows if k != "episode_start" else n], got[k][:rows if k != "episode_start" else n]), k
+
+
 def test_time_chunked_scheduler_is_transparent(rb):
     """the persistent (tile, time-chunk) work queue of the tensor-core kernel must not change results: 1 chunk vs 7 chunks, bit for bit;
     3000 envs = 24 tiles incl. a ragged one, 333 steps (chunks of unequal length), DEFAULT spec keeps its action ring in HBM across chunks"""
