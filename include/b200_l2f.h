@@ -229,6 +229,17 @@ typedef struct {
 int b200l2f_teachers_load(b200l2f_handle* h, int32_t n_teachers, int32_t episodes_per_teacher, const float* blobs, const float* position_offsets, int32_t gemm);
 int b200l2f_dagger_gather(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, const b200l2f_dagger_out* out, int64_t* rows_added);
 
+/* ---- parameter / state JSON wire format: rl_tools::json / from_json (L2F/operations_cpu.h:139-411 parameters, :412-560 state, :565-824 import).
+ * Host functions on the flat rows above; to_json writes the reference's exact text (key order, separators, std::to_string formatting), *length
+ * receives the size without the terminator (call with buf = NULL to query it); from_json reads every key the reference reads (a missing or
+ * mistyped key is an error naming its path, like nlohmann's exception), narrows doubles to float, ignores unknown keys and leaves the row
+ * untouched on error.  The dynamics_parameters / <id>.json files of the foundation-policy data set (sample_dynamics_parameters.cpp:84-111,
+ * loaded by post_training/main.cpp:202-207) are parameters_from_json inputs.  parameters_* accept h = NULL (no handle state is used). */
+int b200l2f_parameters_to_json(b200l2f_handle* h, const float* row145, char* buf, size_t capacity, size_t* length);
+int b200l2f_parameters_from_json(b200l2f_handle* h, const char* json, float* row145_io);
+int b200l2f_state_to_json(b200l2f_handle* h, const float* state_row, char* buf, size_t capacity, size_t* length);
+int b200l2f_state_from_json(b200l2f_handle* h, const char* json, float* state_row_io);
+
 #ifdef __cplusplus
 }
 #endif

@@ -354,6 +354,36 @@ class Ref(_Common):
         self.lib.ref_normalizer_update(spec, data, mean, std, ctypes.byref(a))
         return int(a.value)
 
+    # ---- JSON wire format (the reference's own json / from_json; needs the nlohmann header at build time)
+    def json_available(self):
+        return hasattr(self.lib, "ref_json_available") and bool(self.lib.ref_json_available())
+
+    def parameters_to_json(self, spec, row):
+        row = np.ascontiguousarray(row, np.float32)
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.ref_parameters_to_json(spec, row.ctypes.data_as(ctypes.POINTER(c_float)), buf, 1 << 16)
+        assert n > 0
+        return buf.value.decode()
+
+    def parameters_from_json(self, spec, text, row):
+        out = np.array(row, np.float32, copy=True)
+        self.lib.ref_parameters_from_json(spec, text.encode(), out.ctypes.data_as(ctypes.POINTER(c_float)))
+        return out
+
+    def state_to_json(self, spec, prow, srow):
+        prow, srow = np.ascontiguousarray(prow, np.float32), np.ascontiguousarray(srow, np.float32)
+        buf = ctypes.create_string_buffer(1 << 16)
+        fp = ctypes.POINTER(c_float)
+        n = self.lib.ref_state_to_json(spec, prow.ctypes.data_as(fp), srow.ctypes.data_as(fp), buf, 1 << 16)
+        assert n > 0
+        return buf.value.decode()
+
+    def state_from_json(self, spec, prow, text, srow):
+        out = np.array(srow, np.float32, copy=True)
+        fp = ctypes.POINTER(c_float)
+        self.lib.ref_state_from_json(spec, np.ascontiguousarray(prow, np.float32).ctypes.data_as(fp), text.encode(), out.ctypes.data_as(fp))
+        return out
+
     def dagger_sizes(self):
         a, b = c_int(), c_int()
         self.lib.ref_dagger_sizes(ctypes.byref(a), ctypes.byref(b))

@@ -875,3 +875,53 @@ int ref_dagger_add_to_dataset(const float* params, const float* states, const un
     return (int)added;
 }
 }
+
+// ================================================================================================
+// Parameter / state JSON wire format: the reference's own json(...) / from_json(...) (rl/environments/l2f/operations_cpu.h:139-411, 412-560,
+// 565-824; nlohmann::json comes from the image's cudnn_frontend/thirdparty tree, oracle/Makefile)
+// ================================================================================================
+#ifdef RL_TOOLS_ENABLE_JSON
+template <typename ENV>
+static int params_to_json(const float* row, char* buf, int cap){
+    DEVICE device; ENV env; rlt::init(device, env);
+    typename ENV::Parameters p; unflatten_parameters(row, p);
+    std::string s = rlt::json(device, env, p);
+    if((int)s.size() + 1 > cap) return -(int)s.size() - 1;
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+template <typename ENV>
+static void params_from_json(const char* json, float* row_io){
+    DEVICE device; ENV env; rlt::init(device, env);
+    typename ENV::Parameters p; unflatten_parameters(row_io, p);
+    rlt::from_json(device, env, std::string(json), p);
+    flatten_parameters(p, row_io);
+}
+template <typename ENV>
+static int state_to_json(const float* prow, const float* srow, char* buf, int cap){
+    DEVICE device; ENV env; rlt::init(device, env);
+    typename ENV::Parameters p; unflatten_parameters(prow, p);
+    typename ENV::State s; zero_state(s); unflatten_state(srow, s);
+    std::string js = rlt::json(device, env, p, s);
+    if((int)js.size() + 1 > cap) return -(int)js.size() - 1;
+    std::memcpy(buf, js.c_str(), js.size() + 1);
+    return (int)js.size();
+}
+template <typename ENV>
+static void state_from_json(const float* prow, const char* json, float* srow_io){
+    DEVICE device; ENV env; rlt::init(device, env);
+    typename ENV::Parameters p; unflatten_parameters(prow, p);
+    typename ENV::State s; zero_state(s); unflatten_state(srow_io, s);
+    rlt::from_json(device, env, p, std::string(json), s);
+    flatten_state(s, srow_io);
+}
+extern "C" {
+int ref_json_available(){ return 1; }
+int ref_parameters_to_json(int spec, const float* row, char* buf, int cap){ int r = 0; DISPATCH(spec, r = params_to_json<E>(row, buf, cap)); return r; }
+void ref_parameters_from_json(int spec, const char* json, float* row_io){ DISPATCH(spec, params_from_json<E>(json, row_io)); }
+int ref_state_to_json(int spec, const float* prow, const float* srow, char* buf, int cap){ int r = 0; DISPATCH(spec, r = state_to_json<E>(prow, srow, buf, cap)); return r; }
+void ref_state_from_json(int spec, const float* prow, const char* json, float* srow_io){ DISPATCH(spec, state_from_json<E>(prow, json, srow_io)); }
+}
+#else
+extern "C" { int ref_json_available(){ return 0; } }
+#endif

@@ -82,6 +82,10 @@ SYMBOLS = {
     "b200l2f_estimate_generalized_advantages": (c_int, [vp, c_i32, c_f, c_f, c_int, vp, c_int]),
     "b200l2f_values_and_advantages": (c_int, [vp, c_i32, c_f, c_f, c_int, vp, c_int]),
     "b200l2f_normalizer_update": (c_int, [vp, c_i32, vp, c_int, vp, vp, vp]),
+    "b200l2f_parameters_to_json": (c_int, [vp, vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "b200l2f_parameters_from_json": (c_int, [vp, ctypes.c_char_p, vp]),
+    "b200l2f_state_to_json": (c_int, [vp, vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "b200l2f_state_from_json": (c_int, [vp, ctypes.c_char_p, vp]),
     "b200l2f_teachers_load": (c_int, [vp, c_i32, c_i32, vp, vp, c_i32]),
     "b200l2f_dagger_gather": (c_int, [vp, c_i32, c_i32, ctypes.POINTER(DaggerOut), ctypes.POINTER(c_i64)]),
 }

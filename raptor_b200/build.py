@@ -31,6 +31,7 @@ SOURCES = {
     "collect_ts.cu": TC + ["mlp_tc.cuh"],
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
+    "json_io.cu": [],
 }
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

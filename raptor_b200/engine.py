@@ -26,6 +26,32 @@ def raptor_policy_blob():
     return np.fromfile(os.path.join(HERE, "data", "raptor_policy_2084.f32"), dtype=np.float32)
 
 
+def parameters_to_json(row):
+    """rl_tools::json(device, env, parameters) (rl/environments/l2f/operations_cpu.h:139-411) of one flat parameter row [145]; no GPU needed"""
+    lib = L.load()
+    row = np.ascontiguousarray(row, np.float32)
+    if row.shape != (L.PARAMS_DIM,):
+        raise ValueError("parameters_to_json: expected a row of %d floats" % L.PARAMS_DIM)
+    n = ctypes.c_size_t(0)
+    lib.b200l2f_parameters_to_json(None, row.ctypes.data, None, 0, ctypes.byref(n))
+    buf = ctypes.create_string_buffer(n.value + 1)
+    rc = lib.b200l2f_parameters_to_json(None, row.ctypes.data, buf, n.value + 1, ctypes.byref(n))
+    if rc != 0:
+        raise EngineError("b200l2f_parameters_to_json failed (%d): %s" % (rc, lib.b200l2f_last_error(None).decode()))
+    return buf.value.decode()
+
+
+def parameters_from_json(text, row=None):
+    """rl_tools::from_json (operations_cpu.h:565-728): returns the flat row [145]; `row` supplies the values of keys the format does not carry
+    (none today) and is not modified; no GPU needed"""
+    lib = L.load()
+    out = np.zeros(L.PARAMS_DIM, np.float32) if row is None else np.array(row, np.float32, copy=True)
+    rc = lib.b200l2f_parameters_from_json(None, text.encode(), out.ctypes.data)
+    if rc != 0:
+        raise EngineError("b200l2f_parameters_from_json failed (%d): %s" % (rc, lib.b200l2f_last_error(None).decode()))
+    return out
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
@@ -275,6 +301,20 @@ class VectorEnvironment:
         a = ctypes.c_int32(age)
         self._check(self._lib.b200l2f_normalizer_update(self._h, n_steps, p, ms, pm, ps, ctypes.byref(a)))
         return int(a.value)
+
+    # ---- JSON wire format of the reference (rl/environments/l2f/operations_cpu.h)
+    def state_to_json(self, state_row):
+        row = np.ascontiguousarray(state_row, np.float32)
+        n = ctypes.c_size_t(0)
+        self._lib.b200l2f_state_to_json(self._h, row.ctypes.data, None, 0, ctypes.byref(n))
+        buf = ctypes.create_string_buffer(n.value + 1)
+        self._check(self._lib.b200l2f_state_to_json(self._h, row.ctypes.data, buf, n.value + 1, ctypes.byref(n)))
+        return buf.value.decode()
+
+    def state_from_json(self, text, state_row=None):
+        out = np.zeros(self.STATE_DIM, np.float32) if state_row is None else np.array(state_row, np.float32, copy=True)
+        self._check(self._lib.b200l2f_state_from_json(self._h, text.encode(), out.ctypes.data))
+        return out
 
     # ---- foundation-policy DAgger data path (src/foundation_policy/post_training/helper.h: gather_epoch = sample_trajectories + add_to_dataset)
     def load_teachers(self, blobs, position_offsets=None, episodes_per_teacher=10, gemm=L.GEMM_TCGEN05_3XTF32):

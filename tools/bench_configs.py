@@ -86,6 +86,30 @@ def main():
                 "values_only_ms": ms_v, "gae_only_ms": ms_g, "gae_hbm_gbs_algorithmic": rows * 6 * 4 / ms_g / 1e6,
                 "normalizer_update_ms": ms_n, "normalizer_hbm_gbs": 2 * T * n * row_bytes / ms_n / 1e6,
                 "collect_plus_feed_env_steps_per_s": n * T / (ms + ms_f) * 1e3})
+    del env, data
+    # ---- foundation-policy DAgger epoch: gather_epoch for NUM_TEACHERS = 1000 x NUM_EPISODES = 10 x EPISODE_STEP_LIMIT = 500 (post_training/config.h)
+    nt, E, T = 1000, 10, 500
+    n = nt * E
+    env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR, stream=stream.cuda_stream)
+    row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32); env.set_environment_parameters(row)
+    env.initialize_rng(5, warmup=16); env.sample_initial_parameters()
+    p = env.get_parameters(); env.set_parameters(np.ascontiguousarray(np.repeat(p[::E], E, axis=0)))
+    env.sample_initial_state(); env.load_policy(gemm=gemm)
+    env.load_teachers(np.stack([mlp_blob(rs, 26, 8, False, False) for _ in range(nt)]), None, episodes_per_teacher=E, gemm=gemm)
+    s0 = torch.from_numpy(env.get_state()).to(dev)
+    cap = n * T
+    ds = dict(input_student=torch.zeros((cap, 22), device=dev), output_target=torch.zeros((cap, 4), device=dev), truncated=torch.zeros(cap, dtype=torch.uint8, device=dev),
+              reset=torch.zeros(cap, dtype=torch.uint8, device=dev), episode_start=torch.zeros(n, dtype=torch.int32, device=dev))
+    res = {}
+    def gather():
+        res["rows"] = env.dagger_gather(T, out=ds)["rows"]
+    def reset():
+        env.set_state(s0); env.policy_reset()
+    ms_d = timed(gather, reset, stream=stream, flush=flush)
+    ms_r = timed(lambda: env.rollout(T), reset, stream=stream, flush=flush)
+    out.append({"config": "DAgger epoch data path: gather_epoch for 1000 teachers x 10 episodes x 500 steps (student rollout + add_to_dataset, device-resident dataset)",
+                "ms_per_epoch": ms_d, "env_steps_per_s": n * T / ms_d * 1e3, "dataset_rows": res["rows"], "rows_per_s": res["rows"] / ms_d * 1e3,
+                "student_rollout_only_ms": ms_r})
     for o in out:
         o["gemm"] = gemm_name
         print(json.dumps(o))
