@@ -77,6 +77,10 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
     for(int j = 0; j < HD; j++){ img[TcImage::BIAS2 + 32 + j] = s_n * bih[2 * HD + j]; img[TcImage::BIAS2 + 48 + j] = s_n * bhh[2 * HD + j]; }
 }
 
+#ifndef B200L2F_PACKED_FP32
+#define B200L2F_PACKED_FP32 1      // packed fp32 (FFMA2 / FADD2 / FMUL2, sm_100) in the default-math kernels; 0 = scalar twins (tuning / bisecting)
+#endif
+
 // ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
 enum DynC : int { C_COEF = 0, C_AF = 12, C_AT = 24, C_ITAU_RISE = 36, C_ITAU_FALL = 40, C_GRAVITY = 44, C_J = 47, C_JINV = 56, C_ACT_MIN = 65, C_ACT_MAX = 66, C_TERM_POS = 67, C_DIM = 68 };
 // NC: the parameter columns are read-only for the whole launch (ld.global.nc); false when the kernel itself rewrites them (collect's resets)
@@ -227,6 +231,31 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
         }
 #pragma unroll
         for(int i = 0; i < X_DIM; i++) st.x[i] = acc[i];
+    }
+    else if constexpr(FAST && B200L2F_PACKED_FP32){
+    // state algebra (50_state_algebra.h axpys) on the packed fp32 pipe: one FFMA2 (fma.rn.f32x2) advances two state components, so the 119
+    // FMAs of the four stages issue as 63 instructions.  Same products and sums as the scalar form (an FMA per component), same bits.
+    constexpr int X2 = (X_DIM + 1) / 2;
+    float2 x2[X2], k2[X2], t2[X2], a2[X2];
+#pragma unroll
+    for(int i = 0; i < X2; i++) x2[i] = make_float2(st.x[2 * i], 2 * i + 1 < X_DIM ? st.x[2 * i + 1] : 0.0f);
+    k2[X2 - 1].y = 0.0f;
+    float* kf = reinterpret_cast<float*>(k2); float* tf = reinterpret_cast<float*>(t2);
+    const float2 c6 = make_float2(dt6, dt6), c3 = make_float2(dt3, dt3), c2 = make_float2(dt2, dt2), c1 = make_float2(dt, dt);
+    dynamics_compiled<AXIAL>(p, d, st.x, setpoint, kf);
+#pragma unroll
+    for(int i = 0; i < X2; i++){ a2[i] = __ffma2_rn(c6, k2[i], x2[i]); t2[i] = __ffma2_rn(c2, k2[i], x2[i]); }
+    dynamics_compiled<AXIAL>(p, d, tf, setpoint, kf);
+#pragma unroll
+    for(int i = 0; i < X2; i++){ a2[i] = __ffma2_rn(c3, k2[i], a2[i]); t2[i] = __ffma2_rn(c2, k2[i], x2[i]); }
+    dynamics_compiled<AXIAL>(p, d, tf, setpoint, kf);
+#pragma unroll
+    for(int i = 0; i < X2; i++){ a2[i] = __ffma2_rn(c3, k2[i], a2[i]); t2[i] = __ffma2_rn(c1, k2[i], x2[i]); }
+    dynamics_compiled<AXIAL>(p, d, tf, setpoint, kf);
+#pragma unroll
+    for(int i = 0; i < X2; i++) a2[i] = __ffma2_rn(c6, k2[i], a2[i]);
+#pragma unroll
+    for(int i = 0; i < X_DIM; i++) st.x[i] = (i & 1) ? a2[i >> 1].y : a2[i >> 1].x;
     }
     else{
     dynamics_compiled<AXIAL>(p, d, st.x, setpoint, k);
