@@ -240,6 +240,27 @@ int b200l2f_parameters_from_json(b200l2f_handle* h, const char* json, float* row
 int b200l2f_state_to_json(b200l2f_handle* h, const float* state_row, char* buf, size_t capacity, size_t* length);
 int b200l2f_state_from_json(b200l2f_handle* h, const char* json, float* state_row_io);
 
+/* ---- rl-tools checkpoint code export (`checkpoint.h`): what rl::loop::steps::checkpoint::save_code writes
+ * (INC/rl/loop/steps/checkpoint/operations_cpu.h:56-118; body by rl_tools::save_code of the actor, containers/{matrix,tensor}/persist_code.h)
+ * and what the reference consumes by compiling it in (src/foundation_policy/post_training/load_actor.cpp, INC/inference/applications/l2f/c_backend.h).
+ * Host functions, no handle, no GPU; errors through b200l2f_last_error(NULL).
+ * parse:   reads the header text: every `memory[]` byte list becomes a float tensor named by its namespace path
+ *          ("rl_tools::checkpoint::actor::layer_1::weights_input", "rl_tools::checkpoint::example::input", ...), row padding removed.
+ * tensor:  i-th tensor in file order: path, rank, dims, data (owned by the checkpoint object).
+ * string:  `char name[] = "..."` values, e.g. "rl_tools::checkpoint::meta::name" / "::commit_hash"; NULL if absent.
+ * policy:  recognises the actor under `root` (NULL = "rl_tools::checkpoint::actor") and assembles desc + blob for b200l2f_policy_load /
+ *          b200l2f_critic_load / b200l2f_teachers_load in the blob orders documented above: Dense(ReLU)-GRU-Dense (Raptor) or
+ *          [Standardize] MLP(3 layers, ReLU) [SampleAndSquash | log_std]; anything else -> B200L2F_ERR_UNSUPPORTED.  blob may be NULL to query
+ *          *n_floats.  desc->gemm is preset to TCGEN05_3XTF32, desc->gru_sequence_length to the export's SEQUENCE_LENGTH (500 for Raptor).
+ * The HDF5 twin (checkpoint.h5) is not read: no libhdf5 in this stack. */
+typedef struct b200l2f_checkpoint b200l2f_checkpoint;
+int b200l2f_checkpoint_parse(const char* text, size_t length, b200l2f_checkpoint** out);
+int b200l2f_checkpoint_free(b200l2f_checkpoint* c);
+int b200l2f_checkpoint_tensor_count(const b200l2f_checkpoint* c);
+int b200l2f_checkpoint_tensor(const b200l2f_checkpoint* c, int index, const char** path, int32_t* rank, const int64_t** dims, const float** data);
+const char* b200l2f_checkpoint_string(const b200l2f_checkpoint* c, const char* path);
+int b200l2f_checkpoint_policy(const b200l2f_checkpoint* c, const char* root, b200l2f_policy_desc* desc, float* blob, size_t capacity, size_t* n_floats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -354,6 +354,16 @@ class Ref(_Common):
         self.lib.ref_normalizer_update(spec, data, mean, std, ctypes.byref(a))
         return int(a.value)
 
+    # ---- checkpoint code export: the reference's own save_code (kind 1 = SAC teacher MLP + sample_and_squash, 2 = PPO standardize + MLP + log_std)
+    def save_code(self, kind, blob, has_std=0, name="fixture"):
+        blob = np.ascontiguousarray(blob, np.float32)
+        cap = 1 << 22
+        buf = ctypes.create_string_buffer(cap)
+        n = self.lib.ref_save_code(kind, blob.ctypes.data_as(ctypes.POINTER(c_float)), has_std, name.encode(), buf, cap)
+        if n <= 0:
+            raise RuntimeError("ref_save_code failed (%d)" % n)
+        return buf.raw[:n].decode()
+
     # ---- JSON wire format (the reference's own json / from_json; needs the nlohmann header at build time)
     def json_available(self):
         return hasattr(self.lib, "ref_json_available") and bool(self.lib.ref_json_available())

@@ -925,3 +925,80 @@ void ref_state_from_json(int spec, const float* prow, const char* json, float* s
 #else
 extern "C" { int ref_json_available(){ return 0; } }
 #endif
+
+// ================================================================================================
+// Checkpoint code export: the reference's own rl_tools::save_code (containers/{matrix,tensor}/persist_code.h, nn/layers/*/persist_code.h,
+// nn_models/{mlp,mlp_unconditional_stddev,sequential}/persist_code.h) on the three actor shapes of the path, assembled the way
+// rl::loop::steps::checkpoint::save_code does (rl/loop/steps/checkpoint/operations_cpu.h:56-84: actor, example input / output, meta).
+// Produces the fixtures of tests/golden/checkpoints/ and pins the engine's reader (raptor_b200/csrc/checkpoint_io.cu).
+// ================================================================================================
+#include <rl_tools/containers/matrix/persist_code.h>
+#include <rl_tools/containers/tensor/persist_code.h>
+#include <rl_tools/nn/parameters/persist_code.h>
+#include <rl_tools/nn/layers/dense/persist_code.h>
+#include <rl_tools/nn/layers/gru/persist_code.h>
+#include <rl_tools/nn/layers/standardize/persist_code.h>
+#include <rl_tools/nn/layers/sample_and_squash/persist_code.h>
+#include <rl_tools/nn_models/mlp/persist_code.h>
+#include <rl_tools/nn_models/mlp_unconditional_stddev/persist_code.h>
+#include <rl_tools/nn_models/sequential/persist_code.h>
+
+namespace ref_export{
+    template <typename MODEL>
+    static std::string with_example(DEVICE& device, MODEL& model, const char* name, uint64_t seed){
+        RNG rng; rng.state = seed;
+        std::stringstream ss;
+        ss << rlt::save_code(device, model, std::string("rl_tools::checkpoint::actor"), true);
+        rlt::Tensor<rlt::tensor::Specification<T, TI, typename MODEL::INPUT_SHAPE>> input;
+        rlt::Tensor<rlt::tensor::Specification<T, TI, typename MODEL::OUTPUT_SHAPE>> output;
+        typename MODEL::template Buffer<> buffer;
+        rlt::malloc(device, input); rlt::malloc(device, output); rlt::malloc(device, buffer);
+        rlt::randn(device, input, rng);
+        rlt::Mode<rlt::mode::Evaluation<>> mode;
+        rlt::evaluate(device, model, input, output, buffer, rng, mode);
+        ss << "\n" << rlt::save_code(device, input, std::string("rl_tools::checkpoint::example::input"), true);
+        ss << "\n" << rlt::save_code(device, output, std::string("rl_tools::checkpoint::example::output"), true);
+        ss << "\n" << "namespace rl_tools::checkpoint::meta{";
+        ss << "\n" << "   " << "char name[] = \"" << name << "\";";
+        ss << "\n" << "   " << "char commit_hash[] = \"" << "fixture" << "\";";
+        ss << "\n" << "}";
+        rlt::free(device, input); rlt::free(device, output); rlt::free(device, buffer);
+        return ss.str();
+    }
+    static int emit(const std::string& s, char* buf, int cap){
+        if((int)s.size() + 1 > cap) return -(int)s.size() - 1;
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+        return (int)s.size();
+    }
+}
+extern "C" {
+// (the Dense-GRU-Dense export is the Raptor checkpoint file itself: its tensors are `const`, which save_code cannot take)
+// kind 1: SAC teacher MLP 26-64-64-8 + sample_and_squash from `blob` (6408 floats);
+// kind 2: PPO actor standardize -> mlp_unconditional_stddev 22-64-64-4 from `blob` ([mean precision] W1 b1 W2 b2 W3 b3 log_std[4]).
+// returns the text length, or -(needed capacity) if cap is too small
+int ref_save_code(int kind, const float* blob, int has_std, const char* name, char* buf, int cap){
+    DEVICE device;
+    if(kind == 1){
+        ref_dagger::Teacher::MODEL teacher; rlt::malloc(device, teacher);
+        auto& mlp = rlt::get_first_layer(teacher);
+        const float* b = blob;
+        auto put = [&](auto& layer, TI out, TI in){
+            for(TI o = 0; o < out; o++) for(TI i = 0; i < in; i++) rlt::set(layer.weights.parameters, o, i, *b++);
+            for(TI o = 0; o < out; o++) rlt::set(layer.biases.parameters, 0, o, *b++);
+        };
+        put(mlp.input_layer, 64, 26); put(mlp.hidden_layers[0], 64, 64); put(mlp.output_layer, 8, 64);
+        int r = ref_export::emit(ref_export::with_example(device, teacher, name, 0xC0DE + 1), buf, cap);
+        rlt::free(device, teacher);
+        return r;
+    }
+    if(kind == 2){
+        using NET = ref_ppo::Net<22, 4, 8>;
+        typename NET::MODEL model; rlt::malloc(device, model);
+        ref_ppo::load<typename NET::MODEL, 22, 4>(device, model, blob, has_std, 1);
+        int r = ref_export::emit(ref_export::with_example(device, model, name, 0xC0DE + 2), buf, cap);
+        rlt::free(device, model);
+        return r;
+    }
+    return 0;
+}
+}

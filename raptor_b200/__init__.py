@@ -9,6 +9,6 @@ Everything computes on CUDA through the C ABI in include/b200_l2f.h; importing w
 """
 from ._lib import (DEVICE, FLAG_ACCURATE_MATH, GEMM_FP32_CUDA_CORES, GEMM_TCGEN05_3XTF32, HEAD_IDENTITY, HEAD_PPO_GAUSSIAN, HEAD_SQUASH_EVAL, HOST,  # noqa: F401
                    PARAMS_DIM, POLICY_MLP, POLICY_RAPTOR_GRU, SPEC_DEFAULT, SPEC_DEFAULT_DR, SPEC_RAPTOR, SPEC_RAPTOR_DR, SPEC_TEACHER, SPEC_TEACHER_DR)
-from .engine import EngineError, VectorEnvironment, parameters_from_json, parameters_to_json, raptor_policy_blob  # noqa: F401
+from .engine import Checkpoint, EngineError, VectorEnvironment, parameters_from_json, parameters_to_json, raptor_policy_blob  # noqa: F401
 
-__all__ = ["VectorEnvironment", "EngineError", "raptor_policy_blob", "parameters_to_json", "parameters_from_json"]
+__all__ = ["VectorEnvironment", "Checkpoint", "EngineError", "raptor_policy_blob", "parameters_to_json", "parameters_from_json"]

@@ -32,6 +32,7 @@ SOURCES = {
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
     "json_io.cu": [],
+    "checkpoint_io.cu": [],
 }
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -26,6 +26,61 @@ def raptor_policy_blob():
     return np.fromfile(os.path.join(HERE, "data", "raptor_policy_2084.f32"), dtype=np.float32)
 
 
+class Checkpoint:
+    """an rl-tools checkpoint code export (`checkpoint.h`, rl/loop/steps/checkpoint/operations_cpu.h:56-118) read by the engine's native reader
+    (csrc/checkpoint_io.cu); no GPU needed.  `tensors` maps namespace paths to float32 arrays; `policy()` returns (PolicyDesc, blob) for
+    VectorEnvironment.load_policy(**Checkpoint.policy_kwargs())."""
+
+    def __init__(self, text=None, path=None):
+        lib = L.load()
+        if text is None:
+            with open(path, "rb") as f:
+                text = f.read()
+        if isinstance(text, str):
+            text = text.encode()
+        h = ctypes.c_void_p()
+        if lib.b200l2f_checkpoint_parse(text, len(text), ctypes.byref(h)) != 0:
+            raise EngineError(lib.b200l2f_last_error(None).decode())
+        try:
+            self.tensors = {}
+            for i in range(lib.b200l2f_checkpoint_tensor_count(h)):
+                name, rank = ctypes.c_char_p(), ctypes.c_int32()
+                dims, data = ctypes.POINTER(ctypes.c_int64)(), ctypes.POINTER(ctypes.c_float)()
+                lib.b200l2f_checkpoint_tensor(h, i, ctypes.byref(name), ctypes.byref(rank), ctypes.byref(dims), ctypes.byref(data))
+                shape = tuple(dims[k] for k in range(rank.value))
+                self.tensors[name.value.decode()] = np.ctypeslib.as_array(data, shape=(int(np.prod(shape)),)).reshape(shape).copy()
+            get = lambda k: (lambda v: v.decode() if v is not None else None)(lib.b200l2f_checkpoint_string(h, k.encode()))
+            self.name, self.commit_hash = get("rl_tools::checkpoint::meta::name"), get("rl_tools::checkpoint::meta::commit_hash")
+            self._policy = {}
+            self._errors = {}
+            for root in ("rl_tools::checkpoint::actor",):
+                desc, n = L.PolicyDesc(), ctypes.c_size_t(0)
+                if lib.b200l2f_checkpoint_policy(h, root.encode(), ctypes.byref(desc), None, 0, ctypes.byref(n)) == 0:
+                    blob = np.zeros(n.value, np.float32)
+                    lib.b200l2f_checkpoint_policy(h, root.encode(), ctypes.byref(desc), blob.ctypes.data, blob.size, ctypes.byref(n))
+                    self._policy[root] = (desc, blob)
+                else:
+                    self._errors[root] = lib.b200l2f_last_error(None).decode()
+        finally:
+            lib.b200l2f_checkpoint_free(h)
+
+    def policy(self, root="rl_tools::checkpoint::actor"):
+        if root not in self._policy:
+            raise EngineError(self._errors.get(root, "checkpoint: no actor under " + root))
+        return self._policy[root]
+
+    def policy_kwargs(self, root="rl_tools::checkpoint::actor"):
+        d, blob = self.policy(root)
+        return dict(blob=blob, arch=d.arch, input_dim=d.input_dim, hidden_dim=d.hidden_dim, output_dim=d.output_dim, standardize=d.standardize,
+                    head=d.head, gru_sequence_length=d.gru_sequence_length, gemm=d.gemm)
+
+    @property
+    def example(self):
+        """the known-answer pair stored with the actor (input, output) or None"""
+        i, o = self.tensors.get("rl_tools::checkpoint::example::input"), self.tensors.get("rl_tools::checkpoint::example::output")
+        return None if i is None or o is None else (i, o)
+
+
 def parameters_to_json(row):
     """rl_tools::json(device, env, parameters) (rl/environments/l2f/operations_cpu.h:139-411) of one flat parameter row [145]; no GPU needed"""
     lib = L.load()

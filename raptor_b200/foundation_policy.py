@@ -7,11 +7,14 @@ auto-reset every 500 steps as in training (rl_tools/nn/layers/gru/operations_gen
 import numpy as np
 
 from . import _lib as L
-from .engine import VectorEnvironment, raptor_policy_blob
+from .engine import Checkpoint, VectorEnvironment, raptor_policy_blob
 
 
 class Raptor:
-    def __init__(self, device=0, no_auto_reset=False):
+    def __init__(self, device=0, no_auto_reset=False, checkpoint=None):
+        """checkpoint: path of an rl-tools `checkpoint.h` code export with a Dense-GRU-Dense actor (another training run of the foundation
+        policy); default = the weights of the reference's published checkpoint shipped in raptor_b200/data"""
+        self._policy = dict(blob=raptor_policy_blob()) if checkpoint is None else Checkpoint(path=checkpoint).policy_kwargs()
         self._device = device
         self._no_auto_reset = no_auto_reset
         self._engine = None
@@ -20,7 +23,7 @@ class Raptor:
     def _ensure(self, n):
         if self._engine is None or self._engine.N_ENVIRONMENTS != n:
             self._engine = VectorEnvironment(n, L.SPEC_RAPTOR, device=self._device)
-            self._engine.load_policy(raptor_policy_blob())
+            self._engine.load_policy(**self._policy)
             self._pending_reset = False   # load_policy resets
 
     def reset(self):
