@@ -158,7 +158,14 @@ class OraclePolicy(ctypes.Structure):
 
 
 POLICY_RAPTOR_GRU, POLICY_MLP = 0, 1
-HEAD_IDENTITY, HEAD_SQUASH_EVAL, HEAD_PPO_GAUSSIAN = 0, 1, 2
+HEAD_IDENTITY, HEAD_SQUASH_EVAL, HEAD_PPO_GAUSSIAN, HEAD_SQUASH_SAMPLE = 0, 1, 2, 3
+
+
+def new_off_policy_runner(n, capacity, obs_dim):
+    """runner state after rl_tools::init(device, runner): everything truncated, empty replay rings (off_policy_runner/operations_generic.h:163-180)"""
+    return dict(episode_step=np.zeros(n, np.int32), episode_return=np.zeros(n, np.float32), truncated=np.ones(n, np.uint8),
+                replay=np.zeros((n, capacity, 2 * obs_dim + 7), np.float32), episode_start=np.zeros((n, capacity), np.int32),
+                position=np.zeros(n, np.int32), full=np.zeros(n, np.uint8), current_episode_start=np.zeros(n, np.int32))
 
 
 class Port(_Common):
@@ -177,6 +184,7 @@ class Port(_Common):
         L.oracle_policy_evaluate_step.argtypes = [ctypes.POINTER(OraclePolicy), c_int, f32, c_int, vp, vp, c_int, vp, f32, vp, vp]
         L.oracle_rollout.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, f32, f32, u64, vp, vp, c_int, vp, vp, vp, vp, vp]
         L.oracle_collect.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, f32, c_int]
+        L.oracle_off_policy_steps.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.oracle_evaluate_values.argtypes = [ctypes.POINTER(OraclePolicy), c_int, c_int, f32, c_int]
         L.oracle_estimate_generalized_advantages.argtypes = [c_int, c_int, f32, c_int, c_float, c_float, c_int]
         L.oracle_normalizer_update.argtypes = [c_int, c_int, f32, c_int, f32, f32, ctypes.POINTER(c_int)]
@@ -196,7 +204,7 @@ class Port(_Common):
     def policy_evaluate_step(self, pol, obs, hidden=None, gru_step=None, no_auto_reset=False, rng=None):
         obs = np.ascontiguousarray(obs, np.float32)
         n = obs.shape[0]
-        adim = pol.output_dim // 2 if pol.head == HEAD_SQUASH_EVAL else pol.output_dim
+        adim = pol.output_dim // 2 if pol.head in (HEAD_SQUASH_EVAL, HEAD_SQUASH_SAMPLE) else pol.output_dim
         act = np.zeros((n, adim), np.float32)
         mean = np.zeros((n, adim), np.float32)
         lp = np.zeros(n, np.float32)
@@ -222,6 +230,18 @@ class Port(_Common):
         self.lib.oracle_collect(spec, ctypes.byref(pol), n, T, threads, step_limit, np.ascontiguousarray(env_params, np.float32), params, states, rngs,
                                 _ptr(episode_step), _ptr(episode_return), _ptr(truncated), data, D)
         return data
+
+    def off_policy_steps(self, spec, pol, env_params, params, states, rngs, runner, T, step_limit, sample_parameters=True, with_states=False):
+        """T runner steps IN PLACE on params/states/rngs and the runner dict (episode_step, episode_return, truncated, replay [n, capacity, 2*OBS+7],
+        episode_start [n, capacity], position, full, current_episode_start [n]); optional states / next_states [n, capacity, SD]"""
+        n, capacity = runner["replay"].shape[:2]
+        if with_states and "states" not in runner:
+            runner["states"] = np.zeros((n, capacity, self.state_dim(spec)), np.float32)
+            runner["next_states"] = np.zeros((n, capacity, self.state_dim(spec)), np.float32)
+        self.lib.oracle_off_policy_steps(spec, ctypes.byref(pol), n, T, step_limit, capacity, int(sample_parameters), np.ascontiguousarray(env_params, np.float32), params, states, rngs,
+                                         _ptr(runner["episode_step"]), _ptr(runner["episode_return"]), _ptr(runner["truncated"]), _ptr(runner["replay"]), _ptr(runner["episode_start"]),
+                                         _ptr(runner["position"]), _ptr(runner["full"]), _ptr(runner["current_episode_start"]), _ptr(runner.get("states")), _ptr(runner.get("next_states")))
+        return runner
 
     def evaluate_values(self, critic, data, n, T):
         """critic values over all (T+1)*n observation rows -> the all_values column, in place"""
@@ -278,6 +298,8 @@ class Ref(_Common):
             L.ref_collect.argtypes = [c_int, f32, c_int, f32, f32, f32, u64, vp, vp, vp, f32]
             L.ref_gae.argtypes = [c_int, f32, c_int]
             L.ref_normalizer_update.argtypes = [c_int, f32, f32, f32, ctypes.POINTER(c_int)]
+        if hasattr(L, "ref_off_policy_steps"):
+            L.ref_off_policy_steps.argtypes = [c_int, c_int, f32, f32, f32, f32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         if hasattr(L, "ref_dagger_add_to_dataset"):
             u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
             i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -353,6 +375,24 @@ class Ref(_Common):
         a = c_int(age)
         self.lib.ref_normalizer_update(spec, data, mean, std, ctypes.byref(a))
         return int(a.value)
+
+    # ---- off-policy runner (the reference's own prologue_per_env / epilogue_per_env / replay add); fixed sizes, see off_policy_sizes()
+    def off_policy_sizes(self):
+        v = [c_int() for _ in range(4)]
+        self.lib.ref_off_policy_sizes(*[ctypes.byref(x) for x in v])
+        return tuple(int(x.value) for x in v)      # n, steps, step_limit, capacity
+
+    def off_policy_steps(self, spec, blob, env_params, params, states, rngs, runner, sample_parameters=True, with_states=False):
+        n, T, _, capacity = self.off_policy_sizes()
+        assert runner["replay"].shape[:2] == (n, capacity)
+        if with_states and "states" not in runner:
+            runner["states"] = np.zeros((n, capacity, self.state_dim(spec)), np.float32)
+            runner["next_states"] = np.zeros((n, capacity, self.state_dim(spec)), np.float32)
+        rc = self.lib.ref_off_policy_steps(spec, int(sample_parameters), np.ascontiguousarray(blob, np.float32), np.ascontiguousarray(env_params, np.float32), params, states, rngs,
+                                           _ptr(runner["episode_step"]), _ptr(runner["episode_return"]), _ptr(runner["truncated"]), _ptr(runner["replay"]), _ptr(runner["episode_start"]),
+                                           _ptr(runner["position"]), _ptr(runner["full"]), _ptr(runner["current_episode_start"]), _ptr(runner.get("states")), _ptr(runner.get("next_states")))
+        assert rc == 0, "ref_off_policy_steps: spec not instantiated"
+        return runner
 
     # ---- checkpoint code export: the reference's own save_code (kind 1 = SAC teacher MLP + sample_and_squash, 2 = PPO standardize + MLP + log_std)
     def save_code(self, kind, blob, has_std=0, name="fixture"):

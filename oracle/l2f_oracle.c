@@ -707,6 +707,17 @@ static void mlp_forward(const oracle_policy_t* pol, const float* obs, uint64_t* 
     if(pol->head == ORACLE_HEAD_SQUASH_EVAL){
         for(int i = 0; i < OUT/2; i++) action[i] = tanhf(y[i]); /* Evaluation mode: sample = mean */
     }
+    else if(pol->head == ORACLE_HEAD_SQUASH_SAMPLE){
+        /* Mode<Rollout> / Default of sample_and_squash evaluate_per_sample (operations_generic.h:148-194): noise ~ N(0, 1) per action
+         * dimension, log_std clamped to [-20, 2] (layer.h:31-32), action = tanh(mean + noise * exp(log_std)) */
+        for(int i = 0; i < OUT/2; i++){
+            float log_std = y[OUT/2 + i];
+            float clipped = log_std < -20.0f ? -20.0f : (log_std > 2.0f ? 2.0f : log_std);
+            float std = expf(clipped);
+            float noise = rng_normal(rng, 0.0f, 1.0f);
+            action[i] = tanhf(y[i] + noise * std);
+        }
+    }
     else if(pol->head == ORACLE_HEAD_PPO_GAUSSIAN){
         float lp = 0;
         for(int i = 0; i < OUT; i++){
@@ -728,7 +739,7 @@ static void policy_forward(const oracle_policy_t* pol, const float* obs, float* 
 }
 void oracle_policy_evaluate_step(const oracle_policy_t* pol, int N, const float* obs, int obs_ld, float* hidden, int* gru_step, int no_auto_reset,
                                  uint64_t* rng, float* actions, float* out_mean, float* out_log_prob){
-    int adim = (pol->head == ORACLE_HEAD_SQUASH_EVAL) ? pol->output_dim / 2 : pol->output_dim;
+    int adim = (pol->head == ORACLE_HEAD_SQUASH_EVAL || pol->head == ORACLE_HEAD_SQUASH_SAMPLE) ? pol->output_dim / 2 : pol->output_dim;
     for(int n = 0; n < N; n++){
         policy_forward(pol, obs + (size_t)n * obs_ld, hidden ? hidden + (size_t)n * pol->hidden_dim : NULL, gru_step ? gru_step + n : NULL, no_auto_reset,
                        rng ? rng + n : NULL, actions + (size_t)n * adim, out_mean ? out_mean + (size_t)n * adim : NULL, out_log_prob ? out_log_prob + n : NULL);
@@ -865,6 +876,78 @@ void oracle_collect(int spec, const oracle_policy_t* pol, int N, int T, int thre
     if(threads == 1){ collect_range(&jobs[0]); return; }
     for(int t = 0; t < threads; t++) pthread_create(&th[t], NULL, collect_range, &jobs[t]);
     for(int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Off-policy runner step (SAC teachers): rl::components::off_policy_runner `step` = prologue + interlude + epilogue,
+ * INC/rl/components/off_policy_runner/operations_generic.h:215-238 with operations_generic_per_env.h:8-58 (prologue_per_env), :60-110
+ * (epilogue_per_env) and the replay buffer `add` INC/rl/components/replay_buffer/operations_generic.h:54-79; one RNG stream per
+ * environment as in the reference's CUDA kernels (operations_cuda.h:62-106).  Symmetric observations (the teacher env's
+ * ObservationPrivileged is its Observation), so a replay row is  obs[OBS] | action[4] | reward | next_obs[OBS] | terminated | truncated
+ * (replay_buffer.h:37-58, update_views operations_generic.h:12-22) and every environment owns a ring [capacity][2*OBS + 7]:
+ *   replay [N][capacity][2*OBS+7], episode_start [N][capacity], position / full / current_episode_start [N].
+ * states_out / next_states_out (ReplayBufferWithStates, operations_generic.h:81-85) [N][capacity][SD] may be NULL.
+ * The actor is the SAC MLP with sample_and_squash in Mode<Rollout> (interlude, operations_generic.h:190-204): ORACLE_HEAD_SQUASH_SAMPLE.
+ * ------------------------------------------------------------------------------------------- */
+void oracle_off_policy_steps(int spec, const oracle_policy_t* pol, int N, int T, int episode_step_limit, int capacity, int sample_parameters, const float* env_params,
+                             float* params_io, float* states_io, uint64_t* rng_states, int* episode_step_io, float* episode_return_io, unsigned char* truncated_io,
+                             float* replay, int* episode_start, int* position_io, unsigned char* full_io, int* current_episode_start_io,
+                             float* states_out, float* next_states_out){
+    spec_t sp = get_spec(spec);
+    const int SD = 44 + 4 * sp.H, OBS = sp.obs_dim, D = 2 * OBS + 7;
+    for(int n = 0; n < N; n++){
+        float* p = params_io + (size_t)n * ORACLE_PARAMS_DIM;
+        float* s = states_io + (size_t)n * SD;
+        float* rb = replay + (size_t)n * capacity * D;
+        int* es = episode_start + (size_t)n * capacity;
+        float nx[MAX_STATE_DIM], obs[MAX_OBS_DIM], nobs[MAX_OBS_DIM], act[8];
+        uint64_t rng = rng_states[n];
+        int position = position_io[n], full = full_io[n], current_start = current_episode_start_io[n];
+        for(int t = 0; t < T; t++){
+            /* ---- prologue_per_env */
+            if(truncated_io[n]){
+                if(sample_parameters) oracle_sample_initial_parameters(spec, env_params, &rng, p);
+                float dead_target[12];   /* see collect_range: the reset keeps the previous Langevin block for POSITION trajectories */
+                memcpy(dead_target, s + S_TRAJ_TYPE(sp.H) + 1, sizeof(dead_target));
+                oracle_sample_initial_state(spec, p, &rng, s);
+                if(sp.langevin && (int)s[S_TRAJ_TYPE(sp.H)] == 0) memcpy(s + S_TRAJ_TYPE(sp.H) + 1, dead_target, sizeof(dead_target));
+                episode_step_io[n] = 0; episode_return_io[n] = 0;
+                if(full || position > 0){
+                    int previous = position == 0 ? capacity - 1 : position - 1;
+                    rb[(size_t)previous * D + 2 * OBS + 6] = 1.0f;
+                    current_start = position;
+                }
+            }
+            observe_impl(&sp, p, s, &rng, obs);
+            /* ---- interlude: evaluate_step in Mode<Rollout> */
+            policy_forward(pol, obs, NULL, NULL, 1, &rng, act, NULL, NULL);
+            /* ---- epilogue_per_env */
+            step_impl(&sp, p, s, act, &rng, nx);
+            float r = reward_impl(&sp, p, s, act, nx);
+            observe_impl(&sp, p, nx, &rng, nobs);
+            int term = terminated_impl(p, nx);
+            episode_step_io[n] += 1;
+            episode_return_io[n] += r;
+            int trunc = term || episode_step_io[n] == episode_step_limit;
+            truncated_io[n] = (unsigned char)trunc;
+            float* row = rb + (size_t)position * D;
+            if(states_out) memcpy(states_out + ((size_t)n * capacity + position) * SD, s, sizeof(float) * SD);
+            if(next_states_out) memcpy(next_states_out + ((size_t)n * capacity + position) * SD, nx, sizeof(float) * SD);
+            memcpy(row, obs, sizeof(float) * OBS);
+            memcpy(row + OBS, act, sizeof(float) * 4);
+            row[OBS + 4] = r;
+            memcpy(row + OBS + 5, nobs, sizeof(float) * OBS);
+            row[2 * OBS + 5] = (float)term;
+            row[2 * OBS + 6] = (float)trunc;
+            es[position] = current_start;
+            position = (position + 1) % capacity;
+            if(trunc) current_start = position;
+            if(position == 0 && !full) full = 1;
+            memcpy(s, nx, sizeof(float) * SD);
+        }
+        rng_states[n] = rng;
+        position_io[n] = position; full_io[n] = (unsigned char)full; current_episode_start_io[n] = current_start;
+    }
 }
 
 /* ---------------------------------------------------------------------------------------------

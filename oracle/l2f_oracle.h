@@ -46,7 +46,7 @@ int   oracle_terminated(int spec, const float* p, const float* s);
 
 /* ---- policies ---- */
 enum { ORACLE_POLICY_RAPTOR_GRU = 0, ORACLE_POLICY_MLP = 1 };
-enum { ORACLE_HEAD_IDENTITY = 0, ORACLE_HEAD_SQUASH_EVAL = 1, ORACLE_HEAD_PPO_GAUSSIAN = 2 };
+enum { ORACLE_HEAD_IDENTITY = 0, ORACLE_HEAD_SQUASH_EVAL = 1, ORACLE_HEAD_PPO_GAUSSIAN = 2, ORACLE_HEAD_SQUASH_SAMPLE = 3 /* sample_and_squash in Mode<Rollout>: tanh(mean + N(0,1) exp(clamp(log_std))) */ };
 typedef struct {
     int arch;        /* ORACLE_POLICY_* */
     int input_dim;   /* leading observation columns consumed */
@@ -72,6 +72,11 @@ void oracle_rollout(int spec, const oracle_policy_t* pol, int N, int T, int thre
 void oracle_collect(int spec, const oracle_policy_t* pol, int N, int T, int threads, int episode_step_limit, const float* env_params,
                     float* params_io, float* states_io, uint64_t* rng_states, int* episode_step_io, float* episode_return_io, unsigned char* truncated_io,
                     float* dataset, int data_dim);
+/* off-policy runner steps (SAC teacher data collection into per-environment replay rings); layout documented in l2f_oracle.c */
+void oracle_off_policy_steps(int spec, const oracle_policy_t* pol, int N, int T, int episode_step_limit, int capacity, int sample_parameters, const float* env_params,
+                             float* params_io, float* states_io, uint64_t* rng_states, int* episode_step_io, float* episode_return_io, unsigned char* truncated_io,
+                             float* replay, int* episode_start, int* position_io, unsigned char* full_io, int* current_episode_start_io,
+                             float* states_out, float* next_states_out);
 /* learner feed (PPO loop step between collect and train): critic values, GAE, running observation normalizer */
 void oracle_evaluate_values(const oracle_policy_t* critic, int N, int T, float* dataset, int data_dim);
 void oracle_estimate_generalized_advantages(int N, int T, float* dataset, int data_dim, float gamma, float lambda, int ignore_termination);

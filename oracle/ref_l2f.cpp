@@ -1002,3 +1002,127 @@ int ref_save_code(int kind, const float* blob, int has_std, const char* name, ch
     return 0;
 }
 }
+
+// ================================================================================================
+// Off-policy runner (SAC teacher data collection): the reference's OffPolicyRunner, its own prologue_per_env / epilogue_per_env
+// (rl/components/off_policy_runner/operations_generic_per_env.h:8-110) and replay buffer `add`, driven with ONE RNG STREAM PER ENVIRONMENT
+// exactly as the reference's CUDA kernels drive them (operations_cuda.h:62-106: `get(rng.states, 0, env_i)`); the interlude is the
+// reference's evaluate_step of the SAC actor (MLP 26-64-64-8 + sample_and_squash) in Mode<Rollout> (operations_generic.h:190-204), per
+// environment with that environment's stream.
+// ================================================================================================
+#include <rl_tools/rl/components/replay_buffer/operations_generic.h>
+#include <rl_tools/rl/components/off_policy_runner/operations_generic.h>
+
+namespace ref_opr{
+    constexpr TI N = 16, STEPS = 60, STEP_LIMIT = 20, CAPACITY = 48;   // the ring wraps (60 > 48); episodes end by the step limit and by termination
+    using CAP = rlt::nn::capability::Forward<true>;
+    struct Actor{ // rl/algorithms/sac/loop/core/approximators_mlp.h:14-37
+        using INPUT_SHAPE = rlt::tensor::Shape<TI, 1, 1, ENV_TEACHER::Observation::DIM>;
+        using MLP_CONFIG = rlt::nn_models::mlp::Configuration<T, TI, 2 * 4, 3, 64, rlt::nn::activation_functions::ActivationFunction::RELU, rlt::nn::activation_functions::IDENTITY>;
+        using MLP = rlt::nn_models::mlp::BindConfiguration<MLP_CONFIG>;
+        using SAMPLE_AND_SQUASH_CONFIG = rlt::nn::layers::sample_and_squash::Configuration<T, TI, rlt::nn::layers::sample_and_squash::DefaultParameters<T>>;
+        using SAMPLE_AND_SQUASH = rlt::nn::layers::sample_and_squash::BindConfiguration<SAMPLE_AND_SQUASH_CONFIG>;
+        template <typename T_CONTENT, typename T_NEXT_MODULE = rlt::nn_models::sequential::OutputModule>
+        using Module = typename rlt::nn_models::sequential::Module<T_CONTENT, T_NEXT_MODULE>;
+        using MODEL = rlt::nn_models::sequential::Build<CAP, Module<MLP, Module<SAMPLE_AND_SQUASH>>, INPUT_SHAPE>;
+    };
+    template <typename ENV, bool SAMPLE>
+    struct RunnerSpec{
+        struct PARAMETERS: rlt::rl::components::off_policy_runner::ParametersDefault<T, TI>{
+            static constexpr TI N_ENVIRONMENTS = N;
+            static constexpr bool ASYMMETRIC_OBSERVATIONS = false;
+            static constexpr TI REPLAY_BUFFER_CAPACITY = CAPACITY;
+            static constexpr TI EPISODE_STEP_LIMIT = STEP_LIMIT;
+            static constexpr bool SAMPLE_PARAMETERS = SAMPLE;
+        };
+        using POLICIES = rlt::utils::Tuple<TI, Actor::MODEL>;
+        using SPEC = rlt::rl::components::off_policy_runner::Specification<T, TI, ENV, POLICIES, PARAMETERS, true>;
+        using RUNNER = rlt::rl::components::OffPolicyRunner<SPEC>;
+    };
+    template <typename ENV, bool SAMPLE>
+    static void run(const float* actor_blob, const float* env_params, float* params_io, float* states_io, uint64_t* rng_states,
+                    int* episode_step_io, float* episode_return_io, unsigned char* truncated_io,
+                    float* replay, int* episode_start, int* position_io, unsigned char* full_io, int* current_episode_start_io, float* states_out, float* next_states_out){
+        using RS = RunnerSpec<ENV, SAMPLE>;
+        using RUNNER = typename RS::RUNNER;
+        constexpr TI OBS = ENV::Observation::DIM;
+        constexpr TI D = RUNNER::REPLAY_BUFFER_TYPE::DATA_COLS;
+        static_assert(D == 2 * OBS + 7, "symmetric replay row");
+        DEVICE device;
+        auto* runner_ptr = new RUNNER(); RUNNER& runner = *runner_ptr;
+        rlt::malloc(device, runner);
+        rlt::init(device, runner);
+        Actor::MODEL actor; Actor::MODEL::template Buffer<> buffer; Actor::MODEL::template State<> actor_state;
+        rlt::malloc(device, actor); rlt::malloc(device, buffer); rlt::malloc(device, actor_state);
+        {
+            auto& mlp = rlt::get_first_layer(actor);
+            const float* b = actor_blob;
+            auto put = [&](auto& layer, TI out, TI in){
+                for(TI o = 0; o < out; o++) for(TI i = 0; i < in; i++) rlt::set(layer.weights.parameters, o, i, *b++);
+                for(TI o = 0; o < out; o++) rlt::set(layer.biases.parameters, 0, o, *b++);
+            };
+            put(mlp.input_layer, 64, OBS); put(mlp.hidden_layers[0], 64, 64); put(mlp.output_layer, 8, 64);
+        }
+        const int SD = state_dim(Impl<ENV>::H);
+        std::vector<RNG> rngs(N);
+        for(TI e = 0; e < N; e++){
+            auto& env = rlt::get(runner.envs, 0, e);
+            unflatten_parameters(env_params, env.parameters);
+            unflatten_parameters(params_io + e * PARAMS_DIM, rlt::get(runner.env_parameters, 0, e));
+            auto& st = rlt::get(runner.states, 0, e); zero_state(st); unflatten_state(states_io + e * SD, st);
+            rlt::set(runner.episode_step, 0, e, (TI)episode_step_io[e]);
+            rlt::set(runner.episode_return, 0, e, episode_return_io[e]);
+            rlt::set(runner.truncated, 0, e, truncated_io[e] != 0);
+            auto& rb = rlt::get(runner.replay_buffers, 0, e);
+            for(TI r = 0; r < CAPACITY; r++){
+                for(TI c = 0; c < D; c++) rlt::set(rb.data, r, c, replay[(e * CAPACITY + r) * D + c]);
+                rlt::set(device, rb.episode_start, (TI)episode_start[e * CAPACITY + r], r);
+            }
+            rb.position = position_io[e]; rb.full = full_io[e] != 0; rb.current_episode_start = current_episode_start_io[e];
+            rngs[e].state = rng_states[e];
+        }
+        for(TI step_i = 0; step_i < STEPS; step_i++){
+            for(TI e = 0; e < N; e++) rlt::rl::components::off_policy_runner::prologue_per_env(device, runner, rngs[e], e);
+            for(TI e = 0; e < N; e++){
+                auto obs_row = rlt::row(device, runner.buffers.observations, e);
+                auto act_row = rlt::row(device, runner.buffers.actions, e);
+                auto obs_tensor = rlt::to_tensor(device, obs_row);
+                auto act_tensor = rlt::to_tensor(device, act_row);
+                rlt::Mode<rlt::mode::Rollout<>> mode;
+                rlt::evaluate_step(device, actor, obs_tensor, actor_state, act_tensor, buffer, rngs[e], mode);
+            }
+            for(TI e = 0; e < N; e++) rlt::rl::components::off_policy_runner::epilogue_per_env(device, runner, actor, rngs[e], e);
+        }
+        for(TI e = 0; e < N; e++){
+            flatten_parameters(rlt::get(runner.env_parameters, 0, e), params_io + e * PARAMS_DIM);
+            flatten_state(rlt::get(runner.states, 0, e), states_io + e * SD);
+            rng_states[e] = rngs[e].state;
+            episode_step_io[e] = (int)rlt::get(runner.episode_step, 0, e);
+            episode_return_io[e] = rlt::get(runner.episode_return, 0, e);
+            truncated_io[e] = rlt::get(runner.truncated, 0, e) ? 1 : 0;
+            auto& rb = rlt::get(runner.replay_buffers, 0, e);
+            for(TI r = 0; r < CAPACITY; r++){
+                for(TI c = 0; c < D; c++) replay[(e * CAPACITY + r) * D + c] = rlt::get(rb.data, r, c);
+                episode_start[e * CAPACITY + r] = (int)rlt::get(device, rb.episode_start, r);
+                if(states_out) flatten_state(rlt::get(rb.states, r, 0), states_out + ((size_t)e * CAPACITY + r) * SD);
+                if(next_states_out) flatten_state(rlt::get(rb.next_states, r, 0), next_states_out + ((size_t)e * CAPACITY + r) * SD);
+            }
+            position_io[e] = (int)rb.position; full_io[e] = rb.full ? 1 : 0; current_episode_start_io[e] = (int)rb.current_episode_start;
+        }
+        rlt::free(device, runner); rlt::free(device, actor); rlt::free(device, buffer); rlt::free(device, actor_state);
+        delete runner_ptr;
+    }
+}
+extern "C" {
+void ref_off_policy_sizes(int* n, int* steps, int* step_limit, int* capacity){ *n = ref_opr::N; *steps = ref_opr::STEPS; *step_limit = ref_opr::STEP_LIMIT; *capacity = ref_opr::CAPACITY; }
+// spec: 3 (TEACHER) or 5 (TEACHER_DR); sample_parameters = OffPolicyRunner PARAMETERS::SAMPLE_PARAMETERS
+int ref_off_policy_steps(int spec, int sample_parameters, const float* actor_blob, const float* env_params, float* params_io, float* states_io, uint64_t* rng_states,
+                         int* episode_step_io, float* episode_return_io, unsigned char* truncated_io,
+                         float* replay, int* episode_start, int* position_io, unsigned char* full_io, int* current_episode_start_io, float* states_out, float* next_states_out){
+#define OPR_ARGS actor_blob, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, replay, episode_start, position_io, full_io, current_episode_start_io, states_out, next_states_out
+    if(spec == 3){ if(sample_parameters) ref_opr::run<ENV_TEACHER, true>(OPR_ARGS); else ref_opr::run<ENV_TEACHER, false>(OPR_ARGS); return 0; }
+    if(spec == 5){ if(sample_parameters) ref_opr::run<ENV_TEACHER_DR, true>(OPR_ARGS); else ref_opr::run<ENV_TEACHER_DR, false>(OPR_ARGS); return 0; }
+#undef OPR_ARGS
+    return 1;
+}
+}

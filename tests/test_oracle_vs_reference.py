@@ -233,3 +233,35 @@ def test_dagger_add_to_dataset(port, ref):
         assert np.array_equal(got[k][:rows], want[k][:rows]), k
     assert np.array_equal(got["episode_start"][:ne], want["episode_start"][:ne]) and want["episode_start"][1] == first[0] + 1
     assert want["reset"][:rows].all() and want["truncated"][:rows].sum() == ne
+
+
+# ---- off-policy runner (SAC teacher data collection): the reference's own prologue_per_env / epilogue_per_env / replay-buffer add ------------
+@pytest.mark.parametrize("spec,sample_parameters", [(B.SPEC_TEACHER, True), (B.SPEC_TEACHER_DR, True), (B.SPEC_TEACHER_DR, False)])
+def test_off_policy_runner_steps(port, ref, spec, sample_parameters):
+    """60 runner steps of 16 environments into 48-row replay rings (the ring wraps), step limit 20 plus a tightened position threshold so that
+    episodes end both ways; a second call continues from the carried-over runner state.  Rows, ring bookkeeping, parameters, states and RNG
+    streams must be identical to the reference's."""
+    n, T, limit, capacity = ref.off_policy_sizes()
+    obs = port.observation_dim(spec)
+    rs = np.random.RandomState(41 + spec)
+    actor = random_mlp_blob(rs, obs, 8, False, False)
+    actor[-8 + 4:] += np.float32(-1.0)          # log_std biases: moderate exploration noise
+    env_p, params, states, rng = _collect_inputs(ref, spec, n, 13)
+    env_p = env_p.copy(); env_p[115] = 0.7       # termination.position_threshold
+    params[:, 115] = 0.7
+    pol = port.make_policy(actor, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_SAMPLE)
+    A = dict(params=params.copy(), states=states.copy(), rng=rng.copy(), runner=B.new_off_policy_runner(n, capacity, obs))
+    Bk = dict(params=params.copy(), states=states.copy(), rng=rng.copy(), runner=B.new_off_policy_runner(n, capacity, obs))
+    for it in range(2):
+        port.off_policy_steps(spec, pol, env_p, A["params"], A["states"], A["rng"], A["runner"], T, limit, sample_parameters=sample_parameters, with_states=True)
+        ref.off_policy_steps(spec, actor, env_p, Bk["params"], Bk["states"], Bk["rng"], Bk["runner"], sample_parameters=sample_parameters, with_states=True)
+        for k in ("params", "states", "rng"):
+            assert np.array_equal(A[k], Bk[k]), (it, k)
+        for k, v in Bk["runner"].items():
+            assert np.array_equal(A["runner"][k], v), (it, k)
+    r = Bk["runner"]
+    D = 2 * obs + 7
+    assert r["full"].all() and (r["position"] == (2 * T) % capacity).all()
+    term, trunc = r["replay"][:, :, D - 2], r["replay"][:, :, D - 1]
+    assert term.sum() > 0 and (trunc.sum() > term.sum()), "episodes must end by termination and by the step limit"
+    assert (np.abs(r["replay"][:, :, obs:obs + 4]) <= 1).all()
