@@ -229,6 +229,30 @@ typedef struct {
 int b200l2f_teachers_load(b200l2f_handle* h, int32_t n_teachers, int32_t episodes_per_teacher, const float* blobs, const float* position_offsets, int32_t gemm);
 int b200l2f_dagger_gather(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, const b200l2f_dagger_out* out, int64_t* rows_added);
 
+/* ---- off-policy runner steps (SAC teacher data collection of the foundation-policy pre-training): rl::components::off_policy_runner `step`
+ * = prologue + interlude + epilogue (INC/rl/components/off_policy_runner/operations_generic.h:215-238, operations_generic_per_env.h:8-110; the
+ * reference's CUDA precedent: operations_cuda.h:62-106) with the replay buffer `add` (INC/rl/components/replay_buffer/operations_generic.h:54-79),
+ * n_steps runner steps in one launch.  Handle spec TEACHER / TEACHER_DR; the loaded actor is the SAC MLP OBS-64-64-8 ([mean, log_std], either SQUASH
+ * head): the runner always evaluates it in Mode<Rollout>, action = tanh(mean + N(0,1) exp(clamp(log_std, -20, 2))).  Every environment owns one
+ * ring = the reference's ReplayBuffer::data matrix [capacity][2*OBS + 7], columns obs | action[4] | reward | next_obs | terminated | truncated
+ * (replay_buffer.h:37-58; symmetric observations), plus episode_start[capacity] and position / full / current_episode_start.  A fresh runner is
+ * all-zero buffers + b200l2f_collect_reset (truncated = true).  episode_step_limit = PARAMETERS::EPISODE_STEP_LIMIT (truncated = terminated or
+ * episode_step == limit); sample_parameters = PARAMETERS::SAMPLE_PARAMETERS (re-sample the dynamics on every reset).  The states / next_states
+ * of ReplayBufferWithStates (used by recalculate_rewards only) are not stored.  Buffers are updated in place (device) or staged (host).
+ * runner_get_state / runner_set_state: the per-environment bookkeeping shared with b200l2f_collect; any pointer may be NULL. */
+typedef struct {
+    int32_t memspace;               /* B200L2F_HOST / B200L2F_DEVICE for all pointers below */
+    int32_t capacity;               /* REPLAY_BUFFER_CAPACITY: rows per environment */
+    float*   data;                  /* [n_envs][capacity][2*OBS + 7] */
+    int32_t* episode_start;         /* [n_envs][capacity] */
+    int32_t* position;              /* [n_envs] */
+    uint8_t* full;                  /* [n_envs] */
+    int32_t* current_episode_start; /* [n_envs] */
+} b200l2f_replay_buffers;
+int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, int32_t sample_parameters, const b200l2f_replay_buffers* rb);
+int b200l2f_runner_get_state(b200l2f_handle* h, int32_t* episode_step, float* episode_return, uint8_t* truncated, int memspace);
+int b200l2f_runner_set_state(b200l2f_handle* h, const int32_t* episode_step, const float* episode_return, const uint8_t* truncated, int memspace);
+
 /* ---- parameter / state JSON wire format: rl_tools::json / from_json (L2F/operations_cpu.h:139-411 parameters, :412-560 state, :565-824 import).
  * Host functions on the flat rows above; to_json writes the reference's exact text (key order, separators, std::to_string formatting), *length
  * receives the size without the terminator (call with buf = NULL to query it); from_json reads every key the reference reads (a missing or

@@ -31,6 +31,7 @@ SOURCES = {
     "collect_ts.cu": TC + ["mlp_tc.cuh"],
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
+    "off_policy.cu": TC + ["mlp_tc.cuh", "offpolicy.cuh", "offpolicy_tc.cuh"],
     "json_io.cu": [],
     "checkpoint_io.cu": [],
 }

@@ -1,0 +1,136 @@
+// raptor_b200/csrc/off_policy.cu -- host side of b200l2f_off_policy_steps + instantiations of k_off_policy / k_off_policy_ts, and the accessors of
+// the runner bookkeeping (episode_step / episode_return / truncated) shared with b200l2f_collect.
+#include <vector>
+
+#include "launch.h"
+#include "offpolicy_tc.cuh"
+
+namespace b200l2f {
+namespace {
+
+int launch_off_policy_fp32(b200l2f_handle* h, const OffPolicyArgs& a){
+    auto go = [&](auto dr_c) -> int {
+        using Spec = SpecCompactCode<SpecTeacher>;
+        constexpr int IN = Spec::OBS_DIM;
+        auto kern = k_off_policy<Spec, decltype(dr_c)::value>;
+        const size_t smem = sizeof(float) * (MlpImg<IN, 8>::SIZE + (size_t)P_DYN_DIM * BLOCK + (size_t)(MLP_HD + IN) * BLOCK);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid_for(a.c.n, BLOCK), BLOCK, smem, h->stream>>>(a);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    };
+    return h->dr ? go(std::true_type{}) : go(std::false_type{});
+}
+
+int launch_off_policy_ts(b200l2f_handle* h, const OffPolicyArgs& a, bool follow, bool row_axial){
+    auto go2 = [&](auto dr_c, auto follow_c, auto axial_c) -> int {
+        using Spec = SpecCompactCode<SpecTeacher>;
+        using SM = OffPolicyTsSmem<Spec::OBS_DIM>;
+        auto kern = k_off_policy_ts<Spec, decltype(dr_c)::value, decltype(follow_c)::value, decltype(axial_c)::value>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int sms = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        if(!h->d_sched){ CU(cudaMalloc(&h->d_sched, sizeof(int) * 64)); h->sched_ints = 64; }
+        CU(cudaMemsetAsync(h->d_sched, 0, sizeof(int), h->stream));
+        const int n_tiles = grid_for(a.c.n, BLOCK);
+        const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;    // 256 TMEM columns per CTA -> 2 CTAs/SM, persistent tile loop
+        kern<<<grid, BLOCK, SM::TOTAL, h->stream>>>(a, h->d_mlp_tc_image, h->d_sched);
+        LAUNCH_CHECK();
+        return (int)B200L2F_OK;
+    };
+    auto go = [&](auto dr_c) -> int {
+        if(follow) return row_axial ? go2(dr_c, std::true_type{}, std::true_type{}) : go2(dr_c, std::true_type{}, std::false_type{});
+        return go2(dr_c, std::false_type{}, std::false_type{});
+    };
+    return h->dr ? go(std::true_type{}) : go(std::false_type{});
+}
+
+}  // namespace
+}  // namespace b200l2f
+
+using namespace b200l2f;
+
+extern "C" {
+
+int b200l2f_runner_get_state(b200l2f_handle* h, int32_t* episode_step, float* episode_return, uint8_t* truncated, int memspace){
+    if(!h) return fail(h, B200L2F_ERR_ARGUMENT, "runner_get_state: null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    const cudaMemcpyKind k = memspace == B200L2F_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if(episode_step) CU(cudaMemcpyAsync(episode_step, h->d_episode_step, sizeof(int32_t) * h->n, k, h->stream));
+    if(episode_return) CU(cudaMemcpyAsync(episode_return, h->d_episode_return, sizeof(float) * h->n, k, h->stream));
+    if(truncated) CU(cudaMemcpyAsync(truncated, h->d_truncated, h->n, k, h->stream));
+    if(memspace == B200L2F_HOST) CU(cudaStreamSynchronize(h->stream));
+    return B200L2F_OK;
+}
+int b200l2f_runner_set_state(b200l2f_handle* h, const int32_t* episode_step, const float* episode_return, const uint8_t* truncated, int memspace){
+    if(!h) return fail(h, B200L2F_ERR_ARGUMENT, "runner_set_state: null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    const cudaMemcpyKind k = memspace == B200L2F_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if(episode_step) CU(cudaMemcpyAsync(h->d_episode_step, episode_step, sizeof(int32_t) * h->n, k, h->stream));
+    if(episode_return) CU(cudaMemcpyAsync(h->d_episode_return, episode_return, sizeof(float) * h->n, k, h->stream));
+    if(truncated) CU(cudaMemcpyAsync(h->d_truncated, truncated, h->n, k, h->stream));
+    if(memspace == B200L2F_HOST) CU(cudaStreamSynchronize(h->stream));   // pageable sources must not be reused before the copy has read them
+    return B200L2F_OK;
+}
+
+int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, int32_t sample_parameters, const b200l2f_replay_buffers* rb){
+    if(!h) return fail(h, B200L2F_ERR_ARGUMENT, "off_policy_steps: null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if(!h->policy_loaded || h->pol.arch != B200L2F_POLICY_MLP || h->pol.output_dim != 8 || h->pol.standardize)
+        return fail(h, B200L2F_ERR_STATE, "off_policy_steps: load the SAC actor first (MLP, output_dim 8 = [mean, log_std], no standardize layer)");
+    if(h->kind != KIND_TEACHER) return fail(h, B200L2F_ERR_UNSUPPORTED, "off_policy_steps: instantiated for the pre-training environment (spec TEACHER / TEACHER_DR)");
+    if(!rb || n_steps < 0 || rb->capacity < 1 || !rb->data || !rb->episode_start || !rb->position || !rb->full || !rb->current_episode_start)
+        return fail(h, B200L2F_ERR_ARGUMENT, "off_policy_steps: bad arguments");
+    const int D = 2 * h->obs_dim + 7;
+    const size_t n = (size_t)h->n, rows = n * (size_t)rb->capacity;
+    // host buffers: temporary device copies of the rings and their bookkeeping (tests / small runners); device buffers are used in place
+    struct Part { void* user; size_t bytes; void* dev; };
+    Part parts[5] = {{rb->data, sizeof(float) * rows * D, nullptr}, {rb->episode_start, sizeof(int32_t) * rows, nullptr}, {rb->position, sizeof(int32_t) * n, nullptr},
+                     {rb->full, n, nullptr}, {rb->current_episode_start, sizeof(int32_t) * n, nullptr}};
+    const bool host = rb->memspace == B200L2F_HOST;
+    auto release = [&](){ if(host) for(auto& p : parts) if(p.dev) cudaFree(p.dev); };
+    for(auto& p : parts){
+        if(!host){ p.dev = p.user; continue; }
+        cudaError_t e = cudaMalloc(&p.dev, p.bytes);
+        if(e == cudaSuccess) e = cudaMemcpyAsync(p.dev, p.user, p.bytes, cudaMemcpyHostToDevice, h->stream);
+        if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("off_policy_steps: staging the replay buffers: ") + cudaGetErrorString(e)); }
+    }
+    if(host) cudaStreamSynchronize(h->stream);
+    CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
+    OffPolicyArgs oa{};
+    CollectArgs& a = oa.c;
+    a.params = h->d_params; a.env_row = h->d_env_row; a.state = h->d_state[0]; a.rng = h->d_rng; a.blob = h->d_blob; a.has_std = 0;
+    a.episode_step = h->d_episode_step; a.episode_return = h->d_episode_return; a.truncated = h->d_truncated; a.dataset = nullptr;
+    a.n = h->n; a.T = n_steps; a.step_limit = episode_step_limit; a.error_flag = h->d_flags;
+    std::memcpy(a.row, h->h_env_row, sizeof(a.row));
+    oa.replay = (float*)parts[0].dev; oa.episode_start = (int*)parts[1].dev; oa.position = (int*)parts[2].dev; oa.full = (uint8_t*)parts[3].dev;
+    oa.current_episode_start = (int*)parts[4].dev; oa.capacity = rb->capacity; oa.sample_parameters = sample_parameters ? 1 : 0;
+    const bool follow = h->params_follow_env_row;
+    const bool allow_axial = [](){ const char* e = std::getenv("B200L2F_DYNAMICS"); return !(e && std::string(e) == "general"); }();
+    bool row_axial = allow_axial;
+    for(int r = 0; r < 4; r++) if(a.row[P_THRUST_DIR + 3 * r] != 0.0f || a.row[P_THRUST_DIR + 3 * r + 1] != 0.0f || a.row[P_THRUST_DIR + 3 * r + 2] != 1.0f) row_axial = false;
+    for(int i = 0; i < 9; i++) if(i % 4 != 0 && (a.row[P_J + i] != 0.0f || a.row[P_JINV + i] != 0.0f)) row_axial = false;
+    const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
+    int rc = tensor_cores ? launch_off_policy_ts(h, oa, follow, row_axial) : launch_off_policy_fp32(h, oa);
+    if(rc){ release(); return rc; }
+    if(!follow && sample_parameters) h->features_dirty = true;
+    if(host){
+        for(auto& p : parts){
+            cudaError_t e = cudaMemcpyAsync(p.user, p.dev, p.bytes, cudaMemcpyDeviceToHost, h->stream);
+            if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("off_policy_steps: reading the replay buffers back: ") + cudaGetErrorString(e)); }
+        }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        release();
+        if(e != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("off_policy_steps: ") + cudaGetErrorString(e));
+    }
+    if(sample_parameters && h->dr){
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if(flag) return fail(h, B200L2F_ERR_STATE, "L2f: invalid domain randomization ranges (reset inside off_policy_steps)");
+    }
+    return B200L2F_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// raptor_b200/csrc/offpolicy.cuh -- off-policy runner steps on device: the SAC-teacher data collection of the foundation-policy pre-training.
+//
+// Replaces rl::components::off_policy_runner `step` = prologue + interlude + epilogue
+// (INC/rl/components/off_policy_runner/operations_generic.h:215-238; per environment: operations_generic_per_env.h:8-58 prologue_per_env,
+// :60-110 epilogue_per_env; the reference's own CUDA kernels launch exactly these per-environment bodies, operations_cuda.h:62-106) and the
+// replay buffer `add` (INC/rl/components/replay_buffer/operations_generic.h:54-79) for T runner steps in ONE launch:
+//
+//   per environment and step:  [reset if truncated: parameters (SAMPLE_PARAMETERS) + state re-sampled, ring bookkeeping]  -> observe
+//                              -> SAC actor MLP IN-64-64-8 -> sample_and_squash in Mode<Rollout>: a = tanh(mean + N(0,1) exp(clamp(log_std)))
+//                              -> step -> reward -> observe(next_state) -> terminated -> truncated = terminated | episode_step == limit
+//                              -> replay row  obs[IN] | action[4] | reward | next_obs[IN] | terminated | truncated   at the ring position
+//
+// Data layout: every environment owns the reference's ReplayBuffer::data matrix, a ring [capacity][D = 2 IN + 7] (replay_buffer.h:37-58, views
+// operations_generic.h:12-22; symmetric observations), stored back to back: replay[n][capacity][D]; episode_start[n][capacity]; position, full,
+// current_episode_start[n].  Rows of neighbouring environments are capacity*D*4 bytes apart, so a warp transposes its 32 rows through a private
+// shared-memory window and writes each row as one contiguous run: two phases of <= 32 floats (obs | action | reward, then next_obs | flags), one
+// store instruction per row and phase.  RNG draw order per step = the reference's: reset samplers, observation noise, 4 exploration normals,
+// action noise (step), next-observation noise.
+#pragma once
+#include "mlp.cuh"
+
+namespace b200l2f {
+
+struct OffPolicyArgs {
+    CollectArgs c;            // params / env_row / row / state / rng / blob / episode_step / episode_return / truncated / n / T / step_limit / error_flag
+    float* replay;            // [n][capacity][D]
+    int* episode_start;       // [n][capacity]
+    int* position; uint8_t* full; int* current_episode_start;   // [n]
+    int capacity;
+    int sample_parameters;    // OffPolicyRunner PARAMETERS::SAMPLE_PARAMETERS
+};
+
+// sample_and_squash evaluate_per_sample in Mode<Rollout> (INC/nn/layers/sample_and_squash/operations_generic.h:148-194), bounds layer.h:31-32
+template <bool OOL>
+__device__ __forceinline__ void squash_sample(const float* __restrict__ o, uint64_t& rng, float* __restrict__ act){
+#pragma unroll
+    for(int i = 0; i < 4; i++){
+        const float log_std = fminf(fmaxf(o[4 + i], -20.0f), 2.0f);
+        const float noise = rng_normal_t<OOL>(rng, 0.0f, 1.0f);
+        act[i] = tanhf(o[i] + noise * expf(log_std));
+    }
+}
+
+// one phase of the row write-back: every lane has put its NV values at win[lane * 33 + i]; row r of the warp goes to dst_r = base of lane r
+template <int NV>
+__device__ __forceinline__ void stream_phase(const float* __restrict__ win, float* my_dst, int lane, int rows_valid){
+    static_assert(NV <= 32, "one store instruction per row");
+    __syncwarp();
+    const unsigned long long mine = reinterpret_cast<unsigned long long>(my_dst);
+#pragma unroll 4
+    for(int r = 0; r < 32; r++){
+        float* dst = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, r));
+        if(r < rows_valid && lane < NV) dst[lane] = win[r * 33 + lane];
+    }
+    __syncwarp();
+}
+
+// ---- shared per-step tail: ring bookkeeping after the row is written (replay_buffer/operations_generic.h:70-77)
+struct Ring { int position, current_start; bool full; };
+__device__ __forceinline__ void ring_advance(Ring& rg, int capacity, bool truncated){
+    rg.position = rg.position + 1 == capacity ? 0 : rg.position + 1;
+    if(truncated) rg.current_start = rg.position;
+    if(rg.position == 0 && !rg.full) rg.full = true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// actor on fp32 CUDA cores (B200L2F_GEMM_FP32_CUDA_CORES, B200L2F_FLAG_ACCURATE_MATH): structure of k_collect (mlp.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+template <class Spec, bool DR>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_off_policy(const __grid_constant__ OffPolicyArgs oa){
+    const CollectArgs& a = oa.c;
+    constexpr int IN = Spec::OBS_DIM, OUT = 8;
+    constexpr int D = 2 * IN + 7;
+    constexpr int OBS0 = MLP_HD;                   // scratch rows [0, 64): hidden activations / write-back window; [64, 64 + IN): the observation
+    constexpr int ROWS = MLP_HD + IN;
+    static_assert(33 * 32 <= MLP_HD * 32, "the [32][33] window must fit in the hidden-activation rows");
+    extern __shared__ __align__(16) float smem[];
+    float* img = smem;
+    float* sm_dyn = smem + MlpImg<IN, OUT>::SIZE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* slab = sm_dyn + P_DYN_DIM * BLOCK + (size_t)warp * ROWS * 32;
+    float* scr = slab + lane;
+    stage_mlp_image<IN, OUT>(img, a.blob, a.has_std != 0, false);
+    const int e = blockIdx.x * BLOCK + threadIdx.x;
+    const bool active = e < a.n;
+    const size_t n = (size_t)a.n;
+    const size_t env = active ? (size_t)e : 0;
+    ParamsStagedT<false> p = stage_dynamics<false>(sm_dyn, a.params, n, env);
+    __syncthreads();
+    EnvState<Spec> st;
+    load_state(st, a.state + env, n);
+    DynInvariants d;
+    dyn_invariants(d, p, st);
+    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
+    uint64_t rng = a.rng[env];
+    int ep_step = a.episode_step[env]; float ep_ret = a.episode_return[env]; bool truncated = a.truncated[env] != 0;
+    Ring rg{oa.position[env], oa.current_episode_start[env], oa.full[env] != 0};
+    float* ring = oa.replay + env * (size_t)oa.capacity * D;
+    int* es = oa.episode_start + env * (size_t)oa.capacity;
+    const int rows_valid = min(32, a.n - (blockIdx.x * BLOCK + warp * 32));
+
+    for(int t = 0; t < a.T; t++){
+        if(truncated && active){                          // prologue_per_env (operations_generic_per_env.h:20-57)
+            truncated = false; ep_step = 0; ep_ret = 0.0f;
+            if(oa.sample_parameters){
+                ParamsOverlay o;
+                o.init(a.env_row);
+                if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
+                o.flush(ParamsRW{a.params + env, n});
+                p = stage_dynamics<false>(sm_dyn, a.params, n, env);
+                sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
+            }
+            else sample_state<Spec, ParamsStagedT<false>, true>(st, p, rng, hist_ptr, n);
+            dyn_invariants(d, p, st);
+            if(rg.full || rg.position > 0){
+                const int previous = rg.position == 0 ? oa.capacity - 1 : rg.position - 1;
+                ring[(size_t)previous * D + D - 1] = 1.0f;
+                rg.current_start = rg.position;
+            }
+        }
+        observe_to_scratch(st, p, rng, hist_ptr, n, scr + OBS0 * 32, 32);
+        float o8[OUT], act[4];
+        mlp_forward<IN, OUT, OBS0>(img, scr, 32, o8);
+        squash_sample<Spec::RNG_OOL>(o8, rng, act);        // interlude: evaluate_step in Mode<Rollout>
+        RewardInputs ri;                                  // epilogue_per_env (:60-110)
+        reward_inputs(ri, st);
+        if(Spec::H == 1 || active) env_step<Spec, true, ParamsStagedT<false>, true>(st, p, d, act, rng, hist_ptr, n);
+        const bool term = env_terminated(p, st.x);
+        const float r = env_reward(p, ri, act, st.x, term, d.dt);
+        ep_ret += r; ep_step += 1;
+        truncated = term || ep_step == a.step_limit;
+        float* row = ring + (size_t)rg.position * D;
+        // phase 1: obs | action | reward
+        __syncwarp();
+        for(int i = 0; i < IN; i++) slab[lane * 33 + i] = scr[(OBS0 + i) * 32];
+#pragma unroll
+        for(int i = 0; i < 4; i++) slab[lane * 33 + IN + i] = act[i];
+        slab[lane * 33 + IN + 4] = r;
+        stream_phase<IN + 5>(slab, row, lane, rows_valid);
+        // phase 2: next_obs | terminated | truncated
+        observe_to_scratch(st, p, rng, hist_ptr, n, scr + OBS0 * 32, 32);
+        __syncwarp();
+        for(int i = 0; i < IN; i++) slab[lane * 33 + i] = scr[(OBS0 + i) * 32];
+        slab[lane * 33 + IN] = term ? 1.0f : 0.0f;
+        slab[lane * 33 + IN + 1] = truncated ? 1.0f : 0.0f;
+        stream_phase<IN + 2>(slab, row + IN + 5, lane, rows_valid);
+        if(active) es[rg.position] = rg.current_start;
+        ring_advance(rg, oa.capacity, truncated);
+    }
+    if(!active) return;
+    store_state(st, a.state + env, n);
+    a.rng[env] = rng;
+    a.episode_step[env] = ep_step; a.episode_return[env] = ep_ret; a.truncated[env] = truncated ? 1 : 0;
+    oa.position[env] = rg.position; oa.current_episode_start[env] = rg.current_start; oa.full[env] = rg.full ? 1 : 0;
+}
+
+}  // namespace b200l2f

@@ -145,6 +145,7 @@ class VectorEnvironment:
             raise EngineError("b200l2f_create failed (%d): %s" % (rc, self._lib.b200l2f_last_error(None).decode()))
         self._h = h
         self.spec = spec
+        self.device = device
         self.N_ENVIRONMENTS = n_envs
         self.OBSERVATION_DIM = self._lib.b200l2f_observation_dim(h)
         self.STATE_DIM = self._lib.b200l2f_state_dim(h)
@@ -303,6 +304,46 @@ class VectorEnvironment:
             raise ValueError("evaluate_step: observation and action must live in the same memory space")
         self._check(self._lib.b200l2f_policy_evaluate_step(self._h, po, observation.shape[1], pa, int(no_auto_reset), ms))
         return action
+
+    # ---- off-policy runner (rl::components::off_policy_runner step): SAC-teacher collection into per-environment replay rings
+    def new_replay_buffers(self, capacity, device=False):
+        """empty rings as after rl_tools::init(device, runner): numpy arrays, or torch CUDA tensors (updated in place, no staging) if device"""
+        n, D = self.N_ENVIRONMENTS, 2 * self.OBSERVATION_DIM + 7
+        shapes = dict(data=((n, capacity, D), np.float32), episode_start=((n, capacity), np.int32), position=((n,), np.int32), full=((n,), np.uint8),
+                      current_episode_start=((n,), np.int32))
+        if not device:
+            return {k: np.zeros(sh, dt) for k, (sh, dt) in shapes.items()}
+        import torch
+        tdt = {np.float32: torch.float32, np.int32: torch.int32, np.uint8: torch.uint8}
+        return {k: torch.zeros(sh, dtype=tdt[dt], device="cuda:%d" % self.device) for k, (sh, dt) in shapes.items()}
+
+    def off_policy_steps(self, n_steps, episode_step_limit, replay, sample_parameters=True):
+        n, D = self.N_ENVIRONMENTS, 2 * self.OBSERVATION_DIM + 7
+        capacity = replay["data"].shape[1]
+        pd, ms, _ = _arg(replay["data"], np.float32, (n, capacity, D), "replay.data")
+        ptrs = [pd]
+        for k, dt, sh in (("episode_start", np.int32, (n, capacity)), ("position", np.int32, (n,)), ("full", np.uint8, (n,)), ("current_episode_start", np.int32, (n,))):
+            p, m, _ = _arg(replay[k], dt, sh, "replay." + k)
+            if m != ms:
+                raise ValueError("off_policy_steps: all replay buffers must live in the same memory space")
+            ptrs.append(p)
+        rb = L.ReplayBuffers(ms, capacity, *ptrs)
+        self._check(self._lib.b200l2f_off_policy_steps(self._h, n_steps, episode_step_limit, int(sample_parameters), ctypes.byref(rb)))
+        return replay
+
+    def get_runner_state(self):
+        """(episode_step [N] int32, episode_return [N] float32, truncated [N] uint8) of the on-/off-policy runner bookkeeping"""
+        n = self.N_ENVIRONMENTS
+        s, r, t = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self._check(self._lib.b200l2f_runner_get_state(self._h, s.ctypes.data, r.ctypes.data, t.ctypes.data, L.HOST))
+        return s, r, t
+
+    def set_runner_state(self, episode_step=None, episode_return=None, truncated=None):
+        n = self.N_ENVIRONMENTS
+        ps, _, k1 = _arg(None if episode_step is None else np.ascontiguousarray(episode_step, np.int32), np.int32, (n,), "episode_step")
+        pr, _, k2 = _arg(None if episode_return is None else np.ascontiguousarray(episode_return, np.float32), np.float32, (n,), "episode_return")
+        pt, _, k3 = _arg(None if truncated is None else np.ascontiguousarray(truncated, np.uint8), np.uint8, (n,), "truncated")
+        self._check(self._lib.b200l2f_runner_set_state(self._h, ps, pr, pt, L.HOST))
 
     # ---- PPO collection (rl_tools::collect): on-device auto-reset + trajectory write-back
     def collect_reset(self):

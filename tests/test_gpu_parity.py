@@ -460,6 +460,69 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
 
 
+@pytest.mark.parametrize("gemm", ["fp32", "tcgen05", "tcgen05-edited-parameters", "tcgen05-device-buffers"])
+@pytest.mark.parametrize("spec,sample_parameters", [(B.SPEC_TEACHER, True), (B.SPEC_TEACHER_DR, True), (B.SPEC_TEACHER_DR, False)])
+def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
+    """SAC-teacher collection (rl::components::off_policy_runner step x T) into per-environment replay rings: 200 environments (one full tile + a
+    ragged one), 70 steps into 48-row rings (they wrap), step limit 20 + a tightened position threshold (episodes end both ways), a second call
+    continues from the carried-over runner state; CUDA-core kernel (k_off_policy) and tensor-core kernel (k_off_policy_ts), host and device rings"""
+    import torch
+    edited = gemm.endswith("edited-parameters")
+    on_device = gemm.endswith("device-buffers")
+    g = rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32
+    n, T, limit, capacity, obs = 200, 35, 20, 48, 26
+    rs = np.random.RandomState(17)
+    blob = random_mlp_blob(rs, obs, 8, False, False)
+    blob[-4:] += np.float32(-1.0)                   # log_std biases: moderate exploration noise
+    env_p = foundation_dr_env_params(port, spec) if spec == B.SPEC_TEACHER_DR else port.nominal_parameters(spec).copy()
+    env_p[115] = 0.7                                # termination.position_threshold
+    env = rb.VectorEnvironment(n, spec)
+    env.set_environment_parameters(env_p)
+    env.initialize_rng(43, warmup=16)
+    env.initial_parameters()
+    env.initial_state()
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=g)
+    env.collect_reset()
+    rng = env.get_rng()
+    params, states = env.get_parameters(), env.get_state()
+    if edited:
+        env.set_parameters(params)
+    replay = env.new_replay_buffers(capacity, device=on_device)
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_SAMPLE)
+    runner = B.new_off_policy_runner(n, capacity, obs)
+    D = 2 * obs + 7
+    for it in range(2):
+        env.off_policy_steps(T, limit, replay, sample_parameters=sample_parameters)
+        port.off_policy_steps(spec, pol, env_p, params, states, rng, runner, T, limit, sample_parameters=sample_parameters)
+        got = {k: (v.cpu().numpy() if on_device else v) for k, v in replay.items()}
+        assert np.array_equal(env.get_rng(), rng), it                                  # every draw (resets, exploration, noise) in the same order
+        for k, w in (("position", "position"), ("full", "full"), ("current_episode_start", "current_episode_start"), ("episode_start", "episode_start")):
+            assert np.array_equal(got[k], runner[w]), (it, k)
+        ep_step, ep_ret, trunc = env.get_runner_state()
+        assert np.array_equal(ep_step, runner["episode_step"]) and np.array_equal(trunc, runner["truncated"])
+        close(ep_ret, runner["episode_return"], 2e-3, 2e-2, "episode_return")
+        gd, wd = got["data"], runner["replay"]
+        assert np.array_equal(gd[..., D - 2:], wd[..., D - 2:]), "terminated / truncated flags"
+        close(gd[..., :obs], wd[..., :obs], 2e-3, 2e-4, "observations")
+        close(gd[..., obs:obs + 4], wd[..., obs:obs + 4], 2e-3, 2e-3, "actions")
+        close(gd[..., obs + 4], wd[..., obs + 4], 2e-3, 2e-2, "rewards")
+        close(gd[..., obs + 5:2 * obs + 5], wd[..., obs + 5:2 * obs + 5], 2e-3, 2e-4, "next observations")
+        close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
+        close(env.get_state(), states, 2e-3, 2e-4, "states")
+    assert runner["full"].all() and runner["replay"][..., D - 2].sum() > 0 and runner["replay"][..., D - 1].sum() > runner["replay"][..., D - 2].sum()
+    # a row's next observation is the following row's observation inside an episode (no observation noise in these specs)
+    gd = got["data"]
+    e0 = gd[0]
+    pos = int(got["position"][0])
+    order = np.r_[pos:capacity, 0:pos]              # oldest -> newest
+    for a_, b_ in zip(order[:-1], order[1:]):
+        if e0[a_, D - 1] == 0:
+            assert np.array_equal(e0[a_, obs + 5:2 * obs + 5], e0[b_, :obs])
+    with pytest.raises(rb.EngineError, match="SAC actor"):
+        env.load_policy(random_mlp_blob(rs, obs, 4, False, False), arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=0, head=rb.HEAD_IDENTITY, gemm=g)
+        env.off_policy_steps(1, limit, replay)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("spec,n,gemm", [(B.SPEC_RAPTOR, 256, "tcgen05"), (B.SPEC_RAPTOR_DR, 200, "tcgen05"), (B.SPEC_TEACHER_DR, 203, "tcgen05"), (B.SPEC_RAPTOR, 203, "fp32")])
 def test_learner_feed_vs_oracle(rb, port, spec, n, gemm):
