@@ -110,6 +110,22 @@ def main():
     out.append({"config": "DAgger epoch data path: gather_epoch for 1000 teachers x 10 episodes x 500 steps (student rollout + add_to_dataset, device-resident dataset)",
                 "ms_per_epoch": ms_d, "env_steps_per_s": n * T / ms_d * 1e3, "dataset_rows": res["rows"], "rows_per_s": res["rows"] / ms_d * 1e3,
                 "student_rollout_only_ms": ms_r})
+    del env, s0, ds
+    # ---- SAC-teacher collection (off-policy runner steps): 262 144 environments x 256 steps into per-environment replay rings of 256 rows
+    n, T, cap = 262144, 256, 256
+    env = rb.VectorEnvironment(n, rb.SPEC_TEACHER_DR, stream=stream.cuda_stream)
+    row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32); env.set_environment_parameters(row)
+    env.initialize_rng(6, warmup=16); env.initial_parameters(); env.initial_state()
+    env.load_policy(mlp_blob(rs, 26, 8, False, False), arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=gemm)
+    replay = env.new_replay_buffers(cap, device=True)
+    def reset_runner():
+        env.collect_reset()
+        replay["position"].zero_(); replay["full"].zero_(); replay["current_episode_start"].zero_()
+    ms_o = timed(lambda: env.off_policy_steps(T, 500, replay), reset_runner, stream=stream, flush=flush)
+    written = n * T * (59 + 1) * 4
+    out.append({"config": "off-policy runner: 262 144 envs x 256 steps, SAC actor 26-64-64-8 in Rollout mode, DR resets, replay rings [N][256][59] in HBM (%.1f GB)" % (n * cap * 59 * 4 / 1e9),
+                "env_steps_per_s": n * T / ms_o * 1e3, "ms_per_launch": ms_o, "replay_bytes_written": written, "hbm_write_gbs": written / ms_o / 1e6,
+                "mean_reward": float(replay["data"][:, :, 30].mean().item()), "truncated_fraction": float(replay["data"][:, :, 58].mean().item())})
     for o in out:
         o["gemm"] = gemm_name
         print(json.dumps(o))
