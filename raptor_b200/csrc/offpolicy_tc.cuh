@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_off_policy_ts(const __grid_constan
                 o.init(a.row);
                 if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
                 if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
-                compile_dynamics_block(sm_dyn + tid, [&](int i){ return o[i]; });   // this thread's column only
+                compile_dynamics_block(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
                 sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
                 dyn_invariants(d, o, st);
             }

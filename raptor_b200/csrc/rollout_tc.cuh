@@ -77,56 +77,91 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
     for(int j = 0; j < HD; j++){ img[TcImage::BIAS2 + 32 + j] = s_n * bih[2 * HD + j]; img[TcImage::BIAS2 + 48 + j] = s_n * bhh[2 * HD + j]; }
 }
 
+#ifndef B200L2F_GATES_PACKED
+#define B200L2F_GATES_PACKED 1     // GRU gate epilogue of k_rollout_raptor_ts on the packed fp32 pipe (two hidden units per FADD2 / FFMA2)
+#endif
+#ifndef B200L2F_TMEM_PREFETCH
+#define B200L2F_TMEM_PREFETCH 0    // issue the second batch of accumulator loads (z, h) before the MUFU work on the first (r, n); measured -0.4 %
+#endif
+#ifndef B200L2F_HOIST_LANGEVIN
+#define B200L2F_HOIST_LANGEVIN 0   // draw the Langevin target's normals in the shadow of the first MMA round trip (noise-free kernels only); measured -0.8 %
+#endif
 #ifndef B200L2F_PACKED_FP32
 #define B200L2F_PACKED_FP32 1      // packed fp32 (FFMA2 / FADD2 / FMUL2, sm_100) in the default-math kernels; 0 = scalar twins (tuning / bisecting)
 #endif
 
-// ---- compiled per-environment dynamics block (67 floats), staged as sm[i * BLOCK + tid] ------------------------------------------
-enum DynC : int { C_COEF = 0, C_AF = 12, C_AT = 24, C_ITAU_RISE = 36, C_ITAU_FALL = 40, C_GRAVITY = 44, C_J = 47, C_JINV = 56, C_ACT_MIN = 65, C_ACT_MAX = 66, C_TERM_POS = 67, C_DIM = 68 };
+// ---- compiled per-environment dynamics block (68 floats), staged thread-major as sm_dyn[tid * C_DIM + i] ------------------------------
+// Every read is one LDS.128: the row stride is 68 words (= 4 mod 32), so the eight threads of a quarter-warp hit 8 x 4 distinct banks
+// (conflict-free), and a dynamics evaluation issues ~10 loads instead of 37 scalar ones.  Groups are laid out as the float4s the axial
+// vehicle's evaluation consumes; the general vehicle's extra entries (A_F, off-diagonal inertia) follow.
+enum DynC : int { C_COEF = 0,        // [12] thrust-curve coefficients, rotor r at [3r, 3r + 2]
+                  C_AT = 12,         // [3][4] torque per unit rotor thrust
+                  C_ITAU_RISE = 24, C_ITAU_FALL = 28,
+                  C_G = 32,          // gravity[3] | action min
+                  C_JD = 36,         // diag(J)[3] | action max
+                  C_JID = 40,        // diag(J^-1)[3] | termination position threshold
+                  C_AF = 44,         // [3][4] force per unit rotor thrust (general vehicle only)
+                  C_JOFF = 56, C_JIOFF = 62,   // off-diagonal entries of J, J^-1 in row-major order 01 02 10 12 20 21 (general vehicle only)
+                  C_DIM = 68 };
+static_assert(C_DIM % 4 == 0 && C_DIM % 32 == 4, "row stride must keep LDS.128 aligned and conflict-free");
+__host__ __device__ constexpr int dyn_j_slot(int base_diag, int base_off, int i, int j){   // where entry (i, j) of J / J^-1 lives in the block
+    return i == j ? base_diag + i : base_off + 2 * i + (j > i ? j - 1 : j);
+}
 // NC: the parameter columns are read-only for the whole launch (ld.global.nc); false when the kernel itself rewrites them (collect's resets)
 // FOLLOW: every entry outside the domain-randomised set equals row0 (collect, see k_collect_ts)
 template <bool UNIFORM, bool NC = true, bool FOLLOW = false>
 struct ParamsCompiledT {
-    const float* sm; const float* base; size_t stride;                // sm: staged block (this thread's column); base/stride: full parameter column in HBM
+    const float* sm; const float* base; size_t stride;                // sm: this thread's staged block; base/stride: full parameter column in HBM
     const float* row0;                                                // UNIFORM: environment 0's row in the launch's constant bank
-    __device__ __forceinline__ float c(int i) const { return sm[i * BLOCK]; }
+    __device__ __forceinline__ float4 c4(int i) const { return *reinterpret_cast<const float4*>(sm + i); }      // i % 4 == 0
+    __device__ __forceinline__ float c(int i) const {                 // compile-time i: one LDS.128 + a register pick (loads of a group are merged)
+        const float4 v = c4(i & ~3);
+        return (i & 3) == 0 ? v.x : (i & 3) == 1 ? v.y : (i & 3) == 2 ? v.z : v.w;
+    }
     __device__ __forceinline__ float operator[](int i) const {       // everything outside the dynamics block
-        if(i == P_TERM_POS) return sm[C_TERM_POS * BLOCK];            // per environment even under DR (10_sample_initial_parameters.h:154)
-        if(i == P_ACT_MIN) return sm[C_ACT_MIN * BLOCK];
-        if(i == P_ACT_MAX) return sm[C_ACT_MAX * BLOCK];
+        if(i == P_TERM_POS) return c(C_JID + 3);                      // per environment even under DR (10_sample_initial_parameters.h:154)
+        if(i == P_ACT_MIN) return c(C_G + 3);
+        if(i == P_ACT_MAX) return c(C_JD + 3);
         if(UNIFORM && mdp_uniform_index(i)) return row0[i];
         if(FOLLOW && !dr_overlay_index(i)) return row0[i];
         return NC ? __ldg(base + (size_t)i * stride) : base[(size_t)i * stride];
     }
 };
+__device__ __forceinline__ float* dyn_block_of_thread(float* sm_dyn){ return sm_dyn + threadIdx.x * C_DIM; }
 using ParamsCompiled = ParamsCompiledT<false>;
 // compile this thread's dynamics block from any parameter accessor P(i) (HBM column, register overlay, ...)
 template <class F>
-__device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F&& P){
+__device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F&& P){   // sm = dyn_block_of_thread(sm_dyn)
 #pragma unroll
-    for(int i = 0; i < 12; i++) sm[(C_COEF + i) * BLOCK] = P(P_THRUST_COEF + i);
+    for(int i = 0; i < 12; i++) sm[C_COEF + i] = P(P_THRUST_COEF + i);
 #pragma unroll
     for(int r = 0; r < 4; r++){
         const float dx = P(P_THRUST_DIR + 3 * r), dy = P(P_THRUST_DIR + 3 * r + 1), dz = P(P_THRUST_DIR + 3 * r + 2);
         const float px = P(P_ROTOR_POS + 3 * r), py = P(P_ROTOR_POS + 3 * r + 1), pz = P(P_ROTOR_POS + 3 * r + 2);
         const float kq = P(P_TORQUE_CONST + r);
-        sm[(C_AF + 0 * 4 + r) * BLOCK] = dx; sm[(C_AF + 1 * 4 + r) * BLOCK] = dy; sm[(C_AF + 2 * 4 + r) * BLOCK] = dz;
+        sm[C_AF + 0 * 4 + r] = dx; sm[C_AF + 1 * 4 + r] = dy; sm[C_AF + 2 * 4 + r] = dz;
         // torque of rotor r per unit thrust: torque_dir * k_q + r x dir   (60_dynamics.h:38-39)
-        sm[(C_AT + 0 * 4 + r) * BLOCK] = P(P_TORQUE_DIR + 3 * r + 0) * kq + (py * dz - pz * dy);
-        sm[(C_AT + 1 * 4 + r) * BLOCK] = P(P_TORQUE_DIR + 3 * r + 1) * kq + (pz * dx - px * dz);
-        sm[(C_AT + 2 * 4 + r) * BLOCK] = P(P_TORQUE_DIR + 3 * r + 2) * kq + (px * dy - py * dx);
-        sm[(C_ITAU_RISE + r) * BLOCK] = 1.0f / P(P_TAU_RISE + r);
-        sm[(C_ITAU_FALL + r) * BLOCK] = 1.0f / P(P_TAU_FALL + r);
+        sm[C_AT + 0 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 0) * kq + (py * dz - pz * dy);
+        sm[C_AT + 1 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 1) * kq + (pz * dx - px * dz);
+        sm[C_AT + 2 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 2) * kq + (px * dy - py * dx);
+        sm[C_ITAU_RISE + r] = 1.0f / P(P_TAU_RISE + r);
+        sm[C_ITAU_FALL + r] = 1.0f / P(P_TAU_FALL + r);
     }
 #pragma unroll
-    for(int i = 0; i < 3; i++) sm[(C_GRAVITY + i) * BLOCK] = P(P_GRAVITY + i);
+    for(int i = 0; i < 3; i++) sm[C_G + i] = P(P_GRAVITY + i);
 #pragma unroll
-    for(int i = 0; i < 9; i++){ sm[(C_J + i) * BLOCK] = P(P_J + i); sm[(C_JINV + i) * BLOCK] = P(P_JINV + i); }
-    sm[C_ACT_MIN * BLOCK] = P(P_ACT_MIN); sm[C_ACT_MAX * BLOCK] = P(P_ACT_MAX); sm[C_TERM_POS * BLOCK] = P(P_TERM_POS);
+    for(int i = 0; i < 3; i++){
+#pragma unroll
+        for(int j = 0; j < 3; j++){
+            sm[dyn_j_slot(C_JD, C_JOFF, i, j)] = P(P_J + 3 * i + j);
+            sm[dyn_j_slot(C_JID, C_JIOFF, i, j)] = P(P_JINV + 3 * i + j);
+        }
+    }
+    sm[C_G + 3] = P(P_ACT_MIN); sm[C_JD + 3] = P(P_ACT_MAX); sm[C_JID + 3] = P(P_TERM_POS);
 }
 template <bool UNIFORM, bool NC = true, bool FOLLOW = false>
 __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env, const float* row0){
-    float* sm = sm_dyn + threadIdx.x;
+    float* sm = dyn_block_of_thread(sm_dyn);
     const float* g = params + env;
     compile_dynamics_block(sm, [&](int i){ return NC ? __ldg(g + (size_t)i * n) : g[(size_t)i * n]; });
     ParamsCompiledT<UNIFORM, NC, FOLLOW> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
@@ -138,16 +173,21 @@ __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_c
 template <bool AXIAL = false, class PC>
 __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvariants& d, const float* __restrict__ x, const float* __restrict__ setpoint, float* __restrict__ dx){
     float tm[4];
+    {
+        const float4 k0 = p.c4(C_COEF), k1 = p.c4(C_COEF + 4), k2 = p.c4(C_COEF + 8);
+        const float cf[12] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w};
 #pragma unroll
-    for(int r = 0; r < 4; r++){
-        const float rpm = x[X_RPM + r];
-        tm[r] = p.c(C_COEF + 3 * r) + p.c(C_COEF + 3 * r + 1) * rpm + p.c(C_COEF + 3 * r + 2) * rpm * rpm;
+        for(int r = 0; r < 4; r++){
+            const float rpm = x[X_RPM + r];
+            tm[r] = cf[3 * r] + cf[3 * r + 1] * rpm + cf[3 * r + 2] * rpm * rpm;
+        }
     }
     float thrust[3], torque[3];
 #pragma unroll
     for(int i = 0; i < 3; i++){
-        if constexpr(!AXIAL) thrust[i] = p.c(C_AF + 4 * i) * tm[0] + p.c(C_AF + 4 * i + 1) * tm[1] + p.c(C_AF + 4 * i + 2) * tm[2] + p.c(C_AF + 4 * i + 3) * tm[3];
-        torque[i] = p.c(C_AT + 4 * i) * tm[0] + p.c(C_AT + 4 * i + 1) * tm[1] + p.c(C_AT + 4 * i + 2) * tm[2] + p.c(C_AT + 4 * i + 3) * tm[3];
+        if constexpr(!AXIAL){ const float4 f = p.c4(C_AF + 4 * i); thrust[i] = f.x * tm[0] + f.y * tm[1] + f.z * tm[2] + f.w * tm[3]; }
+        const float4 q = p.c4(C_AT + 4 * i);
+        torque[i] = q.x * tm[0] + q.y * tm[1] + q.z * tm[2] + q.w * tm[3];
     }
     if constexpr(AXIAL) thrust[2] = ((tm[0] + tm[1]) + tm[2]) + tm[3];
 #pragma unroll
@@ -175,24 +215,25 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
             o0 += v0 * q0; o1 += v1 * q0; o2 += v2 * q0;
             o0 += thrust[0]; o1 += thrust[1]; o2 += thrust[2];
         }
-        dx[X_VEL + 0] = o0 * d.inv_mass + p.c(C_GRAVITY + 0) + d.fa[0];
-        dx[X_VEL + 1] = o1 * d.inv_mass + p.c(C_GRAVITY + 1) + d.fa[1];
-        dx[X_VEL + 2] = o2 * d.inv_mass + p.c(C_GRAVITY + 2) + d.fa[2];
+        const float4 g = p.c4(C_G);
+        dx[X_VEL + 0] = o0 * d.inv_mass + g.x + d.fa[0];
+        dx[X_VEL + 1] = o1 * d.inv_mass + g.y + d.fa[1];
+        dx[X_VEL + 2] = o2 * d.inv_mass + g.z + d.fa[2];
     }
     {
         float v[3];
 #pragma unroll
         for(int i = 0; i < 3; i++){
-            if constexpr(AXIAL) v[i] = p.c(C_J + 4 * i) * (i == 0 ? w0 : (i == 1 ? w1 : w2));
-            else v[i] = p.c(C_J + 3 * i) * w0 + p.c(C_J + 3 * i + 1) * w1 + p.c(C_J + 3 * i + 2) * w2;
+            if constexpr(AXIAL) v[i] = p.c(C_JD + i) * (i == 0 ? w0 : (i == 1 ? w1 : w2));
+            else v[i] = p.c(dyn_j_slot(C_JD, C_JOFF, i, 0)) * w0 + p.c(dyn_j_slot(C_JD, C_JOFF, i, 1)) * w1 + p.c(dyn_j_slot(C_JD, C_JOFF, i, 2)) * w2;
         }
         const float t0 = torque[0] - (w1 * v[2] - w2 * v[1]);
         const float t1 = torque[1] - (w2 * v[0] - w0 * v[2]);
         const float t2 = torque[2] - (w0 * v[1] - w1 * v[0]);
 #pragma unroll
         for(int i = 0; i < 3; i++){
-            if constexpr(AXIAL) dx[X_OMEGA + i] = p.c(C_JINV + 4 * i) * (i == 0 ? t0 : (i == 1 ? t1 : t2)) + d.ta[i];
-            else dx[X_OMEGA + i] = p.c(C_JINV + 3 * i) * t0 + p.c(C_JINV + 3 * i + 1) * t1 + p.c(C_JINV + 3 * i + 2) * t2 + d.ta[i];
+            if constexpr(AXIAL) dx[X_OMEGA + i] = p.c(C_JID + i) * (i == 0 ? t0 : (i == 1 ? t1 : t2)) + d.ta[i];
+            else dx[X_OMEGA + i] = p.c(dyn_j_slot(C_JID, C_JIOFF, i, 0)) * t0 + p.c(dyn_j_slot(C_JID, C_JIOFF, i, 1)) * t1 + p.c(dyn_j_slot(C_JID, C_JIOFF, i, 2)) * t2 + d.ta[i];
         }
     }
 #pragma unroll
@@ -204,11 +245,13 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
 }
 // env_step twin for the compiled block (NOISE: action noise as in env_step; Langevin target as in env_step)
 // FAST: default-math variant (min/max clamps, MUFU reciprocal square root for the quaternion, MUFU Box-Muller for the Langevin target)
+// langevin_normals: the three N(0, 1) draws of the Langevin update, drawn by the caller ahead of time (legal only when nothing else draws from the
+// stream in between, i.e. NOISE == false: the values depend on the stream alone, not on the action) or nullptr = draw here
 template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, bool FAST = false, bool AXIAL = false, class PC>
 __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
-                                                  float* __restrict__ hist_ptr, size_t n){
+                                                  float* __restrict__ hist_ptr, size_t n, const float* __restrict__ langevin_normals = nullptr){
     float setpoint[4];
-    const float amin = p.c(C_ACT_MIN), amax = p.c(C_ACT_MAX);
+    const float amin = p.c(C_G + 3), amax = p.c(C_JD + 3);
 #pragma unroll
     for(int i = 0; i < 4; i++){
         float a = action[i];
@@ -313,7 +356,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
 #pragma unroll
             for(int dim = 0; dim < 3; dim++){
                 const float x_prev = st.lang[6 + dim], v_prev = st.lang[9 + dim];
-                const float dW = sqrt_dt * rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, 1.0f);
+                const float dW = sqrt_dt * (langevin_normals ? langevin_normals[dim] : rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, 1.0f));
                 const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
                 const float x_next = x_prev + v_next * dt;
                 st.lang[6 + dim] = x_next; st.lang[9 + dim] = v_next;
@@ -715,6 +758,15 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
             issue_gemm(C_D1, C_OBS_HI, C_OBS_LO, 3, TcImage::B1_HI, TcImage::B1_LO, 0, 16, IDESC16, 0);
             tc::mma_commit(bar_mma);
         }
+        // independent work in the shadow of the MMA round trip: the Langevin target's three normals depend on the RNG stream only
+        constexpr bool HOIST = B200L2F_HOIST_LANGEVIN && Spec::LANGEVIN && !NOISE;
+        float lang_normals[3];
+        if constexpr(HOIST){
+            if(st.traj_type == 1){
+#pragma unroll
+                for(int dim = 0; dim < 3; dim++) lang_normals[dim] = rng_normal_t<Spec::RNG_OOL, true>(rng, 0.0f, 1.0f);
+            }
+        }
         tc::mbar_wait(bar_mma, phase); phase ^= 1;
         tc::tc_fence_after();
         float x1[HD];
@@ -747,15 +799,56 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
             tc::tmem_ld16(tmem_base + lane_off + C_D2 + 32, nx);
             tc::tmem_ld16(tmem_base + lane_off + C_D2 + 48, nh);
             tc::tmem_ld_wait();
-#pragma unroll
-            for(int j = 0; j < HD; j++) nx[j] = tanh_of_scaled((nx[j] + bias[32 + j]) + (nh[j] + bias[48 + j]) * sigmoid_of_scaled(r[j] + bias[j]));   // scaled image
             float z[HD], hh[HD], hl[HD];
-            tc::tmem_ld16(tmem_base + lane_off + C_D2 + 16, z);
-            tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
-            tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
-            tc::tmem_ld_wait();
+            if constexpr(B200L2F_TMEM_PREFETCH){   // in flight while the MUFU chain below runs
+                tc::tmem_ld16(tmem_base + lane_off + C_D2 + 16, z);
+                tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
+                tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+            }
+            if constexpr(B200L2F_GATES_PACKED){
+                // two hidden units per packed instruction; each lane of FADD2 / FFMA2 rounds like the scalar instruction, so the bits are those of
+                // the scalar form below
+                const float2 one2 = make_float2(1.0f, 1.0f), minus2 = make_float2(-2.0f, -2.0f);
 #pragma unroll
-            for(int j = 0; j < HD; j++){ const float zz = sigmoid_of_scaled(z[j] + bias[16 + j]); hn[j] = fmaf(zz, (hh[j] + hl[j]) - nx[j], nx[j]); }   // (1 - z) n + z h
+                for(int j = 0; j < HD; j += 2){
+                    const float2 b_r = *reinterpret_cast<const float2*>(bias + j), b_x = *reinterpret_cast<const float2*>(bias + 32 + j), b_h = *reinterpret_cast<const float2*>(bias + 48 + j);
+                    const float2 tr = __fadd2_rn(make_float2(r[j], r[j + 1]), b_r);
+                    const float2 dr = __fadd2_rn(one2, make_float2(ex2_approx(tr.x), ex2_approx(tr.y)));
+                    const float2 sg = make_float2(rcp_approx(dr.x), rcp_approx(dr.y));
+                    const float2 tn = __ffma2_rn(__fadd2_rn(make_float2(nh[j], nh[j + 1]), b_h), sg, __fadd2_rn(make_float2(nx[j], nx[j + 1]), b_x));
+                    const float2 dn = __fadd2_rn(make_float2(ex2_approx(tn.x), ex2_approx(tn.y)), one2);
+                    const float2 nn = __ffma2_rn(minus2, make_float2(rcp_approx(dn.x), rcp_approx(dn.y)), one2);
+                    nx[j] = nn.x; nx[j + 1] = nn.y;
+                }
+            }
+            else{
+#pragma unroll
+                for(int j = 0; j < HD; j++) nx[j] = tanh_of_scaled((nx[j] + bias[32 + j]) + (nh[j] + bias[48 + j]) * sigmoid_of_scaled(r[j] + bias[j]));   // scaled image
+            }
+            if constexpr(!B200L2F_TMEM_PREFETCH){
+                tc::tmem_ld16(tmem_base + lane_off + C_D2 + 16, z);
+                tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
+                tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+            }
+            tc::tmem_ld_wait();
+            if constexpr(B200L2F_GATES_PACKED){
+                const float2 one2 = make_float2(1.0f, 1.0f);
+#pragma unroll
+                for(int j = 0; j < HD; j += 2){
+                    const float2 b_z = *reinterpret_cast<const float2*>(bias + 16 + j);
+                    const float2 tz = __fadd2_rn(make_float2(z[j], z[j + 1]), b_z);
+                    const float2 dz = __fadd2_rn(one2, make_float2(ex2_approx(tz.x), ex2_approx(tz.y)));
+                    const float2 zz = make_float2(rcp_approx(dz.x), rcp_approx(dz.y));
+                    const float2 n2 = make_float2(nx[j], nx[j + 1]);
+                    const float2 h2 = __fadd2_rn(make_float2(hh[j], hh[j + 1]), make_float2(hl[j], hl[j + 1]));
+                    const float2 o = __ffma2_rn(zz, __fadd2_rn(h2, make_float2(-n2.x, -n2.y)), n2);   // (1 - z) n + z h
+                    hn[j] = o.x; hn[j + 1] = o.y;
+                }
+            }
+            else{
+#pragma unroll
+                for(int j = 0; j < HD; j++){ const float zz = sigmoid_of_scaled(z[j] + bias[16 + j]); hn[j] = fmaf(zz, (hh[j] + hl[j]) - nx[j], nx[j]); }   // (1 - z) n + z h
+            }
         }
         // ---- dense 2 (16 -> 4) on the CUDA cores
         float act[4];
@@ -779,7 +872,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        if(Spec::H == 1 || active) env_step_compiled<Spec, false, NOISE, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
+        if(Spec::H == 1 || active) env_step_compiled<Spec, false, NOISE, true, AXIAL>(st, p, d, act, rng, hist_ptr, n, HOIST ? lang_normals : nullptr);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
