@@ -86,6 +86,9 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
 #ifndef B200L2F_HOIST_LANGEVIN
 #define B200L2F_HOIST_LANGEVIN 0   // draw the Langevin target's normals in the shadow of the first MMA round trip (noise-free kernels only); measured -0.8 %
 #endif
+#ifndef B200L2F_TS_CTAS_AXIAL
+#define B200L2F_TS_CTAS_AXIAL 3    // resident CTAs per SM of k_rollout_raptor_ts for axial vehicles: 4 = compact dynamics block (44 floats) + 128 registers
+#endif
 #ifndef B200L2F_PACKED_FP32
 #define B200L2F_PACKED_FP32 1      // packed fp32 (FFMA2 / FADD2 / FMUL2, sm_100) in the default-math kernels; 0 = scalar twins (tuning / bisecting)
 #endif
@@ -102,7 +105,9 @@ enum DynC : int { C_COEF = 0,        // [12] thrust-curve coefficients, rotor r 
                   C_JID = 40,        // diag(J^-1)[3] | termination position threshold
                   C_AF = 44,         // [3][4] force per unit rotor thrust (general vehicle only)
                   C_JOFF = 56, C_JIOFF = 62,   // off-diagonal entries of J, J^-1 in row-major order 01 02 10 12 20 21 (general vehicle only)
+                  C_DIM_AXIAL = 44,  // the axial vehicle's evaluation reads nothing beyond this: a compact block for kernels that need the shared memory
                   C_DIM = 68 };
+static_assert(C_DIM_AXIAL % 4 == 0 && (C_DIM_AXIAL * 8) % 32 == 0 && C_DIM_AXIAL % 32 == 12, "44-word rows: quarter-warp LDS.128 hits banks 0,12,24,4,16,28,8,20 (+0..3)");
 static_assert(C_DIM % 4 == 0 && C_DIM % 32 == 4, "row stride must keep LDS.128 aligned and conflict-free");
 __host__ __device__ constexpr int dyn_j_slot(int base_diag, int base_off, int i, int j){   // where entry (i, j) of J / J^-1 lives in the block
     return i == j ? base_diag + i : base_off + 2 * i + (j > i ? j - 1 : j);
@@ -127,11 +132,12 @@ struct ParamsCompiledT {
         return NC ? __ldg(base + (size_t)i * stride) : base[(size_t)i * stride];
     }
 };
-__device__ __forceinline__ float* dyn_block_of_thread(float* sm_dyn){ return sm_dyn + threadIdx.x * C_DIM; }
+template <int STRIDE = C_DIM>
+__device__ __forceinline__ float* dyn_block_of_thread(float* sm_dyn){ return sm_dyn + threadIdx.x * STRIDE; }
 using ParamsCompiled = ParamsCompiledT<false>;
 // compile this thread's dynamics block from any parameter accessor P(i) (HBM column, register overlay, ...)
-template <class F>
-__device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F&& P){   // sm = dyn_block_of_thread(sm_dyn)
+template <bool FULL = true, class F>
+__device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F&& P){   // sm = dyn_block_of_thread(sm_dyn); FULL = false: axial entries only
 #pragma unroll
     for(int i = 0; i < 12; i++) sm[C_COEF + i] = P(P_THRUST_COEF + i);
 #pragma unroll
@@ -139,7 +145,7 @@ __device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F
         const float dx = P(P_THRUST_DIR + 3 * r), dy = P(P_THRUST_DIR + 3 * r + 1), dz = P(P_THRUST_DIR + 3 * r + 2);
         const float px = P(P_ROTOR_POS + 3 * r), py = P(P_ROTOR_POS + 3 * r + 1), pz = P(P_ROTOR_POS + 3 * r + 2);
         const float kq = P(P_TORQUE_CONST + r);
-        sm[C_AF + 0 * 4 + r] = dx; sm[C_AF + 1 * 4 + r] = dy; sm[C_AF + 2 * 4 + r] = dz;
+        if constexpr(FULL){ sm[C_AF + 0 * 4 + r] = dx; sm[C_AF + 1 * 4 + r] = dy; sm[C_AF + 2 * 4 + r] = dz; }
         // torque of rotor r per unit thrust: torque_dir * k_q + r x dir   (60_dynamics.h:38-39)
         sm[C_AT + 0 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 0) * kq + (py * dz - pz * dy);
         sm[C_AT + 1 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 1) * kq + (pz * dx - px * dz);
@@ -153,17 +159,19 @@ __device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F
     for(int i = 0; i < 3; i++){
 #pragma unroll
         for(int j = 0; j < 3; j++){
-            sm[dyn_j_slot(C_JD, C_JOFF, i, j)] = P(P_J + 3 * i + j);
-            sm[dyn_j_slot(C_JID, C_JIOFF, i, j)] = P(P_JINV + 3 * i + j);
+            if(FULL || i == j){
+                sm[dyn_j_slot(C_JD, C_JOFF, i, j)] = P(P_J + 3 * i + j);
+                sm[dyn_j_slot(C_JID, C_JIOFF, i, j)] = P(P_JINV + 3 * i + j);
+            }
         }
     }
     sm[C_G + 3] = P(P_ACT_MIN); sm[C_JD + 3] = P(P_ACT_MAX); sm[C_JID + 3] = P(P_TERM_POS);
 }
-template <bool UNIFORM, bool NC = true, bool FOLLOW = false>
+template <bool UNIFORM, bool NC = true, bool FOLLOW = false, int STRIDE = C_DIM>
 __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env, const float* row0){
-    float* sm = dyn_block_of_thread(sm_dyn);
+    float* sm = dyn_block_of_thread<STRIDE>(sm_dyn);
     const float* g = params + env;
-    compile_dynamics_block(sm, [&](int i){ return NC ? __ldg(g + (size_t)i * n) : g[(size_t)i * n]; });
+    compile_dynamics_block<STRIDE == C_DIM>(sm, [&](int i){ return NC ? __ldg(g + (size_t)i * n) : g[(size_t)i * n]; });
     ParamsCompiledT<UNIFORM, NC, FOLLOW> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
     return p;
 }
@@ -618,15 +626,19 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
 //   lifetimes make the overlaps safe: obs/D1 are dead before x1 is written, x1/h are read by G2 while it writes D2 into [64,128).
 // G1 folds its bias in as K column 22 (= 1.0); G2 has no spare K column (K = 32 exactly), its biases are added in the epilogue.
 // =================================================================================================================================
-struct TsSmem {
+template <bool AXIAL>
+struct TsSmemT {
+    static constexpr int CTAS = AXIAL ? B200L2F_TS_CTAS_AXIAL : 3;            // resident CTAs per SM this variant is built for
+    static constexpr int DSTRIDE = CTAS == 4 ? C_DIM_AXIAL : C_DIM;           // 4 CTAs/SM: 28 KB image + 22.5 KB compact block = 50.6 KB per CTA
     static constexpr int B = 0;                                // weight image (TMA destination)
     static constexpr int DYN = B + TcImage::BYTES;
-    static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
+    static constexpr int BAR = DYN + DSTRIDE * BLOCK * 4;
     static constexpr int TOTAL = BAR + 32;
 };
 // NOISE: observation / action noise (18 + 4 normal draws per step, each skipped when its std is 0) with the MUFU Box-Muller.
 template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false>
-__global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
+__global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
+    using TsSmem = TsSmemT<AXIAL>;
     static_assert(FAST, "the TMEM-A kernel reads the scaled-gate image (build_tc_image_host(..., true)): default math only");
     constexpr int HD = 16;
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -707,7 +719,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_rollout_raptor_ts(const __grid_con
     const int e = tile * BLOCK + tid;
     const bool active = e < a.n;
     const size_t env = active ? (size_t)e : 0;
-    const ParamsCompiledT<UNIFORM> p = stage_dynamics_compiled<UNIFORM>(sm_dyn, a.params, n, env, a.row0);
+    const ParamsCompiledT<UNIFORM> p = stage_dynamics_compiled<UNIFORM, true, false, TsSmem::DSTRIDE>(sm_dyn, a.params, n, env, a.row0);
     EnvState<Spec> st;
     load_state_cg(st, a.state + env, n);
     DynInvariants d;

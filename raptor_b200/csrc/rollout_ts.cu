@@ -8,6 +8,7 @@ namespace {
 template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false>
 int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
     auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL, NOISE>;
+    using TsSmem = TsSmemT<AXIAL>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -17,7 +18,7 @@ int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, TsSmem::TOTAL));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] k_rollout_raptor_ts: occupancy API reports %d CTAs/SM on %d SMs\n", per_sm, sms);
-        if(per_sm < 3) per_sm = 3;           // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
+        if(per_sm < TsSmem::CTAS) per_sm = TsSmem::CTAS;   // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
         capacity[dev] = per_sm * sms;        // co-resident CTAs (3 x 148 = 444 on B200)
         configured[dev] = true;
     }
