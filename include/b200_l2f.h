@@ -250,6 +250,27 @@ typedef struct {
     int32_t* current_episode_start; /* [n_envs] */
 } b200l2f_replay_buffers;
 int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, int32_t sample_parameters, const b200l2f_replay_buffers* rb);
+/* gather_batch for SEQUENCE_LENGTH = 1 (the MLP SAC configuration, pre_training/config.h:19,52-58): the learner-side read of the rings,
+ * INC/rl/components/off_policy_runner/operations_generic.h:240-434 with one RNG stream per batch sample (operations_cuda.h:36-60): sample b draws its
+ * environment env_begin + uniform_int(0, env_count - 1) (env_begin / env_count select one runner's group of environments, e.g. one teacher), then its
+ * ring offset; max_episode_length = ENVIRONMENT::EPISODE_STEP_LIMIT (full rings are read from position + max_episode_length on, :300-303).
+ * Outputs in the SequentialBatch layout (off_policy_runner.h:96-141): observations_actions [2][B][OBS + 4] (step 0 = obs | action, step 1 = next_obs | 0),
+ * rewards / terminated [B], masks as the reference fills them for this configuration.  rng_states [B] in/out, memory space of the batch (= of the rings). */
+typedef struct {
+    int32_t memspace;                /* B200L2F_HOST / B200L2F_DEVICE for all pointers below and for rng_states */
+    int32_t batch_size;
+    float*   observations_actions;   /* [2][B][OBS + 4] */
+    float*   rewards;                /* [B] */
+    uint8_t* terminated;             /* [B] */
+    uint8_t* reset;                  /* [B]    = 1, may be NULL */
+    uint8_t* next_reset;             /* [2][B] = 1, may be NULL */
+    uint8_t* final_step_mask;        /* [B]    = 1, may be NULL */
+    uint8_t* next_final_step_mask;   /* [2][B] = {0, 1}, may be NULL */
+    int32_t* env_index;              /* [B] which ring, may be NULL */
+    int32_t* sample_index;           /* [B] which row, may be NULL */
+} b200l2f_batch;
+int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, int32_t max_episode_length, int32_t env_begin, int32_t env_count, uint64_t* rng_states,
+                         const b200l2f_batch* out);
 int b200l2f_runner_get_state(b200l2f_handle* h, int32_t* episode_step, float* episode_return, uint8_t* truncated, int memspace);
 int b200l2f_runner_set_state(b200l2f_handle* h, const int32_t* episode_step, const float* episode_return, const uint8_t* truncated, int memspace);
 

@@ -185,6 +185,7 @@ class Port(_Common):
         L.oracle_rollout.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, f32, f32, u64, vp, vp, c_int, vp, vp, vp, vp, vp]
         L.oracle_collect.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, f32, c_int]
         L.oracle_off_policy_steps.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.oracle_gather_batch.argtypes = [c_int, c_int, c_int, c_int, c_int, f32, vp, vp, c_int, u64, f32, f32, vp, vp, vp, vp, vp, vp, vp]
         L.oracle_evaluate_values.argtypes = [ctypes.POINTER(OraclePolicy), c_int, c_int, f32, c_int]
         L.oracle_estimate_generalized_advantages.argtypes = [c_int, c_int, f32, c_int, c_float, c_float, c_int]
         L.oracle_normalizer_update.argtypes = [c_int, c_int, f32, c_int, f32, f32, ctypes.POINTER(c_int)]
@@ -243,6 +244,18 @@ class Port(_Common):
                                          _ptr(runner["position"]), _ptr(runner["full"]), _ptr(runner["current_episode_start"]), _ptr(runner.get("states")), _ptr(runner.get("next_states")))
         return runner
 
+    def gather_batch(self, runner, rngs, max_episode_length, env_begin=0, env_count=None):
+        """SEQUENCE_LENGTH-1 batch from the replay rings of `runner`, one RNG stream per sample (rngs [B], advanced in place)"""
+        n, capacity, D = runner["replay"].shape
+        obs = (D - 7) // 2
+        B = rngs.shape[0]
+        out = dict(observations_actions=np.zeros((2, B, obs + 4), np.float32), rewards=np.zeros(B, np.float32), terminated=np.zeros(B, np.uint8), reset=np.zeros(B, np.uint8),
+                   next_reset=np.zeros((2, B), np.uint8), final_step_mask=np.zeros(B, np.uint8), next_final_step_mask=np.zeros((2, B), np.uint8),
+                   env_index=np.zeros(B, np.int32), sample_index=np.zeros(B, np.int32))
+        self.lib.oracle_gather_batch(obs, capacity, max_episode_length, env_begin, n if env_count is None else env_count, runner["replay"], _ptr(runner["position"]), _ptr(runner["full"]),
+                                     B, rngs, out["observations_actions"], out["rewards"], *[_ptr(out[k]) for k in ("terminated", "reset", "next_reset", "final_step_mask", "next_final_step_mask", "env_index", "sample_index")])
+        return out
+
     def evaluate_values(self, critic, data, n, T):
         """critic values over all (T+1)*n observation rows -> the all_values column, in place"""
         self.lib.oracle_evaluate_values(ctypes.byref(critic), n, T, data, data.shape[1])
@@ -300,6 +313,8 @@ class Ref(_Common):
             L.ref_normalizer_update.argtypes = [c_int, f32, f32, f32, ctypes.POINTER(c_int)]
         if hasattr(L, "ref_off_policy_steps"):
             L.ref_off_policy_steps.argtypes = [c_int, c_int, f32, f32, f32, f32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        if hasattr(L, "ref_gather_batch"):
+            L.ref_gather_batch.argtypes = [f32, vp, vp, u64, f32, f32, vp, vp, vp, vp, vp]
         if hasattr(L, "ref_dagger_add_to_dataset"):
             u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
             i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -393,6 +408,17 @@ class Ref(_Common):
                                            _ptr(runner["position"]), _ptr(runner["full"]), _ptr(runner["current_episode_start"]), _ptr(runner.get("states")), _ptr(runner.get("next_states")))
         assert rc == 0, "ref_off_policy_steps: spec not instantiated"
         return runner
+
+    def gather_batch(self, runner, rngs):
+        """the reference's gather_batch_step on its own SequentialBatch (SEQUENCE_LENGTH 1, batch ref_gather_batch_size()) over the rings of `runner`"""
+        B = self.lib.ref_gather_batch_size()
+        assert rngs.shape[0] == B
+        obs = (runner["replay"].shape[2] - 7) // 2
+        out = dict(observations_actions=np.zeros((2, B, obs + 4), np.float32), rewards=np.zeros(B, np.float32), terminated=np.zeros(B, np.uint8), reset=np.zeros(B, np.uint8),
+                   next_reset=np.zeros((2, B), np.uint8), final_step_mask=np.zeros(B, np.uint8), next_final_step_mask=np.zeros((2, B), np.uint8))
+        self.lib.ref_gather_batch(runner["replay"], _ptr(runner["position"]), _ptr(runner["full"]), rngs, out["observations_actions"], out["rewards"],
+                                  *[_ptr(out[k]) for k in ("terminated", "reset", "next_reset", "final_step_mask", "next_final_step_mask")])
+        return out
 
     # ---- checkpoint code export: the reference's own save_code (kind 1 = SAC teacher MLP + sample_and_squash, 2 = PPO standardize + MLP + log_std)
     def save_code(self, kind, blob, has_std=0, name="fixture"):

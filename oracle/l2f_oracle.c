@@ -950,6 +950,45 @@ void oracle_off_policy_steps(int spec, const oracle_policy_t* pol, int N, int T,
     }
 }
 
+/* gather_batch for SEQUENCE_LENGTH = 1 (the MLP SAC configuration, pre_training/config.h:19,52-58: no random sequence length, not from the initial
+ * state): INC/rl/components/off_policy_runner/operations_generic.h:240-420 (gather_batch_step) with the environment drawn per sample as in
+ * :423-434 / the CUDA kernel operations_cuda.h:36-60 (one RNG stream per batch sample: env_i = uniform_int(0, N - 1), then the sample offset).
+ * uniform_int = next(state) % range (INC/random/operations_generic.h:43-50).  Outputs in the SequentialBatch layout (off_policy_runner.h:96-141):
+ *   observations_actions [2][B][OBS + 4]: step 0 = obs | action, step 1 = next_obs | 0;  rewards / terminated [B];
+ *   reset [B] = 1, next_reset [2][B] = {1, 1} (base row 0 by :287,303; row 1 through the `next_reset` view, whose offset is 1 when the first step is
+ *   not a target, :288 with :86-92), final_step_mask [B] = 1, next_final_step_mask [2][B] = {0, 1}  (any of the masks may be NULL).
+ * env_begin / env_count select the runner's environments (one teacher's group); env_index / sample_index [B] (optional) report the draw. */
+static uint64_t rng_next_state(uint64_t* s){ rng_next(s); return *s; }
+void oracle_gather_batch(int obs_dim, int capacity, int max_episode_length, int env_begin, int env_count, const float* replay, const int* position, const unsigned char* full,
+                         int B, uint64_t* rng_states, float* observations_actions, float* rewards, unsigned char* terminated,
+                         unsigned char* reset, unsigned char* next_reset, unsigned char* final_step_mask, unsigned char* next_final_step_mask,
+                         int* env_index, int* sample_index_out){
+    const int OBS = obs_dim, D = 2 * OBS + 7, W = OBS + 4;
+    for(int b = 0; b < B; b++){
+        uint64_t* rng = rng_states + b;
+        const int env = env_begin + (int)(rng_next_state(rng) % (uint64_t)env_count);
+        const float* rb = replay + (size_t)env * capacity * D;
+        const int is_full = full[env], pos = position[env];
+        const uint64_t eligible = is_full ? (uint64_t)capacity : (uint64_t)pos;
+        const uint64_t offset = rng_next_state(rng) % eligible;                 /* uniform_int(0, eligible - 1) */
+        const int sample = is_full ? (int)(((uint64_t)pos + (uint64_t)max_episode_length + offset) % (uint64_t)capacity) : (int)offset;
+        const float* row = rb + (size_t)sample * D;
+        float* o0 = observations_actions + (size_t)b * W;
+        float* o1 = observations_actions + ((size_t)B + b) * W;
+        memcpy(o0, row, sizeof(float) * W);                                      /* obs | action */
+        memcpy(o1, row + OBS + 5, sizeof(float) * OBS);                          /* next_obs */
+        for(int i = 0; i < 4; i++) o1[OBS + i] = 0;                              /* next action = 0 (:408-410) */
+        rewards[b] = row[OBS + 4];
+        terminated[b] = row[2 * OBS + 5] != 0;
+        if(reset) reset[b] = 1;
+        if(next_reset){ next_reset[b] = 1; next_reset[B + b] = 1; }
+        if(final_step_mask) final_step_mask[b] = 1;
+        if(next_final_step_mask){ next_final_step_mask[b] = 0; next_final_step_mask[B + b] = 1; }
+        if(env_index) env_index[b] = env;
+        if(sample_index_out) sample_index_out[b] = sample;
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------
  * learner feed of the PPO loop step (INC/rl/algorithms/ppo/loop/core/operations_generic.h:104-117): critic values over
  * all_observations -> all_values column, generalized advantage estimation, running observation normalizer.

@@ -77,6 +77,11 @@ void oracle_off_policy_steps(int spec, const oracle_policy_t* pol, int N, int T,
                              float* params_io, float* states_io, uint64_t* rng_states, int* episode_step_io, float* episode_return_io, unsigned char* truncated_io,
                              float* replay, int* episode_start, int* position_io, unsigned char* full_io, int* current_episode_start_io,
                              float* states_out, float* next_states_out);
+/* gather_batch of the off-policy runner for SEQUENCE_LENGTH = 1; layout documented in l2f_oracle.c */
+void oracle_gather_batch(int obs_dim, int capacity, int max_episode_length, int env_begin, int env_count, const float* replay, const int* position, const unsigned char* full,
+                         int B, uint64_t* rng_states, float* observations_actions, float* rewards, unsigned char* terminated,
+                         unsigned char* reset, unsigned char* next_reset, unsigned char* final_step_mask, unsigned char* next_final_step_mask,
+                         int* env_index, int* sample_index_out);
 /* learner feed (PPO loop step between collect and train): critic values, GAE, running observation normalizer */
 void oracle_evaluate_values(const oracle_policy_t* critic, int N, int T, float* dataset, int data_dim);
 void oracle_estimate_generalized_advantages(int N, int T, float* dataset, int data_dim, float gamma, float lambda, int ignore_termination);

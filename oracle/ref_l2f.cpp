@@ -1113,7 +1113,64 @@ namespace ref_opr{
         delete runner_ptr;
     }
 }
+namespace ref_opr{
+    constexpr TI BATCH = 64;
+    struct BATCH_PARAMETERS{   // pre_training/config.h:52-58
+        static constexpr bool INCLUDE_FIRST_STEP_IN_TARGETS = false;
+        static constexpr bool ALWAYS_SAMPLE_FROM_INITIAL_STATE = false;
+        static constexpr bool RANDOM_SEQ_LENGTH = false;
+        static constexpr bool ENABLE_NOMINAL_SEQUENCE_LENGTH_PROBABILITY = true;
+        static constexpr T NOMINAL_SEQUENCE_LENGTH_PROBABILITY = 0.1;
+    };
+    // the reference's gather_batch_step (operations_generic.h:240-420) on its own SequentialBatch with the MLP SAC settings (SEQUENCE_LENGTH 1,
+    // pre_training/config.h:52-58), one RNG stream per batch sample and the environment drawn from that stream first (operations_cuda.h:36-60)
+    template <typename ENV>
+    static void gather(const float* replay, const int* position_in, const unsigned char* full_in, uint64_t* rng_states, float* observations_actions, float* rewards,
+                       unsigned char* terminated, unsigned char* reset, unsigned char* next_reset, unsigned char* final_step_mask, unsigned char* next_final_step_mask){
+        using RS = RunnerSpec<ENV, true>;
+        using RUNNER = typename RS::RUNNER;
+        using BATCH_SPEC = rlt::rl::components::off_policy_runner::SequentialBatchSpecification<typename RS::SPEC, 1, BATCH, BATCH_PARAMETERS, true>;
+        constexpr TI OBS = ENV::Observation::DIM, D = RUNNER::REPLAY_BUFFER_TYPE::DATA_COLS, W = OBS + 4;
+        DEVICE device;
+        auto* runner_ptr = new RUNNER(); RUNNER& runner = *runner_ptr;
+        rlt::malloc(device, runner);
+        rlt::init(device, runner);
+        rlt::rl::components::off_policy_runner::SequentialBatch<BATCH_SPEC> batch;
+        rlt::malloc(device, batch);
+        for(TI e = 0; e < N; e++){
+            auto& rb = rlt::get(runner.replay_buffers, 0, e);
+            for(TI r = 0; r < CAPACITY; r++) for(TI c = 0; c < D; c++) rlt::set(rb.data, r, c, replay[(e * CAPACITY + r) * D + c]);
+            rb.position = position_in[e]; rb.full = full_in[e] != 0;
+        }
+        for(TI b = 0; b < BATCH; b++){
+            RNG rng; rng.state = rng_states[b];
+            TI env_i = rlt::random::uniform_int_distribution(typename DEVICE::SPEC::RANDOM(), (TI)0, (TI)(N - 1), rng);
+            auto& rb = rlt::get(runner.replay_buffers, 0, env_i);
+            rlt::gather_batch_step<false>(device, runner, rb, batch, b, rng);
+            rng_states[b] = rng.state;
+        }
+        for(TI s = 0; s < 2; s++) for(TI b = 0; b < BATCH; b++){
+            for(TI c = 0; c < W; c++) observations_actions[(s * BATCH + b) * W + c] = rlt::get(device, batch.observations_actions_base, s, b, c);
+            next_reset[s * BATCH + b] = rlt::get(device, batch.next_reset_base, s, b, 0) ? 1 : 0;
+            next_final_step_mask[s * BATCH + b] = rlt::get(device, batch.next_final_step_mask_base, s, b, 0) ? 1 : 0;
+        }
+        for(TI b = 0; b < BATCH; b++){
+            rewards[b] = rlt::get(device, batch.rewards, 0, b, 0);
+            terminated[b] = rlt::get(device, batch.terminated, 0, b, 0) ? 1 : 0;
+            reset[b] = rlt::get(device, batch.reset, 0, b, 0) ? 1 : 0;
+            final_step_mask[b] = rlt::get(device, batch.final_step_mask, 0, b, 0) ? 1 : 0;
+        }
+        rlt::free(device, batch); rlt::free(device, runner);
+        delete runner_ptr;
+    }
+}
 extern "C" {
+int ref_gather_batch_size(){ return ref_opr::BATCH; }
+int ref_gather_batch_max_episode_length(){ return (int)ENV_TEACHER::EPISODE_STEP_LIMIT; }
+void ref_gather_batch(const float* replay, const int* position, const unsigned char* full, uint64_t* rng_states, float* observations_actions, float* rewards,
+                      unsigned char* terminated, unsigned char* reset, unsigned char* next_reset, unsigned char* final_step_mask, unsigned char* next_final_step_mask){
+    ref_opr::gather<ENV_TEACHER>(replay, position, full, rng_states, observations_actions, rewards, terminated, reset, next_reset, final_step_mask, next_final_step_mask);
+}
 void ref_off_policy_sizes(int* n, int* steps, int* step_limit, int* capacity){ *n = ref_opr::N; *steps = ref_opr::STEPS; *step_limit = ref_opr::STEP_LIMIT; *capacity = ref_opr::CAPACITY; }
 // spec: 3 (TEACHER) or 5 (TEACHER_DR); sample_parameters = OffPolicyRunner PARAMETERS::SAMPLE_PARAMETERS
 int ref_off_policy_steps(int spec, int sample_parameters, const float* actor_blob, const float* env_params, float* params_io, float* states_io, uint64_t* rng_states,

@@ -37,6 +37,11 @@ class ReplayBuffers(ctypes.Structure):
     _fields_ = [("memspace", c_i32), ("capacity", c_i32), ("data", vp), ("episode_start", vp), ("position", vp), ("full", vp), ("current_episode_start", vp)]
 
 
+class Batch(ctypes.Structure):
+    _fields_ = [("memspace", c_i32), ("batch_size", c_i32), ("observations_actions", vp), ("rewards", vp), ("terminated", vp), ("reset", vp), ("next_reset", vp),
+                ("final_step_mask", vp), ("next_final_step_mask", vp), ("env_index", vp), ("sample_index", vp)]
+
+
 class DaggerOut(ctypes.Structure):
     _fields_ = [("memspace", c_i32), ("reserved", c_i32), ("capacity_rows", c_i64), ("input_student", vp), ("output_target", vp), ("truncated", vp),
                 ("reset", vp), ("episode_start", vp), ("returns", vp), ("episode_length", vp)]
@@ -97,6 +102,7 @@ SYMBOLS = {
     "b200l2f_checkpoint_string": (ctypes.c_char_p, [vp, ctypes.c_char_p]),
     "b200l2f_checkpoint_policy": (c_int, [vp, ctypes.c_char_p, ctypes.POINTER(PolicyDesc), vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "b200l2f_off_policy_steps": (c_int, [vp, c_i32, c_i32, c_i32, ctypes.POINTER(ReplayBuffers)]),
+    "b200l2f_gather_batch": (c_int, [vp, ctypes.POINTER(ReplayBuffers), c_i32, c_i32, c_i32, vp, ctypes.POINTER(Batch)]),
     "b200l2f_runner_get_state": (c_int, [vp, vp, vp, vp, c_int]),
     "b200l2f_runner_set_state": (c_int, [vp, vp, vp, vp, c_int]),
     "b200l2f_teachers_load": (c_int, [vp, c_i32, c_i32, vp, vp, c_i32]),

@@ -133,4 +133,65 @@ int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode
     return B200L2F_OK;
 }
 
+int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, int32_t max_episode_length, int32_t env_begin, int32_t env_count, uint64_t* rng_states,
+                         const b200l2f_batch* out){
+    if(!h) return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch: null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if(!rb || !out || !rng_states || !rb->data || !rb->position || !rb->full || rb->capacity < 1 || out->batch_size < 0 || !out->observations_actions || !out->rewards || !out->terminated)
+        return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch: bad arguments");
+    if(rb->memspace != out->memspace) return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch: replay buffers and batch must live in the same memory space");
+    if(env_begin < 0 || env_count < 1 || env_begin + env_count > h->n) return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch: environment range outside the handle");
+    const int B = out->batch_size, OBS = h->obs_dim, D = 2 * OBS + 7, W = OBS + 4;
+    if(B == 0) return B200L2F_OK;
+    const size_t n = (size_t)h->n;
+    const bool host = rb->memspace == B200L2F_HOST;
+    // host memory: temporary device copies (tests / small runners); device memory is used in place
+    struct Part { const void* user_in; void* user_out; size_t bytes; void* dev; };
+    Part parts[12] = {
+        {rb->data, nullptr, sizeof(float) * n * rb->capacity * D, nullptr}, {rb->position, nullptr, sizeof(int32_t) * n, nullptr}, {rb->full, nullptr, n, nullptr},
+        {rng_states, rng_states, sizeof(uint64_t) * B, nullptr},
+        {nullptr, out->observations_actions, sizeof(float) * 2 * B * W, nullptr}, {nullptr, out->rewards, sizeof(float) * B, nullptr}, {nullptr, out->terminated, (size_t)B, nullptr},
+        {nullptr, out->reset, (size_t)B, nullptr}, {nullptr, out->next_reset, (size_t)2 * B, nullptr}, {nullptr, out->final_step_mask, (size_t)B, nullptr},
+        {nullptr, out->next_final_step_mask, (size_t)2 * B, nullptr}, {nullptr, nullptr, 0, nullptr}};
+    Part extra[2] = {{nullptr, out->env_index, sizeof(int32_t) * B, nullptr}, {nullptr, out->sample_index, sizeof(int32_t) * B, nullptr}};
+    std::vector<Part*> all;
+    for(auto& p : parts) all.push_back(&p);
+    for(auto& p : extra) all.push_back(&p);
+    auto release = [&](){ if(host) for(auto* p : all) if(p->dev) cudaFree(p->dev); };
+    for(auto* p : all){
+        const void* any = p->user_in ? p->user_in : p->user_out;
+        if(!any || !p->bytes) continue;
+        if(!host){ p->dev = const_cast<void*>(any); continue; }
+        cudaError_t e = cudaMalloc(&p->dev, p->bytes);
+        if(e == cudaSuccess && p->user_in) e = cudaMemcpyAsync(p->dev, p->user_in, p->bytes, cudaMemcpyHostToDevice, h->stream);
+        if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: staging: ") + cudaGetErrorString(e)); }
+    }
+    if(host) cudaStreamSynchronize(h->stream);
+    CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
+    GatherArgs a{};
+    a.replay = (const float*)parts[0].dev; a.position = (const int*)parts[1].dev; a.full = (const uint8_t*)parts[2].dev;
+    a.obs_dim = OBS; a.capacity = rb->capacity; a.max_episode_length = max_episode_length; a.env_begin = env_begin; a.env_count = env_count; a.batch = B;
+    a.rng = (uint64_t*)parts[3].dev; a.observations_actions = (float*)parts[4].dev; a.rewards = (float*)parts[5].dev; a.terminated = (uint8_t*)parts[6].dev;
+    a.reset = (uint8_t*)parts[7].dev; a.next_reset = (uint8_t*)parts[8].dev; a.final_step_mask = (uint8_t*)parts[9].dev; a.next_final_step_mask = (uint8_t*)parts[10].dev;
+    a.env_index = (int*)extra[0].dev; a.sample_index = (int*)extra[1].dev; a.error_flag = h->d_flags;
+    k_gather_batch<<<grid_for(B * 32, 256), 256, 0, h->stream>>>(a);
+    h->launches++;
+    cudaError_t le = cudaGetLastError();
+    if(le != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le)); }
+    if(host){
+        for(auto* p : all){
+            if(!p->dev || !p->user_out) continue;
+            cudaError_t e = cudaMemcpyAsync(p->user_out, p->dev, p->bytes, cudaMemcpyDeviceToHost, h->stream);
+            if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: reading back: ") + cudaGetErrorString(e)); }
+        }
+    }
+    int flag = 0;
+    cudaError_t e = cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    release();
+    if(e != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: ") + cudaGetErrorString(e));
+    if(flag) return fail(h, B200L2F_ERR_STATE, "gather_batch: Replay buffer requires at least one element");
+    return B200L2F_OK;
+}
+
 }  // extern "C"

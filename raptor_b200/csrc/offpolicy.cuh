@@ -64,6 +64,62 @@ __device__ __forceinline__ void ring_advance(Ring& rg, int capacity, bool trunca
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// gather_batch for SEQUENCE_LENGTH = 1 (the MLP SAC configuration): INC/rl/components/off_policy_runner/operations_generic.h:240-420 with the
+// environment drawn per sample (:423-434; one RNG stream per batch sample like operations_cuda.h:36-60).  One warp per sample: lane 0 draws
+// (environment, ring offset) -- uniform_int = next(state) % range, INC/random/operations_generic.h:43-50 -- the warp copies the 236-byte row.
+// ---------------------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    const float* replay; const int* position; const uint8_t* full;
+    int obs_dim, capacity, max_episode_length, env_begin, env_count, batch;
+    uint64_t* rng;
+    float* observations_actions; float* rewards; uint8_t* terminated;
+    uint8_t* reset; uint8_t* next_reset; uint8_t* final_step_mask; uint8_t* next_final_step_mask;
+    int* env_index; int* sample_index;
+    int* error_flag;
+};
+__global__ void __launch_bounds__(256) k_gather_batch(const GatherArgs a){
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(b >= a.batch) return;
+    const int OBS = a.obs_dim, D = 2 * OBS + 7, W = OBS + 4;
+    int env = 0, sample = -1;
+    if(lane == 0){
+        uint64_t s = a.rng[b];
+        rng_next(s);
+        env = a.env_begin + (int)(s % (uint64_t)a.env_count);
+        const bool is_full = a.full[env] != 0;
+        const int pos = a.position[env];
+        const uint64_t eligible = is_full ? (uint64_t)a.capacity : (uint64_t)pos;
+        if(eligible == 0) atomicExch(a.error_flag, 1);           // "Replay buffer requires at least one element" (:252)
+        else{
+            rng_next(s);
+            const uint64_t offset = s % eligible;
+            sample = is_full ? (int)(((uint64_t)pos + (uint64_t)a.max_episode_length + offset) % (uint64_t)a.capacity) : (int)offset;
+        }
+        a.rng[b] = s;
+    }
+    env = __shfl_sync(0xffffffffu, env, 0);
+    sample = __shfl_sync(0xffffffffu, sample, 0);
+    if(sample < 0) return;
+    const float* row = a.replay + ((size_t)env * a.capacity + sample) * D;
+    float* o0 = a.observations_actions + (size_t)b * W;
+    float* o1 = a.observations_actions + ((size_t)a.batch + b) * W;
+    for(int i = lane; i < W; i += 32){
+        o0[i] = row[i];                                          // obs | action
+        o1[i] = i < OBS ? row[OBS + 5 + i] : 0.0f;               // next_obs | next action = 0 (:408-410)
+    }
+    if(lane == 0){
+        a.rewards[b] = row[OBS + 4];
+        a.terminated[b] = row[2 * OBS + 5] != 0.0f ? 1 : 0;
+        if(a.reset) a.reset[b] = 1;
+        if(a.next_reset){ a.next_reset[b] = 1; a.next_reset[a.batch + b] = 1; }
+        if(a.final_step_mask) a.final_step_mask[b] = 1;
+        if(a.next_final_step_mask){ a.next_final_step_mask[b] = 0; a.next_final_step_mask[a.batch + b] = 1; }
+        if(a.env_index) a.env_index[b] = env;
+        if(a.sample_index) a.sample_index[b] = sample;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // actor on fp32 CUDA cores (B200L2F_GEMM_FP32_CUDA_CORES, B200L2F_FLAG_ACCURATE_MATH): structure of k_collect (mlp.cuh)
 // ---------------------------------------------------------------------------------------------------------------
 template <class Spec, bool DR>

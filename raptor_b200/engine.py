@@ -331,6 +331,39 @@ class VectorEnvironment:
         self._check(self._lib.b200l2f_off_policy_steps(self._h, n_steps, episode_step_limit, int(sample_parameters), ctypes.byref(rb)))
         return replay
 
+    def gather_batch(self, replay, rng_states, max_episode_length=500, env_begin=0, env_count=None, out=None):
+        """SEQUENCE_LENGTH-1 batch (rl_tools::gather_batch) from the replay rings: rng_states [B] uint64 (numpy) / int64 (torch CUDA), advanced in place;
+        returns dict(observations_actions [2, B, OBS+4], rewards, terminated, reset, next_reset, final_step_mask, next_final_step_mask, env_index, sample_index)"""
+        n, obs = self.N_ENVIRONMENTS, self.OBSERVATION_DIM
+        capacity = replay["data"].shape[1]
+        pd, ms, _ = _arg(replay["data"], np.float32, (n, capacity, 2 * obs + 7), "replay.data")
+        pp, m1, _ = _arg(replay["position"], np.int32, (n,), "replay.position")
+        pf, m2, _ = _arg(replay["full"], np.uint8, (n,), "replay.full")
+        B = int(rng_states.shape[0])
+        pr, m3, _ = _arg(rng_states, np.uint64, (B,), "rng_states")
+        if not (ms == m1 == m2 == m3):
+            raise ValueError("gather_batch: rings and rng_states must live in the same memory space")
+        shapes = dict(observations_actions=((2, B, obs + 4), np.float32), rewards=((B,), np.float32), terminated=((B,), np.uint8), reset=((B,), np.uint8),
+                      next_reset=((2, B), np.uint8), final_step_mask=((B,), np.uint8), next_final_step_mask=((2, B), np.uint8), env_index=((B,), np.int32),
+                      sample_index=((B,), np.int32))
+        if out is None:
+            if ms == L.HOST:
+                out = {k: np.zeros(sh, dt) for k, (sh, dt) in shapes.items()}
+            else:
+                import torch
+                tdt = {np.float32: torch.float32, np.int32: torch.int32, np.uint8: torch.uint8}
+                out = {k: torch.zeros(sh, dtype=tdt[dt], device=rng_states.device) for k, (sh, dt) in shapes.items()}
+        ptrs = []
+        for k, (sh, dt) in shapes.items():
+            p, m, _ = _arg(out.get(k), dt, sh, "batch." + k)
+            if out.get(k) is not None and m != ms:
+                raise ValueError("gather_batch: batch buffers must live in the memory space of the rings")
+            ptrs.append(p)
+        rb = L.ReplayBuffers(ms, capacity, pd, None, pp, pf, None)
+        batch = L.Batch(ms, B, *ptrs)
+        self._check(self._lib.b200l2f_gather_batch(self._h, ctypes.byref(rb), max_episode_length, env_begin, n if env_count is None else env_count, pr, ctypes.byref(batch)))
+        return out
+
     def get_runner_state(self):
         """(episode_step [N] int32, episode_return [N] float32, truncated [N] uint8) of the on-/off-policy runner bookkeeping"""
         n = self.N_ENVIRONMENTS

@@ -518,6 +518,21 @@ def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
     for a_, b_ in zip(order[:-1], order[1:]):
         if e0[a_, D - 1] == 0:
             assert np.array_equal(e0[a_, obs + 5:2 * obs + 5], e0[b_, :obs])
+    # the learner-side read (rl_tools::gather_batch, SEQUENCE_LENGTH 1): a pure gather of the rings, bit-exact vs the oracle on the same rings
+    ring_host = dict(replay=got["data"], position=got["position"], full=got["full"])
+    for (b0, cnt, B_) in ((0, None, 300), (64, 10, 37)):
+        rng_b = port.rng_states(900 + B_, B_, warmup=3)
+        want_b = port.gather_batch(ring_host, rng_b.copy(), 500, env_begin=b0, env_count=cnt)
+        rng_in = torch.from_numpy(rng_b.view(np.int64).copy()).cuda() if on_device else rng_b.copy()
+        got_b = env.gather_batch(replay, rng_in, 500, env_begin=b0, env_count=cnt)
+        for k, v in want_b.items():
+            g_ = got_b[k].cpu().numpy() if on_device else got_b[k]
+            assert np.array_equal(g_, v), k
+        if cnt:
+            assert want_b["env_index"].min() >= b0 and want_b["env_index"].max() < b0 + cnt
+    fresh = env.new_replay_buffers(capacity, device=on_device)
+    with pytest.raises(rb.EngineError, match="at least one element"):
+        env.gather_batch(fresh, torch.zeros(4, dtype=torch.int64, device="cuda") + 12345 if on_device else np.full(4, 12345, np.uint64))
     with pytest.raises(rb.EngineError, match="SAC actor"):
         env.load_policy(random_mlp_blob(rs, obs, 4, False, False), arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=0, head=rb.HEAD_IDENTITY, gemm=g)
         env.off_policy_steps(1, limit, replay)

@@ -265,3 +265,29 @@ def test_off_policy_runner_steps(port, ref, spec, sample_parameters):
     term, trunc = r["replay"][:, :, D - 2], r["replay"][:, :, D - 1]
     assert term.sum() > 0 and (trunc.sum() > term.sum()), "episodes must end by termination and by the step limit"
     assert (np.abs(r["replay"][:, :, obs:obs + 4]) <= 1).all()
+
+
+def test_gather_batch(port, ref):
+    """the learner-side read of the replay rings: SEQUENCE_LENGTH-1 batches (the MLP SAC configuration) against the reference's own gather_batch_step
+    on its own SequentialBatch, from partially filled rings (position 35 < capacity, not full) and from wrapped ones (full)"""
+    n, T, limit, capacity = ref.off_policy_sizes()
+    spec, obs = B.SPEC_TEACHER, 26
+    rs = np.random.RandomState(77)
+    actor = random_mlp_blob(rs, obs, 8, False, False)
+    env_p, params, states, rng = _collect_inputs(ref, spec, n, 19)
+    pol = port.make_policy(actor, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_SAMPLE)
+    runner = B.new_off_policy_runner(n, capacity, obs)
+    Bsz = ref.lib.ref_gather_batch_size()
+    mel = ref.lib.ref_gather_batch_max_episode_length()
+    assert mel == 500
+    for steps in (35, 40):                       # 35 rows per ring, then 75 (wrapped: full)
+        port.off_policy_steps(spec, pol, env_p, params, states, rng, runner, steps, limit)
+        r_a = port.rng_states(1000 + steps, Bsz, warmup=3)
+        r_b = r_a.copy()
+        got = port.gather_batch(runner, r_a, mel)
+        want = ref.gather_batch(runner, r_b)
+        assert np.array_equal(r_a, r_b)
+        for k, v in want.items():
+            assert np.array_equal(got[k], v), (steps, k)
+        assert len(set(got["env_index"].tolist())) > n // 2 and len(set(got["sample_index"].tolist())) > 10
+    assert runner["full"].all()
