@@ -253,6 +253,46 @@ def test_ragged_sizes_and_errors(rb):
         rb.VectorEnvironment(0)
 
 
+@pytest.mark.parametrize("gemm", ["tcgen05", "fp32"])
+def test_runner_edge_cases(rb, port, gemm):
+    """empty and minimal inputs of the runner-style entry points: zero steps leave everything untouched, one environment / ragged tiles / a ring of
+    one row work, and the collection with zero steps writes just the final observations"""
+    g = rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32
+    rs = np.random.RandomState(3)
+    for n in (1, 33):
+        # ---- PPO collection
+        env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR)
+        env.initialize_rng(5, warmup=8); env.initial_parameters(); env.initial_state()
+        env.load_policy(random_mlp_blob(rs, 22, 4, True, True), arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=g)
+        env.collect_reset()
+        rng0, s0 = env.get_rng(), env.get_state()
+        d0 = env.collect(0, 10)
+        assert d0.shape == (n, 37) and np.all(d0[:, 22:] == 0) and np.isfinite(d0).all()
+        assert np.array_equal(env.get_rng(), rng0) and np.array_equal(env.get_state(), s0)       # T = 0: only the final observe (noise-free), no reset
+        d1 = env.collect(1, 1)                                                                    # step limit 1: every step truncates
+        assert d1.shape == (2 * n, 37) and np.all(d1[:n, 33] == 1)
+        # ---- off-policy runner
+        env = rb.VectorEnvironment(n, rb.SPEC_TEACHER)
+        env.initialize_rng(6, warmup=8); env.initial_parameters(); env.initial_state()
+        env.load_policy(random_mlp_blob(rs, 26, 8, False, False), arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=g)
+        env.collect_reset()
+        ring = env.new_replay_buffers(1)                                                          # capacity 1: every add wraps
+        rng0 = env.get_rng()
+        env.off_policy_steps(0, 5, ring)
+        assert np.array_equal(env.get_rng(), rng0) and not ring["full"].any() and np.all(ring["data"] == 0)
+        env.off_policy_steps(3, 5, ring)
+        assert ring["full"].all() and np.all(ring["position"] == 0) and np.all(ring["episode_start"] == 0) and np.isfinite(ring["data"]).all()
+        step, ret, trunc = env.get_runner_state()
+        assert np.all(step == 3) and np.all(trunc == 0)
+        b = env.gather_batch(ring, port.rng_states(1, 5, warmup=3), 500)
+        assert np.all(b["sample_index"] == 0) and np.array_equal(b["observations_actions"][0, :, :26], ring["data"][b["env_index"], 0, :26])
+        env.set_runner_state(truncated=np.ones(n, np.uint8))                                      # truncate_all (operations_generic.h:152-154)
+        env.off_policy_steps(1, 5, ring)
+        assert np.all(env.get_runner_state()[0] == 1)
+        with pytest.raises(ValueError):
+            env.off_policy_steps(1, 5, env.new_replay_buffers(1) | {"data": np.zeros((n, 1, 58), np.float32)})
+
+
 @pytest.mark.parametrize("name,T_cmp", [("default_8x500.npz", 100), ("raptor_dr_64x100.npz", 100)])
 def test_tcgen05_rollout_vs_golden(rb, name, T_cmp):
     """actor GEMMs on the tensor cores (tcgen05, 3xTF32): same 1e-4 closed-loop bound against the reference fixtures"""
