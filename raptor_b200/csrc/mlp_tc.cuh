@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             dyn_invariants(d, o, st);
         }
         float obs[IN];
-        observe_regs<Spec, true>(st, p, rng, obs);
+        observe_regs<Spec, true, true>(st, p, rng, obs);
         float vals[12];
         if(!last){                                        // uniform across the CTA
             float mean[OUT], act[4];
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
 #pragma unroll
             for(int i = 0; i < 4; i++){                   // epilogue (operations_generic_per_env.h:43-58)
                 const float ls = c.sm_b[I::LOG_STD + i];
-                act[i] = rng_normal_t<Spec::RNG_OOL>(rng, mean[i], expf(ls));
+                act[i] = rng_normal_t<Spec::RNG_OOL, true>(rng, mean[i], ex2_approx(ls * LOG2E));   // default math: MUFU Box-Muller / exponential (the integer stream stays bit-exact)
                 lp += normal_log_prob(mean[i], ls, act[i]);
             }
             RewardInputs ri;

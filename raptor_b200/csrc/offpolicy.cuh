@@ -31,13 +31,15 @@ struct OffPolicyArgs {
 };
 
 // sample_and_squash evaluate_per_sample in Mode<Rollout> (INC/nn/layers/sample_and_squash/operations_generic.h:148-194), bounds layer.h:31-32
-template <bool OOL>
+// FAST: default-math arithmetic (MUFU Box-Muller, ex2 / rcp exponential and tanh; the integer stream stays bit-exact)
+template <bool OOL, bool FAST = false>
 __device__ __forceinline__ void squash_sample(const float* __restrict__ o, uint64_t& rng, float* __restrict__ act){
 #pragma unroll
     for(int i = 0; i < 4; i++){
         const float log_std = fminf(fmaxf(o[4 + i], -20.0f), 2.0f);
-        const float noise = rng_normal_t<OOL>(rng, 0.0f, 1.0f);
-        act[i] = tanhf(o[i] + noise * expf(log_std));
+        const float noise = rng_normal_t<OOL, FAST>(rng, 0.0f, 1.0f);
+        if constexpr(FAST) act[i] = tanh_of_scaled((2.0f * LOG2E) * (o[i] + noise * ex2_approx(log_std * LOG2E)));
+        else act[i] = tanhf(o[i] + noise * expf(log_std));
     }
 }
 

@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_off_policy_ts(const __grid_constan
             }
         }
         float obs[IN];
-        observe_regs<Spec, true>(st, p, rng, obs);
+        observe_regs<Spec, true, true>(st, p, rng, obs);
         float o8[OUT], act[4];
         mlp_forward_ts<IN, OUT>(c, obs, o8);
-        squash_sample<Spec::RNG_OOL>(o8, rng, act);        // interlude: evaluate_step in Mode<Rollout>
+        squash_sample<Spec::RNG_OOL, true>(o8, rng, act);  // interlude: evaluate_step in Mode<Rollout>
         RewardInputs ri;                                  // epilogue_per_env (:60-110)
         reward_inputs(ri, st);
         env_step_compiled<Spec, true, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_off_policy_ts(const __grid_constan
         win[lane * 33 + IN + 4] = r;
         stream_phase<IN + 5>(win, row, lane, rows_valid);
         // phase 2: next_obs | terminated | truncated
-        observe_regs<Spec, true>(st, p, rng, obs);
+        observe_regs<Spec, true, true>(st, p, rng, obs);
 #pragma unroll
         for(int i = 0; i < IN; i++) win[lane * 33 + i] = obs[i];
         win[lane * 33 + IN] = term ? 1.0f : 0.0f;

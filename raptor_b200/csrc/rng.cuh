@@ -55,10 +55,12 @@ __device__ __forceinline__ float rng_normal_draw_fast(uint64_t& s, float mean, f
     const float z = x * __cosf(6.28318548202514648f * u2);
     return fmaf(z, std, mean);
 }
+static __device__ __noinline__ float rng_normal_draw_fast_ool(uint64_t& s, float mean, float std){ return rng_normal_draw_fast(s, mean, std); }
 template <bool OOL, bool FAST = false>
 __device__ __forceinline__ float rng_normal_t(uint64_t& s, float mean, float std){
     if(std == 0.0f){ return mean; }
-    if constexpr(FAST) return rng_normal_draw_fast(s, mean, std);
+    if constexpr(FAST && OOL) return rng_normal_draw_fast_ool(s, mean, std);
+    else if constexpr(FAST) return rng_normal_draw_fast(s, mean, std);
     else if constexpr(OOL) return rng_normal_draw_ool(s, mean, std);
     else return rng_normal_draw(s, mean, std);
 }

@@ -263,7 +263,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
 #pragma unroll
     for(int i = 0; i < 4; i++){
         float a = action[i];
-        if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL, FAST && !Spec::RNG_OOL>(rng, 0.0f, p[P_ACTION_NOISE]);
+        if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, p[P_ACTION_NOISE]);
         setpoint[i] = clamp_t<FAST>(a, -1.0f, 1.0f) * d.half_range + amin + d.half_range;
     }
     const float dt = d.dt;
