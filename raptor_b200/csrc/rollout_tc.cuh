@@ -86,6 +86,9 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
 #ifndef B200L2F_HOIST_LANGEVIN
 #define B200L2F_HOIST_LANGEVIN 0   // draw the Langevin target's normals in the shadow of the first MMA round trip (noise-free kernels only); measured -0.8 %
 #endif
+#ifndef B200L2F_H_IN_SMEM
+
+#endif
 #ifndef B200L2F_TS_CTAS_AXIAL
 #define B200L2F_TS_CTAS_AXIAL 3    // resident CTAs per SM of k_rollout_raptor_ts for axial vehicles: 4 = compact dynamics block (44 floats) + 128 registers
 #endif
@@ -633,7 +636,8 @@ struct TsSmemT {
     static constexpr int B = 0;                                // weight image (TMA destination)
     static constexpr int DYN = B + TcImage::BYTES;
     static constexpr int BAR = DYN + DSTRIDE * BLOCK * 4;
-    static constexpr int TOTAL = BAR + 32;
+    static constexpr int HID = BAR + 32;                       // B200L2F_H_IN_SMEM: h as float4 columns [4][BLOCK] (conflict-free LDS.128 / STS.128)
+    static constexpr int TOTAL = HID + (B200L2F_H_IN_SMEM ? 16 * BLOCK * 4 : 0);
 };
 // NOISE: observation / action noise (18 + 4 normal draws per step, each skipped when its std is 0) with the MUFU Box-Muller.
 template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false>
@@ -674,6 +678,17 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
         for(int i = 0; i < 8; i++) tc::split_tf32(v[i], hi[i], lo[i]);
         tc::tmem_st8(tmem_base + lane_off + col_hi, hi);
         tc::tmem_st8(tmem_base + lane_off + col_lo, lo);
+    };
+    float4* sm_h = reinterpret_cast<float4*>(smraw + TsSmem::HID) + tid;   // this thread's hidden state: sm_h[q * BLOCK], q = 0..3
+    auto keep_h = [&](const float* v){
+        if constexpr(B200L2F_H_IN_SMEM){
+#pragma unroll
+            for(int q = 0; q < 4; q++) sm_h[q * BLOCK] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    };
+    auto load_h = [&](float* v){
+#pragma unroll
+        for(int q = 0; q < 4; q++){ const float4 f = sm_h[q * BLOCK]; v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w; }
     };
     const uint32_t b_s = tc::smem_u32(sm_b);
     constexpr uint32_t SBO = 128;
@@ -737,6 +752,7 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
 #pragma unroll
         for(int j = 0; j < HD; j++) h[j] = __ldcg(a.hidden + (size_t)j * n + env);
         put8(C_H_HI, C_H_LO, h); put8(C_H_HI + 8, C_H_LO + 8, h + 8);
+        keep_h(h);
     }
     tc::tmem_st_wait();
 
@@ -788,6 +804,7 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
         for(int j = 0; j < HD; j++) x1[j] = fmaxf(x1[j], 0.0f);
         if(!no_auto_reset && gs >= a.seq_len){   // reset_truncate (gru/operations_generic.h:76-86)
             put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8);
+            keep_h(sm_b + TcImage::H0);
             gs = 0;
         }
         // ---- G2: GRU pre-activations (A = [x1 | h] in TMEM, K = 32)
@@ -814,8 +831,10 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
             float z[HD], hh[HD], hl[HD];
             if constexpr(B200L2F_TMEM_PREFETCH){   // in flight while the MUFU chain below runs
                 tc::tmem_ld16(tmem_base + lane_off + C_D2 + 16, z);
-                tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
-                tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+                if constexpr(!B200L2F_H_IN_SMEM){
+                    tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
+                    tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+                }
             }
             if constexpr(B200L2F_GATES_PACKED){
                 // two hidden units per packed instruction; each lane of FADD2 / FFMA2 rounds like the scalar instruction, so the bits are those of
@@ -839,8 +858,15 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
             }
             if constexpr(!B200L2F_TMEM_PREFETCH){
                 tc::tmem_ld16(tmem_base + lane_off + C_D2 + 16, z);
-                tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
-                tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+                if constexpr(!B200L2F_H_IN_SMEM){
+                    tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
+                    tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+                }
+            }
+            if constexpr(B200L2F_H_IN_SMEM){       // h itself (hi + lo == h exactly, so the bits are those of the TMEM read-back)
+                load_h(hh);
+#pragma unroll
+                for(int j = 0; j < HD; j++) hl[j] = 0.0f;
             }
             tc::tmem_ld_wait();
             if constexpr(B200L2F_GATES_PACKED){
@@ -877,8 +903,8 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
         {   // gru/operations_generic.h:400-410: this step's output is kept, the stored state resets when the counter wraps
             const int new_step = gs + 1;
             const bool wrap = !no_auto_reset && new_step >= a.seq_len;
-            if(wrap){ put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8); }
-            else{ put8(C_H_HI, C_H_LO, hn); put8(C_H_HI + 8, C_H_LO + 8, hn + 8); }
+            if(wrap){ put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8); keep_h(sm_b + TcImage::H0); }
+            else{ put8(C_H_HI, C_H_LO, hn); put8(C_H_HI + 8, C_H_LO + 8, hn + 8); keep_h(hn); }
             gs = wrap ? 0 : new_step;
         }
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
@@ -893,9 +919,16 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
     }
     tc::tmem_st_wait();
     float hh[HD], hl[HD];   // tcgen05.ld is warp-collective (.sync.aligned): every lane executes it, only active lanes store
-    tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
-    tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
-    tc::tmem_ld_wait();
+    if constexpr(B200L2F_H_IN_SMEM){
+        load_h(hh);
+#pragma unroll
+        for(int j = 0; j < HD; j++) hl[j] = 0.0f;
+    }
+    else{
+        tc::tmem_ld16(tmem_base + lane_off + C_H_HI, hh);
+        tc::tmem_ld16(tmem_base + lane_off + C_H_LO, hl);
+        tc::tmem_ld_wait();
+    }
     const bool last_chunk = chunk == n_chunks - 1;
     if(active){
         if(last_chunk && a.out_states && (a.T % a.state_stride) == 0)
