@@ -87,7 +87,7 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
 #define B200L2F_HOIST_LANGEVIN 0   // draw the Langevin target's normals in the shadow of the first MMA round trip (noise-free kernels only); measured -0.8 %
 #endif
 #ifndef B200L2F_H_IN_SMEM
-
+#define B200L2F_H_IN_SMEM 0        // the epilogue's copy of the GRU hidden state in shared memory (8 KB per CTA) instead of re-reading it from TMEM; measured -0.7 %
 #endif
 #ifndef B200L2F_TS_CTAS_AXIAL
 #define B200L2F_TS_CTAS_AXIAL 3    // resident CTAs per SM of k_rollout_raptor_ts for axial vehicles: 4 = compact dynamics block (44 floats) + 128 registers
