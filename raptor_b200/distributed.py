@@ -34,16 +34,23 @@ def init_process_group(backend=None):
     return rank, local, world
 
 
-def allgather_trajectories(slab, world=None):
+def allgather_trajectories(slab, world=None, n_global=None):
     """slab: this rank's [T, n_local, D] trajectory tensor (device tensor written by rollout/collect) -> [T, n_global, D] on every rank,
-    environments in global-id order (one all_gather_into_tensor; ragged shards are padded to the largest shard and trimmed)."""
+    environments in global-id order (one all_gather_into_tensor; ragged shards are padded to the largest shard and trimmed).
+    n_global: total number of environments when the shards follow shard_range() -- the shard sizes are then known locally and the call is a single
+    collective without a host synchronisation; otherwise the sizes are exchanged first."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return slab
     world = dist.get_world_size() if world is None else world
     T, n_local, D = slab.shape
-    counts = [torch.zeros(1, dtype=torch.int64, device=slab.device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=slab.device))
-    counts = [int(c.item()) for c in counts]
+    if n_global is not None:
+        counts = [shard_range(r, world, n_global)[1] for r in range(world)]
+        if counts[dist.get_rank()] != n_local:
+            raise ValueError("allgather_trajectories: this rank holds %d environments, shard_range gives %d" % (n_local, counts[dist.get_rank()]))
+    else:
+        counts = [torch.zeros(1, dtype=torch.int64, device=slab.device) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=slab.device))
+        counts = [int(c.item()) for c in counts]
     if len(set(counts)) == 1:
         out = torch.empty((world * T, n_local, D), dtype=slab.dtype, device=slab.device)   # rank-major concatenation along dim 0
         dist.all_gather_into_tensor(out, slab.contiguous())

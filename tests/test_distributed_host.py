@@ -34,6 +34,7 @@ SCRIPT = textwrap.dedent("""
         slab = ids[None, :, None].expand(T, cnt, D).contiguous() + torch.arange(T, dtype=torch.float32)[:, None, None] * 1000
         full = allgather_trajectories(slab)
         assert full.shape == (T, n_global, D), full.shape
+        assert torch.equal(full, allgather_trajectories(slab, n_global=n_global))
         want = torch.arange(n_global, dtype=torch.float32)[None, :, None].expand(T, n_global, D) + torch.arange(T, dtype=torch.float32)[:, None, None] * 1000
         assert torch.equal(full, want)
     sys.stdout.write("rank" + str(rank) + "-ok" + chr(10)); sys.stdout.flush()
