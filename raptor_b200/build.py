@@ -92,6 +92,36 @@ def build(force=False, verbose=False, extra_flags=(), jobs=None):
     return LIB
 
 
+def pybind_path():
+    import sysconfig
+    return os.path.join(HERE, "_l2f_pybind" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pybind(force=False, verbose=False):
+    """the pybind11 twin of raptor_b200/l2f.py + foundation_policy.py (csrc/pybind_l2f.cpp, host C++ over the C ABI): g++ + pybind11 headers,
+    linked against the engine library next to it.  Returns the path of the extension module."""
+    import sysconfig
+    import pybind11
+    out = pybind_path()
+    src = os.path.join(CSRC, "pybind_l2f.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "b200_l2f.h")]
+    if not force and os.path.exists(out) and all(_mtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"], src, "-o", out,
+           "-L" + LIB_DIR, "-lb200l2f", "-Wl,-rpath,$ORIGIN/lib",
+           # keep this module's C++ runtime symbols bound inside it (a statically linked libstdc++ must not be interposed by the process's own)
+           "-Wl,-Bsymbolic", "-Wl,--exclude-libs,ALL"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed on pybind_l2f.cpp")
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True, extra_flags=["-Xptxas", "-v"] if "--ptxas" in sys.argv else [])
     print(LIB)
+    print(build_pybind(force="--force" in sys.argv, verbose=True))

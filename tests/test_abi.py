@@ -51,3 +51,23 @@ def test_policy_blob_matches_golden():
     blob = raptor_b200.raptor_policy_blob()
     g = np.load(os.path.join(ROOT, "tests", "golden", "raptor_kat.npz"))
     assert blob.shape == (2084,) and np.array_equal(blob, g["blob"])
+
+
+def test_pybind_module_surface():
+    """the compiled l2f / foundation_policy modules (csrc/pybind_l2f.cpp) build, import without a GPU and expose the README's names"""
+    from raptor_b200 import build
+    build.build()
+    build.build_pybind()
+    import raptor_b200._l2f_pybind as l2f
+    vector = l2f.vector8
+    for name in ("VectorRng", "VectorEnvironment", "VectorParameters", "VectorState", "initialize_rng", "initialize_environment", "sample_initial_parameters",
+                 "sample_initial_state", "observe", "step", "set_ui_message", "set_parameters_message", "set_state_action_message"):
+        assert hasattr(vector, name), name
+    assert vector.N_ENVIRONMENTS == 8 and l2f.vector(24).N_ENVIRONMENTS == 24 and l2f.vector(24) is l2f.vector24
+    assert hasattr(l2f, "Device") and hasattr(l2f, "UI") and hasattr(l2f.foundation_policy, "Raptor")
+    ui = l2f.UI(); ui.ns = "abc"
+    assert ui.ns == "abc"
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+            vector.VectorEnvironment()

@@ -58,3 +58,46 @@ def test_readme_loop_matches_reference_config1():
         sc = np.maximum(np.abs(want[:, sl]).max(axis=1), floor)
         assert (np.abs(got[:, sl] - want[:, sl]).max(axis=1) <= 1e-4 * sc).all()
     assert np.array_equal(got[:, 30], want[:, 30])   # ring-buffer index
+
+
+def test_pybind_modules_run_the_readme_loop_identically():
+    """the compiled modules (pybind11, csrc/pybind_l2f.cpp) against the ctypes ones: same calls, same bits"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import raptor_b200.l2f as l2f_py
+    import raptor_b200._l2f_pybind as l2f_cc
+    from raptor_b200.foundation_policy import Raptor as RaptorPy
+
+    def run(l2f, Raptor):
+        vector = l2f.vector8
+        policy = Raptor()
+        device, rng, env, ui, params, state, next_state = l2f.Device(), vector.VectorRng(), vector.VectorEnvironment(), l2f.UI(), vector.VectorParameters(), vector.VectorState(), vector.VectorState()
+        observation = np.zeros((env.N_ENVIRONMENTS, env.OBSERVATION_DIM), dtype=np.float32)
+        vector.initialize_rng(device, rng, 0)
+        vector.initialize_environment(device, env)
+        vector.sample_initial_parameters(device, env, params, rng)
+        vector.sample_initial_state(device, env, params, state, rng)
+        ui.ns = "ns"
+        ui_state = copy(state)
+        for i, s in enumerate(ui_state.states):
+            s.position[0] += i * 0.1
+        msg = json.loads(vector.set_state_action_message(device, env, params, ui, ui_state, np.zeros((8, 4))))
+        assert msg["channel"] == "setStateAction" and abs(msg["data"][3]["state"]["position"][0] - (state.numpy()[3, 0] + 0.3)) < 1e-6
+        assert json.loads(vector.set_parameters_message(device, env, params, ui))["channel"] == "setParameters"
+        assert json.loads(vector.set_ui_message(device, env, ui))["namespace"] == "ns"
+        policy.reset()
+        acts = []
+        for _ in range(60):
+            vector.observe(device, env, params, state, observation, rng)
+            action = policy.evaluate_step(observation[:, :22])
+            dts = vector.step(device, env, params, state, action, next_state, rng)
+            state.assign(next_state)
+            acts.append(np.array(action))
+            assert abs(dts[-1] - 0.01) < 1e-9
+        return np.array(acts), state.numpy(), observation.copy()
+
+    import json
+    a1, s1, o1 = run(l2f_py, RaptorPy)
+    a2, s2, o2 = run(l2f_cc, l2f_cc.foundation_policy.Raptor)
+    assert np.array_equal(a1, a2) and np.array_equal(s1, s2) and np.array_equal(o1, o2)
