@@ -69,6 +69,7 @@ struct TsCtx {
     uint64_t* bar_mma;
     uint32_t phase;
     int tid;
+    uint64_t desc_n64, desc_n16;   // B descriptors of the image base for N = 64 / N = 16 tiles: every other descriptor is a compile-time offset away
 };
 __device__ __forceinline__ void ts_put8(uint32_t t_hi, uint32_t t_lo, const float* v){
     float hi[8], lo[8];
@@ -80,9 +81,11 @@ __device__ __forceinline__ void ts_put8(uint32_t t_hi, uint32_t t_lo, const floa
 // ksteps instructions of K = 8: A columns [a_hi + 8 s, +8) / [a_lo + 8 s, +8) against the B chunk pair s (issued by one thread)
 __device__ __forceinline__ void ts_issue_gemm(const TsCtx& c, uint32_t dcol, uint32_t a_hi, uint32_t a_lo, int ksteps, int b_hi_off, int b_lo_off, uint32_t N, uint32_t idesc){
     uint32_t acc = 0;
+    const uint64_t base = N == 16 ? c.desc_n16 : c.desc_n64;
+#pragma unroll
     for(int s = 0; s < ksteps; s++){
-        const uint64_t bhi = tc::make_smem_desc(c.b_s + b_hi_off * 4 + s * 2 * N * 16, N * 16, 128);
-        const uint64_t blo = tc::make_smem_desc(c.b_s + b_lo_off * 4 + s * 2 * N * 16, N * 16, 128);
+        const uint64_t bhi = tc::smem_desc_advance(base, b_hi_off * 4 + s * 2 * N * 16);
+        const uint64_t blo = tc::smem_desc_advance(base, b_lo_off * 4 + s * 2 * N * 16);
         tc::mma_tf32_ts(c.tmem_base + dcol, c.tmem_base + a_hi + 8 * s, bhi, idesc, acc); acc = 1;
         tc::mma_tf32_ts(c.tmem_base + dcol, c.tmem_base + a_hi + 8 * s, blo, idesc, 1);
         tc::mma_tf32_ts(c.tmem_base + dcol, c.tmem_base + a_lo + 8 * s, bhi, idesc, 1);
@@ -94,7 +97,7 @@ __device__ __forceinline__ void ts_run(TsCtx& c, F&& issue){
     tc::tmem_st_wait();
     tc::tc_fence_before();
     __syncthreads();
-    if(c.tid == 0){
+    if((c.tid >> 5) == 0 && tc::elect_one()){   // one lane of warp 0 (elect.sync): straight-line predicated MMA issue
         tc::tc_fence_after();
         issue();
         tc::mma_commit(c.bar_mma);
@@ -206,6 +209,7 @@ __device__ __forceinline__ TsCtx mlp_ts_prologue_at(unsigned char* smraw, int b_
     TsCtx c;
     c.sm_b = sm_b; c.b_s = tc::smem_u32(sm_b); c.tmem_base = *tmem_slot; c.tmem_lane = c.tmem_base + ((uint32_t)(warp * 32) << 16);
     c.bar_mma = bar_mma; c.phase = 0; c.tid = tid;
+    c.desc_n64 = tc::make_smem_desc(c.b_s, 64 * 16, 128); c.desc_n16 = tc::make_smem_desc(c.b_s, 16 * 16, 128);
     if(tc_image == nullptr) return c;          // the caller loads (and reloads) the image itself (dagger.cuh: one image per teacher)
     if(tid == 0){
         tc::mbar_expect_tx(bar_tma, MlpTcImage<IN, OUT>::BYTES);

@@ -695,10 +695,14 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
     constexpr uint32_t IDESC16 = tc::make_idesc_tf32(128, 16), IDESC64 = tc::make_idesc_tf32(128, 64);
     uint32_t phase = 0;
     // ksteps K=8 steps: A columns [a_hi + 8 s, +8) / [a_lo + 8 s, +8) against B chunk pairs (b_pair0 + s)
+    // the B descriptors differ only in their start address: two bases (N = 16 / N = 64 tiles), every other one is a compile-time offset away
+    const uint64_t desc_n16 = tc::make_smem_desc(b_s, 16 * 16, SBO), desc_n64 = tc::make_smem_desc(b_s, 64 * 16, SBO);
     auto issue_gemm = [&](uint32_t dcol, uint32_t a_hi, uint32_t a_lo, int ksteps, int b_hi_off, int b_lo_off, int b_pair0, uint32_t N, uint32_t idesc, uint32_t acc){
+        const uint64_t base = N == 16 ? desc_n16 : desc_n64;
+#pragma unroll
         for(int s = 0; s < ksteps; s++){
-            const uint64_t bhi = tc::make_smem_desc(b_s + b_hi_off * 4 + (b_pair0 + s) * 2 * N * 16, N * 16, SBO);
-            const uint64_t blo = tc::make_smem_desc(b_s + b_lo_off * 4 + (b_pair0 + s) * 2 * N * 16, N * 16, SBO);
+            const uint64_t bhi = tc::smem_desc_advance(base, b_hi_off * 4 + (b_pair0 + s) * 2 * N * 16);
+            const uint64_t blo = tc::smem_desc_advance(base, b_lo_off * 4 + (b_pair0 + s) * 2 * N * 16);
             tc::mma_tf32_ts(tmem_base + dcol, tmem_base + a_hi + 8 * s, bhi, idesc, acc); acc = 1;
             tc::mma_tf32_ts(tmem_base + dcol, tmem_base + a_hi + 8 * s, blo, idesc, 1);
             tc::mma_tf32_ts(tmem_base + dcol, tmem_base + a_lo + 8 * s, bhi, idesc, 1);
@@ -781,7 +785,7 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncthreads();
-        if(tid == 0){
+        if(warp == 0 && tc::elect_one()){
             tc::tc_fence_after();
             issue_gemm(C_D1, C_OBS_HI, C_OBS_LO, 3, TcImage::B1_HI, TcImage::B1_LO, 0, 16, IDESC16, 0);
             tc::mma_commit(bar_mma);
@@ -812,7 +816,7 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncthreads();
-        if(tid == 0){
+        if(warp == 0 && tc::elect_one()){
             tc::tc_fence_after();
             issue_gemm(C_D2, C_X1_HI, C_X1_LO, 2, TcImage::B2_HI, TcImage::B2_LO, 0, 64, IDESC64, 0);
             issue_gemm(C_D2, C_H_HI, C_H_LO, 2, TcImage::B2_HI, TcImage::B2_LO, 2, 64, IDESC64, 1);

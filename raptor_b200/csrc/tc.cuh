@@ -68,6 +68,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
     return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
+// descriptor of the same tile `byte_offset` further on (a multiple of 16): the start-address field is the low 14 bits and shared-memory addresses
+// are < 256 KB, so the field cannot carry -- one add instead of rebuilding the descriptor
+__device__ __forceinline__ uint64_t smem_desc_advance(uint64_t desc, uint32_t byte_offset){ return desc + (uint64_t)(byte_offset >> 4); }
+// one lane of a fully active warp (elect.sync): the form the compiler turns into a predicated tcgen05 issue without a per-lane loop
+__device__ __forceinline__ bool elect_one(){
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N){
     return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
