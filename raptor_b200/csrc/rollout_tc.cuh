@@ -86,6 +86,12 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
 #ifndef B200L2F_HOIST_LANGEVIN
 #define B200L2F_HOIST_LANGEVIN 0   // draw the Langevin target's normals in the shadow of the first MMA round trip (noise-free kernels only); measured -0.8 %
 #endif
+#ifndef B200L2F_SPLIT_PACKED
+#define B200L2F_SPLIT_PACKED 0     // 3xTF32 operand split with the low parts on the packed pipe: lo = fma2(hi, -1, x); measured -1.3 % (register moves, 8 B of spills)
+#endif
+#ifndef B200L2F_DENSE2_PACKED
+#define B200L2F_DENSE2_PACKED 1    // dense 2 (16 -> 4) as FFMA2 on (act0, act1) / (act2, act3); measured +1.2 %
+#endif
 #ifndef B200L2F_H_IN_SMEM
 #define B200L2F_H_IN_SMEM 0        // the epilogue's copy of the GRU hidden state in shared memory (8 KB per CTA) instead of re-reading it from TMEM; measured -0.7 %
 #endif
@@ -674,8 +680,19 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
     // write 8 values as a hi block and a lo block (8 columns each) of this thread's lane
     auto put8 = [&](uint32_t col_hi, uint32_t col_lo, const float* v){
         float hi[8], lo[8];
+        if constexpr(B200L2F_SPLIT_PACKED){
+            const float2 minus1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
-        for(int i = 0; i < 8; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+            for(int i = 0; i < 8; i += 2){
+                hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u); hi[i + 1] = __uint_as_float(__float_as_uint(v[i + 1]) & 0xFFFFE000u);
+                const float2 l = __ffma2_rn(make_float2(hi[i], hi[i + 1]), minus1, make_float2(v[i], v[i + 1]));   // x - hi, exact
+                lo[i] = l.x; lo[i + 1] = l.y;
+            }
+        }
+        else{
+#pragma unroll
+            for(int i = 0; i < 8; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+        }
         tc::tmem_st8(tmem_base + lane_off + col_hi, hi);
         tc::tmem_st8(tmem_base + lane_off + col_lo, lo);
     };
@@ -897,11 +914,23 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
         {
             const float* w2 = sm_b + TcImage::W2T;
             const float4 b = *reinterpret_cast<const float4*>(w2 + 64);
+            if constexpr(B200L2F_DENSE2_PACKED){   // same FMAs in the same order, two outputs per instruction
+                float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
+#pragma unroll
+                for(int k = 0; k < HD; k++){
+                    const float4 w = *reinterpret_cast<const float4*>(w2 + 4 * k);
+                    const float2 hk = make_float2(hn[k], hn[k]);
+                    a01 = __ffma2_rn(make_float2(w.x, w.y), hk, a01); a23 = __ffma2_rn(make_float2(w.z, w.w), hk, a23);
+                }
+                act[0] = a01.x; act[1] = a01.y; act[2] = a23.x; act[3] = a23.y;
+            }
+            else{
             act[0] = b.x; act[1] = b.y; act[2] = b.z; act[3] = b.w;
 #pragma unroll
             for(int k = 0; k < HD; k++){
                 const float4 w = *reinterpret_cast<const float4*>(w2 + 4 * k);
                 act[0] += w.x * hn[k]; act[1] += w.y * hn[k]; act[2] += w.z * hn[k]; act[3] += w.w * hn[k];
+            }
             }
         }
         {   // gru/operations_generic.h:400-410: this step's output is kept, the stored state resets when the counter wraps
