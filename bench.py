@@ -38,8 +38,8 @@ FLOP_POLICY_GATES = 150.0
 # what k_rollout_raptor_ts EXECUTES on the CUDA cores per environment step (ncu, profiles/r01_ncu_k_rollout_raptor_ts_v9_default_bench.txt):
 # fadd + fmul + 2 ffma thread instructions, and all thread instructions.  The actor's GEMMs run on tcgen05 and are not in these counts.
 TS_CUDA_CORE_FLOP = 1283.0
-TS_THREAD_INSTRUCTIONS = 1334.0
-TS_WARP_INSTRUCTIONS = 1448.0       # smsp__inst_executed.sum / (65536 / 32 warps x 1000 steps), same capture
+TS_THREAD_INSTRUCTIONS = 1302.0
+TS_WARP_INSTRUCTIONS = 1416.0       # smsp__inst_executed.sum / (65536 / 32 warps x 1000 steps), same capture
 BYTES_PER_ENV_LAUNCH = 4.0 * (2 * (48 + 16 + 2) + 145)   # read+write state, hidden, rng; read parameters (once per launch)
 
 DR_RANGES = [1.5, 5.0, 40, 1200, 0.02, 5.0, 0.1, 0.03, 0.10, 0.03, 0.30, 0.005, 0.05, 0.0, 0.3]  # sample_dynamics_parameters.cpp:48-64
@@ -309,16 +309,16 @@ def main():
             issue = {"achieved": warp_issue_ach, "peak": warp_issue_peak, "unit": "T warp-instructions/s", "frac": warp_issue_ach / warp_issue_peak,
                      "warp_instructions_per_warp_step": TS_WARP_INSTRUCTIONS, "thread_instructions_per_env_step": TS_THREAD_INSTRUCTIONS,
                      "note": "the ceiling that binds this kernel: instruction issue slots (148 SMs x 4 schedulers x max SM clock); executed warp instructions per "
-                             "warp-step (32 environments) from the committed ncu capture, rate measured live; ncu's own sm__inst_issued is 61.6 % of active cycles"}
+                             "warp-step (32 environments) from the committed ncu capture, rate measured live; ncu's own sm__inst_issued is 61.1 % of active cycles"}
         else:
             fp32_ach = steps_per_s_gpu * (FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES) / 1e12
             fp32_note = "algorithmic fp32 FLOPs (SURVEY 8d) of the CUDA-core kernel, actor GEMMs included"
             issue = None
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` capture of this exact configuration
-        # (39.42 MB read + 1.98 MB written: parameters / state in, state out; the per-chunk hand-over lives in the 126 MB L2)
+        # (39.42 MB read + 2.02 MB written: parameters / state in, state out; the per-chunk hand-over lives in the 126 MB L2)
         traffic, traffic_src = None, None
         if args.tcgen05 and n == 65536 and T == 1000 and not args.accurate_math:
-            traffic, traffic_src = 41.39e6, "profiles/r01_ncu_k_rollout_raptor_ts_v9_default_bench.txt"
+            traffic, traffic_src = 41.44e6, "profiles/r01_ncu_k_rollout_raptor_ts_v9_default_bench.txt"
         roofline = {"bound": "tensor", "achieved": tensor_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tensor_ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long launch)",
                     "kernel": "k_rollout_raptor_ts" if args.tcgen05 else "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_values_ts(const __grid_constant__ 
             const float* src = a.dataset + ((size_t)t * n + warp_env0) * D;
             float* dst = win + buf * SM::WIN_FLOATS;
             if(bulk){
-                if(lane == 0){
+                if(tc::elect_one()){                           // all 32 lanes arrive here together (warp-uniform branch after __syncwarp)
                     tc::fence_async_smem();                     // earlier generic-proxy reads of this window are ordered before the async-proxy write
                     tc::mbar_expect_tx(row_bar + buf, SM::WIN_BYTES);
                     tc::tma_load_1d(dst, src, SM::WIN_BYTES, row_bar + buf);
