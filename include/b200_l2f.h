@@ -13,9 +13,12 @@
  *   - every function returns an int status (0 = B200L2F_OK); b200l2f_last_error() gives the message;
  *   - the opaque handle owns all device memory; one handle per GPU; a handle is not thread-safe,
  *     different handles are independent;
- *   - pointer arguments carry a memory-space tag (B200L2F_HOST / B200L2F_DEVICE).  Host transfers are
- *     staged through pinned memory and are complete when the call returns; with device pointers the
- *     work is only enqueued on the handle's stream (b200l2f_stream / b200l2f_synchronize);
+ *   - pointer arguments carry a memory-space tag (B200L2F_HOST / B200L2F_DEVICE).  Host RESULTS are complete when
+ *     the call returns.  Host INPUTS in pageable memory are copied before the call returns (the buffer may be reused
+ *     at once); host inputs in page-locked memory (cudaMallocHost, torch pin_memory) are read by the DMA engine
+ *     asynchronously: do not modify them before the stream has passed the copy (b200l2f_synchronize, or any call that
+ *     returns host results).  With device pointers the work is only enqueued on the handle's stream
+ *     (b200l2f_stream / b200l2f_synchronize);
  *   - there is NO CPU fallback: creating a handle without a usable sm_100 device fails.
  *
  * Flat layouts (float32, row-major [n_envs, DIM] at the boundary; struct-of-arrays [DIM][n_envs] in HBM):

@@ -177,6 +177,7 @@ int b200l2f_destroy(b200l2f_handle* h){
     cudaFree(h->d_dg_states); cudaFree(h->d_dg_term); cudaFree(h->d_dg_eplen); cudaFree(h->d_dg_offsets); cudaFree(h->d_dg_returns);
     if(h->d_stage) cudaFree(h->d_stage);
     if(h->h_pinned) cudaFreeHost(h->h_pinned);
+    if(h->pinned_read) cudaEventDestroy(h->pinned_read);
     if(h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B200L2F_OK;

@@ -57,6 +57,7 @@ struct b200l2f_handle {
     int* d_episode_step = nullptr; float* d_episode_return = nullptr; uint8_t* d_truncated = nullptr;
     // staging
     void* h_pinned = nullptr; size_t pinned_bytes = 0;
+    cudaEvent_t pinned_read = nullptr; bool pinned_read_pending = false;   // an async H2D copy out of h_pinned may still be in flight
     void* d_stage = nullptr; size_t stage_bytes = 0;
     std::string err;
     int64_t launches = 0;
@@ -73,7 +74,14 @@ inline int fail(b200l2f_handle* h, int code, const std::string& msg){
 
 inline int grid_for(int n, int block){ return (n + block - 1) / block; }
 
+// The bounce buffer is read by asynchronous H2D copies: the host may write it again (or free it) only after the last such copy has finished.
+inline int pinned_wait(b200l2f_handle* h){
+    if(h->pinned_read_pending){ CU(cudaEventSynchronize(h->pinned_read)); h->pinned_read_pending = false; }
+    return B200L2F_OK;
+}
 inline int ensure_pinned(b200l2f_handle* h, size_t bytes){
+    int rc0;
+    if((rc0 = pinned_wait(h))) return rc0;
     if(bytes <= h->pinned_bytes) return B200L2F_OK;
     if(h->h_pinned){ cudaFreeHost(h->h_pinned); h->h_pinned = nullptr; h->pinned_bytes = 0; }
     CU(cudaMallocHost(&h->h_pinned, bytes));
@@ -93,7 +101,9 @@ inline bool is_pinned_host(const void* p){
     if(cudaPointerGetAttributes(&attr, p) != cudaSuccess){ cudaGetLastError(); return false; }
     return attr.type == cudaMemoryTypeHost;
 }
-// host -> device staging buffer, returns device pointer in *dev.  Pageable memory bounces through the handle's pinned buffer.
+// host -> device staging buffer, returns device pointer in *dev.  Pageable memory bounces through the handle's pinned buffer (the caller's
+// buffer may be reused as soon as the call returns); page-locked memory is read by the DMA engine directly and asynchronously: the caller must
+// not modify it before the stream has passed the copy (b200l2f_synchronize, or any call that returns host results).
 inline int upload(b200l2f_handle* h, const void* src, size_t bytes, int memspace, const void** dev){
     if(memspace == B200L2F_DEVICE){ *dev = src; return B200L2F_OK; }
     int rc;
@@ -102,9 +112,12 @@ inline int upload(b200l2f_handle* h, const void* src, size_t bytes, int memspace
         CU(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, h->stream));
     }
     else{
-        if((rc = ensure_pinned(h, bytes))) return rc;
+        if((rc = ensure_pinned(h, bytes))) return rc;         // waits for the previous copy out of the bounce buffer
         std::memcpy(h->h_pinned, src, bytes);
         CU(cudaMemcpyAsync(h->d_stage, h->h_pinned, bytes, cudaMemcpyHostToDevice, h->stream));
+        if(!h->pinned_read) CU(cudaEventCreateWithFlags(&h->pinned_read, cudaEventDisableTiming));
+        CU(cudaEventRecord(h->pinned_read, h->stream));
+        h->pinned_read_pending = true;
     }
     *dev = h->d_stage;
     return B200L2F_OK;

@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_off_policy(const __grid_c
     Ring rg{oa.position[env], oa.current_episode_start[env], oa.full[env] != 0};
     float* ring = oa.replay + env * (size_t)oa.capacity * D;
     int* es = oa.episode_start + env * (size_t)oa.capacity;
-    const int rows_valid = min(32, a.n - (blockIdx.x * BLOCK + warp * 32));
+    const int warp_env0 = (int)blockIdx.x * BLOCK + warp * 32;   // signed: a.n - warp_env0 is negative for a fully inactive warp
+    const int rows_valid = min(32, a.n - warp_env0);
 
     for(int t = 0; t < a.T; t++){
         if(truncated && active){                          // prologue_per_env (operations_generic_per_env.h:20-57)

@@ -274,7 +274,8 @@ def test_runner_edge_cases(rb, port, gemm):
         # ---- off-policy runner
         env = rb.VectorEnvironment(n, rb.SPEC_TEACHER)
         env.initialize_rng(6, warmup=8); env.initial_parameters(); env.initial_state()
-        env.load_policy(random_mlp_blob(rs, 26, 8, False, False), arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=g)
+        env_blob = random_mlp_blob(rs, 26, 8, False, False)
+        env.load_policy(env_blob, arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=g)
         env.collect_reset()
         ring = env.new_replay_buffers(1)                                                          # capacity 1: every add wraps
         rng0 = env.get_rng()
@@ -286,6 +287,20 @@ def test_runner_edge_cases(rb, port, gemm):
         assert np.all(step == 3) and np.all(trunc == 0)
         b = env.gather_batch(ring, port.rng_states(1, 5, warmup=3), 500)
         assert np.all(b["sample_index"] == 0) and np.array_equal(b["observations_actions"][0, :, :26], ring["data"][b["env_index"], 0, :26])
+        # regression: fully inactive warps of the last tile (their lanes shadow environment 0) must not write ring rows -- once an unsigned
+        # `n - warp_env0` made them stream their un-reset copy of environment 0 over its rows (timing-dependent; found with compute-sanitizer)
+        for rep in range(4):
+            e2 = rb.VectorEnvironment(n, rb.SPEC_TEACHER)
+            e2.initialize_rng(60 + rep, warmup=8); e2.initial_parameters(); e2.initial_state()
+            e2.load_policy(env_blob, arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=g)
+            e2.collect_reset()
+            r2 = e2.new_replay_buffers(8)
+            rng2, p2, s2 = e2.get_rng(), e2.get_parameters(), e2.get_state()
+            e2.off_policy_steps(6, 50, r2, sample_parameters=False)
+            run2 = B.new_off_policy_runner(n, 8, 26)
+            port.off_policy_steps(B.SPEC_TEACHER, port.make_policy(env_blob, arch=B.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_SAMPLE),
+                                  port.nominal_parameters(B.SPEC_TEACHER), p2, s2, rng2, run2, 6, 50, sample_parameters=False)
+            close(r2["data"][..., :26], run2["replay"][..., :26], 2e-3, 2e-4, "ring observations, n = %d" % n)
         env.set_runner_state(truncated=np.ones(n, np.uint8))                                      # truncate_all (operations_generic.h:152-154)
         env.off_policy_steps(1, 5, ring)
         assert np.all(env.get_runner_state()[0] == 1)
