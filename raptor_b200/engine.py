@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's vector:: environment interface on top of the C ABI (include/b200_l2f.h).
 
 Arguments may be numpy float32 arrays (host memory: copies are staged through pinned memory inside the call) or torch CUDA tensors
-(device memory: zero-copy, work is enqueued on the engine's stream).  Names, argument meaning and error behaviour follow the reference:
+(device memory: zero-copy, work is enqueued on the engine's stream; tensors produced on torch's current stream are ordered before it automatically,
+results must be awaited with synchronize() -- or create the environment on torch's stream: VectorEnvironment(..., stream=torch.cuda.current_stream().cuda_stream)).  Names, argument meaning and error behaviour follow the reference:
   rl_tools::init / initial_parameters / sample_initial_parameters / initial_state / sample_initial_state / observe / step / reward /
   terminated   (rl_tools/rl/environments/l2f/operations_generic.h:43-176)
   rl_tools::reset / evaluate_step  (rl_tools/nn_models/sequential/operations_generic.h:63-66,321-325)
@@ -111,12 +112,17 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-def _arg(x, dtype, shape=None, name="array"):
-    """-> (pointer, memspace, keepalive)"""
+def _arg(x, dtype, shape=None, name="array", engine_stream=None):
+    """-> (pointer, memspace, keepalive).  engine_stream: the cudaStream_t the engine enqueues on; a torch tensor produced on another stream
+    (torch's current one) is ordered before the engine's work by synchronising that stream first (no-op when the streams are the same)."""
     if x is None:
         return None, L.HOST, None
     if _is_torch(x):
         import torch
+        if engine_stream is not None and x.is_cuda:
+            cur = torch.cuda.current_stream(x.device)
+            if (cur.cuda_stream or 0) != (engine_stream or 0):
+                cur.synchronize()
         want = {np.float32: torch.float32, np.uint64: torch.int64, np.int32: torch.int32, np.uint8: torch.uint8}[dtype]
         if x.dtype != want and not (dtype == np.uint64 and x.dtype == getattr(torch, "uint64", None)):
             raise TypeError("%s: expected torch dtype %s, got %s" % (name, want, x.dtype))
@@ -152,8 +158,12 @@ class VectorEnvironment:
         self.ACTION_DIM = 4
         self.ACTION_HISTORY_LENGTH = self._lib.b200l2f_action_history_length(h)
         self.policy = None
+        self._engine_stream = self._lib.b200l2f_stream(h)
 
     # ---- plumbing
+    def _arg(self, x, dtype, shape=None, name="array"):
+        return _arg(x, dtype, shape, name, engine_stream=self._engine_stream)
+
     def _check(self, rc):
         if rc != 0:
             raise EngineError("b200l2f error %d: %s" % (rc, self._lib.b200l2f_last_error(self._h).decode()))
@@ -190,7 +200,7 @@ class VectorEnvironment:
         return out
 
     def set_rng(self, states):
-        p, ms, _ = _arg(states, np.uint64, (self.N_ENVIRONMENTS,), "rng")
+        p, ms, _ = self._arg(states, np.uint64, (self.N_ENVIRONMENTS,), "rng")
         self._check(self._lib.b200l2f_set_rng(self._h, p, ms))
 
     def initialize_environment(self):
@@ -214,12 +224,12 @@ class VectorEnvironment:
 
     def get_parameters(self, out=None):
         out = np.zeros((self.N_ENVIRONMENTS, L.PARAMS_DIM), np.float32) if out is None else out
-        p, ms, _ = _arg(out, np.float32, (self.N_ENVIRONMENTS, L.PARAMS_DIM), "parameters")
+        p, ms, _ = self._arg(out, np.float32, (self.N_ENVIRONMENTS, L.PARAMS_DIM), "parameters")
         self._check(self._lib.b200l2f_get_parameters(self._h, p, ms))
         return out
 
     def set_parameters(self, rows):
-        p, ms, _ = _arg(rows, np.float32, (self.N_ENVIRONMENTS, L.PARAMS_DIM), "parameters")
+        p, ms, _ = self._arg(rows, np.float32, (self.N_ENVIRONMENTS, L.PARAMS_DIM), "parameters")
         self._check(self._lib.b200l2f_set_parameters(self._h, p, ms))
 
     # ---- state
@@ -231,12 +241,12 @@ class VectorEnvironment:
 
     def get_state(self, slot=0, out=None):
         out = np.zeros((self.N_ENVIRONMENTS, self.STATE_DIM), np.float32) if out is None else out
-        p, ms, _ = _arg(out, np.float32, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")
+        p, ms, _ = self._arg(out, np.float32, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")
         self._check(self._lib.b200l2f_get_state(self._h, slot, p, ms))
         return out
 
     def set_state(self, rows, slot=0):
-        p, ms, _ = _arg(rows, np.float32, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")
+        p, ms, _ = self._arg(rows, np.float32, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")
         self._check(self._lib.b200l2f_set_state(self._h, slot, p, ms))
 
     def copy_state(self, dst_slot, src_slot):
@@ -248,24 +258,24 @@ class VectorEnvironment:
             observation = np.zeros((self.N_ENVIRONMENTS, self.OBSERVATION_DIM), np.float32)
         if observation.shape[0] != self.N_ENVIRONMENTS or observation.shape[1] < self.OBSERVATION_DIM:
             raise ValueError("observe: observation must be [N_ENVIRONMENTS, >= OBSERVATION_DIM]")
-        p, ms, _ = _arg(observation, np.float32, None, "observation")
+        p, ms, _ = self._arg(observation, np.float32, None, "observation")
         self._check(self._lib.b200l2f_observe(self._h, slot, p, observation.shape[1], ms))
         return observation
 
     def step(self, action, slot=0, next_slot=1, dts=None):
-        p, ms, _ = _arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
+        p, ms, _ = self._arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
         if dts is None and ms == L.HOST:
             dts = np.zeros(self.N_ENVIRONMENTS, np.float32)
-        pd, msd, _ = _arg(dts, np.float32, (self.N_ENVIRONMENTS,), "dts")
+        pd, msd, _ = self._arg(dts, np.float32, (self.N_ENVIRONMENTS,), "dts")
         if dts is not None and msd != ms:
             raise ValueError("step: action and dts must live in the same memory space")
         self._check(self._lib.b200l2f_step(self._h, slot, p, next_slot, pd, ms))
         return dts
 
     def reward(self, action, slot=0, next_slot=1, out=None):
-        p, ms, _ = _arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
+        p, ms, _ = self._arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
         out = np.zeros(self.N_ENVIRONMENTS, np.float32) if out is None else out
-        po, mso, _ = _arg(out, np.float32, (self.N_ENVIRONMENTS,), "rewards")
+        po, mso, _ = self._arg(out, np.float32, (self.N_ENVIRONMENTS,), "rewards")
         if mso != ms:
             raise ValueError("reward: action and out must live in the same memory space")
         self._check(self._lib.b200l2f_reward(self._h, slot, p, next_slot, po, ms))
@@ -273,7 +283,7 @@ class VectorEnvironment:
 
     def terminated(self, slot=0, out=None):
         out = np.zeros(self.N_ENVIRONMENTS, np.uint8) if out is None else out
-        p, ms, _ = _arg(out, np.uint8, (self.N_ENVIRONMENTS,), "flags")
+        p, ms, _ = self._arg(out, np.uint8, (self.N_ENVIRONMENTS,), "flags")
         self._check(self._lib.b200l2f_terminated(self._h, slot, p, ms))
         return out
 
@@ -286,11 +296,11 @@ class VectorEnvironment:
         self.policy = desc
 
     def policy_reset(self, mask=None):
-        p, ms, _ = _arg(mask, np.uint8, (self.N_ENVIRONMENTS,), "mask")
+        p, ms, _ = self._arg(mask, np.uint8, (self.N_ENVIRONMENTS,), "mask")
         self._check(self._lib.b200l2f_policy_reset(self._h, p, ms))
 
     def policy_evaluate_step(self, observation, action=None, no_auto_reset=False):
-        po, ms, _ = _arg(observation, np.float32, None, "observation")
+        po, ms, _ = self._arg(observation, np.float32, None, "observation")
         if observation.shape[0] != self.N_ENVIRONMENTS or observation.shape[1] < self.policy.input_dim:
             raise ValueError("evaluate_step: observation must be [N_ENVIRONMENTS, >= input_dim]")
         if action is None:
@@ -299,7 +309,7 @@ class VectorEnvironment:
             else:
                 import torch
                 action = torch.empty((self.N_ENVIRONMENTS, 4), dtype=torch.float32, device=observation.device)
-        pa, msa, _ = _arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
+        pa, msa, _ = self._arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
         if msa != ms:
             raise ValueError("evaluate_step: observation and action must live in the same memory space")
         self._check(self._lib.b200l2f_policy_evaluate_step(self._h, po, observation.shape[1], pa, int(no_auto_reset), ms))
@@ -320,10 +330,10 @@ class VectorEnvironment:
     def off_policy_steps(self, n_steps, episode_step_limit, replay, sample_parameters=True):
         n, D = self.N_ENVIRONMENTS, 2 * self.OBSERVATION_DIM + 7
         capacity = replay["data"].shape[1]
-        pd, ms, _ = _arg(replay["data"], np.float32, (n, capacity, D), "replay.data")
+        pd, ms, _ = self._arg(replay["data"], np.float32, (n, capacity, D), "replay.data")
         ptrs = [pd]
         for k, dt, sh in (("episode_start", np.int32, (n, capacity)), ("position", np.int32, (n,)), ("full", np.uint8, (n,)), ("current_episode_start", np.int32, (n,))):
-            p, m, _ = _arg(replay[k], dt, sh, "replay." + k)
+            p, m, _ = self._arg(replay[k], dt, sh, "replay." + k)
             if m != ms:
                 raise ValueError("off_policy_steps: all replay buffers must live in the same memory space")
             ptrs.append(p)
@@ -336,11 +346,11 @@ class VectorEnvironment:
         returns dict(observations_actions [2, B, OBS+4], rewards, terminated, reset, next_reset, final_step_mask, next_final_step_mask, env_index, sample_index)"""
         n, obs = self.N_ENVIRONMENTS, self.OBSERVATION_DIM
         capacity = replay["data"].shape[1]
-        pd, ms, _ = _arg(replay["data"], np.float32, (n, capacity, 2 * obs + 7), "replay.data")
-        pp, m1, _ = _arg(replay["position"], np.int32, (n,), "replay.position")
-        pf, m2, _ = _arg(replay["full"], np.uint8, (n,), "replay.full")
+        pd, ms, _ = self._arg(replay["data"], np.float32, (n, capacity, 2 * obs + 7), "replay.data")
+        pp, m1, _ = self._arg(replay["position"], np.int32, (n,), "replay.position")
+        pf, m2, _ = self._arg(replay["full"], np.uint8, (n,), "replay.full")
         B = int(rng_states.shape[0])
-        pr, m3, _ = _arg(rng_states, np.uint64, (B,), "rng_states")
+        pr, m3, _ = self._arg(rng_states, np.uint64, (B,), "rng_states")
         if not (ms == m1 == m2 == m3):
             raise ValueError("gather_batch: rings and rng_states must live in the same memory space")
         shapes = dict(observations_actions=((2, B, obs + 4), np.float32), rewards=((B,), np.float32), terminated=((B,), np.uint8), reset=((B,), np.uint8),
@@ -355,7 +365,7 @@ class VectorEnvironment:
                 out = {k: torch.zeros(sh, dtype=tdt[dt], device=rng_states.device) for k, (sh, dt) in shapes.items()}
         ptrs = []
         for k, (sh, dt) in shapes.items():
-            p, m, _ = _arg(out.get(k), dt, sh, "batch." + k)
+            p, m, _ = self._arg(out.get(k), dt, sh, "batch." + k)
             if out.get(k) is not None and m != ms:
                 raise ValueError("gather_batch: batch buffers must live in the memory space of the rings")
             ptrs.append(p)
@@ -373,9 +383,9 @@ class VectorEnvironment:
 
     def set_runner_state(self, episode_step=None, episode_return=None, truncated=None):
         n = self.N_ENVIRONMENTS
-        ps, _, k1 = _arg(None if episode_step is None else np.ascontiguousarray(episode_step, np.int32), np.int32, (n,), "episode_step")
-        pr, _, k2 = _arg(None if episode_return is None else np.ascontiguousarray(episode_return, np.float32), np.float32, (n,), "episode_return")
-        pt, _, k3 = _arg(None if truncated is None else np.ascontiguousarray(truncated, np.uint8), np.uint8, (n,), "truncated")
+        ps, _, k1 = self._arg(None if episode_step is None else np.ascontiguousarray(episode_step, np.int32), np.int32, (n,), "episode_step")
+        pr, _, k2 = self._arg(None if episode_return is None else np.ascontiguousarray(episode_return, np.float32), np.float32, (n,), "episode_return")
+        pt, _, k3 = self._arg(None if truncated is None else np.ascontiguousarray(truncated, np.uint8), np.uint8, (n,), "truncated")
         self._check(self._lib.b200l2f_runner_set_state(self._h, ps, pr, pt, L.HOST))
 
     # ---- PPO collection (rl_tools::collect): on-device auto-reset + trajectory write-back
@@ -389,7 +399,7 @@ class VectorEnvironment:
         shape = ((n_steps + 1) * self.N_ENVIRONMENTS, D)
         if dataset is None:
             dataset = np.zeros(shape, np.float32)
-        p, ms, _ = _arg(dataset, np.float32, shape, "dataset")
+        p, ms, _ = self._arg(dataset, np.float32, shape, "dataset")
         self._check(self._lib.b200l2f_collect(self._h, n_steps, episode_step_limit, p, ms))
         return dataset
 
@@ -401,7 +411,7 @@ class VectorEnvironment:
         self._check(self._lib.b200l2f_critic_load(self._h, ctypes.byref(desc), blob.ctypes.data, blob.size))
 
     def _dataset_arg(self, dataset, n_steps):
-        return _arg(dataset, np.float32, ((n_steps + 1) * self.N_ENVIRONMENTS, self.OBSERVATION_DIM + 15), "dataset")
+        return self._arg(dataset, np.float32, ((n_steps + 1) * self.N_ENVIRONMENTS, self.OBSERVATION_DIM + 15), "dataset")
 
     def evaluate_values(self, dataset, n_steps):
         """critic over all (T+1) N observation rows -> the all_values column, in place"""
@@ -425,8 +435,8 @@ class VectorEnvironment:
         """rl::components::running_normalizer update with the dataset's observation block; mean / std: host float32 [OBS], updated in place;
         returns the new age"""
         p, ms, _ = self._dataset_arg(dataset, n_steps)
-        pm, _, _ = _arg(mean, np.float32, (self.OBSERVATION_DIM,), "mean")
-        ps, _, _ = _arg(std, np.float32, (self.OBSERVATION_DIM,), "std")
+        pm, _, _ = self._arg(mean, np.float32, (self.OBSERVATION_DIM,), "mean")
+        ps, _, _ = self._arg(std, np.float32, (self.OBSERVATION_DIM,), "std")
         a = ctypes.c_int32(age)
         self._check(self._lib.b200l2f_normalizer_update(self._h, n_steps, p, ms, pm, ps, ctypes.byref(a)))
         return int(a.value)
@@ -466,7 +476,7 @@ class VectorEnvironment:
         dt = dict(input_student=np.float32, output_target=np.float32, truncated=np.uint8, reset=np.uint8, episode_start=np.int32, returns=np.float32, episode_length=np.int32)
         ptr, spaces = {}, set()
         for k, d in dt.items():
-            p, ms, _ = _arg(out.get(k), d, None, k)
+            p, ms, _ = self._arg(out.get(k), d, None, k)
             ptr[k] = p
             if out.get(k) is not None:
                 spaces.add(ms)
@@ -487,8 +497,8 @@ class VectorEnvironment:
         return h, g
 
     def set_hidden(self, hidden=None, gru_step=None):
-        ph, ms, _ = _arg(hidden, np.float32, (self.N_ENVIRONMENTS, self.policy.hidden_dim), "hidden")
-        pg, msg, _ = _arg(gru_step, np.int32, (self.N_ENVIRONMENTS,), "gru_step")
+        ph, ms, _ = self._arg(hidden, np.float32, (self.N_ENVIRONMENTS, self.policy.hidden_dim), "hidden")
+        pg, msg, _ = self._arg(gru_step, np.int32, (self.N_ENVIRONMENTS,), "gru_step")
         self._check(self._lib.b200l2f_policy_set_hidden(self._h, ph, pg, ms if hidden is not None else msg))
 
     # ---- the fused hot path
@@ -508,7 +518,7 @@ class VectorEnvironment:
         ro.state_stride = state_stride
         spaces = set()
         for k, v in out.items():
-            p, ms, _ = _arg(v, shapes[k][1], shapes[k][0], k)
+            p, ms, _ = self._arg(v, shapes[k][1], shapes[k][0], k)
             setattr(ro, k, p)
             spaces.add(ms)
         if len(spaces) > 1:

@@ -549,6 +549,7 @@ def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
     for it in range(2):
         env.off_policy_steps(T, limit, replay, sample_parameters=sample_parameters)
         port.off_policy_steps(spec, pol, env_p, params, states, rng, runner, T, limit, sample_parameters=sample_parameters)
+        env.synchronize()                                                              # device buffers: the call only enqueues on the engine's stream
         got = {k: (v.cpu().numpy() if on_device else v) for k, v in replay.items()}
         assert np.array_equal(env.get_rng(), rng), it                                  # every draw (resets, exploration, noise) in the same order
         for k, w in (("position", "position"), ("full", "full"), ("current_episode_start", "current_episode_start"), ("episode_start", "episode_start")):
@@ -580,6 +581,7 @@ def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
         want_b = port.gather_batch(ring_host, rng_b.copy(), 500, env_begin=b0, env_count=cnt)
         rng_in = torch.from_numpy(rng_b.view(np.int64).copy()).cuda() if on_device else rng_b.copy()
         got_b = env.gather_batch(replay, rng_in, 500, env_begin=b0, env_count=cnt)
+        env.synchronize()
         for k, v in want_b.items():
             g_ = got_b[k].cpu().numpy() if on_device else got_b[k]
             assert np.array_equal(g_, v), k
