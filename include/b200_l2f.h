@@ -295,18 +295,31 @@ int b200l2f_state_from_json(b200l2f_handle* h, const char* json, float* state_ro
  * parse:   reads the header text: every `memory[]` byte list becomes a float tensor named by its namespace path
  *          ("rl_tools::checkpoint::actor::layer_1::weights_input", "rl_tools::checkpoint::example::input", ...), row padding removed.
  * tensor:  i-th tensor in file order: path, rank, dims, data (owned by the checkpoint object).
- * string:  `char name[] = "..."` values, e.g. "rl_tools::checkpoint::meta::name" / "::commit_hash"; NULL if absent.
+ * string:  `char name[] = "..."` values, e.g. "rl_tools::checkpoint::meta::name" / "::commit_hash"; NULL if absent.  string_count / string_at
+ *          enumerate them (sorted by path).
  * policy:  recognises the actor under `root` (NULL = "rl_tools::checkpoint::actor") and assembles desc + blob for b200l2f_policy_load /
  *          b200l2f_critic_load / b200l2f_teachers_load in the blob orders documented above: Dense(ReLU)-GRU-Dense (Raptor) or
  *          [Standardize] MLP(3 layers, ReLU) [SampleAndSquash | log_std]; anything else -> B200L2F_ERR_UNSUPPORTED.  blob may be NULL to query
  *          *n_floats.  desc->gemm is preset to TCGEN05_3XTF32, desc->gru_sequence_length to the export's SEQUENCE_LENGTH (500 for Raptor).
- * The HDF5 twin (checkpoint.h5) is not read: no libhdf5 in this stack. */
+ * parse_h5: the HDF5 twin `checkpoint.h5` (rl::loop::steps::checkpoint::save, INC/rl/loop/steps/checkpoint/operations_cpu.h:119-160; written by
+ *          rl_tools::save(device, actor, HighFive::Group): nn_models/sequential/persist.h:14-21, nn/layers/{dense,gru,standardize,sample_and_squash}/persist.h,
+ *          nn/parameters/persist.h:10-13, containers/{matrix,tensor}/persist.h) from a memory image of the file, read by the engine's own HDF5 reader
+ *          (no libhdf5): superblock 0/1, version-1 object headers, symbol-table groups, contiguous / compact float32 / float64 datasets, string
+ *          attributes; anything else is an error that names it.  Datasets appear under the code export's paths
+ *          ("/actor/layers/1/weights_input/parameters" -> "rl_tools::checkpoint::actor::layer_1::weights_input"), string attributes under
+ *          "<path>::<attribute>" ("rl_tools::checkpoint::actor::layer_0::activation_function", "rl_tools::checkpoint::actor::meta"), the actor
+ *          group's checkpoint_name also as "rl_tools::checkpoint::meta::name"; tensor / string / policy work as for the code export.  The file
+ *          does not record SEQUENCE_LENGTH: desc->gru_sequence_length is 0 (= the engine default 500).  `parse` forwards here when the buffer
+ *          starts with the HDF5 signature. */
 typedef struct b200l2f_checkpoint b200l2f_checkpoint;
 int b200l2f_checkpoint_parse(const char* text, size_t length, b200l2f_checkpoint** out);
+int b200l2f_checkpoint_parse_h5(const void* bytes, size_t length, b200l2f_checkpoint** out);
 int b200l2f_checkpoint_free(b200l2f_checkpoint* c);
 int b200l2f_checkpoint_tensor_count(const b200l2f_checkpoint* c);
 int b200l2f_checkpoint_tensor(const b200l2f_checkpoint* c, int index, const char** path, int32_t* rank, const int64_t** dims, const float** data);
 const char* b200l2f_checkpoint_string(const b200l2f_checkpoint* c, const char* path);
+int b200l2f_checkpoint_string_count(const b200l2f_checkpoint* c);
+int b200l2f_checkpoint_string_at(const b200l2f_checkpoint* c, int index, const char** path, const char** value);
 int b200l2f_checkpoint_policy(const b200l2f_checkpoint* c, const char* root, b200l2f_policy_desc* desc, float* blob, size_t capacity, size_t* n_floats);
 
 #ifdef __cplusplus

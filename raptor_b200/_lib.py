@@ -96,10 +96,13 @@ SYMBOLS = {
     "b200l2f_state_to_json": (c_int, [vp, vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "b200l2f_state_from_json": (c_int, [vp, ctypes.c_char_p, vp]),
     "b200l2f_checkpoint_parse": (c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "b200l2f_checkpoint_parse_h5": (c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp)]),
     "b200l2f_checkpoint_free": (c_int, [vp]),
     "b200l2f_checkpoint_tensor_count": (c_int, [vp]),
     "b200l2f_checkpoint_tensor": (c_int, [vp, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_i32), ctypes.POINTER(ctypes.POINTER(c_i64)), ctypes.POINTER(ctypes.POINTER(c_f))]),
     "b200l2f_checkpoint_string": (ctypes.c_char_p, [vp, ctypes.c_char_p]),
+    "b200l2f_checkpoint_string_count": (c_int, [vp]),
+    "b200l2f_checkpoint_string_at": (c_int, [vp, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p)]),
     "b200l2f_checkpoint_policy": (c_int, [vp, ctypes.c_char_p, ctypes.POINTER(PolicyDesc), vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "b200l2f_off_policy_steps": (c_int, [vp, c_i32, c_i32, c_i32, ctypes.POINTER(ReplayBuffers)]),
     "b200l2f_gather_batch": (c_int, [vp, ctypes.POINTER(ReplayBuffers), c_i32, c_i32, c_i32, vp, ctypes.POINTER(Batch)]),

@@ -33,7 +33,8 @@ SOURCES = {
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
     "off_policy.cu": TC + ["mlp_tc.cuh", "offpolicy.cuh", "offpolicy_tc.cuh"],
     "json_io.cu": [],
-    "checkpoint_io.cu": [],
+    "checkpoint_io.cu": ["h5_io.h"],
+    "h5_io.cu": ["h5_io.h"],
 }
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -15,16 +15,20 @@
 //     Sequential<Dense(ReLU), GRU, Dense>                         (the Raptor checkpoint, checkpoint.h:40-185)       -> B200L2F_POLICY_RAPTOR_GRU
 //     [Standardize ->] MLP(3 layers, ReLU) [-> SampleAndSquash]   (SAC teachers, rl/algorithms/sac/loop/core/approximators_mlp.h:14-37;
 //                                                                   PPO actors with mlp_unconditional_stddev: log_std)  -> B200L2F_POLICY_MLP
-// The HDF5 twin (checkpoint.h5, operations_cpu.h:119-160) needs libhdf5 / HighFive, which this image does not have; it is not read.
+// The HDF5 twin (checkpoint.h5, operations_cpu.h:119-160; the reference reads it through HighFive / libhdf5, which this image does not have) is
+// read by the engine's own minimal HDF5 reader (h5_io.cu) and mapped onto the same tensor paths (from_h5 below), so both files of a checkpoint
+// folder give the same tensors and the same policy blob.
 #include <cctype>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "handle.h"
+#include "h5_io.h"
 
 using namespace b200l2f;
 
@@ -326,12 +330,68 @@ std::string build_policy(const Ckpt& c, const std::string& root, b200l2f_policy_
 
 int cfail(const std::string& m){ create_error() = m; return B200L2F_ERR_ARGUMENT; }
 
+// ---- checkpoint.h5 -> the code export's namespace paths ---------------------------------------------------------------------------------------
+// "/actor/layers/1/weights_input/parameters" -> "rl_tools::checkpoint::actor::layer_1::weights_input" (nn_models/sequential/persist.h:14-21 names the
+// layer groups "layers/<k>", persist_code.h names the namespaces "layer_<k>"; nn/parameters/persist.h:10-13 stores a parameter's values as the
+// dataset "parameters").  Other datasets of a parameter group ("gradient", optimizer moments of a Gradient-capability save) keep their name.
+std::string h5_path_to_namespace(const std::string& path, bool drop_parameters){
+    std::vector<std::string> parts;
+    for(size_t i = 0; i < path.size();){
+        while(i < path.size() && path[i] == '/') i++;
+        size_t e = i; while(e < path.size() && path[e] != '/') e++;
+        if(e > i) parts.push_back(path.substr(i, e - i));
+        i = e;
+    }
+    if(drop_parameters && !parts.empty() && parts.back() == "parameters") parts.pop_back();
+    std::string ns = "rl_tools::checkpoint";
+    for(size_t i = 0; i < parts.size(); i++){
+        const bool numbered = parts[i] == "layers" && i + 1 < parts.size() && !parts[i + 1].empty() && parts[i + 1].find_first_not_of("0123456789") == std::string::npos;
+        if(numbered){ ns += "::layer_" + parts[i + 1]; i++; }
+        else ns += "::" + parts[i];
+    }
+    return ns;
+}
+void from_h5(const H5Contents& f, Ckpt& c){
+    for(auto& ds : f.datasets){
+        Ckpt::TensorEntry t;
+        t.path = h5_path_to_namespace(ds.path, true); t.dims = ds.dims; t.data = ds.data; t.elem_size = ds.elem_size; t.bytes = (int64_t)ds.data.size() * ds.elem_size; t.shaped = true;
+        c.tensors.push_back(std::move(t));
+    }
+    // attributes: every string attribute is kept under <namespace>::<name>; the ones the code export states as template arguments are restated
+    // in the form build_policy reads (dense/persist.h:17-18 "activation_function" / "type", sample_and_squash/persist.h:13, mlp/persist.h:16)
+    std::vector<std::string> mlps;
+    for(auto& a : f.attributes){
+        const std::string ns = h5_path_to_namespace(a.object, true);
+        c.strings[ns + "::" + a.name] = a.value;
+        if(a.name == "activation_function") c.config[ns] = "ActivationFunction::" + a.value;
+        else if(a.name == "type" && a.value == "sample_and_squash") c.config[ns] = "sample_and_squash";
+        else if(a.name == "type" && a.value == "mlp") mlps.push_back(ns);
+        else if(a.name == "checkpoint_name" && a.object == "/actor") c.strings["rl_tools::checkpoint::meta::name"] = a.value;
+    }
+    for(auto& m : mlps){                                              // hidden activation, then output activation (nn_models/mlp/network.h:15-51)
+        auto hid = c.strings.find(m + "::input_layer::activation_function"), out = c.strings.find(m + "::output_layer::activation_function");
+        if(hid != c.strings.end() && out != c.strings.end()) c.config[m] = "ActivationFunction::" + hid->second + " ActivationFunction::" + out->second;
+    }
+}
+
 }  // namespace
 
 extern "C" {
 
+int b200l2f_checkpoint_parse_h5(const void* bytes, size_t length, b200l2f_checkpoint** out){
+    if(!bytes || !out) return cfail("checkpoint_parse_h5: null argument");
+    *out = nullptr;
+    H5Contents f; std::string err;
+    if(!h5_read((const unsigned char*)bytes, length, f, err)) return cfail("checkpoint_parse_h5: " + err);
+    auto* c = new b200l2f_checkpoint();
+    from_h5(f, *c);
+    if(c->tensors.empty()){ delete c; return cfail("checkpoint_parse_h5: the file holds no numeric datasets"); }
+    *out = c;
+    return B200L2F_OK;
+}
 int b200l2f_checkpoint_parse(const char* text, size_t length, b200l2f_checkpoint** out){
     if(!text || !out) return cfail("checkpoint_parse: null argument");
+    if(h5_has_signature((const unsigned char*)text, length)) return b200l2f_checkpoint_parse_h5(text, length, out);   // checkpoint.h5 handed to the generic entry
     *out = nullptr;
     auto* c = new b200l2f_checkpoint();
     Scanner s{text, text + length, *c, {}, {}, 4, text};
@@ -355,6 +415,14 @@ const char* b200l2f_checkpoint_string(const b200l2f_checkpoint* c, const char* p
     if(!c || !path) return nullptr;
     auto it = c->strings.find(path);
     return it == c->strings.end() ? nullptr : it->second.c_str();
+}
+int b200l2f_checkpoint_string_count(const b200l2f_checkpoint* c){ return c ? (int)c->strings.size() : 0; }
+int b200l2f_checkpoint_string_at(const b200l2f_checkpoint* c, int index, const char** path, const char** value){
+    if(!c || index < 0 || index >= (int)c->strings.size()) return cfail("checkpoint_string_at: index out of range");
+    auto it = c->strings.begin(); std::advance(it, index);
+    if(path) *path = it->first.c_str();
+    if(value) *value = it->second.c_str();
+    return B200L2F_OK;
 }
 int b200l2f_checkpoint_policy(const b200l2f_checkpoint* c, const char* root, b200l2f_policy_desc* desc, float* blob, size_t capacity, size_t* n_floats){
     if(!c || !desc) return cfail("checkpoint_policy: null argument");

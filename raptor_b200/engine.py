@@ -28,8 +28,9 @@ def raptor_policy_blob():
 
 
 class Checkpoint:
-    """an rl-tools checkpoint code export (`checkpoint.h`, rl/loop/steps/checkpoint/operations_cpu.h:56-118) read by the engine's native reader
-    (csrc/checkpoint_io.cu); no GPU needed.  `tensors` maps namespace paths to float32 arrays; `policy()` returns (PolicyDesc, blob) for
+    """an rl-tools checkpoint -- the code export `checkpoint.h` (rl/loop/steps/checkpoint/operations_cpu.h:56-118) or its HDF5 twin `checkpoint.h5`
+    (:119-160; told apart by the HDF5 signature) -- read by the engine's native readers (csrc/checkpoint_io.cu, csrc/h5_io.cu); no GPU needed.
+    `tensors` maps namespace paths to float32 arrays, `strings` the meta strings / HDF5 string attributes; `policy()` returns (PolicyDesc, blob) for
     VectorEnvironment.load_policy(**Checkpoint.policy_kwargs())."""
 
     def __init__(self, text=None, path=None):
@@ -49,9 +50,14 @@ class Checkpoint:
                 dims, data = ctypes.POINTER(ctypes.c_int64)(), ctypes.POINTER(ctypes.c_float)()
                 lib.b200l2f_checkpoint_tensor(h, i, ctypes.byref(name), ctypes.byref(rank), ctypes.byref(dims), ctypes.byref(data))
                 shape = tuple(dims[k] for k in range(rank.value))
-                self.tensors[name.value.decode()] = np.ctypeslib.as_array(data, shape=(int(np.prod(shape)),)).reshape(shape).copy()
-            get = lambda k: (lambda v: v.decode() if v is not None else None)(lib.b200l2f_checkpoint_string(h, k.encode()))
-            self.name, self.commit_hash = get("rl_tools::checkpoint::meta::name"), get("rl_tools::checkpoint::meta::commit_hash")
+                count = int(np.prod(shape, dtype=np.int64))
+                self.tensors[name.value.decode()] = (np.ctypeslib.as_array(data, shape=(count,)).copy() if count else np.zeros(0, np.float32)).reshape(shape)
+            self.strings = {}
+            for i in range(lib.b200l2f_checkpoint_string_count(h)):
+                k, v = ctypes.c_char_p(), ctypes.c_char_p()
+                lib.b200l2f_checkpoint_string_at(h, i, ctypes.byref(k), ctypes.byref(v))
+                self.strings[k.value.decode()] = v.value.decode(errors="replace")
+            self.name, self.commit_hash = self.string("rl_tools::checkpoint::meta::name"), self.string("rl_tools::checkpoint::meta::commit_hash")
             self._policy = {}
             self._errors = {}
             for root in ("rl_tools::checkpoint::actor",):
@@ -64,6 +70,10 @@ class Checkpoint:
                     self._errors[root] = lib.b200l2f_last_error(None).decode()
         finally:
             lib.b200l2f_checkpoint_free(h)
+
+    def string(self, path):
+        """`char name[] = "..."` of the code export / string attribute of the .h5 ("<namespace path>::<name>"), or None"""
+        return self.strings.get(path)
 
     def policy(self, root="rl_tools::checkpoint::actor"):
         if root not in self._policy:

@@ -12,8 +12,8 @@ from .engine import Checkpoint, VectorEnvironment, raptor_policy_blob
 
 class Raptor:
     def __init__(self, device=0, no_auto_reset=False, checkpoint=None):
-        """checkpoint: path of an rl-tools `checkpoint.h` code export with a Dense-GRU-Dense actor (another training run of the foundation
-        policy); default = the weights of the reference's published checkpoint shipped in raptor_b200/data"""
+        """checkpoint: path of an rl-tools `checkpoint.h` code export or `checkpoint.h5` with a Dense-GRU-Dense actor (another training run of
+        the foundation policy); default = the weights of the reference's published checkpoint shipped in raptor_b200/data"""
         self._policy = dict(blob=raptor_policy_blob()) if checkpoint is None else Checkpoint(path=checkpoint).policy_kwargs()
         self._device = device
         self._no_auto_reset = no_auto_reset
