@@ -183,7 +183,9 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
 /* ---- PPO collection with on-device auto-reset and trajectory write-back: replaces rl_tools::collect
  * (INC/rl/components/on_policy_runner/operations_generic.h:99-131, operations_generic_per_env.h:8-75).
  * dataset: [(T+1)*n_envs, OBS+15] rows = step*n_envs + env, columns obs | actions_mean[4] | actions[4] | log_prob | reward |
- * terminated | truncated | value | advantage | target_value (on_policy_runner.h:42-64); the last n_envs rows hold the final observations. */
+ * terminated | truncated | value | advantage | target_value (on_policy_runner.h:42-64); the last n_envs rows hold the final observations.
+ * All specs: RAPTOR / TEACHER (H = 1; tcgen05 or CUDA-core actor) and DEFAULT (the PPO zoo's environment, INC/rl/zoo/l2f/ppo.h: H = 16 action
+ * history, OBS 82, 97-float rows; CUDA-core actor, as for the learner feed below). */
 int b200l2f_collect_reset(b200l2f_handle* h);                                             /* runner init: truncated = true, episode_step/return = 0 (operations_generic.h:65-75) */
 int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, float* dataset, int memspace);
 

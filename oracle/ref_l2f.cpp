@@ -765,12 +765,15 @@ int ref_mlp_evaluate(int in_dim, int out_dim, const float* blob, int has_std, in
     else if(in_dim == 26 && out_dim == 1) ref_ppo::mlp_evaluate<26, 1>(blob, has_std, n_rows, in, ld_in, out, ld_out);
     else if(in_dim == 26 && out_dim == 8) ref_ppo::mlp_evaluate<26, 8>(blob, has_std, n_rows, in, ld_in, out, ld_out);
     else if(in_dim == 82 && out_dim == 4) ref_ppo::mlp_evaluate<82, 4>(blob, has_std, n_rows, in, ld_in, out, ld_out);
+    else if(in_dim == 82 && out_dim == 1) ref_ppo::mlp_evaluate<82, 1>(blob, has_std, n_rows, in, ld_in, out, ld_out);
     else return 1;
     return 0;
 }
 void ref_collect(int spec, const float* actor_blob, int has_std, const float* env_params, float* params_io, float* states_io, uint64_t* rng_states,
                  int* episode_step_io, float* episode_return_io, unsigned char* truncated_io, float* dataset){
     switch(spec){
+        case 0: ref_ppo::collect<ENV_DEFAULT>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;   // the PPO zoo's env (rl/zoo/l2f/ppo.h)
+        case 1: ref_ppo::collect<ENV_DEFAULT_DR>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;
         case 2: ref_ppo::collect<ENV_RAPTOR>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;
         case 4: ref_ppo::collect<ENV_RAPTOR_DR>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;
         case 5: ref_ppo::collect<ENV_TEACHER_DR>(actor_blob, has_std, env_params, params_io, states_io, rng_states, episode_step_io, episode_return_io, truncated_io, dataset); break;
@@ -779,6 +782,7 @@ void ref_collect(int spec, const float* actor_blob, int has_std, const float* en
 }
 void ref_gae(int spec, float* dataset, int ignore_termination){
     switch(spec){
+        case 0: case 1: ref_ppo::gae<ENV_DEFAULT>(dataset, ignore_termination); break;
         case 2: case 4: ref_ppo::gae<ENV_RAPTOR>(dataset, ignore_termination); break;
         case 3: case 5: ref_ppo::gae<ENV_TEACHER>(dataset, ignore_termination); break;
         default: std::fprintf(stderr, "ref_gae: spec %d not instantiated\n", spec); std::abort();
@@ -786,6 +790,7 @@ void ref_gae(int spec, float* dataset, int ignore_termination){
 }
 void ref_normalizer_update(int spec, const float* dataset, float* mean_io, float* std_io, int* age_io){
     switch(spec){
+        case 0: case 1: ref_ppo::normalizer_update<ENV_DEFAULT>(dataset, mean_io, std_io, age_io); break;
         case 2: case 4: ref_ppo::normalizer_update<ENV_RAPTOR>(dataset, mean_io, std_io, age_io); break;
         case 3: case 5: ref_ppo::normalizer_update<ENV_TEACHER>(dataset, mean_io, std_io, age_io); break;
         default: std::fprintf(stderr, "ref_normalizer_update: spec %d not instantiated\n", spec); std::abort();

@@ -619,7 +619,6 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     CU(cudaSetDevice(h->cfg.device));
     if(!h->policy_loaded || h->pol.arch != B200L2F_POLICY_MLP || h->pol.head != B200L2F_HEAD_PPO_GAUSSIAN)
         return fail(h, B200L2F_ERR_STATE, "collect: load an MLP actor with the PPO_GAUSSIAN head first");
-    if(h->kind == KIND_DEFAULT) return fail(h, B200L2F_ERR_UNSUPPORTED, "collect: instantiated for the H = 1 specs (RAPTOR, TEACHER)");
     if(n_steps < 0 || !dataset) return fail(h, B200L2F_ERR_ARGUMENT, "collect: bad arguments");
     const int D = h->obs_dim + 15;
     const size_t bytes = sizeof(float) * (size_t)(n_steps + 1) * h->n * D;

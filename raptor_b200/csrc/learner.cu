@@ -19,17 +19,18 @@ int stage_dataset(b200l2f_handle* h, float* dataset, int T, int memspace, float*
     return B200L2F_OK;
 }
 int check_feed(b200l2f_handle* h, int T, const float* dataset, const char* who){
-    if(h->kind == KIND_DEFAULT) return fail(h, B200L2F_ERR_UNSUPPORTED, std::string(who) + ": instantiated for the H = 1 specs (RAPTOR, TEACHER), like b200l2f_collect");
     if(T < 1 || !dataset) return fail(h, B200L2F_ERR_ARGUMENT, std::string(who) + ": bad arguments");
     return B200L2F_OK;
 }
 
 template <int IN>
 int launch_values(b200l2f_handle* h, FeedArgs a, bool gae){
-    const bool tensor_cores = h->critic_gemm == B200L2F_GEMM_TCGEN05_3XTF32 && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
+    // the tcgen05 kernel is instantiated for the H = 1 specs (the observation is one K <= 32 operand); the DEFAULT spec's 82-wide rows run on CUDA cores
+    constexpr bool HAS_TS = IN <= 32;
+    const bool tensor_cores = HAS_TS && h->critic_gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_critic_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-    if(tensor_cores){
+    if constexpr(HAS_TS) if(tensor_cores){
         using SM = FeedSmem<IN>;
         auto go = [&](auto kern) -> int {
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
@@ -46,7 +47,7 @@ int launch_values(b200l2f_handle* h, FeedArgs a, bool gae){
         return gae ? go(k_values_ts<IN, true>) : go(k_values_ts<IN, false>);
     }
     auto kern = k_values<IN>;
-    const size_t smem = sizeof(float) * (MlpImg<IN, 4>::SIZE + (size_t)MLP_HD * BLOCK);
+    const size_t smem = sizeof(float) * (MlpImg<IN, 4>::SIZE + (size_t)(IN > MLP_HD ? IN : MLP_HD) * BLOCK);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t rows = (size_t)(a.T + 1) * a.n;
     const size_t want = (rows + BLOCK - 1) / BLOCK;
@@ -70,7 +71,7 @@ int values_impl(b200l2f_handle* h, int T, float gamma, float lambda, int ignore_
     FeedArgs a{};
     a.dataset = dev; a.n = h->n; a.T = T; a.gamma = gamma; a.lambda = lambda; a.ignore_termination = ignore_termination;
     a.blob = h->d_critic_blob; a.has_std = h->critic_std;
-    rc = h->obs_dim == 22 ? launch_values<22>(h, a, gae) : launch_values<26>(h, a, gae);
+    rc = h->obs_dim == 22 ? launch_values<22>(h, a, gae) : h->obs_dim == 26 ? launch_values<26>(h, a, gae) : launch_values<82>(h, a, gae);
     if(rc) return rc;
     return download(h, dataset, dev, dataset_bytes(h, T), memspace);
 }
@@ -82,7 +83,6 @@ extern "C" {
 int b200l2f_critic_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, const float* blob, size_t n_floats){
     CU(cudaSetDevice(h->cfg.device));
     if(!desc || !blob) return fail(h, B200L2F_ERR_ARGUMENT, "critic_load: null argument");
-    if(h->kind == KIND_DEFAULT) return fail(h, B200L2F_ERR_UNSUPPORTED, "critic_load: instantiated for the H = 1 specs (RAPTOR, TEACHER)");
     if(desc->arch != B200L2F_POLICY_MLP || desc->hidden_dim != MLP_HD || desc->output_dim != 1 || desc->head != B200L2F_HEAD_IDENTITY || desc->input_dim != h->obs_dim)
         return fail(h, B200L2F_ERR_ARGUMENT, "critic_load: the critic is [standardize ->] Dense(OBS, 64) -> Dense(64, 64) -> Dense(64, 1), head IDENTITY");
     const int in = desc->input_dim, hd = MLP_HD;
@@ -106,7 +106,7 @@ int b200l2f_critic_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
         CU(cudaMemcpy(h->d_critic_tc_image, img.data(), MlpTcImage<IN, 4>::BYTES, cudaMemcpyHostToDevice));
         return (int)B200L2F_OK;
     };
-    int rc = in == 22 ? build(std::integral_constant<int, 22>{}) : build(std::integral_constant<int, 26>{});
+    int rc = in == 22 ? build(std::integral_constant<int, 22>{}) : in == 26 ? build(std::integral_constant<int, 26>{}) : (int)B200L2F_OK;   // OBS 82 (DEFAULT spec): CUDA-core kernel, no operand image
     if(rc) return rc;
     h->critic_loaded = true; h->critic_std = desc->standardize; h->critic_gemm = desc->gemm;
     return B200L2F_OK;
@@ -153,6 +153,7 @@ int b200l2f_normalizer_update(b200l2f_handle* h, int32_t n_steps, const float* d
     }
     double* partials = h->d_colstats; double* d_mean = partials + (size_t)grid * obs; double* d_ss = d_mean + obs;
     const size_t smem = sizeof(float) * (size_t)BLOCK * D;
+    CU(cudaFuncSetAttribute(k_column_partials, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // 49.7 KB for the DEFAULT spec's 97-float rows
     k_column_partials<<<grid, BLOCK, smem, h->stream>>>(dev, rows, obs, nullptr, partials);
     LAUNCH_CHECK();
     k_column_finish<<<1, 128, 0, h->stream>>>(partials, grid, obs, 1.0 / (double)rows, d_mean);

@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_mlp(const __grid_
 // The last three columns belong to the learner and are not touched.  Rows of the 32 environments of a warp are consecutive in
 // memory, so the warp stages its 32 x W floats in shared memory and writes them as contiguous 128-byte lines.
 // ---------------------------------------------------------------------------------------------------------------
+// floats of one warp's shared-memory slab in k_collect: [64 + IN][32] scratch columns (+ a separate [32][IN + 12] write-back window when the
+// row does not fit in the 64 hidden-activation rows)
+template <int IN> struct CollectSlab { static constexpr int FLOATS = (MLP_HD + IN) * 32 + (IN + 12 > MLP_HD ? 32 * (IN + 12) : 0); };
 struct CollectArgs {
     float* params;            // [145][n]   (rewritten on reset)
     const float* env_row;     // [145] nominal / DR-range row the reset sampler starts from (device copy)
@@ -244,13 +247,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
     constexpr int D = IN + 15, W = IN + 12;        // W: columns written per step
     constexpr int OBS0 = MLP_HD;                   // scratch rows [0, 64): hidden activations; [64, 64 + IN): the observation (kept for the write-back)
     constexpr int ROWS = MLP_HD + IN;              // per-warp slab [ROWS][32]; its first 32 * W floats double as the [32][W] write-back window
-    static_assert(W <= MLP_HD, "the [32][W] write-back window must fit in the 64 hidden-activation rows of the slab");
+    constexpr bool WINDOW_APART = W > MLP_HD;      // ... unless the row is wider than the 64 hidden-activation rows (DEFAULT spec, OBS 82): own window
+    constexpr int SLAB = CollectSlab<IN>::FLOATS;
     extern __shared__ __align__(16) float smem[];
     float* img = smem;
     float* sm_dyn = smem + MlpImg<IN, OUT>::SIZE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* slab = sm_dyn + P_DYN_DIM * BLOCK + (size_t)warp * ROWS * 32;   // private to this warp: only __syncwarp is needed
+    float* slab = sm_dyn + P_DYN_DIM * BLOCK + (size_t)warp * SLAB;        // private to this warp: only __syncwarp is needed
     float* scr = slab + lane;                                            // this thread's column, row stride 32
+    float* win = WINDOW_APART ? slab + ROWS * 32 : slab;                 // [32][W] write-back window
     stage_mlp_image<IN, OUT>(img, a.blob, a.has_std != 0, true);
     const int e = blockIdx.x * BLOCK + threadIdx.x;
     const bool active = e < a.n;
@@ -306,10 +311,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
         // ---- coalesced write-back: every lane lays out ITS row in the [32][W] window (the hidden-activation rows are free now), then the warp
         // ---- streams the window to the 32 consecutive dataset rows as contiguous runs of W floats
         __syncwarp();
-        for(int i = 0; i < IN; i++) slab[lane * W + i] = scr[(OBS0 + i) * 32];
+        for(int i = 0; i < IN; i++) win[lane * W + i] = scr[(OBS0 + i) * 32];
         if(!last){
 #pragma unroll
-            for(int i = 0; i < 12; i++) slab[lane * W + IN + i] = vals[i];
+            for(int i = 0; i < 12; i++) win[lane * W + IN + i] = vals[i];
         }
         __syncwarp();
         {
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_cons
                 for(int it = 0; it < NC; it++){
                     const int idx = lane + 32 * it;
                     const int r = idx / NC, c = idx - r * NC;
-                    if(r < rows_valid) gbase[r * D + c] = slab[r * W + c];
+                    if(r < rows_valid) gbase[r * D + c] = win[r * W + c];
                 }
             };
             if(!last) stream_rows(std::integral_constant<int, W>{});

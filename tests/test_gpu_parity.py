@@ -474,45 +474,48 @@ def port_final_rng(port, spec, pol, params, states, rng, T):
     return r
 
 
-@pytest.mark.parametrize("gemm", ["fp32", "tcgen05", "tcgen05-edited-parameters"])
-@pytest.mark.parametrize("spec", [B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR])
+@pytest.mark.parametrize("spec,gemm", [(s_, g_) for s_ in (B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR) for g_ in ("fp32", "tcgen05", "tcgen05-edited-parameters")]
+                         + [(B.SPEC_DEFAULT, "fp32"), (B.SPEC_DEFAULT_DR, "fp32"), (B.SPEC_DEFAULT_DR, "fp32-edited-parameters")])
 def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     """BASELINE config 4 shape: PPO actor (standardize -> 64 -> 64 -> 4, learned log_std), Gaussian sampling, auto-reset on
     terminated-or-step-limit with re-sampled parameters and state, dataset rows in the reference layout; CUDA-core kernel (k_collect)
-    and tensor-core kernel (k_collect_ts); 200 environments = one full tile + a ragged one"""
+    and tensor-core kernel (k_collect_ts); 200 environments = one full tile + a ragged one.  DEFAULT specs: the PPO zoo's environment
+    (rl/zoo/l2f/ppo.h: H = 16 action history, 82-wide observation, 97-float rows) on the CUDA-core kernel."""
     edited = gemm.endswith("edited-parameters")   # parameters written by the caller: the kernel may not assume the columns follow the nominal row
-    gemm = rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32
+    gemm = rb.GEMM_FP32_CUDA_CORES if gemm.startswith("fp32") else rb.GEMM_TCGEN05_3XTF32
     n, T, limit = 200, 40, 12
+    obs = port.observation_dim(spec)
     rs = np.random.RandomState(5)
-    blob = random_mlp_blob(rs, 22, 4, True, True)
+    blob = random_mlp_blob(rs, obs, 4, True, True)
     env = rb.VectorEnvironment(n, spec)
-    env_p = foundation_dr_env_params(port, spec) if spec == B.SPEC_RAPTOR_DR else port.nominal_parameters(spec)
+    env_p = foundation_dr_env_params(port, spec) if spec in (B.SPEC_RAPTOR_DR, B.SPEC_DEFAULT_DR) else port.nominal_parameters(spec)
     env.set_environment_parameters(env_p)
     env.initialize_rng(31, warmup=16)
     env.initial_parameters()
     env.initial_state()
-    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=gemm)
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=gemm)
     env.collect_reset()
     rng = env.get_rng()
     params, states = env.get_parameters(), env.get_state()
     if edited:
         env.set_parameters(params)
     data = env.collect(T, limit)
-    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
     ep_step = np.zeros(n, np.int32); ep_ret = np.zeros(n, np.float32); trunc = np.ones(n, np.uint8)
     want = port.collect(spec, pol, env_p, params, states, rng, ep_step, ep_ret, trunc, T, limit)
-    D = 37
+    D = obs + 15
     got3, want3 = data.reshape(T + 1, n, D), want.reshape(T + 1, n, D)
     assert np.array_equal(env.get_rng(), rng)                                     # every draw (resets, sampling) in the same order
-    assert np.array_equal(got3[:T, :, 32], want3[:T, :, 32])                       # terminated
-    assert np.array_equal(got3[:T, :, 33], want3[:T, :, 33])                       # truncated
-    assert want3[:T, :, 33].sum() >= n * (T // limit)                              # resets really happened
-    close(got3[..., :22], want3[..., :22], 2e-3, 2e-4, "observations (incl. the final row)")
-    close(got3[:T, :, 22:30], want3[:T, :, 22:30], 2e-3, 2e-3, "action means / actions")
-    close(got3[:T, :, 30], want3[:T, :, 30], 1e-3, 1e-3, "log-prob")
-    close(got3[:T, :, 31], want3[:T, :, 31], 2e-3, 2e-2, "reward")
-    assert np.all(got3[..., 34:] == 0)                                            # learner columns untouched
+    assert np.array_equal(got3[:T, :, obs + 10], want3[:T, :, obs + 10])           # terminated
+    assert np.array_equal(got3[:T, :, obs + 11], want3[:T, :, obs + 11])           # truncated
+    assert want3[:T, :, obs + 11].sum() >= n * (T // limit)                        # resets really happened
+    close(got3[..., :obs], want3[..., :obs], 2e-3, 2e-4, "observations (incl. the final row)")
+    close(got3[:T, :, obs:obs + 8], want3[:T, :, obs:obs + 8], 2e-3, 2e-3, "action means / actions")
+    close(got3[:T, :, obs + 8], want3[:T, :, obs + 8], 1e-3, 1e-3, "log-prob")
+    close(got3[:T, :, obs + 9], want3[:T, :, obs + 9], 2e-3, 2e-2, "reward")
+    assert np.all(got3[..., obs + 12:] == 0)                                      # learner columns untouched
     close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
+    close(env.get_state(), states, 5e-3, 2e-3, "final states (incl. the action-history ring)")
 
 
 @pytest.mark.parametrize("gemm", ["fp32", "tcgen05", "tcgen05-edited-parameters", "tcgen05-device-buffers"])
@@ -596,7 +599,8 @@ def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("spec,n,gemm", [(B.SPEC_RAPTOR, 256, "tcgen05"), (B.SPEC_RAPTOR_DR, 200, "tcgen05"), (B.SPEC_TEACHER_DR, 203, "tcgen05"), (B.SPEC_RAPTOR, 203, "fp32")])
+@pytest.mark.parametrize("spec,n,gemm", [(B.SPEC_RAPTOR, 256, "tcgen05"), (B.SPEC_RAPTOR_DR, 200, "tcgen05"), (B.SPEC_TEACHER_DR, 203, "tcgen05"), (B.SPEC_RAPTOR, 203, "fp32"),
+                                         (B.SPEC_DEFAULT, 203, "fp32"), (B.SPEC_DEFAULT_DR, 200, "tcgen05")])
 def test_learner_feed_vs_oracle(rb, port, spec, n, gemm):
     """critic values, GAE and the running normalizer on the collected dataset (the PPO loop step between collect and train) against the oracle,
     which is pinned bit-for-bit to the reference's own evaluate / estimate_generalized_advantages / running_normalizer update
@@ -612,7 +616,7 @@ def test_learner_feed_vs_oracle(rb, port, spec, n, gemm):
     critic = random_mlp_blob(rs, obs, 1, True, False)
     critic[-65:] *= 20.0        # values of order 1..10 so that the advantage recursion is exercised with realistic magnitudes
     env = rb.VectorEnvironment(n, spec)
-    env_p = foundation_dr_env_params(port, spec) if spec in (B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR) else port.nominal_parameters(spec)
+    env_p = foundation_dr_env_params(port, spec) if spec in (B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR, B.SPEC_DEFAULT_DR) else port.nominal_parameters(spec)
     env.set_environment_parameters(env_p)
     env.initialize_rng(3, warmup=16)
     env.initial_parameters()

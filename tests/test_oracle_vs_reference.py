@@ -146,7 +146,7 @@ def test_closed_loop_rollout(port, ref, spec, T):
 from conftest import random_mlp_blob  # noqa: E402
 
 
-@pytest.mark.parametrize("in_dim,out_dim,standardize", [(22, 4, True), (26, 4, False), (22, 1, True), (26, 1, True), (26, 8, False), (82, 4, True)])
+@pytest.mark.parametrize("in_dim,out_dim,standardize", [(22, 4, True), (26, 4, False), (22, 1, True), (26, 1, True), (26, 8, False), (82, 4, True), (82, 1, True)])
 def test_mlp_forward(port, ref, in_dim, out_dim, standardize):
     rs = np.random.RandomState(in_dim * 10 + out_dim)
     blob = random_mlp_blob(rs, in_dim, out_dim, standardize, False)
@@ -158,14 +158,14 @@ def test_mlp_forward(port, ref, in_dim, out_dim, standardize):
 
 
 def _collect_inputs(lib, spec, n, seed):
-    env_p = foundation_dr_env_params(lib, spec) if spec in (B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR) else lib.nominal_parameters(spec)
+    env_p = foundation_dr_env_params(lib, spec) if spec in (B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR, B.SPEC_DEFAULT_DR) else lib.nominal_parameters(spec)
     rng = lib.rng_states(seed, n, warmup=16)
     params = np.tile(env_p, (n, 1)).astype(np.float32)
     states = lib.sample_initial_state_n(spec, params, rng)
     return env_p, params, states, rng
 
 
-@pytest.mark.parametrize("spec", [B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR])
+@pytest.mark.parametrize("spec", [B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR, B.SPEC_TEACHER_DR, B.SPEC_DEFAULT, B.SPEC_DEFAULT_DR])
 def test_collect_gae_normalizer(port, ref, spec):
     n, T, limit = ref.ppo_sizes()
     obs = port.observation_dim(spec)
