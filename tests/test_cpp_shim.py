@@ -8,20 +8,77 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "readme_loop")
+PPO_EXE = os.path.join(ROOT, "tests", "cpp", "ppo_loop")
 
 
-def build_exe():
+def build_exe(name="readme_loop"):
     from raptor_b200 import build
     build.build()
     lib_dir = os.path.join(ROOT, "raptor_b200", "lib")
-    cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "readme_loop.cpp"),
-           "-o", EXE, "-L", lib_dir, "-lb200l2f", "-Wl,-rpath," + lib_dir]
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
+           "-o", os.path.join(ROOT, "tests", "cpp", name), "-L", lib_dir, "-lb200l2f", "-Wl,-rpath," + lib_dir]
     subprocess.run(cmd, check=True)
 
 
 def test_header_shim_compiles_and_links():
     build_exe()
     assert os.path.exists(EXE)
+
+
+def test_training_side_shim_compiles_and_reads_checkpoints():
+    """the runner / learner-feed / DAgger / checkpoint / JSON overloads of the shim compile (-Wall -Werror); its host-only part -- b200::load of a
+    checkpoint file, either format -- runs without a GPU and gives the published Raptor actor"""
+    import raptor_b200 as rb
+    build_exe("ppo_loop")
+    r = subprocess.run([PPO_EXE, "checkpoint", os.path.join(ROOT, "tests", "golden", "checkpoints", "raptor_checkpoint.h5")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    want = "arch %d in 22 hidden 16 out 4 floats 2084 sum %.9g name logs/2025-04-19_16-16-17" % (rb.POLICY_RAPTOR_GRU, float(np.sum(rb.raptor_policy_blob().astype(np.float64))))
+    assert r.stdout.strip() == want, (r.stdout, want)
+    r = subprocess.run([PPO_EXE, "checkpoint", os.path.join(ROOT, "README.md")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "memory[]" in r.stderr          # rl-tools idiom: errors terminate through assert_exit
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec_name", ["raptor", "default"])
+def test_cpp_ppo_loop_equals_the_python_mirror(tmp_path, spec_name):
+    """collect -> critic values -> GAE -> normalizer, two iterations, written in C++ against the shim: the dataset and the normalizer it ends with are
+    bit-identical to the same calls made through the Python mirror (one C ABI underneath; the parity of that ABI with the oracle is
+    tests/test_gpu_parity.py::test_ppo_collect_vs_oracle / test_learner_feed_vs_oracle)"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import raptor_b200 as rb
+    from conftest import random_mlp_blob
+    if not os.path.exists(PPO_EXE):
+        build_exe("ppo_loop")
+    spec, obs = (rb.SPEC_RAPTOR_DR, 22) if spec_name == "raptor" else (rb.SPEC_DEFAULT_DR, 82)
+    n, T, limit = 200, 24, 9
+    rs = np.random.RandomState(9)
+    actor, critic = random_mlp_blob(rs, obs, 4, True, True), random_mlp_blob(rs, obs, 1, True, False)
+    blobs, out = str(tmp_path / "blobs.f32"), str(tmp_path / "out.f32")
+    np.concatenate([actor, critic]).astype(np.float32).tofile(blobs)
+    r = subprocess.run([PPO_EXE, spec_name, blobs, out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out, np.float32)
+    D = obs + 15
+    got, got_mean, got_std = raw[:(T + 1) * n * D].reshape(-1, D), raw[(T + 1) * n * D:][:obs], raw[(T + 1) * n * D + obs:]
+    env = rb.VectorEnvironment(n, spec)
+    row = env.get_environment_parameters()
+    row[124:139] = np.array([1.5, 5.0, 40, 1200, 0.02, 5.0, 0.1, 0.03, 0.10, 0.03, 0.30, 0.005, 0.05, 0.0, 0.3], np.float32)
+    env.set_environment_parameters(row)
+    env.load_policy(actor, arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN)
+    env.load_critic(critic, standardize=1)
+    env.initialize_rng(77, warmup=0)
+    env.initial_parameters(); env.initial_state(); env.collect_reset()
+    mean, std, age = np.zeros(obs, np.float32), np.ones(obs, np.float32), 0
+    for _ in range(2):
+        data = env.collect(T, limit)
+        env.evaluate_values(data, T)
+        env.estimate_generalized_advantages(data, T, 0.99, 0.95, False)
+        age = env.normalizer_update(data, T, mean, std, age)
+    assert data[:T * n, obs + 11].sum() > 0 and np.abs(data[:, obs + 13]).max() > 0
+    assert np.array_equal(got.view(np.uint32), data.view(np.uint32))
+    assert np.array_equal(got_mean, mean) and np.array_equal(got_std, std) and age == 2
 
 
 @pytest.mark.gpu
