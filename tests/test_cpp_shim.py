@@ -49,3 +49,28 @@ def test_training_side_shim_compiles_and_reads_checkpoints(tmp_path):
     again = np.fromfile(str(tmp_path / "again.f32"), np.float32)
     assert np.array_equal(again, rb.parameters_from_json(text, np.full(145, -7.0, np.float32)))
     np.testing.assert_allclose(again, row, rtol=0, atol=6e-7)             # std::to_string keeps 6 decimals (L2F/operations_cpu.h:139-411)
+
+
+@pytest.mark.gpu
+def test_cpp_readme_loop_matches_golden(tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    if not os.path.exists(EXE):
+        build_exe()
+    out = str(tmp_path / "out.bin")
+    r = subprocess.run([EXE, os.path.join(ROOT, "raptor_b200", "data", "raptor_policy_2084.f32"), out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(out, np.float32)
+    T, n = 100, 8
+    actions = raw[: T * n * 4].reshape(T, n, 4)
+    states = raw[T * n * 4: T * n * 4 + n * 108].reshape(n, 108)
+    returns = raw[T * n * 4 + n * 108:]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "default_8x500.npz"))
+    scale = np.maximum(np.abs(g["actions"][:T]).max(axis=(0, 2)), 0.1)
+    assert (np.abs(actions - g["actions"][:T]).max(axis=(0, 2)) <= 1e-4 * scale).all()
+    want = g["states"][list(g["state_steps"]).index(T)]
+    for sl, floor in [(slice(0, 3), 0.1), (slice(3, 7), 1.0), (slice(7, 10), 0.1), (slice(10, 13), 0.1), (slice(26, 30), 0.1)]:
+        sc = np.maximum(np.abs(want[:, sl]).max(axis=1), floor)
+        assert (np.abs(states[:, sl] - want[:, sl]).max(axis=1) <= 1e-4 * sc).all()
+    np.testing.assert_allclose(returns, g["rewards"][:T].sum(0), rtol=1e-3, atol=1e-2)
