@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--rollout-steps", type=int, default=1000)
-    ap.add_argument("--cpu-envs-per-thread", type=int, default=2048)
+    ap.add_argument("--cpu-envs-per-thread", type=int, default=8192)   # ~9 s of CPU work per sample on the 16 host threads of the GPU box
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp32-gemm", action="store_true", help="actor GEMMs on the fp32 CUDA cores instead of tcgen05 (3xTF32)")
     ap.add_argument("--accurate-math", action="store_true")
