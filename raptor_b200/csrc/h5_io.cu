@@ -51,7 +51,7 @@ struct Reader {
         uint64_t a, b;
         if(!rd(at + 13, 1, a) || !rd(at + 14, 1, b)) return false;
         so = (int)a; sl = (int)b;
-        if((so != 4 && so != 8) || (sl != 4 && sl != 8)) return fail("unsupported size of offsets / lengths");
+        if(so != 8 || sl != 8) return fail("size of offsets / lengths " + std::to_string(so) + " / " + std::to_string(sl) + ": only the 8-byte sizes libhdf5 writes are read");
         uint64_t p = at + 24 + (v == 1 ? 4 : 0);                      // version 1 adds indexed-storage K + 2 reserved bytes
         if(!rd(p, so, base)) return false;
         if(undefined(base, so)) base = 0;

@@ -150,20 +150,24 @@ class _Writer:
         return self.header(msgs)
 
 
-def write(tree, fixed_strings=False, userblock=0):
+def write(tree, fixed_strings=False, userblock=0, superblock_version=0):
     """tree: Group or dict of the root's children.  userblock: 0 or a power of two >= 512 -- the superblock then sits at that offset and every
-    address is relative to it (base address), as h5py's `userblock_size` produces."""
+    address is relative to it (base address), as h5py's `userblock_size` produces.  superblock_version 1 adds the indexed-storage K field."""
     root = tree if isinstance(tree, Group) else Group(tree)
     w = _Writer(fixed_strings)
+    sb_len = 96 + (4 if superblock_version == 1 else 0)
+    w.buf = bytearray(sb_len + (-sb_len % 8))
     strings = []
     w.strings_of(root, strings)
     if not fixed_strings:
         w.write_gcol(strings)
     root_at = w.group(root)
     tree_at, heap_at = root._tree_heap
-    sb = b"\x89HDF\r\n\x1a\n" + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0)
+    sb = b"\x89HDF\r\n\x1a\n" + bytes([superblock_version, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0)
+    if superblock_version == 1:
+        sb += struct.pack("<HH", 32, 0)
     sb += struct.pack("<QQQQ", userblock, UNDEF, len(w.buf), UNDEF)
     sb += struct.pack("<QQII", 0, root_at, 1, 0) + struct.pack("<QQ", tree_at, heap_at)
-    assert len(sb) == 96
-    w.buf[:96] = sb
+    assert len(sb) == sb_len
+    w.buf[:sb_len] = sb
     return bytes(userblock) + bytes(w.buf)

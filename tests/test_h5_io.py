@@ -153,8 +153,8 @@ def test_datatypes_layouts_and_wide_groups():
         "i16_be": W.Dataset(np.array([-2, 300], np.int16), dtype=">i2"), "empty": W.Dataset(np.zeros((0, 4), np.float32)), "scalar": W.Dataset(np.float32(2.5)),
         "wide": W.Group({"d%02d" % i: np.full((2,), i, np.float32) for i in range(37)}),
     })}
-    for userblock in (0, 512, 2048):
-        c = rb.Checkpoint(text=W.write(tree, userblock=userblock))
+    for userblock, version in ((0, 0), (512, 0), (2048, 1), (0, 1)):
+        c = rb.Checkpoint(text=W.write(tree, userblock=userblock, superblock_version=version))
         t = {k[len(P + "example::"):]: v for k, v in c.tensors.items()}
         for k in ("f32", "f64", "f32_be", "f64_be", "compact"):
             assert np.array_equal(t[k].view(np.uint32), a.view(np.uint32)), k
@@ -172,6 +172,8 @@ def test_what_the_reader_does_not_read_is_named():
     good = raptor_bytes()
     with pytest.raises(rb.EngineError, match="superblock version 2"):
         rb.Checkpoint(text=good[:8] + b"\x02" + good[9:])
+    with pytest.raises(rb.EngineError, match="size of offsets / lengths 4 / 8"):
+        rb.Checkpoint(text=good[:13] + b"\x04" + good[14:])
     chunked = bytearray(W.write({"example": W.Group({"x": np.ones((4,), np.float32)})}))
     import struct
     at = chunked.find(struct.pack("<HHB3x", 8, 24, 0) + bytes([3, 1])) + 8                   # the layout message: version 3, class 1 (contiguous)
