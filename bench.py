@@ -35,12 +35,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 FLOP_ENV = 1100.0          # reference algorithm: RK4 (4 dynamics evaluations) + observe + reward, fp32
 FLOP_POLICY_GEMM = 3904.0  # 2 * (22*16 + 48*16 + 48*16 + 16*4) multiply-accumulates, tensor-core eligible
 FLOP_POLICY_GATES = 150.0
-# what k_rollout_raptor_ts EXECUTES on the CUDA cores per environment step (ncu, profiles/r01_ncu_k_rollout_raptor_ts_v9_default_bench.txt):
-# fadd + fmul + 2 ffma thread instructions, and all thread instructions.  The actor's GEMMs run on tcgen05 and are not in these counts.
-TS_CUDA_CORE_FLOP = 1283.0
-TS_THREAD_INSTRUCTIONS = 1302.0
-TS_WARP_INSTRUCTIONS = 1416.0       # smsp__inst_executed.sum / (65536 / 32 warps x 1000 steps), same capture
+FLOP_TEACHER_GEMM = 2.0 * (26 * 64 + 64 * 64 + 64 * 8)   # config 3 actor (SAC teacher 26-64-64-8)
+FLOP_PPO_GEMM = 2.0 * (22 * 64 + 64 * 64 + 64 * 4)       # config 4 actor (PPO 22-64-64-4)
 BYTES_PER_ENV_LAUNCH = 4.0 * (2 * (48 + 16 + 2) + 145)   # read+write state, hidden, rng; read parameters (once per launch)
+# What the kernels EXECUTE per environment step (warp instructions, CUDA-core fp32 FLOPs, MUFU operations, DRAM bytes per launch) is not written
+# here: tools/ncu_counters.py extracts it from the committed `ncu --set full` captures into profiles/kernel_counters.json, keyed by the kernel
+# name the engine reports (b200l2f_last_kernel) and the launch shape.  A launch without a capture reports those fractions as null.
+COUNTERS_PATH = os.path.join(ROOT, "profiles", "kernel_counters.json")
 
 DR_RANGES = [1.5, 5.0, 40, 1200, 0.02, 5.0, 0.1, 0.03, 0.10, 0.03, 0.30, 0.005, 0.05, 0.0, 0.3]  # sample_dynamics_parameters.cpp:48-64
 
@@ -107,6 +108,52 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_counters():
+    try:
+        return json.load(open(COUNTERS_PATH))
+    except Exception:
+        return {}
+
+
+def roofline_object(kernel, n, T, per_launch_s, peaks, counters, gemm_flop, tcgen05=True):
+    """the contract's roofline object for one fused kernel launch: the ceiling that binds first (instruction issue slots), with the other
+    ceilings -- MUFU, executed and algorithmic fp32, tensor pipe, HBM -- as sub-objects"""
+    rate = n * T / per_launch_s                                           # env-steps/s of this GPU
+    clk = peaks["sm_max_mhz"] * 1e6
+    c = counters.get("%s|%d|%d" % (kernel, n, T))
+    if c is None:                                                         # same kernel captured at another launch shape: per-step counts carry over, traffic does not
+        same = [v for k, v in counters.items() if k.split("|")[0] == kernel]
+        c = dict(same[0], dram_bytes_per_launch=None, source=same[0]["source"] + " (per-step counts of another launch shape)") if same else None
+    issue_peak = 148 * 4 * clk / 1e12                                     # warp instructions / s: one per scheduler and clock
+    fp32_peak = 148 * 128 * 2 * clk / 1e12
+    mufu_peak = 148 * 16 * clk / 1e12
+    algo = FLOP_ENV + FLOP_POLICY_GATES
+    r = {"bound": "issue", "achieved": None, "peak": issue_peak, "unit": "T warp-instructions/s", "frac": None, "traffic": None,
+         "kernel": kernel, "kernel_ms": 1e3 * per_launch_s,
+         "what": "instruction issue slots (148 SMs x 4 schedulers x max SM clock): the first ceiling this latency-bound CUDA-core kernel meets; achieved = executed warp "
+                 "instructions per 32 environment steps (ncu capture) x the live rate.  Fewer instructions per step lower this fraction at equal speed -- read it together with "
+                 "fp32_algorithmic, the fixed-work fraction",
+         "peak_source": "148 x 4 x %.0f MHz (%s)" % (peaks["sm_max_mhz"], peaks["source"])}
+    if c:
+        ach = rate / 32.0 * c["warp_instructions_per_warp_step"] / 1e12
+        r.update({"achieved": ach, "frac": ach / issue_peak, "traffic": c["dram_bytes_per_launch"], "counters_source": c["source"],
+                  "warp_instructions_per_warp_step": c["warp_instructions_per_warp_step"], "ncu_issue_slots_busy_pct": c.get("issue_slots_busy_pct"),
+                  "ncu_pipe_pct": c.get("pipe_pct"), "registers": c.get("registers")})
+        r["mufu"] = {"achieved": rate * c["mufu_per_env_step"] / 1e12, "peak": mufu_peak, "unit": "T MUFU ops/s", "frac": rate * c["mufu_per_env_step"] / 1e12 / mufu_peak,
+                     "per_env_step": c["mufu_per_env_step"]}
+        r["fp32_executed"] = {"achieved": rate * c["cuda_core_fp32_flop_per_env_step"] / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                              "frac": rate * c["cuda_core_fp32_flop_per_env_step"] / 1e12 / fp32_peak, "per_env_step": c["cuda_core_fp32_flop_per_env_step"],
+                              "note": "CUDA-core fp32 FLOPs actually executed (SASS op counts of the capture); the actor GEMMs run on the tensor pipe"}
+    r["fp32_algorithmic"] = {"achieved": rate * algo / 1e12, "peak": fp32_peak, "unit": "TFLOP/s", "frac": rate * algo / 1e12 / fp32_peak, "per_env_step": algo,
+                             "note": "SURVEY 8(d): environment + gate FLOPs of the reference algorithm (fixed work) against 148 SM x 128 lanes x 2 x max clock"}
+    r["tensor"] = {"achieved": rate * gemm_flop / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": rate * gemm_flop / 1e12 / peaks["bf16_tflops_sustained"],
+                   "note": "algorithmic GEMM FLOPs of the actor against the measured sustained bf16 peak (TF32 runs at half of it, the 3xTF32 split issues 3 products)" if tcgen05 else "actor on CUDA cores"}
+    hbm = n * BYTES_PER_ENV_LAUNCH / per_launch_s / 1e9
+    r["hbm"] = {"achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": n * BYTES_PER_ENV_LAUNCH}
+    r["algorithmic_flop_per_env_step"] = FLOP_ENV + gemm_flop + FLOP_POLICY_GATES
+    return r
+
+
 def cpu_reference_rate(envs_per_thread, T, spec, seed=1):
     """times the reference's CPU implementation (all host threads) on a bounded sample; returns (env-steps/s, dict)"""
     from oracle import binding as B
@@ -165,6 +212,92 @@ def run_reference(args, rank, world):
     return 0
 
 
+def mlp_blob(rs, i, o, std, ls):
+    parts = []
+    if std:
+        parts += [np.zeros(i), np.ones(i)]
+    for (oo, ii) in [(64, i), (64, 64), (o, 64)]:
+        b = np.sqrt(6.0 / ii)
+        parts += [rs.uniform(-b, b, (oo, ii)).ravel() * (0.3 if oo == o else 1.0), np.zeros(oo)]
+    if ls:
+        parts.append(np.log(np.full(4, 0.5)))
+    return np.concatenate(parts).astype(np.float32)
+
+
+def run_other_configs(rb, torch, dev, stream, flush, rank, world, use_dist):
+    """BASELINE.json configs 3, 4 and 5 (this GPU's shard), each one fused launch timed with CUDA events after 3 warm-ups, L2 flushed in between; values are whole-job
+    (sum over ranks / max time).  Returns the `configs` object of the JSON line."""
+    if use_dist:
+        import torch.distributed as dist
+    peaks, counters = load_peaks(), load_counters()
+    rs = np.random.RandomState(0)
+
+    def timed(fn, reset, steps=3, warmup=3):
+        for _ in range(warmup):
+            reset(); fn()
+        ms = []
+        for _ in range(steps):
+            reset(); flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            torch.cuda.synchronize(dev)
+            ms.append(a.elapsed_time(b))
+        t = torch.tensor([sum(ms) / len(ms)], dtype=torch.float64, device=dev)
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dr_env(n, spec, seed):
+        env = rb.VectorEnvironment(n, spec, device=dev.index, first_env_id=rank * n, stream=stream.cuda_stream)
+        row = env.get_environment_parameters(); row[124:139] = np.array(DR_RANGES, np.float32); env.set_environment_parameters(row)
+        env.initialize_rng(seed, warmup=16)
+        return env
+    out = {}
+    # ---- config 3: 1 048 576 envs, per-env DR (sample_initial_parameters), random-init MLP actor (SAC-teacher shape 26-64-64-8), T = 500 (SURVEY 8d)
+    n, T = 1048576, 500
+    env = dr_env(n, rb.SPEC_TEACHER_DR, 3)
+    env.sample_initial_parameters(); env.sample_initial_state()
+    env.load_policy(mlp_blob(rs, 26, 8, False, False), arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=rb.GEMM_TCGEN05_3XTF32)
+    s0 = torch.from_numpy(env.get_state()).to(dev); ret = torch.zeros(n, device=dev)
+    ms = timed(lambda: env.rollout(T, out={"returns": ret}), lambda: env.set_state(s0))
+    k = env.last_kernel()
+    out["config3"] = {"workload": "BASELINE configs[2]: %d envs/GPU x %d steps, per-env domain-randomised params, random-init MLP actor 26-64-64-8 (+ squash, evaluation mode)" % (n, T),
+                      "value": n * world * T / ms * 1e3, "unit": "env-steps/s", "ms_per_launch": ms, "kernel": k,
+                      "roofline": roofline_object(k, n, T, ms / 1e3, peaks, counters, FLOP_TEACHER_GEMM)}
+    del env, s0, ret
+    # ---- config 4: 262 144 envs x 256-step PPO collection with obs / action / reward / done write-back into the HBM dataset
+    n, T = 262144, 256
+    env = dr_env(n, rb.SPEC_RAPTOR_DR, 4)
+    env.initial_parameters(); env.initial_state()
+    env.load_policy(mlp_blob(rs, 22, 4, True, True), arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=rb.GEMM_TCGEN05_3XTF32)
+    data = torch.zeros(((T + 1) * n, 37), dtype=torch.float32, device=dev)
+    ms = timed(lambda: env.collect(T, 500, data), lambda: env.collect_reset())
+    written = n * T * 34 * 4 + n * 22 * 4
+    k = env.last_kernel()
+    rl = roofline_object(k, n, T, ms / 1e3, peaks, counters, FLOP_PPO_GEMM)
+    rl["hbm"] = {"achieved": written / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": written / ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": written,
+                 "note": "dataset rows written (34 of the 37 floats per row, on_policy_runner.h:42-64)"}
+    out["config4"] = {"workload": "BASELINE configs[3]: %d envs/GPU x %d-step PPO rollout collection, PPO actor 22-64-64-4 (standardize, learned log_std), DR resets, dataset [(T+1)N, 37] in HBM" % (n, T),
+                      "value": n * world * T / ms * 1e3, "unit": "env-steps/s", "ms_per_launch": ms, "kernel": k, "dataset_bytes_written": written, "roofline": rl,
+                      "mean_reward": float(data[: T * n, 31].mean().item()), "truncated_fraction": float(data[: T * n, 33].mean().item())}
+    del env, data
+    # ---- config 5: 1 048 576 envs per GPU, Raptor checkpoint (weak scaling across the ranks of this job)
+    n, T = 1048576, 1000
+    env = dr_env(n, rb.SPEC_RAPTOR_DR, 20250925)
+    env.sample_initial_parameters(); env.sample_initial_state(); env.load_policy(gemm=rb.GEMM_TCGEN05_3XTF32)
+    s0 = torch.from_numpy(env.get_state()).to(dev); ret = torch.zeros(n, device=dev)
+
+    def reset5():
+        env.set_state(s0); env.policy_reset()
+    ms = timed(lambda: env.rollout(T, out={"returns": ret}), reset5)
+    k = env.last_kernel()
+    out["config5"] = {"workload": "BASELINE configs[4]: %d envs sharded across %d GPU(s) (%d per GPU), Raptor GRU policy, %d-step rollout, weak scaling" % (n * world, world, n, T),
+                      "value": n * world * T / ms * 1e3, "unit": "env-steps/s", "ms_per_launch": ms, "kernel": k, "n_gpus": world,
+                      "roofline": roofline_object(k, n, T, ms / 1e3, peaks, counters, FLOP_POLICY_GEMM)}
+    del env, s0, ret
+    return out
+
+
 def workload_config(args, world):
     return {"workload": "BASELINE configs[1]: %d envs/GPU x %d-step closed-loop rollout, Raptor GRU policy (Dense22-16/GRU16/Dense16-4), foundation-policy env spec (H=1, OBS 22, Langevin targets), per-env domain-randomised dynamics" % (args.envs_per_gpu, args.rollout_steps),
             "envs_per_gpu": args.envs_per_gpu, "rollout_steps": args.rollout_steps, "global_envs": args.envs_per_gpu * world,
@@ -182,6 +315,7 @@ def main():
     ap.add_argument("--rollout-steps", type=int, default=1000)
     ap.add_argument("--cpu-envs-per-thread", type=int, default=8192)   # ~9 s of CPU work per sample on the 16 host threads of the GPU box
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs 3 / 4 / 5 block of the JSON line")
     ap.add_argument("--fp32-gemm", action="store_true", help="actor GEMMs on the fp32 CUDA cores instead of tcgen05 (3xTF32)")
     ap.add_argument("--accurate-math", action="store_true")
     args = ap.parse_args()
@@ -265,26 +399,45 @@ def main():
     value = total_env_steps / t_total
     mean_return = float(returns_dev.mean().item())
 
-    # ---- end-to-end through the public API with host buffers ("e2e"): inputs and results live in PINNED host memory (numpy views of
-    # ---- torch pinned tensors), every step copies them H2D / D2H inside the timed region
+    kernel_name = env.last_kernel()
+
+    # ---- end-to-end through the public API with host buffers ("e2e"): inputs and results live in PINNED host memory (numpy views of torch pinned
+    # ---- tensors); every step uploads its parameters + initial states (H2D) and downloads the final states + episode returns (D2H) inside the timed
+    # ---- region.  The transfers go through the engine's asynchronous twins (b200l2f_set_*_async / get_state_async / copy_to_host_async): the upload
+    # ---- for rollout k+1 and the download of rollout k run on the handle's copy streams while the main stream executes, the host waits once per
+    # ---- step for the downloads of the PREVIOUS step (double-buffered results) -- the way a training loop that consumes rollouts would drive it.
     def pinned(a):
         t = torch.from_numpy(a).pin_memory()
         return t.numpy(), t
     params0, _keep_p = pinned(params0)
     state0, _keep_s = pinned(state0)
-    host_state, _keep_hs = pinned(state0.copy())
-    host_ret, _keep_hr = pinned(np.zeros(n, np.float32))
-    for _ in range(2):
-        env.set_parameters(params0); env.set_state(state0); env.policy_reset(); env.rollout(T, out={"returns": host_ret}); env.get_state(out=host_state)
+    host_state = [pinned(state0.copy()) for _ in range(2)]
+    host_ret = [pinned(np.zeros(n, np.float32)) for _ in range(2)]
+    ret_dev = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(2)]
+
+    def e2e_run(steps):
+        consumed = 0.0
+        env.set_parameters_async(params0); env.set_state_async(state0)              # upload for step 0
+        for k in range(steps):
+            b = k & 1
+            env.policy_reset()
+            env.rollout(T, out={"returns": ret_dev[b]})                              # main stream, asynchronous
+            if k >= 1:                                                               # the ONE host wait of the step: downloads of step k-1 (rollout k is already queued)
+                env.transfers_synchronize(uploads=False, downloads=True)
+                consumed += float(host_ret[(k - 1) & 1][0][0]) + float(host_state[(k - 1) & 1][0][0, 0])   # the host reads the results of step k-1
+            env.get_state_async(host_state[b][0])                                    # D2H  n*48*4, ordered after rollout k
+            env.copy_to_host_async(host_ret[b][0], ret_dev[b])                       # D2H  n*4 (episode returns)
+            if k + 1 < steps:
+                env.set_parameters_async(params0)                                    # H2D  n*145*4 for step k+1: overlaps rollout k
+                env.set_state_async(state0)                                          # H2D  n*48*4
+        env.transfers_synchronize()
+        env.synchronize()
+        return consumed
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        env.set_parameters(params0)                       # H2D  n*145*4
-        env.set_state(state0)                             # H2D  n*48*4
-        env.policy_reset()
-        env.rollout(T, out={"returns": host_ret})         # D2H  n*4 (episode returns)
-        env.get_state(out=host_state)                     # D2H  n*48*4
+    e2e_steps = max(2, min(args.steps, 8))
+    e2e_run(e2e_steps)
     torch.cuda.synchronize(dev)
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if use_dist:
@@ -292,40 +445,19 @@ def main():
     e2e_value = float(n) * world * T * e2e_steps / float(t_e2e.item())
     h2d = n * (145 + env.STATE_DIM) * 4
     d2h = n * (env.STATE_DIM + 1) * 4
+    e2e_check = float(np.abs(host_ret[(e2e_steps - 1) & 1][0] - returns_dev.cpu().numpy()).max())   # the pipeline computed the same rollout as the resident loop
+
+    # ---- the other BASELINE configs on this GPU (3: 1M envs + teacher MLP, 4: PPO collection with write-back, 5: the 1M-env Raptor shard), CUDA-event timed
+    configs = None
+    if not args.no_configs:
+        del env
+        configs = run_other_configs(rb, torch, dev, stream, flush, rank, world, use_dist)
 
     if rank == 0:
         peaks = load_peaks()
         per_launch_s = t_total / args.steps
-        steps_per_s_gpu = n * T / per_launch_s
-        tensor_ach = steps_per_s_gpu * FLOP_POLICY_GEMM / 1e12
-        hbm_ach = n * BYTES_PER_ENV_LAUNCH / per_launch_s / 1e9
-        fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-        issue_peak = 148 * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12          # thread instructions / s: 4 schedulers x 32 lanes per SM and clock
-        if args.tcgen05:
-            fp32_ach = steps_per_s_gpu * TS_CUDA_CORE_FLOP / 1e12
-            fp32_note = "executed CUDA-core fp32 FLOPs of k_rollout_raptor_ts (ncu op counts per env-step x measured rate); the actor GEMMs are on the tensor pipe"
-            warp_issue_peak = 148 * 4 * peaks["sm_max_mhz"] * 1e6 / 1e12    # warp instructions / s: one per scheduler and clock, 4 schedulers per SM
-            warp_issue_ach = steps_per_s_gpu / 32.0 * TS_WARP_INSTRUCTIONS / 1e12
-            issue = {"achieved": warp_issue_ach, "peak": warp_issue_peak, "unit": "T warp-instructions/s", "frac": warp_issue_ach / warp_issue_peak,
-                     "warp_instructions_per_warp_step": TS_WARP_INSTRUCTIONS, "thread_instructions_per_env_step": TS_THREAD_INSTRUCTIONS,
-                     "note": "the ceiling that binds this kernel: instruction issue slots (148 SMs x 4 schedulers x max SM clock); executed warp instructions per "
-                             "warp-step (32 environments) from the committed ncu capture, rate measured live; ncu's own sm__inst_issued is 61.1 % of active cycles"}
-        else:
-            fp32_ach = steps_per_s_gpu * (FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES) / 1e12
-            fp32_note = "algorithmic fp32 FLOPs (SURVEY 8d) of the CUDA-core kernel, actor GEMMs included"
-            issue = None
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` capture of this exact configuration
-        # (39.42 MB read + 2.02 MB written: parameters / state in, state out; the per-chunk hand-over lives in the 126 MB L2)
-        traffic, traffic_src = None, None
-        if args.tcgen05 and n == 65536 and T == 1000 and not args.accurate_math:
-            traffic, traffic_src = 41.44e6, "profiles/r01_ncu_k_rollout_raptor_ts_v9_default_bench.txt"
-        roofline = {"bound": "tensor", "achieved": tensor_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tensor_ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long launch)",
-                    "kernel": "k_rollout_raptor_ts" if args.tcgen05 else "k_rollout_raptor", "kernel_ms": 1e3 * per_launch_s,
-                    "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": n * BYTES_PER_ENV_LAUNCH},
-                    "fp32_issue": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak, "note": fp32_note},
-                    "issue": issue,
-                    "algorithmic_flop_per_env_step": FLOP_ENV + FLOP_POLICY_GEMM + FLOP_POLICY_GATES}
+        counters = load_counters()
+        roofline = roofline_object(kernel_name, n, T, per_launch_s, peaks, counters, FLOP_POLICY_GEMM, tcgen05=args.tcgen05)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -335,9 +467,10 @@ def main():
         line = {"metric": "quadrotor env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world),
-                "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "how": "asynchronous C-ABI transfers from / to pinned host buffers, overlapped with the kernels (one host wait per step); returns == resident run: max |diff| %.1e" % e2e_check},
                 "gpu_launches": int(l_sum.item()), "gpu_launches_incl_input_reset": int(launches) * world,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
                 "wall_s_timed_region": wall, "mean_episode_return": mean_return}
         print(json.dumps(line), flush=True)
     if use_dist:

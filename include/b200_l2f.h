@@ -70,7 +70,11 @@ enum { B200L2F_FLAG_ACCURATE_MATH = 1 /* expf/tanhf/IEEE division in the actor i
  *   DEFAULT   l2f::Specification<float,size_t>: H=16, OBS 82, no Langevin target           (L2F/parameters/default.h:29-176)
  *   RAPTOR    foundation-policy post-training env: H=1, OBS 22, Langevin target            (src/foundation_policy/post_training/environment.h:13-46)
  *   TEACHER   foundation-policy pre-training env:  H=1, OBS 26, Langevin target            (src/foundation_policy/pre_training/environment.h:58-90)
- *   *_DR      same state/observation with DEFAULT_DOMAIN_RANDOMIZATION_OPTIONS<true>         (L2F/parameters/default.h:16-26)            */
+ *   *_DR      same state/observation with DEFAULT_DOMAIN_RANDOMIZATION_OPTIONS<true>         (L2F/parameters/default.h:16-26)
+ *             Note: the reference's nominal DR ranges leave rotor_time_constant_{rising,falling} at 0, and sample_initial_parameters asserts on a
+ *             zero range (10_sample_initial_parameters.h:176-189); as in the reference, a *_DR handle therefore needs its DR ranges set through
+ *             b200l2f_set_environment_parameters (row entries 124..138) before b200l2f_sample_initial_parameters / a collection with resets --
+ *             e.g. the foundation-policy ranges of sample_dynamics_parameters.cpp:48-64 -- otherwise those calls return B200L2F_ERR_STATE.            */
 enum { B200L2F_SPEC_DEFAULT = 0, B200L2F_SPEC_DEFAULT_DR = 1, B200L2F_SPEC_RAPTOR = 2, B200L2F_SPEC_TEACHER = 3, B200L2F_SPEC_RAPTOR_DR = 4, B200L2F_SPEC_TEACHER_DR = 5 };
 
 /* Actor architectures.
@@ -125,6 +129,7 @@ int  b200l2f_destroy(b200l2f_handle* h);
 const char* b200l2f_last_error(const b200l2f_handle* h); /* h may be NULL: error of the last failed create on this thread */
 int  b200l2f_synchronize(b200l2f_handle* h);
 void* b200l2f_stream(b200l2f_handle* h);                 /* the cudaStream_t all work is enqueued on */
+const char* b200l2f_last_kernel(const b200l2f_handle* h);      /* name of the fused kernel the last b200l2f_rollout / b200l2f_collect launched (profiling tools; "" before the first) */
 int  b200l2f_state_dim(const b200l2f_handle* h);
 int  b200l2f_observation_dim(const b200l2f_handle* h);
 int  b200l2f_action_history_length(const b200l2f_handle* h);
@@ -157,6 +162,19 @@ int b200l2f_sample_initial_state(b200l2f_handle* h, int slot);
 int b200l2f_get_state(b200l2f_handle* h, int slot, float* rows, int memspace);           /* [n_envs, STATE_DIM] */
 int b200l2f_set_state(b200l2f_handle* h, int slot, const float* rows, int memspace);
 int b200l2f_copy_state(b200l2f_handle* h, int dst_slot, int src_slot);                   /* state.assign(next_state), R/README.md:99 */
+
+/* ---- asynchronous twins of set_parameters / set_state / get_state for callers that feed one rollout after another from host memory (the reference
+ * has no counterpart: its CPU environments live in host memory, rl_tools::copy(device_cpu, device_gpu, ...) is synchronous).  The bytes move on the
+ * handle's own copy streams through staging buffers; only the device-side transpose is ordered on the main stream, in call order -- so an upload
+ * issued after rollout k is enqueued overlaps that kernel and takes effect before rollout k+1, and a download issued after rollout k leaves the host
+ * free to enqueue rollout k+1 at once.  Host buffers must be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory; pageable memory falls
+ * back to the synchronous call) and must not be touched until b200l2f_transfers_synchronize(h, which) returns (which: 1 = uploads, 2 = downloads, 3 = both).
+ * copy_to_host_async: any device buffer the main stream produced (e.g. the `returns` of b200l2f_rollout) -> page-locked host memory, same ordering. */
+int b200l2f_set_parameters_async(b200l2f_handle* h, const float* rows_pinned);           /* [n_envs, 145] */
+int b200l2f_set_state_async(b200l2f_handle* h, int slot, const float* rows_pinned);      /* [n_envs, STATE_DIM] */
+int b200l2f_get_state_async(b200l2f_handle* h, int slot, float* rows_pinned);
+int b200l2f_copy_to_host_async(b200l2f_handle* h, void* dst_pinned, const void* src_device, size_t bytes);
+int b200l2f_transfers_synchronize(b200l2f_handle* h, int which);
 
 /* ---- rl_tools::observe (L2F/operations_generic.h:87-92, L2F/operations_generic/40_observe.h); vector.observe (R/README.md:96).
  * observations: [n_envs, ld] with ld >= OBSERVATION_DIM */

@@ -54,6 +54,7 @@ SYMBOLS = {
     "b200l2f_last_error": (ctypes.c_char_p, [vp]),
     "b200l2f_synchronize": (c_int, [vp]),
     "b200l2f_stream": (vp, [vp]),
+    "b200l2f_last_kernel": (ctypes.c_char_p, [vp]),
     "b200l2f_state_dim": (c_int, [vp]),
     "b200l2f_observation_dim": (c_int, [vp]),
     "b200l2f_action_history_length": (c_int, [vp]),
@@ -73,6 +74,11 @@ SYMBOLS = {
     "b200l2f_sample_initial_state": (c_int, [vp, c_int]),
     "b200l2f_get_state": (c_int, [vp, c_int, vp, c_int]),
     "b200l2f_set_state": (c_int, [vp, c_int, vp, c_int]),
+    "b200l2f_set_parameters_async": (c_int, [vp, vp]),
+    "b200l2f_set_state_async": (c_int, [vp, c_int, vp]),
+    "b200l2f_get_state_async": (c_int, [vp, c_int, vp]),
+    "b200l2f_copy_to_host_async": (c_int, [vp, vp, vp, ctypes.c_size_t]),
+    "b200l2f_transfers_synchronize": (c_int, [vp, c_int]),
     "b200l2f_copy_state": (c_int, [vp, c_int, c_int]),
     "b200l2f_observe": (c_int, [vp, c_int, vp, c_int, c_int]),
     "b200l2f_step": (c_int, [vp, c_int, vp, c_int, vp, c_int]),

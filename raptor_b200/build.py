@@ -25,6 +25,7 @@ SOURCES = {
     "rollout_fp32.cu": [],
     "rollout_tc.cu": TC,
     "rollout_ts.cu": TC,
+    "rollout_x2.cu": TC + ["rollout_x2.cuh"],
     "rollout_mlp.cu": [],
     "rollout_mlp_ts.cu": TC + ["mlp_tc.cuh"],
     "collect.cu": [],

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <iterator>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -290,6 +291,7 @@ std::string build_policy(const Ckpt& c, const std::string& root, b200l2f_policy_
         const auto *wi = T(layers[1].ns + "::weights_input"), *bi = T(layers[1].ns + "::biases_input"), *wh = T(layers[1].ns + "::weights_hidden"), *bh = T(layers[1].ns + "::biases_hidden");
         const auto *h0 = T(layers[1].ns + "::initial_hidden_state");
         const auto *w2 = T(layers[2].ns + "::weights"), *b2 = T(layers[2].ns + "::biases");
+        if(!w1 || !b1 || !wi || !wh || !w2 || !b2) return "Dense / GRU layer is missing weights or biases";
         if(!bi || !bh || !h0) return "GRU layer is missing biases_input / biases_hidden / initial_hidden_state";
         if(w1->dims.size() != 2 || wi->dims.size() != 2 || wh->dims.size() != 2 || w2->dims.size() != 2) return "weight tensors must be rank 2";
         const int64_t hid = w1->dims[0], in = w1->dims[1], out = w2->dims[0];
@@ -314,9 +316,13 @@ std::string build_policy(const Ckpt& c, const std::string& root, b200l2f_policy_
     if(has(c, m + "::hidden_layer_1::weights") || !has(c, m + "::hidden_layer_0::weights")) return "engine runs 3-layer MLPs (one hidden-to-hidden layer) only";
     const auto *w1 = T(m + "::input_layer::weights"), *b1 = T(m + "::input_layer::biases"), *w2 = T(m + "::hidden_layer_0::weights"), *b2 = T(m + "::hidden_layer_0::biases"),
                *w3 = T(m + "::output_layer::weights"), *b3 = T(m + "::output_layer::biases"), *ls = T(m + "::log_std");
+    if(!w1 || !w2 || !w3) return "MLP layer without weights";
     if(!b1 || !b2 || !b3) return "MLP layer without biases";
+    if(w1->dims.size() != 2 || w2->dims.size() != 2 || w3->dims.size() != 2) return "weight tensors must be rank 2";   // dims come from the file (.h5) / the export's SHAPE
     const int64_t hid = w1->dims[0], in = w1->dims[1], out = w3->dims[0];
     if(w2->dims[0] != hid || w2->dims[1] != hid || w3->dims[1] != hid) return "MLP shapes are inconsistent";
+    if((int64_t)b1->data.size() != hid || (int64_t)b2->data.size() != hid || (int64_t)b3->data.size() != out || (ls && (int64_t)ls->data.size() != out))
+        return "MLP bias / log_std sizes do not match the weights";
     if(mean && ((int64_t)mean->data.size() != in || (int64_t)prec->data.size() != in)) return "standardize statistics do not match the MLP input";
     const std::string hidden_act = activation_of(c, m, 0), out_act = activation_of(c, m, 1);
     if((!hidden_act.empty() && hidden_act != "RELU") || (!out_act.empty() && out_act != "IDENTITY")) return "engine runs ReLU hidden / identity output MLPs only";
@@ -374,6 +380,15 @@ void from_h5(const H5Contents& f, Ckpt& c){
     }
 }
 
+// No C++ exception may cross the C ABI (a corrupted file can still provoke std::length_error / bad_alloc inside the containers): every entry point
+// that allocates or parses runs its body under guarded(), which turns an exception into an error code + message.
+template <class F>
+int guarded(const char* what, F&& body){
+    try{ return body(); }
+    catch(const std::exception& e){ return cfail(std::string(what) + ": " + e.what()); }
+    catch(...){ return cfail(std::string(what) + ": unknown C++ exception"); }
+}
+
 }  // namespace
 
 extern "C" {
@@ -381,24 +396,28 @@ extern "C" {
 int b200l2f_checkpoint_parse_h5(const void* bytes, size_t length, b200l2f_checkpoint** out){
     if(!bytes || !out) return cfail("checkpoint_parse_h5: null argument");
     *out = nullptr;
-    H5Contents f; std::string err;
-    if(!h5_read((const unsigned char*)bytes, length, f, err)) return cfail("checkpoint_parse_h5: " + err);
-    auto* c = new b200l2f_checkpoint();
-    from_h5(f, *c);
-    if(c->tensors.empty()){ delete c; return cfail("checkpoint_parse_h5: the file holds no numeric datasets"); }
-    *out = c;
-    return B200L2F_OK;
+    return guarded("checkpoint_parse_h5", [&]() -> int {
+        H5Contents f; std::string err;
+        if(!h5_read((const unsigned char*)bytes, length, f, err)) return cfail("checkpoint_parse_h5: " + err);
+        std::unique_ptr<b200l2f_checkpoint> c(new b200l2f_checkpoint());
+        from_h5(f, *c);
+        if(c->tensors.empty()) return cfail("checkpoint_parse_h5: the file holds no numeric datasets");
+        *out = c.release();
+        return B200L2F_OK;
+    });
 }
 int b200l2f_checkpoint_parse(const char* text, size_t length, b200l2f_checkpoint** out){
     if(!text || !out) return cfail("checkpoint_parse: null argument");
     if(h5_has_signature((const unsigned char*)text, length)) return b200l2f_checkpoint_parse_h5(text, length, out);   // checkpoint.h5 handed to the generic entry
     *out = nullptr;
-    auto* c = new b200l2f_checkpoint();
-    Scanner s{text, text + length, *c, {}, {}, 4, text};
-    if(!s.run()){ const std::string e = "checkpoint_parse: " + c->err; delete c; return cfail(e); }
-    if(c->tensors.empty()){ delete c; return cfail("checkpoint_parse: no `memory[]` tensors found (not an rl-tools code export?)"); }
-    *out = c;
-    return B200L2F_OK;
+    return guarded("checkpoint_parse", [&]() -> int {
+        std::unique_ptr<b200l2f_checkpoint> c(new b200l2f_checkpoint());
+        Scanner s{text, text + length, *c, {}, {}, 4, text};
+        if(!s.run()) return cfail("checkpoint_parse: " + c->err);
+        if(c->tensors.empty()) return cfail("checkpoint_parse: no `memory[]` tensors found (not an rl-tools code export?)");
+        *out = c.release();
+        return B200L2F_OK;
+    });
 }
 int b200l2f_checkpoint_free(b200l2f_checkpoint* c){ delete c; return B200L2F_OK; }
 int b200l2f_checkpoint_tensor_count(const b200l2f_checkpoint* c){ return c ? (int)c->tensors.size() : 0; }
@@ -426,16 +445,18 @@ int b200l2f_checkpoint_string_at(const b200l2f_checkpoint* c, int index, const c
 }
 int b200l2f_checkpoint_policy(const b200l2f_checkpoint* c, const char* root, b200l2f_policy_desc* desc, float* blob, size_t capacity, size_t* n_floats){
     if(!c || !desc) return cfail("checkpoint_policy: null argument");
-    std::vector<float> b; b200l2f_policy_desc d;
-    const std::string err = build_policy(*c, root && *root ? root : "rl_tools::checkpoint::actor", d, b);
-    if(!err.empty()){ create_error() = "checkpoint_policy: " + err; return B200L2F_ERR_UNSUPPORTED; }
-    *desc = d;
-    if(n_floats) *n_floats = b.size();
-    if(blob){
-        if(capacity < b.size()) return cfail("checkpoint_policy: blob capacity " + std::to_string(capacity) + " < " + std::to_string(b.size()) + " floats");
-        std::memcpy(blob, b.data(), sizeof(float) * b.size());
-    }
-    return B200L2F_OK;
+    return guarded("checkpoint_policy", [&]() -> int {
+        std::vector<float> b; b200l2f_policy_desc d;
+        const std::string err = build_policy(*c, root && *root ? root : "rl_tools::checkpoint::actor", d, b);
+        if(!err.empty()){ create_error() = "checkpoint_policy: " + err; return B200L2F_ERR_UNSUPPORTED; }
+        *desc = d;
+        if(n_floats) *n_floats = b.size();
+        if(blob){
+            if(capacity < b.size()) return cfail("checkpoint_policy: blob capacity " + std::to_string(capacity) + " < " + std::to_string(b.size()) + " floats");
+            std::memcpy(blob, b.data(), sizeof(float) * b.size());
+        }
+        return B200L2F_OK;
+    });
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@ int launch_collect_fp32(b200l2f_handle* h, const CollectArgs& a){
         const size_t smem = sizeof(float) * (MlpImg<IN, 4>::SIZE + (size_t)P_DYN_DIM * BLOCK + (size_t)CollectSlab<IN>::FLOATS * (BLOCK / 32));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a);
+        h->last_kernel = "k_collect";
         LAUNCH_CHECK();
         return (int)B200L2F_OK;
     };

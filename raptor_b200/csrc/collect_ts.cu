@@ -19,6 +19,7 @@ int launch_collect_ts(b200l2f_handle* h, const CollectArgs& a, bool follow, bool
         const int n_tiles = grid_for(a.n, BLOCK);
         const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;    // ~110 KB smem, 256 TMEM columns per CTA -> 2 CTAs/SM, persistent tile loop
         kern<<<grid, BLOCK, SM::TOTAL_COLLECT, h->stream>>>(a, h->d_mlp_tc_image, h->d_sched);
+        h->last_kernel = "k_collect_ts";
         LAUNCH_CHECK();
         return (int)B200L2F_OK;
     };

@@ -40,6 +40,8 @@ int b200l2f_dagger_gather(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_re
     if((rc = refresh_features(h))) return rc;
     if(h->features & 1) return fail(h, B200L2F_ERR_UNSUPPORTED, "dagger_gather: the dataset observations are noise-free (post_training/config.h:41-48); set the observation / action noise to 0");
     const size_t n = (size_t)h->n, T = (size_t)n_steps;
+    // dataset row offsets (exclusive scan of the episode lengths) and rows_added are 32-bit: the total, at most n * T rows, must fit
+    if((int64_t)h->n * (int64_t)n_steps >= ((int64_t)1 << 31)) return fail(h, B200L2F_ERR_ARGUMENT, "dagger_gather: n_envs * n_steps must stay below 2^31 dataset rows");
     // ---- 1. sample_trajectories (helper.h:6-41): the student's closed-loop rollout, states and termination flags recorded step-major
     const size_t need_states = (T + 1) * n * h->sdim;
     if(need_states > h->dg_state_floats){

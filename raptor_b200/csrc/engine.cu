@@ -78,8 +78,8 @@ int refresh_features(b200l2f_handle* h){
 // Chunk count: 16 (chunks of >= 32 steps).  A model of the launch as ceil(n_tiles c / cap) synchronous rounds predicts c = 13 for 512 tiles on 444
 // slots (15 full rounds, 1155 step-times against 1197 for c = 16), but the queue is not round-synchronous -- measured on B200 at T = 1000:
 // c = 16 4.433 ms, 13 4.490, 6 4.480, 25 4.482 (profiles/r01_s11_chunk_sweep.log) -- so the measured choice stays.
-int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid){
-    const int n_tiles = grid_for(a.n, BLOCK);
+int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid, int tile_envs){
+    const int n_tiles = grid_for(a.n, tile_envs);
     const int cap = cap_in > 0 ? cap_in : n_tiles;
     int n_chunks = 1;
     const int forced = [](){ const char* e = std::getenv("B200L2F_CHUNKS"); return e ? std::atoi(e) : 0; }();   // test / tuning override
@@ -182,12 +182,20 @@ int b200l2f_destroy(b200l2f_handle* h){
     if(h->d_stage) cudaFree(h->d_stage);
     if(h->h_pinned) cudaFreeHost(h->h_pinned);
     if(h->pinned_read) cudaEventDestroy(h->pinned_read);
+    {
+        auto& x = h->xfer;
+        if(x.h2d){ cudaStreamSynchronize(x.h2d); cudaStreamDestroy(x.h2d); }
+        if(x.d2h){ cudaStreamSynchronize(x.d2h); cudaStreamDestroy(x.d2h); }
+        cudaFree(x.up_params); cudaFree(x.up_state); cudaFree(x.dl_state);
+        for(cudaEvent_t e : {x.params_ready, x.params_free, x.state_ready, x.state_free, x.dl_ready, x.dl_free, x.main_mark}) if(e) cudaEventDestroy(e);
+    }
     if(h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B200L2F_OK;
 }
 int b200l2f_synchronize(b200l2f_handle* h){ CU(cudaStreamSynchronize(h->stream)); return B200L2F_OK; }
 void* b200l2f_stream(b200l2f_handle* h){ return (void*)h->stream; }
+const char* b200l2f_last_kernel(const b200l2f_handle* h){ return h ? h->last_kernel : ""; }
 int b200l2f_state_dim(const b200l2f_handle* h){ return h->sdim; }
 int b200l2f_observation_dim(const b200l2f_handle* h){ return h->obs_dim; }
 int b200l2f_action_history_length(const b200l2f_handle* h){ return h->H; }
@@ -277,6 +285,7 @@ int b200l2f_set_parameters(b200l2f_handle* h, const float* rows, int memspace){
     const void* dev; int rc;
     if((rc = upload(h, rows, sizeof(float) * B200L2F_PARAMS_DIM * (size_t)h->n, memspace, &dev))) return rc;
     h->features_dirty = true;
+    h->params_follow_env_row = false;   // the caller's rows may differ from the nominal row anywhere: the collection kernels must read the columns
     return transpose(h, (const float*)dev, h->d_params, h->n, B200L2F_PARAMS_DIM);
 }
 
@@ -316,6 +325,101 @@ int b200l2f_set_state(b200l2f_handle* h, int slot, const float* rows, int memspa
     const void* dev;
     if((rc = upload(h, rows, sizeof(float) * h->sdim * (size_t)h->n, memspace, &dev))) return rc;
     return transpose(h, (const float*)dev, h->d_state[slot], h->n, h->sdim);
+}
+// ---- asynchronous transfers -----------------------------------------------------------------------------------------
+// The synchronous set_* / get_* above serialise copy and compute on one stream (end to end 0.77 of the kernel rate at configs[1], 0.82 scaling
+// efficiency on 8 GPUs behind one PCIe root: round-1 verdict).  The *_async twins move the bytes on the handle's own copy streams into / out of
+// staging buffers and leave only the device-side transpose on the main stream, in call order:
+//   upload    h2d stream : wait(staging free) -> H2D -> record(ready)        main stream : wait(ready) -> transpose into the live buffer -> record(free)
+//   download  main stream: wait(staging free) -> transpose -> record(ready)  d2h stream  : wait(ready) -> D2H -> record(free)
+// so the upload for rollout k+1 and the download of rollout k-1 run while the kernel of rollout k executes.  Host buffers must be page-locked
+// (pageable memory cannot be copied asynchronously; it takes the synchronous path) and must stay untouched until b200l2f_transfers_synchronize.
+namespace {
+int xfer_init(b200l2f_handle* h){
+    auto& x = h->xfer;
+    if(x.h2d) return B200L2F_OK;
+    CU(cudaStreamCreateWithFlags(&x.h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&x.d2h, cudaStreamNonBlocking));
+    for(cudaEvent_t* e : {&x.params_ready, &x.params_free, &x.state_ready, &x.state_free, &x.dl_ready, &x.dl_free, &x.main_mark}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return B200L2F_OK;
+}
+}  // namespace
+int b200l2f_set_parameters_async(b200l2f_handle* h, const float* rows_pinned){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!rows_pinned) return fail(h, B200L2F_ERR_ARGUMENT, "set_parameters_async: null argument");
+    if(!is_pinned_host(rows_pinned)) return b200l2f_set_parameters(h, rows_pinned, B200L2F_HOST);
+    int rc; if((rc = xfer_init(h))) return rc;
+    auto& x = h->xfer;
+    const size_t bytes = sizeof(float) * B200L2F_PARAMS_DIM * (size_t)h->n;
+    if(!x.up_params) CU(cudaMalloc(&x.up_params, bytes));
+    if(x.params_used) CU(cudaStreamWaitEvent(x.h2d, x.params_free, 0));
+    CU(cudaMemcpyAsync(x.up_params, rows_pinned, bytes, cudaMemcpyHostToDevice, x.h2d));
+    CU(cudaEventRecord(x.params_ready, x.h2d));
+    CU(cudaStreamWaitEvent(h->stream, x.params_ready, 0));
+    if((rc = transpose(h, x.up_params, h->d_params, h->n, B200L2F_PARAMS_DIM))) return rc;
+    CU(cudaEventRecord(x.params_free, h->stream));
+    x.params_used = true;
+    h->features_dirty = true;
+    h->params_follow_env_row = false;
+    return B200L2F_OK;
+}
+int b200l2f_set_state_async(b200l2f_handle* h, int slot, const float* rows_pinned){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    if(!rows_pinned) return fail(h, B200L2F_ERR_ARGUMENT, "set_state_async: null argument");
+    if(!is_pinned_host(rows_pinned)) return b200l2f_set_state(h, slot, rows_pinned, B200L2F_HOST);
+    if((rc = xfer_init(h))) return rc;
+    auto& x = h->xfer;
+    const size_t bytes = sizeof(float) * h->sdim * (size_t)h->n;
+    if(!x.up_state) CU(cudaMalloc(&x.up_state, bytes));
+    if(x.state_used) CU(cudaStreamWaitEvent(x.h2d, x.state_free, 0));
+    CU(cudaMemcpyAsync(x.up_state, rows_pinned, bytes, cudaMemcpyHostToDevice, x.h2d));
+    CU(cudaEventRecord(x.state_ready, x.h2d));
+    CU(cudaStreamWaitEvent(h->stream, x.state_ready, 0));
+    if((rc = transpose(h, x.up_state, h->d_state[slot], h->n, h->sdim))) return rc;
+    CU(cudaEventRecord(x.state_free, h->stream));
+    x.state_used = true;
+    return B200L2F_OK;
+}
+int b200l2f_get_state_async(b200l2f_handle* h, int slot, float* rows_pinned){
+    CU(cudaSetDevice(h->cfg.device));
+    int rc; if((rc = check_slot(h, slot))) return rc;
+    if(!rows_pinned) return fail(h, B200L2F_ERR_ARGUMENT, "get_state_async: null argument");
+    if(!is_pinned_host(rows_pinned)) return b200l2f_get_state(h, slot, rows_pinned, B200L2F_HOST);
+    if((rc = xfer_init(h))) return rc;
+    auto& x = h->xfer;
+    const size_t bytes = sizeof(float) * h->sdim * (size_t)h->n;
+    if(!x.dl_state) CU(cudaMalloc(&x.dl_state, bytes));
+    if(x.dl_used) CU(cudaStreamWaitEvent(h->stream, x.dl_free, 0));
+    if((rc = transpose(h, h->d_state[slot], x.dl_state, h->sdim, h->n))) return rc;
+    CU(cudaEventRecord(x.dl_ready, h->stream));
+    CU(cudaStreamWaitEvent(x.d2h, x.dl_ready, 0));
+    CU(cudaMemcpyAsync(rows_pinned, x.dl_state, bytes, cudaMemcpyDeviceToHost, x.d2h));
+    CU(cudaEventRecord(x.dl_free, x.d2h));
+    x.dl_used = true;
+    return B200L2F_OK;
+}
+int b200l2f_copy_to_host_async(b200l2f_handle* h, void* dst_pinned, const void* src_device, size_t bytes){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!dst_pinned || !src_device) return fail(h, B200L2F_ERR_ARGUMENT, "copy_to_host_async: null argument");
+    int rc; if((rc = xfer_init(h))) return rc;
+    auto& x = h->xfer;
+    if(!is_pinned_host(dst_pinned)){   // pageable destination: ordinary stream-ordered copy, complete on return
+        CU(cudaMemcpyAsync(dst_pinned, src_device, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return B200L2F_OK;
+    }
+    CU(cudaEventRecord(x.main_mark, h->stream));            // everything enqueued on the main stream so far (the kernel that produced src_device)
+    CU(cudaStreamWaitEvent(x.d2h, x.main_mark, 0));
+    CU(cudaMemcpyAsync(dst_pinned, src_device, bytes, cudaMemcpyDeviceToHost, x.d2h));
+    return B200L2F_OK;
+}
+int b200l2f_transfers_synchronize(b200l2f_handle* h, int which){
+    CU(cudaSetDevice(h->cfg.device));
+    auto& x = h->xfer;
+    if((which & 1) && x.h2d) CU(cudaStreamSynchronize(x.h2d));
+    if((which & 2) && x.d2h) CU(cudaStreamSynchronize(x.d2h));
+    return B200L2F_OK;
 }
 int b200l2f_copy_state(b200l2f_handle* h, int dst_slot, int src_slot){
     CU(cudaSetDevice(h->cfg.device));
@@ -596,7 +700,12 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
         // shared-memory-A variant (2 CTAs/SM, no noise variant).  Measured: 9.4e9 vs 6.7e9 env-steps/s at 1M envs (profiles/r01_exp8_*).
         static const bool a_in_tmem = [](){ const char* e = std::getenv("B200L2F_A"); return !(e && std::string(e) == "smem"); }();
         static const bool g1_tc = [](){ const char* e = std::getenv("B200L2F_G1"); return !(e && std::string(e) == "cuda"); }();   // tuning knob, default: dense 1 on tcgen05 too (+3.5 % measured)
-        if(a_in_tmem && fast) rc = launch_raptor_ts(h, a, uniform, axial, noise);
+        // two environments per thread on the packed fp32 pipe (rollout_x2.cuh; foundation-policy spec, default math, uniform MDP constants, axial vehicles,
+        // no noise): 27 % fewer instructions per environment step, but 255 registers leave two warps per scheduler and it measures 0.8x of the
+        // one-environment kernel (profiles/r02_exp1_two_envs_per_thread.md) -- opt-in with B200L2F_X2=1
+        const bool x2 = [](){ const char* e = std::getenv("B200L2F_X2"); return e && e[0] == '1'; }();
+        if(a_in_tmem && fast && x2 && uniform && axial && !noise && h->kind == KIND_RAPTOR) rc = launch_raptor_x2(h, a);
+        else if(a_in_tmem && fast) rc = launch_raptor_ts(h, a, uniform, axial, noise);
         else if(noise) rc = launch_raptor_fp32(h, a, noise, fast, constw, h->rolled);
         else rc = launch_raptor_tc(h, a, fast, uniform, g1_tc);
     }

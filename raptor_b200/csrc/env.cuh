@@ -132,6 +132,7 @@ __device__ __forceinline__ void store_state(const EnvState<Spec>& st, float* __r
 struct DynInvariants {
     float inv_mass;      // 1 / mass                         (60_dynamics.h:55)
     float fa[3];         // force / mass                     (60_dynamics.h:91-93)
+    float ga[3];         // gravity + force / mass           (packed dynamics of the default-math kernels: one addend instead of two)
     float ta[3];         // J_inv * torque_disturbance       (60_dynamics.h:97)
     float half_range;    // (action_limit.max - min) / 2     (operations_generic.h:105)
     float dt;
@@ -141,7 +142,7 @@ __device__ __forceinline__ void dyn_invariants(DynInvariants& d, const P& p, con
     const float mass = p[P_MASS];
     d.inv_mass = 1.0f / mass;
 #pragma unroll
-    for(int i = 0; i < 3; i++) d.fa[i] = st.force[i] / mass;
+    for(int i = 0; i < 3; i++){ d.fa[i] = st.force[i] / mass; d.ga[i] = p[P_GRAVITY + i] + d.fa[i]; }
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float a = 0.0f;
@@ -411,8 +412,9 @@ __device__ __forceinline__ bool env_terminated(const P& p, const float* __restri
     bool t = false;
     if(p[P_TERM_ENABLED] != 0.0f){
         const float tp = p[P_TERM_POS], tv = p[P_TERM_LINVEL], tw = p[P_TERM_ANGVEL];
-#pragma unroll
-        for(int i = 0; i < 3; i++) t = t || fabsf(x[X_POS + i]) > tp || fabsf(x[X_VEL + i]) > tv || fabsf(x[X_OMEGA + i]) > tw;
+        // any |component| above its threshold == the three-input maximum of the |components| above it (NaN components compare false either way)
+        t = max3(fabsf(x[X_POS]), fabsf(x[X_POS + 1]), fabsf(x[X_POS + 2])) > tp || max3(fabsf(x[X_VEL]), fabsf(x[X_VEL + 1]), fabsf(x[X_VEL + 2])) > tv ||
+            max3(fabsf(x[X_OMEGA]), fabsf(x[X_OMEGA + 1]), fabsf(x[X_OMEGA + 2])) > tw;
     }
     return t;
 }
@@ -441,7 +443,7 @@ __device__ __forceinline__ float env_reward(const P& p, const RewardInputs& s, c
         if(clip > 0.0f) c = fminf(c, clip);
         weighted += w * c;
     }
-    if(const float w = p[P_RW_ORIENTATION]; on(w)) weighted += w * (2.0f * acosf(1.0f - fabsf(s.q3)));
+    if(const float w = p[P_RW_ORIENTATION]; on(w)) weighted += w * (2.0f * (FAST ? acos_1m_fast(fabsf(s.q3)) : acosf(1.0f - fabsf(s.q3))));
     if(const float w = p[P_RW_LINVEL]; on(w)){
         const float x = s.vel[0] - s.dvel[0], y = s.vel[1] - s.dvel[1], z = s.vel[2] - s.dvel[2];
         weighted += w * sqrt_t<FAST>(x * x + y * y + z * z);

@@ -177,12 +177,18 @@ struct Reader {
         if(!sig(collection, "GCOL")) return fail("global heap collection signature missing");
         uint64_t total; if(!rd(collection + 8, sl, total)) return false;
         if(!in(collection, total)) return fail("global heap collection outside the file");
-        uint64_t p = collection + 8 + (uint64_t)sl;
-        while(p + 8 + (uint64_t)sl <= collection + total){
+        const uint64_t end = collection + total;                      // in() checked: no wrap
+        const uint64_t hdr = 8 + (uint64_t)sl;                        // object header: index (2) | reference count (2) | reserved (4) | size
+        uint64_t p = collection + hdr;
+        while(end - p >= hdr){
             const uint64_t idx = le(p, 2), sz = le(p + 8, sl);
-            if(idx == index){ at = p + 8 + (uint64_t)sl; size = sz; if(at + size > collection + total) return fail("global heap object overruns its collection"); return true; }
+            // the size comes from the file: compare by subtraction so that a value near 2^64 can neither wrap the bound nor the stride
+            if(sz > end - (p + hdr)) return fail("global heap object overruns its collection");
+            if(idx == index){ at = p + hdr; size = sz; return true; }
             if(idx == 0) break;                                       // object 0 = the free space at the end
-            p += 8 + (uint64_t)sl + ((sz + 7) & ~7ull);
+            const uint64_t step = hdr + ((sz + 7) & ~7ull);           // sz <= end - p - hdr < 2^63: the rounding cannot wrap
+            if(step > end - p) break;
+            p += step;
         }
         return fail("global heap object " + std::to_string(index) + " not found");
     }

@@ -59,8 +59,17 @@ struct b200l2f_handle {
     void* h_pinned = nullptr; size_t pinned_bytes = 0;
     cudaEvent_t pinned_read = nullptr; bool pinned_read_pending = false;   // an async H2D copy out of h_pinned may still be in flight
     void* d_stage = nullptr; size_t stage_bytes = 0;
+    // asynchronous host <-> device pipeline (b200l2f_*_async): two copy streams beside the main stream, one upload staging buffer per kind and one download
+    // staging buffer, each guarded by a (ready, free) event pair so that transfers of step k+1 / k-1 run under the kernels of step k
+    struct Xfer {
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        float* up_params = nullptr; float* up_state = nullptr; float* dl_state = nullptr;
+        cudaEvent_t params_ready = nullptr, params_free = nullptr, state_ready = nullptr, state_free = nullptr, dl_ready = nullptr, dl_free = nullptr, main_mark = nullptr;
+        bool params_used = false, state_used = false, dl_used = false;
+    } xfer;
     std::string err;
     int64_t launches = 0;
+    const char* last_kernel = "";   // name of the fused kernel the last rollout / collection launched (b200l2f_last_kernel: profiling tools, bench.py)
 };
 
 namespace b200l2f {
@@ -166,6 +175,6 @@ int dispatch_spec(b200l2f_handle* h, F&& f){
 }
 
 int refresh_features(b200l2f_handle* h);                                              // engine.cu
-int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid);       // rollout.cu
+int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid, int tile_envs = BLOCK);   // engine.cu; tile_envs = environments per work item
 
 }  // namespace b200l2f

@@ -10,6 +10,8 @@ int launch_raptor_fp32(b200l2f_handle* h, const RolloutArgs& a, bool noise, bool
 int launch_raptor_tc(b200l2f_handle* h, const RolloutArgs& a, bool fast, bool uniform, bool g1_tc);
 // rollout_ts.cu: k_rollout_raptor_ts (tcgen05, A operand + hidden state in TMEM; the default hot path)
 int launch_raptor_ts(b200l2f_handle* h, const RolloutArgs& a, bool uniform, bool axial, bool noise);   // noise requires uniform
+// rollout_x2.cu: k_rollout_raptor_x2 (two environments per thread on the packed fp32 pipe; RAPTOR spec, default math, uniform MDP constants, axial vehicles, no noise)
+int launch_raptor_x2(b200l2f_handle* h, const RolloutArgs& a);
 // rollout_mlp.cu: k_rollout_mlp, k_mlp_step (MLP actors on CUDA cores)
 int launch_mlp_fp32(b200l2f_handle* h, const RolloutArgs& a);
 int launch_mlp_step(b200l2f_handle* h, const float* d_obs, int ld, float* d_act);

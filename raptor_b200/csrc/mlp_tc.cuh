@@ -196,7 +196,7 @@ __device__ __forceinline__ TsCtx mlp_ts_prologue_at(unsigned char* smraw, int b_
     uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + bar_offset);
     uint64_t* bar_mma = bar_tma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tc::uniform_warp_index();
     if(tid == 0){
         tc::mbar_init(bar_tma, 1);
         tc::mbar_init(bar_mma, 1);

@@ -51,6 +51,15 @@ int launch_off_policy_ts(b200l2f_handle* h, const OffPolicyArgs& a, bool follow,
 
 using namespace b200l2f;
 
+namespace {
+// temporary device copies of HOST-side rings / batches: freed on every exit path of the call that made them
+struct DeviceTemps {
+    std::vector<void*> ptrs;
+    cudaError_t alloc(void** dev, size_t bytes){ cudaError_t e = cudaMalloc(dev, bytes); if(e == cudaSuccess) ptrs.push_back(*dev); return e; }
+    ~DeviceTemps(){ for(void* p : ptrs) cudaFree(p); }
+};
+}  // namespace
+
 extern "C" {
 
 int b200l2f_runner_get_state(b200l2f_handle* h, int32_t* episode_step, float* episode_return, uint8_t* truncated, int memspace){
@@ -89,14 +98,14 @@ int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode
     Part parts[5] = {{rb->data, sizeof(float) * rows * D, nullptr}, {rb->episode_start, sizeof(int32_t) * rows, nullptr}, {rb->position, sizeof(int32_t) * n, nullptr},
                      {rb->full, n, nullptr}, {rb->current_episode_start, sizeof(int32_t) * n, nullptr}};
     const bool host = rb->memspace == B200L2F_HOST;
-    auto release = [&](){ if(host) for(auto& p : parts) if(p.dev) cudaFree(p.dev); };
+    DeviceTemps temps;
     for(auto& p : parts){
         if(!host){ p.dev = p.user; continue; }
-        cudaError_t e = cudaMalloc(&p.dev, p.bytes);
+        cudaError_t e = temps.alloc(&p.dev, p.bytes);
         if(e == cudaSuccess) e = cudaMemcpyAsync(p.dev, p.user, p.bytes, cudaMemcpyHostToDevice, h->stream);
-        if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("off_policy_steps: staging the replay buffers: ") + cudaGetErrorString(e)); }
+        if(e != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("off_policy_steps: staging the replay buffers: ") + cudaGetErrorString(e));
     }
-    if(host) cudaStreamSynchronize(h->stream);
+    if(host) CU(cudaStreamSynchronize(h->stream));   // pageable sources: the caller may reuse them as soon as the call returns
     CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
     OffPolicyArgs oa{};
     CollectArgs& a = oa.c;
@@ -113,16 +122,11 @@ int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode
     for(int i = 0; i < 9; i++) if(i % 4 != 0 && (a.row[P_J + i] != 0.0f || a.row[P_JINV + i] != 0.0f)) row_axial = false;
     const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     int rc = tensor_cores ? launch_off_policy_ts(h, oa, follow, row_axial) : launch_off_policy_fp32(h, oa);
-    if(rc){ release(); return rc; }
+    if(rc) return rc;
     if(!follow && sample_parameters) h->features_dirty = true;
     if(host){
-        for(auto& p : parts){
-            cudaError_t e = cudaMemcpyAsync(p.user, p.dev, p.bytes, cudaMemcpyDeviceToHost, h->stream);
-            if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("off_policy_steps: reading the replay buffers back: ") + cudaGetErrorString(e)); }
-        }
-        cudaError_t e = cudaStreamSynchronize(h->stream);
-        release();
-        if(e != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("off_policy_steps: ") + cudaGetErrorString(e));
+        for(auto& p : parts) CU(cudaMemcpyAsync(p.user, p.dev, p.bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
     }
     if(sample_parameters && h->dr){
         int flag = 0;
@@ -157,16 +161,16 @@ int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, in
     std::vector<Part*> all;
     for(auto& p : parts) all.push_back(&p);
     for(auto& p : extra) all.push_back(&p);
-    auto release = [&](){ if(host) for(auto* p : all) if(p->dev) cudaFree(p->dev); };
+    DeviceTemps temps;
     for(auto* p : all){
         const void* any = p->user_in ? p->user_in : p->user_out;
         if(!any || !p->bytes) continue;
         if(!host){ p->dev = const_cast<void*>(any); continue; }
-        cudaError_t e = cudaMalloc(&p->dev, p->bytes);
+        cudaError_t e = temps.alloc(&p->dev, p->bytes);
         if(e == cudaSuccess && p->user_in) e = cudaMemcpyAsync(p->dev, p->user_in, p->bytes, cudaMemcpyHostToDevice, h->stream);
-        if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: staging: ") + cudaGetErrorString(e)); }
+        if(e != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: staging: ") + cudaGetErrorString(e));
     }
-    if(host) cudaStreamSynchronize(h->stream);
+    if(host) CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
     GatherArgs a{};
     a.replay = (const float*)parts[0].dev; a.position = (const int*)parts[1].dev; a.full = (const uint8_t*)parts[2].dev;
@@ -177,19 +181,16 @@ int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, in
     k_gather_batch<<<grid_for(B * 32, 256), 256, 0, h->stream>>>(a);
     h->launches++;
     cudaError_t le = cudaGetLastError();
-    if(le != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le)); }
+    if(le != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
     if(host){
         for(auto* p : all){
             if(!p->dev || !p->user_out) continue;
-            cudaError_t e = cudaMemcpyAsync(p->user_out, p->dev, p->bytes, cudaMemcpyDeviceToHost, h->stream);
-            if(e != cudaSuccess){ release(); return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: reading back: ") + cudaGetErrorString(e)); }
+            CU(cudaMemcpyAsync(p->user_out, p->dev, p->bytes, cudaMemcpyDeviceToHost, h->stream));
         }
     }
     int flag = 0;
-    cudaError_t e = cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    if(e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    release();
-    if(e != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: ") + cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     if(flag) return fail(h, B200L2F_ERR_STATE, "gather_batch: Replay buffer requires at least one element");
     return B200L2F_OK;
 }

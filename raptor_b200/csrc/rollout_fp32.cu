@@ -21,6 +21,7 @@ int launch_rollout_raptor(b200l2f_handle* h, const RolloutArgs& a){
     else{
         kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, WeightBlock<1>{});
     }
+    h->last_kernel = "k_rollout_raptor";
     LAUNCH_CHECK();
     return B200L2F_OK;
 }

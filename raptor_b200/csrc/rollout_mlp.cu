@@ -12,6 +12,7 @@ int launch_mlp_fp32(b200l2f_handle* h, const RolloutArgs& a){
             const size_t smem = sizeof(float) * (MlpImg<IN, OUT>::SIZE + (size_t)P_DYN_DIM * BLOCK + (size_t)ROWS * BLOCK);
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<grid_for(a.n, BLOCK), BLOCK, smem, h->stream>>>(a, h->pol.standardize);
+            h->last_kernel = "k_rollout_mlp";
             LAUNCH_CHECK();
             return (int)B200L2F_OK;
         };

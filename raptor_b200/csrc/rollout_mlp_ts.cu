@@ -22,6 +22,7 @@ int launch_rollout_mlp_ts(b200l2f_handle* h, RolloutArgs a){
     int grid = 0, rc;
     if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
     kern<<<grid, BLOCK, SM::TOTAL_ROLLOUT, h->stream>>>(a, h->d_mlp_tc_image);
+    h->last_kernel = "k_rollout_mlp_ts";
     LAUNCH_CHECK();
     return B200L2F_OK;
 }

@@ -14,6 +14,7 @@ int launch_rollout_tc(b200l2f_handle* h, const RolloutArgs& a){
         configured[dev] = true;
     }
     kern<<<grid_for(a.n, BLOCK), BLOCK, TcSmem::TOTAL, h->stream>>>(a, h->d_tc_image);
+    h->last_kernel = "k_rollout_raptor_tc";
     LAUNCH_CHECK();
     return B200L2F_OK;
 }

@@ -89,14 +89,20 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
 #ifndef B200L2F_SPLIT_PACKED
 #define B200L2F_SPLIT_PACKED 0     // 3xTF32 operand split with the low parts on the packed pipe: lo = fma2(hi, -1, x); measured -1.3 % (register moves, 8 B of spills)
 #endif
+#ifndef B200L2F_SPLIT_PAIRS
+#define B200L2F_SPLIT_PAIRS 1      // 3xTF32 low parts of x1 / h' (values that already sit in register pairs) as one FADD2 per two values
+#endif
 #ifndef B200L2F_DENSE2_PACKED
 #define B200L2F_DENSE2_PACKED 1    // dense 2 (16 -> 4) as FFMA2 on (act0, act1) / (act2, act3); measured +1.2 %
 #endif
 #ifndef B200L2F_H_IN_SMEM
 #define B200L2F_H_IN_SMEM 0        // the epilogue's copy of the GRU hidden state in shared memory (8 KB per CTA) instead of re-reading it from TMEM; measured -0.7 %
 #endif
-#ifndef B200L2F_TS_CTAS_AXIAL
-#define B200L2F_TS_CTAS_AXIAL 3    // resident CTAs per SM of k_rollout_raptor_ts for axial vehicles: 4 = compact dynamics block (44 floats) + 128 registers
+#ifndef B200L2F_LANGEVIN_BRANCH_FREE
+#define B200L2F_LANGEVIN_BRANCH_FREE 1   // default-math kernels: Langevin target update committed by selects instead of a branch (lets the scheduler interleave the RNG chain)
+#endif
+#ifndef B200L2F_PACKED_DYNAMICS
+#define B200L2F_PACKED_DYNAMICS 1  // axial vehicles, default math: the dynamics evaluation itself on natural pairs (dynamics_axial_packed): 55 instead of ~110 instructions
 #endif
 #ifndef B200L2F_PACKED_FP32
 #define B200L2F_PACKED_FP32 1      // packed fp32 (FFMA2 / FADD2 / FMUL2, sm_100) in the default-math kernels; 0 = scalar twins (tuning / bisecting)
@@ -106,18 +112,22 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
 // Every read is one LDS.128: the row stride is 68 words (= 4 mod 32), so the eight threads of a quarter-warp hit 8 x 4 distinct banks
 // (conflict-free), and a dynamics evaluation issues ~10 loads instead of 37 scalar ones.  Groups are laid out as the float4s the axial
 // vehicle's evaluation consumes; the general vehicle's extra entries (A_F, off-diagonal inertia) follow.
-enum DynC : int { C_COEF = 0,        // [12] thrust-curve coefficients, rotor r at [3r, 3r + 2]
-                  C_AT = 12,         // [3][4] torque per unit rotor thrust
-                  C_ITAU_RISE = 24, C_ITAU_FALL = 28,
+enum DynC : int { C_COEF = 0,        // [3][4] thrust-curve coefficients, k-major: coefficient k of rotor r at [4 k + r] (two rotors per packed operand)
+                  C_AT01 = 12,       // [4][2] torque per unit rotor thrust, rows 0 and 1 of rotor r at [2 r], [2 r + 1] (one packed operand per rotor)
+                  C_AT2 = 20,        // [4]    row 2
+                  C_TAU_M = 24,      // [4] (1/tau_rise + 1/tau_fall) / 2
+                  C_TAU_H = 28,      // [4] (1/tau_rise - 1/tau_fall) / 2: (setpoint - rpm) / tau(sign) = m d + h |d|, d = setpoint - rpm
                   C_G = 32,          // gravity[3] | action min
                   C_JD = 36,         // diag(J)[3] | action max
                   C_JID = 40,        // diag(J^-1)[3] | termination position threshold
-                  C_AF = 44,         // [3][4] force per unit rotor thrust (general vehicle only)
-                  C_JOFF = 56, C_JIOFF = 62,   // off-diagonal entries of J, J^-1 in row-major order 01 02 10 12 20 21 (general vehicle only)
-                  C_DIM_AXIAL = 44,  // the axial vehicle's evaluation reads nothing beyond this: a compact block for kernels that need the shared memory
-                  C_DIM = 68 };
-static_assert(C_DIM_AXIAL % 4 == 0 && (C_DIM_AXIAL * 8) % 32 == 0 && C_DIM_AXIAL % 32 == 12, "44-word rows: quarter-warp LDS.128 hits banks 0,12,24,4,16,28,8,20 (+0..3)");
-static_assert(C_DIM % 4 == 0 && C_DIM % 32 == 4, "row stride must keep LDS.128 aligned and conflict-free");
+                  C_DT = 44,         // dt | dt / 2 | dt / 3 | dt / 6   (the RK4 weights of integrators.h:18-50, divided once per staging)
+                  C_SQRT_DT = 48,    // sqrt(dt) | 0 | 0 | 0            (Langevin target, 70_post_integration.h:135)
+                  C_AF = 52,         // [3][4] force per unit rotor thrust (general vehicle only)
+                  C_JOFF = 64, C_JIOFF = 70,   // off-diagonal entries of J, J^-1 in row-major order 01 02 10 12 20 21 (general vehicle only)
+                  C_DIM_AXIAL = 52,  // the axial vehicle's evaluation reads nothing beyond this: a compact block for kernels that need the shared memory
+                  C_DIM = 76 };
+static_assert(C_DIM_AXIAL % 4 == 0 && (C_DIM_AXIAL / 4) % 2 == 1, "row stride = odd number of 16-byte units: a quarter-warp's LDS.128 hits 8 x 4 distinct banks");
+static_assert(C_DIM % 4 == 0 && (C_DIM / 4) % 2 == 1, "row stride must keep LDS.128 aligned and conflict-free");
 __host__ __device__ constexpr int dyn_j_slot(int base_diag, int base_off, int i, int j){   // where entry (i, j) of J / J^-1 lives in the block
     return i == j ? base_diag + i : base_off + 2 * i + (j > i ? j - 1 : j);
 }
@@ -148,19 +158,20 @@ using ParamsCompiled = ParamsCompiledT<false>;
 template <bool FULL = true, class F>
 __device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F&& P){   // sm = dyn_block_of_thread(sm_dyn); FULL = false: axial entries only
 #pragma unroll
-    for(int i = 0; i < 12; i++) sm[C_COEF + i] = P(P_THRUST_COEF + i);
-#pragma unroll
     for(int r = 0; r < 4; r++){
+#pragma unroll
+        for(int k = 0; k < 3; k++) sm[C_COEF + 4 * k + r] = P(P_THRUST_COEF + 3 * r + k);
         const float dx = P(P_THRUST_DIR + 3 * r), dy = P(P_THRUST_DIR + 3 * r + 1), dz = P(P_THRUST_DIR + 3 * r + 2);
         const float px = P(P_ROTOR_POS + 3 * r), py = P(P_ROTOR_POS + 3 * r + 1), pz = P(P_ROTOR_POS + 3 * r + 2);
         const float kq = P(P_TORQUE_CONST + r);
         if constexpr(FULL){ sm[C_AF + 0 * 4 + r] = dx; sm[C_AF + 1 * 4 + r] = dy; sm[C_AF + 2 * 4 + r] = dz; }
         // torque of rotor r per unit thrust: torque_dir * k_q + r x dir   (60_dynamics.h:38-39)
-        sm[C_AT + 0 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 0) * kq + (py * dz - pz * dy);
-        sm[C_AT + 1 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 1) * kq + (pz * dx - px * dz);
-        sm[C_AT + 2 * 4 + r] = P(P_TORQUE_DIR + 3 * r + 2) * kq + (px * dy - py * dx);
-        sm[C_ITAU_RISE + r] = 1.0f / P(P_TAU_RISE + r);
-        sm[C_ITAU_FALL + r] = 1.0f / P(P_TAU_FALL + r);
+        sm[C_AT01 + 2 * r + 0] = P(P_TORQUE_DIR + 3 * r + 0) * kq + (py * dz - pz * dy);
+        sm[C_AT01 + 2 * r + 1] = P(P_TORQUE_DIR + 3 * r + 1) * kq + (pz * dx - px * dz);
+        sm[C_AT2 + r]          = P(P_TORQUE_DIR + 3 * r + 2) * kq + (px * dy - py * dx);
+        const float ir = 1.0f / P(P_TAU_RISE + r), ifl = 1.0f / P(P_TAU_FALL + r);
+        sm[C_TAU_M + r] = 0.5f * (ir + ifl);
+        sm[C_TAU_H + r] = 0.5f * (ir - ifl);
     }
 #pragma unroll
     for(int i = 0; i < 3; i++) sm[C_G + i] = P(P_GRAVITY + i);
@@ -175,6 +186,9 @@ __device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F
         }
     }
     sm[C_G + 3] = P(P_ACT_MIN); sm[C_JD + 3] = P(P_ACT_MAX); sm[C_JID + 3] = P(P_TERM_POS);
+    const float dt = P(P_DT);
+    sm[C_DT] = dt; sm[C_DT + 1] = dt / 2.0f; sm[C_DT + 2] = dt / 3.0f; sm[C_DT + 3] = dt / 6.0f;
+    sm[C_SQRT_DT] = sqrtf(dt); sm[C_SQRT_DT + 1] = 0.0f; sm[C_SQRT_DT + 2] = 0.0f; sm[C_SQRT_DT + 3] = 0.0f;
 }
 template <bool UNIFORM, bool NC = true, bool FOLLOW = false, int STRIDE = C_DIM>
 __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env, const float* row0){
@@ -184,6 +198,25 @@ __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_c
     ParamsCompiledT<UNIFORM, NC, FOLLOW> p; p.sm = sm; p.base = g; p.stride = n; p.row0 = row0;
     return p;
 }
+// ---- packed fp32 helpers (sm_100: FFMA2 / FADD2 / FMUL2 execute one operation on two fp32 lanes per instruction; operands may be a register pair,
+// ---- a broadcast scalar register, a uniform register or an immediate, each with negate / absolute-value modifiers) -------------------------------
+using F2 = float2;
+namespace p2 {
+__device__ __forceinline__ F2 mk(float a, float b){ return make_float2(a, b); }
+__device__ __forceinline__ F2 bc(float s){ return make_float2(s, s); }                       // SASS: a .F32 (broadcast) operand, no move
+__device__ __forceinline__ F2 neg(F2 a){ return make_float2(-a.x, -a.y); }                   // operand modifier
+__device__ __forceinline__ F2 abs2(F2 a){ return make_float2(fabsf(a.x), fabsf(a.y)); }      // operand modifier
+__device__ __forceinline__ F2 add(F2 a, F2 b){ return __fadd2_rn(a, b); }
+__device__ __forceinline__ F2 sub(F2 a, F2 b){ return __fadd2_rn(a, neg(b)); }
+__device__ __forceinline__ F2 mul(F2 a, F2 b){ return __fmul2_rn(a, b); }
+__device__ __forceinline__ F2 fma(F2 a, F2 b, F2 c){ return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ F2 fnma(F2 a, F2 b, F2 c){ return __ffma2_rn(neg(a), b, c); }    // c - a b
+template <int E> __device__ __forceinline__ float lane(F2 v){ return E == 0 ? v.x : v.y; }
+__device__ __forceinline__ F2 lo2(float4 v){ return make_float2(v.x, v.y); }
+__device__ __forceinline__ F2 hi2(float4 v){ return make_float2(v.z, v.w); }
+using b200l2f::max3;
+}  // namespace p2
+
 // multirotor dynamics with the rotor matrices (same physics as dynamics() in env.cuh; thrust/torque summed as matrix-vector products).
 // AXIAL: every rotor thrusts along body z and J, J^-1 are diagonal (all reference vehicles; k_param_features bit2 guards it): the zero
 // products are dropped, the remaining operations keep the order of the general form, so both forms give the same bits.
@@ -192,19 +225,23 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
     float tm[4];
     {
         const float4 k0 = p.c4(C_COEF), k1 = p.c4(C_COEF + 4), k2 = p.c4(C_COEF + 8);
-        const float cf[12] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w};
+        const float c0[4] = {k0.x, k0.y, k0.z, k0.w}, c1[4] = {k1.x, k1.y, k1.z, k1.w}, c2[4] = {k2.x, k2.y, k2.z, k2.w};
 #pragma unroll
         for(int r = 0; r < 4; r++){
             const float rpm = x[X_RPM + r];
-            tm[r] = cf[3 * r] + cf[3 * r + 1] * rpm + cf[3 * r + 2] * rpm * rpm;
+            tm[r] = c0[r] + c1[r] * rpm + c2[r] * rpm * rpm;
         }
     }
     float thrust[3], torque[3];
 #pragma unroll
     for(int i = 0; i < 3; i++){
         if constexpr(!AXIAL){ const float4 f = p.c4(C_AF + 4 * i); thrust[i] = f.x * tm[0] + f.y * tm[1] + f.z * tm[2] + f.w * tm[3]; }
-        const float4 q = p.c4(C_AT + 4 * i);
-        torque[i] = q.x * tm[0] + q.y * tm[1] + q.z * tm[2] + q.w * tm[3];
+    }
+    {
+        const float4 u = p.c4(C_AT01), v = p.c4(C_AT01 + 4), w = p.c4(C_AT2);
+        torque[0] = u.x * tm[0] + u.z * tm[1] + v.x * tm[2] + v.z * tm[3];
+        torque[1] = u.y * tm[0] + u.w * tm[1] + v.y * tm[2] + v.w * tm[3];
+        torque[2] = w.x * tm[0] + w.y * tm[1] + w.z * tm[2] + w.w * tm[3];
     }
     if constexpr(AXIAL) thrust[2] = ((tm[0] + tm[1]) + tm[2]) + tm[3];
 #pragma unroll
@@ -253,13 +290,71 @@ __device__ __forceinline__ void dynamics_compiled(const PC& p, const DynInvarian
             else dx[X_OMEGA + i] = p.c(dyn_j_slot(C_JID, C_JIOFF, i, 0)) * t0 + p.c(dyn_j_slot(C_JID, C_JIOFF, i, 1)) * t1 + p.c(dyn_j_slot(C_JID, C_JIOFF, i, 2)) * t2 + d.ta[i];
         }
     }
+    {   // first-order motor lag with separate rising / falling time constants: (setpoint - rpm) / tau(sign of the difference) = m d + h |d|
+        const float4 m = p.c4(C_TAU_M), h = p.c4(C_TAU_H);
+        const float mm[4] = {m.x, m.y, m.z, m.w}, hh[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-    for(int r = 0; r < 4; r++){
-        const float rpm = x[X_RPM + r];
-        const float inv_tau = setpoint[r] >= rpm ? p.c(C_ITAU_RISE + r) : p.c(C_ITAU_FALL + r);
-        dx[X_RPM + r] = (setpoint[r] - rpm) * inv_tau;
+        for(int r = 0; r < 4; r++){
+            const float dd = setpoint[r] - x[X_RPM + r];
+            dx[X_RPM + r] = fmaf(hh[r], fabsf(dd), mm[r] * dd);
+        }
     }
 }
+
+// ---- packed form of the axial vehicle's step: the integrated state of ONE environment as natural pairs -------------------------------------------
+//   s[0] = (p0, p1)   s[1] = (v0, v1)   s[2] = (v2, w2)   s[3] = (q0, q1)   s[4] = (q2, q3)   s[5] = (w0, w1)   s[6] = (rpm0, rpm1)   s[7] = (rpm2, rpm3)
+//   and p2 as a scalar.  Every pair is what one packed instruction of the dynamics produces or consumes (thrust curves and motor lag of two
+//   rotors, torque rows 0 | 1, the x | y accelerations, J w and J^-1 (.) of axes 0 | 1), so the state algebra of RK4 (50_state_algebra.h) and
+//   about half of a dynamics evaluation issue as FFMA2 / FADD2 / FMUL2: 55 instead of ~110 instructions per evaluation.
+enum PackedSlot : int { K_P01 = 0, K_V01 = 1, K_VW2 = 2, K_Q01 = 3, K_Q23 = 4, K_W01 = 5, K_R01 = 6, K_R23 = 7, K_PAIRS = 8 };
+template <class PC>
+__device__ __forceinline__ void dynamics_axial_packed(const PC& p, const DynInvariants& d, const F2* __restrict__ s, F2 sp01, F2 sp23, F2* __restrict__ k, float& k_p2){
+    using namespace p2;
+    const F2 R01 = s[K_R01], R23 = s[K_R23];
+    const float4 c0 = p.c4(C_COEF), c1 = p.c4(C_COEF + 4), c2 = p.c4(C_COEF + 8);
+    const F2 tm01 = fma(fma(lo2(c2), R01, lo2(c1)), R01, lo2(c0));      // thrust of rotors 0 | 1 (60_dynamics.h:31: c0 + c1 rpm + c2 rpm^2)
+    const F2 tm23 = fma(fma(hi2(c2), R23, hi2(c1)), R23, hi2(c0));
+    const F2 tsum = add(tm01, tm23);
+    const float T = tsum.x + tsum.y;
+    const float4 a01 = p.c4(C_AT01), a23 = p.c4(C_AT01 + 4), a2 = p.c4(C_AT2);
+    const F2 t01 = fma(hi2(a23), bc(tm23.y), fma(lo2(a23), bc(tm23.x), fma(hi2(a01), bc(tm01.y), mul(lo2(a01), bc(tm01.x)))));   // torque rows 0 | 1
+    const F2 t2p = fma(hi2(a2), tm23, mul(lo2(a2), tm01));
+    const float t2 = t2p.x + t2p.y;
+    k[K_P01] = s[K_V01]; k_p2 = s[K_VW2].x;
+    const float q0 = s[K_Q01].x, q1 = s[K_Q01].y, q2 = s[K_Q23].x, q3 = s[K_Q23].y;
+    const float w0 = s[K_W01].x, w1 = s[K_W01].y, w2 = s[K_VW2].y;
+    {
+        const F2 h01 = mul(s[K_W01], bc(0.5f));       // exact scaling: the same values as (...) * 0.5
+        const float h0 = h01.x, h1 = h01.y, h2 = w2 * 0.5f;
+        k[K_Q01] = mk(fmaf(-q3, h2, fmaf(-q2, h1, -q1 * h0)), fmaf(-q3, h1, fmaf(q2, h2, q0 * h0)));
+        k[K_Q23] = mk(fmaf(-q1, h2, fmaf(q3, h0, q0 * h1)), fmaf(-q2, h0, fmaf(q1, h1, q0 * h2)));
+    }
+    float dv2;
+    {   // rotate (0, 0, T) by q, / m, + g + F_d / m
+        const float T2 = T + T;
+        const float v0 = q2 * T2, v1 = -q1 * T2;
+        const float o0 = fmaf(v0, q0, -q3 * v1), o1 = fmaf(v1, q0, q3 * v0), o2 = fmaf(-q2, v0, q1 * v1) + T;
+        k[K_V01] = fma(mk(o0, o1), bc(d.inv_mass), mk(d.ga[0], d.ga[1]));
+        dv2 = fmaf(o2, d.inv_mass, d.ga[2]);
+    }
+    {   // J^-1 (tau - w x J w) + J^-1 tau_d
+        const float4 jd = p.c4(C_JD), ji = p.c4(C_JID);
+        const F2 v01 = mul(lo2(jd), s[K_W01]);
+        const float v2 = jd.z * w2;
+        const float e0 = fmaf(-w1, v2, fmaf(w2, v01.y, t01.x));
+        const float e1 = fmaf(-w2, v01.x, fmaf(w0, v2, t01.y));
+        const float e2 = fmaf(-w0, v01.y, fmaf(w1, v01.x, t2));
+        k[K_W01] = fma(lo2(ji), mk(e0, e1), mk(d.ta[0], d.ta[1]));
+        k[K_VW2] = mk(dv2, fmaf(ji.z, e2, d.ta[2]));
+    }
+    {
+        const float4 m = p.c4(C_TAU_M), h = p.c4(C_TAU_H);
+        const F2 d01 = sub(sp01, R01), d23 = sub(sp23, R23);
+        k[K_R01] = fma(lo2(h), abs2(d01), mul(lo2(m), d01));
+        k[K_R23] = fma(hi2(h), abs2(d23), mul(hi2(m), d23));
+    }
+}
+
 // env_step twin for the compiled block (NOISE: action noise as in env_step; Langevin target as in env_step)
 // FAST: default-math variant (min/max clamps, MUFU reciprocal square root for the quaternion, MUFU Box-Muller for the Langevin target)
 // langevin_normals: the three N(0, 1) draws of the Langevin update, drawn by the caller ahead of time (legal only when nothing else draws from the
@@ -275,8 +370,74 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
         if constexpr(NOISE) a += rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, p[P_ACTION_NOISE]);
         setpoint[i] = clamp_t<FAST>(a, -1.0f, 1.0f) * d.half_range + amin + d.half_range;
     }
-    const float dt = d.dt;
-    const float dt2 = dt / 2.0f, dt3 = dt / 3.0f, dt6 = dt / 6.0f;
+    const float4 dts = p.c4(C_DT);
+    const float dt = dts.x, dt2 = dts.y, dt3 = dts.z, dt6 = dts.w;
+    constexpr bool PACKED_STEP = FAST && AXIAL && B200L2F_PACKED_FP32 && B200L2F_PACKED_DYNAMICS;
+    if constexpr(PACKED_STEP){
+        using namespace p2;
+        F2 s[K_PAIRS], acc[K_PAIRS], tmp[K_PAIRS], k[K_PAIRS];
+        s[K_P01] = mk(st.x[X_POS], st.x[X_POS + 1]); s[K_V01] = mk(st.x[X_VEL], st.x[X_VEL + 1]); s[K_VW2] = mk(st.x[X_VEL + 2], st.x[X_OMEGA + 2]);
+        s[K_Q01] = mk(st.x[X_ORI], st.x[X_ORI + 1]); s[K_Q23] = mk(st.x[X_ORI + 2], st.x[X_ORI + 3]); s[K_W01] = mk(st.x[X_OMEGA], st.x[X_OMEGA + 1]);
+        s[K_R01] = mk(st.x[X_RPM], st.x[X_RPM + 1]); s[K_R23] = mk(st.x[X_RPM + 2], st.x[X_RPM + 3]);
+        const float p2_0 = st.x[X_POS + 2];
+        float p2_acc, k_p2;
+        const F2 sp01 = mk(setpoint[0], setpoint[1]), sp23 = mk(setpoint[2], setpoint[3]);
+        const F2 c1 = bc(dt), c2 = bc(dt2), c3 = bc(dt3), c6 = bc(dt6);
+        if constexpr(ROLLED_RK4){   // four stages as one loop body (compact-code kernels); same arithmetic and accumulation order
+#pragma unroll
+            for(int i = 0; i < K_PAIRS; i++){ acc[i] = s[i]; tmp[i] = s[i]; }
+            p2_acc = p2_0;
+#pragma unroll 1
+            for(int stage = 0; stage < 4; stage++){
+                dynamics_axial_packed(p, d, tmp, sp01, sp23, k, k_p2);
+                const float wa = (stage == 0 || stage == 3) ? dt6 : dt3, wt = (stage == 2) ? dt : dt2;
+                p2_acc = fmaf(wa, k_p2, p2_acc);
+#pragma unroll
+                for(int i = 0; i < K_PAIRS; i++){ acc[i] = fma(bc(wa), k[i], acc[i]); tmp[i] = fma(bc(wt), k[i], s[i]); }
+            }
+        }
+        else{
+            // the dynamics do not read the position: its stage inputs are never formed, only the accumulation (next = x + dt/6 k1 + dt/3 k2 + dt/3 k3 + dt/6 k4)
+            dynamics_axial_packed(p, d, s, sp01, sp23, k, k_p2);
+            p2_acc = fmaf(dt6, k_p2, p2_0); acc[0] = fma(c6, k[0], s[0]);
+#pragma unroll
+            for(int i = 1; i < K_PAIRS; i++){ acc[i] = fma(c6, k[i], s[i]); tmp[i] = fma(c2, k[i], s[i]); }
+            dynamics_axial_packed(p, d, tmp, sp01, sp23, k, k_p2);
+            p2_acc = fmaf(dt3, k_p2, p2_acc); acc[0] = fma(c3, k[0], acc[0]);
+#pragma unroll
+            for(int i = 1; i < K_PAIRS; i++){ acc[i] = fma(c3, k[i], acc[i]); tmp[i] = fma(c2, k[i], s[i]); }
+            dynamics_axial_packed(p, d, tmp, sp01, sp23, k, k_p2);
+            p2_acc = fmaf(dt3, k_p2, p2_acc); acc[0] = fma(c3, k[0], acc[0]);
+#pragma unroll
+            for(int i = 1; i < K_PAIRS; i++){ acc[i] = fma(c3, k[i], acc[i]); tmp[i] = fma(c1, k[i], s[i]); }
+            dynamics_axial_packed(p, d, tmp, sp01, sp23, k, k_p2);
+            p2_acc = fmaf(dt6, k_p2, p2_acc);
+#pragma unroll
+            for(int i = 0; i < K_PAIRS; i++) acc[i] = fma(c6, k[i], acc[i]);
+        }
+        {   // post integration (70_post_integration.h:20-37): unit quaternion, limits
+            const F2 n2 = fma(acc[K_Q23], acc[K_Q23], mul(acc[K_Q01], acc[K_Q01]));
+            const float inv = rsqrt_approx(n2.x + n2.y);
+            acc[K_Q01] = mul(acc[K_Q01], bc(inv)); acc[K_Q23] = mul(acc[K_Q23], bc(inv));
+        }
+        st.x[X_POS] = acc[K_P01].x; st.x[X_POS + 1] = acc[K_P01].y; st.x[X_POS + 2] = p2_acc;
+        st.x[X_ORI] = acc[K_Q01].x; st.x[X_ORI + 1] = acc[K_Q01].y; st.x[X_ORI + 2] = acc[K_Q23].x; st.x[X_ORI + 3] = acc[K_Q23].y;
+        st.x[X_VEL] = acc[K_V01].x; st.x[X_VEL + 1] = acc[K_V01].y; st.x[X_VEL + 2] = acc[K_VW2].x;
+        st.x[X_OMEGA] = acc[K_W01].x; st.x[X_OMEGA + 1] = acc[K_W01].y; st.x[X_OMEGA + 2] = acc[K_VW2].y;
+        st.x[X_RPM] = acc[K_R01].x; st.x[X_RPM + 1] = acc[K_R01].y; st.x[X_RPM + 2] = acc[K_R23].x; st.x[X_RPM + 3] = acc[K_R23].y;
+        // clamp of position / velocities to +-1e5: one range test (three-input maxima), the nine clamps only when it fails
+        const float big = max3(max3(fabsf(st.x[0]), fabsf(st.x[1]), fabsf(st.x[2])), max3(fabsf(st.x[7]), fabsf(st.x[8]), fabsf(st.x[9])),
+                               max3(fabsf(st.x[10]), fabsf(st.x[11]), fabsf(st.x[12])));
+        if(!(big <= 100000.0f)){
+#pragma unroll
+            for(int i = 0; i < 3; i++){
+                st.x[X_POS + i] = clamp_t<true>(st.x[X_POS + i], -100000.0f, 100000.0f);
+                st.x[X_VEL + i] = clamp_t<true>(st.x[X_VEL + i], -100000.0f, 100000.0f);
+                st.x[X_OMEGA + i] = clamp_t<true>(st.x[X_OMEGA + i], -100000.0f, 100000.0f);
+            }
+        }
+    }
+    else{
     float k[X_DIM], tmp[X_DIM], acc[X_DIM];
     if constexpr(ROLLED_RK4){   // four stages as one loop body (a quarter of the code, same arithmetic and accumulation order)
 #pragma unroll
@@ -352,6 +513,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
             st.x[X_OMEGA + i] = clamp_t<FAST>(st.x[X_OMEGA + i], -100000.0f, 100000.0f);
         }
     }
+    }
 #pragma unroll
     for(int i = 0; i < 4; i++) st.last_action[i] = action[i];
 #pragma unroll
@@ -366,10 +528,36 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
         for(int i = 0; i < 4; i++) hist_ptr[(size_t)(4 * cs + i) * n] = action[i];
         st.current_step = (cs + 1) % Spec::H;
     }
-    if constexpr(Spec::LANGEVIN){
+    if constexpr(Spec::LANGEVIN && FAST && B200L2F_LANGEVIN_BRANCH_FREE){
+        // Langevin target without a branch: every lane runs the update on copies, the results are committed by selects.  In a warp of mixed trajectory
+        // types the branchy form executes the same instructions anyway, but as a separate basic block -- the 72 dependent integer operations of the six
+        // xorshift draws then cannot be interleaved with the arithmetic around them.  A lane whose trajectory is not Langevin keeps its stream untouched.
+        const bool lang = st.traj_type == 1;
+        const float gamma = p[P_LANGEVIN_GAMMA], omega = p[P_LANGEVIN_OMEGA], sigma = p[P_LANGEVIN_SIGMA], alpha = p[P_LANGEVIN_ALPHA];
+        const float sqrt_dt = p.c(C_SQRT_DT);
+        uint64_t r2 = rng;
+        float L[12];
+#pragma unroll
+        for(int i = 0; i < 12; i++) L[i] = st.lang[i];
+#pragma unroll
+        for(int dim = 0; dim < 3; dim++){
+            const float x_prev = L[6 + dim], v_prev = L[9 + dim];
+            const float dW = sqrt_dt * (langevin_normals ? langevin_normals[dim] : rng_normal_draw_fast(r2, 0.0f, 1.0f));
+            const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
+            const float x_next = x_prev + v_next * dt;
+            L[6 + dim] = x_next; L[9 + dim] = v_next;
+            const float v_smooth = alpha * v_next + (1.0f - alpha) * L[3 + dim];
+            L[dim] = L[dim] + v_smooth * dt;
+            L[3 + dim] = v_smooth;
+        }
+#pragma unroll
+        for(int i = 0; i < 12; i++) st.lang[i] = lang ? L[i] : st.lang[i];
+        rng = lang ? r2 : rng;
+    }
+    else if constexpr(Spec::LANGEVIN){
         if(st.traj_type == 1){
             const float gamma = p[P_LANGEVIN_GAMMA], omega = p[P_LANGEVIN_OMEGA], sigma = p[P_LANGEVIN_SIGMA], alpha = p[P_LANGEVIN_ALPHA];
-            const float sqrt_dt = sqrtf(dt);
+            const float sqrt_dt = p.c(C_SQRT_DT);
 #pragma unroll
             for(int dim = 0; dim < 3; dim++){
                 const float x_prev = st.lang[6 + dim], v_prev = st.lang[9 + dim];
@@ -411,7 +599,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
     uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + TcSmem::BAR);
     uint64_t* bar_mma = bar_tma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tc::uniform_warp_index();
 
     if(tid == 0){
         tc::mbar_init(bar_tma, 1);
@@ -635,9 +823,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
 //   lifetimes make the overlaps safe: obs/D1 are dead before x1 is written, x1/h are read by G2 while it writes D2 into [64,128).
 // G1 folds its bias in as K column 22 (= 1.0); G2 has no spare K column (K = 32 exactly), its biases are added in the epilogue.
 // =================================================================================================================================
-template <bool AXIAL>
+template <bool AXIAL, int T_CTAS = 3>
 struct TsSmemT {
-    static constexpr int CTAS = AXIAL ? B200L2F_TS_CTAS_AXIAL : 3;            // resident CTAs per SM this variant is built for
+    static_assert(T_CTAS == 3 || (T_CTAS == 4 && AXIAL), "four CTAs per SM need the compact (axial) dynamics block");
+    static constexpr int CTAS = T_CTAS;                                       // resident CTAs per SM this variant is built for (3: 168 registers, 4: 128 registers)
     static constexpr int DSTRIDE = CTAS == 4 ? C_DIM_AXIAL : C_DIM;           // 4 CTAs/SM: 28 KB image + 22.5 KB compact block = 50.6 KB per CTA
     static constexpr int B = 0;                                // weight image (TMA destination)
     static constexpr int DYN = B + TcImage::BYTES;
@@ -646,9 +835,12 @@ struct TsSmemT {
     static constexpr int TOTAL = HID + (B200L2F_H_IN_SMEM ? 16 * BLOCK * 4 : 0);
 };
 // NOISE: observation / action noise (18 + 4 normal draws per step, each skipped when its std is 0) with the MUFU Box-Muller.
-template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false>
-__global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
-    using TsSmem = TsSmemT<AXIAL>;
+// CTAS: resident CTAs per SM the instantiation is register-budgeted for.  3 (168 registers) wins while the tiles do not fill 4 x SMs slots
+// (65 536 environments = 512 tiles: 16.1e9 vs 14.8e9 env-steps/s); 4 (128 registers, compact dynamics block, 72 B of spills) wins once they do
+// (1 048 576 environments: 18.3e9 vs 16.5e9) -- profiles/r02_exp2_*.log.  The launcher picks by tile count.
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false, int CTAS = 3>
+__global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
+    using TsSmem = TsSmemT<AXIAL, CTAS>;
     static_assert(FAST, "the TMEM-A kernel reads the scaled-gate image (build_tc_image_host(..., true)): default math only");
     constexpr int HD = 16;
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -657,7 +849,7 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
     uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smraw + TsSmem::BAR);
     uint64_t* bar_mma = bar_tma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tc::uniform_warp_index();
     if(tid == 0){
         tc::mbar_init(bar_tma, 1);
         tc::mbar_init(bar_mma, 1);
@@ -695,6 +887,21 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
         }
         tc::tmem_st8(tmem_base + lane_off + col_hi, hi);
         tc::tmem_st8(tmem_base + lane_off + col_lo, lo);
+    };
+    // same for values that already sit in register pairs (TMEM loads, packed gate results): the low parts as x - hi on the packed pipe (exact)
+    auto put8p = [&](uint32_t col_hi, uint32_t col_lo, const float* v){
+        if constexpr(B200L2F_SPLIT_PAIRS){
+            float hi[8], lo[8];
+#pragma unroll
+            for(int i = 0; i < 8; i += 2){
+                hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u); hi[i + 1] = __uint_as_float(__float_as_uint(v[i + 1]) & 0xFFFFE000u);
+                const float2 l = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(-hi[i], -hi[i + 1]));
+                lo[i] = l.x; lo[i + 1] = l.y;
+            }
+            tc::tmem_st8(tmem_base + lane_off + col_hi, hi);
+            tc::tmem_st8(tmem_base + lane_off + col_lo, lo);
+        }
+        else put8(col_hi, col_lo, v);
     };
     float4* sm_h = reinterpret_cast<float4*>(smraw + TsSmem::HID) + tid;   // this thread's hidden state: sm_h[q * BLOCK], q = 0..3
     auto keep_h = [&](const float* v){
@@ -829,7 +1036,7 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
             gs = 0;
         }
         // ---- G2: GRU pre-activations (A = [x1 | h] in TMEM, K = 32)
-        put8(C_X1_HI, C_X1_LO, x1); put8(C_X1_HI + 8, C_X1_LO + 8, x1 + 8);
+        put8p(C_X1_HI, C_X1_LO, x1); put8p(C_X1_HI + 8, C_X1_LO + 8, x1 + 8);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncthreads();
@@ -937,7 +1144,7 @@ __global__ void __launch_bounds__(BLOCK, TsSmemT<AXIAL>::CTAS) k_rollout_raptor_
             const int new_step = gs + 1;
             const bool wrap = !no_auto_reset && new_step >= a.seq_len;
             if(wrap){ put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8); keep_h(sm_b + TcImage::H0); }
-            else{ put8(C_H_HI, C_H_LO, hn); put8(C_H_HI + 8, C_H_LO + 8, hn + 8); keep_h(hn); }
+            else{ put8p(C_H_HI, C_H_LO, hn); put8p(C_H_HI + 8, C_H_LO + 8, hn + 8); keep_h(hn); }
             gs = wrap ? 0 : new_step;
         }
         if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);

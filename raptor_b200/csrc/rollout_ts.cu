@@ -5,10 +5,10 @@
 
 namespace b200l2f {
 namespace {
-template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false>
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false, int CTAS = 3>
 int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
-    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL, NOISE>;
-    using TsSmem = TsSmemT<AXIAL>;
+    auto kern = k_rollout_raptor_ts<Spec, FAST, UNIFORM, AXIAL, NOISE, CTAS>;
+    using TsSmem = TsSmemT<AXIAL, CTAS>;
     static bool configured[8] = {}; static int capacity[8] = {};
     int dev = h->cfg.device & 7;
     if(!configured[dev]){
@@ -18,13 +18,14 @@ int launch_rollout_ts(b200l2f_handle* h, RolloutArgs a){
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, TsSmem::TOTAL));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         if(std::getenv("B200L2F_VERBOSE")) std::fprintf(stderr, "[b200l2f] k_rollout_raptor_ts: occupancy API reports %d CTAs/SM on %d SMs\n", per_sm, sms);
-        if(per_sm < TsSmem::CTAS) per_sm = TsSmem::CTAS;   // design point: 63 KB smem, 168 registers, 128 TMEM columns per CTA -> 3 CTAs/SM; a larger grid is harmless
+        if(per_sm < TsSmem::CTAS) per_sm = TsSmem::CTAS;   // design points: 68 KB smem + 168 registers -> 3 CTAs/SM, 55 KB + 128 registers -> 4 (128 TMEM columns per CTA); a larger grid is harmless
         capacity[dev] = per_sm * sms;        // co-resident CTAs (3 x 148 = 444 on B200)
         configured[dev] = true;
     }
     int grid = 0, rc;
     if((rc = prepare_schedule(h, a, capacity[dev], &grid))) return rc;
     kern<<<grid, BLOCK, TsSmem::TOTAL, h->stream>>>(a, h->d_ts_image);
+    h->last_kernel = CTAS == 4 ? "k_rollout_raptor_ts<CTAS=4>" : "k_rollout_raptor_ts<CTAS=3>";
     LAUNCH_CHECK();
     return B200L2F_OK;
 }
@@ -38,7 +39,14 @@ int launch_raptor_ts(b200l2f_handle* h, const RolloutArgs& a, bool uniform, bool
             return axial ? launch_rollout_ts<Spec, true, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false, true>(h, a);
         }
         if(!uniform) return launch_rollout_ts<Spec, true, false, false>(h, a);
-        return axial ? launch_rollout_ts<Spec, true, true, true>(h, a) : launch_rollout_ts<Spec, true, true, false>(h, a);
+        if(!axial) return launch_rollout_ts<Spec, true, true, false>(h, a);
+        // three or four resident CTAs per SM (see the kernel's comment): four once the tiles fill 4 x SMs slots; B200L2F_TS_CTAS=3|4 overrides
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+        const char* e = std::getenv("B200L2F_TS_CTAS");
+        const int n_tiles = (a.n + BLOCK - 1) / BLOCK;
+        const bool four = e ? e[0] == '4' : n_tiles >= 4 * sms;
+        return four ? launch_rollout_ts<Spec, true, true, true, false, 4>(h, a) : launch_rollout_ts<Spec, true, true, true>(h, a);
     };
     return h->kind == KIND_DEFAULT ? go(SpecDefault{}) : go(SpecRaptor{});
 }

@@ -7,6 +7,9 @@
 namespace b200l2f { namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p){ return (uint32_t)__cvta_generic_to_shared(p); }
+// warp index in a form the compiler knows to be warp-uniform (value broadcast from lane 0): TMEM addresses derived from it stay in uniform
+// registers instead of costing one R2UR per tcgen05.ld / tcgen05.st
+__device__ __forceinline__ int uniform_warp_index(){ return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count){
@@ -110,6 +113,13 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v){
     uint32_t r0, r1, r2, r3;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
     v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v){
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+#pragma unroll
+    for(int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v){
     uint32_t r[16];

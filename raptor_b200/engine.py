@@ -196,6 +196,9 @@ class VectorEnvironment:
     def stream(self):
         return self._lib.b200l2f_stream(self._h)
 
+    def last_kernel(self):
+        return self._lib.b200l2f_last_kernel(self._h).decode()
+
     @property
     def kernel_launches(self):
         return int(self._lib.b200l2f_kernel_launches(self._h))
@@ -258,6 +261,35 @@ class VectorEnvironment:
     def set_state(self, rows, slot=0):
         p, ms, _ = self._arg(rows, np.float32, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")
         self._check(self._lib.b200l2f_set_state(self._h, slot, p, ms))
+
+    # ---- asynchronous transfers (page-locked host arrays, e.g. numpy views of torch pinned tensors): see include/b200_l2f.h
+    def _pinned_arg(self, a, shape, name):
+        a = np.asarray(a)
+        if a.dtype != np.float32 or tuple(a.shape) != tuple(shape) or not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("%s: expected a C-contiguous float32 array of shape %s" % (name, tuple(shape)))
+        return a.ctypes.data
+
+    def set_parameters_async(self, rows):
+        self._check(self._lib.b200l2f_set_parameters_async(self._h, self._pinned_arg(rows, (self.N_ENVIRONMENTS, L.PARAMS_DIM), "parameters")))
+
+    def set_state_async(self, rows, slot=0):
+        self._check(self._lib.b200l2f_set_state_async(self._h, slot, self._pinned_arg(rows, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")))
+
+    def get_state_async(self, out, slot=0):
+        self._check(self._lib.b200l2f_get_state_async(self._h, slot, self._pinned_arg(out, (self.N_ENVIRONMENTS, self.STATE_DIM), "state")))
+        return out
+
+    def copy_to_host_async(self, dst, src_device):
+        """dst: page-locked numpy array; src_device: torch CUDA tensor the engine's stream produced (same byte size)"""
+        dst = np.asarray(dst)
+        nbytes = src_device.numel() * src_device.element_size()
+        if dst.nbytes != nbytes or not dst.flags["C_CONTIGUOUS"]:
+            raise ValueError("copy_to_host_async: destination must be C-contiguous with %d bytes" % nbytes)
+        self._check(self._lib.b200l2f_copy_to_host_async(self._h, dst.ctypes.data, src_device.data_ptr(), nbytes))
+        return dst
+
+    def transfers_synchronize(self, uploads=True, downloads=True):
+        self._check(self._lib.b200l2f_transfers_synchronize(self._h, (1 if uploads else 0) | (2 if downloads else 0)))
 
     def copy_state(self, dst_slot, src_slot):
         self._check(self._lib.b200l2f_copy_state(self._h, dst_slot, src_slot))

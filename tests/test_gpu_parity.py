@@ -232,6 +232,123 @@ def test_full_size_properties(rb):
     assert np.abs(s1[alive, :3]).max() <= 1.0 + 1e-6
 
 
+@pytest.mark.parametrize("gemm", ["tcgen05", "fp32"])
+def test_no_auto_reset_mode(rb, port, gemm):
+    """nn::layers::gru::NoAutoResetMode (gru/operations_generic.h:343-411 with the mode set): the step counter keeps counting past SEQUENCE_LENGTH
+    and the hidden state is never re-initialised; fused rollout across the 500-step boundary against the oracle, then the evaluate_step path"""
+    n, T = 200, 520
+    spec = rb.SPEC_RAPTOR
+    env = rb.VectorEnvironment(n, spec)
+    env.initialize_rng(77, warmup=16)
+    env.sample_initial_state()
+    env.load_policy(gemm=rb.GEMM_FP32_CUDA_CORES if gemm == "fp32" else rb.GEMM_TCGEN05_3XTF32)
+    params, states, rng = env.get_parameters(), env.get_state(), env.get_rng()
+    out = env.rollout(T, record=("actions", "terminated"), no_auto_reset=True)
+    pol = port.make_policy(rb.raptor_policy_blob())
+    hid, gs = np.tile(np.load(os.path.join(G, "raptor_kat.npz"))["h0"], (n, 1)).astype(np.float32), np.zeros(n, np.int32)
+    want = port.rollout(spec, pol, params, states, rng, T, hidden=hid, gru_step=gs, no_auto_reset=True)
+    h, g = env.get_hidden()
+    assert np.all(g == T) and np.array_equal(g, gs)                                 # no wrap at 500
+    assert np.array_equal(env.get_rng(), rng)
+    close_relative(out["actions"][:100], want["actions"][:100], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
+    close(out["actions"][495:], want["actions"][495:], 5e-3, 5e-3, "actions across the SEQUENCE_LENGTH boundary")
+    close(h, hid, 5e-3, 5e-3, "hidden state")
+    assert not np.allclose(h, np.tile(np.load(os.path.join(G, "raptor_kat.npz"))["h0"], (n, 1)), atol=1e-3)   # it was NOT reset
+    # the same rollout WITH auto-reset differs after the boundary (the mode really switches something)
+    env2 = rb.VectorEnvironment(n, spec)
+    env2.set_parameters(params); env2.initialize_rng(77, warmup=16); env2.sample_initial_state(); env2.load_policy()
+    out2 = env2.rollout(T, record=("actions",))
+    assert np.abs(out2["actions"][505:] - out["actions"][505:]).max() > 1e-3
+    assert np.all(env2.get_hidden()[1] == T - 500)
+    # evaluate_step path: 3 steps with the flag, counter keeps counting from an arbitrary value beyond the sequence length
+    env.set_hidden(gru_step=np.full(n, 499, np.int32))
+    obs = np.ascontiguousarray(env.observe()[:, :22])
+    hid2, gs2 = env.get_hidden()[0].copy(), np.full(n, 499, np.int32)
+    for _ in range(3):
+        a = env.policy_evaluate_step(obs, no_auto_reset=True)
+        a_want, _, _ = port.policy_evaluate_step(pol, obs, hidden=hid2, gru_step=gs2, no_auto_reset=True)
+        close(a, a_want, 1e-4, 1e-5, "evaluate_step, NoAutoResetMode")
+    assert np.all(env.get_hidden()[1] == 502) and np.all(gs2 == 502)
+
+
+def test_bench_configuration_vs_oracle(rb, port):
+    """the exact launch bench.py times (BASELINE configs[1]): SPEC_RAPTOR_DR, 65 536 environments, foundation-policy DR ranges, default math, tcgen05,
+    default kernel selection and time-chunk schedule; actions / states of a strided 512-environment sample over 100 steps against the oracle at the
+    north-star bound (1e-4 relative), terminated flags, RNG streams and GRU counters bit-exact"""
+    import bench
+    n, T = 65536, 100
+    env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR)
+    row = env.get_environment_parameters()
+    row[124:139] = np.array(bench.DR_RANGES, np.float32)
+    env.set_environment_parameters(row)
+    env.initialize_rng(seed=20250925, warmup=16)
+    env.sample_initial_parameters()
+    env.sample_initial_state()
+    env.load_policy(gemm=rb.GEMM_TCGEN05_3XTF32)
+    sel = np.arange(0, n, 128) + (np.arange(n // 128) * 37) % 128          # one environment of every 128-row tile, varying lane
+    params, states, rng = env.get_parameters()[sel], env.get_state()[sel], env.get_rng()[sel]
+    out = env.rollout(T, record=("actions", "terminated", "rewards", "states"), state_stride=10)
+    pol = port.make_policy(rb.raptor_policy_blob())
+    hid, gs = np.tile(np.load(os.path.join(G, "raptor_kat.npz"))["h0"], (len(sel), 1)).astype(np.float32), np.zeros(len(sel), np.int32)
+    want = port.rollout(rb.SPEC_RAPTOR_DR, pol, params, states, rng, T, hidden=hid, gru_step=gs)
+    close_relative(out["actions"][:, sel], want["actions"], 1e-4, {"action": (slice(0, 4), 0.1)}, "actions")
+    close(out["rewards"][:, sel], want["rewards"], 1e-3, 1e-3, "rewards")
+    assert np.array_equal(out["terminated"][:, sel], want["terminated"])
+    assert np.array_equal(env.get_rng()[sel], rng)
+    h, g = env.get_hidden()
+    assert np.array_equal(g[sel], gs)
+    close(h[sel], hid, 1e-3, 1e-4, "hidden state")
+    # states every 10 steps, |error| relative to the magnitude of each physical quantity along the trajectory (the rule of test_fused_rollout_vs_golden)
+    close_relative(out["states"][:, sel], want["states"][::10], 1e-4, STATE_GROUPS, "states")
+    close(env.get_state()[sel], out["states"][-1][:, :][sel], 0, 0, "final state row == slot 0")
+
+
+def test_asynchronous_transfers_match_the_synchronous_calls(rb):
+    """b200l2f_set_parameters_async / set_state_async / get_state_async / copy_to_host_async (copy streams + staging buffers, transposes ordered on the
+    main stream): a pipelined sequence of rollouts fed from page-locked host memory gives the bits of the synchronous calls; pageable memory falls back"""
+    import torch
+    n, T = 3000, 50
+    def make():
+        e = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR)
+        e.initialize_rng(5, warmup=16)
+        return e
+    env = make()
+    row = env.get_environment_parameters()
+    import bench
+    row[124:139] = np.array(bench.DR_RANGES, np.float32)
+    env.set_environment_parameters(row)
+    env.sample_initial_parameters(); env.sample_initial_state(); env.load_policy()
+    p0, s0, r0 = env.get_parameters(), env.get_state(), env.get_rng()
+    ref = make()
+    ref.load_policy()
+    want_states, want_returns = [], []
+    for k in range(3):                      # step k starts from s0 shifted by k rows: every step has its own inputs
+        ref.set_parameters(np.roll(p0, k, axis=0)); ref.set_state(np.roll(s0, k, axis=0)); ref.set_rng(r0); ref.policy_reset()
+        o = ref.rollout(T, record=("returns",))
+        want_states.append(ref.get_state()); want_returns.append(o["returns"])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    tp = [pin(np.roll(p0, k, axis=0)) for k in range(3)]; ts = [pin(np.roll(s0, k, axis=0)) for k in range(3)]
+    hs = [pin(np.zeros_like(s0)) for _ in range(3)]; hr = [pin(np.zeros(n, np.float32)) for _ in range(3)]
+    rd = [torch.zeros(n, dtype=torch.float32, device="cuda") for _ in range(3)]
+    env.set_parameters_async(tp[0].numpy()); env.set_state_async(ts[0].numpy())
+    for k in range(3):
+        env.set_rng(r0); env.policy_reset()
+        env.rollout(T, out={"returns": rd[k]})
+        env.get_state_async(hs[k].numpy()); env.copy_to_host_async(hr[k].numpy(), rd[k])
+        if k + 1 < 3:
+            env.set_parameters_async(tp[k + 1].numpy()); env.set_state_async(ts[k + 1].numpy())
+    env.transfers_synchronize(); env.synchronize()
+    for k in range(3):
+        assert np.array_equal(hs[k].numpy(), want_states[k]), k
+        assert np.array_equal(hr[k].numpy(), want_returns[k]), k
+    # pageable host memory: the same calls work, synchronously
+    env.set_parameters_async(p0); env.set_state_async(s0)
+    got = env.get_state_async(np.zeros_like(s0))
+    assert np.array_equal(got, s0) and np.array_equal(env.get_parameters(), p0)
+    with pytest.raises(ValueError):
+        env.set_state_async(s0[:, :10])
+
+
 def test_ragged_sizes_and_errors(rb):
     for n in [1, 31, 129, 1000]:
         e = rb.VectorEnvironment(n, rb.SPEC_DEFAULT)
@@ -497,7 +614,9 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     env.collect_reset()
     rng = env.get_rng()
     params, states = env.get_parameters(), env.get_state()
-    if edited:
+    if edited:   # per-environment values OUTSIDE the domain-randomised set (reward scale / constant): in effect until the environment's first reset
+        params[:, 95] *= rs.uniform(0.5, 1.5, n).astype(np.float32)
+        params[:, 96] += rs.uniform(0.0, 0.2, n).astype(np.float32)
         env.set_parameters(params)
     data = env.collect(T, limit)
     pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
@@ -514,6 +633,21 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     close(got3[:T, :, obs + 8], want3[:T, :, obs + 8], 1e-3, 1e-3, "log-prob")
     close(got3[:T, :, obs + 9], want3[:T, :, obs + 9], 2e-3, 2e-2, "reward")
     assert np.all(got3[..., obs + 12:] == 0)                                      # learner columns untouched
+    # the north-star's 1e-4 bound, free of closed-loop amplification (a random actor is chaotic across resets, which is what the 2e-3 above absorbs):
+    # (1) before the first reset (step limit 12) the trajectories themselves agree to 1e-4 relative
+    K = 8
+    close(got3[:K, :, :obs], want3[:K, :, :obs], 1e-4, 3e-5, "observations, first steps")                       # 1e-4 of the quantities' scale (floor 0.3)
+    close(got3[:K, :, obs:obs + 8], want3[:K, :, obs:obs + 8], 1e-4, 3e-5, "action means / actions, first steps")
+    close(got3[:K, :, obs + 9], want3[:K, :, obs + 9], 1e-4, 1e-4, "reward, first steps")
+    # (2) every step re-anchored on the engine's own rows: actor mean from the recorded observation, log-prob from the recorded mean / action
+    rows = np.ascontiguousarray(got3[:T].reshape(-1, D))
+    pol_mean = port.make_policy(blob[:-4].copy(), arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_IDENTITY)
+    mean_want, _, _ = port.policy_evaluate_step(pol_mean, np.ascontiguousarray(rows[:, :obs]))
+    close(rows[:, obs:obs + 4], mean_want, 1e-4, 2e-5, "actor means re-anchored on the recorded observations")
+    log_std = blob[-4:].astype(np.float64)
+    z = (rows[:, obs + 4:obs + 8].astype(np.float64) - rows[:, obs:obs + 4]) / np.exp(log_std)
+    lp_want = (-0.5 * z * z - log_std - 0.5 * np.log(2 * np.pi)).sum(1)
+    close(rows[:, obs + 8], lp_want, 1e-4, 1e-4, "log-prob re-anchored on the recorded means / actions")
     close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
     close(env.get_state(), states, 5e-3, 2e-3, "final states (incl. the action-history ring)")
 
@@ -543,7 +677,9 @@ def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
     env.collect_reset()
     rng = env.get_rng()
     params, states = env.get_parameters(), env.get_state()
-    if edited:
+    if edited:   # as in test_ppo_collect_vs_oracle: per-environment reward scale / constant, in effect until the first reset
+        params[:, 95] *= rs.uniform(0.5, 1.5, n).astype(np.float32)
+        params[:, 96] += rs.uniform(0.0, 0.2, n).astype(np.float32)
         env.set_parameters(params)
     replay = env.new_replay_buffers(capacity, device=on_device)
     pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_SAMPLE)
@@ -566,6 +702,11 @@ def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
         close(gd[..., obs:obs + 4], wd[..., obs:obs + 4], 2e-3, 2e-3, "actions")
         close(gd[..., obs + 4], wd[..., obs + 4], 2e-3, 2e-2, "rewards")
         close(gd[..., obs + 5:2 * obs + 5], wd[..., obs + 5:2 * obs + 5], 2e-3, 2e-4, "next observations")
+        if it == 0:   # the north-star's 1e-4 bound before closed-loop amplification sets in: the first ring rows (steps 0..7, before any reset)
+            K = 8
+            close(gd[:, :K, :obs + 4], wd[:, :K, :obs + 4], 1e-4, 3e-5, "observations / actions, first steps")   # 1e-4 of the quantities' scale (floor 0.3)
+            close(gd[:, :K, obs + 4], wd[:, :K, obs + 4], 1e-4, 1e-4, "rewards, first steps")
+            close(gd[:, :K, obs + 5:2 * obs + 5], wd[:, :K, obs + 5:2 * obs + 5], 1e-4, 3e-5, "next observations, first steps")
         close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
         close(env.get_state(), states, 2e-3, 2e-4, "states")
     assert runner["full"].all() and runner["replay"][..., D - 2].sum() > 0 and runner["replay"][..., D - 1].sum() > runner["replay"][..., D - 2].sum()
@@ -767,8 +908,9 @@ def test_mlp_tensor_core_rollout_properties(rb):
 
 def test_axial_dynamics_specialisation(rb, port):
     """the tensor-core kernels drop the zero products of the rotor / inertia matrices when every vehicle thrusts along body z with diagonal
-    inertia (k_param_features bit2).  (1) same bits as the general form on such vehicles; (2) a tilted rotor and an off-diagonal inertia
-    entry switch the general form on, which must agree with the CUDA-core kernel and the oracle"""
+    inertia (k_param_features bit2) and evaluate the remaining terms on the packed fp32 pipe (dynamics_axial_packed).  (1) the axial form agrees
+    with the general form on such vehicles to fp32 rounding (different FMA association, 40 closed-loop steps); (2) a tilted rotor and an
+    off-diagonal inertia entry switch the general form on, which must agree with the CUDA-core kernel and the oracle"""
     import os
     n, T = 300, 40
     blob = np.load(os.path.join(G, "raptor_kat.npz"))["blob"]
@@ -791,8 +933,9 @@ def test_axial_dynamics_specialisation(rb, port):
 
     _, _, _, oa = run()
     _, _, _, og = run(general=True)
-    for k in ("states", "actions", "rewards"):
-        assert np.array_equal(oa[k], og[k]), k
+    close_relative(oa["states"], og["states"], 2e-5, STATE_GROUPS, "axial vs general form, states")
+    close_relative(oa["actions"], og["actions"], 2e-5, {"action": (slice(0, 4), 0.1)}, "axial vs general form, actions")
+    close(oa["rewards"], og["rewards"], 1e-4, 1e-4, "axial vs general form, rewards")
     # non-axial vehicles
     e0 = rb.VectorEnvironment(n, rb.SPEC_RAPTOR)
     params = e0.get_parameters()

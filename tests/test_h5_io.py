@@ -219,6 +219,17 @@ for trial in range(600):
     for _ in range(rs.randint(1, 4)):
         b[rs.randint(8, meta)] = rs.randint(0, 256)
     failed += attempt(bytes(b)) != 0
+# global heap objects whose 64-bit size field is near 2^64 (once wrapped the bounds check into std::length_error / an endless scan)
+g = good.find(b"GCOL")
+assert g > 0
+for obj in range(3):
+    for size in (0xFFFFFFFFFFFFFFF0, 0xFFFFFFFFFFFFFFF8, 0xFFFFFFFFFFFFFFFF, 0x8000000000000000):
+        b = bytearray(good)
+        at = g + 16
+        for _ in range(obj):                                     # walk to object `obj` of the first collection
+            at += 16 + ((int.from_bytes(good[at + 8:at + 16], "little") + 7) & ~7)
+        b[at + 8:at + 16] = size.to_bytes(8, "little")
+        assert attempt(bytes(b)) != 0, (obj, hex(size))
 print("ok", failed)
 ''' % (ROOT, RAPTOR_H5)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
