@@ -207,6 +207,25 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
 int b200l2f_collect_reset(b200l2f_handle* h);                                             /* runner init: truncated = true, episode_step/return = 0 (operations_generic.h:65-75) */
 int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_limit, float* dataset, int memspace);
 
+/* ---- status of the last b200l2f_rollout / b200l2f_collect on this handle, reduced on the device right behind the fused kernel:
+ *   n_nonfinite          environments whose state holds a NaN or Inf afterwards (the reference's per-state check: L2F/operations_generic/05_state_is_nan.h;
+ *                        nonfinite_flags [n_envs] receives the per-environment flags, or NULL)
+ *   rollout only (has_episodes = 1): the aggregates of rl::utils::evaluation::Result (INC/rl/utils/evaluation/operations_generic.h:201-213) over the
+ *   n_envs episodes -- returns / episode length mean and std (population std, max(0, E[x^2] - E[x]^2)), num_terminated, share_terminated */
+typedef struct {
+    int64_t n_envs, n_nonfinite, n_terminated;
+    int32_t has_episodes, reserved;
+    double returns_mean, returns_std, episode_length_mean, episode_length_std, share_terminated;
+} b200l2f_status;
+int b200l2f_last_status(b200l2f_handle* h, b200l2f_status* out, uint8_t* nonfinite_flags, int memspace);
+
+/* ---- multi-GPU: environments shard by global id (b200l2f_config.first_env_id) and the rollout path has NO collective.  The one optional call:
+ * all-gather of equally sized trajectory slabs (e.g. the dataset b200l2f_collect wrote) across the ranks of the caller's NCCL communicator, enqueued on the
+ * handle's stream behind the kernel that produced the slab.  nccl_comm: ncclComm_t (one rank per GPU / process); send: count_per_rank floats on this device;
+ * recv: n_ranks * count_per_rank floats on this device, rank-major; n_ranks_out: ncclCommCount, or NULL.  NCCL is bound at run time (dlopen libnccl.so.2,
+ * B200L2F_NCCL_LIB overrides the name): B200L2F_ERR_UNSUPPORTED when it is not in the process / on the library path. */
+int b200l2f_allgather_trajectories(b200l2f_handle* h, void* nccl_comm, const float* send, float* recv, size_t count_per_rank, int32_t* n_ranks_out);
+
 /* ---- PPO learner feed: what the reference's loop step does between collect and train on the dataset above
  * (INC/rl/algorithms/ppo/loop/core/operations_generic.h:104-117), without the data leaving the GPU.
  * critic_load: the value network [standardize ->] Dense(OBS,64,ReLU) -> Dense(64,64,ReLU) -> Dense(64,1) (loop/core/config.h:62-76), blob in the

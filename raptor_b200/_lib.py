@@ -42,6 +42,12 @@ class Batch(ctypes.Structure):
                 ("final_step_mask", vp), ("next_final_step_mask", vp), ("env_index", vp), ("sample_index", vp)]
 
 
+class Status(ctypes.Structure):
+    _fields_ = [("n_envs", c_i64), ("n_nonfinite", c_i64), ("n_terminated", c_i64), ("has_episodes", c_i32), ("reserved", c_i32),
+                ("returns_mean", ctypes.c_double), ("returns_std", ctypes.c_double), ("episode_length_mean", ctypes.c_double), ("episode_length_std", ctypes.c_double),
+                ("share_terminated", ctypes.c_double)]
+
+
 class DaggerOut(ctypes.Structure):
     _fields_ = [("memspace", c_i32), ("reserved", c_i32), ("capacity_rows", c_i64), ("input_student", vp), ("output_target", vp), ("truncated", vp),
                 ("reset", vp), ("episode_start", vp), ("returns", vp), ("episode_length", vp)]
@@ -55,6 +61,8 @@ SYMBOLS = {
     "b200l2f_synchronize": (c_int, [vp]),
     "b200l2f_stream": (vp, [vp]),
     "b200l2f_last_kernel": (ctypes.c_char_p, [vp]),
+    "b200l2f_allgather_trajectories": (c_int, [vp, vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(c_i32)]),
+    "b200l2f_last_status": (c_int, [vp, ctypes.POINTER(Status), vp, c_int]),
     "b200l2f_state_dim": (c_int, [vp]),
     "b200l2f_observation_dim": (c_int, [vp]),
     "b200l2f_action_history_length": (c_int, [vp]),

@@ -33,6 +33,7 @@ SOURCES = {
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
     "off_policy.cu": TC + ["mlp_tc.cuh", "offpolicy.cuh", "offpolicy_tc.cuh"],
+    "collective.cu": [],
     "json_io.cu": [],
     "checkpoint_io.cu": ["h5_io.h"],
     "h5_io.cu": ["h5_io.h"],
@@ -87,7 +88,7 @@ def build(force=False, verbose=False, extra_flags=(), jobs=None):
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode:
                 raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(s) for s in SOURCES]
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

@@ -5,6 +5,7 @@
 // state [HD][n]); every entry point enqueues hand-written sm_100a kernels on the handle's stream.  There is no CPU path.  The heavy kernel
 // instantiations live in rollout_*.cu / collect*.cu (launch.h).
 #include "launch.h"
+#include <cmath>
 #include "rollout_tc.cuh"   // TcImage, build_tc_image_host
 
 using namespace b200l2f;
@@ -59,18 +60,60 @@ void nominal_parameters(int spec, float* p){
 
 namespace b200l2f {
 
-int refresh_features(b200l2f_handle* h){
-    if(!h->features_dirty) return B200L2F_OK;
+int enqueue_features(b200l2f_handle* h){
+    if(!h->features_ready){
+        CU(cudaEventCreateWithFlags(&h->features_ready, cudaEventDisableTiming));
+        CU(cudaMallocHost(&h->h_features, sizeof(int)));
+        CU(cudaMallocHost(&h->h_row0_pinned, sizeof(float) * B200L2F_PARAMS_DIM));
+    }
     CU(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->stream));
     k_param_features<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->n, h->d_flags + 1);
     LAUNCH_CHECK();
-    CU(cudaMemcpyAsync(&h->features, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpy2DAsync(h->row0, sizeof(float), h->d_params, sizeof(float) * (size_t)h->n, sizeof(float), B200L2F_PARAMS_DIM, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    k_publish_features<<<1, 160, 0, h->stream>>>(h->d_flags + 1, h->d_params, h->n, h->h_features, h->h_row0_pinned);   // page-locked host memory is device-addressable (UVA)
+    LAUNCH_CHECK();
+    CU(cudaEventRecord(h->features_ready, h->stream));
+    h->features_version = h->params_version;
+    return B200L2F_OK;
+}
+int refresh_features(b200l2f_handle* h){
+    if(!h->features_dirty) return B200L2F_OK;
+    int rc;
+    if(h->features_version != h->params_version){ if((rc = enqueue_features(h))) return rc; }   // parameters written by a path that did not enqueue the pass itself
+    CU(cudaEventSynchronize(h->features_ready));
+    h->features = *h->h_features;
+    std::memcpy(h->row0, h->h_row0_pinned, sizeof(float) * B200L2F_PARAMS_DIM);
     h->features_dirty = false;
     return B200L2F_OK;
 }
 
+
+int flush_pending_downloads(b200l2f_handle* h){
+    auto& x = h->xfer;
+    for(auto& p : x.pending){
+        CU(cudaStreamWaitEvent(x.d2h, p.after, 0));
+        CU(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyDeviceToHost, x.d2h));
+        if(p.releases_dl_staging) CU(cudaEventRecord(x.dl_free, x.d2h));
+        else x.event_pool.push_back(p.after);               // the wait has been enqueued: the event object may be re-recorded
+    }
+    x.pending.clear();
+    return B200L2F_OK;
+}
+
+constexpr int STATUS_BLOCKS = 256;
+int enqueue_status(b200l2f_handle* h, const float* d_returns, const int* d_eplen, const uint8_t* d_done){
+    if(!h->d_status){
+        CU(cudaMalloc(&h->d_status, sizeof(StatusPartial) * (STATUS_BLOCKS + 1)));
+        CU(cudaMalloc(&h->d_nonfinite, (size_t)h->n));
+    }
+    const int blocks = grid_for(h->n, 256) < STATUS_BLOCKS ? grid_for(h->n, 256) : STATUS_BLOCKS;
+    StatusPartial* part = (StatusPartial*)h->d_status;
+    k_status_partials<<<blocks, 256, 0, h->stream>>>(h->d_state[0], h->sdim, h->n, d_returns, d_eplen, d_done, h->d_nonfinite, part + 1);
+    LAUNCH_CHECK();
+    k_status_finish<<<1, 32, 0, h->stream>>>(part + 1, blocks, part);
+    LAUNCH_CHECK();
+    h->status_valid = true; h->status_has_episodes = d_returns != nullptr;
+    return B200L2F_OK;
+}
 
 // persistent grid + work queue of the tcgen05 rollout kernels.  When the tiles do not fill an integer number of waves (e.g. 65 536 envs =
 // 512 tiles on 444 slots), the rollout is cut into time chunks so that every slot stays busy until the end: makespan 512/444 instead of 2
@@ -179,15 +222,21 @@ int b200l2f_destroy(b200l2f_handle* h){
     cudaFree(h->d_critic_blob); cudaFree(h->d_critic_tc_image); cudaFree(h->d_colstats);
     cudaFree(h->d_teacher_images); cudaFree(h->d_teacher_blobs); cudaFree(h->d_teacher_offsets);
     cudaFree(h->d_dg_states); cudaFree(h->d_dg_term); cudaFree(h->d_dg_eplen); cudaFree(h->d_dg_offsets); cudaFree(h->d_dg_returns);
+    cudaFree(h->d_last_returns); cudaFree(h->d_last_eplen); cudaFree(h->d_last_done); cudaFree(h->d_nonfinite); cudaFree(h->d_status);
     if(h->d_stage) cudaFree(h->d_stage);
     if(h->h_pinned) cudaFreeHost(h->h_pinned);
     if(h->pinned_read) cudaEventDestroy(h->pinned_read);
+    if(h->features_ready) cudaEventDestroy(h->features_ready);
+    if(h->h_features) cudaFreeHost(h->h_features);
+    if(h->h_row0_pinned) cudaFreeHost(h->h_row0_pinned);
     {
         auto& x = h->xfer;
         if(x.h2d){ cudaStreamSynchronize(x.h2d); cudaStreamDestroy(x.h2d); }
         if(x.d2h){ cudaStreamSynchronize(x.d2h); cudaStreamDestroy(x.d2h); }
         cudaFree(x.up_params); cudaFree(x.up_state); cudaFree(x.dl_state);
         for(cudaEvent_t e : {x.params_ready, x.params_free, x.state_ready, x.state_free, x.dl_ready, x.dl_free, x.main_mark}) if(e) cudaEventDestroy(e);
+        for(auto& p : x.pending) if(!p.releases_dl_staging) cudaEventDestroy(p.after);
+        for(cudaEvent_t e : x.event_pool) cudaEventDestroy(e);
     }
     if(h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -244,7 +293,7 @@ int b200l2f_initial_parameters(b200l2f_handle* h){
     CU(cudaSetDevice(h->cfg.device));
     k_fill_params<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->d_params, h->d_env_row, h->n);
     LAUNCH_CHECK();
-    h->features_dirty = true;
+    h->features_dirty = true; h->params_version++;
     h->params_follow_env_row = true;
     return B200L2F_OK;
 }
@@ -268,7 +317,7 @@ int b200l2f_sample_initial_parameters(b200l2f_handle* h){
         CU(cudaStreamSynchronize(h->stream));
         if(flag) return fail(h, B200L2F_ERR_STATE, "L2f: invalid domain randomization ranges (see the reference's assert_exit conditions in 10_sample_initial_parameters.h:68-199)");
     }
-    h->features_dirty = true;
+    h->features_dirty = true; h->params_version++;
     h->params_follow_env_row = true;
     return B200L2F_OK;
 }
@@ -284,9 +333,10 @@ int b200l2f_set_parameters(b200l2f_handle* h, const float* rows, int memspace){
     CU(cudaSetDevice(h->cfg.device));
     const void* dev; int rc;
     if((rc = upload(h, rows, sizeof(float) * B200L2F_PARAMS_DIM * (size_t)h->n, memspace, &dev))) return rc;
-    h->features_dirty = true;
+    h->features_dirty = true; h->params_version++;
     h->params_follow_env_row = false;   // the caller's rows may differ from the nominal row anywhere: the collection kernels must read the columns
-    return transpose(h, (const float*)dev, h->d_params, h->n, B200L2F_PARAMS_DIM);
+    if((rc = transpose(h, (const float*)dev, h->d_params, h->n, B200L2F_PARAMS_DIM))) return rc;
+    return enqueue_features(h);
 }
 
 // ---- state ------------------------------------------------------------------------------------------------------
@@ -359,9 +409,9 @@ int b200l2f_set_parameters_async(b200l2f_handle* h, const float* rows_pinned){
     if((rc = transpose(h, x.up_params, h->d_params, h->n, B200L2F_PARAMS_DIM))) return rc;
     CU(cudaEventRecord(x.params_free, h->stream));
     x.params_used = true;
-    h->features_dirty = true;
+    h->features_dirty = true; h->params_version++;
     h->params_follow_env_row = false;
-    return B200L2F_OK;
+    return enqueue_features(h);
 }
 int b200l2f_set_state_async(b200l2f_handle* h, int slot, const float* rows_pinned){
     CU(cudaSetDevice(h->cfg.device));
@@ -390,12 +440,11 @@ int b200l2f_get_state_async(b200l2f_handle* h, int slot, float* rows_pinned){
     auto& x = h->xfer;
     const size_t bytes = sizeof(float) * h->sdim * (size_t)h->n;
     if(!x.dl_state) CU(cudaMalloc(&x.dl_state, bytes));
+    if((rc = flush_pending_downloads(h))) return rc;            // an earlier download out of the same staging buffer must be on its way before the buffer is rewritten
     if(x.dl_used) CU(cudaStreamWaitEvent(h->stream, x.dl_free, 0));
     if((rc = transpose(h, h->d_state[slot], x.dl_state, h->sdim, h->n))) return rc;
     CU(cudaEventRecord(x.dl_ready, h->stream));
-    CU(cudaStreamWaitEvent(x.d2h, x.dl_ready, 0));
-    CU(cudaMemcpyAsync(rows_pinned, x.dl_state, bytes, cudaMemcpyDeviceToHost, x.d2h));
-    CU(cudaEventRecord(x.dl_free, x.d2h));
+    x.pending.push_back({rows_pinned, x.dl_state, bytes, x.dl_ready, true});
     x.dl_used = true;
     return B200L2F_OK;
 }
@@ -409,14 +458,18 @@ int b200l2f_copy_to_host_async(b200l2f_handle* h, void* dst_pinned, const void* 
         CU(cudaStreamSynchronize(h->stream));
         return B200L2F_OK;
     }
-    CU(cudaEventRecord(x.main_mark, h->stream));            // everything enqueued on the main stream so far (the kernel that produced src_device)
-    CU(cudaStreamWaitEvent(x.d2h, x.main_mark, 0));
-    CU(cudaMemcpyAsync(dst_pinned, src_device, bytes, cudaMemcpyDeviceToHost, x.d2h));
+    cudaEvent_t ev;
+    if(x.event_pool.empty()) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    else{ ev = x.event_pool.back(); x.event_pool.pop_back(); }
+    CU(cudaEventRecord(ev, h->stream));                     // everything enqueued on the main stream so far (the kernel that produced src_device)
+    x.pending.push_back({dst_pinned, src_device, bytes, ev, false});
     return B200L2F_OK;
 }
 int b200l2f_transfers_synchronize(b200l2f_handle* h, int which){
     CU(cudaSetDevice(h->cfg.device));
     auto& x = h->xfer;
+    int rc;
+    if((which & 2) && (rc = flush_pending_downloads(h))) return rc;
     if((which & 1) && x.h2d) CU(cudaStreamSynchronize(x.h2d));
     if((which & 2) && x.d2h) CU(cudaStreamSynchronize(x.d2h));
     return B200L2F_OK;
@@ -679,6 +732,13 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     }
     if(ms == B200L2F_HOST && total){ if((rc = ensure_stage(h, total))) return rc; }
     for(auto& s : slices) *s.kernel_ptr = (ms == B200L2F_HOST) ? (void*)((char*)h->d_stage + s.offset) : s.user;
+    // the per-environment episode summary is always produced (12 bytes per environment and launch): b200l2f_last_status reduces it
+    if(!h->d_last_returns){
+        CU(cudaMalloc(&h->d_last_returns, sizeof(float) * n)); CU(cudaMalloc(&h->d_last_eplen, sizeof(int) * n)); CU(cudaMalloc(&h->d_last_done, n));
+    }
+    if(!a.out_returns) a.out_returns = h->d_last_returns;
+    if(!a.out_eplen) a.out_eplen = h->d_last_eplen;
+    a.out_done = h->d_last_done;
     const bool noise = (h->features & 1) != 0;
     const bool fast = !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     const bool constw = h->weights_in_constant_bank;
@@ -711,11 +771,38 @@ int b200l2f_rollout(b200l2f_handle* h, int32_t n_steps, int32_t no_auto_reset, c
     }
     else rc = launch_raptor_fp32(h, a, noise, fast, constw, h->rolled);
     if(rc) return rc;
+    if((rc = enqueue_status(h, a.out_returns, a.out_eplen, a.out_done))) return rc;
+    if((rc = flush_pending_downloads(h))) return rc;        // asynchronous downloads of the previous results start now, under this kernel
     if(ms == B200L2F_HOST && total){
         if((rc = ensure_pinned(h, total))) return rc;
         CU(cudaMemcpyAsync(h->h_pinned, h->d_stage, total, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         for(auto& s : slices) std::memcpy(s.user, (char*)h->h_pinned + s.offset, s.bytes);
+    }
+    return B200L2F_OK;
+}
+
+// ---- status of the last fused call -------------------------------------------------------------------------------------
+int b200l2f_last_status(b200l2f_handle* h, b200l2f_status* out, uint8_t* nonfinite_flags, int memspace){
+    CU(cudaSetDevice(h->cfg.device));
+    if(!out) return fail(h, B200L2F_ERR_ARGUMENT, "last_status: null argument");
+    if(!h->status_valid) return fail(h, B200L2F_ERR_STATE, "last_status: no rollout / collection has run on this handle yet");
+    StatusPartial t;
+    CU(cudaMemcpyAsync(&t, h->d_status, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
+    if(nonfinite_flags){
+        if(memspace == B200L2F_DEVICE) CU(cudaMemcpyAsync(nonfinite_flags, h->d_nonfinite, (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+        else CU(cudaMemcpyAsync(nonfinite_flags, h->d_nonfinite, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    std::memset(out, 0, sizeof(*out));
+    const double n = (double)h->n;
+    out->n_envs = h->n; out->n_nonfinite = (int64_t)t.nonfinite; out->has_episodes = h->status_has_episodes ? 1 : 0;
+    if(h->status_has_episodes){
+        out->n_terminated = (int64_t)t.terminated;
+        out->returns_mean = t.ret / n; out->episode_length_mean = t.len / n;
+        const double vr = t.ret2 / n - out->returns_mean * out->returns_mean, vl = t.len2 / n - out->episode_length_mean * out->episode_length_mean;
+        out->returns_std = std::sqrt(vr > 0 ? vr : 0); out->episode_length_std = std::sqrt(vl > 0 ? vl : 0);      // max(0, E[x^2] - E[x]^2) as operations_generic.h:210-212
+        out->share_terminated = (double)t.terminated / n;
     }
     return B200L2F_OK;
 }
@@ -753,7 +840,8 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     rc = tensor_cores ? launch_collect_ts(h, a, follow, row_axial) : launch_collect_fp32(h, a);
     if(rc) return rc;
-    if(!follow) h->features_dirty = true;   // resets rewrite parameter columns (when they follow the row, the variant-selecting features cannot change)
+    if((rc = enqueue_status(h, nullptr, nullptr, nullptr))) return rc;
+    if(!follow){ h->features_dirty = true; h->params_version++; }   // resets rewrite parameter columns (when they follow the row, the variant-selecting features cannot change)
     if((rc = download(h, dataset, dev, bytes, memspace))) return rc;
     if(h->dr){
         int flag = 0;

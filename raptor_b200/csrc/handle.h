@@ -31,6 +31,9 @@ struct b200l2f_handle {
     uint64_t* d_rng = nullptr;
     int* d_flags = nullptr;          // [0] error flag, [1] parameter features
     bool features_dirty = true; int features = 0;
+    // the feature pass of the LAST parameter upload, enqueued right behind it on the main stream: results land in page-locked host words, refresh_features
+    // then waits for the event only (no launch + synchronise in front of the rollout).  Any later writer of d_params bumps params_version, which invalidates it.
+    cudaEvent_t features_ready = nullptr; int* h_features = nullptr; float* h_row0_pinned = nullptr; int64_t params_version = 0, features_version = -1;
     bool params_follow_env_row = false;   // every column was filled from h_env_row (initial / sampled parameters, collect's resets) and not edited since
     float row0[B200L2F_PARAMS_DIM];   // parameter row of environment 0 (uniform MDP constants of the fused kernels)
     // actor
@@ -66,7 +69,17 @@ struct b200l2f_handle {
         float* up_params = nullptr; float* up_state = nullptr; float* dl_state = nullptr;
         cudaEvent_t params_ready = nullptr, params_free = nullptr, state_ready = nullptr, state_free = nullptr, dl_ready = nullptr, dl_free = nullptr, main_mark = nullptr;
         bool params_used = false, state_used = false, dl_used = false;
+        // downloads are ENQUEUED lazily: the copy would otherwise start the moment its source is ready -- right behind the kernel, where its PCIe traffic delays
+        // the (tiny, host-visible) feature words and completion signals the next launch is waiting for (measured: +0.1 ms per pipelined rollout).  They are handed
+        // to the d2h stream once the next rollout has been launched (or at b200l2f_transfers_synchronize), and then overlap that kernel.
+        struct Pending { void* dst; const void* src; size_t bytes; cudaEvent_t after; bool releases_dl_staging; };
+        std::vector<Pending> pending;
+        std::vector<cudaEvent_t> event_pool;
     } xfer;
+    // status of the last fused call (b200l2f_last_status): per-environment returns / lengths / done flags the kernels always write, reduction scratch
+    float* d_last_returns = nullptr; int* d_last_eplen = nullptr; uint8_t* d_last_done = nullptr; uint8_t* d_nonfinite = nullptr;
+    void* d_status = nullptr;        // StatusPartial[STATUS_BLOCKS + 1]
+    bool status_valid = false, status_has_episodes = false;
     std::string err;
     int64_t launches = 0;
     const char* last_kernel = "";   // name of the fused kernel the last rollout / collection launched (b200l2f_last_kernel: profiling tools, bench.py)
@@ -175,6 +188,9 @@ int dispatch_spec(b200l2f_handle* h, F&& f){
 }
 
 int refresh_features(b200l2f_handle* h);                                              // engine.cu
+int flush_pending_downloads(b200l2f_handle* h);                                      // engine.cu
+int enqueue_features(b200l2f_handle* h);
+int enqueue_status(b200l2f_handle* h, const float* d_returns, const int* d_eplen, const uint8_t* d_done);   // engine.cu: status reduction behind the fused kernel just launched                                              // engine.cu: feature pass behind the parameter write just enqueued
 int prepare_schedule(b200l2f_handle* h, RolloutArgs& a, int cap_in, int* grid, int tile_envs = BLOCK);   // engine.cu; tile_envs = environments per work item
 
 }  // namespace b200l2f

@@ -98,6 +98,52 @@ static __global__ void k_param_features(const float* __restrict__ params, int n,
     if((threadIdx.x & 31) == 0 && f) atomicOr(features, f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// status of the last fused call: non-finite environments (L2F/operations_generic/05_state_is_nan.h: any NaN in the state; Inf counted as well)
+// and the aggregates of rl::utils::evaluation::Result (operations_generic.h:201-213).  Two deterministic passes: per-block partial sums in
+// double, then one block adds the partials in block order.
+// ---------------------------------------------------------------------------------------------------------------
+struct StatusPartial { double ret, ret2, len, len2; unsigned long long terminated, nonfinite; };
+static __global__ void __launch_bounds__(256) k_status_partials(const float* __restrict__ state, int sdim, int n, const float* __restrict__ returns, const int* __restrict__ eplen,
+                                                                  const uint8_t* __restrict__ done, uint8_t* __restrict__ nonfinite_flags, StatusPartial* __restrict__ partials){
+    double ret = 0, ret2 = 0, len = 0, len2 = 0; unsigned long long term = 0, bad = 0;
+    for(int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x){
+        bool finite = true;
+        for(int i = 0; i < sdim; i++) finite = finite && isfinite(state[(size_t)i * n + e]);
+        if(nonfinite_flags) nonfinite_flags[e] = finite ? 0 : 1;
+        bad += finite ? 0 : 1;
+        if(returns){ const double r = returns[e]; ret += r; ret2 += r * r; }
+        if(eplen){ const double l = eplen[e]; len += l; len2 += l * l; }
+        if(done) term += done[e] ? 1 : 0;
+    }
+    __shared__ StatusPartial sm[256];
+    sm[threadIdx.x] = StatusPartial{ret, ret2, len, len2, term, bad};
+    __syncthreads();
+    for(int s = 128; s > 0; s >>= 1){
+        if((int)threadIdx.x < s){
+            StatusPartial& a = sm[threadIdx.x]; const StatusPartial& b = sm[threadIdx.x + s];
+            a.ret += b.ret; a.ret2 += b.ret2; a.len += b.len; a.len2 += b.len2; a.terminated += b.terminated; a.nonfinite += b.nonfinite;
+        }
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+static __global__ void k_status_finish(const StatusPartial* __restrict__ partials, int n_partials, StatusPartial* __restrict__ out){
+    if(threadIdx.x != 0 || blockIdx.x != 0) return;
+    StatusPartial t{0, 0, 0, 0, 0, 0};
+    for(int i = 0; i < n_partials; i++){ const StatusPartial& b = partials[i]; t.ret += b.ret; t.ret2 += b.ret2; t.len += b.len; t.len2 += b.len2; t.terminated += b.terminated; t.nonfinite += b.nonfinite; }
+    *out = t;
+}
+
+// features + parameter row of environment 0 -> page-locked host words, written by the device itself (zero-copy store over PCIe): a cudaMemcpy D2H would queue
+// on the copy engine behind whatever download is in flight (measured: 0.25 ms behind a 12.6 MB state download, per pipelined rollout)
+static __global__ void k_publish_features(const int* __restrict__ features, const float* __restrict__ params, int n, int* __restrict__ host_features, float* __restrict__ host_row0){
+    const int i = threadIdx.x;
+    if(i < PARAMS_DIM) host_row0[i] = params[(size_t)i * n];
+    if(i == 0) *host_features = *features;
+    __threadfence_system();
+}
+
 template <class Spec, bool SAMPLE>
 __global__ void k_init_state(const float* __restrict__ params, float* __restrict__ state, uint64_t* __restrict__ rng, int n){
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,6 +287,7 @@ struct RolloutArgs {
     uint8_t* out_term;     // [T][n]
     float* out_returns;    // [n]
     int* out_eplen;        // [n]
+    uint8_t* out_done;     // [n] the episode terminated within the rollout (rl/utils/evaluation: num_terminated)
     float row0[PARAMS_DIM];  // parameter row of environment 0 (source of the uniform MDP constants)
     // time-chunked persistent scheduler (tensor-core TS kernel): sched[0] = work counter, sched[1 + tile] = chunks published for the tile
     int* sched; int n_chunks, chunk_steps;
@@ -363,6 +410,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor(const __gr
     a.gru_step[env] = gs;
     if(a.out_returns) a.out_returns[env] = ret;
     if(a.out_eplen) a.out_eplen[env] = eplen;
+    if(a.out_done) a.out_done[env] = done ? 1 : 0;
 }
 
 }  // namespace b200l2f

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_mlp(const __grid_
     a.rng[env] = rng;
     if(a.out_returns) a.out_returns[env] = ret;
     if(a.out_eplen) a.out_eplen[env] = eplen;
+    if(a.out_done) a.out_done[env] = done ? 1 : 0;
     (void)ROWS;
 }
 

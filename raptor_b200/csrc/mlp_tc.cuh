@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
         if(last_chunk){
             if(a.out_returns) a.out_returns[env] = ret;
             if(a.out_eplen) a.out_eplen[env] = eplen;
+            if(a.out_done) a.out_done[env] = done ? 1 : 0;
         }
         else{ a.acc_ret[env] = ret; a.acc_len[env] = (eplen << 1) | (done ? 1 : 0); }
     }

@@ -123,7 +123,7 @@ int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode
     const bool tensor_cores = h->pol.gemm == B200L2F_GEMM_TCGEN05_3XTF32 && h->d_mlp_tc_image && !(h->cfg.flags & B200L2F_FLAG_ACCURATE_MATH);
     int rc = tensor_cores ? launch_off_policy_ts(h, oa, follow, row_axial) : launch_off_policy_fp32(h, oa);
     if(rc) return rc;
-    if(!follow && sample_parameters) h->features_dirty = true;
+    if(!follow && sample_parameters){ h->features_dirty = true; h->params_version++; }
     if(host){
         for(auto& p : parts) CU(cudaMemcpyAsync(p.user, p.dev, p.bytes, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));

@@ -807,6 +807,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_rollout_raptor_tc(const _
         a.gru_step[env] = gs;
         if(a.out_returns) a.out_returns[env] = ret;
         if(a.out_eplen) a.out_eplen[env] = eplen;
+        if(a.out_done) a.out_done[env] = done ? 1 : 0;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -838,7 +839,10 @@ struct TsSmemT {
 // CTAS: resident CTAs per SM the instantiation is register-budgeted for.  3 (168 registers) wins while the tiles do not fill 4 x SMs slots
 // (65 536 environments = 512 tiles: 16.1e9 vs 14.8e9 env-steps/s); 4 (128 registers, compact dynamics block, 72 B of spills) wins once they do
 // (1 048 576 environments: 18.3e9 vs 16.5e9) -- profiles/r02_exp2_*.log.  The launcher picks by tile count.
-template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false, int CTAS = 3>
+// RECORD = false: the launch asks for no per-step output (states / observations / actions / rewards / terminated flags; returns and episode lengths are
+// per-item outputs and always available): the five uniform `if(a.out_*)` tests of a step disappear, and with them five basic-block boundaries the
+// instruction scheduler could not move code across.
+template <class Spec, bool FAST, bool UNIFORM, bool AXIAL, bool NOISE = false, int CTAS = 3, bool RECORD = true>
 __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_constant__ RolloutArgs a, const float* __restrict__ tc_image){
     using TsSmem = TsSmemT<AXIAL, CTAS>;
     static_assert(FAST, "the TMEM-A kernel reads the scaled-gate image (build_tc_image_host(..., true)): default math only");
@@ -985,7 +989,7 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
     tc::tmem_st_wait();
 
     for(int t = t_begin; t < t_end; t++){
-        if(a.out_states && active && (t % a.state_stride) == 0)
+        if(RECORD && a.out_states && active && (t % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
         float obs[24];
         observe18<Spec, NOISE, true>(st, p, rng, obs);
@@ -998,7 +1002,7 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
 #pragma unroll
             for(int i = 0; i < 4; i++) obs[18 + i] = hist_ptr[(size_t)(4 * cur + i) * n];
         }
-        if(a.out_obs && active){
+        if(RECORD && a.out_obs && active){
             float* row = a.out_obs + ((size_t)t * n + env) * 22;
 #pragma unroll
             for(int i = 0; i < 22; i++) row[i] = obs[i];
@@ -1147,14 +1151,14 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
             else{ put8p(C_H_HI, C_H_LO, hn); put8p(C_H_HI + 8, C_H_LO + 8, hn + 8); keep_h(hn); }
             gs = wrap ? 0 : new_step;
         }
-        if(a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
+        if(RECORD && a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
         if(Spec::H == 1 || active) env_step_compiled<Spec, false, NOISE, true, AXIAL>(st, p, d, act, rng, hist_ptr, n, HOIST ? lang_normals : nullptr);
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
-        if(a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
-        if(a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
+        if(RECORD && a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
+        if(RECORD && a.out_term && active) a.out_term[(size_t)t * n + env] = term ? 1 : 0;
         if(!done){ ret += rw; eplen += 1; done = term; }
     }
     tc::tmem_st_wait();
@@ -1171,7 +1175,7 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
     }
     const bool last_chunk = chunk == n_chunks - 1;
     if(active){
-        if(last_chunk && a.out_states && (a.T % a.state_stride) == 0)
+        if(RECORD && last_chunk && a.out_states && (a.T % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(a.T / a.state_stride) * n + env) * Spec::STATE_DIM);
         store_state(st, a.state + env, n);
         a.rng[env] = rng;
@@ -1181,6 +1185,7 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
         if(last_chunk){
             if(a.out_returns) a.out_returns[env] = ret;
             if(a.out_eplen) a.out_eplen[env] = eplen;
+            if(a.out_done) a.out_done[env] = done ? 1 : 0;
         }
         else{ a.acc_ret[env] = ret; a.acc_len[env] = (eplen << 1) | (done ? 1 : 0); }
     }

@@ -62,3 +62,70 @@ def allgather_trajectories(slab, world=None, n_global=None):
     dist.all_gather_into_tensor(out, padded)
     out = out.view(world, T, cmax, D)
     return torch.cat([out[r, :, :counts[r]] for r in range(world)], dim=1)
+
+
+# ---- the same gather through the engine's C ABI (b200l2f_allgather_trajectories): NCCL bound by the engine at run time, communicator owned by the caller ----------
+class NcclCommunicator:
+    """an ncclComm_t for this process (one rank per GPU), created with the libnccl the process already carries (torch's): rank 0 draws the unique id, the
+    ranks exchange it through the initialised torch.distributed group, every rank calls ncclCommInitRank.  Use: comm = NcclCommunicator(); comm.handle"""
+
+    def __init__(self):
+        import ctypes
+        if not dist.is_initialized():
+            raise RuntimeError("NcclCommunicator needs an initialised torch.distributed process group (for the unique-id exchange)")
+        self._ctypes = ctypes
+        self.lib = self._load()
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        class UniqueId(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_char * 128)]
+        uid = UniqueId()
+        if rank == 0:
+            self._check(self.lib.ncclGetUniqueId(ctypes.byref(uid)), "ncclGetUniqueId")
+        box = [bytes(uid.internal) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctypes.memmove(ctypes.byref(uid), box[0].ljust(128, b"\0"), 128)
+        self.handle = ctypes.c_void_p()
+        self.lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+        self._check(self.lib.ncclCommInitRank(ctypes.byref(self.handle), world, uid, rank), "ncclCommInitRank")
+        self.rank, self.world = rank, world
+
+    def _load(self):
+        ctypes = self._ctypes
+        for name in (os.environ.get("B200L2F_NCCL_LIB"), "libnccl.so.2"):
+            if not name:
+                continue
+            try:
+                return ctypes.CDLL(name, mode=ctypes.RTLD_GLOBAL)
+            except OSError:
+                pass
+        import glob
+        import sys
+        for base in sys.path:                       # torch's wheel: site-packages/nvidia/nccl/lib/libnccl.so.2
+            hits = glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2"))
+            if hits:
+                return ctypes.CDLL(hits[0], mode=ctypes.RTLD_GLOBAL)
+        raise OSError("libnccl.so.2 not found")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed with ncclResult_t %d" % (what, rc))
+
+    def destroy(self):
+        if self.handle:
+            self.lib.ncclCommDestroy.argtypes = [self._ctypes.c_void_p]
+            self.lib.ncclCommDestroy(self.handle)
+            self.handle = None
+
+
+def allgather_trajectories_native(env, comm, slab):
+    """slab: this rank's [T, n_local, D] float32 CUDA tensor (every rank the same shape) -> [T, world * n_local, D], through b200l2f_allgather_trajectories on the
+    engine's stream (ordered behind the kernel that wrote the slab)."""
+    import ctypes
+    T, n_local, D = slab.shape
+    slab = slab.contiguous()
+    out = torch.empty((comm.world * T, n_local, D), dtype=torch.float32, device=slab.device)
+    ranks = ctypes.c_int32(0)
+    env._check(env._lib.b200l2f_allgather_trajectories(env._h, comm.handle, slab.data_ptr(), out.data_ptr(), slab.numel(), ctypes.byref(ranks)))
+    assert ranks.value == comm.world
+    return out.view(comm.world, T, n_local, D).permute(1, 0, 2, 3).reshape(T, comm.world * n_local, D)

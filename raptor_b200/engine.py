@@ -196,6 +196,17 @@ class VectorEnvironment:
     def stream(self):
         return self._lib.b200l2f_stream(self._h)
 
+    def last_status(self, flags=False):
+        """status of the last rollout / collect: dict(n_nonfinite, and for rollouts the rl::utils::evaluation::Result aggregates returns_mean / returns_std /
+        episode_length_mean / episode_length_std / n_terminated / share_terminated); flags=True adds the per-environment non-finite flags"""
+        st = L.Status()
+        f = np.zeros(self.N_ENVIRONMENTS, np.uint8) if flags else None
+        self._check(self._lib.b200l2f_last_status(self._h, ctypes.byref(st), f.ctypes.data if flags else None, L.HOST))
+        out = {k: getattr(st, k) for k, _ in L.Status._fields_ if k != "reserved"}
+        if flags:
+            out["nonfinite_flags"] = f
+        return out
+
     def last_kernel(self):
         return self._lib.b200l2f_last_kernel(self._h).decode()
 

@@ -349,6 +349,38 @@ def test_asynchronous_transfers_match_the_synchronous_calls(rb):
         env.set_state_async(s0[:, :10])
 
 
+def test_last_status_aggregates_and_nonfinite_flags(rb):
+    """b200l2f_last_status: the rl::utils::evaluation::Result aggregates (operations_generic.h:201-213) of a rollout reduced on the device, and the
+    per-environment non-finite flag (05_state_is_nan.h) with its count"""
+    n, T = 1000, 120
+    env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR)
+    env.initialize_rng(3, warmup=16)
+    p = env.get_parameters(); p[:, 115] = 0.6; env.set_parameters(p)        # tighter position threshold: some episodes terminate
+    env.sample_initial_state(); env.load_policy()
+    out = env.rollout(T, record=("returns", "episode_length", "terminated"))
+    st = env.last_status(flags=True)
+    term = out["terminated"].any(0)
+    assert st["n_envs"] == n and st["has_episodes"] == 1 and st["n_nonfinite"] == 0 and not st["nonfinite_flags"].any()
+    assert st["n_terminated"] == int(term.sum()) and 0 < term.sum() < n
+    np.testing.assert_allclose(st["share_terminated"], term.mean(), rtol=1e-12)
+    np.testing.assert_allclose(st["returns_mean"], out["returns"].astype(np.float64).mean(), rtol=1e-9)
+    np.testing.assert_allclose(st["returns_std"], out["returns"].astype(np.float64).std(), rtol=1e-7)
+    np.testing.assert_allclose(st["episode_length_mean"], out["episode_length"].mean(), rtol=1e-12)
+    np.testing.assert_allclose(st["episode_length_std"], out["episode_length"].astype(np.float64).std(), rtol=1e-9)
+    # a rollout that does not ask for returns still reports them
+    env.sample_initial_state(); env.policy_reset()
+    env.rollout(T)
+    assert env.last_status()["has_episodes"] == 1 and np.isfinite(env.last_status()["returns_mean"])
+    # poisoned states are flagged and counted
+    s = env.get_state(); s[7, 0] = np.nan; s[400, 9] = np.nan; env.set_state(s)       # (an Inf would be clamped to the +-1e5 state limit by the step)
+    env.rollout(3)
+    st = env.last_status(flags=True)
+    assert st["n_nonfinite"] >= 2 and st["nonfinite_flags"][7] == 1 and st["nonfinite_flags"][400] == 1 and st["nonfinite_flags"].sum() == st["n_nonfinite"]
+    fresh = rb.VectorEnvironment(4, rb.SPEC_RAPTOR)
+    with pytest.raises(rb.EngineError, match="no rollout"):
+        fresh.last_status()
+
+
 def test_ragged_sizes_and_errors(rb):
     for n in [1, 31, 129, 1000]:
         e = rb.VectorEnvironment(n, rb.SPEC_DEFAULT)

@@ -32,10 +32,10 @@ def num(x):
 def engine_kernel_name(demangled):
     m = re.search(r"(k_[a-z0-9_]+)", demangled)
     base = m.group(1) if m else demangled
-    if base == "k_rollout_raptor_ts":
-        last = re.search(r"(\d+)\s*>\s*\(", demangled)
-        ctas = last.group(1) if last else "3"
-        return "k_rollout_raptor_ts<CTAS=%s>" % ctas
+    if base == "k_rollout_raptor_ts":      # k_rollout_raptor_ts<EnvSpec<...>, FAST, UNIFORM, AXIAL, NOISE, CTAS, RECORD>
+        tail = re.search(r">((?:,\s*\d+)+)\s*>\s*\(", demangled)
+        ints = [int(x) for x in re.findall(r"\d+", tail.group(1))] if tail else []
+        return "k_rollout_raptor_ts<CTAS=%d>" % (ints[4] if len(ints) >= 5 else 3)
     return base
 
 
