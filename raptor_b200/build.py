@@ -30,6 +30,7 @@ SOURCES = {
     "rollout_mlp_ts.cu": TC + ["mlp_tc.cuh"],
     "collect.cu": [],
     "collect_ts.cu": TC + ["mlp_tc.cuh"],
+    "collect_ts_default.cu": TC + ["mlp_tc.cuh"],
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
     "off_policy.cu": TC + ["mlp_tc.cuh", "offpolicy.cuh", "offpolicy_tc.cuh"],

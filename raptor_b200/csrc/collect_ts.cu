@@ -27,6 +27,7 @@ int launch_collect_ts(b200l2f_handle* h, const CollectArgs& a, bool follow, bool
         if(follow) return row_axial ? gots2(spec, dr_c, std::true_type{}, std::true_type{}) : gots2(spec, dr_c, std::true_type{}, std::false_type{});
         return gots2(spec, dr_c, std::false_type{}, std::false_type{});
     };
+    if(h->kind == KIND_DEFAULT) return launch_collect_ts_default(h, a, follow, row_axial);   // collect_ts_default.cu (its own translation unit: compile time)
     if(h->kind == KIND_RAPTOR) return h->dr ? gots(SpecRaptor{}, std::true_type{}) : gots(SpecRaptor{}, std::false_type{});
     return h->dr ? gots(SpecTeacher{}, std::true_type{}) : gots(SpecTeacher{}, std::false_type{});
 }

@@ -594,7 +594,7 @@ int b200l2f_policy_load(b200l2f_handle* h, const b200l2f_policy_desc* desc, cons
     if(desc->arch == B200L2F_POLICY_MLP){
         h->pol = *desc; h->blob_floats = n_floats; h->policy_loaded = true;
         cudaFree(h->d_mlp_tc_image); h->d_mlp_tc_image = nullptr;
-        if(h->kind != KIND_DEFAULT){   // tensor-core operand image (H = 1 specs: the observation fits one K <= 32 operand)
+        {   // tensor-core operand image (H = 1 specs: K1 <= 32; DEFAULT spec, PPO actor: K1 = 88)
             int brc = build_mlp_tc_image(h, desc, blob);
             if(brc) return brc;
         }

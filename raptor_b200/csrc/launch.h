@@ -21,4 +21,6 @@ int build_mlp_tc_image(b200l2f_handle* h, const b200l2f_policy_desc* desc, const
 // collect.cu / collect_ts.cu: k_collect, k_collect_ts
 int launch_collect_fp32(b200l2f_handle* h, const CollectArgs& a);
 int launch_collect_ts(b200l2f_handle* h, const CollectArgs& a, bool follow, bool row_axial);
+// collect_ts_default.cu: k_collect_ts for the DEFAULT spec (H = 16 action ring, OBS 82: the first layer is a K = 88 operand, one CTA per SM)
+int launch_collect_ts_default(b200l2f_handle* h, const CollectArgs& a, bool follow, bool row_axial);
 }  // namespace b200l2f

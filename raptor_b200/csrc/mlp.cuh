@@ -100,11 +100,11 @@ __device__ __forceinline__ void mlp_forward(const float* __restrict__ img, float
 }
 
 // full observation of the spec into the scratch column (and optionally a global row)
-template <class Spec, class P>
+template <class Spec, bool FAST = false, class P>
 __device__ __forceinline__ void observe_to_scratch(const EnvState<Spec>& st, const P& p, uint64_t& rng, const float* hist_ptr, size_t n,
                                                    float* __restrict__ scr, int stride){
     float o[18];
-    observe18<Spec, true>(st, p, rng, o);
+    observe18<Spec, true, FAST>(st, p, rng, o);
 #pragma unroll
     for(int i = 0; i < 18; i++) scr[i * stride] = o[i];
     if constexpr(Spec::H == 1){

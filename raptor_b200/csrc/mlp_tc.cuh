@@ -9,6 +9,10 @@
 // TMEM plan (256 columns per CTA, 2 CTAs/SM):      layer 1: A1 hi [0,32)   lo [32,64)    -> D1 [64,128)
 //                                                  layer 2: A2 hi [128,192) lo [192,256) -> D2 [0,64)      (A1 is dead)
 //                                                  layer 3: A3 hi [64,128)  lo [128,192) -> D3 [192,208)   (D1, A2 are dead)
+// Wide first layer (K1 > 32: the DEFAULT spec's 82-wide observation, K1 = 88, eleven K = 8 operand blocks per plane):
+//                                                  layer 1: A1 hi [0,88)   lo [88,176)   -> D1 [176,240)
+//                                                  layer 2: A2 hi [0,64)   lo [64,128)   -> D2 [128,192)   (A1 dead; D1 [176,192) is read before G2 is issued)
+//                                                  layer 3: A3 hi [0,64)   lo [64,128)   -> D3 [240,256)   (A2, D1 dead)
 // Layer 1 carries its bias as an extra K column (A = 1.0); the biases of layers 2 and 3 (K = 64 is full) are added in the epilogues.
 #pragma once
 #include "mlp.cuh"
@@ -21,7 +25,8 @@ struct MlpTcImage {
     static constexpr int HD = MLP_HD;
     static constexpr int K1 = (IN + 1 + 7) / 8 * 8;   // observation + bias column, padded to the instruction K
     static constexpr int N3 = 16;                     // smallest N of an M = 128 instruction
-    static_assert(K1 <= 32 && OUT <= N3, "TMEM plan");
+    static_assert(K1 <= 88 && OUT <= N3, "TMEM plan");
+    static constexpr bool WIDE = K1 > 32;             // which TMEM column plan mlp_forward_ts uses (see the file header)
     static constexpr int B1_HI = 0, B1_LO = B1_HI + K1 * HD;
     static constexpr int B2_HI = B1_LO + K1 * HD, B2_LO = B2_HI + HD * HD;
     static constexpr int B3_HI = B2_LO + HD * HD, B3_LO = B3_HI + HD * N3;
@@ -106,27 +111,31 @@ __device__ __forceinline__ void ts_run(TsCtx& c, F&& issue){
     tc::tc_fence_after();
 }
 
-// obs: RAW observation (IN values, registers) -> out[OUT] (pre-head outputs).  Called by all 128 threads (inactive lanes compute garbage rows).
-template <int IN, int OUT>
-__device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict__ obs, float* __restrict__ out){
+// obs_at(k): RAW observation column k of this thread's environment (k is a compile-time constant after unrolling: registers or shared memory)
+// -> out[OUT] (pre-head outputs).  Called by all 128 threads (inactive lanes compute garbage rows).
+template <int IN, int OUT, class OBS>
+__device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, float* __restrict__ out){
     using I = MlpTcImage<IN, OUT>;
     constexpr int HD = MLP_HD, K1 = I::K1;
-    constexpr uint32_t A1_HI = 0, A1_LO = 32, D1 = 64, A2_HI = 128, A2_LO = 192, D2 = 0, A3_HI = 64, A3_LO = 128, D3 = 192;
+    constexpr bool WIDE = I::WIDE;
+    constexpr uint32_t A1_HI = 0, A1_LO = WIDE ? 88 : 32, D1 = WIDE ? 176 : 64, A2_HI = WIDE ? 0 : 128, A2_LO = WIDE ? 64 : 192, D2 = WIDE ? 128 : 0,
+                       A3_HI = WIDE ? 0 : 64, A3_LO = WIDE ? 64 : 128, D3 = WIDE ? 240 : 192;
     constexpr uint32_t IDESC64 = tc::make_idesc_tf32(128, 64), IDESC16 = tc::make_idesc_tf32(128, 16);
-    {
-        float x[K1];
 #pragma unroll
-        for(int k = 0; k < IN; k++){   // standardize: (x - mean) [* precision unless it is 0]
-            float v = obs[k] - c.sm_b[I::MEAN + k];
-            const float pr = c.sm_b[I::PREC + k];
-            if(pr != 0.0f) v *= pr;
-            x[k] = v;
+    for(int g = 0; g < K1 / 8; g++){       // one K = 8 operand block at a time: at most 8 observation values live in registers
+        float x[8];
+#pragma unroll
+        for(int j = 0; j < 8; j++){
+            const int k = 8 * g + j;
+            if(k < IN){                    // standardize: (x - mean) [* precision unless it is 0]
+                float v = obs_at(k) - c.sm_b[I::MEAN + k];
+                const float pr = c.sm_b[I::PREC + k];
+                if(pr != 0.0f) v *= pr;
+                x[j] = v;
+            }
+            else x[j] = k == IN ? 1.0f : 0.0f;   // bias column, padding
         }
-        x[IN] = 1.0f;                  // bias column
-#pragma unroll
-        for(int k = IN + 1; k < K1; k++) x[k] = 0.0f;
-#pragma unroll
-        for(int g = 0; g < K1 / 8; g++) ts_put8(c.tmem_lane + A1_HI + 8 * g, c.tmem_lane + A1_LO + 8 * g, x + 8 * g);
+        ts_put8(c.tmem_lane + A1_HI + 8 * g, c.tmem_lane + A1_LO + 8 * g, x);
     }
     ts_run(c, [&](){ ts_issue_gemm(c, D1, A1_HI, A1_LO, K1 / 8, I::B1_HI, I::B1_LO, HD, IDESC64); });
 #pragma unroll
@@ -164,6 +173,10 @@ __device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict
 #pragma unroll
         for(int j = 0; j < OUT; j++) out[j] = v[j] + c.sm_b[I::BIAS3 + j];
     }
+}
+template <int IN, int OUT>
+__device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict__ obs, float* __restrict__ out){   // observation in registers
+    mlp_forward_ts_from<IN, OUT>(c, [&](int k){ return obs[k]; }, out);
 }
 
 // full observation of an H = 1 spec in registers (same values and RNG order as observe_to_scratch)
@@ -383,12 +396,20 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
             dyn_invariants(d, o, st);
         }
-        float obs[IN];
-        observe_regs<Spec, true, true>(st, p, rng, obs);
+        // H == 1: the observation lives in registers.  H > 1 (DEFAULT spec, 82 columns incl. the 16-deep action ring in HBM): it is written straight into
+        // this lane's row of the warp's write-back window and the first layer's operand blocks are read back from there, eight columns at a time
+        float obs[Spec::H == 1 ? IN : 1];
+        float* myrow = slab + lane * WS;
+        if constexpr(Spec::H == 1) observe_regs<Spec, true, true>(st, p, rng, obs);
+        else{
+            __syncwarp();                                 // the previous step's row stream has read the window
+            observe_to_scratch<Spec, true>(st, p, rng, hist_ptr, n, myrow, 1);
+        }
         float vals[12];
         if(!last){                                        // uniform across the CTA
             float mean[OUT], act[4];
-            mlp_forward_ts<IN, OUT>(c, obs, mean);
+            if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT>(c, obs, mean);
+            else mlp_forward_ts_from<IN, OUT>(c, [&](int k){ return myrow[k]; }, mean);
             float lp = 0.0f;
 #pragma unroll
             for(int i = 0; i < 4; i++){                   // epilogue (operations_generic_per_env.h:43-58)
@@ -398,7 +419,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             }
             RewardInputs ri;
             reward_inputs(ri, st);
-            env_step_compiled<Spec, true, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);
+            if(Spec::H == 1 || active) env_step_compiled<Spec, true, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);   // H > 1 writes the action ring in HBM: shadow lanes must not
             const bool term = env_terminated(p, st.x);
             const float r = env_reward<true>(p, ri, act, st.x, term, d.dt);
             ep_ret += r; ep_step += 1;
@@ -409,8 +430,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         }
         // ---- coalesced write-back through the warp's [32][WS] window
         __syncwarp();
+        if constexpr(Spec::H == 1){
 #pragma unroll
-        for(int i = 0; i < IN; i++) slab[lane * WS + i] = obs[i];
+            for(int i = 0; i < IN; i++) slab[lane * WS + i] = obs[i];
+        }
         if(!last){
 #pragma unroll
             for(int i = 0; i < 12; i++) slab[lane * WS + IN + i] = vals[i];

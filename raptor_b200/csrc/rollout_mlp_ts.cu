@@ -60,7 +60,11 @@ int build_mlp_tc_image(b200l2f_handle* h, const b200l2f_policy_desc* desc, const
             using I22 = std::integral_constant<int, 22>; using I26 = std::integral_constant<int, 26>;
             using O4 = std::integral_constant<int, 4>; using O8 = std::integral_constant<int, 8>;
             int brc;
-            if(h->obs_dim == 22) brc = desc->output_dim == 8 ? build(I22{}, O8{}) : build(I22{}, O4{});
+            if(h->obs_dim == 82){   // DEFAULT spec: the PPO actor shape only (collection); squash-head rollouts stay on the CUDA-core kernels
+                if(desc->output_dim != 4) return B200L2F_OK;
+                brc = build(std::integral_constant<int, 82>{}, O4{});
+            }
+            else if(h->obs_dim == 22) brc = desc->output_dim == 8 ? build(I22{}, O8{}) : build(I22{}, O4{});
             else brc = desc->output_dim == 8 ? build(I26{}, O8{}) : build(I26{}, O4{});
             if(brc) return brc;
     return B200L2F_OK;

@@ -624,7 +624,8 @@ def port_final_rng(port, spec, pol, params, states, rng, T):
 
 
 @pytest.mark.parametrize("spec,gemm", [(s_, g_) for s_ in (B.SPEC_RAPTOR, B.SPEC_RAPTOR_DR) for g_ in ("fp32", "tcgen05", "tcgen05-edited-parameters")]
-                         + [(B.SPEC_DEFAULT, "fp32"), (B.SPEC_DEFAULT_DR, "fp32"), (B.SPEC_DEFAULT_DR, "fp32-edited-parameters")])
+                         + [(B.SPEC_DEFAULT, "fp32"), (B.SPEC_DEFAULT_DR, "fp32"), (B.SPEC_DEFAULT_DR, "fp32-edited-parameters"),
+                            (B.SPEC_DEFAULT, "tcgen05"), (B.SPEC_DEFAULT_DR, "tcgen05"), (B.SPEC_DEFAULT_DR, "tcgen05-edited-parameters")])
 def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     """BASELINE config 4 shape: PPO actor (standardize -> 64 -> 64 -> 4, learned log_std), Gaussian sampling, auto-reset on
     terminated-or-step-limit with re-sampled parameters and state, dataset rows in the reference layout; CUDA-core kernel (k_collect)
