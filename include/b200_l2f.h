@@ -181,6 +181,10 @@ int b200l2f_transfers_synchronize(b200l2f_handle* h, int which);
 int b200l2f_observe(b200l2f_handle* h, int slot, float* observations, int ld, int memspace);
 /* ---- rl_tools::step (L2F/operations_generic.h:94-130); vector.step (R/README.md:98). actions [n_envs, 4]; dts [n_envs] or NULL */
 int b200l2f_step(b200l2f_handle* h, int slot, const float* actions, int next_slot, float* dts, int memspace);
+/* ---- n_steps x rl_tools::step under ONE held action (host pointer, 4 floats) for every environment, in place on `slot`, state in registers across the
+ * steps: the loop of the reference's GPU benchmark (RT/src/rl/environments/l2f/cuda/benchmark.cu:111-120: action 0, step, state = next_state).
+ * Default-math arithmetic of the fused kernels; needs noise-free parameters with uniform MDP constants. */
+int b200l2f_step_repeated(b200l2f_handle* h, int slot, const float* action4, int32_t n_steps);
 /* ---- rl_tools::reward / terminated (L2F/operations_generic.h:142-176, L2F/parameters/reward_functions/squared/operations_generic.h:100-129) */
 int b200l2f_reward(b200l2f_handle* h, int slot, const float* actions, int next_slot, float* rewards, int memspace);
 int b200l2f_terminated(b200l2f_handle* h, int slot, uint8_t* flags, int memspace);

@@ -61,6 +61,7 @@ SYMBOLS = {
     "b200l2f_synchronize": (c_int, [vp]),
     "b200l2f_stream": (vp, [vp]),
     "b200l2f_last_kernel": (ctypes.c_char_p, [vp]),
+    "b200l2f_step_repeated": (c_int, [vp, c_int, vp, c_i32]),
     "b200l2f_allgather_trajectories": (c_int, [vp, vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(c_i32)]),
     "b200l2f_last_status": (c_int, [vp, ctypes.POINTER(Status), vp, c_int]),
     "b200l2f_state_dim": (c_int, [vp]),

@@ -34,6 +34,7 @@ SOURCES = {
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],
     "off_policy.cu": TC + ["mlp_tc.cuh", "offpolicy.cuh", "offpolicy_tc.cuh"],
+    "step_only.cu": TC,
     "collective.cu": [],
     "json_io.cu": [],
     "checkpoint_io.cu": ["h5_io.h"],

@@ -168,6 +168,7 @@ int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, in
         if(!host){ p->dev = const_cast<void*>(any); continue; }
         cudaError_t e = temps.alloc(&p->dev, p->bytes);
         if(e == cudaSuccess && p->user_in) e = cudaMemcpyAsync(p->dev, p->user_in, p->bytes, cudaMemcpyHostToDevice, h->stream);
+        else if(e == cudaSuccess) e = cudaMemsetAsync(p->dev, 0, p->bytes, h->stream);   // outputs: defined contents even when the call fails before writing them (initcheck)
         if(e != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("gather_batch: staging: ") + cudaGetErrorString(e));
     }
     if(host) CU(cudaStreamSynchronize(h->stream));

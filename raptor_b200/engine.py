@@ -325,6 +325,11 @@ class VectorEnvironment:
         self._check(self._lib.b200l2f_step(self._h, slot, p, next_slot, pd, ms))
         return dts
 
+    def step_repeated(self, action4, n_steps, slot=0):
+        """n_steps x step under one held action for every environment, in place on `slot` (the loop of the reference's GPU benchmark)"""
+        a = np.ascontiguousarray(action4, np.float32).reshape(4)
+        self._check(self._lib.b200l2f_step_repeated(self._h, slot, a.ctypes.data, int(n_steps)))
+
     def reward(self, action, slot=0, next_slot=1, out=None):
         p, ms, _ = self._arg(action, np.float32, (self.N_ENVIRONMENTS, 4), "action")
         out = np.zeros(self.N_ENVIRONMENTS, np.float32) if out is None else out

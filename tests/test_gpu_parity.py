@@ -381,6 +381,30 @@ def test_last_status_aggregates_and_nonfinite_flags(rb):
         fresh.last_status()
 
 
+@pytest.mark.parametrize("spec", [B.SPEC_DEFAULT, B.SPEC_RAPTOR, B.SPEC_TEACHER])
+def test_step_repeated_equals_repeated_steps(rb, port, spec):
+    """b200l2f_step_repeated (the loop of the reference's GPU benchmark, benchmark.cu:111-120: T x step under a held action, state in registers) against
+    T x rl_tools::step of the oracle from the same states: 1e-4 relative over 50 steps, RNG streams (Langevin targets) bit-exact"""
+    n, T = 300, 50
+    env = rb.VectorEnvironment(n, spec)
+    env.initialize_rng(9, warmup=16)
+    env.sample_initial_state()
+    p, s0, rng = env.get_parameters(), env.get_state(), env.get_rng()
+    a = np.array([0.1, -0.2, 0.05, 0.3], np.float32)
+    env.step_repeated(a, T)
+    got = env.get_state()
+    want = s0.copy()
+    for i in range(n):
+        r = rng[i:i + 1].copy()
+        for _ in range(T):
+            want[i], _dt = port.step(spec, p[i], want[i], a, r)
+        rng[i] = r[0]
+    assert np.array_equal(env.get_rng(), rng)
+    close_relative(got[None], want[None], 1e-4, STATE_GROUPS, "states after %d held-action steps" % T)
+    env.step_repeated(a, 0)
+    assert np.array_equal(env.get_state(), got)
+
+
 def test_ragged_sizes_and_errors(rb):
     for n in [1, 31, 129, 1000]:
         e = rb.VectorEnvironment(n, rb.SPEC_DEFAULT)
