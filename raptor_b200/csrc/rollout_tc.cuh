@@ -98,6 +98,9 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
 #ifndef B200L2F_H_IN_SMEM
 #define B200L2F_H_IN_SMEM 0        // the epilogue's copy of the GRU hidden state in shared memory (8 KB per CTA) instead of re-reading it from TMEM; measured -0.7 %
 #endif
+#ifndef B200L2F_PIPELINE_G1
+#define B200L2F_PIPELINE_G1 0      // k_rollout_raptor_ts: dense 1 of step t + 1 issued before the reward / termination / Langevin work of step t; measured -4 % (profiles/r02_exp4_*)
+#endif
 #ifndef B200L2F_LANGEVIN_BRANCH_FREE
 #define B200L2F_LANGEVIN_BRANCH_FREE 1   // default-math kernels: Langevin target update committed by selects instead of a branch (lets the scheduler interleave the RNG chain)
 #endif
@@ -359,7 +362,56 @@ __device__ __forceinline__ void dynamics_axial_packed(const PC& p, const DynInva
 // FAST: default-math variant (min/max clamps, MUFU reciprocal square root for the quaternion, MUFU Box-Muller for the Langevin target)
 // langevin_normals: the three N(0, 1) draws of the Langevin update, drawn by the caller ahead of time (legal only when nothing else draws from the
 // stream in between, i.e. NOISE == false: the values depend on the stream alone, not on the action) or nullptr = draw here
-template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, bool FAST = false, bool AXIAL = false, class PC>
+// Langevin target of the trajectory (70_post_integration.h:127-170), the last part of post_integration: a function of its own so that a kernel can
+// place it after the next step's observation has been handed to the tensor core (WITH_LANGEVIN = false in env_step_compiled, see k_rollout_raptor_ts)
+template <class Spec, bool FAST, class PC>
+__device__ __forceinline__ void langevin_update_compiled(EnvState<Spec>& st, const PC& p, uint64_t& rng, float dt, const float* __restrict__ langevin_normals = nullptr){
+    if constexpr(Spec::LANGEVIN && FAST && B200L2F_LANGEVIN_BRANCH_FREE){
+        // without a branch: every lane runs the update on copies, the results are committed by selects.  In a warp of mixed trajectory types the branchy
+        // form executes the same instructions anyway, but as a separate basic block -- the 72 dependent integer operations of the six xorshift draws then
+        // cannot be interleaved with the arithmetic around them.  A lane whose trajectory is not Langevin keeps its stream untouched.
+        const bool lang = st.traj_type == 1;
+        const float gamma = p[P_LANGEVIN_GAMMA], omega = p[P_LANGEVIN_OMEGA], sigma = p[P_LANGEVIN_SIGMA], alpha = p[P_LANGEVIN_ALPHA];
+        const float sqrt_dt = p.c(C_SQRT_DT);
+        uint64_t r2 = rng;
+        float L[12];
+#pragma unroll
+        for(int i = 0; i < 12; i++) L[i] = st.lang[i];
+#pragma unroll
+        for(int dim = 0; dim < 3; dim++){
+            const float x_prev = L[6 + dim], v_prev = L[9 + dim];
+            const float dW = sqrt_dt * (langevin_normals ? langevin_normals[dim] : rng_normal_draw_fast(r2, 0.0f, 1.0f));
+            const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
+            const float x_next = x_prev + v_next * dt;
+            L[6 + dim] = x_next; L[9 + dim] = v_next;
+            const float v_smooth = alpha * v_next + (1.0f - alpha) * L[3 + dim];
+            L[dim] = L[dim] + v_smooth * dt;
+            L[3 + dim] = v_smooth;
+        }
+#pragma unroll
+        for(int i = 0; i < 12; i++) st.lang[i] = lang ? L[i] : st.lang[i];
+        rng = lang ? r2 : rng;
+    }
+    else if constexpr(Spec::LANGEVIN){
+        if(st.traj_type == 1){
+            const float gamma = p[P_LANGEVIN_GAMMA], omega = p[P_LANGEVIN_OMEGA], sigma = p[P_LANGEVIN_SIGMA], alpha = p[P_LANGEVIN_ALPHA];
+            const float sqrt_dt = p.c(C_SQRT_DT);
+#pragma unroll
+            for(int dim = 0; dim < 3; dim++){
+                const float x_prev = st.lang[6 + dim], v_prev = st.lang[9 + dim];
+                const float dW = sqrt_dt * (langevin_normals ? langevin_normals[dim] : rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, 1.0f));
+                const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
+                const float x_next = x_prev + v_next * dt;
+                st.lang[6 + dim] = x_next; st.lang[9 + dim] = v_next;
+                const float v_smooth = alpha * v_next + (1.0f - alpha) * st.lang[3 + dim];
+                st.lang[dim] = st.lang[dim] + v_smooth * dt;
+                st.lang[3 + dim] = v_smooth;
+            }
+        }
+    }
+}
+
+template <class Spec, bool ROLLED_RK4 = false, bool NOISE = false, bool FAST = false, bool AXIAL = false, bool WITH_LANGEVIN = true, class PC>
 __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& p, const DynInvariants& d, const float* __restrict__ action, uint64_t& rng,
                                                   float* __restrict__ hist_ptr, size_t n, const float* __restrict__ langevin_normals = nullptr){
     float setpoint[4];
@@ -528,49 +580,7 @@ __device__ __forceinline__ void env_step_compiled(EnvState<Spec>& st, const PC& 
         for(int i = 0; i < 4; i++) hist_ptr[(size_t)(4 * cs + i) * n] = action[i];
         st.current_step = (cs + 1) % Spec::H;
     }
-    if constexpr(Spec::LANGEVIN && FAST && B200L2F_LANGEVIN_BRANCH_FREE){
-        // Langevin target without a branch: every lane runs the update on copies, the results are committed by selects.  In a warp of mixed trajectory
-        // types the branchy form executes the same instructions anyway, but as a separate basic block -- the 72 dependent integer operations of the six
-        // xorshift draws then cannot be interleaved with the arithmetic around them.  A lane whose trajectory is not Langevin keeps its stream untouched.
-        const bool lang = st.traj_type == 1;
-        const float gamma = p[P_LANGEVIN_GAMMA], omega = p[P_LANGEVIN_OMEGA], sigma = p[P_LANGEVIN_SIGMA], alpha = p[P_LANGEVIN_ALPHA];
-        const float sqrt_dt = p.c(C_SQRT_DT);
-        uint64_t r2 = rng;
-        float L[12];
-#pragma unroll
-        for(int i = 0; i < 12; i++) L[i] = st.lang[i];
-#pragma unroll
-        for(int dim = 0; dim < 3; dim++){
-            const float x_prev = L[6 + dim], v_prev = L[9 + dim];
-            const float dW = sqrt_dt * (langevin_normals ? langevin_normals[dim] : rng_normal_draw_fast(r2, 0.0f, 1.0f));
-            const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
-            const float x_next = x_prev + v_next * dt;
-            L[6 + dim] = x_next; L[9 + dim] = v_next;
-            const float v_smooth = alpha * v_next + (1.0f - alpha) * L[3 + dim];
-            L[dim] = L[dim] + v_smooth * dt;
-            L[3 + dim] = v_smooth;
-        }
-#pragma unroll
-        for(int i = 0; i < 12; i++) st.lang[i] = lang ? L[i] : st.lang[i];
-        rng = lang ? r2 : rng;
-    }
-    else if constexpr(Spec::LANGEVIN){
-        if(st.traj_type == 1){
-            const float gamma = p[P_LANGEVIN_GAMMA], omega = p[P_LANGEVIN_OMEGA], sigma = p[P_LANGEVIN_SIGMA], alpha = p[P_LANGEVIN_ALPHA];
-            const float sqrt_dt = p.c(C_SQRT_DT);
-#pragma unroll
-            for(int dim = 0; dim < 3; dim++){
-                const float x_prev = st.lang[6 + dim], v_prev = st.lang[9 + dim];
-                const float dW = sqrt_dt * (langevin_normals ? langevin_normals[dim] : rng_normal_t<Spec::RNG_OOL, FAST>(rng, 0.0f, 1.0f));
-                const float v_next = v_prev + (-gamma * v_prev - omega * omega * x_prev) * dt + sigma * dW;
-                const float x_next = x_prev + v_next * dt;
-                st.lang[6 + dim] = x_next; st.lang[9 + dim] = v_next;
-                const float v_smooth = alpha * v_next + (1.0f - alpha) * st.lang[3 + dim];
-                st.lang[dim] = st.lang[dim] + v_smooth * dt;
-                st.lang[3 + dim] = v_smooth;
-            }
-        }
-    }
+    if constexpr(WITH_LANGEVIN) langevin_update_compiled<Spec, FAST>(st, p, rng, dt, langevin_normals);
 }
 
 // ---- shared-memory plan (bytes) ---------------------------------------------------------------------------------------
@@ -988,7 +998,15 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
     }
     tc::tmem_st_wait();
 
-    for(int t = t_begin; t < t_end; t++){
+    // (Experiment, off by default: measured 16.27e9 against 16.97e9 env-steps/s -- with three CTAs per SM the round trip is already hidden by the other
+    // CTAs, and the longer live ranges of the reward inputs across the barrier cost more than the shorter dependency chain gains.)
+    // Software pipeline over the two tensor-core round trips of a step: once the integrator has produced the next state, the NEXT step's observation is
+    // split, stored and handed to the tensor core (G1) BEFORE this step's termination test, reward and Langevin target update run -- those ~250
+    // instructions then execute in the shadow of the G1 round trip instead of after it.  Legal when nothing between the two points feeds the
+    // observation or the RNG order: no observation noise (its draws would have to follow the Langevin draws) and an observation that does not read the
+    // trajectory target (RAPTOR layout; DEFAULT has no Langevin target).
+    constexpr bool PIPELINE_G1 = B200L2F_PIPELINE_G1 && !NOISE && (Spec::OBS_LAYOUT == OBS_RAPTOR || !Spec::LANGEVIN);
+    auto start_g1 = [&](int t){      // observation of step t (state row / observation row recorded as of step t) -> TMEM -> dense 1 issued
         if(RECORD && a.out_states && active && (t % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
         float obs[24];
@@ -1018,8 +1036,12 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
             issue_gemm(C_D1, C_OBS_HI, C_OBS_LO, 3, TcImage::B1_HI, TcImage::B1_LO, 0, 16, IDESC16, 0);
             tc::mma_commit(bar_mma);
         }
+    };
+    if(PIPELINE_G1 && t_begin < t_end) start_g1(t_begin);
+    for(int t = t_begin; t < t_end; t++){
+        if constexpr(!PIPELINE_G1) start_g1(t);
         // independent work in the shadow of the MMA round trip: the Langevin target's three normals depend on the RNG stream only
-        constexpr bool HOIST = B200L2F_HOIST_LANGEVIN && Spec::LANGEVIN && !NOISE;
+        constexpr bool HOIST = B200L2F_HOIST_LANGEVIN && Spec::LANGEVIN && !NOISE && !PIPELINE_G1;
         float lang_normals[3];
         if constexpr(HOIST){
             if(st.traj_type == 1){
@@ -1154,7 +1176,14 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
         if(RECORD && a.out_actions && active) *reinterpret_cast<float4*>(a.out_actions + ((size_t)t * n + env) * 4) = make_float4(act[0], act[1], act[2], act[3]);
         RewardInputs ri;
         reward_inputs(ri, st);
-        if(Spec::H == 1 || active) env_step_compiled<Spec, false, NOISE, true, AXIAL>(st, p, d, act, rng, hist_ptr, n, HOIST ? lang_normals : nullptr);
+        if constexpr(PIPELINE_G1){
+            if(Spec::H == 1 || active) env_step_compiled<Spec, false, NOISE, true, AXIAL, false>(st, p, d, act, rng, hist_ptr, n);
+            if(t + 1 < t_end) start_g1(t + 1);                 // the next step's dense 1 is on the tensor core from here on
+            if(Spec::H == 1 || active) langevin_update_compiled<Spec, true>(st, p, rng, d.dt);
+        }
+        else{
+            if(Spec::H == 1 || active) env_step_compiled<Spec, false, NOISE, true, AXIAL>(st, p, d, act, rng, hist_ptr, n, HOIST ? lang_normals : nullptr);
+        }
         const bool term = env_terminated(p, st.x);
         const float rw = env_reward<true>(p, ri, act, st.x, term, d.dt);
         if(RECORD && a.out_rewards && active) a.out_rewards[(size_t)t * n + env] = rw;
