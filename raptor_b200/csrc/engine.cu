@@ -830,6 +830,7 @@ int b200l2f_collect(b200l2f_handle* h, int32_t n_steps, int32_t episode_step_lim
     a.params = h->d_params; a.env_row = h->d_env_row; a.state = h->d_state[0]; a.rng = h->d_rng; a.blob = h->d_blob; a.has_std = h->pol.standardize;
     a.episode_step = h->d_episode_step; a.episode_return = h->d_episode_return; a.truncated = h->d_truncated; a.dataset = (float*)dev;
     a.n = h->n; a.T = n_steps; a.step_limit = episode_step_limit; a.error_flag = h->d_flags;
+    a.bulk_rows = ((uintptr_t)dev % 16 == 0 && h->n % 4 == 0 && !std::getenv("B200L2F_NO_BULK_ROWS")) ? 1 : 0;
     std::memcpy(a.row, h->h_env_row, sizeof(a.row));
     const bool follow = h->params_follow_env_row;
     // axial vehicles (see b200l2f_rollout): decided from the nominal row when the columns follow it (domain randomisation keeps the property)

@@ -241,6 +241,7 @@ struct CollectArgs {
     float* dataset;           // [(T+1)*n][D]
     int n, T, step_limit;
     int* error_flag;
+    int bulk_rows;            // tensor-core kernel: dataset 16-byte aligned and n % 4 == 0 -> a warp's 32 rows leave as one bulk copy
 };
 template <class Spec, bool DR>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_constant__ CollectArgs a){

@@ -18,6 +18,10 @@
 #include "mlp.cuh"
 #include "rollout_tc.cuh"
 
+#ifndef B200L2F_COLLECT_ROLLED_RK4
+#define B200L2F_COLLECT_ROLLED_RK4 1   // the collection kernel's integrator as one rolled stage loop (code size, see k_collect_ts)
+#endif
+
 namespace b200l2f {
 
 template <int IN, int OUT>
@@ -199,7 +203,7 @@ struct MlpTsSmem {
     static constexpr int BAR = DYN + C_DIM * BLOCK * 4;
     static constexpr int SLAB = BAR + 32;                                 // collect only: per-warp [32][W] write-back windows
     static constexpr int TOTAL_ROLLOUT = SLAB;
-    static constexpr int TOTAL_COLLECT = SLAB + 4 * 32 * (IN + 13) * 4;   // row stride W + 1 (odd): conflict-free on both sides
+    static constexpr int TOTAL_COLLECT = SLAB + 4 * 32 * (IN + 15) * 4;   // the warp's 32 dataset rows, row stride D = IN + 15 (odd for every spec: conflict-free)
 };
 
 // CTA prologue shared by both kernels: barriers, TMEM allocation, weight image by TMA.  Returns the context; every thread must call it.
@@ -350,17 +354,21 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_mlp_ts(const __grid_consta
 template <class Spec, bool DR, bool FOLLOW, bool AXIAL>
 __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__ CollectArgs a, const float* __restrict__ tc_image, int* __restrict__ sched){
     constexpr int IN = Spec::OBS_DIM, OUT = 4;
-    constexpr int D = IN + 15, W = IN + 12, WS = W + 1;   // W columns written per step; WS: row stride of the staging window
+    constexpr int D = IN + 15, W = IN + 12, WS = D;        // W columns produced per step; the staging window has the dataset's own row stride
     using SM = MlpTsSmem<IN, OUT>;
     using I = MlpTcImage<IN, OUT>;
     extern __shared__ __align__(1024) unsigned char smraw[];
     float* sm_dyn = reinterpret_cast<float*>(smraw + SM::DYN);
     TsCtx c = mlp_ts_prologue<IN, OUT>(smraw, tc_image);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* slab = reinterpret_cast<float*>(smraw + SM::SLAB) + (size_t)warp * 32 * WS;   // private to this warp
+    float* slab = reinterpret_cast<float*>(smraw + SM::SLAB) + (size_t)warp * 32 * WS;   // private to this warp: the image of its 32 consecutive dataset rows
+    float* myrow = slab + lane * WS;                       // odd stride: conflict-free
+#pragma unroll
+    for(int i = W; i < D; i++) myrow[i] = 0.0f;            // the learner's columns (value | advantage | target_value) leave as zeros, see b200l2f_collect
     const size_t n = (size_t)a.n;
     __shared__ int s_item;
     const int n_tiles = (a.n + BLOCK - 1) / BLOCK;
+    bool store_pending = false;                            // this warp has a bulk store in flight that still reads the window
     for(;;){
     if(tid == 0) s_item = atomicAdd(sched, 1);
     __syncthreads();
@@ -383,6 +391,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
     int ep_step = a.episode_step[env]; float ep_ret = a.episode_return[env]; bool truncated = a.truncated[env] != 0;
     const int warp_env0 = tile * BLOCK + warp * 32;
     const int rows_valid = min(32, a.n - warp_env0);
+    // a full warp's 32 rows are one contiguous, 16-byte aligned run of 32 * D floats in the dataset: ONE bulk copy (TMA, shared -> global) per
+    // warp and step instead of a store loop.  Ragged last warp / unaligned dataset: the element loop below.
+    const bool bulk = a.bulk_rows != 0 && rows_valid == 32;
 
     for(int t = 0; t <= a.T; t++){
         const bool last = t == a.T;                       // final observation only (operations_generic.h:122-129)
@@ -396,16 +407,22 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
             dyn_invariants(d, o, st);
         }
-        // H == 1: the observation lives in registers.  H > 1 (DEFAULT spec, 82 columns incl. the 16-deep action ring in HBM): it is written straight into
-        // this lane's row of the warp's write-back window and the first layer's operand blocks are read back from there, eight columns at a time
+        // the previous step's bulk store has read the window (in flight since the end of that step: the wait is free)
+        if(store_pending){ if(lane == 0) tc::bulk_store_wait_read(); store_pending = false; }
+        __syncwarp();
+        // The observation goes straight into this lane's row of the window.  H == 1: it also stays in registers for the first layer's operand.
+        // H > 1 (DEFAULT spec, 82 columns incl. the 16-deep action ring in HBM): the first layer's operand blocks are read back from the window,
+        // eight columns at a time
         float obs[Spec::H == 1 ? IN : 1];
-        float* myrow = slab + lane * WS;
-        if constexpr(Spec::H == 1) observe_regs<Spec, true, true>(st, p, rng, obs);
-        else{
-            __syncwarp();                                 // the previous step's row stream has read the window
-            observe_to_scratch<Spec, true>(st, p, rng, hist_ptr, n, myrow, 1);
+        if constexpr(Spec::H == 1){
+            observe_regs<Spec, true, true>(st, p, rng, obs);
+#pragma unroll
+            for(int i = 0; i < IN; i++) myrow[i] = obs[i];
         }
+        else observe_to_scratch<Spec, true>(st, p, rng, hist_ptr, n, myrow, 1);
         float vals[12];
+#pragma unroll
+        for(int i = 0; i < 12; i++) vals[i] = 0.0f;       // the final rows carry the observation only
         if(!last){                                        // uniform across the CTA
             float mean[OUT], act[4];
             if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT>(c, obs, mean);
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             }
             RewardInputs ri;
             reward_inputs(ri, st);
-            if(Spec::H == 1 || active) env_step_compiled<Spec, true, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);   // H > 1 writes the action ring in HBM: shadow lanes must not
+            if(Spec::H == 1 || active) env_step_compiled<Spec, B200L2F_COLLECT_ROLLED_RK4 != 0, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);   // H > 1 writes the action ring in HBM: shadow lanes must not
             const bool term = env_terminated(p, st.x);
             const float r = env_reward<true>(p, ri, act, st.x, term, d.dt);
             ep_ret += r; ep_step += 1;
@@ -428,33 +445,26 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             for(int i = 0; i < 4; i++){ vals[i] = mean[i]; vals[4 + i] = act[i]; }
             vals[8] = lp; vals[9] = r; vals[10] = term ? 1.0f : 0.0f; vals[11] = truncated ? 1.0f : 0.0f;
         }
-        // ---- coalesced write-back through the warp's [32][WS] window
-        __syncwarp();
-        if constexpr(Spec::H == 1){
 #pragma unroll
-            for(int i = 0; i < IN; i++) slab[lane * WS + i] = obs[i];
+        for(int i = 0; i < 12; i++) myrow[IN + i] = vals[i];
+        float* gbase = a.dataset + ((size_t)t * n + warp_env0) * D;
+        if(bulk){
+            tc::fence_async_smem();                       // this lane's row -> visible to the async proxy
+            __syncwarp();
+            if(lane == 0) tc::bulk_store(gbase, slab, 32 * D * 4);
+            store_pending = true;
         }
-        if(!last){
-#pragma unroll
-            for(int i = 0; i < 12; i++) slab[lane * WS + IN + i] = vals[i];
-        }
-        __syncwarp();
-        {
-            float* gbase = a.dataset + ((size_t)t * n + warp_env0) * D;
-            // the window is the 32 rows back to back: element idx sits in row idx / ncols (compile-time divisor -> multiply-shift)
-            auto stream_rows = [&](auto ncols_c){
-                constexpr int NC = decltype(ncols_c)::value;
+        else{
+            __syncwarp();
+            // the window is the rows back to back (learner columns included: zeros), so is the dataset
 #pragma unroll 2
-                for(int it = 0; it < NC; it++){
-                    const int idx = lane + 32 * it;
-                    const int r = idx / NC, cc = idx - r * NC;
-                    if(r < rows_valid) gbase[r * D + cc] = slab[r * WS + cc];
-                }
-            };
-            if(!last) stream_rows(std::integral_constant<int, W>{});
-            else stream_rows(std::integral_constant<int, IN>{});
+            for(int it = 0; it < D; it++){
+                const int idx = lane + 32 * it;
+                const int r = idx / D;
+                if(r < rows_valid) gbase[idx] = slab[idx];
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     if(active){
         store_state(st, a.state + env, n);
@@ -462,6 +472,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         a.episode_step[env] = ep_step; a.episode_return[env] = ep_ret; a.truncated[env] = truncated ? 1 : 0;
     }
     }   // tile loop
+    if(store_pending && lane == 0) tc::bulk_store_wait_all();   // the window must outlive the copy
     mlp_ts_epilogue(c);
 }
 

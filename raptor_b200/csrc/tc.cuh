@@ -42,6 +42,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- TMA: 1-D bulk copy shared -> global (bulk async-group completion; SASS: UBLKCP.S2G).  dst, src and bytes are multiples of 16.
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes){
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read(){ asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // the source may be rewritten
+__device__ __forceinline__ void bulk_store_wait_all(){ asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // the writes are complete
+
 // ---- proxy / tcgen05 fences -------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem(){ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }   // generic-proxy STS -> visible to the tensor core
 __device__ __forceinline__ void tc_fence_before(){ asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
