@@ -317,6 +317,22 @@ typedef struct {
 } b200l2f_batch;
 int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, int32_t max_episode_length, int32_t env_begin, int32_t env_count, uint64_t* rng_states,
                          const b200l2f_batch* out);
+/* gather_batch for any SEQUENCE_LENGTH (recurrent SAC): INC/rl/components/off_policy_runner/operations_generic.h:240-434 with the batch parameters of
+ * off_policy_runner.h:78-85 as run-time values (b200l2f_batch_parameters_default = the reference's defaults for SEQUENCE_LENGTH > 1).  One RNG stream per batch
+ * sample as above.  With L = sequence_length the batch tensors have the SequentialBatch shapes (off_policy_runner.h:96-141): observations_actions [L+1][B][OBS+4],
+ * rewards / terminated / reset / final_step_mask [L][B], next_reset / next_final_step_mask [L+1][B] (the `*_base` tensors; the reference's `next_*` views start
+ * at row include_first_step_in_targets ? 0 : 1, operations_generic.h:87-92).  All four masks and rb->episode_start are required; env_index / sample_index report
+ * the environment and the first ring row of each sample.  rewards / terminated of padding steps, which the reference never writes, are 0. */
+typedef struct {
+    int32_t sequence_length;                              /* SEQUENCE_LENGTH >= 1 */
+    int32_t include_first_step_in_targets;                /* INCLUDE_FIRST_STEP_IN_TARGETS */
+    int32_t always_sample_from_initial_state;             /* ALWAYS_SAMPLE_FROM_INITIAL_STATE (needs capacity >= max_episode_length, :258) */
+    int32_t random_seq_length;                            /* RANDOM_SEQ_LENGTH */
+    int32_t enable_nominal_sequence_length_probability;   /* ENABLE_NOMINAL_SEQUENCE_LENGTH_PROBABILITY */
+    float   nominal_sequence_length_probability;          /* NOMINAL_SEQUENCE_LENGTH_PROBABILITY */
+} b200l2f_batch_parameters;
+int b200l2f_gather_batch_sequential(b200l2f_handle* h, const b200l2f_replay_buffers* rb, const b200l2f_batch_parameters* parameters, int32_t max_episode_length, int32_t env_begin,
+                                    int32_t env_count, uint64_t* rng_states, const b200l2f_batch* out);
 int b200l2f_runner_get_state(b200l2f_handle* h, int32_t* episode_step, float* episode_return, uint8_t* truncated, int memspace);
 int b200l2f_runner_set_state(b200l2f_handle* h, const int32_t* episode_step, const float* episode_return, const uint8_t* truncated, int memspace);
 

@@ -161,6 +161,37 @@ POLICY_RAPTOR_GRU, POLICY_MLP = 0, 1
 HEAD_IDENTITY, HEAD_SQUASH_EVAL, HEAD_PPO_GAUSSIAN, HEAD_SQUASH_SAMPLE = 0, 1, 2, 3
 
 
+def new_sequential_batch(B, L, obs):
+    """SequentialBatch tensors (off_policy_runner.h:96-141) for SEQUENCE_LENGTH L: [L + 1] = the padded (`*_base`) tensors"""
+    return dict(observations_actions=np.zeros((L + 1, B, obs + 4), np.float32), rewards=np.zeros((L, B), np.float32), terminated=np.zeros((L, B), np.uint8),
+                reset=np.zeros((L, B), np.uint8), next_reset=np.zeros((L + 1, B), np.uint8), final_step_mask=np.zeros((L, B), np.uint8),
+                next_final_step_mask=np.zeros((L + 1, B), np.uint8), env_index=np.zeros(B, np.int32), sample_index=np.zeros(B, np.int32))
+
+
+def synthetic_replay_rings(rs, n, capacity, obs, p_truncated=0.12, fill=None):
+    """replay rings with arbitrary contents but CONSISTENT bookkeeping (what `add` maintains, replay_buffer/operations_generic.h:54-79): rows written in
+    order from row 0, `truncated` ends an episode, episode_start[row] = first row of the row's episode; fill[e] rows were added to ring e (>= capacity: wrapped)"""
+    D = 2 * obs + 7
+    runner = new_off_policy_runner(n, capacity, obs)
+    for e in range(n):
+        total = int(fill[e]) if fill is not None else int(rs.randint(capacity // 2, 3 * capacity))
+        pos, start = 0, 0
+        for _ in range(total):
+            row = rs.uniform(-1, 1, D).astype(np.float32)
+            trunc = rs.uniform() < p_truncated
+            row[D - 2] = float(trunc and rs.uniform() < 0.5); row[D - 1] = float(trunc)
+            runner["replay"][e, pos] = row
+            runner["episode_start"][e, pos] = start
+            pos = (pos + 1) % capacity
+            if trunc:
+                start = pos
+            if pos == 0:
+                runner["full"][e] = 1
+        runner["position"][e] = pos
+        runner["current_episode_start"][e] = start
+    return runner
+
+
 def new_off_policy_runner(n, capacity, obs_dim):
     """runner state after rl_tools::init(device, runner): everything truncated, empty replay rings (off_policy_runner/operations_generic.h:163-180)"""
     return dict(episode_step=np.zeros(n, np.int32), episode_return=np.zeros(n, np.float32), truncated=np.ones(n, np.uint8),
@@ -186,6 +217,7 @@ class Port(_Common):
         L.oracle_collect.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, f32, c_int]
         L.oracle_off_policy_steps.argtypes = [c_int, ctypes.POINTER(OraclePolicy), c_int, c_int, c_int, c_int, c_int, f32, f32, f32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.oracle_gather_batch.argtypes = [c_int, c_int, c_int, c_int, c_int, f32, vp, vp, c_int, u64, f32, f32, vp, vp, vp, vp, vp, vp, vp]
+        L.oracle_gather_batch_sequential.argtypes = [c_int, c_int, c_int, c_int, c_int, f32, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_float, c_int, u64, f32, f32, vp, vp, vp, vp, vp, vp, vp]
         L.oracle_evaluate_values.argtypes = [ctypes.POINTER(OraclePolicy), c_int, c_int, f32, c_int]
         L.oracle_estimate_generalized_advantages.argtypes = [c_int, c_int, f32, c_int, c_float, c_float, c_int]
         L.oracle_normalizer_update.argtypes = [c_int, c_int, f32, c_int, f32, f32, ctypes.POINTER(c_int)]
@@ -256,6 +288,21 @@ class Port(_Common):
                                      B, rngs, out["observations_actions"], out["rewards"], *[_ptr(out[k]) for k in ("terminated", "reset", "next_reset", "final_step_mask", "next_final_step_mask", "env_index", "sample_index")])
         return out
 
+    def gather_batch_sequential(self, runner, rngs, max_episode_length, sequence_length, include_first_step_in_targets=True, always_sample_from_initial_state=True,
+                                random_seq_length=True, enable_nominal_sequence_length_probability=True, nominal_sequence_length_probability=0.5, env_begin=0, env_count=None):
+        """batch of sequences (any SEQUENCE_LENGTH) from the replay rings of `runner`, one RNG stream per sample (rngs [B], advanced in place); the flag defaults
+        are the reference's for SEQUENCE_LENGTH > 1 (off_policy_runner.h:78-85)"""
+        n, capacity, D = runner["replay"].shape
+        obs = (D - 7) // 2
+        B, L = rngs.shape[0], sequence_length
+        out = new_sequential_batch(B, L, obs)
+        self.lib.oracle_gather_batch_sequential(obs, capacity, max_episode_length, env_begin, n if env_count is None else env_count, runner["replay"], _ptr(runner["episode_start"]),
+                                                _ptr(runner["position"]), _ptr(runner["full"]), L, int(include_first_step_in_targets), int(always_sample_from_initial_state),
+                                                int(random_seq_length), int(enable_nominal_sequence_length_probability), nominal_sequence_length_probability, B, rngs,
+                                                out["observations_actions"], out["rewards"],
+                                                *[_ptr(out[k]) for k in ("terminated", "reset", "next_reset", "final_step_mask", "next_final_step_mask", "env_index", "sample_index")])
+        return out
+
     def evaluate_values(self, critic, data, n, T):
         """critic values over all (T+1)*n observation rows -> the all_values column, in place"""
         self.lib.oracle_evaluate_values(ctypes.byref(critic), n, T, data, data.shape[1])
@@ -315,6 +362,8 @@ class Ref(_Common):
             L.ref_off_policy_steps.argtypes = [c_int, c_int, f32, f32, f32, f32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         if hasattr(L, "ref_gather_batch"):
             L.ref_gather_batch.argtypes = [f32, vp, vp, u64, f32, f32, vp, vp, vp, vp, vp]
+        if hasattr(L, "ref_gather_batch_sequential"):
+            L.ref_gather_batch_sequential.argtypes = [c_int, f32, vp, vp, vp, u64, f32, f32, vp, vp, vp, vp, vp]
         if hasattr(L, "ref_dagger_add_to_dataset"):
             u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
             i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -418,6 +467,30 @@ class Ref(_Common):
                    next_reset=np.zeros((2, B), np.uint8), final_step_mask=np.zeros(B, np.uint8), next_final_step_mask=np.zeros((2, B), np.uint8))
         self.lib.ref_gather_batch(runner["replay"], _ptr(runner["position"]), _ptr(runner["full"]), rngs, out["observations_actions"], out["rewards"],
                                   *[_ptr(out[k]) for k in ("terminated", "reset", "next_reset", "final_step_mask", "next_final_step_mask")])
+        return out
+
+    def gather_batch_sequential_configs(self):
+        """the parameter sets ref_gather_batch_sequential was instantiated for: list of dicts (sequence_length, flags, probability, ring capacity)"""
+        out = []
+        for i in range(self.lib.ref_gather_batch_sequential_configs()):
+            v = [c_int() for _ in range(5)]; prob = c_float(); cap = c_int()
+            self.lib.ref_gather_batch_sequential_config(i, *[ctypes.byref(x) for x in v], ctypes.byref(prob), ctypes.byref(cap))
+            out.append(dict(config=i, sequence_length=v[0].value, include_first_step_in_targets=bool(v[1].value), always_sample_from_initial_state=bool(v[2].value),
+                            random_seq_length=bool(v[3].value), enable_nominal_sequence_length_probability=bool(v[4].value),
+                            nominal_sequence_length_probability=prob.value, capacity=cap.value))
+        return out
+
+    def gather_batch_sequential(self, config, runner, rngs):
+        """the reference's gather_batch_step for compiled parameter set `config` (batch ref_gather_batch_size()) over the rings of `runner`"""
+        B = self.lib.ref_gather_batch_size()
+        cfg = self.gather_batch_sequential_configs()[config]
+        assert rngs.shape[0] == B and runner["replay"].shape[1] == cfg["capacity"]
+        obs = (runner["replay"].shape[2] - 7) // 2
+        out = new_sequential_batch(B, cfg["sequence_length"], obs)
+        rc = self.lib.ref_gather_batch_sequential(config, runner["replay"], _ptr(runner["episode_start"]), _ptr(runner["position"]), _ptr(runner["full"]), rngs,
+                                                  out["observations_actions"], out["rewards"], *[_ptr(out[k]) for k in ("terminated", "reset", "next_reset", "final_step_mask", "next_final_step_mask")])
+        assert rc == 0
+        del out["env_index"], out["sample_index"]
         return out
 
     # ---- checkpoint code export: the reference's own save_code (kind 1 = SAC teacher MLP + sample_and_squash, 2 = PPO standardize + MLP + log_std)

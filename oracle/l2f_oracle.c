@@ -989,6 +989,110 @@ void oracle_gather_batch(int obs_dim, int capacity, int max_episode_length, int 
     }
 }
 
+/* gather_batch for any SEQUENCE_LENGTH (recurrent SAC): INC/rl/components/off_policy_runner/operations_generic.h:240-420 (gather_batch_step) restated
+ * line by line, with the batch parameters of off_policy_runner.h:78-85 as run-time values and one RNG stream per batch sample, the environment drawn
+ * from it first (:423-434, operations_cuda.h:36-60).  L = SEQUENCE_LENGTH, P = L + 1 = PADDED_SEQUENCE_LENGTH.  Outputs (off_policy_runner.h:96-141):
+ *   observations_actions [P][B][OBS + 4]; rewards / terminated / reset / final_step_mask [L][B]; next_reset / next_final_step_mask [P][B] (the
+ *   *_base tensors; the reference's `next_*` views start at row include_first_step_in_targets ? 0 : 1, operations_generic.h:87-92).
+ * uniform_real(0.0, 1.0) is the double overload: state / (double)MAX_INDEX (random/operations_generic.h:52-58), compared with the float parameter.
+ * rewards / terminated of padding steps are not written by the reference (stale memory): this restatement, like the CUDA path, writes zeros there. */
+void oracle_gather_batch_sequential(int obs_dim, int capacity, int max_episode_length, int env_begin, int env_count, const float* replay, const int* episode_start,
+                                    const int* position, const unsigned char* full, int L, int include_first_step_in_targets, int always_sample_from_initial_state,
+                                    int random_seq_length, int enable_nominal, float nominal_probability,
+                                    int B, uint64_t* rng_states, float* observations_actions, float* rewards, unsigned char* terminated,
+                                    unsigned char* reset, unsigned char* next_reset_base, unsigned char* final_step_mask, unsigned char* next_final_step_mask_base,
+                                    int* env_index, int* sample_index_out){
+    const int OBS = obs_dim, D = 2 * OBS + 7, W = OBS + 4, P = L + 1;
+    const int next_offset = include_first_step_in_targets ? 0 : 1;
+    for(int b = 0; b < B; b++){
+        uint64_t* rng = rng_states + b;
+        const int env = env_begin + (int)(rng_next_state(rng) % (uint64_t)env_count);
+        const float* rb = replay + (size_t)env * capacity * D;
+        const int* ep_start = episode_start + (size_t)env * capacity;
+        const int is_full = full[env], pos = position[env];
+        const size_t eligible = is_full ? (always_sample_from_initial_state ? (size_t)(capacity - max_episode_length) : (size_t)capacity) : (size_t)pos;
+        const size_t sample_index_max = eligible - 1;
+        size_t sample_index = 0;
+        size_t current_seq_length = (size_t)L;
+        if(random_seq_length){
+            /* the reference evaluates `ENABLE && uniform_real(...) < p` first: the draw happens only when ENABLE is set (:266) */
+            if(enable_nominal){
+                const double u = (double)rng_next_state(rng) / (double)UINT64_MAX;
+                if(u < (double)nominal_probability) current_seq_length = (size_t)L;
+                else if(L > 1) current_seq_length = 1 + (size_t)(rng_next_state(rng) % (uint64_t)(L - 1));
+            }
+            else if(L > 1) current_seq_length = 1 + (size_t)(rng_next_state(rng) % (uint64_t)(L - 1));
+        }
+        size_t current_seq_step = 0;
+        int previous_step_truncated = 0, previous_padding_step = 1;
+        for(int s = 0; s < L; s++){ final_step_mask[(size_t)s * B + b] = 0; reset[(size_t)s * B + b] = 0; rewards[(size_t)s * B + b] = 0; terminated[(size_t)s * B + b] = 0; }
+        for(int s = 0; s < P; s++){ next_final_step_mask_base[(size_t)s * B + b] = 0; next_reset_base[(size_t)s * B + b] = 0; }
+        reset[b] = 1;                                              /* :286-288 */
+        next_reset_base[b] = 1;
+        next_reset_base[(size_t)next_offset * B + b] = 1;
+        int first_sample = -1;
+        for(int seq = 0; seq < P; seq++){
+            if(previous_step_truncated){                           /* :290-299 */
+                previous_step_truncated = 0;
+                previous_padding_step = 1;
+                next_final_step_mask_base[(size_t)seq * B + b] = 1;
+                if(seq < P - 1) reset[(size_t)seq * B + b] = 1;
+                continue;
+            }
+            if(previous_padding_step){                             /* :300-321 */
+                if(seq < P - 1) reset[(size_t)seq * B + b] = 1;
+                next_reset_base[(size_t)seq * B + b] = 1;
+                const size_t sample_offset = (size_t)(rng_next_state(rng) % (uint64_t)(sample_index_max + 1));
+                if(is_full) sample_index = ((size_t)pos + (size_t)max_episode_length + sample_offset) % (size_t)capacity;
+                else sample_index = sample_offset;
+                if(always_sample_from_initial_state) sample_index = (size_t)ep_start[sample_index];
+                if(first_sample < 0) first_sample = (int)sample_index;
+            }
+            const float* row = rb + sample_index * D;
+            float* oa = observations_actions + ((size_t)seq * B + b) * W;
+            memcpy(oa, row, sizeof(float) * W);                    /* obs | action (:324-345) */
+            if(seq < P - 1){
+                rewards[(size_t)seq * B + b] = row[OBS + 4];
+                terminated[(size_t)seq * B + b] = row[2 * OBS + 5] != 0;
+            }
+            int truncated = row[2 * OBS + 6] != 0;                 /* :352 */
+            size_t next_sample_index = sample_index + 1;
+            if(is_full) next_sample_index = next_sample_index % (size_t)capacity;
+            if(next_sample_index == (size_t)pos) truncated = 1;
+            if(seq == P - 2) truncated = 1;
+            if(random_seq_length){                                 /* :363-388 */
+                if(current_seq_step == current_seq_length - 1){
+                    truncated = 1;
+                    if(L > 1){
+                        if(enable_nominal){
+                            const double u = (double)rng_next_state(rng) / (double)UINT64_MAX;
+                            if(u < (double)nominal_probability) current_seq_length = (size_t)L;
+                            else current_seq_length = 1 + (size_t)(rng_next_state(rng) % (uint64_t)(L - 1));
+                        }
+                        else current_seq_length = 1 + (size_t)(rng_next_state(rng) % (uint64_t)(L - 1));
+                    }
+                    else current_seq_length = (size_t)L;
+                }
+                if(truncated) current_seq_step = 0;
+                else current_seq_step += 1;
+            }
+            if(truncated){                                         /* :393-417 */
+                if(seq < P - 1){
+                    final_step_mask[(size_t)seq * B + b] = 1;
+                    float* nx = observations_actions + ((size_t)(seq + 1) * B + b) * W;
+                    memcpy(nx, row + OBS + 5, sizeof(float) * OBS);
+                    for(int i = 0; i < 4; i++) nx[OBS + i] = 0;
+                }
+            }
+            sample_index = next_sample_index;
+            previous_padding_step = 0;
+            previous_step_truncated = truncated;
+        }
+        if(env_index) env_index[b] = env;
+        if(sample_index_out) sample_index_out[b] = first_sample;
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------
  * learner feed of the PPO loop step (INC/rl/algorithms/ppo/loop/core/operations_generic.h:104-117): critic values over
  * all_observations -> all_values column, generalized advantage estimation, running observation normalizer.

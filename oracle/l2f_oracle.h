@@ -82,6 +82,12 @@ void oracle_gather_batch(int obs_dim, int capacity, int max_episode_length, int 
                          int B, uint64_t* rng_states, float* observations_actions, float* rewards, unsigned char* terminated,
                          unsigned char* reset, unsigned char* next_reset, unsigned char* final_step_mask, unsigned char* next_final_step_mask,
                          int* env_index, int* sample_index_out);
+void oracle_gather_batch_sequential(int obs_dim, int capacity, int max_episode_length, int env_begin, int env_count, const float* replay, const int* episode_start,
+                                    const int* position, const unsigned char* full, int L, int include_first_step_in_targets, int always_sample_from_initial_state,
+                                    int random_seq_length, int enable_nominal, float nominal_probability,
+                                    int B, uint64_t* rng_states, float* observations_actions, float* rewards, unsigned char* terminated,
+                                    unsigned char* reset, unsigned char* next_reset_base, unsigned char* final_step_mask, unsigned char* next_final_step_mask_base,
+                                    int* env_index, int* sample_index_out);
 /* learner feed (PPO loop step between collect and train): critic values, GAE, running observation normalizer */
 void oracle_evaluate_values(const oracle_policy_t* critic, int N, int T, float* dataset, int data_dim);
 void oracle_estimate_generalized_advantages(int N, int T, float* dataset, int data_dim, float gamma, float lambda, int ignore_termination);

@@ -1031,12 +1031,12 @@ namespace ref_opr{
         using Module = typename rlt::nn_models::sequential::Module<T_CONTENT, T_NEXT_MODULE>;
         using MODEL = rlt::nn_models::sequential::Build<CAP, Module<MLP, Module<SAMPLE_AND_SQUASH>>, INPUT_SHAPE>;
     };
-    template <typename ENV, bool SAMPLE>
+    template <typename ENV, bool SAMPLE, TI CAP = CAPACITY>
     struct RunnerSpec{
         struct PARAMETERS: rlt::rl::components::off_policy_runner::ParametersDefault<T, TI>{
             static constexpr TI N_ENVIRONMENTS = N;
             static constexpr bool ASYMMETRIC_OBSERVATIONS = false;
-            static constexpr TI REPLAY_BUFFER_CAPACITY = CAPACITY;
+            static constexpr TI REPLAY_BUFFER_CAPACITY = CAP;
             static constexpr TI EPISODE_STEP_LIMIT = STEP_LIMIT;
             static constexpr bool SAMPLE_PARAMETERS = SAMPLE;
         };
@@ -1168,6 +1168,91 @@ namespace ref_opr{
         rlt::free(device, batch); rlt::free(device, runner);
         delete runner_ptr;
     }
+}
+namespace ref_opr{
+    // ---- any SEQUENCE_LENGTH: the reference's gather_batch_step on its own SequentialBatch, for a handful of compile-time parameter sets
+    // (off_policy_runner.h:78-85 defaults for SEQUENCE_LENGTH > 1 and variations of every switch)
+    template <bool FIRST, bool INITIAL, bool RANDOM, bool ENABLE, int PROB_PERCENT>
+    struct SeqParameters{
+        static constexpr bool INCLUDE_FIRST_STEP_IN_TARGETS = FIRST;
+        static constexpr bool ALWAYS_SAMPLE_FROM_INITIAL_STATE = INITIAL;
+        static constexpr bool RANDOM_SEQ_LENGTH = RANDOM;
+        static constexpr bool ENABLE_NOMINAL_SEQUENCE_LENGTH_PROBABILITY = ENABLE;
+        static constexpr T NOMINAL_SEQUENCE_LENGTH_PROBABILITY = (T)PROB_PERCENT / (T)100;
+    };
+    template <TI L, typename PARAMS, TI CAP>
+    static void gather_sequential(const float* replay, const int* episode_start, const int* position_in, const unsigned char* full_in, uint64_t* rng_states,
+                                  float* observations_actions, float* rewards, unsigned char* terminated, unsigned char* reset, unsigned char* next_reset_base,
+                                  unsigned char* final_step_mask, unsigned char* next_final_step_mask_base){
+        using ENV = ENV_TEACHER;
+        using RS = RunnerSpec<ENV, true, CAP>;
+        using RUNNER = typename RS::RUNNER;
+        constexpr TI CAPACITY = CAP;
+        using BATCH_SPEC = rlt::rl::components::off_policy_runner::SequentialBatchSpecification<typename RS::SPEC, L, BATCH, PARAMS, true>;
+        constexpr TI OBS = ENV::Observation::DIM, D = RUNNER::REPLAY_BUFFER_TYPE::DATA_COLS, W = OBS + 4, P = L + 1;
+        DEVICE device;
+        auto* runner_ptr = new RUNNER(); RUNNER& runner = *runner_ptr;
+        rlt::malloc(device, runner);
+        rlt::init(device, runner);
+        rlt::rl::components::off_policy_runner::SequentialBatch<BATCH_SPEC> batch;
+        rlt::malloc(device, batch);
+        rlt::set_all(device, batch.observations_actions_base, 0); rlt::set_all(device, batch.rewards, 0); rlt::set_all(device, batch.terminated, false);
+        for(TI e = 0; e < N; e++){
+            auto& rb = rlt::get(runner.replay_buffers, 0, e);
+            for(TI r = 0; r < CAPACITY; r++){
+                for(TI c = 0; c < D; c++) rlt::set(rb.data, r, c, replay[(e * CAPACITY + r) * D + c]);
+                rlt::set(device, rb.episode_start, (TI)episode_start[e * CAPACITY + r], r);
+            }
+            rb.position = position_in[e]; rb.full = full_in[e] != 0;
+        }
+        for(TI b = 0; b < BATCH; b++){
+            RNG rng; rng.state = rng_states[b];
+            TI env_i = rlt::random::uniform_int_distribution(typename DEVICE::SPEC::RANDOM(), (TI)0, (TI)(N - 1), rng);
+            auto& rb = rlt::get(runner.replay_buffers, 0, env_i);
+            rlt::gather_batch_step<false>(device, runner, rb, batch, b, rng);
+            rng_states[b] = rng.state;
+        }
+        for(TI s = 0; s < P; s++) for(TI b = 0; b < BATCH; b++){
+            for(TI c = 0; c < W; c++) observations_actions[(s * BATCH + b) * W + c] = rlt::get(device, batch.observations_actions_base, s, b, c);
+            next_reset_base[s * BATCH + b] = rlt::get(device, batch.next_reset_base, s, b, 0) ? 1 : 0;
+            next_final_step_mask_base[s * BATCH + b] = rlt::get(device, batch.next_final_step_mask_base, s, b, 0) ? 1 : 0;
+        }
+        for(TI s = 0; s < L; s++) for(TI b = 0; b < BATCH; b++){
+            rewards[s * BATCH + b] = rlt::get(device, batch.rewards, s, b, 0);
+            terminated[s * BATCH + b] = rlt::get(device, batch.terminated, s, b, 0) ? 1 : 0;
+            reset[s * BATCH + b] = rlt::get(device, batch.reset, s, b, 0) ? 1 : 0;
+            final_step_mask[s * BATCH + b] = rlt::get(device, batch.final_step_mask, s, b, 0) ? 1 : 0;
+        }
+        rlt::free(device, batch); rlt::free(device, runner);
+        delete runner_ptr;
+    }
+    // sampling from the initial state needs CAPACITY >= MAX_EPISODE_LENGTH = ENVIRONMENT::EPISODE_STEP_LIMIT (operations_generic.h:258; 500 here): rings of 640 rows
+    struct SeqConfig{ int L, first, initial, random, enable, prob_percent, capacity; };
+    static const SeqConfig SEQ_CONFIGS[] = {{8, 1, 0, 0, 1, 50, 48}, {8, 1, 1, 1, 1, 50, 640}, {8, 0, 0, 1, 0, 50, 48}, {24, 1, 1, 1, 1, 10, 640}, {2, 1, 1, 1, 1, 50, 640}, {8, 0, 1, 0, 1, 50, 640}};
+}
+extern "C" {
+int ref_gather_batch_sequential_configs(){ return (int)(sizeof(ref_opr::SEQ_CONFIGS) / sizeof(ref_opr::SEQ_CONFIGS[0])); }
+void ref_gather_batch_sequential_config(int config, int* L, int* first, int* initial, int* random, int* enable, float* probability, int* capacity){
+    const auto& c = ref_opr::SEQ_CONFIGS[config];
+    *capacity = c.capacity;
+    *L = c.L; *first = c.first; *initial = c.initial; *random = c.random; *enable = c.enable; *probability = (float)((T)c.prob_percent / (T)100);
+}
+int ref_gather_batch_sequential(int config, const float* replay, const int* episode_start, const int* position, const unsigned char* full, uint64_t* rng_states,
+                                float* observations_actions, float* rewards, unsigned char* terminated, unsigned char* reset, unsigned char* next_reset_base,
+                                unsigned char* final_step_mask, unsigned char* next_final_step_mask_base){
+#define SEQ_ARGS replay, episode_start, position, full, rng_states, observations_actions, rewards, terminated, reset, next_reset_base, final_step_mask, next_final_step_mask_base
+    using namespace ref_opr;
+    switch(config){
+        case 0: gather_sequential<8, SeqParameters<true, false, false, true, 50>, 48>(SEQ_ARGS); return 0;
+        case 1: gather_sequential<8, SeqParameters<true, true, true, true, 50>, 640>(SEQ_ARGS); return 0;
+        case 2: gather_sequential<8, SeqParameters<false, false, true, false, 50>, 48>(SEQ_ARGS); return 0;
+        case 3: gather_sequential<24, SeqParameters<true, true, true, true, 10>, 640>(SEQ_ARGS); return 0;
+        case 4: gather_sequential<2, SeqParameters<true, true, true, true, 50>, 640>(SEQ_ARGS); return 0;
+        case 5: gather_sequential<8, SeqParameters<false, true, false, true, 50>, 640>(SEQ_ARGS); return 0;
+    }
+#undef SEQ_ARGS
+    return 1;
+}
 }
 extern "C" {
 int ref_gather_batch_size(){ return ref_opr::BATCH; }

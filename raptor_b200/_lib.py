@@ -42,6 +42,11 @@ class Batch(ctypes.Structure):
                 ("final_step_mask", vp), ("next_final_step_mask", vp), ("env_index", vp), ("sample_index", vp)]
 
 
+class BatchParameters(ctypes.Structure):
+    _fields_ = [("sequence_length", c_i32), ("include_first_step_in_targets", c_i32), ("always_sample_from_initial_state", c_i32), ("random_seq_length", c_i32),
+                ("enable_nominal_sequence_length_probability", c_i32), ("nominal_sequence_length_probability", ctypes.c_float)]
+
+
 class Status(ctypes.Structure):
     _fields_ = [("n_envs", c_i64), ("n_nonfinite", c_i64), ("n_terminated", c_i64), ("has_episodes", c_i32), ("reserved", c_i32),
                 ("returns_mean", ctypes.c_double), ("returns_std", ctypes.c_double), ("episode_length_mean", ctypes.c_double), ("episode_length_std", ctypes.c_double),
@@ -121,6 +126,7 @@ SYMBOLS = {
     "b200l2f_checkpoint_policy": (c_int, [vp, ctypes.c_char_p, ctypes.POINTER(PolicyDesc), vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "b200l2f_off_policy_steps": (c_int, [vp, c_i32, c_i32, c_i32, ctypes.POINTER(ReplayBuffers)]),
     "b200l2f_gather_batch": (c_int, [vp, ctypes.POINTER(ReplayBuffers), c_i32, c_i32, c_i32, vp, ctypes.POINTER(Batch)]),
+    "b200l2f_gather_batch_sequential": (c_int, [vp, ctypes.POINTER(ReplayBuffers), ctypes.POINTER(BatchParameters), c_i32, c_i32, c_i32, vp, ctypes.POINTER(Batch)]),
     "b200l2f_runner_get_state": (c_int, [vp, vp, vp, vp, c_int]),
     "b200l2f_runner_set_state": (c_int, [vp, vp, vp, vp, c_int]),
     "b200l2f_teachers_load": (c_int, [vp, c_i32, c_i32, vp, vp, c_i32]),

@@ -29,7 +29,7 @@ SOURCES = {
     "rollout_mlp.cu": [],
     "rollout_mlp_ts.cu": TC + ["mlp_tc.cuh"],
     "collect.cu": [],
-    "collect_ts.cu": TC + ["mlp_tc.cuh"],
+    "collect_ts.cu": TC + ["mlp_tc.cuh", "collect_lag.cuh"],
     "collect_ts_default.cu": TC + ["mlp_tc.cuh"],
     "learner.cu": TC + ["mlp_tc.cuh", "learner.cuh"],
     "dagger.cu": TC + ["mlp_tc.cuh", "dagger.cuh"],

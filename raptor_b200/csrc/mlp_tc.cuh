@@ -78,6 +78,7 @@ struct TsCtx {
     uint64_t* bar_mma;
     uint32_t phase;
     int tid;
+    const volatile int* probe; int probe_value;   // see ts_run<.., PROBE>
     uint64_t desc_n64, desc_n16;   // B descriptors of the image base for N = 64 / N = 16 tiles: every other descriptor is a compile-time offset away
 };
 __device__ __forceinline__ void ts_put8(uint32_t t_hi, uint32_t t_lo, const float* v){
@@ -101,11 +102,15 @@ __device__ __forceinline__ void ts_issue_gemm(const TsCtx& c, uint32_t dcol, uin
     }
 }
 // the A operand of the next GEMM is complete in TMEM: hand it to the tensor core, wait for the accumulator.  Called by ALL threads of the CTA.
-template <class F>
+// NAMED_BAR: the CTA holds more warps than the four that own the tile (k_collect_lag's reset warp): those four meet on barrier 1
+// PROBE: read *c.probe right behind the barrier (a CTA-uniform value: every warp reads it between the same two barriers)
+template <bool NAMED_BAR = false, bool PROBE = false, class F>
 __device__ __forceinline__ void ts_run(TsCtx& c, F&& issue){
     tc::tmem_st_wait();
     tc::tc_fence_before();
-    __syncthreads();
+    if constexpr(NAMED_BAR) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else __syncthreads();
+    if constexpr(PROBE) c.probe_value = *c.probe;
     if((c.tid >> 5) == 0 && tc::elect_one()){   // one lane of warp 0 (elect.sync): straight-line predicated MMA issue
         tc::tc_fence_after();
         issue();
@@ -117,7 +122,7 @@ __device__ __forceinline__ void ts_run(TsCtx& c, F&& issue){
 
 // obs_at(k): RAW observation column k of this thread's environment (k is a compile-time constant after unrolling: registers or shared memory)
 // -> out[OUT] (pre-head outputs).  Called by all 128 threads (inactive lanes compute garbage rows).
-template <int IN, int OUT, class OBS>
+template <int IN, int OUT, bool NAMED_BAR = false, class OBS>
 __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, float* __restrict__ out){
     using I = MlpTcImage<IN, OUT>;
     constexpr int HD = MLP_HD, K1 = I::K1;
@@ -141,7 +146,7 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         }
         ts_put8(c.tmem_lane + A1_HI + 8 * g, c.tmem_lane + A1_LO + 8 * g, x);
     }
-    ts_run(c, [&](){ ts_issue_gemm(c, D1, A1_HI, A1_LO, K1 / 8, I::B1_HI, I::B1_LO, HD, IDESC64); });
+    ts_run<NAMED_BAR, NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D1, A1_HI, A1_LO, K1 / 8, I::B1_HI, I::B1_LO, HD, IDESC64); });
 #pragma unroll
     for(int g = 0; g < HD / 32; g++){
         float v[32];
@@ -153,7 +158,7 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
 #pragma unroll
         for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A2_HI + 32 * g + 8 * q, c.tmem_lane + A2_LO + 32 * g + 8 * q, v + 8 * q);
     }
-    ts_run(c, [&](){ ts_issue_gemm(c, D2, A2_HI, A2_LO, HD / 8, I::B2_HI, I::B2_LO, HD, IDESC64); });
+    ts_run<NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D2, A2_HI, A2_LO, HD / 8, I::B2_HI, I::B2_LO, HD, IDESC64); });
 #pragma unroll
     for(int g = 0; g < HD / 32; g++){
         float v[32];
@@ -169,7 +174,7 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
 #pragma unroll
         for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A3_HI + 32 * g + 8 * q, c.tmem_lane + A3_LO + 32 * g + 8 * q, v + 8 * q);
     }
-    ts_run(c, [&](){ ts_issue_gemm(c, D3, A3_HI, A3_LO, HD / 8, I::B3_HI, I::B3_LO, I::N3, IDESC16); });
+    ts_run<NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D3, A3_HI, A3_LO, HD / 8, I::B3_HI, I::B3_LO, I::N3, IDESC16); });
     {
         float v[16];
         tc::tmem_ld16(c.tmem_lane + D3, v);
@@ -178,9 +183,9 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         for(int j = 0; j < OUT; j++) out[j] = v[j] + c.sm_b[I::BIAS3 + j];
     }
 }
-template <int IN, int OUT>
+template <int IN, int OUT, bool NAMED_BAR = false>
 __device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict__ obs, float* __restrict__ out){   // observation in registers
-    mlp_forward_ts_from<IN, OUT>(c, [&](int k){ return obs[k]; }, out);
+    mlp_forward_ts_from<IN, OUT, NAMED_BAR>(c, [&](int k){ return obs[k]; }, out);
 }
 
 // full observation of an H = 1 spec in registers (same values and RNG order as observe_to_scratch)

@@ -137,8 +137,9 @@ int b200l2f_off_policy_steps(b200l2f_handle* h, int32_t n_steps, int32_t episode
     return B200L2F_OK;
 }
 
-int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, int32_t max_episode_length, int32_t env_begin, int32_t env_count, uint64_t* rng_states,
-                         const b200l2f_batch* out){
+// bp == nullptr: SEQUENCE_LENGTH 1 with the MLP SAC parameters (k_gather_batch); otherwise the general walk (k_gather_batch_sequential)
+static int gather_common(b200l2f_handle* h, const b200l2f_replay_buffers* rb, const b200l2f_batch_parameters* bp, int32_t max_episode_length, int32_t env_begin, int32_t env_count,
+                         uint64_t* rng_states, const b200l2f_batch* out){
     if(!h) return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch: null handle");
     CU(cudaSetDevice(h->cfg.device));
     if(!rb || !out || !rng_states || !rb->data || !rb->position || !rb->full || rb->capacity < 1 || out->batch_size < 0 || !out->observations_actions || !out->rewards || !out->terminated)
@@ -146,6 +147,13 @@ int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, in
     if(rb->memspace != out->memspace) return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch: replay buffers and batch must live in the same memory space");
     if(env_begin < 0 || env_count < 1 || env_begin + env_count > h->n) return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch: environment range outside the handle");
     const int B = out->batch_size, OBS = h->obs_dim, D = 2 * OBS + 7, W = OBS + 4;
+    const int L = bp ? bp->sequence_length : 1, P = L + 1;
+    if(bp){
+        if(L < 1 || !rb->episode_start || !out->reset || !out->next_reset || !out->final_step_mask || !out->next_final_step_mask)
+            return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch_sequential: sequence_length >= 1, episode_start and all four masks are required");
+        if(bp->always_sample_from_initial_state && rb->capacity < max_episode_length)
+            return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch_sequential: sampling from the initial state needs capacity >= max_episode_length");   // operations_generic.h:258
+    }
     if(B == 0) return B200L2F_OK;
     const size_t n = (size_t)h->n;
     const bool host = rb->memspace == B200L2F_HOST;
@@ -154,9 +162,10 @@ int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, in
     Part parts[12] = {
         {rb->data, nullptr, sizeof(float) * n * rb->capacity * D, nullptr}, {rb->position, nullptr, sizeof(int32_t) * n, nullptr}, {rb->full, nullptr, n, nullptr},
         {rng_states, rng_states, sizeof(uint64_t) * B, nullptr},
-        {nullptr, out->observations_actions, sizeof(float) * 2 * B * W, nullptr}, {nullptr, out->rewards, sizeof(float) * B, nullptr}, {nullptr, out->terminated, (size_t)B, nullptr},
-        {nullptr, out->reset, (size_t)B, nullptr}, {nullptr, out->next_reset, (size_t)2 * B, nullptr}, {nullptr, out->final_step_mask, (size_t)B, nullptr},
-        {nullptr, out->next_final_step_mask, (size_t)2 * B, nullptr}, {nullptr, nullptr, 0, nullptr}};
+        {nullptr, out->observations_actions, sizeof(float) * P * B * W, nullptr}, {nullptr, out->rewards, sizeof(float) * L * B, nullptr}, {nullptr, out->terminated, (size_t)L * B, nullptr},
+        {nullptr, out->reset, (size_t)L * B, nullptr}, {nullptr, out->next_reset, (size_t)P * B, nullptr}, {nullptr, out->final_step_mask, (size_t)L * B, nullptr},
+        {nullptr, out->next_final_step_mask, (size_t)P * B, nullptr},
+        {bp ? rb->episode_start : nullptr, nullptr, bp ? sizeof(int32_t) * n * rb->capacity : 0, nullptr}};
     Part extra[2] = {{nullptr, out->env_index, sizeof(int32_t) * B, nullptr}, {nullptr, out->sample_index, sizeof(int32_t) * B, nullptr}};
     std::vector<Part*> all;
     for(auto& p : parts) all.push_back(&p);
@@ -179,7 +188,13 @@ int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, in
     a.rng = (uint64_t*)parts[3].dev; a.observations_actions = (float*)parts[4].dev; a.rewards = (float*)parts[5].dev; a.terminated = (uint8_t*)parts[6].dev;
     a.reset = (uint8_t*)parts[7].dev; a.next_reset = (uint8_t*)parts[8].dev; a.final_step_mask = (uint8_t*)parts[9].dev; a.next_final_step_mask = (uint8_t*)parts[10].dev;
     a.env_index = (int*)extra[0].dev; a.sample_index = (int*)extra[1].dev; a.error_flag = h->d_flags;
-    k_gather_batch<<<grid_for(B * 32, 256), 256, 0, h->stream>>>(a);
+    if(bp){
+        GatherSeqArgs q{};
+        q.g = a; q.episode_start = (const int*)parts[11].dev; q.L = L; q.include_first = bp->include_first_step_in_targets; q.always_initial = bp->always_sample_from_initial_state;
+        q.random_len = bp->random_seq_length; q.enable_nominal = bp->enable_nominal_sequence_length_probability; q.nominal_probability = bp->nominal_sequence_length_probability;
+        k_gather_batch_sequential<<<grid_for(B * 32, 256), 256, 0, h->stream>>>(q);
+    }
+    else k_gather_batch<<<grid_for(B * 32, 256), 256, 0, h->stream>>>(a);
     h->launches++;
     cudaError_t le = cudaGetLastError();
     if(le != cudaSuccess) return fail(h, B200L2F_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
@@ -194,6 +209,16 @@ int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, in
     CU(cudaStreamSynchronize(h->stream));
     if(flag) return fail(h, B200L2F_ERR_STATE, "gather_batch: Replay buffer requires at least one element");
     return B200L2F_OK;
+}
+
+int b200l2f_gather_batch(b200l2f_handle* h, const b200l2f_replay_buffers* rb, int32_t max_episode_length, int32_t env_begin, int32_t env_count, uint64_t* rng_states,
+                         const b200l2f_batch* out){
+    return gather_common(h, rb, nullptr, max_episode_length, env_begin, env_count, rng_states, out);
+}
+int b200l2f_gather_batch_sequential(b200l2f_handle* h, const b200l2f_replay_buffers* rb, const b200l2f_batch_parameters* parameters, int32_t max_episode_length, int32_t env_begin,
+                                    int32_t env_count, uint64_t* rng_states, const b200l2f_batch* out){
+    if(!parameters) return fail(h, B200L2F_ERR_ARGUMENT, "gather_batch_sequential: null parameters");
+    return gather_common(h, rb, parameters, max_episode_length, env_begin, env_count, rng_states, out);
 }
 
 }  // extern "C"

@@ -122,6 +122,108 @@ __global__ void __launch_bounds__(256) k_gather_batch(const GatherArgs a){
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// gather_batch for any SEQUENCE_LENGTH (recurrent SAC; the batch parameters of off_policy_runner.h:78-85 as run-time values): gather_batch_step
+// (operations_generic.h:240-420) per batch sample.  One warp per sample: lane 0 walks the padded sequence -- ring indices, the random sequence lengths
+// (uniform_real in double = state * 2^-64, uniform_int = next(state) % range), the reset / final-step masks -- and broadcasts, per step, which ring
+// row to copy and whether its next-observation opens the following (padding) step; the warp copies the rows.  rewards / terminated of padding steps,
+// which the reference leaves unwritten, are zero.
+// ---------------------------------------------------------------------------------------------------------------
+struct GatherSeqArgs {
+    GatherArgs g;                 // rings, rng, outputs (the masks are mandatory here), environment range, batch
+    const int* episode_start;     // [n][capacity]
+    int L, include_first, always_initial, random_len, enable_nominal;
+    float nominal_probability;
+};
+__device__ __forceinline__ double rng_unit_double(uint64_t& s){ rng_next(s); return __ull2double_rn(s) * 5.42101086242752217e-20; }   // state / (double)MAX_INDEX, exact scaling by 2^-64
+__global__ void __launch_bounds__(256) k_gather_batch_sequential(const GatherSeqArgs q){
+    const GatherArgs& a = q.g;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(b >= a.batch) return;
+    const int OBS = a.obs_dim, D = 2 * OBS + 7, W = OBS + 4, L = q.L, P = L + 1, B = a.batch;
+    // lane 0's walk state
+    uint64_t s = 0;
+    int env = 0, pos = 0, sample_index = 0, first_sample = -1;
+    unsigned eligible = 0, cur_len = (unsigned)L, cur_step = 0;
+    bool is_full = false, prev_trunc = false, prev_pad = true, ok = true;
+    auto draw_length = [&]() -> unsigned {   // :265-274, :361-370
+        if(q.enable_nominal && rng_unit_double(s) < (double)q.nominal_probability) return (unsigned)L;
+        if(L > 1){ rng_next(s); return 1u + (unsigned)(s % (uint64_t)(L - 1)); }
+        return (unsigned)L;
+    };
+    if(lane == 0){
+        s = a.rng[b];
+        rng_next(s);
+        env = a.env_begin + (int)(s % (uint64_t)a.env_count);
+        is_full = a.full[env] != 0; pos = a.position[env];
+        const int el = is_full ? (q.always_initial ? a.capacity - a.max_episode_length : a.capacity) : pos;
+        if(el < 1){ atomicExch(a.error_flag, 1); ok = false; }      // "Replay buffer requires at least one element" (:252-256)
+        eligible = (unsigned)max(el, 1);
+        if(q.random_len) cur_len = draw_length();
+        for(int t = 0; t < L; t++){ a.final_step_mask[(size_t)t * B + b] = 0; a.reset[(size_t)t * B + b] = 0; a.rewards[(size_t)t * B + b] = 0.0f; a.terminated[(size_t)t * B + b] = 0; }
+        for(int t = 0; t < P; t++){ a.next_final_step_mask[(size_t)t * B + b] = 0; a.next_reset[(size_t)t * B + b] = 0; }
+        a.reset[b] = 1; a.next_reset[b] = 1; a.next_reset[(size_t)(q.include_first ? 0 : 1) * B + b] = 1;   // :286-288 (the `next_reset` view starts at row 0 or 1)
+    }
+    ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if(!ok) return;
+    const float* ring = a.replay + (size_t)env * a.capacity * D;
+    for(int seq = 0; seq < P; seq++){
+        int row_i = -1; bool truncated = false;                      // row_i < 0: padding step, nothing to copy
+        if(lane == 0){
+            if(prev_trunc){                                          // :290-299
+                prev_trunc = false; prev_pad = true;
+                a.next_final_step_mask[(size_t)seq * B + b] = 1;
+                if(seq < P - 1) a.reset[(size_t)seq * B + b] = 1;
+            }
+            else{
+                if(prev_pad){                                        // a new sequence starts here (:300-321)
+                    if(seq < P - 1) a.reset[(size_t)seq * B + b] = 1;
+                    a.next_reset[(size_t)seq * B + b] = 1;
+                    rng_next(s);
+                    const unsigned offset = (unsigned)(s % (uint64_t)eligible);
+                    sample_index = is_full ? (int)(((uint64_t)pos + (uint64_t)a.max_episode_length + offset) % (uint64_t)a.capacity) : (int)offset;
+                    if(q.always_initial) sample_index = q.episode_start[(size_t)env * a.capacity + sample_index];
+                    if(first_sample < 0) first_sample = sample_index;
+                }
+                row_i = sample_index;
+                const float* row = ring + (size_t)row_i * D;
+                if(seq < P - 1){ a.rewards[(size_t)seq * B + b] = row[OBS + 4]; a.terminated[(size_t)seq * B + b] = row[2 * OBS + 5] != 0.0f ? 1 : 0; }
+                truncated = row[2 * OBS + 6] != 0.0f;                // :352-360
+                int next = sample_index + 1;
+                if(is_full) next = next % a.capacity;
+                if(next == pos) truncated = true;
+                if(seq == P - 2) truncated = true;
+                if(q.random_len){                                    // :361-388
+                    if(cur_step == cur_len - 1){
+                        truncated = true;
+                        cur_len = L > 1 ? draw_length() : (unsigned)L;
+                    }
+                    cur_step = truncated ? 0 : cur_step + 1;
+                }
+                if(truncated && seq < P - 1) a.final_step_mask[(size_t)seq * B + b] = 1;
+                sample_index = next;
+                prev_pad = false; prev_trunc = truncated;
+            }
+        }
+        row_i = __shfl_sync(0xffffffffu, row_i, 0);
+        truncated = __shfl_sync(0xffffffffu, (int)truncated, 0) != 0;
+        if(row_i < 0) continue;
+        const float* row = ring + (size_t)row_i * D;
+        float* oa = a.observations_actions + ((size_t)seq * B + b) * W;
+        const bool open_next = truncated && seq < P - 1;             // next_obs | action 0 into the following step (:393-417)
+        for(int i = lane; i < W; i += 32){
+            oa[i] = row[i];
+            if(open_next) oa[(size_t)B * W + i] = i < OBS ? row[OBS + 5 + i] : 0.0f;
+        }
+    }
+    if(lane == 0){
+        a.rng[b] = s;
+        if(a.env_index) a.env_index[b] = env;
+        if(a.sample_index) a.sample_index[b] = first_sample;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // actor on fp32 CUDA cores (B200L2F_GEMM_FP32_CUDA_CORES, B200L2F_FLAG_ACCURATE_MATH): structure of k_collect (mlp.cuh)
 // ---------------------------------------------------------------------------------------------------------------
 template <class Spec, bool DR>

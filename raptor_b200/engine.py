@@ -399,9 +399,13 @@ class VectorEnvironment:
         self._check(self._lib.b200l2f_off_policy_steps(self._h, n_steps, episode_step_limit, int(sample_parameters), ctypes.byref(rb)))
         return replay
 
-    def gather_batch(self, replay, rng_states, max_episode_length=500, env_begin=0, env_count=None, out=None):
-        """SEQUENCE_LENGTH-1 batch (rl_tools::gather_batch) from the replay rings: rng_states [B] uint64 (numpy) / int64 (torch CUDA), advanced in place;
-        returns dict(observations_actions [2, B, OBS+4], rewards, terminated, reset, next_reset, final_step_mask, next_final_step_mask, env_index, sample_index)"""
+    def gather_batch(self, replay, rng_states, max_episode_length=500, env_begin=0, env_count=None, out=None, sequence_length=None, include_first_step_in_targets=None,
+                     always_sample_from_initial_state=None, random_seq_length=None, enable_nominal_sequence_length_probability=True, nominal_sequence_length_probability=0.5):
+        """batch (rl_tools::gather_batch) from the replay rings: rng_states [B] uint64 (numpy) / int64 (torch CUDA), advanced in place.
+        sequence_length None: the SEQUENCE_LENGTH-1 MLP SAC configuration; returns dict(observations_actions [2, B, OBS+4], rewards [B], terminated, reset, next_reset [2, B],
+        final_step_mask, next_final_step_mask [2, B], env_index, sample_index).
+        sequence_length L: the general walk (recurrent SAC); the flags default to the reference's for the given length (off_policy_runner.h:78-85: all three = L > 1);
+        tensors in the SequentialBatch shapes: observations_actions [L+1, B, OBS+4], rewards / terminated / reset / final_step_mask [L, B], next_* [L+1, B]."""
         n, obs = self.N_ENVIRONMENTS, self.OBSERVATION_DIM
         capacity = replay["data"].shape[1]
         pd, ms, _ = self._arg(replay["data"], np.float32, (n, capacity, 2 * obs + 7), "replay.data")
@@ -411,8 +415,11 @@ class VectorEnvironment:
         pr, m3, _ = self._arg(rng_states, np.uint64, (B,), "rng_states")
         if not (ms == m1 == m2 == m3):
             raise ValueError("gather_batch: rings and rng_states must live in the same memory space")
-        shapes = dict(observations_actions=((2, B, obs + 4), np.float32), rewards=((B,), np.float32), terminated=((B,), np.uint8), reset=((B,), np.uint8),
-                      next_reset=((2, B), np.uint8), final_step_mask=((B,), np.uint8), next_final_step_mask=((2, B), np.uint8), env_index=((B,), np.int32),
+        sequential = sequence_length is not None
+        Lq = int(sequence_length) if sequential else 1
+        cur = (Lq, B) if sequential else (B,)
+        shapes = dict(observations_actions=((Lq + 1, B, obs + 4), np.float32), rewards=(cur, np.float32), terminated=(cur, np.uint8), reset=(cur, np.uint8),
+                      next_reset=((Lq + 1, B), np.uint8), final_step_mask=(cur, np.uint8), next_final_step_mask=((Lq + 1, B), np.uint8), env_index=((B,), np.int32),
                       sample_index=((B,), np.int32))
         if out is None:
             if ms == L.HOST:
@@ -427,9 +434,21 @@ class VectorEnvironment:
             if out.get(k) is not None and m != ms:
                 raise ValueError("gather_batch: batch buffers must live in the memory space of the rings")
             ptrs.append(p)
-        rb = L.ReplayBuffers(ms, capacity, pd, None, pp, pf, None)
         batch = L.Batch(ms, B, *ptrs)
-        self._check(self._lib.b200l2f_gather_batch(self._h, ctypes.byref(rb), max_episode_length, env_begin, n if env_count is None else env_count, pr, ctypes.byref(batch)))
+        count = n if env_count is None else env_count
+        if not sequential:
+            rb = L.ReplayBuffers(ms, capacity, pd, None, pp, pf, None)
+            self._check(self._lib.b200l2f_gather_batch(self._h, ctypes.byref(rb), max_episode_length, env_begin, count, pr, ctypes.byref(batch)))
+            return out
+        pe, m4, _ = self._arg(replay["episode_start"], np.int32, (n, capacity), "replay.episode_start")
+        if m4 != ms:
+            raise ValueError("gather_batch: rings and episode_start must live in the same memory space")
+        dflt = Lq > 1
+        flag = lambda v: int(dflt if v is None else bool(v))  # noqa: E731
+        bp = L.BatchParameters(Lq, flag(include_first_step_in_targets), flag(always_sample_from_initial_state), flag(random_seq_length),
+                               int(bool(enable_nominal_sequence_length_probability)), float(nominal_sequence_length_probability))
+        rb = L.ReplayBuffers(ms, capacity, pd, pe, pp, pf, None)
+        self._check(self._lib.b200l2f_gather_batch_sequential(self._h, ctypes.byref(rb), ctypes.byref(bp), max_episode_length, env_begin, count, pr, ctypes.byref(batch)))
         return out
 
     def get_runner_state(self):

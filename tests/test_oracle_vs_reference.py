@@ -291,3 +291,34 @@ def test_gather_batch(port, ref):
             assert np.array_equal(got[k], v), (steps, k)
         assert len(set(got["env_index"].tolist())) > n // 2 and len(set(got["sample_index"].tolist())) > 10
     assert runner["full"].all()
+
+
+def test_gather_batch_sequential(port, ref):
+    """recurrent-SAC batches (SEQUENCE_LENGTH > 1): the restatement against the reference's own gather_batch_step for every compiled parameter set --
+    fixed / random sequence lengths, with and without the nominal-length draw, from any row / from the episode's first row, next-views at offset 0 / 1 --
+    on rings that are partially filled and on wrapped ones.  Bit-exact, RNG streams included."""
+    n = ref.off_policy_sizes()[0]
+    obs = 26
+    Bsz = ref.lib.ref_gather_batch_size()
+    mel = ref.lib.ref_gather_batch_max_episode_length()
+    configs = ref.gather_batch_sequential_configs()
+    assert len(configs) >= 6 and {c["sequence_length"] for c in configs} >= {2, 8, 24}
+    for cfg in configs:
+        cap = cfg["capacity"]
+        for case, fill in enumerate(([cap * 3 // 4] * n, [cap + 7 * e + 3 for e in range(n)])):   # not full (position > MAX_EPISODE_LENGTH where needed) / wrapped
+            rs = np.random.RandomState(100 * cfg["config"] + case)
+            runner = B.synthetic_replay_rings(rs, n, cap, obs, fill=fill)
+            assert bool(runner["full"].all()) == (case == 1)
+            r_a = port.rng_states(4000 + cfg["config"], Bsz, warmup=3)
+            r_b = r_a.copy()
+            kw = {k: v for k, v in cfg.items() if k not in ("config", "capacity", "sequence_length")}
+            got = port.gather_batch_sequential(runner, r_a, mel, cfg["sequence_length"], **kw)
+            want = ref.gather_batch_sequential(cfg["config"], runner, r_b)
+            assert np.array_equal(r_a, r_b), cfg
+            for k, v in want.items():
+                assert np.array_equal(got[k], v), (cfg, case, k)
+            # the structure the learner relies on: every sample starts with a reset, the last real step of every sequence is a final step
+            assert got["reset"][0].all() and got["next_reset"][0].all()
+            assert got["final_step_mask"].sum() >= Bsz
+            if cfg["random_seq_length"]:
+                assert got["final_step_mask"][: cfg["sequence_length"] - 1].sum() > 0   # sequences really end early

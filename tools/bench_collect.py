@@ -18,7 +18,9 @@ def main():
     rs = np.random.RandomState(0)
     mlp_blob(rs, 26, 8, False, False)   # same random stream position as bench.py / bench_configs.py
     env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR, stream=stream.cuda_stream)
-    row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32); env.set_environment_parameters(row)
+    row = env.get_environment_parameters(); row[124:139] = np.array(DR, np.float32)
+    if "--no-term" in sys.argv: row[114] = 0.0   # termination off: only the forced reset at t = 0 (upper bound with the reset path out of the way)
+    env.set_environment_parameters(row)
     env.initialize_rng(4, warmup=16); env.initial_parameters(); env.initial_state()
     env.load_policy(mlp_blob(rs, 22, 4, True, True), arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=rb.GEMM_TCGEN05_3XTF32)
     data = torch.zeros(((T + 1) * n, 37), dtype=torch.float32, device=dev)
