@@ -280,6 +280,30 @@ def run_other_configs(rb, torch, dev, stream, flush, rank, world, use_dist):
     out["config4"] = {"workload": "BASELINE configs[3]: %d envs/GPU x %d-step PPO rollout collection, PPO actor 22-64-64-4 (standardize, learned log_std), DR resets, dataset [(T+1)N, 37] in HBM" % (n, T),
                       "value": n * world * T / ms * 1e3, "unit": "env-steps/s", "ms_per_launch": ms, "kernel": k, "dataset_bytes_written": written, "roofline": rl,
                       "mean_reward": float(data[: T * n, 31].mean().item()), "truncated_fraction": float(data[: T * n, 33].mean().item())}
+    if use_dist and world > 1:
+        # SURVEY 8(e)'s one optional exchange: config 4 sharded over the job (262 144 / world environments per rank), every rank ends with the whole dataset.
+        # b200l2f_allgather_trajectories (NCCL over NVLink, enqueued on the engine's stream behind the kernel that wrote the slab); never on the rollout path.
+        try:
+            import ctypes
+            from raptor_b200.distributed import NcclCommunicator
+            comm = NcclCommunicator()
+            nl = n // world
+            slab = data.view(T + 1, n, 37)[:, :nl].contiguous()
+            gathered = torch.empty((world, T + 1, nl, 37), dtype=torch.float32, device=dev)
+            ranks = ctypes.c_int32(0)
+
+            def gather():
+                env._check(env._lib.b200l2f_allgather_trajectories(env._h, comm.handle, slab.data_ptr(), gathered.data_ptr(), slab.numel(), ctypes.byref(ranks)))
+            ms_g = timed(gather, lambda: None)
+            ok = bool(torch.equal(gathered[rank], slab)) and ranks.value == world
+            out["config4"]["allgather"] = {"what": "all-gather of the config-4 dataset sharded over the job: %d envs/rank x %d rows x 37 floats -> the whole dataset on every rank" % (nl, T + 1),
+                                           "ms": ms_g, "bytes_in_per_rank": slab.numel() * 4, "bytes_out_per_rank": gathered.numel() * 4,
+                                           "algbw_gbs": gathered.numel() * 4 / ms_g / 1e6, "busbw_gbs": gathered.numel() * 4 * (world - 1) / world / ms_g / 1e6,
+                                           "own_shard_intact": ok, "entry": "b200l2f_allgather_trajectories (NCCL, %d ranks)" % ranks.value}
+            comm.destroy()
+            del slab, gathered
+        except Exception as e:   # the exchange is optional: never lose the bench line over it
+            out["config4"]["allgather"] = {"error": repr(e)[:200]}
     del env, data
     # ---- config 5: 1 048 576 envs per GPU, Raptor checkpoint (weak scaling across the ranks of this job)
     n, T = 1048576, 1000

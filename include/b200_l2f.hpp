@@ -314,11 +314,23 @@ namespace off_policy_runner {
         std::vector<uint8_t> full = std::vector<uint8_t>(N, 0);
         b200l2f_replay_buffers buffers(){ return b200l2f_replay_buffers{B200L2F_HOST, (int32_t)T_CAPACITY, data.data(), episode_start.data(), position.data(), full.data(), current_episode_start.data()}; }
     };
-    template <typename SPEC, size_t T_BATCH_SIZE>
-    struct SequentialBatch {          // SEQUENCE_LENGTH 1 (off_policy_runner.h:96-141)
-        static constexpr size_t BATCH_SIZE = T_BATCH_SIZE, DIM = SPEC::OBSERVATION_DIM + 4;
-        std::vector<float> observations_actions = std::vector<float>(2 * T_BATCH_SIZE * DIM, 0.0f), rewards = std::vector<float>(T_BATCH_SIZE, 0.0f);
-        std::vector<uint8_t> terminated = std::vector<uint8_t>(T_BATCH_SIZE, 0);
+    // batch sampling parameters: the reference's SequentialBatchParameters (off_policy_runner.h:78-85), defaults as there
+    template <size_t T_SEQUENCE_LENGTH>
+    struct SequentialBatchParameters {
+        static constexpr bool INCLUDE_FIRST_STEP_IN_TARGETS = T_SEQUENCE_LENGTH > 1;
+        static constexpr bool ALWAYS_SAMPLE_FROM_INITIAL_STATE = T_SEQUENCE_LENGTH > 1;
+        static constexpr bool RANDOM_SEQ_LENGTH = T_SEQUENCE_LENGTH > 1;
+        static constexpr bool ENABLE_NOMINAL_SEQUENCE_LENGTH_PROBABILITY = true;
+        static constexpr float NOMINAL_SEQUENCE_LENGTH_PROBABILITY = 0.5f;
+    };
+    template <typename SPEC, size_t T_BATCH_SIZE, size_t T_SEQUENCE_LENGTH = 1, typename T_PARAMETERS = SequentialBatchParameters<T_SEQUENCE_LENGTH>>
+    struct SequentialBatch {          // off_policy_runner.h:96-141; [PADDED_SEQUENCE_LENGTH] tensors are the reference's `*_base` ones
+        using PARAMETERS = T_PARAMETERS;
+        static constexpr size_t BATCH_SIZE = T_BATCH_SIZE, SEQUENCE_LENGTH = T_SEQUENCE_LENGTH, PADDED_SEQUENCE_LENGTH = T_SEQUENCE_LENGTH + 1, DIM = SPEC::OBSERVATION_DIM + 4;
+        std::vector<float> observations_actions = std::vector<float>(PADDED_SEQUENCE_LENGTH * T_BATCH_SIZE * DIM, 0.0f), rewards = std::vector<float>(SEQUENCE_LENGTH * T_BATCH_SIZE, 0.0f);
+        std::vector<uint8_t> terminated = std::vector<uint8_t>(SEQUENCE_LENGTH * T_BATCH_SIZE, 0), reset = std::vector<uint8_t>(SEQUENCE_LENGTH * T_BATCH_SIZE, 0),
+                             final_step_mask = std::vector<uint8_t>(SEQUENCE_LENGTH * T_BATCH_SIZE, 0), next_reset = std::vector<uint8_t>(PADDED_SEQUENCE_LENGTH * T_BATCH_SIZE, 0),
+                             next_final_step_mask = std::vector<uint8_t>(PADDED_SEQUENCE_LENGTH * T_BATCH_SIZE, 0);
         std::vector<uint64_t> rng = std::vector<uint64_t>(T_BATCH_SIZE, 0);   // one stream per batch sample (operations_cuda.h:36-60); seed them once
     };
 }
@@ -336,13 +348,16 @@ void step(devices::B200& device, off_policy_runner::Runner<SPEC, N, CAPACITY>& r
     const b200l2f_replay_buffers rb = runner.buffers();
     detail::check(device, *runner.env, b200l2f_off_policy_steps(runner.env->handle, n_steps, runner.step_limit, runner.sample_parameters ? 1 : 0, &rb));
 }
-// rl_tools::gather_batch(device, runner, batch, rng) (operations_generic.h:240-434), SEQUENCE_LENGTH 1
-template <typename SPEC, size_t N, size_t CAPACITY, size_t BATCH>
-void gather_batch(devices::B200& device, off_policy_runner::Runner<SPEC, N, CAPACITY>& runner, off_policy_runner::SequentialBatch<SPEC, BATCH>& batch, int env_begin = 0, int env_count = (int)N){
+// rl_tools::gather_batch(device, runner, batch, rng) (operations_generic.h:240-434), any SEQUENCE_LENGTH; the batch's PARAMETERS select the sampling
+template <typename SPEC, size_t N, size_t CAPACITY, size_t BATCH, size_t SEQUENCE_LENGTH, typename PARAMETERS>
+void gather_batch(devices::B200& device, off_policy_runner::Runner<SPEC, N, CAPACITY>& runner, off_policy_runner::SequentialBatch<SPEC, BATCH, SEQUENCE_LENGTH, PARAMETERS>& batch, int env_begin = 0, int env_count = (int)N){
     const b200l2f_replay_buffers rb = runner.buffers();
     b200l2f_batch out{};
     out.memspace = B200L2F_HOST; out.batch_size = (int32_t)BATCH; out.observations_actions = batch.observations_actions.data(); out.rewards = batch.rewards.data(); out.terminated = batch.terminated.data();
-    detail::check(device, *runner.env, b200l2f_gather_batch(runner.env->handle, &rb, runner.step_limit, env_begin, env_count, batch.rng.data(), &out));
+    out.reset = batch.reset.data(); out.next_reset = batch.next_reset.data(); out.final_step_mask = batch.final_step_mask.data(); out.next_final_step_mask = batch.next_final_step_mask.data();
+    const b200l2f_batch_parameters bp{(int32_t)SEQUENCE_LENGTH, PARAMETERS::INCLUDE_FIRST_STEP_IN_TARGETS, PARAMETERS::ALWAYS_SAMPLE_FROM_INITIAL_STATE, PARAMETERS::RANDOM_SEQ_LENGTH,
+                                      PARAMETERS::ENABLE_NOMINAL_SEQUENCE_LENGTH_PROBABILITY, PARAMETERS::NOMINAL_SEQUENCE_LENGTH_PROBABILITY};
+    detail::check(device, *runner.env, b200l2f_gather_batch_sequential(runner.env->handle, &rb, &bp, runner.step_limit, env_begin, env_count, batch.rng.data(), &out));
 }
 
 // ---- DAgger (src/foundation_policy/post_training/helper.h): gather_epoch for all teachers in one call ----------------------------------------------

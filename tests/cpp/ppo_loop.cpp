@@ -67,7 +67,54 @@ int run(const char* blobs_path, const char* out_path){
     return 0;
 }
 
+// SAC-teacher data path (off-policy runner steps into the replay rings, then the learner-side batches): `ppo_loop sac actor.f32 out.f32`
+// out.f32 = rings | batch (SEQUENCE_LENGTH 1) | batch (SEQUENCE_LENGTH 6, random lengths, from any row), every tensor as float
+struct SacSequenceParameters {   // rings of 64 rows < EPISODE_STEP_LIMIT: sampling from the episode's first row is not available (operations_generic.h:258)
+    static constexpr bool INCLUDE_FIRST_STEP_IN_TARGETS = true, ALWAYS_SAMPLE_FROM_INITIAL_STATE = false, RANDOM_SEQ_LENGTH = true, ENABLE_NOMINAL_SEQUENCE_LENGTH_PROBABILITY = true;
+    static constexpr float NOMINAL_SEQUENCE_LENGTH_PROBABILITY = 0.25f;
+};
+int run_sac(const char* actor_path, const char* out_path){
+    using SPEC = rlt::l2f::TeacherDRSpecification;
+    constexpr size_t N = 64, CAPACITY = 64, BATCH = 32;
+    constexpr int OBS = SPEC::OBSERVATION_DIM;
+    rlt::devices::B200 device;
+    rlt::l2f::vector::Environment<SPEC, N> env;
+    rlt::l2f::vector::Rng<N> rng;
+    rlt::malloc(device, env);
+    rlt::init(device, env);
+    rlt::init(device, rng, 91);
+    float row[B200L2F_PARAMS_DIM];
+    rlt::get_environment_parameters(device, env, row);
+    const float dr[15] = {1.5f, 5.0f, 40.f, 1200.f, 0.02f, 5.0f, 0.1f, 0.03f, 0.10f, 0.03f, 0.30f, 0.005f, 0.05f, 0.0f, 0.3f};
+    std::memcpy(row + 124, dr, sizeof(dr));
+    rlt::set_environment_parameters(device, env, row);
+    rlt::policy::MLP actor;
+    actor.blob.resize(64 * OBS + 64 + 64 * 64 + 64 + 8 * 64 + 8); actor.input_dim = OBS; actor.output_dim = 8; actor.head = B200L2F_HEAD_SQUASH_EVAL;
+    std::ifstream f(actor_path, std::ios::binary);
+    f.read((char*)actor.blob.data(), sizeof(float) * actor.blob.size());
+    rlt::utils::assert_exit(device, (size_t)f.gcount() == sizeof(float) * actor.blob.size(), "actor file too short");
+    rlt::malloc(device, env, actor);
+    rlt::off_policy_runner::Runner<SPEC, N, CAPACITY> runner;
+    runner.step_limit = 30;
+    rlt::init(device, runner, env, rng);
+    rlt::step(device, runner, 100);                               // the rings wrap
+    rlt::off_policy_runner::SequentialBatch<SPEC, BATCH> batch1;
+    rlt::off_policy_runner::SequentialBatch<SPEC, BATCH, 6, SacSequenceParameters> batch6;
+    for(size_t b = 0; b < BATCH; b++){ batch1.rng[b] = 0xAAAAAAAAull + 5000 + b; batch6.rng[b] = 0xAAAAAAAAull + 6000 + b; }
+    rlt::gather_batch(device, runner, batch1);
+    rlt::gather_batch(device, runner, batch6, 16, 24);            // one group of environments (a teacher's)
+    std::ofstream o(out_path, std::ios::binary);
+    auto put = [&](const auto& v){ for(auto x : v){ const float y = (float)x; o.write((const char*)&y, sizeof(float)); } };
+    put(runner.data); put(runner.position); put(runner.full);
+    put(batch1.observations_actions); put(batch1.rewards); put(batch1.terminated);
+    put(batch6.observations_actions); put(batch6.rewards); put(batch6.terminated); put(batch6.reset); put(batch6.next_reset); put(batch6.final_step_mask); put(batch6.next_final_step_mask);
+    std::printf("rings full %d, batch6 final steps %d\n", (int)runner.full[0], (int)batch6.final_step_mask[0]);
+    rlt::free(device, env);
+    return 0;
+}
+
 int main(int argc, char** argv){
+    if(argc >= 4 && std::string(argv[1]) == "sac") return run_sac(argv[2], argv[3]);
     if(argc >= 3 && std::string(argv[1]) == "checkpoint"){        // host only: no GPU needed
         rlt::devices::B200 device;
         rlt::policy::Checkpoint c;

@@ -797,6 +797,61 @@ def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("on_device", [False, True])
+def test_gather_batch_sequential_vs_oracle(rb, port, on_device):
+    """rl_tools::gather_batch for SEQUENCE_LENGTH > 1 (recurrent SAC; operations_generic.h:240-434): the CUDA walk against the oracle (itself bit-exact against the
+    reference's gather_batch_step for the same parameter sets, tests/test_oracle_vs_reference.py::test_gather_batch_sequential) -- fixed / random sequence
+    lengths, with / without the nominal-length draw, from any row / from the episode's first row, both `next_*` view offsets, rings partially filled and wrapped,
+    an environment sub-range; host and device buffers.  Bit-exact: a pure gather plus integer / double RNG arithmetic."""
+    import torch
+    n, obs, mel = 40, 26, 500
+    env = rb.VectorEnvironment(n, B.SPEC_TEACHER)
+    cases = [dict(sequence_length=8, include_first_step_in_targets=True, always_sample_from_initial_state=False, random_seq_length=False, capacity=48),
+             dict(sequence_length=8, capacity=640),                                                        # the reference's defaults for L > 1: all three switches on
+             dict(sequence_length=8, include_first_step_in_targets=False, always_sample_from_initial_state=False, random_seq_length=True,
+                  enable_nominal_sequence_length_probability=False, capacity=48),
+             dict(sequence_length=24, nominal_sequence_length_probability=0.1, capacity=640),
+             dict(sequence_length=2, capacity=640),
+             dict(sequence_length=1, capacity=48),                                                         # L = 1 through the general walk (defaults: all switches off)
+             dict(sequence_length=130, nominal_sequence_length_probability=0.3, capacity=700)]              # longer than a warp, than most episodes
+    for ci, case in enumerate(cases):
+        case = dict(case)
+        cap = case.pop("capacity")
+        for wrapped in (False, True):
+            rs = np.random.RandomState(50 * ci + wrapped)
+            fill = [cap + 11 * e + 5 for e in range(n)] if wrapped else [mel + 30 + e if cap > mel else cap * 3 // 4 for e in range(n)]
+            ring = B.synthetic_replay_rings(rs, n, cap, obs, fill=fill)
+            for (b0, cnt, Bsz) in ((0, None, 97), (8, 5, 33)):
+                rng_b = port.rng_states(7000 + ci, Bsz, warmup=3)
+                rng_want = rng_b.copy()
+                kw = dict(case); Lq = kw.pop("sequence_length")
+                dflt = Lq > 1
+                want = port.gather_batch_sequential(ring, rng_want, mel, Lq, include_first_step_in_targets=kw.get("include_first_step_in_targets", dflt),
+                                                    always_sample_from_initial_state=kw.get("always_sample_from_initial_state", dflt),
+                                                    random_seq_length=kw.get("random_seq_length", dflt),
+                                                    enable_nominal_sequence_length_probability=kw.get("enable_nominal_sequence_length_probability", True),
+                                                    nominal_sequence_length_probability=kw.get("nominal_sequence_length_probability", 0.5), env_begin=b0, env_count=cnt)
+                replay = dict(data=ring["replay"], episode_start=ring["episode_start"], position=ring["position"], full=ring["full"])
+                rng_in = rng_b.copy()
+                if on_device:
+                    replay = {k: torch.from_numpy(v).cuda() for k, v in replay.items()}
+                    rng_in = torch.from_numpy(rng_b.view(np.int64).copy()).cuda()
+                got = env.gather_batch(replay, rng_in, mel, env_begin=b0, env_count=cnt, **case)
+                env.synchronize()
+                g = lambda v: v.cpu().numpy() if on_device else v  # noqa: E731
+                assert np.array_equal(g(rng_in).view(np.uint64), rng_want), (case, wrapped)
+                for k, v in want.items():
+                    assert np.array_equal(g(got[k]), v), (case, wrapped, k)
+    with pytest.raises(rb.EngineError, match="capacity >= max_episode_length"):
+        ring = B.synthetic_replay_rings(np.random.RandomState(1), n, 48, obs, fill=[30] * n)
+        env.gather_batch(dict(data=ring["replay"], episode_start=ring["episode_start"], position=ring["position"], full=ring["full"]), port.rng_states(1, 4), mel, sequence_length=4)
+    with pytest.raises(rb.EngineError, match="at least one element"):
+        ring = B.synthetic_replay_rings(np.random.RandomState(1), n, 48, obs, fill=[0] * n)
+        env.gather_batch(dict(data=ring["replay"], episode_start=ring["episode_start"], position=ring["position"], full=ring["full"]), port.rng_states(1, 4), mel,
+                         sequence_length=4, always_sample_from_initial_state=False)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("spec,n,gemm", [(B.SPEC_RAPTOR, 256, "tcgen05"), (B.SPEC_RAPTOR_DR, 200, "tcgen05"), (B.SPEC_TEACHER_DR, 203, "tcgen05"), (B.SPEC_RAPTOR, 203, "fp32"),
                                          (B.SPEC_DEFAULT, 203, "fp32"), (B.SPEC_DEFAULT_DR, 200, "tcgen05")])
 def test_learner_feed_vs_oracle(rb, port, spec, n, gemm):
