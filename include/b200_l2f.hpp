@@ -357,7 +357,7 @@ void gather_batch(devices::B200& device, off_policy_runner::Runner<SPEC, N, CAPA
     out.reset = batch.reset.data(); out.next_reset = batch.next_reset.data(); out.final_step_mask = batch.final_step_mask.data(); out.next_final_step_mask = batch.next_final_step_mask.data();
     const b200l2f_batch_parameters bp{(int32_t)SEQUENCE_LENGTH, PARAMETERS::INCLUDE_FIRST_STEP_IN_TARGETS, PARAMETERS::ALWAYS_SAMPLE_FROM_INITIAL_STATE, PARAMETERS::RANDOM_SEQ_LENGTH,
                                       PARAMETERS::ENABLE_NOMINAL_SEQUENCE_LENGTH_PROBABILITY, PARAMETERS::NOMINAL_SEQUENCE_LENGTH_PROBABILITY};
-    detail::check(device, *runner.env, b200l2f_gather_batch_sequential(runner.env->handle, &rb, &bp, runner.step_limit, env_begin, env_count, batch.rng.data(), &out));
+    detail::check(device, *runner.env, b200l2f_gather_batch_sequential(runner.env->handle, &rb, &bp, SPEC::EPISODE_STEP_LIMIT, env_begin, env_count, batch.rng.data(), &out));   // MAX_EPISODE_LENGTH = ENVIRONMENT::EPISODE_STEP_LIMIT (off_policy_runner.h:41), not the runner's own step limit
 }
 
 // ---- DAgger (src/foundation_policy/post_training/helper.h): gather_epoch for all teachers in one call ----------------------------------------------

@@ -82,7 +82,7 @@ class NcclCommunicator:
         uid = UniqueId()
         if rank == 0:
             self._check(self.lib.ncclGetUniqueId(ctypes.byref(uid)), "ncclGetUniqueId")
-        box = [bytes(uid.internal) if rank == 0 else None]
+        box = [ctypes.string_at(ctypes.byref(uid), 128) if rank == 0 else None]   # all 128 bytes (a c_char array read as a value stops at the first NUL)
         dist.broadcast_object_list(box, src=0)
         ctypes.memmove(ctypes.byref(uid), box[0].ljust(128, b"\0"), 128)
         self.handle = ctypes.c_void_p()
@@ -128,4 +128,5 @@ def allgather_trajectories_native(env, comm, slab):
     ranks = ctypes.c_int32(0)
     env._check(env._lib.b200l2f_allgather_trajectories(env._h, comm.handle, slab.data_ptr(), out.data_ptr(), slab.numel(), ctypes.byref(ranks)))
     assert ranks.value == comm.world
+    env.synchronize()   # the gather runs on the ENGINE's stream; the re-layout below is a torch kernel on torch's stream
     return out.view(comm.world, T, n_local, D).permute(1, 0, 2, 3).reshape(T, comm.world * n_local, D)
