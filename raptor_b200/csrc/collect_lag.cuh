@@ -113,11 +113,11 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
                 float* hist_ptr = a.state + (size_t)S_HIST * n + env;
                 ParamsOverlay o;                             // sampled in registers: no dependent HBM round trips
                 o.init(a.row);
-                if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
+                if(!sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, rng)) atomicExch(a.error_flag, 1);
                 if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
-                compile_dynamics_block(sm_dyn + (size_t)slot * C_DIM, [&](int i){ return o[i]; });   // the owner's block (it sits out: nobody reads it now)
+                compile_dynamics_block<true, B200L2F_FAST_RESET != 0>(sm_dyn + (size_t)slot * C_DIM, [&](int i){ return o[i]; });   // the owner's block (it sits out: nobody reads it now)
                 EnvState<Spec> st;                           // built from scratch; the dead Langevin target stays with the owner (see the resume path)
-                sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
+                sample_state<Spec, ParamsOverlay, true, B200L2F_FAST_RESET != 0>(st, o, rng, hist_ptr, n);
 #pragma unroll
                 for(int i = 0; i < X_DIM; i++) mb[MB_X + i] = st.x[i];
 #pragma unroll
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
                         return p[i];
                     };
                     struct Acc { decltype(pa)& f; __device__ __forceinline__ float operator[](int i) const { return f(i); } } acc{pa};
-                    dyn_invariants(d, acc, st);
+                    dyn_invariants<Spec, Acc, B200L2F_FAST_RESET != 0>(d, acc, st);
                 }
                 sh.flag[tid] = LAG_IDLE;
                 truncated = false; ep_step = 0; ep_ret = 0.0f;

@@ -137,12 +137,12 @@ struct DynInvariants {
     float half_range;    // (action_limit.max - min) / 2     (operations_generic.h:105)
     float dt;
 };
-template <class Spec, class P>
+template <class Spec, class P, bool FAST = false>
 __device__ __forceinline__ void dyn_invariants(DynInvariants& d, const P& p, const EnvState<Spec>& st){
     const float mass = p[P_MASS];
-    d.inv_mass = 1.0f / mass;
+    d.inv_mass = FAST ? rcp_approx(mass) : 1.0f / mass;
 #pragma unroll
-    for(int i = 0; i < 3; i++){ d.fa[i] = st.force[i] / mass; d.ga[i] = p[P_GRAVITY + i] + d.fa[i]; }
+    for(int i = 0; i < 3; i++){ d.fa[i] = FAST ? st.force[i] * d.inv_mass : st.force[i] / mass; d.ga[i] = p[P_GRAVITY + i] + d.fa[i]; }
 #pragma unroll
     for(int i = 0; i < 3; i++){
         float a = 0.0f;

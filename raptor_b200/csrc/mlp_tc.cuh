@@ -18,6 +18,9 @@
 #include "mlp.cuh"
 #include "rollout_tc.cuh"
 
+#ifndef B200L2F_FAST_RESET
+#define B200L2F_FAST_RESET 1            // in-kernel resets of the default-math collection / runner kernels on the MUFU pipe (samplers.cuh: FAST twins)
+#endif
 #ifndef B200L2F_COLLECT_ROLLED_RK4
 #define B200L2F_COLLECT_ROLLED_RK4 1   // the collection kernel's integrator as one rolled stage loop (code size, see k_collect_ts)
 #endif
@@ -406,11 +409,11 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             truncated = false; ep_step = 0; ep_ret = 0.0f;
             ParamsOverlay o;                              // sampled in registers: no dependent HBM round trips on the reset path
             o.init(a.row);
-            if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
+            if(!sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, rng)) atomicExch(a.error_flag, 1);
             if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
-            compile_dynamics_block(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
-            sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
-            dyn_invariants(d, o, st);
+            compile_dynamics_block<true, B200L2F_FAST_RESET != 0>(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
+            sample_state<Spec, ParamsOverlay, true, B200L2F_FAST_RESET != 0>(st, o, rng, hist_ptr, n);
+            dyn_invariants<Spec, ParamsOverlay, B200L2F_FAST_RESET != 0>(d, o, st);
         }
         // the previous step's bulk store has read the window (in flight since the end of that step: the wait is free)
         if(store_pending){ if(lane == 0) tc::bulk_store_wait_read(); store_pending = false; }

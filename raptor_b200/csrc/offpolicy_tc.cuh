@@ -59,15 +59,15 @@ __global__ void __launch_bounds__(BLOCK, 2) k_off_policy_ts(const __grid_constan
             if(oa.sample_parameters){
                 ParamsOverlay o;                          // sampled in registers: no dependent HBM round trips on the reset path
                 o.init(a.row);
-                if(!sample_parameters<DR, Spec::RNG_OOL>(o, rng)) atomicExch(a.error_flag, 1);
+                if(!sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, rng)) atomicExch(a.error_flag, 1);
                 if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
-                compile_dynamics_block(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
-                sample_state<Spec, ParamsOverlay, true>(st, o, rng, hist_ptr, n);
-                dyn_invariants(d, o, st);
+                compile_dynamics_block<true, B200L2F_FAST_RESET != 0>(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
+                sample_state<Spec, ParamsOverlay, true, B200L2F_FAST_RESET != 0>(st, o, rng, hist_ptr, n);
+                dyn_invariants<Spec, ParamsOverlay, B200L2F_FAST_RESET != 0>(d, o, st);
             }
             else{
                 ParamsRW pg{a.params + env, n};
-                sample_state<Spec, ParamsRW, true>(st, pg, rng, hist_ptr, n);
+                sample_state<Spec, ParamsRW, true, B200L2F_FAST_RESET != 0>(st, pg, rng, hist_ptr, n);
                 dyn_invariants(d, pg, st);
             }
             if(rg.full || rg.position > 0){

@@ -158,7 +158,8 @@ template <int STRIDE = C_DIM>
 __device__ __forceinline__ float* dyn_block_of_thread(float* sm_dyn){ return sm_dyn + threadIdx.x * STRIDE; }
 using ParamsCompiled = ParamsCompiledT<false>;
 // compile this thread's dynamics block from any parameter accessor P(i) (HBM column, register overlay, ...)
-template <bool FULL = true, class F>
+// FAST: MUFU reciprocals / square root (the in-kernel resets of the default-math collection kernels; ~2 ulp on the rotor time constants and RK4 weights)
+template <bool FULL = true, bool FAST = false, class F>
 __device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F&& P){   // sm = dyn_block_of_thread(sm_dyn); FULL = false: axial entries only
 #pragma unroll
     for(int r = 0; r < 4; r++){
@@ -172,7 +173,7 @@ __device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F
         sm[C_AT01 + 2 * r + 0] = P(P_TORQUE_DIR + 3 * r + 0) * kq + (py * dz - pz * dy);
         sm[C_AT01 + 2 * r + 1] = P(P_TORQUE_DIR + 3 * r + 1) * kq + (pz * dx - px * dz);
         sm[C_AT2 + r]          = P(P_TORQUE_DIR + 3 * r + 2) * kq + (px * dy - py * dx);
-        const float ir = 1.0f / P(P_TAU_RISE + r), ifl = 1.0f / P(P_TAU_FALL + r);
+        const float ir = FAST ? rcp_approx(P(P_TAU_RISE + r)) : 1.0f / P(P_TAU_RISE + r), ifl = FAST ? rcp_approx(P(P_TAU_FALL + r)) : 1.0f / P(P_TAU_FALL + r);
         sm[C_TAU_M + r] = 0.5f * (ir + ifl);
         sm[C_TAU_H + r] = 0.5f * (ir - ifl);
     }
@@ -190,8 +191,8 @@ __device__ __forceinline__ void compile_dynamics_block(float* __restrict__ sm, F
     }
     sm[C_G + 3] = P(P_ACT_MIN); sm[C_JD + 3] = P(P_ACT_MAX); sm[C_JID + 3] = P(P_TERM_POS);
     const float dt = P(P_DT);
-    sm[C_DT] = dt; sm[C_DT + 1] = dt / 2.0f; sm[C_DT + 2] = dt / 3.0f; sm[C_DT + 3] = dt / 6.0f;
-    sm[C_SQRT_DT] = sqrtf(dt); sm[C_SQRT_DT + 1] = 0.0f; sm[C_SQRT_DT + 2] = 0.0f; sm[C_SQRT_DT + 3] = 0.0f;
+    sm[C_DT] = dt; sm[C_DT + 1] = dt / 2.0f; sm[C_DT + 2] = FAST ? dt * 0.333333343267440796f : dt / 3.0f; sm[C_DT + 3] = FAST ? dt * 0.16666667163372040f : dt / 6.0f;
+    sm[C_SQRT_DT] = sqrt_t<FAST>(dt); sm[C_SQRT_DT + 1] = 0.0f; sm[C_SQRT_DT + 2] = 0.0f; sm[C_SQRT_DT + 3] = 0.0f;
 }
 template <bool UNIFORM, bool NC = true, bool FOLLOW = false, int STRIDE = C_DIM>
 __device__ __forceinline__ ParamsCompiledT<UNIFORM, NC, FOLLOW> stage_dynamics_compiled(float* __restrict__ sm_dyn, const float* params, size_t n, size_t env, const float* row0){

@@ -25,6 +25,14 @@ struct ParamsRW {  // read/write view of one environment's parameter column in t
 #define B200_ADD(a, b) __fadd_rn((a), (b))
 #define B200_SUB(a, b) __fsub_rn((a), (b))
 #define B200_DIV(a, b) __fdiv_rn((a), (b))
+// FAST twins for the in-kernel resets of the default-math kernels (k_collect_ts, k_off_policy_ts): MUFU reciprocal / cube root / square root / sine /
+// cosine and the MUFU Box-Muller instead of IEEE division, libdevice cbrtf / sinf / cosf / logf and fp64 detours.  Every result stays within ~5e-7
+// relative of the accurate form (the parity tests bound the re-sampled parameters at 2e-6); the integer RNG stream is untouched, so is the draw order.
+template <bool FAST> __device__ __forceinline__ float div_t(float a, float b){ if constexpr(FAST) return a * rcp_approx(b); else return __fdiv_rn(a, b); }
+template <bool FAST> __device__ __forceinline__ float cbrt_t(float x){   // x > 0 (masses)
+    if constexpr(FAST){ float l; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x)); return ex2_approx(l * 0.333333343267440796f); }
+    else return cbrtf(x);
+}
 
 // Register overlay over the (uniform) nominal row: the 47 entries domain randomisation rewrites live in registers, everything else is read
 // from the row.  The sampler therefore issues no dependent global loads; the column in HBM is written once at the end (flush).  All indices
@@ -84,13 +92,13 @@ struct ParamsOverlay {
 
 // sample_initial_parameters on the overlay (p.init(row) done by the caller).  Returns false if the DR ranges violate the reference's
 // assert_exit conditions (the caller records the error).  Arithmetic and draw order: 10_sample_initial_parameters.h:20-160.
-template <bool DR, bool RNG_OOL = false>
+template <bool DR, bool RNG_OOL = false, bool FAST = false>
 __device__ __forceinline__ bool sample_parameters(ParamsOverlay& p, uint64_t& rng){
     if constexpr(!DR){ return true; }
     else{
         const float* __restrict__ row = p.row;
         float t2w_nominal;
-        float gravity_norm = sqrtf(B200_ADD(B200_ADD(B200_MUL(row[P_GRAVITY], row[P_GRAVITY]), B200_MUL(row[P_GRAVITY + 1], row[P_GRAVITY + 1])), B200_MUL(row[P_GRAVITY + 2], row[P_GRAVITY + 2])));
+        float gravity_norm = sqrt_t<FAST>(B200_ADD(B200_ADD(B200_MUL(row[P_GRAVITY], row[P_GRAVITY]), B200_MUL(row[P_GRAVITY + 1], row[P_GRAVITY + 1])), B200_MUL(row[P_GRAVITY + 2], row[P_GRAVITY + 2])));
         {
             const float max_action = row[P_ACT_MAX];
             float max_thrust_nominal = 0.0f;
@@ -99,46 +107,46 @@ __device__ __forceinline__ bool sample_parameters(ParamsOverlay& p, uint64_t& rn
                 float v = B200_ADD(B200_ADD(p.coef[3 * r], B200_MUL(p.coef[3 * r + 1], max_action)), B200_MUL(B200_MUL(p.coef[3 * r + 2], max_action), max_action));
                 max_thrust_nominal = B200_ADD(max_thrust_nominal, v);
             }
-            t2w_nominal = B200_DIV(max_thrust_nominal, B200_MUL(p.mass, gravity_norm));
+            t2w_nominal = div_t<FAST>(max_thrust_nominal, B200_MUL(p.mass, gravity_norm));
         }
         if(!(row[P_DR_T2W_MIN] < row[P_DR_T2W_MAX]) || !(row[P_DR_T2W_MIN] >= 1.5f)) return false;
         const float t2w = rng_uniform(rng, row[P_DR_T2W_MIN], row[P_DR_T2W_MAX]);
-        const float factor_t2w = B200_DIV(t2w, t2w_nominal);
+        const float factor_t2w = div_t<FAST>(t2w, t2w_nominal);
         if(!(row[P_DR_MASS_MIN] < row[P_DR_MASS_MAX])) return false;
-        const float size_min = cbrtf(row[P_DR_MASS_MIN]);
-        const float size_max = cbrtf(row[P_DR_MASS_MAX]);
+        const float size_min = cbrt_t<FAST>(row[P_DR_MASS_MIN]);
+        const float size_max = cbrt_t<FAST>(row[P_DR_MASS_MAX]);
         const float size_new = rng_uniform(rng, size_min, size_max);
         float mass_new = B200_MUL(B200_MUL(size_new, size_new), size_new);
         mass_new = clampf(mass_new, row[P_DR_MASS_MIN], row[P_DR_MASS_MAX]);
-        const float scale_relative = cbrtf(B200_DIV(mass_new, p.mass));
-        const float factor_mass = B200_DIV(mass_new, p.mass);
+        const float scale_relative = cbrt_t<FAST>(div_t<FAST>(mass_new, p.mass));
+        const float factor_mass = div_t<FAST>(mass_new, p.mass);
         p.mass = mass_new;
         const float factor_coef = B200_MUL(factor_t2w, factor_mass);
 #pragma unroll
         for(int i = 0; i < 12; i++) p.coef[i] = B200_MUL(p.coef[i], factor_coef);
         float t2i_factor;
         {
-            const float max_thrust = B200_DIV(B200_MUL(B200_MUL(t2w, p.mass), gravity_norm), 4.0f);
+            const float max_thrust = div_t<FAST>(B200_MUL(B200_MUL(t2w, p.mass), gravity_norm), 4.0f);
             const float first_rotor_distance = fabsf(p.rpos[0]);
-            const float max_torque = (float)((double)first_rotor_distance * 1.414213562373095 * (double)max_thrust);
-            const float t2i_nominal = B200_DIV(max_torque, p.jd[0]);
+            const float max_torque = FAST ? first_rotor_distance * 1.41421353816986084f * max_thrust : (float)((double)first_rotor_distance * 1.414213562373095 * (double)max_thrust);
+            const float t2i_nominal = div_t<FAST>(max_torque, p.jd[0]);
             if(!(row[P_DR_T2I_MIN] < row[P_DR_T2I_MAX])) return false;
             const float t2i = rng_uniform(rng, row[P_DR_T2I_MIN], row[P_DR_T2I_MAX]);
-            t2i_factor = B200_DIV(t2i, t2i_nominal);
+            t2i_factor = div_t<FAST>(t2i, t2i_nominal);
         }
         if(row[P_DR_MASS_SIZE_DEV] == 0.0f) return false;
         float size_factor;
         {
             const float range = row[P_DR_MASS_SIZE_DEV];
-            const float f = rng_normal_t<RNG_OOL>(rng, -range, range);
-            size_factor = f < 0.0f ? B200_DIV(1.0f, B200_SUB(1.0f, f)) : B200_ADD(1.0f, f);
+            const float f = rng_normal_t<RNG_OOL, FAST>(rng, -range, range);
+            size_factor = f < 0.0f ? div_t<FAST>(1.0f, B200_SUB(1.0f, f)) : B200_ADD(1.0f, f);
         }
         const float rotor_distance_factor = B200_MUL(scale_relative, size_factor);
         {
-            const float inertia_factor = B200_DIV(t2i_factor, rotor_distance_factor);
+            const float inertia_factor = div_t<FAST>(t2i_factor, rotor_distance_factor);
 #pragma unroll
             for(int a = 0; a < 3; a++){
-                p.jd[a] = B200_DIV(p.jd[a], inertia_factor);
+                p.jd[a] = div_t<FAST>(p.jd[a], inertia_factor);
                 p.jinvd[a] = B200_MUL(p.jinvd[a], inertia_factor);
             }
 #pragma unroll
@@ -147,7 +155,7 @@ __device__ __forceinline__ bool sample_parameters(ParamsOverlay& p, uint64_t& rn
 #pragma unroll
             for(int r = 0; r < 4; r++){
                 const float x = p.rpos[3 * r], y = p.rpos[3 * r + 1], z = p.rpos[3 * r + 2];
-                const float dd = sqrtf(B200_ADD(B200_ADD(B200_MUL(x, x), B200_MUL(y, y)), B200_MUL(z, z)));
+                const float dd = sqrt_t<FAST>(B200_ADD(B200_ADD(B200_MUL(x, x), B200_MUL(y, y)), B200_MUL(z, z)));
                 if(dd > max_rotor_distance) max_rotor_distance = dd;
             }
             p.term_pos = B200_MUL(max_rotor_distance, 20.0f);
@@ -161,11 +169,11 @@ __device__ __forceinline__ bool sample_parameters(ParamsOverlay& p, uint64_t& rn
         }
         if(row[P_DR_DIST_FORCE_MAX] == 0.0f) return false;
         {
-            float surplus = (float)((double)t2w - 1.0);
+            float surplus = FAST ? t2w - 1.0f : (float)((double)t2w - 1.0);
             if(surplus < 0.0f) surplus = 0.0f;
             const float multiple = rng_uniform(rng, 0.0f, B200_MUL(surplus, row[P_DR_DIST_FORCE_MAX]));
             p.dist_f_mean = 0.0f;
-            p.dist_f_std = B200_DIV(B200_MUL(B200_MUL(multiple, t2w), p.mass), 3.0f);
+            p.dist_f_std = div_t<FAST>(B200_MUL(B200_MUL(multiple, t2w), p.mass), 3.0f);
         }
         if(row[P_DR_TAU_RISE_MIN] == 0.0f || row[P_DR_TAU_RISE_MAX] == 0.0f || row[P_DR_TAU_FALL_MIN] == 0.0f || row[P_DR_TAU_FALL_MAX] == 0.0f) return false;
         {
@@ -188,11 +196,11 @@ __device__ __forceinline__ bool sample_parameters(const float* __restrict__ env_
 }
 
 // hist_ptr: SoA rows of action_history for H > 1 (element (h,a) at hist_ptr[(4h+a)*n]); unused for H == 1
-template <class Spec, class P>
+template <class Spec, class P, bool FAST = false>
 __device__ __forceinline__ void set_history_from_rpm(EnvState<Spec>& st, const P& p, float* __restrict__ hist_ptr, size_t n){
     float v[4];
 #pragma unroll
-    for(int i = 0; i < 4; i++) v[i] = B200_SUB(B200_MUL(B200_DIV(B200_SUB(st.x[X_RPM + i], p[P_ACT_MIN]), B200_SUB(p[P_ACT_MAX], p[P_ACT_MIN])), 2.0f), 1.0f);
+    for(int i = 0; i < 4; i++) v[i] = B200_SUB(B200_MUL(div_t<FAST>(B200_SUB(st.x[X_RPM + i], p[P_ACT_MIN]), B200_SUB(p[P_ACT_MAX], p[P_ACT_MIN])), 2.0f), 1.0f);
     if constexpr(Spec::H == 1){
 #pragma unroll
         for(int i = 0; i < 4; i++) st.hist[i] = v[i];
@@ -228,7 +236,7 @@ __device__ __forceinline__ void initial_state(EnvState<Spec>& st, const P& p, fl
 // KEEP_DEAD_TARGET: a reset that draws the POSITION trajectory leaves the previous episode's Langevin target in the state, exactly as the
 // reference does (30_sample_initial_state.h:217-219: `case POSITION: break;`); the values are never read while the type is POSITION and are
 // zeroed when the type becomes LANGEVIN again.  false: the state is built from scratch (the vector-API call on a fresh State).
-template <class Spec, class P, bool KEEP_DEAD_TARGET = false>
+template <class Spec, class P, bool KEEP_DEAD_TARGET = false, bool FAST = false>
 __device__ __forceinline__ void sample_state(EnvState<Spec>& st, const P& p, uint64_t& rng, float* __restrict__ hist_ptr, size_t n){
 #pragma unroll
     for(int i = 0; i < X_DIM; i++) st.x[i] = 0.0f;
@@ -240,16 +248,25 @@ __device__ __forceinline__ void sample_state(EnvState<Spec>& st, const P& p, uin
     if(p[P_INIT_MAX_ANGLE] > 0.0f && !guidance){
         const float u = rng_uniform(rng, 0.0f, 1.0f);
         const float v = rng_uniform(rng, 0.0f, 1.0f);
-        const float phi = (float)(2.0 * (double)3.14159274101257324f * (double)u);
-        const float cos_theta = (float)(1.0 - 2.0 * (double)v);
-        const float sin_theta = (float)sqrt(1.0 - (double)B200_MUL(cos_theta, cos_theta));
-        const float ax = B200_MUL(sin_theta, cosf(phi));
-        const float ay = B200_MUL(sin_theta, sinf(phi));
-        const float az = cos_theta;
-        const float angle = rng_uniform(rng, 0.0f, 1.0f);   // the limit only gates (30_sample_initial_state.h:31,60)
+        float ax, ay, az, angle;
+        if constexpr(FAST){                                  // same quantities on the MUFU pipe: phi reduced to (-pi, pi], sin(theta) = sqrt((1 - c)(1 + c)) without the fp64 detour
+            const float phi = 6.28318548202514648f * (u > 0.5f ? u - 1.0f : u);
+            const float cos_theta = 1.0f - 2.0f * v;
+            const float sin_theta = sqrt_approx((1.0f - cos_theta) * (1.0f + cos_theta));
+            ax = sin_theta * __cosf(phi); ay = sin_theta * __sinf(phi); az = cos_theta;
+        }
+        else{
+            const float phi = (float)(2.0 * (double)3.14159274101257324f * (double)u);
+            const float cos_theta = (float)(1.0 - 2.0 * (double)v);
+            const float sin_theta = (float)sqrt(1.0 - (double)B200_MUL(cos_theta, cos_theta));
+            ax = B200_MUL(sin_theta, cosf(phi));
+            ay = B200_MUL(sin_theta, sinf(phi));
+            az = cos_theta;
+        }
+        angle = rng_uniform(rng, 0.0f, 1.0f);               // the limit only gates (30_sample_initial_state.h:31,60)
         const float half = 0.5f * angle;
-        const float sn = sinf(half);
-        st.x[X_ORI] = cosf(half); st.x[X_ORI + 1] = B200_MUL(ax, sn); st.x[X_ORI + 2] = B200_MUL(ay, sn); st.x[X_ORI + 3] = B200_MUL(az, sn);
+        const float sn = FAST ? __sinf(half) : sinf(half);
+        st.x[X_ORI] = FAST ? __cosf(half) : cosf(half); st.x[X_ORI + 1] = B200_MUL(ax, sn); st.x[X_ORI + 2] = B200_MUL(ay, sn); st.x[X_ORI + 3] = B200_MUL(az, sn);
     }
     else{
         st.x[X_ORI] = 1.0f;
@@ -263,17 +280,17 @@ __device__ __forceinline__ void sample_state(EnvState<Spec>& st, const P& p, uin
     for(int i = 0; i < 4; i++) st.last_action[i] = 0.0f;
     {
         const float fm = p[P_DIST_FORCE_MEAN], fs = p[P_DIST_FORCE_STD], tm = p[P_DIST_TORQUE_MEAN], ts = p[P_DIST_TORQUE_STD];
-        for(int i = 0; i < 3; i++) st.force[i] = rng_normal_t<Spec::RNG_OOL>(rng, fm, fs);
-        st.torque[0] = rng_normal_t<Spec::RNG_OOL>(rng, tm, ts);
-        st.torque[1] = rng_normal_t<Spec::RNG_OOL>(rng, tm, ts);
-        st.torque[2] = rng_normal_t<Spec::RNG_OOL>(rng, tm, B200_DIV(ts, 100.0f));
+        for(int i = 0; i < 3; i++) st.force[i] = rng_normal_t<Spec::RNG_OOL, FAST>(rng, fm, fs);
+        st.torque[0] = rng_normal_t<Spec::RNG_OOL, FAST>(rng, tm, ts);
+        st.torque[1] = rng_normal_t<Spec::RNG_OOL, FAST>(rng, tm, ts);
+        st.torque[2] = rng_normal_t<Spec::RNG_OOL, FAST>(rng, tm, div_t<FAST>(ts, 100.0f));
     }
     {
         float min_rpm, max_rpm;
         const float amin = p[P_ACT_MIN], amax = p[P_ACT_MAX];
         if(p[P_INIT_REL_RPM] != 0.0f){
-            min_rpm = B200_ADD(B200_MUL(B200_DIV(B200_ADD(p[P_INIT_MIN_RPM], 1.0f), 2.0f), B200_SUB(amax, amin)), amin);
-            max_rpm = B200_ADD(B200_MUL(B200_DIV(B200_ADD(p[P_INIT_MAX_RPM], 1.0f), 2.0f), B200_SUB(amax, amin)), amin);
+            min_rpm = B200_ADD(B200_MUL(B200_MUL(B200_ADD(p[P_INIT_MIN_RPM], 1.0f), 0.5f), B200_SUB(amax, amin)), amin);   // / 2.0f == * 0.5f exactly
+            max_rpm = B200_ADD(B200_MUL(B200_MUL(B200_ADD(p[P_INIT_MAX_RPM], 1.0f), 0.5f), B200_SUB(amax, amin)), amin);
         }
         else{
             min_rpm = p[P_INIT_MIN_RPM] < 0.0f ? amin : p[P_INIT_MIN_RPM];
@@ -283,7 +300,7 @@ __device__ __forceinline__ void sample_state(EnvState<Spec>& st, const P& p, uin
         }
         for(int i = 0; i < 4; i++) st.x[X_RPM + i] = rng_uniform(rng, min_rpm, max_rpm);
     }
-    set_history_from_rpm(st, p, hist_ptr, n);
+    set_history_from_rpm<Spec, P, FAST>(st, p, hist_ptr, n);
     st.traj_type = 0;
     if constexpr(Spec::LANGEVIN){
         const float threshold = rng_uniform(rng, 0.0f, 1.0f);
