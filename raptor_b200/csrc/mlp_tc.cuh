@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
     float* hist_ptr = a.state + (size_t)S_HIST * n + env;
     uint64_t rng = a.rng[env];
     int ep_step = a.episode_step[env]; float ep_ret = a.episode_return[env]; bool truncated = a.truncated[env] != 0;
+    uint64_t rng_at_reset = 0; bool reset_seen = false;
     const int warp_env0 = tile * BLOCK + warp * 32;
     const int rows_valid = min(32, a.n - warp_env0);
     // a full warp's 32 rows are one contiguous, 16-byte aligned run of 32 * D floats in the dataset: ONE bulk copy (TMA, shared -> global) per
@@ -409,8 +410,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             truncated = false; ep_step = 0; ep_ret = 0.0f;
             ParamsOverlay o;                              // sampled in registers: no dependent HBM round trips on the reset path
             o.init(a.row);
+            if constexpr(DR && FOLLOW){ rng_at_reset = rng; reset_seen = true; }   // the column is written once, after the step loop (see there)
             if(!sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, rng)) atomicExch(a.error_flag, 1);
-            if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
+            if constexpr(!FOLLOW) o.template flush<true>(ParamsRW{a.params + env, n});
             compile_dynamics_block<true, B200L2F_FAST_RESET != 0>(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
             sample_state<Spec, ParamsOverlay, true, B200L2F_FAST_RESET != 0>(st, o, rng, hist_ptr, n);
             dyn_invariants<Spec, ParamsOverlay, B200L2F_FAST_RESET != 0>(d, o, st);
@@ -478,6 +480,19 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         store_state(st, a.state + env, n);
         a.rng[env] = rng;
         a.episode_step[env] = ep_step; a.episode_return[env] = ep_ret; a.truncated[env] = truncated ? 1 : 0;
+    }
+    if constexpr(DR && FOLLOW){
+        // Deferred parameter write-back: while the columns follow the nominal row nothing in the step loop reads the randomised entries from HBM (they live in
+        // the dynamics block / the step invariants), and a reset starts from the nominal row again -- so only the LAST reset's parameters have to reach the
+        // column.  They are a function of the RNG state that reset started from: re-sample once here, all lanes together, instead of 47 scattered stores
+        // inside every divergent reset (~270 instructions of each reset execution).
+        if(active && reset_seen){
+            ParamsOverlay o;
+            o.init(a.row);
+            uint64_t r = rng_at_reset;
+            sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, r);
+            o.template flush<false>(ParamsRW{a.params + env, n});
+        }
     }
     }   // tile loop
     if(store_pending && lane == 0) tc::bulk_store_wait_all();   // the window must outlive the copy

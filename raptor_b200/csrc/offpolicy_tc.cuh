@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_off_policy_ts(const __grid_constan
     float* hist_ptr = a.state + (size_t)S_HIST * n + env;
     uint64_t rng = a.rng[env];
     int ep_step = a.episode_step[env]; float ep_ret = a.episode_return[env]; bool truncated = a.truncated[env] != 0;
+    uint64_t rng_at_reset = 0; bool reset_seen = false;
     Ring rg{oa.position[env], oa.current_episode_start[env], oa.full[env] != 0};
     float* ring = oa.replay + env * (size_t)oa.capacity * D;
     int* es = oa.episode_start + env * (size_t)oa.capacity;
@@ -59,8 +60,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_off_policy_ts(const __grid_constan
             if(oa.sample_parameters){
                 ParamsOverlay o;                          // sampled in registers: no dependent HBM round trips on the reset path
                 o.init(a.row);
+                if constexpr(DR && FOLLOW){ rng_at_reset = rng; reset_seen = true; }   // deferred parameter write-back, as in k_collect_ts
                 if(!sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, rng)) atomicExch(a.error_flag, 1);
-                if constexpr(DR || !FOLLOW) o.template flush<!FOLLOW>(ParamsRW{a.params + env, n});
+                if constexpr(!FOLLOW) o.template flush<true>(ParamsRW{a.params + env, n});
                 compile_dynamics_block<true, B200L2F_FAST_RESET != 0>(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
                 sample_state<Spec, ParamsOverlay, true, B200L2F_FAST_RESET != 0>(st, o, rng, hist_ptr, n);
                 dyn_invariants<Spec, ParamsOverlay, B200L2F_FAST_RESET != 0>(d, o, st);
@@ -112,6 +114,15 @@ __global__ void __launch_bounds__(BLOCK, 2) k_off_policy_ts(const __grid_constan
         a.rng[env] = rng;
         a.episode_step[env] = ep_step; a.episode_return[env] = ep_ret; a.truncated[env] = truncated ? 1 : 0;
         oa.position[env] = rg.position; oa.current_episode_start[env] = rg.current_start; oa.full[env] = rg.full ? 1 : 0;
+    }
+    if constexpr(DR && FOLLOW){                           // the last reset's parameters reach the column here (k_collect_ts has the argument)
+        if(active && reset_seen){
+            ParamsOverlay o;
+            o.init(a.row);
+            uint64_t r = rng_at_reset;
+            sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, r);
+            o.template flush<false>(ParamsRW{a.params + env, n});
+        }
     }
     }   // tile loop
     mlp_ts_epilogue(c);

@@ -50,12 +50,17 @@ static __device__ __noinline__ float rng_normal_draw_ool(uint64_t& s, float mean
 __device__ __forceinline__ float rng_normal_draw_fast(uint64_t& s, float mean, float std){
     const float u1 = rng_unit(s);
     float u2 = rng_unit(s);
-    const float x = sqrt_approx(-2.0f * __logf(u1));
+    float l2; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));   // u1 >= 2^-64: never denormal, no scaling needed (what __logf adds)
+    const float x = sqrt_approx(-1.38629436111989062f * l2);              // -2 ln u1 = -2 ln 2 * log2 u1
     if(u2 > 0.5f) u2 -= 1.0f;                            // cos(2 pi u) with the argument reduced to (-pi, pi], where cos.approx is tight
     const float z = x * __cosf(6.28318548202514648f * u2);
     return fmaf(z, std, mean);
 }
-static __device__ __noinline__ float rng_normal_draw_fast_ool(uint64_t& s, float mean, float std){ return rng_normal_draw_fast(s, mean, std); }
+// out of line with the stream state passed and returned BY VALUE (registers): a reference parameter makes the caller spill the state to local memory around
+// every call (LDL / STL + their latency on the dependent chain of draws)
+struct NormalDraw { uint64_t s; float z; };
+static __device__ __noinline__ NormalDraw rng_normal_draw_fast_ool_value(uint64_t s, float mean, float std){ NormalDraw r; r.z = rng_normal_draw_fast(s, mean, std); r.s = s; return r; }
+__device__ __forceinline__ float rng_normal_draw_fast_ool(uint64_t& s, float mean, float std){ const NormalDraw r = rng_normal_draw_fast_ool_value(s, mean, std); s = r.s; return r.z; }
 template <bool OOL, bool FAST = false>
 __device__ __forceinline__ float rng_normal_t(uint64_t& s, float mean, float std){
     if(std == 0.0f){ return mean; }
