@@ -276,7 +276,7 @@ def run_other_configs(rb, torch, dev, stream, flush, rank, world, use_dist):
     k = env.last_kernel()
     rl = roofline_object(k, n, T, ms / 1e3, peaks, counters, FLOP_PPO_GEMM)
     rl["hbm"] = {"achieved": written / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": written / ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": written,
-                 "note": "dataset rows written (34 of the 37 floats per row, on_policy_runner.h:42-64)"}
+                 "note": "algorithmic bytes: the 34 of 37 floats per row that collect produces (on_policy_runner.h:42-64) + the final observations; the kernel writes whole 148-byte rows (learner columns zero-filled) as one TMA bulk copy per warp-step"}
     out["config4"] = {"workload": "BASELINE configs[3]: %d envs/GPU x %d-step PPO rollout collection, PPO actor 22-64-64-4 (standardize, learned log_std), DR resets, dataset [(T+1)N, 37] in HBM" % (n, T),
                       "value": n * world * T / ms * 1e3, "unit": "env-steps/s", "ms_per_launch": ms, "kernel": k, "dataset_bytes_written": written, "roofline": rl,
                       "mean_reward": float(data[: T * n, 31].mean().item()), "truncated_fraction": float(data[: T * n, 33].mean().item())}
