@@ -303,6 +303,71 @@ def test_bench_configuration_vs_oracle(rb, port):
     close(env.get_state()[sel], out["states"][-1][:, :][sel], 0, 0, "final state row == slot 0")
 
 
+@pytest.mark.gpu
+def test_config3_and_config4_launches_vs_oracle(rb, port):
+    """the other two single-GPU launches bench.py times, at FULL size, against the oracle on a strided environment sample (one environment of every eighth tile,
+    varying lane): config 3 = 1 048 576 environments, per-environment DR, SAC-teacher MLP 26-64-64-8 (k_rollout_mlp_ts, time-chunked scheduler, 2 CTAs/SM);
+    config 4 = 262 144 environments, PPO collection with in-kernel resets and the bulk-copy write-back (k_collect_ts).  First 20 steps at the north-star bound,
+    flags and RNG streams bit-exact."""
+    import bench
+    import torch
+    rs = np.random.RandomState(0)
+    dev = torch.device("cuda", 0)
+    # ---- config 3
+    n, T = 1048576, 20
+    env = rb.VectorEnvironment(n, rb.SPEC_TEACHER_DR)
+    row = env.get_environment_parameters(); row[124:139] = np.array(bench.DR_RANGES, np.float32); env.set_environment_parameters(row)
+    env.initialize_rng(3, warmup=16); env.sample_initial_parameters(); env.sample_initial_state()
+    blob = bench.mlp_blob(rs, 26, 8, False, False)
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=rb.HEAD_SQUASH_EVAL, gemm=rb.GEMM_TCGEN05_3XTF32)
+    sel = np.arange(0, n, 1024) + (np.arange(n // 1024) * 37) % 128
+    params, states, rng = env.get_parameters()[sel], env.get_state()[sel], env.get_rng()[sel]
+    out = dict(actions=torch.zeros((T, n, 4), device=dev), rewards=torch.zeros((T, n), device=dev), terminated=torch.zeros((T, n), dtype=torch.uint8, device=dev))
+    env.rollout(T, out=out)
+    env.synchronize()
+    assert env.last_kernel() == "k_rollout_mlp_ts"
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=26, hidden_dim=64, output_dim=8, standardize=0, head=B.HEAD_SQUASH_EVAL)
+    want = port.rollout(rb.SPEC_TEACHER_DR, pol, params, states, rng, T)
+    tsel = torch.from_numpy(sel).to(dev)
+    close_relative(out["actions"][:, tsel].cpu().numpy(), want["actions"], 1e-4, {"action": (slice(0, 4), 0.1)}, "config 3 actions")
+    close(out["rewards"][:, tsel].cpu().numpy(), want["rewards"], 1e-3, 1e-3, "config 3 rewards")
+    assert np.array_equal(out["terminated"][:, tsel].cpu().numpy(), want["terminated"])
+    assert np.array_equal(env.get_rng()[sel], rng)
+    close_relative(env.get_state()[sel][None], states[None], 1e-4, STATE_GROUPS, "config 3 final states")
+    del env, out
+    # ---- config 4
+    n, T, limit = 262144, 20, 500
+    obs, D = 22, 37
+    env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR)
+    row = env.get_environment_parameters(); row[124:139] = np.array(bench.DR_RANGES, np.float32); env.set_environment_parameters(row)
+    env.initialize_rng(4, warmup=16); env.initial_parameters(); env.initial_state()
+    blob = bench.mlp_blob(rs, 22, 4, True, True)
+    env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=22, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=rb.GEMM_TCGEN05_3XTF32)
+    env.collect_reset()
+    sel = np.arange(0, n, 1024) + (np.arange(n // 1024) * 37) % 128
+    params, states, rng = env.get_parameters()[sel], env.get_state()[sel], env.get_rng()[sel]
+    data = torch.full(((T + 1) * n, D), 7.0, dtype=torch.float32, device=dev)          # stale contents: every row must be rewritten
+    env.collect(T, limit, data)
+    env.synchronize()
+    assert env.last_kernel() == "k_collect_ts"
+    got3 = data.view(T + 1, n, D)[:, torch.from_numpy(sel).to(dev)].cpu().numpy()
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
+    m = len(sel)
+    ep_step = np.zeros(m, np.int32); ep_ret = np.zeros(m, np.float32); trunc = np.ones(m, np.uint8)
+    want3 = port.collect(rb.SPEC_RAPTOR_DR, pol, row, params, states, rng, ep_step, ep_ret, trunc, T, limit).reshape(T + 1, m, D)
+    assert np.array_equal(env.get_rng()[sel], rng)
+    assert np.array_equal(got3[:T, :, obs + 10:obs + 12], want3[:T, :, obs + 10:obs + 12])      # terminated | truncated
+    assert want3[:T, :, obs + 11].sum() > 0                                                      # episodes ended (and were reset in the kernel) inside the window
+    K = 8
+    close(got3[:K, :, :obs], want3[:K, :, :obs], 1e-4, 3e-5, "config 4 observations, first steps")
+    close(got3[:K, :, obs:obs + 8], want3[:K, :, obs:obs + 8], 1e-4, 3e-5, "config 4 action means / actions, first steps")
+    close(got3[..., :obs], want3[..., :obs], 2e-3, 2e-4, "config 4 observations (incl. the final row)")
+    close(got3[:T, :, obs + 8], want3[:T, :, obs + 8], 1e-3, 1e-3, "config 4 log-prob")
+    assert np.all(got3[..., obs + 12:] == 0) and np.all(got3[T, :, obs:] == 0)                   # learner columns and the final rows' step columns: zeros
+    assert int((data == 7.0).sum().item()) == 0                                                  # no stale element survived anywhere in the 0.8 GB dataset
+    close(env.get_parameters()[sel], params, 2e-6, 0, "config 4 parameters after the in-kernel resets (deferred write-back)")
+
+
 def test_asynchronous_transfers_match_the_synchronous_calls(rb):
     """b200l2f_set_parameters_async / set_state_async / get_state_async / copy_to_host_async (copy streams + staging buffers, transposes ordered on the
     main stream): a pipelined sequence of rollouts fed from page-locked host memory gives the bits of the synchronous calls; pageable memory falls back"""
@@ -689,7 +754,7 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     close(got3[:T, :, obs:obs + 8], want3[:T, :, obs:obs + 8], 2e-3, 2e-3, "action means / actions")
     close(got3[:T, :, obs + 8], want3[:T, :, obs + 8], 1e-3, 1e-3, "log-prob")
     close(got3[:T, :, obs + 9], want3[:T, :, obs + 9], 2e-3, 2e-2, "reward")
-    assert np.all(got3[..., obs + 12:] == 0)                                      # learner columns untouched
+    assert np.all(got3[..., obs + 12:] == 0)                                      # learner columns: zero-filled by collect (dead until evaluate / GAE write them)
     # the north-star's 1e-4 bound, free of closed-loop amplification (a random actor is chaotic across resets, which is what the 2e-3 above absorbs):
     # (1) before the first reset (step limit 12) the trajectories themselves agree to 1e-4 relative
     K = 8
