@@ -62,11 +62,11 @@ inline void build_mlp_tc_image_host(float* img, const float* blob, bool has_std,
     for(int n = 0; n < HD; n++){
         for(int k = 0; k < IN; k++) put(I::B1_HI, I::B1_LO, HD, n, k, W1[n * IN + k]);
         put(I::B1_HI, I::B1_LO, HD, n, IN, b1[n]);
-        for(int k = 0; k < HD; k++) put(I::B2_HI, I::B2_LO, HD, n, k, W2[n * HD + k]);
+        for(int k = 0; k < HD; k++) put(I::B2_HI, I::B2_LO, HD, n, k, 0.5f * W2[n * HD + k]);   // the hidden activations arrive doubled (packed ReLU, see relu2x): exact
         img[I::BIAS2 + n] = b2[n];
     }
     for(int n = 0; n < OUT; n++){
-        for(int k = 0; k < HD; k++) put(I::B3_HI, I::B3_LO, I::N3, n, k, W3[n * HD + k]);
+        for(int k = 0; k < HD; k++) put(I::B3_HI, I::B3_LO, I::N3, n, k, 0.5f * W3[n * HD + k]);
         img[I::BIAS3 + n] = b3[n];
     }
     for(int i = 0; i < 4; i++) img[I::LOG_STD + i] = has_log_std ? ls[i] : 0.0f;
@@ -87,9 +87,23 @@ struct TsCtx {
 __device__ __forceinline__ void ts_put8(uint32_t t_hi, uint32_t t_lo, const float* v){
     float hi[8], lo[8];
 #pragma unroll
-    for(int i = 0; i < 8; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+    for(int i = 0; i < 8; i += 2){                        // hi: one LOP3 each; lo = v - hi (exact) two at a time on the packed pipe
+        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u); hi[i + 1] = __uint_as_float(__float_as_uint(v[i + 1]) & 0xFFFFE000u);
+        const float2 l = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(-hi[i], -hi[i + 1]));
+        lo[i] = l.x; lo[i + 1] = l.y;
+    }
     tc::tmem_st8(t_hi, hi);
     tc::tmem_st8(t_lo, lo);
+}
+// 2 ReLU(v) = v + |v| on the packed pipe: one FADD2 (|.| is an operand modifier) for two activations instead of two FMNMX.  The factor 2 is exact (an exponent
+// increment, carried through the hi / lo split) and is taken back by the 0.5 folded into the next layer's weights in the image: bit-identical to max(v, 0).
+__device__ __forceinline__ void relu2x_pairs(float* __restrict__ v, int n){
+#pragma unroll
+    for(int j = 0; j < n; j += 2){
+        const float2 a = make_float2(v[j], v[j + 1]);
+        const float2 r = __fadd2_rn(a, make_float2(fabsf(a.x), fabsf(a.y)));
+        v[j] = r.x; v[j + 1] = r.y;
+    }
 }
 // ksteps instructions of K = 8: A columns [a_hi + 8 s, +8) / [a_lo + 8 s, +8) against the B chunk pair s (issued by one thread)
 __device__ __forceinline__ void ts_issue_gemm(const TsCtx& c, uint32_t dcol, uint32_t a_hi, uint32_t a_lo, int ksteps, int b_hi_off, int b_lo_off, uint32_t N, uint32_t idesc){
@@ -156,8 +170,7 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         tc::tmem_ld16(c.tmem_lane + D1 + 32 * g, v);
         tc::tmem_ld16(c.tmem_lane + D1 + 32 * g + 16, v + 16);
         tc::tmem_ld_wait();
-#pragma unroll
-        for(int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.0f);
+        relu2x_pairs(v, 32);
 #pragma unroll
         for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A2_HI + 32 * g + 8 * q, c.tmem_lane + A2_LO + 32 * g + 8 * q, v + 8 * q);
     }
@@ -171,9 +184,10 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
 #pragma unroll
         for(int j4 = 0; j4 < 8; j4++){
             const float4 b = *reinterpret_cast<const float4*>(c.sm_b + I::BIAS2 + 32 * g + 4 * j4);
-            v[4 * j4] = fmaxf(v[4 * j4] + b.x, 0.0f); v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b.y, 0.0f);
-            v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b.z, 0.0f); v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b.w, 0.0f);
+            const float2 s01 = __fadd2_rn(make_float2(v[4 * j4], v[4 * j4 + 1]), make_float2(b.x, b.y)), s23 = __fadd2_rn(make_float2(v[4 * j4 + 2], v[4 * j4 + 3]), make_float2(b.z, b.w));
+            v[4 * j4] = s01.x; v[4 * j4 + 1] = s01.y; v[4 * j4 + 2] = s23.x; v[4 * j4 + 3] = s23.y;
         }
+        relu2x_pairs(v, 32);
 #pragma unroll
         for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A3_HI + 32 * g + 8 * q, c.tmem_lane + A3_LO + 32 * g + 8 * q, v + 8 * q);
     }
