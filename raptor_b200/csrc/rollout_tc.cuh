@@ -39,6 +39,7 @@ inline void tc_split_host(float x, float& hi, float& lo){
 // their activation -- r, z rows times -log2(e), n rows times 2 log2(e) -- so the epilogue feeds the accumulators straight into ex2.
 inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates = false){
     const float s_rz = scaled_gates ? -1.4426950408889634f : 1.0f, s_n = scaled_gates ? 2.8853900817779268f : 1.0f;
+    const float s_x = scaled_gates ? 0.5f : 1.0f;   // TMEM-A kernel: dense 1's ReLU arrives doubled (x1 + |x1| on the packed pipe); the exact factor 0.5 sits in the W_ih columns
     constexpr int IN = 22, HD = 16, OUT = 4;
     const float* W1 = blob; const float* b1 = W1 + HD * IN;
     const float* Wih = b1 + HD; const float* bih = Wih + 3 * HD * HD;
@@ -56,11 +57,11 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
     }
     // G2 columns: 0..15 x1, 16..31 h, 32 -> b_hh, 33 -> b_ih (A holds 1.0 in both)
     for(int j = 0; j < 2 * HD; j++){            // r, z rows
-        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, j, k, s_rz * Wih[j * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 16 + k, s_rz * Whh[j * HD + k]); }
+        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, j, k, (s_rz * Wih[j * HD + k]) * s_x); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 16 + k, s_rz * Whh[j * HD + k]); }
         put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 32, s_rz * bhh[j]); put(TcImage::B2_HI, TcImage::B2_LO, 64, j, 33, s_rz * bih[j]);
     }
     for(int j = 0; j < HD; j++){                // n_x rows 32..47, n_h rows 48..63
-        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, k, s_n * Wih[(2 * HD + j) * HD + k]); put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 16 + k, s_n * Whh[(2 * HD + j) * HD + k]); }
+        for(int k = 0; k < HD; k++){ put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, k, (s_n * Wih[(2 * HD + j) * HD + k]) * s_x); put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 16 + k, s_n * Whh[(2 * HD + j) * HD + k]); }
         put(TcImage::B2_HI, TcImage::B2_LO, 64, 32 + j, 33, s_n * bih[2 * HD + j]);
         put(TcImage::B2_HI, TcImage::B2_LO, 64, 48 + j, 32, s_n * bhh[2 * HD + j]);
     }
@@ -1056,7 +1057,11 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
         tc::tmem_ld16(tmem_base + lane_off + C_D1, x1);
         tc::tmem_ld_wait();
 #pragma unroll
-        for(int j = 0; j < HD; j++) x1[j] = fmaxf(x1[j], 0.0f);
+        for(int j = 0; j < HD; j += 2){                       // 2 ReLU(x1) = x1 + |x1|: one FADD2 per two units (the image's W_ih columns carry the 0.5: bit-identical)
+            const float2 v = make_float2(x1[j], x1[j + 1]);
+            const float2 r = __fadd2_rn(v, make_float2(fabsf(v.x), fabsf(v.y)));
+            x1[j] = r.x; x1[j + 1] = r.y;
+        }
         if(!no_auto_reset && gs >= a.seq_len){   // reset_truncate (gru/operations_generic.h:76-86)
             put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8);
             keep_h(sm_b + TcImage::H0);

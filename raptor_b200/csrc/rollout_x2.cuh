@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_rollout_raptor_x2(const __grid_con
             tc::tmem_ld16(lane_addr + TILE + C_D1, xb);
             tc::tmem_ld_wait();
 #pragma unroll
-            for(int j = 0; j < HD; j++){ xa[j] = fmaxf(xa[j], 0.0f); xb[j] = fmaxf(xb[j], 0.0f); }
+            for(int j = 0; j < HD; j++){ xa[j] = xa[j] + fabsf(xa[j]); xb[j] = xb[j] + fabsf(xb[j]); }   // 2 ReLU: the scaled-gate image carries the 0.5 in its W_ih columns (build_tc_image_host)
             if(!no_auto_reset){   // reset_truncate (gru/operations_generic.h:76-86)
                 if(gs0 >= a.seq_len){ put8(C_H_HI, C_H_LO, sm_b + TcImage::H0); put8(C_H_HI + 8, C_H_LO + 8, sm_b + TcImage::H0 + 8); gs0 = 0; }
                 if(gs1 >= a.seq_len){ put8(TILE + C_H_HI, TILE + C_H_LO, sm_b + TcImage::H0); put8(TILE + C_H_HI + 8, TILE + C_H_LO + 8, sm_b + TcImage::H0 + 8); gs1 = 0; }
