@@ -774,6 +774,48 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     close(env.get_state(), states, 5e-3, 2e-3, "final states (incl. the action-history ring)")
 
 
+def test_ppo_collect_write_back_paths(rb, port):
+    """the two write-back paths of k_collect_ts give the same dataset as the oracle: n = 203 (n % 4 != 0: a warp's 32 rows are not 16-byte aligned, every warp takes
+    the element loop) and n = 256 into a device buffer whose base is offset by one row (unaligned base: element loop) vs the aligned bulk-copy path on the same inputs"""
+    import torch
+    spec, obs, D, T, limit = B.SPEC_RAPTOR_DR, 22, 37, 24, 9
+    rs = np.random.RandomState(15)
+    blob = random_mlp_blob(rs, obs, 4, True, True)
+    env_p = foundation_dr_env_params(port, spec)
+    pol = port.make_policy(blob, arch=B.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=B.HEAD_PPO_GAUSSIAN)
+
+    def fresh(n):
+        env = rb.VectorEnvironment(n, spec)
+        env.set_environment_parameters(env_p)
+        env.initialize_rng(41, warmup=16); env.initial_parameters(); env.initial_state()
+        env.load_policy(blob, arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1, head=rb.HEAD_PPO_GAUSSIAN, gemm=rb.GEMM_TCGEN05_3XTF32)
+        env.collect_reset()
+        return env
+    # ---- n % 4 != 0
+    n = 203
+    env = fresh(n)
+    rng, params, states = env.get_rng(), env.get_parameters(), env.get_state()
+    got3 = env.collect(T, limit).reshape(T + 1, n, D)
+    ep_step = np.zeros(n, np.int32); ep_ret = np.zeros(n, np.float32); trunc = np.ones(n, np.uint8)
+    want3 = port.collect(spec, pol, env_p, params, states, rng, ep_step, ep_ret, trunc, T, limit).reshape(T + 1, n, D)
+    assert np.array_equal(env.get_rng(), rng)
+    assert np.array_equal(got3[:T, :, obs + 10:obs + 12], want3[:T, :, obs + 10:obs + 12]) and want3[:T, :, obs + 11].sum() >= 2 * n
+    close(got3[:8, :, :obs + 8], want3[:8, :, :obs + 8], 1e-4, 3e-5, "observations / means / actions, first steps (n = 203)")
+    close(got3[..., :obs], want3[..., :obs], 2e-3, 2e-4, "observations (n = 203)")
+    assert np.all(got3[..., obs + 12:] == 0) and np.all(got3[T, :, obs:] == 0)
+    # ---- aligned (bulk copy) vs unaligned base (element loop): bit-identical datasets
+    n = 256
+    rows = (T + 1) * n
+    a = fresh(n); buf_a = torch.full((rows, D), 3.0, dtype=torch.float32, device="cuda")
+    a.collect(T, limit, buf_a); a.synchronize()
+    b = fresh(n); big = torch.full((rows + 1, D), 3.0, dtype=torch.float32, device="cuda")
+    buf_b = big[1:]                                                        # base + 148 bytes: not a multiple of 16
+    assert buf_b.data_ptr() % 16 != 0 and buf_b.is_contiguous()
+    b.collect(T, limit, buf_b); b.synchronize()
+    assert torch.equal(buf_a, buf_b) and float(big[0].min().item()) == 3.0 and int((buf_a == 3.0).sum().item()) == 0
+    assert np.array_equal(a.get_rng(), b.get_rng()) and np.array_equal(a.get_parameters(), b.get_parameters())
+
+
 @pytest.mark.parametrize("gemm", ["fp32", "tcgen05", "tcgen05-edited-parameters", "tcgen05-device-buffers"])
 @pytest.mark.parametrize("spec,sample_parameters", [(B.SPEC_TEACHER, True), (B.SPEC_TEACHER_DR, True), (B.SPEC_TEACHER_DR, False)])
 def test_off_policy_steps_vs_oracle(rb, port, spec, sample_parameters, gemm):
