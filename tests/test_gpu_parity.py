@@ -13,6 +13,7 @@ from oracle import binding as B
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -772,6 +773,44 @@ def test_ppo_collect_vs_oracle(rb, port, spec, gemm):
     close(rows[:, obs + 8], lp_want, 1e-4, 1e-4, "log-prob re-anchored on the recorded means / actions")
     close(env.get_parameters(), params, 2e-6, 0, "parameters after the in-kernel resets")
     close(env.get_state(), states, 5e-3, 2e-3, "final states (incl. the action-history ring)")
+
+
+def test_collect_reset_warp_variant_is_bit_identical(tmp_path):
+    """k_collect_lag (B200L2F_COLLECT_LAG=1: resets on a fifth warp, terminated lanes sit out, per-lane step counters; experimental, off by default) writes the same
+    dataset, parameters, states and RNG streams as k_collect_ts, bit for bit -- the kernel choice is read once per process, hence two subprocesses"""
+    import subprocess
+    import sys
+    script = tmp_path / "collect_once.py"
+    script.write_text("""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import raptor_b200 as rb
+from conftest import random_mlp_blob, FOUNDATION_DR
+n, T, limit, obs = 333, 48, 11, 22
+env = rb.VectorEnvironment(n, rb.SPEC_RAPTOR_DR)
+row = env.get_environment_parameters(); d = FOUNDATION_DR
+row[124:139] = np.array([d["t2w"][0], d["t2w"][1], d["t2i"][0], d["t2i"][1], d["mass"][0], d["mass"][1], d["size_dev"], d["tau_rise"][0], d["tau_rise"][1],
+                         d["tau_fall"][0], d["tau_fall"][1], d["kq"][0], d["kq"][1], 0.0, d["dist_force"]], np.float32)
+env.set_environment_parameters(row)
+env.initialize_rng(5, warmup=16); env.initial_parameters(); env.initial_state()
+env.load_policy(random_mlp_blob(np.random.RandomState(3), obs, 4, True, True), arch=rb.POLICY_MLP, input_dim=obs, hidden_dim=64, output_dim=4, standardize=1,
+                head=rb.HEAD_PPO_GAUSSIAN, gemm=rb.GEMM_TCGEN05_3XTF32)
+env.collect_reset()
+a = env.collect(T, limit); b = env.collect(T, limit)          # the second call starts from the carried-over runner state
+print(env.last_kernel())
+np.savez(sys.argv[1], a=a, b=b, params=env.get_parameters(), state=env.get_state(), rng=env.get_rng())
+""" % (ROOT, os.path.join(ROOT, "tests")))
+    outs = {}
+    for lag in ("0", "1"):
+        out = str(tmp_path / ("lag%s.npz" % lag))
+        r = subprocess.run([sys.executable, str(script), out], capture_output=True, text=True, timeout=300, env=dict(os.environ, B200L2F_COLLECT_LAG=lag))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.strip().splitlines()[-1] == ("k_collect_lag" if lag == "1" else "k_collect_ts")
+        outs[lag] = np.load(out)
+    for k in ("a", "b", "params", "state", "rng"):
+        assert np.array_equal(outs["0"][k].view(np.uint32) if outs["0"][k].dtype == np.float32 else outs["0"][k],
+                              outs["1"][k].view(np.uint32) if outs["1"][k].dtype == np.float32 else outs["1"][k]), k
+    assert outs["0"]["a"][:, 33].sum() > 100                                     # resets happened
 
 
 def test_ppo_collect_write_back_paths(rb, port):
