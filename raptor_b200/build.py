@@ -41,6 +41,8 @@ SOURCES = {
     "h5_io.cu": ["h5_io.h"],
 }
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+# per-unit flags.  collect_ts_default.cu: every global load through L2 (ld.cg) -- its kernel hands a tile over between SMs inside one launch (time-chunked collection)
+UNIT_FLAGS = {"collect_ts_default.cu": ["-Xptxas", "-dlcm=cg"]}
 
 
 def nvcc():
@@ -78,7 +80,7 @@ def build(force=False, verbose=False, extra_flags=(), jobs=None):
     todo = [s for s in SOURCES if force or extra_flags or _unit_stale(s)]
 
     def compile_unit(src):
-        cmd = [nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-c", "-o", _obj(src), os.path.join(CSRC, src)]
+        cmd = [nvcc()] + NVCC_FLAGS + UNIT_FLAGS.get(src, []) + list(extra_flags) + ["-c", "-o", _obj(src), os.path.join(CSRC, src)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -242,6 +242,7 @@ struct CollectArgs {
     int n, T, step_limit;
     int* error_flag;
     int bulk_rows;            // tensor-core kernel: dataset 16-byte aligned and n % 4 == 0 -> a warp's 32 rows leave as one bulk copy
+    int n_chunks, chunk_steps; // tensor-core kernel: time-chunked scheduler (0 / 1 = one item per tile); the launcher enables it only for translation units built with ld.cg global loads
 };
 template <class Spec, bool DR>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_collect(const __grid_constant__ CollectArgs a){

@@ -226,6 +226,7 @@ struct MlpTsSmem {
     static constexpr int SLAB = BAR + 32;                                 // collect only: per-warp [32][W] write-back windows
     static constexpr int TOTAL_ROLLOUT = SLAB;
     static constexpr int TOTAL_COLLECT = SLAB + 4 * 32 * (IN + 15) * 4;   // the warp's 32 dataset rows, row stride D = IN + 15 (odd for every spec: conflict-free)
+    static constexpr int HIST_RING = 64 * BLOCK * 4;                      // H = 16 specs: the CTA's action-history rings [16 x 4][128] (k_collect_ts keeps them on chip)
 };
 
 // CTA prologue shared by both kernels: barriers, TMEM allocation, weight image by TMA.  Returns the context; every thread must call it.
@@ -391,26 +392,55 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
     __shared__ int s_item;
     const int n_tiles = (a.n + BLOCK - 1) / BLOCK;
     bool store_pending = false;                            // this warp has a bulk store in flight that still reads the window
+    // Time-chunked scheduler (a.n_chunks > 1; as in k_rollout_mlp_ts): the collection of a tile is cut into chunks handed out chunk-major by one atomic counter, so
+    // a tile count that is not a multiple of the resident CTAs (DEFAULT spec: one CTA per SM, 512 tiles on 148 SMs = 4 rounds for 3.46 rounds of work) no longer
+    // quantises the launch.  A chunk hands the environment over through HBM exactly like the end of a launch does (state, RNG, runner bookkeeping, parameters); the
+    // next chunk may run on another SM, so every global load of such a build must bypass L1 (the launcher enables chunks only for units compiled with -dlcm=cg).
+    const int n_chunks = a.n_chunks > 1 ? a.n_chunks : 1;
+    const int total_items = n_tiles * n_chunks;
     for(;;){
     if(tid == 0) s_item = atomicAdd(sched, 1);
     __syncthreads();
-    const int tile = s_item;
+    const int item = s_item;
     __syncthreads();
-    if(tile >= n_tiles) break;
+    if(item >= total_items) break;
+    const int tile = item % n_tiles, chunk = item / n_tiles;
+    if(chunk > 0){
+        if(tid == 0){
+            const int* prog = sched + 1 + tile;
+            int v;
+            do{ asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prog) : "memory"); if(v < chunk) __nanosleep(64); } while(v < chunk);
+        }
+        __syncthreads();
+        __threadfence();
+    }
+    const int t_begin = n_chunks > 1 ? chunk * a.chunk_steps : 0;
+    const int t_end = (chunk == n_chunks - 1) ? a.T + 1 : min(a.T + 1, t_begin + a.chunk_steps);   // the last chunk carries the final-observation row (t == T)
     const int e = tile * BLOCK + tid;
     const bool active = e < a.n;
     const size_t env = active ? (size_t)e : 0;
     ParamsCompiledT<FOLLOW, false, FOLLOW> p = stage_dynamics_compiled<FOLLOW, false, FOLLOW>(sm_dyn, a.params, n, env, a.row);
     EnvState<Spec> st;
-    load_state(st, a.state + env, n);
+    load_state_cg(st, a.state + env, n);                  // through L2: with time chunks another SM may have written it in this launch
     DynInvariants d;
     {
         ParamsRW pg{a.params + env, n};
         dyn_invariants(d, pg, st);
     }
-    float* hist_ptr = a.state + (size_t)S_HIST * n + env;
-    uint64_t rng = a.rng[env];
-    int ep_step = a.episode_step[env]; float ep_ret = a.episode_return[env]; bool truncated = a.truncated[env] != 0;
+    // H > 1 (DEFAULT spec): the 16-deep action-history ring of every environment lives in shared memory for the tile visit (element (h, a) of thread t at
+    // ring[(4 h + a) * BLOCK + t]: the same (pointer, stride) form the environment code uses for the HBM rows, bank-conflict-free) -- the observation reads all 64 values
+    // every step, which from HBM was one L2 round trip per step with nothing to hide it at one warp per scheduler
+    float* const hist_hbm = a.state + (size_t)S_HIST * n + env;
+    float* hist_ptr = hist_hbm;
+    size_t hist_stride = n;
+    if constexpr(Spec::H > 1){
+        float* ring = reinterpret_cast<float*>(smraw + SM::TOTAL_COLLECT) + tid;
+#pragma unroll 8
+        for(int i = 0; i < 4 * Spec::H; i++) ring[i * BLOCK] = __ldcg(hist_hbm + (size_t)i * n);
+        hist_ptr = ring; hist_stride = BLOCK;
+    }
+    uint64_t rng = __ldcg(a.rng + env);
+    int ep_step = __ldcg(a.episode_step + env); float ep_ret = __ldcg(a.episode_return + env); bool truncated = __ldcg(a.truncated + env) != 0;
     uint64_t rng_at_reset = 0; bool reset_seen = false;
     const int warp_env0 = tile * BLOCK + warp * 32;
     const int rows_valid = min(32, a.n - warp_env0);
@@ -418,7 +448,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
     // warp and step instead of a store loop.  Ragged last warp / unaligned dataset: the element loop below.
     const bool bulk = a.bulk_rows != 0 && rows_valid == 32;
 
-    for(int t = 0; t <= a.T; t++){
+    for(int t = t_begin; t < t_end; t++){
         const bool last = t == a.T;                       // final observation only (operations_generic.h:122-129)
         if(!last && truncated && active){                 // prologue (operations_generic_per_env.h:17-25): re-sample parameters and state
             truncated = false; ep_step = 0; ep_ret = 0.0f;
@@ -428,7 +458,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             if(!sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, rng)) atomicExch(a.error_flag, 1);
             if constexpr(!FOLLOW) o.template flush<true>(ParamsRW{a.params + env, n});
             compile_dynamics_block<true, B200L2F_FAST_RESET != 0>(dyn_block_of_thread(sm_dyn), [&](int i){ return o[i]; });   // this thread's block only
-            sample_state<Spec, ParamsOverlay, true, B200L2F_FAST_RESET != 0>(st, o, rng, hist_ptr, n);
+            sample_state<Spec, ParamsOverlay, true, B200L2F_FAST_RESET != 0>(st, o, rng, hist_ptr, hist_stride);
             dyn_invariants<Spec, ParamsOverlay, B200L2F_FAST_RESET != 0>(d, o, st);
         }
         // the previous step's bulk store has read the window (in flight since the end of that step: the wait is free)
@@ -443,7 +473,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
 #pragma unroll
             for(int i = 0; i < IN; i++) myrow[i] = obs[i];
         }
-        else observe_to_scratch<Spec, true>(st, p, rng, hist_ptr, n, myrow, 1);
+        else observe_to_scratch<Spec, true>(st, p, rng, hist_ptr, hist_stride, myrow, 1);
         float vals[12];
 #pragma unroll
         for(int i = 0; i < 12; i++) vals[i] = 0.0f;       // the final rows carry the observation only
@@ -460,7 +490,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             }
             RewardInputs ri;
             reward_inputs(ri, st);
-            if(Spec::H == 1 || active) env_step_compiled<Spec, B200L2F_COLLECT_ROLLED_RK4 != 0, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, n);   // H > 1 writes the action ring in HBM: shadow lanes must not
+            env_step_compiled<Spec, B200L2F_COLLECT_ROLLED_RK4 != 0, true, true, AXIAL>(st, p, d, act, rng, hist_ptr, hist_stride);   // H > 1: the ring is this thread's own shared-memory column (shadow lanes too)
             const bool term = env_terminated(p, st.x);
             const float r = env_reward<true>(p, ri, act, st.x, term, d.dt);
             ep_ret += r; ep_step += 1;
@@ -494,6 +524,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         store_state(st, a.state + env, n);
         a.rng[env] = rng;
         a.episode_step[env] = ep_step; a.episode_return[env] = ep_ret; a.truncated[env] = truncated ? 1 : 0;
+        if constexpr(Spec::H > 1){                         // the action-history ring goes back to its HBM rows
+#pragma unroll 8
+            for(int i = 0; i < 4 * Spec::H; i++) hist_hbm[(size_t)i * n] = hist_ptr[i * BLOCK];
+        }
     }
     if constexpr(DR && FOLLOW){
         // Deferred parameter write-back: while the columns follow the nominal row nothing in the step loop reads the randomised entries from HBM (they live in
@@ -507,6 +541,11 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
             sample_parameters<DR, Spec::RNG_OOL, B200L2F_FAST_RESET != 0>(o, r);
             o.template flush<false>(ParamsRW{a.params + env, n});
         }
+    }
+    if(chunk < n_chunks - 1){                             // publish: the tile's next chunk may start (on any SM)
+        __threadfence();
+        __syncthreads();
+        if(tid == 0) atomicExch(sched + 1 + tile, chunk + 1);
     }
     }   // tile loop
     if(store_pending && lane == 0) tc::bulk_store_wait_all();   // the window must outlive the copy
