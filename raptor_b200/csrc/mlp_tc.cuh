@@ -18,6 +18,9 @@
 #include "mlp.cuh"
 #include "rollout_tc.cuh"
 
+#ifndef B200L2F_L3_CUDA
+#define B200L2F_L3_CUDA 1               // actors / critics with <= 4 outputs: last MLP layer on the CUDA cores (one tensor-core round trip less per step)
+#endif
 #ifndef B200L2F_FAST_RESET
 #define B200L2F_FAST_RESET 1            // in-kernel resets of the default-math collection / runner kernels on the MUFU pipe (samplers.cuh: FAST twins)
 #endif
@@ -39,7 +42,8 @@ struct MlpTcImage {
     static constexpr int B3_HI = B2_LO + HD * HD, B3_LO = B3_HI + HD * N3;
     static constexpr int MEAN = B3_LO + HD * N3, PREC = MEAN + K1;
     static constexpr int BIAS2 = PREC + K1, BIAS3 = BIAS2 + HD, LOG_STD = BIAS3 + N3;
-    static constexpr int SIZE = LOG_STD + 4;
+    static constexpr int W3T = LOG_STD + 4;           // OUT <= 4: the last layer in fp32, k-major [64][4], times 0.5 (the hidden activations arrive doubled) -- the CUDA-core
+    static constexpr int SIZE = W3T + (OUT <= 4 ? HD * 4 : 0);   // form of layer 3 (mlp_forward_ts_from<.., L3_CUDA>)
     static constexpr int BYTES = SIZE * 4;
     static_assert(BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 };
@@ -70,6 +74,9 @@ inline void build_mlp_tc_image_host(float* img, const float* blob, bool has_std,
         img[I::BIAS3 + n] = b3[n];
     }
     for(int i = 0; i < 4; i++) img[I::LOG_STD + i] = has_log_std ? ls[i] : 0.0f;
+    if constexpr(OUT <= 4){
+        for(int k = 0; k < HD; k++) for(int n = 0; n < 4; n++) img[I::W3T + 4 * k + n] = n < OUT ? 0.5f * W3[n * HD + k] : 0.0f;
+    }
 }
 
 // per-thread view of the CTA's tensor-core state
@@ -139,7 +146,9 @@ __device__ __forceinline__ void ts_run(TsCtx& c, F&& issue){
 
 // obs_at(k): RAW observation column k of this thread's environment (k is a compile-time constant after unrolling: registers or shared memory)
 // -> out[OUT] (pre-head outputs).  Called by all 128 threads (inactive lanes compute garbage rows).
-template <int IN, int OUT, bool NAMED_BAR = false, class OBS>
+// L3_CUDA (OUT <= 4): the last layer (64 -> OUT) on the CUDA cores, straight from the registers that hold the second hidden layer: 2 x 64 FFMA2 + 64 broadcast LDS.128
+// instead of splitting / storing the 64 activations to TMEM and a third barrier + MMA round trip (24 N = 16 instructions for at most 4 useful columns)
+template <int IN, int OUT, bool NAMED_BAR = false, bool L3_CUDA = false, class OBS>
 __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, float* __restrict__ out){
     using I = MlpTcImage<IN, OUT>;
     constexpr int HD = MLP_HD, K1 = I::K1;
@@ -175,6 +184,7 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A2_HI + 32 * g + 8 * q, c.tmem_lane + A2_LO + 32 * g + 8 * q, v + 8 * q);
     }
     ts_run<NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D2, A2_HI, A2_LO, HD / 8, I::B2_HI, I::B2_LO, HD, IDESC64); });
+    float2 acc01 = make_float2(0.0f, 0.0f), acc23 = make_float2(0.0f, 0.0f);   // L3_CUDA: outputs 0 | 1 and 2 | 3
 #pragma unroll
     for(int g = 0; g < HD / 32; g++){
         float v[32];
@@ -188,11 +198,29 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
             v[4 * j4] = s01.x; v[4 * j4 + 1] = s01.y; v[4 * j4 + 2] = s23.x; v[4 * j4 + 3] = s23.y;
         }
         relu2x_pairs(v, 32);
+        if constexpr(L3_CUDA){
+            static_assert(!L3_CUDA || OUT <= 4, "the CUDA-core last layer covers at most four outputs");
+            if(g == 0){ acc01 = make_float2(c.sm_b[I::BIAS3], c.sm_b[I::BIAS3 + 1]); acc23 = make_float2(c.sm_b[I::BIAS3 + 2], c.sm_b[I::BIAS3 + 3]); }
 #pragma unroll
-        for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A3_HI + 32 * g + 8 * q, c.tmem_lane + A3_LO + 32 * g + 8 * q, v + 8 * q);
+            for(int k = 0; k < 32; k++){
+                const float4 w = *reinterpret_cast<const float4*>(c.sm_b + I::W3T + 4 * (32 * g + k));   // same address in every lane: broadcast
+                const float2 x = make_float2(v[k], v[k]);
+                acc01 = __ffma2_rn(x, make_float2(w.x, w.y), acc01);
+                if constexpr(OUT > 2) acc23 = __ffma2_rn(x, make_float2(w.z, w.w), acc23);
+            }
+        }
+        else{
+#pragma unroll
+            for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A3_HI + 32 * g + 8 * q, c.tmem_lane + A3_LO + 32 * g + 8 * q, v + 8 * q);
+        }
     }
-    ts_run<NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D3, A3_HI, A3_LO, HD / 8, I::B3_HI, I::B3_LO, I::N3, IDESC16); });
-    {
+    if constexpr(L3_CUDA){
+        const float o4[4] = {acc01.x, acc01.y, acc23.x, acc23.y};
+#pragma unroll
+        for(int j = 0; j < OUT; j++) out[j] = o4[j];
+    }
+    else{
+        ts_run<NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D3, A3_HI, A3_LO, HD / 8, I::B3_HI, I::B3_LO, I::N3, IDESC16); });
         float v[16];
         tc::tmem_ld16(c.tmem_lane + D3, v);
         tc::tmem_ld_wait();
@@ -200,9 +228,9 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         for(int j = 0; j < OUT; j++) out[j] = v[j] + c.sm_b[I::BIAS3 + j];
     }
 }
-template <int IN, int OUT, bool NAMED_BAR = false>
+template <int IN, int OUT, bool NAMED_BAR = false, bool L3_CUDA = false>
 __device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict__ obs, float* __restrict__ out){   // observation in registers
-    mlp_forward_ts_from<IN, OUT, NAMED_BAR>(c, [&](int k){ return obs[k]; }, out);
+    mlp_forward_ts_from<IN, OUT, NAMED_BAR, L3_CUDA>(c, [&](int k){ return obs[k]; }, out);
 }
 
 // full observation of an H = 1 spec in registers (same values and RNG order as observe_to_scratch)
@@ -479,8 +507,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         for(int i = 0; i < 12; i++) vals[i] = 0.0f;       // the final rows carry the observation only
         if(!last){                                        // uniform across the CTA
             float mean[OUT], act[4];
-            if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT>(c, obs, mean);
-            else mlp_forward_ts_from<IN, OUT>(c, [&](int k){ return myrow[k]; }, mean);
+            if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT, false, B200L2F_L3_CUDA != 0>(c, obs, mean);
+            else mlp_forward_ts_from<IN, OUT, false, B200L2F_L3_CUDA != 0>(c, [&](int k){ return myrow[k]; }, mean);
             float lp = 0.0f;
 #pragma unroll
             for(int i = 0; i < 4; i++){                   // epilogue (operations_generic_per_env.h:43-58)
