@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
                 running = false; finished = true;
             }
             float mean[OUT], act[4];
-            if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT, true, B200L2F_L3_CUDA != 0>(c, obs, mean);
-            else mlp_forward_ts_from<IN, OUT, true, B200L2F_L3_CUDA != 0>(c, [&](int k){ return myrow[k]; }, mean);
+            if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT, true>(c, obs, mean);
+            else mlp_forward_ts_from<IN, OUT, true>(c, [&](int k){ return myrow[k]; }, mean);
             // uniform exit: `done` (read behind the MLP's first barrier, incremented at the end of an iteration, i.e. never between that barrier and
             // the next one) counts the lanes whose rows were all written in EARLIER iterations
             if(c.probe_value == n_active){

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_values_ts(const __grid_constant__ 
             float reward = 0.0f; bool terminated = false, truncated = false;
             if(GAE && active && t < a.T){ reward = row[IN + 9]; terminated = row[IN + 10] != 0.0f; truncated = row[IN + 11] != 0.0f; }
             float v[4];
-            mlp_forward_ts<IN, 4, false, B200L2F_L3_CUDA != 0>(c, obs, v);
+            mlp_forward_ts<IN, 4>(c, obs, v);
             if(active){
                 float* out = a.dataset + ((size_t)t * n + env) * D + IN + 12;
                 out[0] = v[0];

@@ -21,6 +21,9 @@
 #ifndef B200L2F_L3_CUDA
 #define B200L2F_L3_CUDA 1               // actors / critics with <= 4 outputs: last MLP layer on the CUDA cores (one tensor-core round trip less per step)
 #endif
+#ifndef B200L2F_L3_CUDA8
+#define B200L2F_L3_CUDA8 1              // the same for eight outputs (SAC actors): +2.5 % on config 3, profiles/r02_exp10_last_layer_cuda_cores.log
+#endif
 #ifndef B200L2F_FAST_RESET
 #define B200L2F_FAST_RESET 1            // in-kernel resets of the default-math collection / runner kernels on the MUFU pipe (samplers.cuh: FAST twins)
 #endif
@@ -30,6 +33,8 @@
 
 namespace b200l2f {
 
+template <int OUT> constexpr bool mlp_l3_cuda_default(){ return OUT <= 4 ? B200L2F_L3_CUDA != 0 : B200L2F_L3_CUDA8 != 0; }
+
 template <int IN, int OUT>
 struct MlpTcImage {
     static constexpr int HD = MLP_HD;
@@ -37,13 +42,17 @@ struct MlpTcImage {
     static constexpr int N3 = 16;                     // smallest N of an M = 128 instruction
     static_assert(K1 <= 88 && OUT <= N3, "TMEM plan");
     static constexpr bool WIDE = K1 > 32;             // which TMEM column plan mlp_forward_ts uses (see the file header)
+    // L3_CUDA: the last layer runs on the CUDA cores (mlp_forward_ts_from) from an fp32 k-major copy of W3 -- the image then carries that copy INSTEAD of the hi / lo
+    // operand planes of layer 3 (7 / 6 KB less shared memory per CTA, which is what keeps the runner kernels at two CTAs per SM)
+    static constexpr bool L3_CUDA = mlp_l3_cuda_default<OUT>();
     static constexpr int B1_HI = 0, B1_LO = B1_HI + K1 * HD;
     static constexpr int B2_HI = B1_LO + K1 * HD, B2_LO = B2_HI + HD * HD;
-    static constexpr int B3_HI = B2_LO + HD * HD, B3_LO = B3_HI + HD * N3;
-    static constexpr int MEAN = B3_LO + HD * N3, PREC = MEAN + K1;
+    static constexpr int B3_HI = B2_LO + HD * HD, B3_LO = B3_HI + (L3_CUDA ? 0 : HD * N3);
+    static constexpr int MEAN = B3_LO + (L3_CUDA ? 0 : HD * N3), PREC = MEAN + K1;
     static constexpr int BIAS2 = PREC + K1, BIAS3 = BIAS2 + HD, LOG_STD = BIAS3 + N3;
-    static constexpr int W3T = LOG_STD + 4;           // OUT <= 4: the last layer in fp32, k-major [64][4], times 0.5 (the hidden activations arrive doubled) -- the CUDA-core
-    static constexpr int SIZE = W3T + (OUT <= 4 ? HD * 4 : 0);   // form of layer 3 (mlp_forward_ts_from<.., L3_CUDA>)
+    static constexpr int W3T = LOG_STD + 4;           // L3_CUDA: the last layer in fp32, k-major [64][W3N], times 0.5 (the hidden activations arrive doubled)
+    static constexpr int W3N = L3_CUDA ? (OUT <= 4 ? 4 : 8) : 0;
+    static constexpr int SIZE = W3T + HD * W3N;
     static constexpr int BYTES = SIZE * 4;
     static_assert(BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 };
@@ -70,13 +79,11 @@ inline void build_mlp_tc_image_host(float* img, const float* blob, bool has_std,
         img[I::BIAS2 + n] = b2[n];
     }
     for(int n = 0; n < OUT; n++){
-        for(int k = 0; k < HD; k++) put(I::B3_HI, I::B3_LO, I::N3, n, k, 0.5f * W3[n * HD + k]);
+        if constexpr(!I::L3_CUDA){ for(int k = 0; k < HD; k++) put(I::B3_HI, I::B3_LO, I::N3, n, k, 0.5f * W3[n * HD + k]); }
         img[I::BIAS3 + n] = b3[n];
     }
     for(int i = 0; i < 4; i++) img[I::LOG_STD + i] = has_log_std ? ls[i] : 0.0f;
-    if constexpr(OUT <= 4){
-        for(int k = 0; k < HD; k++) for(int n = 0; n < 4; n++) img[I::W3T + 4 * k + n] = n < OUT ? 0.5f * W3[n * HD + k] : 0.0f;
-    }
+    for(int k = 0; k < HD; k++) for(int n = 0; n < I::W3N; n++) img[I::W3T + I::W3N * k + n] = n < OUT ? 0.5f * W3[n * HD + k] : 0.0f;
 }
 
 // per-thread view of the CTA's tensor-core state
@@ -148,9 +155,10 @@ __device__ __forceinline__ void ts_run(TsCtx& c, F&& issue){
 // -> out[OUT] (pre-head outputs).  Called by all 128 threads (inactive lanes compute garbage rows).
 // L3_CUDA (OUT <= 4): the last layer (64 -> OUT) on the CUDA cores, straight from the registers that hold the second hidden layer: 2 x 64 FFMA2 + 64 broadcast LDS.128
 // instead of splitting / storing the 64 activations to TMEM and a third barrier + MMA round trip (24 N = 16 instructions for at most 4 useful columns)
-template <int IN, int OUT, bool NAMED_BAR = false, bool L3_CUDA = false, class OBS>
+template <int IN, int OUT, bool NAMED_BAR = false, class OBS>
 __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, float* __restrict__ out){
     using I = MlpTcImage<IN, OUT>;
+    constexpr bool L3_CUDA = I::L3_CUDA;
     constexpr int HD = MLP_HD, K1 = I::K1;
     constexpr bool WIDE = I::WIDE;
     constexpr uint32_t A1_HI = 0, A1_LO = WIDE ? 88 : 32, D1 = WIDE ? 176 : 64, A2_HI = WIDE ? 0 : 128, A2_LO = WIDE ? 64 : 192, D2 = WIDE ? 128 : 0,
@@ -184,7 +192,7 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         for(int q = 0; q < 4; q++) ts_put8(c.tmem_lane + A2_HI + 32 * g + 8 * q, c.tmem_lane + A2_LO + 32 * g + 8 * q, v + 8 * q);
     }
     ts_run<NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D2, A2_HI, A2_LO, HD / 8, I::B2_HI, I::B2_LO, HD, IDESC64); });
-    float2 acc01 = make_float2(0.0f, 0.0f), acc23 = make_float2(0.0f, 0.0f);   // L3_CUDA: outputs 0 | 1 and 2 | 3
+    float2 acc01 = make_float2(0.0f, 0.0f), acc23 = acc01, acc45 = acc01, acc67 = acc01;   // L3_CUDA: outputs 0 | 1, 2 | 3, 4 | 5, 6 | 7
 #pragma unroll
     for(int g = 0; g < HD / 32; g++){
         float v[32];
@@ -199,14 +207,22 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         }
         relu2x_pairs(v, 32);
         if constexpr(L3_CUDA){
-            static_assert(!L3_CUDA || OUT <= 4, "the CUDA-core last layer covers at most four outputs");
-            if(g == 0){ acc01 = make_float2(c.sm_b[I::BIAS3], c.sm_b[I::BIAS3 + 1]); acc23 = make_float2(c.sm_b[I::BIAS3 + 2], c.sm_b[I::BIAS3 + 3]); }
+            if(g == 0){
+                acc01 = make_float2(c.sm_b[I::BIAS3], c.sm_b[I::BIAS3 + 1]); acc23 = make_float2(c.sm_b[I::BIAS3 + 2], c.sm_b[I::BIAS3 + 3]);
+                if constexpr(OUT > 4){ acc45 = make_float2(c.sm_b[I::BIAS3 + 4], c.sm_b[I::BIAS3 + 5]); acc67 = make_float2(c.sm_b[I::BIAS3 + 6], c.sm_b[I::BIAS3 + 7]); }
+            }
 #pragma unroll
             for(int k = 0; k < 32; k++){
-                const float4 w = *reinterpret_cast<const float4*>(c.sm_b + I::W3T + 4 * (32 * g + k));   // same address in every lane: broadcast
+                const float* wr = c.sm_b + I::W3T + I::W3N * (32 * g + k);                                // same address in every lane: broadcast
+                const float4 w = *reinterpret_cast<const float4*>(wr);
                 const float2 x = make_float2(v[k], v[k]);
                 acc01 = __ffma2_rn(x, make_float2(w.x, w.y), acc01);
                 if constexpr(OUT > 2) acc23 = __ffma2_rn(x, make_float2(w.z, w.w), acc23);
+                if constexpr(OUT > 4){
+                    const float4 u = *reinterpret_cast<const float4*>(wr + 4);
+                    acc45 = __ffma2_rn(x, make_float2(u.x, u.y), acc45);
+                    acc67 = __ffma2_rn(x, make_float2(u.z, u.w), acc67);
+                }
             }
         }
         else{
@@ -215,9 +231,9 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         }
     }
     if constexpr(L3_CUDA){
-        const float o4[4] = {acc01.x, acc01.y, acc23.x, acc23.y};
+        const float o8[8] = {acc01.x, acc01.y, acc23.x, acc23.y, acc45.x, acc45.y, acc67.x, acc67.y};
 #pragma unroll
-        for(int j = 0; j < OUT; j++) out[j] = o4[j];
+        for(int j = 0; j < OUT; j++) out[j] = o8[j];
     }
     else{
         ts_run<NAMED_BAR>(c, [&](){ ts_issue_gemm(c, D3, A3_HI, A3_LO, HD / 8, I::B3_HI, I::B3_LO, I::N3, IDESC16); });
@@ -228,9 +244,9 @@ __device__ __forceinline__ void mlp_forward_ts_from(TsCtx& c, OBS&& obs_at, floa
         for(int j = 0; j < OUT; j++) out[j] = v[j] + c.sm_b[I::BIAS3 + j];
     }
 }
-template <int IN, int OUT, bool NAMED_BAR = false, bool L3_CUDA = false>
+template <int IN, int OUT, bool NAMED_BAR = false>
 __device__ __forceinline__ void mlp_forward_ts(TsCtx& c, const float* __restrict__ obs, float* __restrict__ out){   // observation in registers
-    mlp_forward_ts_from<IN, OUT, NAMED_BAR, L3_CUDA>(c, [&](int k){ return obs[k]; }, out);
+    mlp_forward_ts_from<IN, OUT, NAMED_BAR>(c, [&](int k){ return obs[k]; }, out);
 }
 
 // full observation of an H = 1 spec in registers (same values and RNG order as observe_to_scratch)
@@ -507,8 +523,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_collect_ts(const __grid_constant__
         for(int i = 0; i < 12; i++) vals[i] = 0.0f;       // the final rows carry the observation only
         if(!last){                                        // uniform across the CTA
             float mean[OUT], act[4];
-            if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT, false, B200L2F_L3_CUDA != 0>(c, obs, mean);
-            else mlp_forward_ts_from<IN, OUT, false, B200L2F_L3_CUDA != 0>(c, [&](int k){ return myrow[k]; }, mean);
+            if constexpr(Spec::H == 1) mlp_forward_ts<IN, OUT>(c, obs, mean);
+            else mlp_forward_ts_from<IN, OUT>(c, [&](int k){ return myrow[k]; }, mean);
             float lp = 0.0f;
 #pragma unroll
             for(int i = 0; i < 4; i++){                   // epilogue (operations_generic_per_env.h:43-58)
