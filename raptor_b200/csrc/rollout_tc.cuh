@@ -78,6 +78,9 @@ inline void build_tc_image_host(float* img, const float* blob, bool scaled_gates
     for(int j = 0; j < HD; j++){ img[TcImage::BIAS2 + 32 + j] = s_n * bih[2 * HD + j]; img[TcImage::BIAS2 + 48 + j] = s_n * bhh[2 * HD + j]; }
 }
 
+#ifndef B200L2F_G1_CUDA
+#define B200L2F_G1_CUDA 0          // dense 1 of k_rollout_raptor_ts on the packed CUDA-core pipe instead of a tensor-core round trip: experiment, see start_g1
+#endif
 #ifndef B200L2F_GATES_PACKED
 #define B200L2F_GATES_PACKED 1     // GRU gate epilogue of k_rollout_raptor_ts on the packed fp32 pipe (two hidden units per FADD2 / FFMA2)
 #endif
@@ -1008,6 +1011,7 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
     // observation or the RNG order: no observation noise (its draws would have to follow the Langevin draws) and an observation that does not read the
     // trajectory target (RAPTOR layout; DEFAULT has no Langevin target).
     constexpr bool PIPELINE_G1 = B200L2F_PIPELINE_G1 && !NOISE && (Spec::OBS_LAYOUT == OBS_RAPTOR || !Spec::LANGEVIN);
+    float x1_cuda[B200L2F_G1_CUDA != 0 ? HD : 1];
     auto start_g1 = [&](int t){      // observation of step t (state row / observation row recorded as of step t) -> TMEM -> dense 1 issued
         if(RECORD && a.out_states && active && (t % a.state_stride) == 0)
             write_state_row(st, hist_ptr, n, a.out_states + ((size_t)(t / a.state_stride) * n + env) * Spec::STATE_DIM);
@@ -1026,6 +1030,27 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
             float* row = a.out_obs + ((size_t)t * n + env) * 22;
 #pragma unroll
             for(int i = 0; i < 22; i++) row[i] = obs[i];
+        }
+        if constexpr(B200L2F_G1_CUDA != 0){
+            // experiment (profiles/r02_exp11_dense1_cuda_cores.log): dense 1 (22 -> 16) on the packed fp32 pipe from the image's fp32 k-major copy of W1 -- 176 FFMA2 +
+            // 88 broadcast LDS.128 instead of the operand split, a CTA barrier and a tensor-core round trip
+            const float* w1 = sm_b + TcImage::W1T;
+            float2 acc[8];
+#pragma unroll
+            for(int j = 0; j < 8; j++) acc[j] = make_float2(w1[22 * 16 + 2 * j], w1[22 * 16 + 2 * j + 1]);
+#pragma unroll
+            for(int k = 0; k < 22; k++){
+                const float2 x = make_float2(obs[k], obs[k]);
+#pragma unroll
+                for(int q = 0; q < 4; q++){
+                    const float4 w = *reinterpret_cast<const float4*>(w1 + 16 * k + 4 * q);
+                    acc[2 * q] = __ffma2_rn(x, make_float2(w.x, w.y), acc[2 * q]);
+                    acc[2 * q + 1] = __ffma2_rn(x, make_float2(w.z, w.w), acc[2 * q + 1]);
+                }
+            }
+#pragma unroll
+            for(int j = 0; j < 8; j++){ x1_cuda[2 * j] = acc[j].x; x1_cuda[2 * j + 1] = acc[j].y; }
+            return;
         }
         obs[22] = 1.0f; obs[23] = 0.0f;   // bias column, pad
         // ---- G1: dense 1 (A = obs in TMEM)
@@ -1051,11 +1076,17 @@ __global__ void __launch_bounds__(BLOCK, CTAS) k_rollout_raptor_ts(const __grid_
                 for(int dim = 0; dim < 3; dim++) lang_normals[dim] = rng_normal_t<Spec::RNG_OOL, true>(rng, 0.0f, 1.0f);
             }
         }
-        tc::mbar_wait(bar_mma, phase); phase ^= 1;
-        tc::tc_fence_after();
         float x1[HD];
-        tc::tmem_ld16(tmem_base + lane_off + C_D1, x1);
-        tc::tmem_ld_wait();
+        if constexpr(B200L2F_G1_CUDA != 0){
+#pragma unroll
+            for(int j = 0; j < HD; j++) x1[j] = x1_cuda[j];
+        }
+        else{
+            tc::mbar_wait(bar_mma, phase); phase ^= 1;
+            tc::tc_fence_after();
+            tc::tmem_ld16(tmem_base + lane_off + C_D1, x1);
+            tc::tmem_ld_wait();
+        }
 #pragma unroll
         for(int j = 0; j < HD; j += 2){                       // 2 ReLU(x1) = x1 + |x1|: one FADD2 per two units (the image's W_ih columns carry the 0.5: bit-identical)
             const float2 v = make_float2(x1[j], x1[j + 1]);
