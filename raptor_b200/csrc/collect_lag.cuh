@@ -72,17 +72,7 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
     if(reset_warp){
         // ---------------------------------------------------------------- the reset warp: serve requests until the tile is over
         uint32_t idle_spins = 0;
-#ifdef B200L2F_LAG_DEBUG
-        int dbg_passes = 0, dbg_served = 0, dbg_pending = 0; long long dbg_t0 = clock64(), dbg_busy = 0, dbg_t1 = 0;
-#endif
         for(;;){
-#ifdef B200L2F_LAG_DEBUG
-            if(dbg_t1) dbg_busy += clock64() - dbg_t1;
-            dbg_t1 = 0;
-            if(*(volatile int*)&sh.tile_over == tile + 1){
-                if(lane == 0 && tile < 3) printf("tile %d reset warp: %d passes, %d served, mean pending %.1f, busy %lld of %lld cycles (%.0f per pass)\n", tile, dbg_passes, dbg_served, (double)dbg_pending / max(dbg_passes, 1), dbg_busy, clock64() - dbg_t0, (double)dbg_busy / max(dbg_passes, 1));
-            }
-#endif
             if(*(volatile int*)&sh.tile_over == tile + 1) break;
             uint32_t m[4]; int total = 0;
 #pragma unroll
@@ -93,9 +83,6 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
                 continue;
             }
             idle_spins = 0;
-#ifdef B200L2F_LAG_DEBUG
-            dbg_t1 = clock64();
-#endif
             int slot = -1, k = lane;                         // lane j takes the j-th pending request of the CTA
 #pragma unroll
             for(int g = 0; g < 4; g++){
@@ -133,9 +120,6 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
                 else __threadfence_block();
                 *(volatile int*)&sh.flag[slot] = LAG_DONE;
             }
-#ifdef B200L2F_LAG_DEBUG
-            dbg_passes++; dbg_served += min(total, 32); dbg_pending += total;
-#endif
             __syncwarp();
         }
     }
@@ -240,9 +224,6 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
             // uniform exit: `done` (read behind the MLP's first barrier, incremented at the end of an iteration, i.e. never between that barrier and
             // the next one) counts the lanes whose rows were all written in EARLIER iterations
             if(c.probe_value == n_active){
-#ifdef B200L2F_LAG_DEBUG
-                if(tid == 0 && tile < 3) printf("tile %d: %u iterations\n", tile, iteration);
-#endif
                 break;
             }
             float vals[12];
@@ -301,9 +282,6 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_collect_lag(const __grid_con
             request_if(running && truncated && t < a.T);
             if(finishing) atomicAdd(&sh.done, 1);
         }
-#ifdef B200L2F_LAG_DEBUG
-        if(tid == 0 && tile < 3) printf("tile %d: T %d\n", tile, a.T);
-#endif
         asm volatile("bar.sync 1, 128;" ::: "memory");        // every tile warp has left the loop
         if(tid == 0) *(volatile int*)&sh.tile_over = tile + 1;
     }
