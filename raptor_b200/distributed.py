@@ -64,6 +64,12 @@ def allgather_trajectories(slab, world=None, n_global=None):
     return torch.cat([out[r, :, :counts[r]] for r in range(world)], dim=1)
 
 
+def unique_id_bytes(uid):
+    """all 128 bytes of an ncclUniqueId structure (reading its c_char array as a VALUE stops at the first NUL byte and the other ranks would join a different id)"""
+    import ctypes
+    return ctypes.string_at(ctypes.byref(uid), ctypes.sizeof(uid))
+
+
 # ---- the same gather through the engine's C ABI (b200l2f_allgather_trajectories): NCCL bound by the engine at run time, communicator owned by the caller ----------
 class NcclCommunicator:
     """an ncclComm_t for this process (one rank per GPU), created with the libnccl the process already carries (torch's): rank 0 draws the unique id, the
@@ -82,7 +88,7 @@ class NcclCommunicator:
         uid = UniqueId()
         if rank == 0:
             self._check(self.lib.ncclGetUniqueId(ctypes.byref(uid)), "ncclGetUniqueId")
-        box = [ctypes.string_at(ctypes.byref(uid), 128) if rank == 0 else None]   # all 128 bytes (a c_char array read as a value stops at the first NUL)
+        box = [unique_id_bytes(uid) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         ctypes.memmove(ctypes.byref(uid), box[0].ljust(128, b"\0"), 128)
         self.handle = ctypes.c_void_p()

@@ -58,3 +58,18 @@ def test_reference_arm_under_torchrun_only_rank0_works(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and '"impl": "reference"' in lines[0] and '"n_gpus": 2' in lines[0]
+
+
+def test_nccl_unique_id_marshalling_keeps_embedded_nul_bytes():
+    """regression: the 128-byte ncclUniqueId travels between ranks as bytes; a c_char array read as a value is cut at its first NUL (found on the first 2-GPU run
+    of b200l2f_allgather_trajectories: ncclCommInitRank failed with a remote error on every rank but 0)"""
+    import ctypes
+    from raptor_b200.distributed import unique_id_bytes
+
+    class UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_char * 128)]
+    uid = UniqueId()
+    raw = bytes([7, 0, 9, 0, 0, 200] + list(range(122)))
+    ctypes.memmove(ctypes.byref(uid), raw, 128)
+    assert bytes(uid.internal) != raw              # the trap
+    assert unique_id_bytes(uid) == raw
